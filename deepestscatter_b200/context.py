@@ -1,0 +1,336 @@
+"""Thin numpy-facing wrapper over the C ABI (one `Context` per GPU).
+
+Only plumbing lives here: argument marshalling and error translation.  All arithmetic runs in the
+sm_100a kernels behind include/ds_abi.h.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import json
+
+import numpy as np
+
+from . import _lib
+from ._lib import DsCamera, DsCounters, DsPointRadianceTask, DsRadianceSettings, DsSceneParams
+
+MODE_ALL_SCATTER = 0       # Cloud::Rendering::Mode::SunAndSkyAllScatter -> totalRadiance
+MODE_MULTIPLE_SCATTER = 1  # SunMultipleScatter -> multipleScatterSunRadiance
+MODE_SINGLE_SCATTER = 2    # SunSingleScatter -> singleScatterSunRadiance
+PRECISION_EXACT = 0
+PRECISION_FAST = 1
+
+TASK_DTYPE = np.dtype(
+    [
+        ("id", "<i4"),
+        ("experimentCount", "<u4"),
+        ("radiance", "<f4"),
+        ("runningVariance", "<f4"),
+        ("position", "<f4", 3),
+        ("direction", "<f4", 3),
+    ]
+)
+
+
+class DsError(RuntimeError):
+    def __init__(self, code: int, message: str):
+        super().__init__(f"[{code}] {message}")
+        self.code = code
+
+
+def _f32(a) -> np.ndarray:
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def _ptr(a: np.ndarray):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def camera_look_at(eye=(2.5, -0.4, 0.0), lookat=(0.0, 0.0, 0.0), up=(0.0, 1.0, 0.0), hfov=30.0, aspect=2.0) -> DsCamera:
+    """sutil::calculateCameraVariables with the defaults of Camera::init (Camera.cpp:37-39,102)."""
+    lib = _lib.load()
+    cam = DsCamera()
+    f3 = C.c_float * 3
+    lib.ds_camera_look_at(f3(*eye), f3(*lookat), f3(*up), hfov, aspect, C.byref(cam))
+    return cam
+
+
+def camera_array(cam: DsCamera) -> np.ndarray:
+    return np.array(list(cam.eye) + list(cam.U) + list(cam.V) + list(cam.W), dtype=np.float32)
+
+
+class _DevArray:
+    """Minimal __cuda_array_interface__ carrier so torch.as_tensor can alias library-owned memory."""
+
+    def __init__(self, ptr: int, shape, typestr: str):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (ptr, False), "version": 2}
+
+
+class Context:
+    def __init__(self, device: int = 0):
+        self.lib = _lib.load()
+        h = C.c_void_p()
+        rc = self.lib.ds_context_create(device, C.byref(h))
+        if rc != 0:
+            raise DsError(rc, (self.lib.ds_last_error(None) or b"").decode())
+        self.h = h
+        self.device = device
+        self.width = self.height = 0
+
+    # ---- plumbing ----
+    def _ck(self, rc: int):
+        if rc != 0:
+            raise DsError(rc, (self.lib.ds_last_error(self.h) or b"").decode())
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.ds_context_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def set_stream(self, cuda_stream_ptr: int):
+        self._ck(self.lib.ds_context_set_stream(self.h, C.c_void_p(cuda_stream_ptr)))
+
+    def sync(self):
+        self._ck(self.lib.ds_sync(self.h))
+
+    def set_option(self, name: str, value: int):
+        self._ck(self.lib.ds_set_option(self.h, name.encode(), int(value)))
+
+    def get_option(self, name: str) -> int:
+        v = C.c_int()
+        self._ck(self.lib.ds_get_option(self.h, name.encode(), C.byref(v)))
+        return v.value
+
+    def describe(self) -> dict:
+        return json.loads(self.lib.ds_describe(self.h).decode())
+
+    def counters(self) -> dict:
+        c = DsCounters()
+        self._ck(self.lib.ds_get_counters(self.h, C.byref(c)))
+        return dict(paths=c.paths, events=c.events, steps=c.steps, density_taps=c.density_taps, nonfinite=c.nonfinite)
+
+    def counters_reset(self):
+        self._ck(self.lib.ds_reset_counters(self.h))
+
+    def launch_stats(self) -> dict:
+        a, b, ms = C.c_uint64(), C.c_uint64(), C.c_double()
+        self._ck(self.lib.ds_get_launch_stats(self.h, C.byref(a), C.byref(b), C.byref(ms)))
+        return dict(kernel_launches=a.value, trace_launches_timed=b.value, trace_ms_total=ms.value)
+
+    # ---- volume ----
+    def volume_upload(self, grid_u8: np.ndarray, build_mips: bool = True):
+        g = np.ascontiguousarray(grid_u8, dtype=np.uint8)
+        nz, ny, nx = g.shape
+        self._ck(self.lib.ds_volume_upload(self.h, _ptr(g), nx, ny, nz, int(build_mips)))
+
+    def volume_upload_float(self, grid_f32: np.ndarray, max_density: float, build_mips: bool = True):
+        g = _f32(grid_f32)
+        nz, ny, nx = g.shape
+        self._ck(self.lib.ds_volume_upload_float(self.h, _ptr(g), nx, ny, nz, float(max_density), int(build_mips)))
+
+    def volume_synth(self, n: int, kind: int = 0, seed: int = 1234, build_mips: bool = True):
+        self._ck(self.lib.ds_volume_synth(self.h, n, kind, seed, int(build_mips)))
+
+    def level_count(self) -> int:
+        v = C.c_int()
+        self._ck(self.lib.ds_volume_level_count(self.h, C.byref(v)))
+        return v.value
+
+    def level_dims(self, level: int):
+        d = (C.c_int * 3)()
+        self._ck(self.lib.ds_volume_level_dims(self.h, level, d))
+        return d[0], d[1], d[2]
+
+    def level(self, level: int) -> np.ndarray:
+        nx, ny, nz = self.level_dims(level)
+        out = np.empty((nz, ny, nx), dtype=np.uint8)
+        self._ck(self.lib.ds_volume_download_level(self.h, level, _ptr(out)))
+        return out
+
+    # ---- scene ----
+    def scene_set(self, cloud_size_m=7000.0, light_dir=(-0.03, -0.25, 0.8), mean_free_path_m=10.0, sample_step=1.0 / 512.0,
+                  light_color=(1.0, 1.0, 1.0), light_intensity=1e6):
+        p = DsSceneParams()
+        self.lib.ds_scene_params_default(C.byref(p))
+        p.cloud_size_m = cloud_size_m
+        p.mean_free_path_m = mean_free_path_m
+        p.sample_step = sample_step
+        p.light_direction[:] = list(map(float, light_dir))
+        p.light_color[:] = list(map(float, light_color))
+        p.light_intensity = light_intensity
+        self._ck(self.lib.ds_scene_set(self.h, C.byref(p)))
+
+    def derived(self) -> dict:
+        o = np.empty(12, dtype=np.float32)
+        self._ck(self.lib.ds_scene_get_derived(self.h, o.ctypes.data_as(C.POINTER(C.c_float))))
+        return dict(bbox=o[0:3].copy(), texture_scale=o[3:6].copy(), density_multiplier=float(o[6]), voxel_m=float(o[7]),
+                    voxel_free_path=float(o[8]), light=o[9:12].copy())
+
+    def bake(self):
+        self._ck(self.lib.ds_bake_sun_transmittance(self.h))
+
+    def inscatter(self) -> np.ndarray:
+        nx, ny, nz = self.level_dims(0)
+        out = np.empty((nz, ny, nx), dtype=np.uint8)
+        self._ck(self.lib.ds_inscatter_download(self.h, _ptr(out)))
+        return out
+
+    def inscatter_set(self, vol: np.ndarray):
+        v = np.ascontiguousarray(vol, dtype=np.uint8)
+        self._ck(self.lib.ds_inscatter_upload(self.h, _ptr(v)))
+
+    # ---- progressive renderer ----
+    def frame_create(self, width: int, height: int):
+        self._ck(self.lib.ds_frame_create(self.h, width, height))
+        self.width, self.height = width, height
+
+    def frame_clear(self):
+        self._ck(self.lib.ds_frame_clear(self.h))
+
+    def render_frame(self, cam: DsCamera, mode: int, subframe: int) -> np.ndarray:
+        out = np.empty((self.height, self.width, 4), dtype=np.float32)
+        self._ck(self.lib.ds_render_frame_result(self.h, C.byref(cam), mode, subframe, _ptr(out)))
+        return out
+
+    def render_subframes(self, cam: DsCamera, mode: int, first: int, n: int):
+        self._ck(self.lib.ds_render_subframes(self.h, C.byref(cam), mode, first, n))
+
+    def render_subframes_host(self, cam: DsCamera, mode: int, first: int, n: int, progressive: np.ndarray, variance: np.ndarray):
+        assert progressive.dtype == np.float32 and variance.dtype == np.float32
+        self._ck(self.lib.ds_render_subframes_host(self.h, C.byref(cam), mode, first, n, _ptr(progressive), _ptr(variance)))
+
+    def render_subframes_host_ptr(self, cam: DsCamera, mode: int, first: int, n: int, progressive_ptr: int, variance_ptr: int):
+        """Same call with raw host addresses (e.g. pinned torch tensors' data_ptr())."""
+        self._ck(self.lib.ds_render_subframes_host(self.h, C.byref(cam), mode, first, n, C.c_void_p(progressive_ptr), C.c_void_p(variance_ptr)))
+
+    def frame_download(self):
+        p = np.empty((self.height, self.width, 4), dtype=np.float32)
+        v = np.empty((self.height, self.width, 4), dtype=np.float32)
+        self._ck(self.lib.ds_frame_download(self.h, _ptr(p), _ptr(v)))
+        return p, v
+
+    def frame_upload(self, progressive: np.ndarray, variance: np.ndarray):
+        p, v = _f32(progressive), _f32(variance)
+        self._ck(self.lib.ds_frame_upload(self.h, _ptr(p), _ptr(v)))
+        self.sync()
+
+    def frame_device_arrays(self):
+        """(progressive, variance) as __cuda_array_interface__ objects aliasing the device buffers."""
+        a, b = C.c_void_p(), C.c_void_p()
+        self._ck(self.lib.ds_frame_device_ptrs(self.h, C.byref(a), C.byref(b)))
+        shape = (self.height, self.width, 4)
+        return _DevArray(a.value, shape, "<f4"), _DevArray(b.value, shape, "<f4")
+
+    def tonemap(self, exposure: float = 0.4):
+        out = np.empty((self.height, self.width, 4), dtype=np.uint8)
+        avg = C.c_float()
+        self._ck(self.lib.ds_tonemap(self.h, exposure, _ptr(out), C.byref(avg)))
+        return out, avg.value
+
+    def unconverged(self, subframe: int) -> int:
+        v = C.c_uint32()
+        self._ck(self.lib.ds_frame_unconverged(self.h, subframe, C.byref(v)))
+        return v.value
+
+    def export_moments(self, n: int, device_ptr: int):
+        self._ck(self.lib.ds_frame_export_moments_device(self.h, n, C.c_void_p(device_ptr)))
+
+    def import_moments(self, n_total: int, device_ptr: int):
+        self._ck(self.lib.ds_frame_import_moments_device(self.h, n_total, C.c_void_p(device_ptr)))
+
+    # ---- generic paths ----
+    def trace_paths(self, mode: int, origins, dirs, seed_val0, stream) -> np.ndarray:
+        o, d = _f32(origins).reshape(-1, 3), _f32(dirs).reshape(-1, 3)
+        s0 = np.ascontiguousarray(seed_val0, dtype=np.uint32)
+        st = np.ascontiguousarray(stream, dtype=np.uint32)
+        out = np.empty((len(o), 3), dtype=np.float32)
+        self._ck(self.lib.ds_trace_paths(self.h, mode, len(o), _ptr(o), _ptr(d), _ptr(s0), _ptr(st), _ptr(out)))
+        return out
+
+    # ---- dataset generation ----
+    def generate_points(self, first_index: int, n: int, stream: int = 0):
+        p = np.empty((n, 3), dtype=np.float32)
+        d = np.empty((n, 3), dtype=np.float32)
+        self._ck(self.lib.ds_generate_points(self.h, first_index, n, stream, _ptr(p), _ptr(d)))
+        return p, d
+
+    def descriptors(self, pos, dirs, as_float: bool = False, want_index: bool = False):
+        p, d = _f32(pos).reshape(-1, 3), _f32(dirs).reshape(-1, 3)
+        n = len(p)
+        if not as_float:
+            out = np.empty((n, 10, 225), dtype=np.uint8)
+            self._ck(self.lib.ds_collect_descriptors(self.h, _ptr(p), _ptr(d), n, _ptr(out)))
+            return out
+        out = np.empty((n, 10, 225), dtype=np.float32)
+        idx = np.empty((n, 10, 225, 4), dtype=np.int32) if want_index else None
+        self._ck(self.lib.ds_collect_descriptors_float(self.h, _ptr(p), _ptr(d), n, _ptr(out), _ptr(idx) if want_index else None))
+        return (out, idx) if want_index else out
+
+    def point_radiance(self, pos, dirs, max_threads: int = 20480, launches_per_update: int = 100, max_updates: int = 0):
+        p, d = _f32(pos).reshape(-1, 3), _f32(dirs).reshape(-1, 3)
+        n = len(p)
+        s = DsRadianceSettings()
+        self.lib.ds_radiance_settings_default(C.byref(s))
+        s.max_thread_count = max_threads
+        s.launches_per_update = launches_per_update
+        s.max_updates = max_updates
+        tasks = np.zeros(n, dtype=TASK_DTYPE)
+        conv = np.zeros(n, dtype=np.uint8)
+        upd = C.c_uint32()
+        self._ck(self.lib.ds_point_radiance_run(self.h, _ptr(p), _ptr(d), n, C.byref(s), _ptr(tasks), _ptr(conv), C.byref(upd)))
+        return tasks, conv.astype(bool), int(conv.sum()), upd.value
+
+
+# ---- records (host only; usable without a GPU) ----
+
+def record_scatter_sample(point, view_direction) -> bytes:
+    lib = _lib.load()
+    buf = (C.c_uint8 * 64)()
+    f3 = C.c_float * 3
+    n = lib.ds_record_scatter_sample(f3(*map(float, point)), f3(*map(float, view_direction)), buf, 64)
+    if n < 0:
+        raise DsError(n, "ds_record_scatter_sample failed")
+    return bytes(buf[:n])
+
+
+def record_disney_descriptor(grid: bytes) -> bytes:
+    lib = _lib.load()
+    cap = len(grid) + 16
+    buf = (C.c_uint8 * cap)()
+    src = (C.c_uint8 * max(1, len(grid))).from_buffer_copy(grid if grid else b"\0")
+    n = lib.ds_record_disney_descriptor(src, len(grid), buf, cap)
+    if n < 0:
+        raise DsError(n, "ds_record_disney_descriptor failed")
+    return bytes(buf[:n])
+
+
+def record_result(light_intensity: float, is_converged: bool) -> bytes:
+    lib = _lib.load()
+    buf = (C.c_uint8 * 16)()
+    n = lib.ds_record_result(float(light_intensity), int(bool(is_converged)), buf, 16)
+    if n < 0:
+        raise DsError(n, "ds_record_result failed")
+    return bytes(buf[:n])
+
+
+def record_scene_setup(cloud_path: str, cloud_size_m: float, light_direction) -> bytes:
+    lib = _lib.load()
+    raw = cloud_path.encode("utf-8")
+    cap = len(raw) + 64
+    buf = (C.c_uint8 * cap)()
+    f3 = C.c_float * 3
+    n = lib.ds_record_scene_setup(raw, float(cloud_size_m), f3(*map(float, light_direction)), buf, cap)
+    if n < 0:
+        raise DsError(n, "ds_record_scene_setup failed")
+    return bytes(buf[:n])

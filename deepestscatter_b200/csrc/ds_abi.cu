@@ -1,0 +1,1148 @@
+/*
+ * ds_abi.cu -- implementation of include/ds_abi.h: context, volume, scene, progressive renderer and
+ * dataset-generation entry points on top of the sm_100a kernels.  No CPU fallback: every entry point
+ * that computes needs a CUDA device and fails loudly without one.
+ */
+#include <algorithm>
+#include <cfloat>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "ds_kernels.h"
+
+extern "C" {
+extern const unsigned char ds_mie_blob[];     /* deepestscatter_b200/data/mie_tables.f32 (ds_mie_blob.S) */
+extern const unsigned char ds_mie_blob_end[];
+}
+
+using namespace dsk;
+
+struct DsContext {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool ownStream = true;
+    cudaDeviceProp prop{};
+    std::string err;
+    std::string desc;
+    std::map<std::string, int> opt;
+
+    /* volume */
+    std::vector<uint8_t*> levels;
+    std::vector<int> lnx, lny, lnz;
+    uint8_t* inscatter = nullptr;
+    bool baked = false;
+    cudaArray_t densityArr = nullptr, inscatterArr = nullptr;
+    cudaTextureObject_t densityTex = 0, inscatterTex = 0;
+    uint32_t* occ = nullptr;
+    int occShift = 0, ocx = 0, ocy = 0, ocz = 0, occWords = 0;
+
+    /* scene */
+    DsSceneParams params{};
+    bool sceneSet = false;
+    float derived[12] = {0};
+    float* mie = nullptr;     /* 3 * 4096 floats: mie, chopped, cdf */
+
+    /* frame */
+    int width = 0, height = 0;
+    float4 *progressive = nullptr, *variance = nullptr, *staging = nullptr;
+    size_t stagingSubframes = 0;
+    uchar4* screen = nullptr;
+    float *columns = nullptr, *average = nullptr;
+    uint32_t* unconv = nullptr;
+
+    /* counters + queue */
+    unsigned long long* stats = nullptr; /* CNT_COUNT */
+    unsigned long long* queue = nullptr;
+
+    /* launch accounting */
+    unsigned long long launches = 0;       /* kernels launched by this context since the last reset */
+    std::vector<cudaEvent_t> traceEvents;  /* start/stop pairs around k_trace launches ("profile_events") */
+    size_t traceEventsUsed = 0;
+
+    /* scratch */
+    void* scratch[8] = {nullptr};
+    size_t scratchSize[8] = {0};
+};
+
+static thread_local std::string g_createError;
+
+#define DS_FAIL(ctx, code, ...)                         \
+    do {                                                \
+        char _b[512];                                   \
+        snprintf(_b, sizeof(_b), __VA_ARGS__);          \
+        (ctx)->err = _b;                                \
+        return (code);                                  \
+    } while (0)
+
+#define DS_CUDA(ctx, call)                                                                              \
+    do {                                                                                                \
+        cudaError_t _e = (call);                                                                        \
+        if (_e != cudaSuccess) DS_FAIL(ctx, DS_ERR_CUDA, "%s: %s (%s:%d)", #call, cudaGetErrorString(_e), __FILE__, __LINE__); \
+    } while (0)
+
+#define DS_CHECK_CTX(ctx)          \
+    if (!(ctx)) return DS_ERR_INVALID; \
+    cudaSetDevice((ctx)->device)
+
+static int ensureScratch(DsContext* ctx, int slot, size_t bytes)
+{
+    if (ctx->scratchSize[slot] >= bytes) return DS_OK;
+    if (ctx->scratch[slot]) cudaFree(ctx->scratch[slot]);
+    ctx->scratch[slot] = nullptr;
+    ctx->scratchSize[slot] = 0;
+    DS_CUDA(ctx, cudaMalloc(&ctx->scratch[slot], bytes));
+    ctx->scratchSize[slot] = bytes;
+    return DS_OK;
+}
+
+static void freeVolume(DsContext* ctx)
+{
+    for (uint8_t* p : ctx->levels) cudaFree(p);
+    ctx->levels.clear();
+    ctx->lnx.clear();
+    ctx->lny.clear();
+    ctx->lnz.clear();
+    if (ctx->inscatter) cudaFree(ctx->inscatter);
+    ctx->inscatter = nullptr;
+    ctx->baked = false;
+    if (ctx->densityTex) cudaDestroyTextureObject(ctx->densityTex);
+    if (ctx->inscatterTex) cudaDestroyTextureObject(ctx->inscatterTex);
+    ctx->densityTex = ctx->inscatterTex = 0;
+    if (ctx->densityArr) cudaFreeArray(ctx->densityArr);
+    if (ctx->inscatterArr) cudaFreeArray(ctx->inscatterArr);
+    ctx->densityArr = ctx->inscatterArr = nullptr;
+    if (ctx->occ) cudaFree(ctx->occ);
+    ctx->occ = nullptr;
+}
+
+static void freeFrame(DsContext* ctx)
+{
+    cudaFree(ctx->progressive);
+    cudaFree(ctx->variance);
+    cudaFree(ctx->staging);
+    cudaFree(ctx->screen);
+    cudaFree(ctx->columns);
+    cudaFree(ctx->average);
+    cudaFree(ctx->unconv);
+    ctx->progressive = ctx->variance = ctx->staging = nullptr;
+    ctx->screen = nullptr;
+    ctx->columns = ctx->average = nullptr;
+    ctx->unconv = nullptr;
+    ctx->stagingSubframes = 0;
+    ctx->width = ctx->height = 0;
+}
+
+/* DG/Mie.cpp:8206-8282: phase samplers = table / mean(table); integral = running sum of table / sum(table) */
+static void buildMieSamplers(const float* mieRaw, const float* choppedRaw, float* out /* 3*4096 */)
+{
+    auto phase = [](const float* src, float* dst) {
+        float average = 0;
+        for (int i = 0; i < MIE_N; i++) average += src[i];
+        average /= MIE_N;
+        for (int i = 0; i < MIE_N; i++) dst[i] = src[i] / average;
+    };
+    phase(mieRaw, out);
+    phase(choppedRaw, out + MIE_N);
+    float sum = 0;
+    for (int i = 0; i < MIE_N; i++) sum += choppedRaw[i];
+    float integral = 0;
+    for (int i = 0; i < MIE_N; i++) {
+        integral += choppedRaw[i] / sum;
+        out[2 * MIE_N + i] = integral;
+    }
+}
+
+static int makeTexture(DsContext* ctx, const uint8_t* linear, int nx, int ny, int nz, cudaArray_t* arr, cudaTextureObject_t* tex)
+{
+    if (*tex) {
+        cudaDestroyTextureObject(*tex);
+        *tex = 0;
+    }
+    if (!*arr) {
+        cudaChannelFormatDesc cd = cudaCreateChannelDesc<unsigned char>();
+        DS_CUDA(ctx, cudaMalloc3DArray(arr, &cd, make_cudaExtent(nx, ny, nz)));
+    }
+    cudaMemcpy3DParms cp = {};
+    cp.srcPtr = make_cudaPitchedPtr((void*)linear, (size_t)nx, (size_t)nx, (size_t)ny);
+    cp.dstArray = *arr;
+    cp.extent = make_cudaExtent(nx, ny, nz);
+    cp.kind = cudaMemcpyDeviceToDevice;
+    DS_CUDA(ctx, cudaMemcpy3DAsync(&cp, ctx->stream));
+    cudaResourceDesc rd = {};
+    rd.resType = cudaResourceTypeArray;
+    rd.res.array.array = *arr;
+    cudaTextureDesc td = {};
+    /* VDBCloud::createSamplerForBuffer3D (VDBCloud.cpp:119-137) */
+    td.addressMode[0] = td.addressMode[1] = td.addressMode[2] = cudaAddressModeClamp;
+    td.filterMode = cudaFilterModeLinear;
+    td.readMode = cudaReadModeNormalizedFloat;
+    td.normalizedCoords = 1;
+    DS_CUDA(ctx, cudaCreateTextureObject(tex, &rd, &td, nullptr));
+    return DS_OK;
+}
+
+static void fillDevScene(DsContext* ctx, DevScene& sc)
+{
+    memset(&sc, 0, sizeof(sc));
+    sc.density = ctx->levels.empty() ? nullptr : ctx->levels[0];
+    sc.inscatter = ctx->inscatter;
+    sc.densityTex = ctx->densityTex;
+    sc.inscatterTex = ctx->inscatterTex;
+    if (!ctx->levels.empty()) {
+        sc.nx = ctx->lnx[0];
+        sc.ny = ctx->lny[0];
+        sc.nz = ctx->lnz[0];
+    }
+    const float* d = ctx->derived;
+    sc.bbox = V3{d[0], d[1], d[2]};
+    sc.texScale = V3{d[3], d[4], d[5]};
+    sc.mult = d[6];
+    sc.step = ctx->params.sample_step;
+    sc.minRay = ctx->params.minimal_ray_distance;
+    sc.light = V3{d[9], d[10], d[11]};
+    sc.lightColor = V3{ctx->params.light_color[0], ctx->params.light_color[1], ctx->params.light_color[2]};
+    sc.lightIntensity = ctx->params.light_intensity;
+    sc.mie = ctx->mie;
+    sc.chopped = ctx->mie + MIE_N;
+    sc.cdf = ctx->mie + 2 * MIE_N;
+    sc.occ = ctx->occ;
+    sc.occShift = ctx->occShift;
+    sc.ocx = ctx->ocx;
+    sc.ocy = ctx->ocy;
+    sc.ocz = ctx->ocz;
+    sc.occWords = ctx->occWords;
+}
+
+/* VDBCloud::setupVolumeVariables / setupVariables (VDBCloud.cpp:88-117) + Sun (SceneDescription.h:17-19) */
+static void computeDerived(DsContext* ctx)
+{
+    float* d = ctx->derived;
+    if (!ctx->levels.empty()) {
+        const float fx = (float)ctx->lnx[0], fy = (float)ctx->lny[0], fz = (float)ctx->lnz[0];
+        const float maxSize = std::max({fx, fy, fz});
+        d[0] = fx / maxSize;
+        d[1] = fy / maxSize;
+        d[2] = fz / maxSize;
+        d[3] = maxSize / fx;
+        d[4] = maxSize / fy;
+        d[5] = maxSize / fz;
+        const size_t mx = (size_t)std::max({ctx->lnx[0], ctx->lny[0], ctx->lnz[0]});
+        d[7] = ctx->params.cloud_size_m / mx;
+    }
+    d[6] = ctx->params.cloud_size_m / ctx->params.mean_free_path_m;
+    d[8] = d[7] / ctx->params.mean_free_path_m;
+    const float lx = ctx->params.light_direction[0], ly = ctx->params.light_direction[1], lz = ctx->params.light_direction[2];
+    const float invLen = 1.0f / sqrtf(lx * lx + ly * ly + lz * lz);
+    d[9] = lx * invLen;
+    d[10] = ly * invLen;
+    d[11] = lz * invLen;
+}
+
+static int finishVolume(DsContext* ctx, int buildMips)
+{
+    const int nx = ctx->lnx[0], ny = ctx->lny[0], nz = ctx->lnz[0];
+    if (buildMips) {
+        /* Resources.cpp:110-115 level count; optix getMipLevelSize = max(1, n >> level) */
+        int maxSize = std::max({nx, ny, nz});
+        int levelCount = 1;
+        while (maxSize /= 2) levelCount++;
+        if (levelCount > MAX_LEVELS) DS_FAIL(ctx, DS_ERR_INVALID, "volume too large: %d mip levels", levelCount);
+        for (int l = 1; l < levelCount; l++) {
+            const int cx = std::max(1, nx >> l), cy = std::max(1, ny >> l), cz = std::max(1, nz >> l);
+            uint8_t* p = nullptr;
+            DS_CUDA(ctx, cudaMalloc(&p, (size_t)cx * cy * cz));
+            ctx->levels.push_back(p);
+            ctx->lnx.push_back(cx);
+            ctx->lny.push_back(cy);
+            ctx->lnz.push_back(cz);
+            DS_CUDA(ctx, launchMip(ctx->levels[l - 1], ctx->lnx[l - 1], ctx->lny[l - 1], ctx->lnz[l - 1], p, cx, cy, cz, ctx->stream));
+        }
+    }
+    /* occupancy mask: smallest power-of-two cell with <= 2^18 cells (<= 32 KiB of bits in shared memory) */
+    int shift = 0;
+    for (;; shift++) {
+        const long long c = 1ll << shift;
+        const long long cells = ((nx + c - 1) / c) * ((ny + c - 1) / c) * ((nz + c - 1) / c);
+        if (cells <= (1ll << 18)) break;
+    }
+    const int c = 1 << shift;
+    ctx->occShift = shift;
+    ctx->ocx = (nx + c - 1) / c;
+    ctx->ocy = (ny + c - 1) / c;
+    ctx->ocz = (nz + c - 1) / c;
+    ctx->occWords = (ctx->ocx * ctx->ocy * ctx->ocz + 31) / 32;
+    DS_CUDA(ctx, cudaMalloc(&ctx->occ, (size_t)ctx->occWords * 4));
+    DS_CUDA(ctx, cudaMemsetAsync(ctx->occ, 0, (size_t)ctx->occWords * 4, ctx->stream));
+    DS_CUDA(ctx, launchOccupancy(ctx->levels[0], nx, ny, nz, shift, ctx->ocx, ctx->ocy, ctx->ocz, ctx->occ, ctx->stream));
+    int rc = makeTexture(ctx, ctx->levels[0], nx, ny, nz, &ctx->densityArr, &ctx->densityTex);
+    if (rc) return rc;
+    DS_CUDA(ctx, cudaMalloc(&ctx->inscatter, (size_t)nx * ny * nz));
+    DS_CUDA(ctx, cudaMemsetAsync(ctx->inscatter, 0, (size_t)nx * ny * nz, ctx->stream));
+    computeDerived(ctx);
+    DS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return DS_OK;
+}
+
+static int beginVolume(DsContext* ctx, int nx, int ny, int nz)
+{
+    if (nx <= 0 || ny <= 0 || nz <= 0) DS_FAIL(ctx, DS_ERR_INVALID, "bad volume size %dx%dx%d", nx, ny, nz);
+    freeVolume(ctx);
+    uint8_t* p = nullptr;
+    DS_CUDA(ctx, cudaMalloc(&p, (size_t)nx * ny * nz));
+    ctx->levels.push_back(p);
+    ctx->lnx.push_back(nx);
+    ctx->lny.push_back(ny);
+    ctx->lnz.push_back(nz);
+    return DS_OK;
+}
+
+static LaunchConfig launchConfig(DsContext* ctx)
+{
+    LaunchConfig cfg;
+    cfg.blockThreads = ctx->opt["block_threads"];
+    cfg.blocksPerSm = ctx->opt["blocks_per_sm"];
+    cfg.smCount = ctx->prop.multiProcessorCount;
+    cfg.skipEmpty = ctx->opt["skip_empty"];
+    return cfg;
+}
+
+static int runTrace(DsContext* ctx, TraceJob& job)
+{
+    DevScene sc;
+    fillDevScene(ctx, sc);
+    job.queue = ctx->queue;
+    job.stats = ctx->stats;
+    job.marchKeepQuarters = ctx->opt["march_keep_quarters"];
+    job.marchMaxIters = ctx->opt["march_max_iters"];
+    DS_CUDA(ctx, cudaMemsetAsync(ctx->queue, 0, sizeof(unsigned long long), ctx->stream));
+    const LaunchConfig cfg = launchConfig(ctx);
+    const bool prof = ctx->opt["profile_events"] != 0;
+    if (prof) {
+        while (ctx->traceEvents.size() < ctx->traceEventsUsed + 2) {
+            cudaEvent_t e;
+            DS_CUDA(ctx, cudaEventCreate(&e));
+            ctx->traceEvents.push_back(e);
+        }
+        DS_CUDA(ctx, cudaEventRecord(ctx->traceEvents[ctx->traceEventsUsed], ctx->stream));
+    }
+    if (ctx->opt["precision"] == DS_PRECISION_FAST)
+        DS_CUDA(ctx, KernelSet<true>::trace(sc, job, cfg, ctx->stream));
+    else
+        DS_CUDA(ctx, KernelSet<false>::trace(sc, job, cfg, ctx->stream));
+    ctx->launches++;
+    if (prof) {
+        DS_CUDA(ctx, cudaEventRecord(ctx->traceEvents[ctx->traceEventsUsed + 1], ctx->stream));
+        ctx->traceEventsUsed += 2;
+    }
+    return DS_OK;
+}
+
+static int requireScene(DsContext* ctx, bool needBake)
+{
+    if (ctx->levels.empty()) DS_FAIL(ctx, DS_ERR_STATE, "no volume uploaded");
+    if (!ctx->sceneSet) DS_FAIL(ctx, DS_ERR_STATE, "ds_scene_set has not been called");
+    if (needBake && !ctx->baked) DS_FAIL(ctx, DS_ERR_STATE, "sun transmittance volume not baked (ds_bake_sun_transmittance)");
+    return DS_OK;
+}
+
+extern "C" {
+
+/* ================================================================ context */
+
+int ds_context_create(int device, DsContext** out)
+{
+    if (!out) return DS_ERR_INVALID;
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        g_createError = std::string("no CUDA device available: ") + cudaGetErrorString(e) + " (this library has no CPU fallback)";
+        return DS_ERR_CUDA;
+    }
+    if (device < 0 || device >= count) {
+        g_createError = "device index out of range";
+        return DS_ERR_INVALID;
+    }
+    DsContext* ctx = new DsContext();
+    ctx->device = device;
+    if (cudaSetDevice(device) != cudaSuccess || cudaGetDeviceProperties(&ctx->prop, device) != cudaSuccess) {
+        g_createError = "cudaSetDevice / cudaGetDeviceProperties failed";
+        delete ctx;
+        return DS_ERR_CUDA;
+    }
+    if (ctx->prop.major < 10) {
+        char b[256];
+        snprintf(b, sizeof(b), "device %d (%s, sm_%d%d) is not a Blackwell sm_100 GPU; kernels are built for sm_100a only", device,
+                 ctx->prop.name, ctx->prop.major, ctx->prop.minor);
+        g_createError = b;
+        delete ctx;
+        return DS_ERR_CUDA;
+    }
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        g_createError = "cudaStreamCreate failed";
+        delete ctx;
+        return DS_ERR_CUDA;
+    }
+    ctx->opt["precision"] = DS_PRECISION_FAST;
+    ctx->opt["variant"] = 0;
+    ctx->opt["block_threads"] = 512;
+    ctx->opt["blocks_per_sm"] = 2;
+    ctx->opt["skip_empty"] = 1;
+    ctx->opt["march_keep_quarters"] = 2;
+    ctx->opt["march_max_iters"] = 64;
+    ctx->opt["staging_subframes"] = 16;
+    ctx->opt["stream_offset"] = 0;
+    ctx->opt["profile_events"] = 0;
+    ds_scene_params_default(&ctx->params);
+    bool ok = cudaMalloc(&ctx->stats, CNT_COUNT * sizeof(unsigned long long)) == cudaSuccess &&
+              cudaMalloc(&ctx->queue, sizeof(unsigned long long)) == cudaSuccess &&
+              cudaMemset(ctx->stats, 0, CNT_COUNT * sizeof(unsigned long long)) == cudaSuccess &&
+              cudaMalloc(&ctx->mie, 3 * MIE_N * sizeof(float)) == cudaSuccess;
+    if (ok) {
+        if ((size_t)(ds_mie_blob_end - ds_mie_blob) != 2 * MIE_N * sizeof(float)) {
+            g_createError = "embedded Mie table blob has the wrong size";
+            ok = false;
+        } else {
+            std::vector<float> raw(2 * MIE_N), samplers(3 * MIE_N);
+            memcpy(raw.data(), ds_mie_blob, raw.size() * sizeof(float));
+            buildMieSamplers(raw.data(), raw.data() + MIE_N, samplers.data());
+            ok = cudaMemcpy(ctx->mie, samplers.data(), samplers.size() * sizeof(float), cudaMemcpyHostToDevice) == cudaSuccess;
+        }
+    }
+    if (!ok) {
+        if (g_createError.empty()) g_createError = "device allocation failed";
+        ds_context_destroy(ctx);
+        return DS_ERR_CUDA;
+    }
+    *out = ctx;
+    return DS_OK;
+}
+
+int ds_context_destroy(DsContext* ctx)
+{
+    if (!ctx) return DS_ERR_INVALID;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    freeVolume(ctx);
+    freeFrame(ctx);
+    cudaFree(ctx->stats);
+    cudaFree(ctx->queue);
+    cudaFree(ctx->mie);
+    for (int i = 0; i < 8; i++) cudaFree(ctx->scratch[i]);
+    for (cudaEvent_t e : ctx->traceEvents) cudaEventDestroy(e);
+    if (ctx->ownStream && ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return DS_OK;
+}
+
+const char* ds_last_error(DsContext* ctx) { return ctx ? ctx->err.c_str() : g_createError.c_str(); }
+
+int ds_context_set_stream(DsContext* ctx, void* cuda_stream)
+{
+    DS_CHECK_CTX(ctx);
+    DS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (ctx->ownStream && ctx->stream) cudaStreamDestroy(ctx->stream);
+    ctx->stream = (cudaStream_t)cuda_stream;
+    ctx->ownStream = false;
+    return DS_OK;
+}
+
+int ds_sync(DsContext* ctx)
+{
+    DS_CHECK_CTX(ctx);
+    DS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return DS_OK;
+}
+
+int ds_set_option(DsContext* ctx, const char* name, int value)
+{
+    DS_CHECK_CTX(ctx);
+    if (!name || ctx->opt.find(name) == ctx->opt.end()) DS_FAIL(ctx, DS_ERR_INVALID, "unknown option '%s'", name ? name : "(null)");
+    const std::string n = name;
+    if (n == "block_threads" && (value < 32 || value > 512 || value % 32)) DS_FAIL(ctx, DS_ERR_INVALID, "block_threads must be 32..512, multiple of 32");
+    if (n == "blocks_per_sm" && (value < 1 || value > 32)) DS_FAIL(ctx, DS_ERR_INVALID, "blocks_per_sm must be 1..32");
+    if (n == "precision" && value != DS_PRECISION_EXACT && value != DS_PRECISION_FAST) DS_FAIL(ctx, DS_ERR_INVALID, "precision must be 0 or 1");
+    if (n == "staging_subframes" && value < 1) DS_FAIL(ctx, DS_ERR_INVALID, "staging_subframes must be >= 1");
+    if (n == "march_max_iters" && value < 1) DS_FAIL(ctx, DS_ERR_INVALID, "march_max_iters must be >= 1");
+    ctx->opt[n] = value;
+    return DS_OK;
+}
+
+int ds_get_option(DsContext* ctx, const char* name, int* value)
+{
+    DS_CHECK_CTX(ctx);
+    if (!name || !value || ctx->opt.find(name) == ctx->opt.end()) DS_FAIL(ctx, DS_ERR_INVALID, "unknown option '%s'", name ? name : "(null)");
+    *value = ctx->opt[name];
+    return DS_OK;
+}
+
+int ds_get_counters(DsContext* ctx, DsCounters* out)
+{
+    DS_CHECK_CTX(ctx);
+    if (!out) return DS_ERR_INVALID;
+    unsigned long long h[CNT_COUNT];
+    DS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    DS_CUDA(ctx, cudaMemcpy(h, ctx->stats, sizeof(h), cudaMemcpyDeviceToHost));
+    out->paths = h[CNT_PATHS];
+    out->events = h[CNT_EVENTS];
+    out->steps = h[CNT_STEPS];
+    out->density_taps = h[CNT_TAPS];
+    out->nonfinite = h[CNT_NONFINITE];
+    return DS_OK;
+}
+
+int ds_reset_counters(DsContext* ctx)
+{
+    DS_CHECK_CTX(ctx);
+    DS_CUDA(ctx, cudaMemsetAsync(ctx->stats, 0, CNT_COUNT * sizeof(unsigned long long), ctx->stream));
+    DS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->launches = 0;
+    ctx->traceEventsUsed = 0;
+    return DS_OK;
+}
+
+int ds_get_launch_stats(DsContext* ctx, uint64_t* kernel_launches, uint64_t* trace_launches_timed, double* trace_ms_total)
+{
+    DS_CHECK_CTX(ctx);
+    DS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    double total = 0;
+    for (size_t i = 0; i + 1 < ctx->traceEventsUsed; i += 2) {
+        float ms = 0;
+        DS_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->traceEvents[i], ctx->traceEvents[i + 1]));
+        total += ms;
+    }
+    if (kernel_launches) *kernel_launches = ctx->launches;
+    if (trace_launches_timed) *trace_launches_timed = ctx->traceEventsUsed / 2;
+    if (trace_ms_total) *trace_ms_total = total;
+    return DS_OK;
+}
+
+const char* ds_describe(DsContext* ctx)
+{
+    if (!ctx) return "{}";
+    char b[512];
+    snprintf(b, sizeof(b),
+             "{\"library\": \"deepestscatter_b200\", \"device\": \"%s\", \"sm\": %d%d, \"sm_count\": %d, \"l2_bytes\": %d, "
+             "\"global_mem_bytes\": %zu, \"arch\": \"sm_100a\"}",
+             ctx->prop.name, ctx->prop.major, ctx->prop.minor, ctx->prop.multiProcessorCount, ctx->prop.l2CacheSize,
+             (size_t)ctx->prop.totalGlobalMem);
+    ctx->desc = b;
+    return ctx->desc.c_str();
+}
+
+/* ================================================================ volume */
+
+int ds_volume_upload(DsContext* ctx, const uint8_t* level0, int nx, int ny, int nz, int build_mips)
+{
+    DS_CHECK_CTX(ctx);
+    if (!level0) DS_FAIL(ctx, DS_ERR_INVALID, "level0 is NULL");
+    int rc = beginVolume(ctx, nx, ny, nz);
+    if (rc) return rc;
+    DS_CUDA(ctx, cudaMemcpyAsync(ctx->levels[0], level0, (size_t)nx * ny * nz, cudaMemcpyHostToDevice, ctx->stream));
+    return finishVolume(ctx, build_mips);
+}
+
+int ds_volume_upload_float(DsContext* ctx, const float* dense, int nx, int ny, int nz, double max_density, int build_mips)
+{
+    DS_CHECK_CTX(ctx);
+    if (!dense) DS_FAIL(ctx, DS_ERR_INVALID, "dense is NULL");
+    if (!(max_density > 0)) DS_FAIL(ctx, DS_ERR_INVALID, "max_density must be positive");
+    int rc = beginVolume(ctx, nx, ny, nz);
+    if (rc) return rc;
+    const size_t count = (size_t)nx * ny * nz;
+    rc = ensureScratch(ctx, 0, count * sizeof(float));
+    if (rc) return rc;
+    DS_CUDA(ctx, cudaMemcpyAsync(ctx->scratch[0], dense, count * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    DS_CUDA(ctx, launchQuantize((const float*)ctx->scratch[0], count, max_density, ctx->levels[0], ctx->stream));
+    return finishVolume(ctx, build_mips);
+}
+
+int ds_volume_synth(DsContext* ctx, int n, int kind, uint32_t seed, int build_mips)
+{
+    DS_CHECK_CTX(ctx);
+    if (n < 4 || n > 2048) DS_FAIL(ctx, DS_ERR_INVALID, "synthetic grid size %d out of range [4, 2048]", n);
+    if (kind < 0 || kind > 2) DS_FAIL(ctx, DS_ERR_INVALID, "unknown synthetic kind %d", kind);
+    int rc = beginVolume(ctx, n, n, n);
+    if (rc) return rc;
+    DS_CUDA(ctx, launchSynth(ctx->levels[0], n, kind, seed, ctx->stream));
+    return finishVolume(ctx, build_mips);
+}
+
+int ds_volume_level_count(DsContext* ctx, int* count)
+{
+    DS_CHECK_CTX(ctx);
+    if (!count) return DS_ERR_INVALID;
+    *count = (int)ctx->levels.size();
+    return DS_OK;
+}
+
+int ds_volume_level_dims(DsContext* ctx, int level, int dims[3])
+{
+    DS_CHECK_CTX(ctx);
+    if (level < 0 || level >= (int)ctx->levels.size()) DS_FAIL(ctx, DS_ERR_INVALID, "mip level %d out of range", level);
+    dims[0] = ctx->lnx[level];
+    dims[1] = ctx->lny[level];
+    dims[2] = ctx->lnz[level];
+    return DS_OK;
+}
+
+int ds_volume_download_level(DsContext* ctx, int level, uint8_t* out)
+{
+    DS_CHECK_CTX(ctx);
+    if (level < 0 || level >= (int)ctx->levels.size() || !out) DS_FAIL(ctx, DS_ERR_INVALID, "mip level %d out of range", level);
+    DS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    DS_CUDA(ctx, cudaMemcpy(out, ctx->levels[level], (size_t)ctx->lnx[level] * ctx->lny[level] * ctx->lnz[level], cudaMemcpyDeviceToHost));
+    return DS_OK;
+}
+
+/* ================================================================ scene */
+
+void ds_scene_params_default(DsSceneParams* p)
+{
+    if (!p) return;
+    p->cloud_size_m = 7000.0f;      /* main.cpp:63 */
+    p->mean_free_path_m = 10.0f;    /* SceneDescription.h:80 */
+    p->sample_step = 1.0f / 512.f;  /* installers.cpp:86 */
+    p->light_direction[0] = -0.03f; /* LightDirection::Side, Tasks.cpp:58 */
+    p->light_direction[1] = -0.25f;
+    p->light_direction[2] = 0.8f;
+    p->light_color[0] = p->light_color[1] = p->light_color[2] = 1.0f; /* installers.cpp:99 */
+    p->light_intensity = 1e6f;                                           /* installers.cpp:100 */
+    p->minimal_ray_distance = 0.000001f;                                 /* CloudMaterial.cpp:23 */
+}
+
+int ds_scene_set(DsContext* ctx, const DsSceneParams* p)
+{
+    DS_CHECK_CTX(ctx);
+    if (!p) DS_FAIL(ctx, DS_ERR_INVALID, "params is NULL");
+    if (!(p->cloud_size_m > 0) || !(p->mean_free_path_m > 0) || !(p->sample_step > 0) || p->sample_step > 1)
+        DS_FAIL(ctx, DS_ERR_INVALID, "cloud_size_m, mean_free_path_m must be > 0 and sample_step in (0, 1]");
+    const float l2 = p->light_direction[0] * p->light_direction[0] + p->light_direction[1] * p->light_direction[1] +
+                     p->light_direction[2] * p->light_direction[2];
+    if (!(l2 > 0)) DS_FAIL(ctx, DS_ERR_INVALID, "light_direction is zero");
+    const bool lightChanged = !ctx->sceneSet || memcmp(p->light_direction, ctx->params.light_direction, 12) != 0 ||
+                              p->cloud_size_m != ctx->params.cloud_size_m || p->mean_free_path_m != ctx->params.mean_free_path_m ||
+                              p->sample_step != ctx->params.sample_step;
+    ctx->params = *p;
+    ctx->sceneSet = true;
+    if (lightChanged) ctx->baked = false;
+    computeDerived(ctx);
+    return DS_OK;
+}
+
+int ds_scene_get_derived(DsContext* ctx, float out[12])
+{
+    DS_CHECK_CTX(ctx);
+    memcpy(out, ctx->derived, sizeof(ctx->derived));
+    return DS_OK;
+}
+
+int ds_bake_sun_transmittance(DsContext* ctx)
+{
+    DS_CHECK_CTX(ctx);
+    int rc = requireScene(ctx, false);
+    if (rc) return rc;
+    DevScene sc;
+    fillDevScene(ctx, sc);
+    if (ctx->opt["precision"] == DS_PRECISION_FAST)
+        DS_CUDA(ctx, KernelSet<true>::bake(sc, ctx->inscatter, ctx->opt["skip_empty"], ctx->stream));
+    else
+        DS_CUDA(ctx, KernelSet<false>::bake(sc, ctx->inscatter, ctx->opt["skip_empty"], ctx->stream));
+    rc = makeTexture(ctx, ctx->inscatter, ctx->lnx[0], ctx->lny[0], ctx->lnz[0], &ctx->inscatterArr, &ctx->inscatterTex);
+    if (rc) return rc;
+    ctx->baked = true;
+    return DS_OK;
+}
+
+int ds_inscatter_download(DsContext* ctx, uint8_t* out)
+{
+    DS_CHECK_CTX(ctx);
+    if (ctx->levels.empty() || !out) DS_FAIL(ctx, DS_ERR_STATE, "no volume");
+    DS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    DS_CUDA(ctx, cudaMemcpy(out, ctx->inscatter, (size_t)ctx->lnx[0] * ctx->lny[0] * ctx->lnz[0], cudaMemcpyDeviceToHost));
+    return DS_OK;
+}
+
+int ds_inscatter_upload(DsContext* ctx, const uint8_t* in)
+{
+    DS_CHECK_CTX(ctx);
+    if (ctx->levels.empty() || !in) DS_FAIL(ctx, DS_ERR_STATE, "no volume");
+    DS_CUDA(ctx, cudaMemcpyAsync(ctx->inscatter, in, (size_t)ctx->lnx[0] * ctx->lny[0] * ctx->lnz[0], cudaMemcpyHostToDevice, ctx->stream));
+    int rc = makeTexture(ctx, ctx->inscatter, ctx->lnx[0], ctx->lny[0], ctx->lnz[0], &ctx->inscatterArr, &ctx->inscatterTex);
+    if (rc) return rc;
+    ctx->baked = true;
+    return DS_OK;
+}
+
+void ds_camera_look_at(const float eye[3], const float lookat[3], const float up[3], float hfov_deg, float aspect, DsCamera* out)
+{
+    /* sutil::calculateCameraVariables, fov_is_vertical = false */
+    float W[3] = {lookat[0] - eye[0], lookat[1] - eye[1], lookat[2] - eye[2]};
+    const float wlen = sqrtf(W[0] * W[0] + W[1] * W[1] + W[2] * W[2]);
+    auto cross3 = [](const float* a, const float* b, float* c) {
+        c[0] = a[1] * b[2] - a[2] * b[1];
+        c[1] = a[2] * b[0] - a[0] * b[2];
+        c[2] = a[0] * b[1] - a[1] * b[0];
+    };
+    auto norm3 = [](float* v) {
+        const float inv = 1.0f / sqrtf(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
+        v[0] *= inv;
+        v[1] *= inv;
+        v[2] *= inv;
+    };
+    float U[3], V[3];
+    cross3(W, up, U);
+    norm3(U);
+    cross3(U, W, V);
+    norm3(V);
+    const float ulen = wlen * tanf(0.5f * hfov_deg * PI_F / 180.0f);
+    const float vlen = ulen / aspect;
+    for (int i = 0; i < 3; i++) {
+        out->eye[i] = eye[i];
+        out->U[i] = U[i] * ulen;
+        out->V[i] = V[i] * vlen;
+        out->W[i] = W[i];
+    }
+}
+
+void ds_camera_default(int width, int height, DsCamera* out)
+{
+    const float eye[3] = {2.5f, -0.4f, 0.0f}, lookat[3] = {0, 0, 0}, up[3] = {0, 1, 0};
+    ds_camera_look_at(eye, lookat, up, 30.0f, (float)width / (float)height, out);
+}
+
+/* ================================================================ progressive renderer */
+
+int ds_frame_create(DsContext* ctx, int width, int height)
+{
+    DS_CHECK_CTX(ctx);
+    if (width <= 0 || height <= 0 || width > 4096 || height > 4096)
+        DS_FAIL(ctx, DS_ERR_INVALID, "frame size %dx%d out of range (seed packs x*4096+y, cloudRadianceMaterials.cu:21)", width, height);
+    freeFrame(ctx);
+    const size_t px = (size_t)width * height;
+    DS_CUDA(ctx, cudaMalloc(&ctx->progressive, px * sizeof(float4)));
+    DS_CUDA(ctx, cudaMalloc(&ctx->variance, px * sizeof(float4)));
+    DS_CUDA(ctx, cudaMalloc(&ctx->screen, px * sizeof(uchar4)));
+    DS_CUDA(ctx, cudaMalloc(&ctx->columns, (size_t)width * sizeof(float)));
+    DS_CUDA(ctx, cudaMalloc(&ctx->average, sizeof(float)));
+    DS_CUDA(ctx, cudaMalloc(&ctx->unconv, sizeof(uint32_t)));
+    ctx->width = width;
+    ctx->height = height;
+    return ds_frame_clear(ctx);
+}
+
+int ds_frame_clear(DsContext* ctx)
+{
+    DS_CHECK_CTX(ctx);
+    if (!ctx->progressive) DS_FAIL(ctx, DS_ERR_STATE, "no frame (ds_frame_create)");
+    const size_t px = (size_t)ctx->width * ctx->height;
+    DS_CUDA(ctx, cudaMemsetAsync(ctx->progressive, 0, px * sizeof(float4), ctx->stream));
+    DS_CUDA(ctx, cudaMemsetAsync(ctx->variance, 0, px * sizeof(float4), ctx->stream));
+    return DS_OK;
+}
+
+static int ensureStaging(DsContext* ctx, size_t subframes)
+{
+    if (ctx->stagingSubframes >= subframes) return DS_OK;
+    cudaFree(ctx->staging);
+    ctx->staging = nullptr;
+    ctx->stagingSubframes = 0;
+    DS_CUDA(ctx, cudaMalloc(&ctx->staging, subframes * (size_t)ctx->width * ctx->height * sizeof(float4)));
+    ctx->stagingSubframes = subframes;
+    return DS_OK;
+}
+
+static void fillRenderJob(DsContext* ctx, TraceJob& job, const DsCamera* cam, DsMode mode, uint32_t first, uint32_t n)
+{
+    memset(&job, 0, sizeof(job));
+    job.kind = JOB_RENDER;
+    job.mode = (int)mode;
+    memcpy(job.eye, cam->eye, 12);
+    memcpy(job.U, cam->U, 12);
+    memcpy(job.V, cam->V, 12);
+    memcpy(job.W, cam->W, 12);
+    job.width = ctx->width;
+    job.height = ctx->height;
+    job.tilesX = (ctx->width + 7) / 8;
+    const int tilesY = (ctx->height + 3) / 4;
+    job.itemsPerSubframe = (unsigned long long)job.tilesX * tilesY * 32ull;
+    /* RNG stream id of a subframe; stream_offset lets a rank render global subframes [offset+1, offset+n]
+     * while its local Welford weights still run 1/1, 1/2, ... (multi-GPU split) */
+    job.firstSubframe = first + (uint32_t)ctx->opt["stream_offset"];
+    job.total = job.itemsPerSubframe * n;
+    job.staging = ctx->staging;
+}
+
+static int checkRender(DsContext* ctx, const DsCamera* cam, DsMode mode)
+{
+    int rc = requireScene(ctx, true);
+    if (rc) return rc;
+    if (!ctx->progressive) DS_FAIL(ctx, DS_ERR_STATE, "no frame (ds_frame_create)");
+    if (!cam) DS_FAIL(ctx, DS_ERR_INVALID, "camera is NULL");
+    if ((int)mode < 0 || (int)mode > 2) DS_FAIL(ctx, DS_ERR_INVALID, "Invalid Render Mode"); /* CloudMaterial.cpp:62 */
+    return DS_OK;
+}
+
+int ds_render_frame_result(DsContext* ctx, const DsCamera* cam, DsMode mode, uint32_t subframe_id, float* frame_result_out)
+{
+    DS_CHECK_CTX(ctx);
+    int rc = checkRender(ctx, cam, mode);
+    if (rc) return rc;
+    rc = ensureStaging(ctx, 1);
+    if (rc) return rc;
+    TraceJob job;
+    fillRenderJob(ctx, job, cam, mode, subframe_id, 1);
+    rc = runTrace(ctx, job);
+    if (rc) return rc;
+    if (frame_result_out) {
+        DS_CUDA(ctx, cudaMemcpyAsync(frame_result_out, ctx->staging, (size_t)ctx->width * ctx->height * sizeof(float4), cudaMemcpyDeviceToHost,
+                                     ctx->stream));
+        DS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    return DS_OK;
+}
+
+int ds_render_subframes(DsContext* ctx, const DsCamera* cam, DsMode mode, uint32_t first_subframe, uint32_t n)
+{
+    DS_CHECK_CTX(ctx);
+    int rc = checkRender(ctx, cam, mode);
+    if (rc) return rc;
+    if (first_subframe == 0) DS_FAIL(ctx, DS_ERR_INVALID, "subframe ids are 1-based (Camera.cpp:191)");
+    const uint32_t chunkMax = (uint32_t)ctx->opt["staging_subframes"];
+    rc = ensureStaging(ctx, std::min<uint32_t>(chunkMax, n));
+    if (rc) return rc;
+    const size_t px = (size_t)ctx->width * ctx->height;
+    for (uint32_t done = 0; done < n;) {
+        const uint32_t chunk = std::min<uint32_t>(chunkMax, n - done);
+        TraceJob job;
+        fillRenderJob(ctx, job, cam, mode, first_subframe + done, chunk);
+        rc = runTrace(ctx, job);
+        if (rc) return rc;
+        DS_CUDA(ctx, launchUpdateFrame(ctx->staging, ctx->progressive, ctx->variance, px, first_subframe + done, chunk, ctx->stream));
+        ctx->launches++;
+        done += chunk;
+    }
+    return DS_OK;
+}
+
+int ds_render_subframes_host(DsContext* ctx, const DsCamera* cam, DsMode mode, uint32_t first_subframe, uint32_t n, float* progressive_inout,
+                             float* variance_inout)
+{
+    DS_CHECK_CTX(ctx);
+    if (!progressive_inout || !variance_inout) DS_FAIL(ctx, DS_ERR_INVALID, "host buffers are NULL");
+    int rc = ds_frame_upload(ctx, progressive_inout, variance_inout);
+    if (rc) return rc;
+    rc = ds_render_subframes(ctx, cam, mode, first_subframe, n);
+    if (rc) return rc;
+    return ds_frame_download(ctx, progressive_inout, variance_inout);
+}
+
+int ds_frame_download(DsContext* ctx, float* progressive_out, float* variance_out)
+{
+    DS_CHECK_CTX(ctx);
+    if (!ctx->progressive) DS_FAIL(ctx, DS_ERR_STATE, "no frame (ds_frame_create)");
+    const size_t bytes = (size_t)ctx->width * ctx->height * sizeof(float4);
+    if (progressive_out) DS_CUDA(ctx, cudaMemcpyAsync(progressive_out, ctx->progressive, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    if (variance_out) DS_CUDA(ctx, cudaMemcpyAsync(variance_out, ctx->variance, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    DS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return DS_OK;
+}
+
+int ds_frame_upload(DsContext* ctx, const float* progressive, const float* variance)
+{
+    DS_CHECK_CTX(ctx);
+    if (!ctx->progressive) DS_FAIL(ctx, DS_ERR_STATE, "no frame (ds_frame_create)");
+    const size_t bytes = (size_t)ctx->width * ctx->height * sizeof(float4);
+    if (progressive) DS_CUDA(ctx, cudaMemcpyAsync(ctx->progressive, progressive, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    if (variance) DS_CUDA(ctx, cudaMemcpyAsync(ctx->variance, variance, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    return DS_OK;
+}
+
+int ds_frame_device_ptrs(DsContext* ctx, void** progressive, void** variance)
+{
+    DS_CHECK_CTX(ctx);
+    if (!ctx->progressive) DS_FAIL(ctx, DS_ERR_STATE, "no frame (ds_frame_create)");
+    if (progressive) *progressive = ctx->progressive;
+    if (variance) *variance = ctx->variance;
+    return DS_OK;
+}
+
+int ds_tonemap(DsContext* ctx, float exposure, uint8_t* screen_out, float* average_luminance_out)
+{
+    DS_CHECK_CTX(ctx);
+    if (!ctx->progressive) DS_FAIL(ctx, DS_ERR_STATE, "no frame (ds_frame_create)");
+    DS_CUDA(ctx, launchTonemap(ctx->progressive, ctx->width, ctx->height, exposure, ctx->columns, ctx->average, ctx->screen, ctx->stream));
+    if (screen_out)
+        DS_CUDA(ctx, cudaMemcpyAsync(screen_out, ctx->screen, (size_t)ctx->width * ctx->height * sizeof(uchar4), cudaMemcpyDeviceToHost, ctx->stream));
+    if (average_luminance_out)
+        DS_CUDA(ctx, cudaMemcpyAsync(average_luminance_out, ctx->average, sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    DS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return DS_OK;
+}
+
+int ds_frame_unconverged(DsContext* ctx, uint32_t subframe_id, uint32_t* unconverged_out)
+{
+    DS_CHECK_CTX(ctx);
+    if (!ctx->progressive || !unconverged_out) DS_FAIL(ctx, DS_ERR_STATE, "no frame (ds_frame_create)");
+    DS_CUDA(ctx, cudaMemsetAsync(ctx->unconv, 0, sizeof(uint32_t), ctx->stream));
+    DS_CUDA(ctx, launchUnconverged(ctx->progressive, ctx->variance, (size_t)ctx->width * ctx->height, subframe_id, ctx->unconv, ctx->stream));
+    DS_CUDA(ctx, cudaMemcpyAsync(unconverged_out, ctx->unconv, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    DS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return DS_OK;
+}
+
+int ds_frame_export_moments_device(DsContext* ctx, uint32_t n, double* moments_device)
+{
+    DS_CHECK_CTX(ctx);
+    if (!ctx->progressive || !moments_device) DS_FAIL(ctx, DS_ERR_STATE, "no frame (ds_frame_create)");
+    DS_CUDA(ctx, launchExportMoments(ctx->progressive, ctx->variance, (size_t)ctx->width * ctx->height, n, moments_device, ctx->stream));
+    return DS_OK;
+}
+
+int ds_frame_import_moments_device(DsContext* ctx, uint32_t n_total, const double* moments_device)
+{
+    DS_CHECK_CTX(ctx);
+    if (!ctx->progressive || !moments_device || n_total == 0) DS_FAIL(ctx, DS_ERR_STATE, "no frame (ds_frame_create) or n_total == 0");
+    DS_CUDA(ctx, launchImportMoments(moments_device, (size_t)ctx->width * ctx->height, n_total, ctx->progressive, ctx->variance, ctx->stream));
+    return DS_OK;
+}
+
+/* ================================================================ generic paths */
+
+int ds_trace_paths(DsContext* ctx, DsMode mode, uint32_t n, const float* origins, const float* directions, const uint32_t* seed_val0,
+                   const uint32_t* stream, float* radiance_out)
+{
+    DS_CHECK_CTX(ctx);
+    int rc = requireScene(ctx, true);
+    if (rc) return rc;
+    if ((int)mode < 0 || (int)mode > 2) DS_FAIL(ctx, DS_ERR_INVALID, "Invalid Render Mode");
+    if (n == 0) return DS_OK;
+    if (!origins || !directions || !seed_val0 || !stream || !radiance_out) DS_FAIL(ctx, DS_ERR_INVALID, "NULL argument");
+    const size_t f3 = (size_t)n * 3 * sizeof(float), u1 = (size_t)n * sizeof(uint32_t);
+    if ((rc = ensureScratch(ctx, 0, f3)) || (rc = ensureScratch(ctx, 1, f3)) || (rc = ensureScratch(ctx, 2, u1)) ||
+        (rc = ensureScratch(ctx, 3, u1)) || (rc = ensureScratch(ctx, 4, f3)))
+        return rc;
+    DS_CUDA(ctx, cudaMemcpyAsync(ctx->scratch[0], origins, f3, cudaMemcpyHostToDevice, ctx->stream));
+    DS_CUDA(ctx, cudaMemcpyAsync(ctx->scratch[1], directions, f3, cudaMemcpyHostToDevice, ctx->stream));
+    DS_CUDA(ctx, cudaMemcpyAsync(ctx->scratch[2], seed_val0, u1, cudaMemcpyHostToDevice, ctx->stream));
+    DS_CUDA(ctx, cudaMemcpyAsync(ctx->scratch[3], stream, u1, cudaMemcpyHostToDevice, ctx->stream));
+    TraceJob job;
+    memset(&job, 0, sizeof(job));
+    job.kind = JOB_PATHS;
+    job.mode = (int)mode;
+    job.total = n;
+    job.origins = (const float*)ctx->scratch[0];
+    job.dirs = (const float*)ctx->scratch[1];
+    job.seedVal0 = (const uint32_t*)ctx->scratch[2];
+    job.stream = (const uint32_t*)ctx->scratch[3];
+    job.radianceOut = (float*)ctx->scratch[4];
+    rc = runTrace(ctx, job);
+    if (rc) return rc;
+    DS_CUDA(ctx, cudaMemcpyAsync(radiance_out, ctx->scratch[4], f3, cudaMemcpyDeviceToHost, ctx->stream));
+    DS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return DS_OK;
+}
+
+/* ================================================================ dataset generation */
+
+int ds_generate_points(DsContext* ctx, uint32_t first_index, uint32_t n, uint32_t stream, float* positions_out, float* directions_out)
+{
+    DS_CHECK_CTX(ctx);
+    int rc = requireScene(ctx, false);
+    if (rc) return rc;
+    if (n == 0) return DS_OK;
+    if (!positions_out || !directions_out) DS_FAIL(ctx, DS_ERR_INVALID, "NULL argument");
+    const size_t f3 = (size_t)n * 3 * sizeof(float);
+    if ((rc = ensureScratch(ctx, 0, f3)) || (rc = ensureScratch(ctx, 1, f3))) return rc;
+    DevScene sc;
+    fillDevScene(ctx, sc);
+    if (ctx->opt["precision"] == DS_PRECISION_FAST)
+        DS_CUDA(ctx, KernelSet<true>::generatePoints(sc, first_index, n, stream, (float*)ctx->scratch[0], (float*)ctx->scratch[1], ctx->stats, ctx->stream));
+    else
+        DS_CUDA(ctx, KernelSet<false>::generatePoints(sc, first_index, n, stream, (float*)ctx->scratch[0], (float*)ctx->scratch[1], ctx->stats, ctx->stream));
+    DS_CUDA(ctx, cudaMemcpyAsync(positions_out, ctx->scratch[0], f3, cudaMemcpyDeviceToHost, ctx->stream));
+    DS_CUDA(ctx, cudaMemcpyAsync(directions_out, ctx->scratch[1], f3, cudaMemcpyDeviceToHost, ctx->stream));
+    DS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return DS_OK;
+}
+
+static int collectDescriptors(DsContext* ctx, const float* positions, const float* directions, uint32_t n, uint8_t* outU8, float* outF32,
+                              int32_t* tapIndex)
+{
+    int rc = requireScene(ctx, false);
+    if (rc) return rc;
+    if (n == 0) return DS_OK;
+    if (!positions || !directions) DS_FAIL(ctx, DS_ERR_INVALID, "NULL argument");
+    const size_t f3 = (size_t)n * 3 * sizeof(float), taps = (size_t)n * 2250;
+    if ((rc = ensureScratch(ctx, 0, f3)) || (rc = ensureScratch(ctx, 1, f3))) return rc;
+    if (outU8 && (rc = ensureScratch(ctx, 2, taps))) return rc;
+    if (outF32 && (rc = ensureScratch(ctx, 3, taps * sizeof(float)))) return rc;
+    if (tapIndex && (rc = ensureScratch(ctx, 4, taps * 4 * sizeof(int32_t)))) return rc;
+    DS_CUDA(ctx, cudaMemcpyAsync(ctx->scratch[0], positions, f3, cudaMemcpyHostToDevice, ctx->stream));
+    DS_CUDA(ctx, cudaMemcpyAsync(ctx->scratch[1], directions, f3, cudaMemcpyHostToDevice, ctx->stream));
+    DevScene sc;
+    fillDevScene(ctx, sc);
+    LevelTable lv;
+    memset(&lv, 0, sizeof(lv));
+    lv.count = (int)ctx->levels.size();
+    for (int l = 0; l < lv.count; l++) {
+        lv.data[l] = ctx->levels[l];
+        lv.nx[l] = ctx->lnx[l];
+        lv.ny[l] = ctx->lny[l];
+        lv.nz[l] = ctx->lnz[l];
+    }
+    /* DisneyDescriptor.cuh:81-88,109-110: per-layer scale, mip level and mip voxel size */
+    DescriptorLayers layers;
+    float scale = 0.5f / ctx->derived[6];
+    float mipmapLevel = -ds_log2f(ctx->derived[8]) - 1;
+    for (int l = 0; l < 10; l++) {
+        layers.scale[l] = scale;
+        layers.lod[l] = fmaxf(0.0f, mipmapLevel);
+        layers.mipVoxelSize[l] = ds_exp2f(mipmapLevel) * ctx->derived[7] / ctx->params.cloud_size_m;
+        scale *= 2;
+        mipmapLevel++;
+    }
+    DS_CUDA(ctx, launchDescriptors(sc, lv, layers, (const float*)ctx->scratch[0], (const float*)ctx->scratch[1], n,
+                                   outU8 ? (uint8_t*)ctx->scratch[2] : nullptr, outF32 ? (float*)ctx->scratch[3] : nullptr,
+                                   tapIndex ? (int32_t*)ctx->scratch[4] : nullptr, ctx->stream));
+    if (outU8) DS_CUDA(ctx, cudaMemcpyAsync(outU8, ctx->scratch[2], taps, cudaMemcpyDeviceToHost, ctx->stream));
+    if (outF32) DS_CUDA(ctx, cudaMemcpyAsync(outF32, ctx->scratch[3], taps * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    if (tapIndex) DS_CUDA(ctx, cudaMemcpyAsync(tapIndex, ctx->scratch[4], taps * 4 * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    DS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return DS_OK;
+}
+
+int ds_collect_descriptors(DsContext* ctx, const float* positions, const float* directions, uint32_t n, uint8_t* descriptors_out)
+{
+    DS_CHECK_CTX(ctx);
+    if (!descriptors_out && n) DS_FAIL(ctx, DS_ERR_INVALID, "NULL argument");
+    return collectDescriptors(ctx, positions, directions, n, descriptors_out, nullptr, nullptr);
+}
+
+int ds_collect_descriptors_float(DsContext* ctx, const float* positions, const float* directions, uint32_t n, float* out, int32_t* tap_index_out)
+{
+    DS_CHECK_CTX(ctx);
+    if (!out && n) DS_FAIL(ctx, DS_ERR_INVALID, "NULL argument");
+    return collectDescriptors(ctx, positions, directions, n, nullptr, out, tap_index_out);
+}
+
+void ds_radiance_settings_default(DsRadianceSettings* s)
+{
+    if (!s) return;
+    s->max_thread_count = 10 * 2048; /* RadianceCollector.cpp:17 */
+    s->launches_per_update = 100;    /* :88 */
+    s->max_updates = 0;
+    s->relative_ci = 2e-2f;          /* :113 */
+    s->absolute_ci = 1e-4f;          /* :114 */
+    s->zero_radiance_min_experiments = 100000; /* :117 */
+}
+
+/* CU/PointRadianceTask.h:23-36 */
+static float absoluteCI(const DsPointRadianceTask& t)
+{
+    const float N = (float)t.experiment_count;
+    const float sigma = sqrtf(t.running_variance / N);
+    return 1.96f * sigma / sqrtf(N);
+}
+static float relativeCI(const DsPointRadianceTask& t) { return absoluteCI(t) / (t.radiance + FLT_EPSILON); }
+
+/* CU/PointRadianceTask.h:54-68 */
+static void mergeTask(DsPointRadianceTask& a, const DsPointRadianceTask& other)
+{
+    const float newWeight = other.experiment_count * 1.0f / (a.experiment_count + other.experiment_count);
+    a.radiance += (other.radiance - a.radiance) * newWeight;
+    a.running_variance += other.running_variance;
+    a.experiment_count += other.experiment_count;
+}
+
+int ds_point_radiance_run(DsContext* ctx, const float* positions, const float* directions, uint32_t n, const DsRadianceSettings* settings,
+                          DsPointRadianceTask* tasks_out, uint8_t* converged_out, uint32_t* updates_out)
+{
+    DS_CHECK_CTX(ctx);
+    int rc = requireScene(ctx, true);
+    if (rc) return rc;
+    DsRadianceSettings cfg;
+    if (settings)
+        cfg = *settings;
+    else
+        ds_radiance_settings_default(&cfg);
+    if (n == 0) return DS_OK;
+    if (!positions || !directions || !tasks_out || !converged_out) DS_FAIL(ctx, DS_ERR_INVALID, "NULL argument");
+    if (cfg.max_thread_count < n) DS_FAIL(ctx, DS_ERR_INVALID, "taskRepeatCount would be 0 (RadianceCollector.cpp:179): max_thread_count < n");
+    if (cfg.launches_per_update == 0) DS_FAIL(ctx, DS_ERR_INVALID, "launches_per_update must be > 0");
+
+    /* RadianceCollector::init (:27-47) */
+    std::vector<DsPointRadianceTask> todo(n);
+    for (uint32_t i = 0; i < n; i++) {
+        DsPointRadianceTask t{};
+        t.id = (int32_t)i;
+        memcpy(t.position, positions + 3 * i, 12);
+        memcpy(t.direction, directions + 3 * i, 12);
+        todo[i] = t;
+        converged_out[i] = 0;
+        tasks_out[i] = t;
+    }
+    const size_t taskBytes = (size_t)cfg.max_thread_count * sizeof(DsPointRadianceTask);
+    const size_t xBytes = (size_t)cfg.max_thread_count * cfg.launches_per_update * sizeof(float);
+    if ((rc = ensureScratch(ctx, 5, taskBytes)) || (rc = ensureScratch(ctx, 6, xBytes))) return rc;
+    DsPointRadianceTask* dTasks = (DsPointRadianceTask*)ctx->scratch[5];
+    float* dX = (float*)ctx->scratch[6];
+    std::vector<DsPointRadianceTask> threads;
+    uint32_t frameId = 0, updates = 0;
+    while (!todo.empty() && (cfg.max_updates == 0 || updates < cfg.max_updates)) {
+        /* scheduleTasks (:176-192) */
+        const uint32_t taskRepeatCount = cfg.max_thread_count / (uint32_t)todo.size();
+        const uint32_t threadsCount = (uint32_t)todo.size() * taskRepeatCount;
+        threads.assign(threadsCount, DsPointRadianceTask{});
+        for (uint32_t i = 0; i < todo.size(); i++) {
+            threads[(size_t)i * taskRepeatCount] = todo[i];
+            for (uint32_t j = 1; j < taskRepeatCount; j++) {
+                DsPointRadianceTask f{};
+                f.id = todo[i].id;
+                memcpy(f.position, todo[i].position, 12);
+                memcpy(f.direction, todo[i].direction, 12);
+                threads[(size_t)i * taskRepeatCount + j] = f;
+            }
+        }
+        DS_CUDA(ctx, cudaMemcpyAsync(dTasks, threads.data(), (size_t)threadsCount * sizeof(DsPointRadianceTask), cudaMemcpyHostToDevice, ctx->stream));
+        /* update (:88-93): launches_per_update launches of estimateEmission, fused into one queue */
+        TraceJob job;
+        memset(&job, 0, sizeof(job));
+        job.kind = JOB_POINT;
+        job.mode = DS_MODE_SUN_MULTIPLE_SCATTER; /* Tasks.cpp:134 */
+        job.tasks = dTasks;
+        job.launches = cfg.launches_per_update;
+        job.frame0 = frameId;
+        job.xOut = dX;
+        job.total = (unsigned long long)threadsCount * cfg.launches_per_update;
+        rc = runTrace(ctx, job);
+        if (rc) return rc;
+        DS_CUDA(ctx, launchTaskWelford(dTasks, dX, threadsCount, cfg.launches_per_update, ctx->stream));
+        DS_CUDA(ctx, cudaMemcpyAsync(threads.data(), dTasks, (size_t)threadsCount * sizeof(DsPointRadianceTask), cudaMemcpyDeviceToHost, ctx->stream));
+        DS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        frameId += cfg.launches_per_update;
+        updates++;
+        /* merge repeats + convergence test (:100-130) */
+        std::vector<DsPointRadianceTask> next;
+        for (uint32_t i = 0; i < todo.size(); i++) {
+            DsPointRadianceTask& representative = threads[(size_t)i * taskRepeatCount];
+            for (uint32_t j = 1; j < taskRepeatCount; j++) mergeTask(representative, threads[(size_t)i * taskRepeatCount + j]);
+            bool isConverged = relativeCI(representative) < cfg.relative_ci || absoluteCI(representative) < cfg.absolute_ci;
+            if (representative.radiance < FLT_EPSILON) isConverged = representative.experiment_count > cfg.zero_radiance_min_experiments;
+            tasks_out[representative.id] = representative;
+            if (isConverged)
+                converged_out[representative.id] = 1;
+            else
+                next.push_back(representative);
+        }
+        todo.swap(next);
+    }
+    if (updates_out) *updates_out = updates;
+    return DS_OK;
+}
+
+} /* extern "C" */

@@ -1,0 +1,368 @@
+/*
+ * ds_kernels.cuh -- the estimator kernels, templated on the arithmetic flavour.
+ *
+ * k_trace is a persistent-threads kernel: every lane owns one light path at a time and, when the
+ * path ends, pulls the next work item (pixel sample, explicit ray, or point-radiance experiment)
+ * from a device-side queue with one warp-aggregated atomic ("path regeneration").  Per-path RNG
+ * streams depend only on the work item, never on the lane that runs it, so results do not depend
+ * on scheduling.  Inside a warp the loop alternates between a MARCH phase (one ray-march step per
+ * iteration for lanes in free flight) and an EVENT phase (next-event estimate + Mie direction
+ * sampling for lanes that collided); the warp leaves the march phase by vote, which keeps both
+ * phases populated instead of serialising the two nested data-dependent loops of the reference
+ * (CU/cloudRadianceMaterials.cu:28-62 around CU/cloud.cuh:87-104).
+ *
+ * Shared memory per block: chopped-Mie phase table (16 KiB), chopped-Mie CDF (16 KiB) and the
+ * empty-space occupancy bit mask (<= 32 KiB).
+ */
+#pragma once
+
+#include "ds_kernels.h"
+
+namespace dsk {
+
+enum LaneState { ST_IDLE = 0, ST_MARCH = 1, ST_EVENT = 2, ST_DONE = 3 };
+
+struct PathState {
+    V3 p;    /* marching position / scatter position (box-local) */
+    V3 dir;
+    V3 rad;
+    float T; /* transmittance accumulated in the current free flight */
+    float xi;
+    uint32_t seed;
+    int depth;
+    unsigned long long out; /* output slot of the work item */
+};
+
+/* start of an iteration of the reference's `while (isInBox(pos))` loop (cloudRadianceMaterials.cu:28-35) */
+__device__ __forceinline__ int loopTop(const DevScene& sc, PathState& s)
+{
+    if (!isInBox(sc, s.p)) return ST_DONE;
+    s.depth++;
+    if (s.depth == MAX_DEPTH) return ST_DONE;
+    s.xi = rnd(s.seed); /* getNextScatteringEvent(seed, ...), cloud.cuh:120 */
+    s.T = 1.0f;
+    return ST_MARCH;
+}
+
+/* Decode work item `idx`, generate its ray and intersect the cloud box.  Returns the lane state. */
+template <bool FAST>
+__device__ __forceinline__ int beginItem(const DevScene& sc, const TraceJob& job, const float* sCdf, unsigned long long idx, PathState& s,
+                                         bool& valid)
+{
+    V3 o, d;
+    uint32_t val0, stream;
+    valid = true;
+    if (job.kind == JOB_RENDER) {
+        /* CU/pathTracingCamera.cu:12-21 + CU/cameraCommon.cuh:19-29 */
+        const unsigned long long sub = idx / job.itemsPerSubframe;
+        const uint32_t rem = (uint32_t)(idx - sub * job.itemsPerSubframe);
+        const uint32_t tile = rem >> 5, within = rem & 31u;
+        const uint32_t px = (tile % (uint32_t)job.tilesX) * 8u + (within & 7u);
+        const uint32_t py = (tile / (uint32_t)job.tilesX) * 4u + (within >> 3);
+        if (px >= (uint32_t)job.width || py >= (uint32_t)job.height) {
+            valid = false;
+            return ST_IDLE;
+        }
+        const float dx = (float)px / (float)job.width * 2.f - 1.f;
+        const float dy = (float)py / (float)job.height * 2.f - 1.f;
+        const V3 U = mk(job.U[0], job.U[1], job.U[2]), V = mk(job.V[0], job.V[1], job.V[2]), W = mk(job.W[0], job.W[1], job.W[2]);
+        o = mk(job.eye[0], job.eye[1], job.eye[2]);
+        d = normalize<FAST>(dx * U + dy * V + W);
+        val0 = px * 4096u + py; /* cloudRadianceMaterials.cu:21 */
+        stream = job.firstSubframe + (uint32_t)sub;
+        s.out = sub * (unsigned long long)job.width * job.height + (unsigned long long)py * job.width + px;
+    } else if (job.kind == JOB_POINT) {
+        /* CU/pointEmissionCamera.cu:20-33: thread t, launch l -> tea<4>(t*4096 + 0, frameId) */
+        const uint32_t t = (uint32_t)(idx / job.launches);
+        const uint32_t l = (uint32_t)(idx - (unsigned long long)t * job.launches);
+        const DsPointRadianceTask* task = job.tasks + t;
+        o = mk(task->position[0], task->position[1], task->position[2]);
+        d = mk(task->direction[0], task->direction[1], task->direction[2]);
+        val0 = t * 4096u;
+        stream = job.frame0 + l + 1u;
+        s.out = idx;
+    } else {
+        o = mk(job.origins[3 * idx], job.origins[3 * idx + 1], job.origins[3 * idx + 2]);
+        d = mk(job.dirs[3 * idx], job.dirs[3 * idx + 1], job.dirs[3 * idx + 2]);
+        val0 = job.seedVal0[idx];
+        stream = job.stream[idx];
+        s.out = idx;
+    }
+    s.rad = mk(0.f, 0.f, 0.f);
+    const float tHit = intersectBox(sc, o, d);
+    if (tHit < 0.0f) return ST_DONE; /* miss program is a no-op (progressive.cu:44-46) */
+    /* closest hit prologue, cloudRadianceMaterials.cu:11-21 */
+    V3 hit = o + tHit * d;
+    hit = hit + 0.5f * sc.bbox;
+    s.p = hit;
+    s.dir = normalize<FAST>(d);
+    s.seed = tea4(val0, stream);
+    s.depth = 0;
+    if (job.mode == DS_MODE_SUN_MULTIPLE_SCATTER) {
+        s.dir = getNewDirection<FAST>(sCdf, s.seed, s.dir); /* cloudRadianceMaterials.cu:86 */
+    }
+    return loopTop(sc, s);
+}
+
+__device__ __forceinline__ void writeResult(const TraceJob& job, const PathState& s, uint32_t& nonfinite)
+{
+    const float sum = s.rad.x + s.rad.y + s.rad.z;
+    if (!(fabsf(sum) <= 3.0e38f)) nonfinite++;
+    if (job.kind == JOB_RENDER) {
+        job.staging[s.out] = make_float4(s.rad.x, s.rad.y, s.rad.z, 1.0f); /* pathTracingCamera.cu:20 */
+    } else if (job.kind == JOB_POINT) {
+        job.xOut[s.out] = s.rad.x; /* pointEmissionCamera.cu:32 */
+    } else {
+        job.radianceOut[3 * s.out] = s.rad.x;
+        job.radianceOut[3 * s.out + 1] = s.rad.y;
+        job.radianceOut[3 * s.out + 2] = s.rad.z;
+    }
+}
+
+template <bool FAST, bool SKIP>
+__global__ void __launch_bounds__(512, 2) k_trace(const DevScene sc, const TraceJob job)
+{
+    extern __shared__ __align__(16) unsigned char smemRaw[];
+    float* sChopped = reinterpret_cast<float*>(smemRaw);
+    float* sCdf = sChopped + MIE_N;
+    uint32_t* sOcc = reinterpret_cast<uint32_t*>(sCdf + MIE_N);
+    for (int i = threadIdx.x; i < MIE_N; i += blockDim.x) {
+        sChopped[i] = sc.chopped[i];
+        sCdf[i] = sc.cdf[i];
+    }
+    if (SKIP) {
+        for (int i = threadIdx.x; i < sc.occWords; i += blockDim.x) sOcc[i] = sc.occ[i];
+    }
+    __syncthreads();
+
+    const unsigned FULL = 0xffffffffu;
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned laneLt = (1u << lane) - 1u;
+
+    PathState s;
+    s.p = s.dir = s.rad = mk(0.f, 0.f, 0.f);
+    s.T = 1.f;
+    s.xi = 0.f;
+    s.seed = 0;
+    s.depth = 0;
+    s.out = 0;
+    int st = ST_IDLE;
+    bool exhausted = false;
+    uint32_t nPaths = 0, nEvents = 0, nSteps = 0, nTaps = 0, nNonfinite = 0;
+
+    for (;;) {
+        /* ---- finish + regenerate ---- */
+        if (st == ST_DONE) {
+            writeResult(job, s, nNonfinite);
+            st = ST_IDLE;
+        }
+        const unsigned need = __ballot_sync(FULL, st == ST_IDLE && !exhausted);
+        if (need) {
+            unsigned long long base = 0;
+            const int leader = __ffs(need) - 1;
+            if ((int)lane == leader) base = atomicAdd(job.queue, (unsigned long long)__popc(need));
+            base = __shfl_sync(FULL, base, leader);
+            if (st == ST_IDLE && !exhausted) {
+                const unsigned long long idx = base + __popc(need & laneLt);
+                if (idx >= job.total) {
+                    exhausted = true;
+                } else {
+                    bool valid;
+                    st = beginItem<FAST>(sc, job, sCdf, idx, s, valid);
+                    if (valid) nPaths++;
+                }
+            }
+        }
+        const unsigned alive = __ballot_sync(FULL, st != ST_IDLE);
+        if (alive == 0u) {
+            if (__all_sync(FULL, exhausted)) break;
+            continue;
+        }
+        const int nAlive = __popc(alive);
+
+        /* ---- march phase: CU/cloud.cuh:87-104, one step per iteration ---- */
+#pragma unroll 1
+        for (int it = 0; it < job.marchMaxIters; ++it) {
+            if (st == ST_MARCH) {
+                if (!isInBox(sc, s.p)) {
+                    st = ST_DONE; /* left the box without colliding */
+                } else {
+                    s.p = s.p + s.dir * sc.step;
+                    nSteps++;
+                    if (!(SKIP && tapIsEmpty(sc, sOcc, s.p))) {
+                        nTaps++;
+                        const float density = sampleCloud<FAST>(sc, s.p) * sc.mult;
+                        const float extinction = density * sc.step;
+                        s.T *= expNeg<FAST>(-extinction);
+                        if (s.xi > s.T) {
+                            const float lg = logPos<FAST>(FAST ? __fdividef(s.xi, s.T) : s.xi / s.T);
+                            const float inv = FAST ? __fdividef(1.0f, density) : 1.0f / density;
+                            s.p = s.p - (s.dir * lg) * inv; /* cloud.cuh:99 */
+                            st = ST_EVENT;
+                        }
+                    }
+                }
+            }
+            const int nMarch = __popc(__ballot_sync(FULL, st == ST_MARCH));
+            if (nMarch * 4 <= nAlive * job.marchKeepQuarters) break;
+        }
+
+        /* ---- event phase: cloudRadianceMaterials.cu:49-61 ---- */
+        if (st == ST_EVENT) {
+            if (!isInBox(sc, s.p)) {
+                st = ST_DONE;
+            } else {
+                /* getInScattering, cloud.cuh:146-158 */
+                const float cosLightAngle = dot(-sc.light, s.dir);
+                const bool choppedPhase = (job.mode == DS_MODE_SUN_AND_SKY_ALL_SCATTER) ? (s.depth != 1) : (job.mode == DS_MODE_SUN_MULTIPLE_SCATTER);
+                const float u = (cosLightAngle + 1) / 2;
+                const float phase = choppedPhase ? tex1dSoft(sChopped, u) : tex1dSoft(sc.mie, u);
+                const float tsun = sampleInScatter<FAST>(sc, s.p);
+                const V3 li = sc.lightColor * sc.lightIntensity * tsun * phase * SUN_TO_SPHERE;
+                s.rad = s.rad + li;
+                nEvents++;
+                if (job.mode == DS_MODE_SUN_SINGLE_SCATTER) {
+                    st = ST_DONE;
+                } else {
+                    s.dir = getNewDirection<FAST>(sCdf, s.seed, s.dir);
+                    st = loopTop(sc, s);
+                }
+            }
+        }
+    }
+
+    /* fold the per-lane counters */
+    unsigned long long c[5] = {nPaths, nEvents, nSteps, nTaps, nNonfinite};
+#pragma unroll
+    for (int k = 0; k < 5; k++) {
+        unsigned long long v = c[k];
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(FULL, v, o);
+        if (lane == 0 && v) atomicAdd(job.stats + k, v);
+    }
+}
+
+template <bool FAST>
+cudaError_t KernelSet<FAST>::trace(const DevScene& sc, const TraceJob& job, const LaunchConfig& cfg, cudaStream_t st)
+{
+    const size_t smem = (size_t)(2 * MIE_N + (cfg.skipEmpty ? sc.occWords : 0)) * 4;
+    const int threads = cfg.blockThreads;
+    unsigned long long wantBlocks = (job.total + threads - 1) / threads;
+    const unsigned long long maxBlocks = (unsigned long long)cfg.smCount * cfg.blocksPerSm;
+    const int blocks = (int)(wantBlocks < maxBlocks ? (wantBlocks ? wantBlocks : 1) : maxBlocks);
+    cudaError_t e;
+    if (cfg.skipEmpty) {
+        e = cudaFuncSetAttribute(k_trace<FAST, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        k_trace<FAST, true><<<blocks, threads, smem, st>>>(sc, job);
+    } else {
+        e = cudaFuncSetAttribute(k_trace<FAST, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        k_trace<FAST, false><<<blocks, threads, smem, st>>>(sc, job);
+    }
+    return cudaGetLastError();
+}
+
+/* ---- CU/inScatter.cu:40-66: one thread per voxel, x fastest ---- */
+template <bool FAST, bool SKIP>
+__global__ void __launch_bounds__(256) k_bake(const DevScene sc, uint8_t* __restrict__ out)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y;
+    const int z = blockIdx.z;
+    if (x >= sc.nx) return;
+    const int maxN = max(max(sc.nx, sc.ny), sc.nz);
+    const float minScale = fminf(fminf(sc.texScale.x, sc.texScale.y), sc.texScale.z);
+    const float invMinScale = 1.0f / minScale;
+    V3 pos = mk(((float)x / (float)maxN) * invMinScale, ((float)y / (float)maxN) * invMinScale, ((float)z / (float)maxN) * invMinScale);
+    const V3 stepToLight = (-normalize<FAST>(sc.light)) * sc.step;
+    const int stepCount = (int)(1 / sc.step);
+    float transmittance = 1;
+    for (int i = 0; i < stepCount; i++) {
+        if (!(SKIP && tapIsEmpty(sc, sc.occ, pos))) {
+            const float density = sampleCloud<FAST>(sc, pos) * sc.mult;
+            const float extinction = density * sc.step;
+            transmittance *= expNeg<FAST>(-extinction);
+        }
+        pos = pos + stepToLight;
+        if (transmittance * 255.f < 1.f) break;
+    }
+    out[((size_t)z * sc.ny + y) * sc.nx + x] = (uint8_t)(transmittance * 255.f);
+}
+
+template <bool FAST>
+cudaError_t KernelSet<FAST>::bake(const DevScene& sc, uint8_t* out, int skipEmpty, cudaStream_t st)
+{
+    dim3 block(256, 1, 1);
+    dim3 grid((sc.nx + 255) / 256, sc.ny, sc.nz);
+    if (skipEmpty)
+        k_bake<FAST, true><<<grid, block, 0, st>>>(sc, out);
+    else
+        k_bake<FAST, false><<<grid, block, 0, st>>>(sc, out);
+    return cudaGetLastError();
+}
+
+/* ---- CU/pointGeneratorCamera.cu:20-42 + CU/cloudFirstScatterMaterial.cu:8-28 ---- */
+template <bool FAST>
+__global__ void __launch_bounds__(128) k_generate_points(const DevScene sc, uint32_t firstIndex, uint32_t n, uint32_t stream, float* pos,
+                                                         float* dir, unsigned long long* stats)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t launchID = firstIndex + i;
+    uint32_t seed = tea4(launchID, stream);
+    uint32_t attempt = 0;
+    unsigned long long steps = 0;
+    for (;;) {
+        attempt++;
+        const V3 discNormal = uniformOnSphere<FAST>(seed);
+        const float discRadius = sqrtf(3.0f) / 2;
+        const V3 position = uniformOnDisc<FAST>(seed, discNormal) * discRadius;
+        const V3 origin = position + discNormal * 2;
+        const V3 direction = -discNormal;
+        const float tHit = intersectBox(sc, origin, direction);
+        if (tHit < 0.0f) continue;
+        V3 p = origin + tHit * direction;
+        p = p + 0.5f * sc.bbox;
+        const V3 d = normalize<FAST>(direction);
+        uint32_t hitSeed = tea4(launchID * 4096u, attempt);
+        const float xi = rnd(hitSeed);
+        float T = 1.0f;
+        bool scattered = false;
+        while (isInBox(sc, p)) {
+            p = p + d * sc.step;
+            steps++;
+            const float density = sampleCloud<FAST>(sc, p) * sc.mult;
+            const float extinction = density * sc.step;
+            T *= expNeg<FAST>(-extinction);
+            if (xi > T) {
+                const float lg = logPos<FAST>(xi / T);
+                const float inv = 1.0f / density;
+                p = p - (d * lg) * inv;
+                scattered = true;
+                break;
+            }
+        }
+        if (scattered && isInBox(sc, p)) {
+            const V3 w = p - 0.5f * sc.bbox;
+            pos[3 * i] = w.x;
+            pos[3 * i + 1] = w.y;
+            pos[3 * i + 2] = w.z;
+            dir[3 * i] = -discNormal.x;
+            dir[3 * i + 1] = -discNormal.y;
+            dir[3 * i + 2] = -discNormal.z;
+            break;
+        }
+    }
+    if (stats) atomicAdd(stats + CNT_STEPS, steps);
+}
+
+template <bool FAST>
+cudaError_t KernelSet<FAST>::generatePoints(const DevScene& sc, uint32_t firstIndex, uint32_t n, uint32_t stream, float* pos, float* dir,
+                                            unsigned long long* stats, cudaStream_t st)
+{
+    if (n == 0) return cudaSuccess;
+    k_generate_points<FAST><<<(n + 127) / 128, 128, 0, st>>>(sc, firstIndex, n, stream, pos, dir, stats);
+    return cudaGetLastError();
+}
+
+} // namespace dsk

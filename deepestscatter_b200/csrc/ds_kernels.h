@@ -1,0 +1,92 @@
+/*
+ * ds_kernels.h -- host-callable launchers of the sm_100a kernels (internal to the library).
+ */
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/ds_abi.h"
+#include "ds_device.cuh"
+
+namespace dsk {
+
+enum JobKind { JOB_RENDER = 0, JOB_PATHS = 1, JOB_POINT = 2 };
+
+/* index of the 64-bit work counters on the device */
+enum { CNT_PATHS = 0, CNT_EVENTS = 1, CNT_STEPS = 2, CNT_TAPS = 3, CNT_NONFINITE = 4, CNT_COUNT = 8 };
+
+/* One launch of the path-tracing kernel: `total` work items pulled from a device-side queue. */
+struct TraceJob {
+    int kind;
+    int mode;
+    unsigned long long total;
+    unsigned long long* queue;  /* work counter, zeroed before launch */
+    unsigned long long* stats;  /* CNT_COUNT counters */
+    int marchKeepQuarters;      /* leave the march phase when marching*4 <= alive*q */
+    int marchMaxIters;
+    /* JOB_RENDER: item = (subframe, 8x4 pixel tile, pixel in tile) */
+    float eye[3], U[3], V[3], W[3];
+    int width, height, tilesX;
+    uint32_t firstSubframe;
+    unsigned long long itemsPerSubframe;
+    float4* staging; /* [n][H][W] */
+    /* JOB_PATHS */
+    const float* origins;
+    const float* dirs;
+    const uint32_t* seedVal0;
+    const uint32_t* stream;
+    float* radianceOut;
+    /* JOB_POINT: item = (thread t, launch l) */
+    const DsPointRadianceTask* tasks;
+    uint32_t launches;
+    uint32_t frame0;
+    float* xOut; /* [threads][launches] */
+};
+
+struct LevelTable {
+    const uint8_t* data[MAX_LEVELS];
+    int nx[MAX_LEVELS], ny[MAX_LEVELS], nz[MAX_LEVELS];
+    int count;
+};
+
+struct DescriptorLayers {
+    float scale[10];
+    float lod[10];        /* max(0, mipmapLevel) */
+    float mipVoxelSize[10];
+};
+
+struct LaunchConfig {
+    int blockThreads;
+    int blocksPerSm;
+    int smCount;
+    int skipEmpty;
+};
+
+template <bool FAST>
+struct KernelSet {
+    static cudaError_t trace(const DevScene& sc, const TraceJob& job, const LaunchConfig& cfg, cudaStream_t st);
+    static cudaError_t bake(const DevScene& sc, uint8_t* out, int skipEmpty, cudaStream_t st);
+    static cudaError_t generatePoints(const DevScene& sc, uint32_t firstIndex, uint32_t n, uint32_t stream, float* pos, float* dir,
+                                      unsigned long long* stats, cudaStream_t st);
+};
+
+/* exact-arithmetic helpers (compiled in the -fmad=false translation unit only) */
+cudaError_t launchSynth(uint8_t* out, int n, int kind, uint32_t seed, cudaStream_t st);
+cudaError_t launchQuantize(const float* in, size_t count, double maxDensity, uint8_t* out, cudaStream_t st);
+cudaError_t launchMip(const uint8_t* prev, int pnx, int pny, int pnz, uint8_t* cur, int cnx, int cny, int cnz, cudaStream_t st);
+cudaError_t launchOccupancy(const uint8_t* density, int nx, int ny, int nz, int shift, int ocx, int ocy, int ocz, uint32_t* bits,
+                            cudaStream_t st);
+cudaError_t launchUpdateFrame(const float4* staging, float4* progressive, float4* variance, size_t pixels, uint32_t firstSubframe,
+                              uint32_t n, cudaStream_t st);
+cudaError_t launchTonemap(const float4* progressive, int w, int h, float exposure, float* columns, float* average, uchar4* screen,
+                          cudaStream_t st);
+cudaError_t launchUnconverged(const float4* progressive, const float4* variance, size_t pixels, uint32_t subframeId, uint32_t* count,
+                              cudaStream_t st);
+cudaError_t launchExportMoments(const float4* progressive, const float4* variance, size_t pixels, uint32_t n, double* out, cudaStream_t st);
+cudaError_t launchImportMoments(const double* in, size_t pixels, uint32_t nTotal, float4* progressive, float4* variance, cudaStream_t st);
+cudaError_t launchDescriptors(const DevScene& sc, const LevelTable& lv, const DescriptorLayers& layers, const float* pos, const float* dir,
+                              uint32_t n, uint8_t* outU8, float* outF32, int32_t* tapIndex, cudaStream_t st);
+cudaError_t launchTaskWelford(DsPointRadianceTask* tasks, const float* x, uint32_t nThreads, uint32_t launches, cudaStream_t st);
+
+} // namespace dsk

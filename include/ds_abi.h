@@ -1,0 +1,232 @@
+/*
+ * ds_abi.h -- C ABI of libdeepestscatter_b200.so: the drop-in boundary for the radiance
+ * estimation hot path of marsermd/DeepestScatter's DataGen subsystem on NVIDIA B200.
+ *
+ * Every entry point replaces a piece of the reference's host<->OptiX interface; the
+ * reference interface it stands in for is cited as file:line with
+ *   DG/ = DeepestScatter_DataGen/DeepestScatter_DataGen/src/      CU/ = DG/CUDA/
+ *
+ * Conventions
+ *   - plain C types only; all functions return 0 (DS_OK) or a negative DS_ERR_* code and
+ *     record a message readable with ds_last_error().  No exceptions cross the boundary
+ *     (the reference throws optix::Exception / sutil::APIError, DG/main.cpp:73-76).
+ *   - a DsContext owns one CUDA device, one stream and all device memory (the analogue of
+ *     the per-task optix::Context, DG/ExecutionLoop/GuiExecutionLoop.cpp:93-97).  It is
+ *     thread-compatible: one host thread at a time.  One context per GPU.
+ *   - host pointers are caller-owned; `_device` variants take device pointers.
+ *   - images are float4 / uchar4 [H][W], row 0 at the bottom (CU/cameraCommon.cuh:22);
+ *     volumes are u8 [Nz][Ny][Nx], x fastest (DG/Util/Resources.cpp:127-141).
+ *   - there is no CPU fallback: every call fails with DS_ERR_CUDA when no sm_100 device
+ *     is usable.
+ */
+#ifndef DS_ABI_H
+#define DS_ABI_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DS_OK 0
+#define DS_ERR_INVALID (-1) /* bad argument / call order */
+#define DS_ERR_CUDA (-2)    /* CUDA runtime error (message in ds_last_error) */
+#define DS_ERR_STATE (-3)   /* required state missing (no volume, no frame, ...) */
+#define DS_ERR_IO (-4)      /* file system error (record writer) */
+
+typedef struct DsContext DsContext;
+
+/* Cloud::Rendering::Mode (DG/Scene/SceneDescription.h:41-46) -> closest-hit program
+ * (DG/Scene/CloudMaterial.cpp:51-64) */
+typedef enum DsMode {
+    DS_MODE_SUN_AND_SKY_ALL_SCATTER = 0, /* totalRadiance,              CU/cloudRadianceMaterials.cu:9  */
+    DS_MODE_SUN_MULTIPLE_SCATTER = 1,    /* multipleScatterSunRadiance, CU/cloudRadianceMaterials.cu:72 */
+    DS_MODE_SUN_SINGLE_SCATTER = 2       /* singleScatterSunRadiance,   CU/cloudRadianceMaterials.cu:120 */
+} DsMode;
+
+/* Arithmetic flavour of the estimator kernels.
+ *  EXACT: software fp32 trilinear + include/ds_detmath.h transcendental kernels, compiled
+ *         -fmad=false; bit-identical to the host oracle (tests assert equality).
+ *  FAST:  hardware 3-D texture filtering + MUFU intrinsics, i.e. what the reference itself
+ *         runs (--use_fast_math, vcxproj:320; rtTex3D, CU/cloud.cuh:61); checked against
+ *         the oracle statistically (3 sigma per pixel, <0.5 % relative RMSE). */
+typedef enum DsPrecision { DS_PRECISION_EXACT = 0, DS_PRECISION_FAST = 1 } DsPrecision;
+
+/* The OptiX context variables of the scene (SURVEY.md 8b "parameter surface"). */
+typedef struct DsSceneParams {
+    float cloud_size_m;         /* Cloud::Model::size, SceneDescription.h:76; "cloudSizeInMeters" VDBCloud.cpp:110 */
+    float mean_free_path_m;     /* SceneDescription.h:80 (10 m) -> densityMultiplier = size / mfp, VDBCloud.cpp:109 */
+    float sample_step;          /* "sampleStep", installers.cpp:86 (1/512) */
+    float light_direction[3];   /* "lightDirection", Sun.cpp:15; normalised like DirectionalLight's ctor */
+    float light_color[3];       /* "lightColor", Sun.cpp:16 */
+    float light_intensity;      /* "lightIntensity", Sun.cpp:17 (1e6, installers.cpp:100) */
+    float minimal_ray_distance; /* "minimalRayDistance", CloudMaterial.cpp:23 (1e-6) */
+} DsSceneParams;
+
+/* "eye", "U", "V", "W" (DG/Scene/Cameras/Camera.cpp:129-132) */
+typedef struct DsCamera {
+    float eye[3];
+    float U[3];
+    float V[3];
+    float W[3];
+} DsCamera;
+
+/* Gpu::PointRadianceTask (CU/PointRadianceTask.h:70-77), 40 bytes, same field order */
+typedef struct DsPointRadianceTask {
+    int32_t id;
+    uint32_t experiment_count;
+    float radiance;
+    float running_variance;
+    float position[3];
+    float direction[3];
+} DsPointRadianceTask;
+
+/* Work counters accumulated by the estimator kernels since the last reset. */
+typedef struct DsCounters {
+    uint64_t paths;        /* primary samples started (hit or miss) */
+    uint64_t events;       /* scatter events with a next-event estimate (getInScattering calls) */
+    uint64_t steps;        /* ray-march steps of the reference algorithm (CU/cloud.cuh:87-104 iterations) */
+    uint64_t density_taps; /* density fetches actually issued (<= steps when empty space is skipped) */
+    uint64_t nonfinite;    /* samples that were NaN/Inf (the reference paints an error colour, progressive.cu:36) */
+} DsCounters;
+
+/* RadianceCollector constants (DG/Scene/RadianceCollector.cpp:17,88,112-118) */
+typedef struct DsRadianceSettings {
+    uint32_t max_thread_count;    /* MAX_THREAD_COUNT = 10 * 2048 */
+    uint32_t launches_per_update; /* 100 */
+    uint32_t max_updates;         /* safety cap on update() calls; 0 = unlimited */
+    float relative_ci;            /* 2e-2 */
+    float absolute_ci;            /* 1e-4 */
+    uint32_t zero_radiance_min_experiments; /* 100000 */
+} DsRadianceSettings;
+
+/* ---------------------------------------------------------------- context */
+
+/* optix::Context::create (DG/installers.cpp:111) */
+int ds_context_create(int device, DsContext** out);
+/* context->destroy (GuiExecutionLoop.cpp:93-97) */
+int ds_context_destroy(DsContext* ctx);
+/* message of the last failing call on this context (ctx may be NULL for create failures) */
+const char* ds_last_error(DsContext* ctx);
+/* run all work of this context on an externally owned cudaStream_t (e.g. torch's current stream) */
+int ds_context_set_stream(DsContext* ctx, void* cuda_stream);
+/* block until all work queued by this context is complete */
+int ds_sync(DsContext* ctx);
+/* named integer options: "precision" (DsPrecision), "variant", "block_threads", "blocks_per_sm",
+ * "skip_empty", "march_keep_quarters", "march_max_iters", "staging_subframes" -- tuning knobs of the
+ * estimator kernels; "stream_offset" -- added to the subframe id to form the RNG stream id; "profile_events"  */
+int ds_set_option(DsContext* ctx, const char* name, int value);
+int ds_get_option(DsContext* ctx, const char* name, int* value);
+int ds_get_counters(DsContext* ctx, DsCounters* out);
+int ds_reset_counters(DsContext* ctx);
+/* launch accounting since the last ds_reset_counters: kernels launched by the estimator entry points; with
+ * option "profile_events" = 1 also the summed CUDA-event duration (ms) of the path-tracing kernel launches */
+int ds_get_launch_stats(DsContext* ctx, uint64_t* kernel_launches, uint64_t* trace_launches_timed, double* trace_ms_total);
+/* library / device description as a JSON string owned by the context */
+const char* ds_describe(DsContext* ctx);
+
+/* ---------------------------------------------------------------- volume (cloud importer back end) */
+
+/* Resources::loadVolumeBuffer after the VDB parse (Resources.cpp:103-148): dense u8 level 0,
+ * optional box-filter mip chain generateMipmaps (Resources.cpp:169-209) built on the device. */
+int ds_volume_upload(DsContext* ctx, const uint8_t* level0, int nx, int ny, int nz, int build_mips);
+/* Resources.cpp:127-141: value / max_density * 255 truncated to u8, then as ds_volume_upload */
+int ds_volume_upload_float(DsContext* ctx, const float* dense, int nx, int ny, int nz, double max_density, int build_mips);
+/* synthetic procedural grid (include/ds_synth.h) generated on the device: n^3, kind 0/1/2 */
+int ds_volume_synth(DsContext* ctx, int n, int kind, uint32_t seed, int build_mips);
+int ds_volume_level_count(DsContext* ctx, int* count);
+int ds_volume_level_dims(DsContext* ctx, int level, int dims[3]);
+int ds_volume_download_level(DsContext* ctx, int level, uint8_t* out);
+
+/* ---------------------------------------------------------------- scene */
+
+void ds_scene_params_default(DsSceneParams* p);
+/* Sun::init (Sun.cpp:13-18) + VDBCloud::setupVariables (VDBCloud.cpp:88-117) + CloudMaterial (CloudMaterial.cpp:14,23) */
+int ds_scene_set(DsContext* ctx, const DsSceneParams* p);
+/* derived variables as the reference sets them: out[0..2] bboxSize, [3..5] textureScale, [6] densityMultiplier,
+ * [7] voxelSizeInMeters, [8] voxelSizeInTermsOfFreePath, [9..11] normalised lightDirection */
+int ds_scene_get_derived(DsContext* ctx, float out[12]);
+/* VDBCloud::InitInScatter (VDBCloud.cpp:57-86) launching CU/inScatter.cu:40-66 */
+int ds_bake_sun_transmittance(DsContext* ctx);
+int ds_inscatter_download(DsContext* ctx, uint8_t* out);
+int ds_inscatter_upload(DsContext* ctx, const uint8_t* in);
+
+/* sutil::calculateCameraVariables with fov_is_vertical = false (DG/Util/sutil.cpp:501-524), host only */
+void ds_camera_look_at(const float eye[3], const float lookat[3], const float up[3], float hfov_deg, float aspect, DsCamera* out);
+/* Camera::init defaults: eye (2.5,-0.4,0), lookat 0, up +y, hfov 30 (Camera.cpp:37-39,102) */
+void ds_camera_default(int width, int height, DsCamera* out);
+
+/* ---------------------------------------------------------------- progressive renderer */
+
+/* Camera::init buffers frameResult/progressive/variance/screen (Camera.cpp:45-48) */
+int ds_frame_create(DsContext* ctx, int width, int height);
+/* Camera::reset -> clearScreen (Camera.cpp:77-86, CU/progressive.cu:29-34) */
+int ds_frame_clear(DsContext* ctx);
+/* ARenderer::render (DG/Scene/Cameras/ARenderer.h:15; PathTracingRenderer.cpp:21-31): one new sample per
+ * pixel for `subframe_id`; frame_result_out (float4 [H][W], may be NULL) receives frameResultBuffer. */
+int ds_render_frame_result(DsContext* ctx, const DsCamera* cam, DsMode mode, uint32_t subframe_id, float* frame_result_out);
+/* Camera::render loop body (Camera.cpp:189-199) for subframes first..first+n-1: render + updateFrameResult
+ * (CU/progressive.cu:17-27) into the device-resident progressive / variance buffers. */
+int ds_render_subframes(DsContext* ctx, const DsCamera* cam, DsMode mode, uint32_t first_subframe, uint32_t n);
+/* as ds_render_subframes, but with HOST accumulation buffers: uploads progressive/variance (float4 [H][W]),
+ * renders, downloads them again -- the plugin-boundary call with all copies inside. */
+int ds_render_subframes_host(DsContext* ctx, const DsCamera* cam, DsMode mode, uint32_t first_subframe, uint32_t n,
+                             float* progressive_inout, float* variance_inout);
+int ds_frame_download(DsContext* ctx, float* progressive_out, float* variance_out);
+int ds_frame_upload(DsContext* ctx, const float* progressive, const float* variance);
+/* raw device pointers of the float4 buffers (for torch.distributed / NCCL plumbing) */
+int ds_frame_device_ptrs(DsContext* ctx, void** progressive, void** variance);
+/* reinhard firstPass/secondPass/applyReinhard (CU/reinhard.cu:26-83; Camera.cpp:202-210): uchar4 [H][W] */
+int ds_tonemap(DsContext* ctx, float exposure, uint8_t* screen_out, float* average_luminance_out);
+/* Camera::isConverged (Camera.cpp:232-268): number of pixels failing the 95 % CI test at `subframe_id` */
+int ds_frame_unconverged(DsContext* ctx, uint32_t subframe_id, uint32_t* unconverged_out);
+/* Multi-GPU merge support.  Exports per pixel 8 doubles {n*mean_rgba, M2_rgba + n*mean_rgba^2} (device
+ * pointer, 8*W*H doubles) for `n` subframes; sums over ranks can then be re-imported with the total n. */
+int ds_frame_export_moments_device(DsContext* ctx, uint32_t n, double* moments_device);
+int ds_frame_import_moments_device(DsContext* ctx, uint32_t n_total, const double* moments_device);
+
+/* ---------------------------------------------------------------- generic path tracing (tests, tools) */
+
+/* rtTrace of one radiance ray per (origin, direction) in world space; seed = tea<4>(seed_val0[i], stream[i])
+ * (CU/cloudRadianceMaterials.cu:21 with clock() replaced by stream).  radiance_out: float3 per path. */
+int ds_trace_paths(DsContext* ctx, DsMode mode, uint32_t n, const float* origins, const float* directions,
+                   const uint32_t* seed_val0, const uint32_t* stream, float* radiance_out);
+
+/* ---------------------------------------------------------------- dataset generation */
+
+/* ScatterSampleCollector::collect launch (ScatterSampleCollector.cpp:35-40; CU/pointGeneratorCamera.cu:20-42,
+ * CU/cloudFirstScatterMaterial.cu:8-28) for launch ids first_index..first_index+n-1 */
+int ds_generate_points(DsContext* ctx, uint32_t first_index, uint32_t n, uint32_t stream, float* positions_out, float* directions_out);
+/* DisneyDescriptorCollector::collect (DisneyDescriptorCollector.cpp:61-67; CU/disneyDescriptorCollector.cu:22-29,
+ * CU/DisneyDescriptor.cuh:72-112): n descriptors of 10*225 u8 */
+int ds_collect_descriptors(DsContext* ctx, const float* positions, const float* directions, uint32_t n, uint8_t* descriptors_out);
+/* float variant (TElement = float, the density members of DisneyNetworkInput) and optional floor-corner voxel
+ * addresses {x, y, z, level} per tap for index parity */
+int ds_collect_descriptors_float(DsContext* ctx, const float* positions, const float* directions, uint32_t n, float* out,
+                                 int32_t* tap_index_out);
+void ds_radiance_settings_default(DsRadianceSettings* s);
+/* RadianceCollector::init/update loop until all samples converge (RadianceCollector.cpp:19-54,73-141,176-192;
+ * CU/pointEmissionCamera.cu:20-33; CU/PointRadianceTask.h).  tasks_out[i] is the merged representative of
+ * sample i, converged_out[i] its flag; returns the number of update() rounds in *updates_out. */
+int ds_point_radiance_run(DsContext* ctx, const float* positions, const float* directions, uint32_t n,
+                          const DsRadianceSettings* settings, DsPointRadianceTask* tasks_out, uint8_t* converged_out,
+                          uint32_t* updates_out);
+
+/* ---------------------------------------------------------------- records (protobuf wire format, host only) */
+
+/* Persistance::ScatterSample (DeepestScatter_Train/Protocols/ScatterSample.proto; ScatterSampleCollector.cpp:48-56).
+ * Returns the encoded length (<= 64) or a negative error. */
+int ds_record_scatter_sample(const float point[3], const float view_direction[3], uint8_t* out, size_t cap);
+/* Persistance::DisneyDescriptor{bytes grid} (DisneyDescriptorCollector.cpp:76-96) */
+int ds_record_disney_descriptor(const uint8_t* grid, size_t grid_len, uint8_t* out, size_t cap);
+/* Persistance::Result{light_intensity, is_converged} (RadianceCollector.cpp:160-164) */
+int ds_record_result(float light_intensity, int is_converged, uint8_t* out, size_t cap);
+/* Persistance::SceneSetup (DG/ExecutionLoop/Tasks.cpp:77-85) */
+int ds_record_scene_setup(const char* cloud_path, float cloud_size_m, const float light_direction[3], uint8_t* out, size_t cap);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* DS_ABI_H */

@@ -1,0 +1,362 @@
+"""Parity of the sm_100a CUDA path (called through the C ABI) against the host oracle.
+
+EXACT arithmetic flavour: bit-for-bit equality on the same seeded inputs (integer work AND radiance).
+FAST flavour (hardware texture filtering + MUFU intrinsics, what the reference itself runs): statistical
+agreement -- per pixel within 3 sigma, image mean within 0.5 %.
+"""
+import numpy as np
+import pytest
+
+import oracle_lib as ol
+from conftest import SCENE_SMALL
+
+pytestmark = pytest.mark.gpu
+
+W, H = 40, 22  # deliberately not multiples of the 8x4 work tiles
+
+
+def cam_pair(ds, w, h):
+    cam = ds.camera_look_at(aspect=w / h)
+    return cam, ds.camera_array(cam)
+
+
+# ---------------------------------------------------------------- integer / byte work: bit exact
+
+@pytest.mark.parametrize("kind", [0, 1, 2])
+def test_synthetic_grid_and_mips_bit_exact(built_library, kind):
+    ds = built_library
+    o = ol.Oracle()
+    o.volume_synth(48, kind, 99, True)
+    with ds.Context(0) as ctx:
+        ctx.volume_synth(48, kind, 99, True)
+        assert ctx.level_count() == o.level_count()
+        for l in range(o.level_count()):
+            assert ctx.level_dims(l) == o.level_dims(l)
+            assert np.array_equal(ctx.level(l), o.level(l)), f"kind {kind} level {l}"
+
+
+@pytest.mark.parametrize("shape", [(13, 7, 21), (1, 5, 9), (33, 32, 31), (64, 64, 64)])
+def test_uploaded_volume_mips_bit_exact(built_library, shape):
+    ds = built_library
+    rng = np.random.default_rng(7)
+    g = rng.integers(0, 256, shape, dtype=np.uint8)
+    o = ol.Oracle()
+    o.volume_upload(g, True)
+    with ds.Context(0) as ctx:
+        ctx.volume_upload(g, True)
+        assert ctx.level_count() == o.level_count()
+        for l in range(o.level_count()):
+            assert np.array_equal(ctx.level(l), o.level(l))
+        assert ctx.level(ctx.level_count() - 1).shape == (1, 1, 1)
+        ctx.volume_upload(g, False)
+        assert ctx.level_count() == 1
+
+
+def test_float_grid_quantisation_bit_exact(built_library):
+    ds = built_library
+    rng = np.random.default_rng(3)
+    v = rng.uniform(0, 2.5, (9, 10, 11)).astype(np.float32)
+    ref = np.empty(v.size, dtype=np.uint8)
+    ol.lib().orc_quantize_float_grid(v.reshape(-1), v.size, 2.5, ref)
+    with ds.Context(0) as ctx:
+        ctx.volume_upload_float(v, 2.5, False)
+        assert np.array_equal(ctx.level(0).reshape(-1), ref)
+
+
+def test_derived_scene_variables_equal(gpu_small, oracle_small):
+    a, b = gpu_small.derived(), oracle_small.derived()
+    for k in a:
+        assert np.array_equal(np.asarray(a[k]), np.asarray(b[k])), k
+
+
+def test_bake_exact_is_bit_exact(gpu_small, oracle_small):
+    assert np.array_equal(gpu_small.inscatter(), oracle_small.inscatter())
+
+
+def test_bake_fast_within_one_lsb(built_library, oracle_small):
+    ds = built_library
+    with ds.Context(0) as ctx:
+        ctx.set_option("precision", ds.PRECISION_FAST)
+        ctx.volume_synth(SCENE_SMALL["n"], SCENE_SMALL["kind"], SCENE_SMALL["seed"])
+        ctx.scene_set(SCENE_SMALL["cloud_size_m"], SCENE_SMALL["light_dir"])
+        ctx.bake()
+        diff = np.abs(ctx.inscatter().astype(int) - oracle_small.inscatter().astype(int))
+        assert diff.max() <= 3 and (diff > 1).mean() < 0.01 and diff.mean() < 0.2
+
+
+def test_bake_skip_empty_does_not_change_a_byte(built_library, oracle_small):
+    ds = built_library
+    with ds.Context(0) as ctx:
+        ctx.set_option("precision", ds.PRECISION_EXACT)
+        ctx.set_option("skip_empty", 0)
+        ctx.volume_synth(SCENE_SMALL["n"], SCENE_SMALL["kind"], SCENE_SMALL["seed"])
+        ctx.scene_set(SCENE_SMALL["cloud_size_m"], SCENE_SMALL["light_dir"])
+        ctx.bake()
+        assert np.array_equal(ctx.inscatter(), oracle_small.inscatter())
+
+
+# ---------------------------------------------------------------- estimators, EXACT flavour: bit exact
+
+def _random_rays(n, seed):
+    rng = np.random.default_rng(seed)
+    origins = rng.normal(size=(n, 3))
+    origins = (origins / np.linalg.norm(origins, axis=1, keepdims=True) * 2.0).astype(np.float32)
+    target = rng.uniform(-0.3, 0.3, (n, 3)).astype(np.float32)
+    dirs = target - origins
+    dirs = (dirs / np.linalg.norm(dirs, axis=1, keepdims=True)).astype(np.float32)
+    # a few rays from inside the box and a few that miss
+    origins[:8] = rng.uniform(-0.2, 0.2, (8, 3))
+    dirs[8:16] = -dirs[8:16]
+    val0 = rng.integers(0, 2**32, n, dtype=np.uint32)
+    stream = rng.integers(1, 1000, n).astype(np.uint32)
+    return origins, dirs, val0, stream
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2])
+def test_trace_paths_bit_exact_and_counters_equal(gpu_small, oracle_small, mode):
+    origins, dirs, val0, stream = _random_rays(3000, 42 + mode)
+    oracle_small.counters_reset()
+    ref = oracle_small.trace_paths(mode, origins, dirs, val0, stream)
+    oc = oracle_small.counters()
+    gpu_small.counters_reset()
+    got = gpu_small.trace_paths(mode, origins, dirs, val0, stream)
+    gc = gpu_small.counters()
+    assert np.array_equal(got.view(np.uint32), ref.view(np.uint32))
+    assert ref[:, 0].max() > 0
+    assert (gc["paths"], gc["events"], gc["steps"]) == (oc["paths"], oc["events"], oc["steps"])
+    assert gc["density_taps"] <= gc["steps"] and gc["nonfinite"] == 0
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2])
+def test_render_frame_result_bit_exact(gpu_small, oracle_small, built_library, mode):
+    cam, cam_np = cam_pair(built_library, W, H)
+    gpu_small.frame_create(W, H)
+    got = gpu_small.render_frame(cam, mode, 5)
+    ref = oracle_small.render_frame(cam_np, W, H, mode, 5)
+    assert np.array_equal(got.view(np.uint32), ref.view(np.uint32))
+    assert np.all(got[..., 3] == 1)
+
+
+def test_progressive_accumulation_bit_exact(gpu_small, oracle_small, built_library):
+    """Camera::render loop: 10 subframes then 7 more, chunked through a 4-subframe staging buffer."""
+    cam, cam_np = cam_pair(built_library, W, H)
+    gpu_small.frame_create(W, H)
+    gpu_small.set_option("staging_subframes", 4)
+    gpu_small.render_subframes(cam, 0, 1, 10)
+    gpu_small.render_subframes(cam, 0, 11, 7)
+    gpu_small.set_option("staging_subframes", 16)
+    p, v = gpu_small.frame_download()
+    rp, rv = oracle_small.render_accumulate(cam_np, W, H, 0, 1, 17)
+    assert np.array_equal(p.view(np.uint32), rp.view(np.uint32))
+    assert np.array_equal(v.view(np.uint32), rv.view(np.uint32))
+    assert gpu_small.unconverged(17) == int(ol.lib().orc_unconverged_pixels(rp.reshape(-1), rv.reshape(-1), W * H, 17))
+
+
+def test_render_subframes_host_round_trip(gpu_small, oracle_small, built_library):
+    cam, cam_np = cam_pair(built_library, W, H)
+    gpu_small.frame_create(W, H)
+    p = np.zeros((H, W, 4), dtype=np.float32)
+    v = np.zeros((H, W, 4), dtype=np.float32)
+    gpu_small.render_subframes_host(cam, 2, 1, 3, p, v)
+    gpu_small.render_subframes_host(cam, 2, 4, 2, p, v)
+    rp, rv = oracle_small.render_accumulate(cam_np, W, H, 2, 1, 5)
+    assert np.array_equal(p, rp) and np.array_equal(v, rv)
+
+
+def test_results_do_not_depend_on_scheduling_knobs(gpu_small, built_library):
+    """Per-path RNG streams depend on the work item only: block size, residency, the march/event vote
+    and empty-space skipping must not change a bit."""
+    cam, _ = cam_pair(built_library, W, H)
+    gpu_small.frame_create(W, H)
+    base = gpu_small.render_frame(cam, 0, 2)
+    gpu_small.counters_reset()
+    gpu_small.render_frame(cam, 0, 2)
+    c0 = gpu_small.counters()
+    try:
+        for opts in (dict(block_threads=64, blocks_per_sm=1), dict(march_keep_quarters=0), dict(march_keep_quarters=4, march_max_iters=3),
+                     dict(skip_empty=0)):
+            for k, val in opts.items():
+                gpu_small.set_option(k, val)
+            gpu_small.counters_reset()
+            again = gpu_small.render_frame(cam, 0, 2)
+            c = gpu_small.counters()
+            assert np.array_equal(again.view(np.uint32), base.view(np.uint32)), opts
+            assert (c["paths"], c["events"], c["steps"]) == (c0["paths"], c0["events"], c0["steps"])
+            if opts.get("skip_empty") == 0:
+                assert c["density_taps"] == c["steps"] and c0["density_taps"] < c0["steps"]
+            for k, val in dict(block_threads=512, blocks_per_sm=2, march_keep_quarters=2, march_max_iters=64, skip_empty=1).items():
+                gpu_small.set_option(k, val)
+    finally:
+        for k, val in dict(block_threads=512, blocks_per_sm=2, march_keep_quarters=2, march_max_iters=64, skip_empty=1).items():
+            gpu_small.set_option(k, val)
+
+
+# ---------------------------------------------------------------- estimators, FAST flavour: statistical
+
+def test_fast_flavour_matches_oracle_statistically(built_library, oracle_small):
+    ds = built_library
+    w, h, spp = 48, 27, 48
+    cam, cam_np = cam_pair(ds, w, h)
+    rp, rv = oracle_small.render_accumulate(cam_np, w, h, 0, 1, spp)
+    with ds.Context(0) as ctx:
+        assert ctx.get_option("precision") == ds.PRECISION_FAST  # the default flavour
+        ctx.volume_synth(SCENE_SMALL["n"], SCENE_SMALL["kind"], SCENE_SMALL["seed"])
+        ctx.scene_set(SCENE_SMALL["cloud_size_m"], SCENE_SMALL["light_dir"])
+        ctx.bake()
+        ctx.frame_create(w, h)
+        ctx.render_subframes(cam, 0, 1, spp)
+        p, v = ctx.frame_download()
+        assert ctx.counters()["nonfinite"] == 0
+    a, b = p[..., 0].astype(np.float64), rp[..., 0].astype(np.float64)
+    va, vb = v[..., 0].astype(np.float64) / (spp - 1), rv[..., 0].astype(np.float64) / (spp - 1)
+    sigma = np.sqrt((va + vb) / spp)
+    lit = sigma > 0
+    z = np.abs(a - b)[lit] / sigma[lit]
+    assert (z < 3).mean() > 0.99, f"per-pixel 3-sigma agreement only {(z < 3).mean():.4f}"
+    assert np.all((a == 0) == (b == 0)) or ((a == 0) != (b == 0)).mean() < 0.01  # same silhouette
+    assert abs(a.mean() - b.mean()) / b.mean() < 0.005 + 3 * np.sqrt((sigma**2).sum()) / a.size / b.mean()
+
+
+# ---------------------------------------------------------------- dataset generation
+
+def test_generate_points_bit_exact(gpu_small, oracle_small):
+    p, d = gpu_small.generate_points(100, 257, 0)
+    rp, rd = oracle_small.generate_points(100, 257, 0)
+    assert np.array_equal(p.view(np.uint32), rp.view(np.uint32))
+    assert np.array_equal(d.view(np.uint32), rd.view(np.uint32))
+
+
+@pytest.mark.parametrize("size_m", [1000.0, 7000.0, 12000.0])
+def test_descriptors_u8_and_indices_bit_exact_floats_1e6(built_library, size_m):
+    ds = built_library
+    o = ol.Oracle()
+    o.volume_synth(64, 0, 1234, True)
+    o.scene_set(size_m, (0.3, -0.8, 0.52))
+    with ds.Context(0) as ctx:
+        ctx.set_option("precision", ds.PRECISION_EXACT)
+        ctx.volume_synth(64, 0, 1234, True)
+        ctx.scene_set(size_m, (0.3, -0.8, 0.52))
+        p, d = ctx.generate_points(0, 96, 0)
+        # add samples at the box faces / corners to exercise the edge fade and clamping
+        p[:4] = [[0.49, 0.0, 0.0], [-0.5, -0.5, -0.5], [0.0, 0.499, 0.3], [0.2, -0.1, -0.5]]
+        got_u8 = ctx.descriptors(p, d)
+        got_f, got_idx = ctx.descriptors(p, d, as_float=True, want_index=True)
+    ref_u8 = o.descriptors(p, d)
+    ref_f, ref_idx = o.descriptors(p, d, as_float=True, want_index=True)
+    assert got_u8.shape == (96, 10, 225)
+    assert np.array_equal(got_idx, ref_idx)  # stencil voxel addresses + mip level
+    assert np.array_equal(got_u8, ref_u8)  # record bytes
+    denom = np.maximum(np.abs(ref_f), 1e-12)
+    assert (np.abs(got_f - ref_f) / denom).max() <= 1e-6
+    assert got_u8.max() > 0
+
+
+def test_point_radiance_collector_bit_exact(gpu_small, oracle_small):
+    p, d = oracle_small.generate_points(0, 6)
+    rt, rc, rn, ru = oracle_small.point_radiance(p, d, max_threads=48, launches_per_update=20, max_updates=3)
+    gt, gc, gn, gu = gpu_small.point_radiance(p, d, max_threads=48, launches_per_update=20, max_updates=3)
+    assert gu == ru and gn == rn and np.array_equal(gc, rc)
+    for f in ("id", "experimentCount"):
+        assert np.array_equal(gt[f], rt[f])
+    for f in ("radiance", "runningVariance", "position", "direction"):
+        assert np.array_equal(gt[f].view(np.uint32), rt[f].view(np.uint32)), f
+
+
+# ---------------------------------------------------------------- tone map, moments
+
+def test_tonemap_matches_reinhard_oracle(gpu_small, oracle_small, built_library):
+    cam, cam_np = cam_pair(built_library, W, H)
+    gpu_small.frame_create(W, H)
+    gpu_small.render_subframes(cam, 0, 1, 4)
+    p, _ = gpu_small.frame_download()
+    got, avg = gpu_small.tonemap(0.4)
+    ref, ravg = ol.tonemap(p, 0.4)
+    assert avg == ravg  # same summation order as reinhard.cu firstPass/secondPass
+    assert np.abs(got.astype(int) - ref.astype(int)).max() <= 1  # powf differs by an ulp between libm and CUDA
+    assert np.all(got[..., 3] == 255)
+
+
+def test_moments_export_import_round_trip_and_merge(gpu_small, built_library):
+    import torch
+
+    cam, _ = cam_pair(built_library, W, H)
+    gpu_small.frame_create(W, H)
+    gpu_small.render_subframes(cam, 0, 1, 6)
+    full_p, full_v = gpu_small.frame_download()
+    ma = torch.zeros(W * H * 8, dtype=torch.float64, device="cuda")
+    mb = torch.zeros_like(ma)
+    gpu_small.frame_clear()
+    gpu_small.render_subframes(cam, 0, 1, 4)  # "rank 0": subframes 1..4
+    gpu_small.export_moments(4, ma.data_ptr())
+    gpu_small.frame_clear()
+    # "rank 1": global subframes 5..6 (RNG streams 5, 6) accumulated as a fresh Welford stream (weights 1/1, 1/2)
+    gpu_small.set_option("stream_offset", 4)
+    gpu_small.render_subframes(cam, 0, 1, 2)
+    gpu_small.set_option("stream_offset", 0)
+    gpu_small.export_moments(2, mb.data_ptr())
+    gpu_small.sync()
+    torch.cuda.synchronize()
+    total = ma + mb
+    gpu_small.import_moments(6, total.data_ptr())
+    p, v = gpu_small.frame_download()
+    assert np.allclose(p, full_p, rtol=2e-6, atol=1e-7)
+    assert np.allclose(v, full_v, rtol=1e-4, atol=1e-3 * max(1.0, float(full_v.max()) * 1e-6))
+
+
+# ---------------------------------------------------------------- error behaviour and edge cases
+
+def test_error_paths(built_library):
+    ds = built_library
+    with ds.Context(0) as ctx:
+        cam = ds.camera_look_at()
+        with pytest.raises(ds.DsError):  # no volume yet
+            ctx.bake()
+        ctx.volume_synth(16, 0, 1, True)
+        with pytest.raises(ds.DsError):  # scene not set
+            ctx.bake()
+        ctx.scene_set()
+        ctx.frame_create(8, 8)
+        with pytest.raises(ds.DsError):  # not baked
+            ctx.render_subframes(cam, 0, 1, 1)
+        ctx.bake()
+        with pytest.raises(ds.DsError):  # "Invalid Render Mode" (CloudMaterial.cpp:62)
+            ctx.render_subframes(cam, 7, 1, 1)
+        with pytest.raises(ds.DsError):  # subframe ids are 1-based
+            ctx.render_subframes(cam, 0, 0, 1)
+        with pytest.raises(ds.DsError):
+            ctx.frame_create(5000, 10)
+        with pytest.raises(ds.DsError):
+            ctx.set_option("no_such_option", 1)
+        # empty inputs are fine
+        assert ctx.trace_paths(0, np.zeros((0, 3)), np.zeros((0, 3)), [], []).shape == (0, 3)
+        assert ctx.descriptors(np.zeros((0, 3)), np.zeros((0, 3))).shape == (0, 10, 225)
+        ctx.render_subframes(cam, 0, 1, 0)
+        # a changed sun invalidates the baked volume
+        ctx.scene_set(light_dir=(0, -1, 0))
+        with pytest.raises(ds.DsError):
+            ctx.render_subframes(cam, 0, 1, 1)
+
+
+def test_full_size_frame_properties(built_library):
+    """1920x1080 at the C2 grid size (512^3): properties that need no oracle."""
+    ds = built_library
+    with ds.Context(0) as ctx:
+        ctx.volume_synth(512, 0, 1234, True)
+        ctx.scene_set(7000.0, (-0.586, -0.766, -0.271))
+        ctx.bake()
+        ins = ctx.inscatter()
+        assert ins.max() == 255 and ins.min() == 0
+        ctx.frame_create(1920, 1080)
+        cam = ds.camera_look_at(aspect=1920 / 1080)
+        ctx.render_subframes(cam, 0, 1, 2)
+        p, v = ctx.frame_download()
+        c = ctx.counters()
+        assert c["paths"] == 2 * 1920 * 1080 and c["nonfinite"] == 0
+        assert np.isfinite(p).all() and np.isfinite(v).all() and p.min() >= 0
+        assert np.all(p[..., 3] == 1) and np.all(v[..., 3] == 0)
+        assert np.all(p[:8, :, :3] == 0) and np.all(p[-8:, :, :3] == 0)  # rows that look past the box
+        assert (p[..., 0] > 0).mean() > 0.05
+        # determinism: a second context renders the same bits
+        again = ctx.render_frame(cam, 0, 1)
+        again2 = ctx.render_frame(cam, 0, 1)
+        assert np.array_equal(again, again2)
