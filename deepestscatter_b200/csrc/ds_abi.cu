@@ -38,6 +38,7 @@ struct DsContext {
     cudaArray_t densityArr = nullptr, inscatterArr = nullptr;
     cudaTextureObject_t densityTex = 0, inscatterTex = 0;
     uint32_t* occ = nullptr;
+    uint8_t* cellDist = nullptr;
     int occShift = 0, ocx = 0, ocy = 0, ocz = 0, occWords = 0;
 
     /* scene */
@@ -45,6 +46,7 @@ struct DsContext {
     bool sceneSet = false;
     float derived[12] = {0};
     float* mie = nullptr;     /* 3 * 4096 floats: mie, chopped, cdf */
+    uint16_t* guide = nullptr; /* GUIDE_N + 1 entries */
 
     /* frame */
     int width = 0, height = 0;
@@ -117,6 +119,8 @@ static void freeVolume(DsContext* ctx)
     ctx->densityArr = ctx->inscatterArr = nullptr;
     if (ctx->occ) cudaFree(ctx->occ);
     ctx->occ = nullptr;
+    if (ctx->cellDist) cudaFree(ctx->cellDist);
+    ctx->cellDist = nullptr;
 }
 
 static void freeFrame(DsContext* ctx)
@@ -215,6 +219,8 @@ static void fillDevScene(DsContext* ctx, DevScene& sc)
     sc.ocy = ctx->ocy;
     sc.ocz = ctx->ocz;
     sc.occWords = ctx->occWords;
+    sc.cellDist = ctx->cellDist;
+    sc.guide = ctx->guide;
 }
 
 /* VDBCloud::setupVolumeVariables / setupVariables (VDBCloud.cpp:88-117) + Sun (SceneDescription.h:17-19) */
@@ -278,6 +284,13 @@ static int finishVolume(DsContext* ctx, int buildMips)
     DS_CUDA(ctx, cudaMalloc(&ctx->occ, (size_t)ctx->occWords * 4));
     DS_CUDA(ctx, cudaMemsetAsync(ctx->occ, 0, (size_t)ctx->occWords * 4, ctx->stream));
     DS_CUDA(ctx, launchOccupancy(ctx->levels[0], nx, ny, nz, shift, ctx->ocx, ctx->ocy, ctx->ocz, ctx->occ, ctx->stream));
+    {
+        const size_t cells = (size_t)ctx->ocx * ctx->ocy * ctx->ocz;
+        DS_CUDA(ctx, cudaMalloc(&ctx->cellDist, cells));
+        int rcs = ensureScratch(ctx, 7, cells);
+        if (rcs) return rcs;
+        DS_CUDA(ctx, launchCellDistance(ctx->occ, ctx->ocx, ctx->ocy, ctx->ocz, ctx->cellDist, (uint8_t*)ctx->scratch[7], ctx->stream));
+    }
     int rc = makeTexture(ctx, ctx->levels[0], nx, ny, nz, &ctx->densityArr, &ctx->densityTex);
     if (rc) return rc;
     DS_CUDA(ctx, cudaMalloc(&ctx->inscatter, (size_t)nx * ny * nz));
@@ -307,6 +320,7 @@ static LaunchConfig launchConfig(DsContext* ctx)
     cfg.blocksPerSm = ctx->opt["blocks_per_sm"];
     cfg.smCount = ctx->prop.multiProcessorCount;
     cfg.skipEmpty = ctx->opt["skip_empty"];
+    cfg.variant = ctx->opt["variant"];
     return cfg;
 }
 
@@ -318,6 +332,7 @@ static int runTrace(DsContext* ctx, TraceJob& job)
     job.stats = ctx->stats;
     job.marchKeepQuarters = ctx->opt["march_keep_quarters"];
     job.marchMaxIters = ctx->opt["march_max_iters"];
+    job.marchKeep32 = ctx->opt["march_keep32"];
     DS_CUDA(ctx, cudaMemsetAsync(ctx->queue, 0, sizeof(unsigned long long), ctx->stream));
     const LaunchConfig cfg = launchConfig(ctx);
     const bool prof = ctx->opt["profile_events"] != 0;
@@ -394,6 +409,7 @@ int ds_context_create(int device, DsContext** out)
     ctx->opt["skip_empty"] = 1;
     ctx->opt["march_keep_quarters"] = 2;
     ctx->opt["march_max_iters"] = 64;
+    ctx->opt["march_keep32"] = 6;
     ctx->opt["staging_subframes"] = 16;
     ctx->opt["stream_offset"] = 0;
     ctx->opt["profile_events"] = 0;
@@ -411,6 +427,17 @@ int ds_context_create(int device, DsContext** out)
             memcpy(raw.data(), ds_mie_blob, raw.size() * sizeof(float));
             buildMieSamplers(raw.data(), raw.data() + MIE_N, samplers.data());
             ok = cudaMemcpy(ctx->mie, samplers.data(), samplers.size() * sizeof(float), cudaMemcpyHostToDevice) == cudaSuccess;
+            /* guide[k] = first index with cdf[i] >= k / GUIDE_N (binary-search bounds for the fast CDF inversion) */
+            std::vector<uint16_t> guide(GUIDE_N + 1);
+            const float* cdf = samplers.data() + 2 * MIE_N;
+            int idx = 0;
+            for (int k = 0; k <= GUIDE_N; k++) {
+                const float v = (float)k / (float)GUIDE_N;
+                while (idx < MIE_N && cdf[idx] < v) idx++;
+                guide[k] = (uint16_t)idx;
+            }
+            ok = ok && cudaMalloc(&ctx->guide, guide.size() * sizeof(uint16_t)) == cudaSuccess &&
+                 cudaMemcpy(ctx->guide, guide.data(), guide.size() * sizeof(uint16_t), cudaMemcpyHostToDevice) == cudaSuccess;
         }
     }
     if (!ok) {
@@ -432,6 +459,7 @@ int ds_context_destroy(DsContext* ctx)
     cudaFree(ctx->stats);
     cudaFree(ctx->queue);
     cudaFree(ctx->mie);
+    cudaFree(ctx->guide);
     for (int i = 0; i < 8; i++) cudaFree(ctx->scratch[i]);
     for (cudaEvent_t e : ctx->traceEvents) cudaEventDestroy(e);
     if (ctx->ownStream && ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -463,7 +491,7 @@ int ds_set_option(DsContext* ctx, const char* name, int value)
     DS_CHECK_CTX(ctx);
     if (!name || ctx->opt.find(name) == ctx->opt.end()) DS_FAIL(ctx, DS_ERR_INVALID, "unknown option '%s'", name ? name : "(null)");
     const std::string n = name;
-    if (n == "block_threads" && (value < 32 || value > 512 || value % 32)) DS_FAIL(ctx, DS_ERR_INVALID, "block_threads must be 32..512, multiple of 32");
+    if (n == "block_threads" && (value < 32 || value > 1024 || value % 32)) DS_FAIL(ctx, DS_ERR_INVALID, "block_threads must be 32..1024, multiple of 32");
     if (n == "blocks_per_sm" && (value < 1 || value > 32)) DS_FAIL(ctx, DS_ERR_INVALID, "blocks_per_sm must be 1..32");
     if (n == "precision" && value != DS_PRECISION_EXACT && value != DS_PRECISION_FAST) DS_FAIL(ctx, DS_ERR_INVALID, "precision must be 0 or 1");
     if (n == "staging_subframes" && value < 1) DS_FAIL(ctx, DS_ERR_INVALID, "staging_subframes must be >= 1");

@@ -98,7 +98,13 @@ struct DevScene {
     int occShift;
     int ocx, ocy, ocz;
     int occWords;
+    /* Chebyshev distance (in cells, saturated at 255) from each cell to the nearest occupied cell; 0 = occupied */
+    const uint8_t* cellDist;
+    /* guide table of the chopped-Mie CDF: guide[k] = first index i with cdf[i] >= k / GUIDE_N, k = 0..GUIDE_N */
+    const uint16_t* guide;
 };
+
+constexpr int GUIDE_N = 1024;
 
 /* ---- CU/random.cuh ---- */
 

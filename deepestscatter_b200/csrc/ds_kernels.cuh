@@ -242,7 +242,7 @@ __global__ void __launch_bounds__(512, 2) k_trace(const DevScene sc, const Trace
 }
 
 template <bool FAST>
-cudaError_t KernelSet<FAST>::trace(const DevScene& sc, const TraceJob& job, const LaunchConfig& cfg, cudaStream_t st)
+cudaError_t traceGeneric(const DevScene& sc, const TraceJob& job, const LaunchConfig& cfg, cudaStream_t st)
 {
     const size_t smem = (size_t)(2 * MIE_N + (cfg.skipEmpty ? sc.occWords : 0)) * 4;
     const int threads = cfg.blockThreads;

@@ -23,7 +23,8 @@ struct TraceJob {
     unsigned long long total;
     unsigned long long* queue;  /* work counter, zeroed before launch */
     unsigned long long* stats;  /* CNT_COUNT counters */
-    int marchKeepQuarters;      /* leave the march phase when marching*4 <= alive*q */
+    int marchKeepQuarters;      /* generic kernel: leave the march phase when marching*4 <= alive*q */
+    int marchKeep32;            /* fast kernel: leave the march phase when marching*32 <= alive*k */
     int marchMaxIters;
     /* JOB_RENDER: item = (subframe, 8x4 pixel tile, pixel in tile) */
     float eye[3], U[3], V[3], W[3];
@@ -61,6 +62,7 @@ struct LaunchConfig {
     int blocksPerSm;
     int smCount;
     int skipEmpty;
+    int variant; /* FAST flavour: 0 = optimised k_trace_fast, 1 = generic k_trace<true, SKIP> (round-1 baseline) */
 };
 
 template <bool FAST>
@@ -75,6 +77,7 @@ struct KernelSet {
 cudaError_t launchSynth(uint8_t* out, int n, int kind, uint32_t seed, cudaStream_t st);
 cudaError_t launchQuantize(const float* in, size_t count, double maxDensity, uint8_t* out, cudaStream_t st);
 cudaError_t launchMip(const uint8_t* prev, int pnx, int pny, int pnz, uint8_t* cur, int cnx, int cny, int cnz, cudaStream_t st);
+cudaError_t launchCellDistance(const uint32_t* occBits, int ocx, int ocy, int ocz, uint8_t* dist, uint8_t* tmp, cudaStream_t st);
 cudaError_t launchOccupancy(const uint8_t* density, int nx, int ny, int nz, int shift, int ocx, int ocy, int ocz, uint32_t* bits,
                             cudaStream_t st);
 cudaError_t launchUpdateFrame(const float4* staging, float4* progressive, float4* variance, size_t pixels, uint32_t firstSubframe,

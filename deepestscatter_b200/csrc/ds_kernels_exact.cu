@@ -9,6 +9,12 @@
 
 namespace dsk {
 
+template <>
+cudaError_t KernelSet<false>::trace(const DevScene& sc, const TraceJob& job, const LaunchConfig& cfg, cudaStream_t st)
+{
+    return traceGeneric<false>(sc, job, cfg, st);
+}
+
 template struct KernelSet<false>;
 
 /* ---- synthetic grid (include/ds_synth.h) ---- */
@@ -93,6 +99,47 @@ cudaError_t launchOccupancy(const uint8_t* density, int nx, int ny, int nz, int 
 {
     const int cells = ocx * ocy * ocz;
     k_occupancy<<<(cells + 127) / 128, 128, 0, st>>>(density, nx, ny, nz, shift, ocx, ocy, ocz, bits);
+    return cudaGetLastError();
+}
+
+/* ---- Chebyshev distance transform over occupancy cells (iterated 26-neighbour relaxation) ---- */
+__global__ void __launch_bounds__(128) k_cell_dist_init(const uint32_t* __restrict__ bits, int cells, uint8_t* dist)
+{
+    const int cell = blockIdx.x * blockDim.x + threadIdx.x;
+    if (cell >= cells) return;
+    dist[cell] = ((bits[cell >> 5] >> (cell & 31)) & 1u) ? 0 : 255;
+}
+
+__global__ void __launch_bounds__(128) k_cell_dist_relax(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, int ocx, int ocy, int ocz)
+{
+    const int cell = blockIdx.x * blockDim.x + threadIdx.x;
+    if (cell >= ocx * ocy * ocz) return;
+    const int cx = cell % ocx, cy = (cell / ocx) % ocy, cz = cell / (ocx * ocy);
+    int best = in[cell];
+    for (int dz = -1; dz <= 1; dz++)
+        for (int dy = -1; dy <= 1; dy++)
+            for (int dx = -1; dx <= 1; dx++) {
+                const int x = cx + dx, y = cy + dy, z = cz + dz;
+                if (x < 0 || y < 0 || z < 0 || x >= ocx || y >= ocy || z >= ocz) continue;
+                best = min(best, min(254, (int)in[(z * ocy + y) * ocx + x]) + 1);
+            }
+    out[cell] = (uint8_t)best;
+}
+
+cudaError_t launchCellDistance(const uint32_t* occBits, int ocx, int ocy, int ocz, uint8_t* dist, uint8_t* tmp, cudaStream_t st)
+{
+    const int cells = ocx * ocy * ocz;
+    const int blocks = (cells + 127) / 128;
+    k_cell_dist_init<<<blocks, 128, 0, st>>>(occBits, cells, dist);
+    int iters = max(max(ocx, ocy), ocz);
+    iters += iters & 1; /* even number of ping-pong passes: the result ends up in `dist` */
+    uint8_t *a = dist, *b = tmp;
+    for (int i = 0; i < iters; i++) {
+        k_cell_dist_relax<<<blocks, 128, 0, st>>>(a, b, ocx, ocy, ocz);
+        uint8_t* t = a;
+        a = b;
+        b = t;
+    }
     return cudaGetLastError();
 }
 

@@ -1,11 +1,362 @@
 /*
  * ds_kernels_fast.cu -- translation unit compiled with FMA contraction: the throughput flavour of the
- * estimator kernels (hardware 3-D texture filtering, MUFU exp/log/sincos), i.e. the arithmetic the
- * reference itself runs (rtTex3D + --use_fast_math).  Validated against the oracle statistically.
+ * estimator (DsPrecision FAST).  Same algorithm and the same per-path RNG streams as the reference
+ * estimator (CU/cloudRadianceMaterials.cu, CU/cloud.cuh), evaluated the way the reference itself runs on a
+ * GPU -- hardware trilinear texture filtering (rtTex3D, cloud.cuh:61) and approximate transcendentals
+ * (--use_fast_math, vcxproj:320) -- and validated against the oracle statistically.
+ *
+ * k_trace_fast differs from the generic kernel (ds_kernels.cuh) only in how it spends instructions:
+ *   - the path marches in TEXTURE space (q = pos * textureScale), so a tap is one TEX instruction;
+ *   - transmittance is carried as optical depth: tau += sigma*step and the collision test xi > exp(-tau)
+ *     becomes tau > -ln(xi); one logarithm per free flight instead of one exponential per march step;
+ *   - empty space: when the last tap returned exactly 0, the lane looks up the occupancy bit of its tap cell
+ *     (shared memory) and, if the cell is empty, the Chebyshev distance to the nearest occupied cell; it
+ *     then advances k whole march steps at once, k chosen so that every skipped tap lies in cells that are
+ *     known to be empty.  Skipped steps read density 0, i.e. tau and the collision test are unchanged;
+ *     the step counter still advances by k (the reference algorithm performs those steps);
+ *   - the 16-step bisection of the chopped-Mie CDF (cloud.cuh:167-178) is replaced by the closed-form
+ *     inverse of the same piecewise-linear CDF: guide table -> short binary search for the table cell ->
+ *     linear solve.  The bisection converges to that root within 2^-16;
+ *   - radiance is accumulated as the scalar sum of Tsun*phase and scaled by lightColor*lightIntensity*ratio
+ *     once per path.
  */
 #include "ds_kernels.cuh"
 
 namespace dsk {
+
+struct FastState {
+    V3 q;   /* position in texture coordinates */
+    V3 dir; /* unit direction (world / box-local axes) */
+    float rad;
+    float tau;     /* optical depth accumulated in the current free flight */
+    float tauStar; /* -ln(xi) */
+    uint32_t seed;
+    int depth;
+    unsigned long long out;
+    bool lastZero; /* the previous density tap returned exactly 0 (or the flight has just started outside the cloud) */
+};
+
+struct FastConsts {
+    V3 stepTs;  /* sampleStep * textureScale */
+    V3 half;    /* 0.5 + 0.01 * textureScale: half extent of the in-box slab in texture space */
+    float c1;   /* densityMultiplier * sampleStep */
+    float nxf, nyf, nzf;
+};
+
+__device__ __forceinline__ bool inBoxTs(const FastConsts& k, V3 q)
+{
+    return fabsf(q.x - 0.5f) <= k.half.x && fabsf(q.y - 0.5f) <= k.half.y && fabsf(q.z - 0.5f) <= k.half.z;
+}
+
+/* closed-form inverse of the piecewise-linear CDF that cloud.cuh:167-178 bisects */
+__device__ __forceinline__ float invertCdf(const float* sCdf, const uint16_t* sGuide, float val)
+{
+    const int k = min((int)(val * (float)GUIDE_N), GUIDE_N - 1);
+    int lo = sGuide[k], hi = sGuide[k + 1];
+    while (lo < hi) { /* first index with cdf[i] >= val */
+        const int mid = (lo + hi) >> 1;
+        if (sCdf[mid] < val)
+            lo = mid + 1;
+        else
+            hi = mid;
+    }
+    float u;
+    if (lo == 0) {
+        u = 0.0f;
+    } else if (lo >= MIE_N) {
+        u = 1.0f;
+    } else {
+        const float a = sCdf[lo - 1], b = sCdf[lo];
+        const float t = __fdividef(val - a, b - a);
+        u = ((float)lo - 0.5f + t) * (1.0f / (float)MIE_N);
+    }
+    return 2.0f * u - 1.0f;
+}
+
+/* CU/cloud.cuh:160-188 */
+__device__ __forceinline__ V3 newDirectionFast(const float* sCdf, const uint16_t* sGuide, uint32_t& seed, V3 prev)
+{
+    const float val = rnd(seed);
+    const float cosTheta = invertCdf(sCdf, sGuide, val);
+    const float phi = rnd(seed) * (PI_F * 2.0f);
+    const float sinTheta = sqrtf(fmaxf(1.0f - cosTheta * cosTheta, 0.0f));
+    float s, c;
+    __sincosf(phi, &s, &c);
+    V3 d = onbInverseTransform<true>(prev, mk(sinTheta * c, sinTheta * s, cosTheta));
+    return d * rsqrtf(dot(d, d));
+}
+
+__device__ __forceinline__ int loopTopFast(const FastConsts& k, FastState& s)
+{
+    if (!inBoxTs(k, s.q)) return ST_DONE;
+    s.depth++;
+    if (s.depth == MAX_DEPTH) return ST_DONE;
+    const float xi = rnd(s.seed);
+    s.tauStar = -__logf(xi); /* xi == 0 -> +inf: never collides, as `0 > T` in the reference */
+    s.tau = 0.0f;
+    return ST_MARCH;
+}
+
+/* The tap at q is about to be taken and the previous one read 0.  If the tap cell is empty, skip the tap and
+ * advance as many whole steps as stay inside the cube of cells known to be empty.  Returns true when the tap
+ * is skipped. */
+__device__ __forceinline__ bool skipEmpty(const DevScene& sc, const FastConsts& k, const uint32_t* sOcc, FastState& s, uint32_t& nSteps)
+{
+    const float x = fmaf(s.q.x, k.nxf, -0.5f), y = fmaf(s.q.y, k.nyf, -0.5f), z = fmaf(s.q.z, k.nzf, -0.5f);
+    const int cx = min(max(__float2int_rd(x), 0), sc.nx - 1) >> sc.occShift;
+    const int cy = min(max(__float2int_rd(y), 0), sc.ny - 1) >> sc.occShift;
+    const int cz = min(max(__float2int_rd(z), 0), sc.nz - 1) >> sc.occShift;
+    const int cell = (cz * sc.ocy + cy) * sc.ocx + cx;
+    if ((sOcc[cell >> 5] >> (cell & 31)) & 1u) return false;
+    const int d = __ldg(sc.cellDist + cell); /* >= 1: every cell within Chebyshev distance d-1 is empty */
+    const float cs = (float)(1 << sc.occShift);
+    const float eps = 0.02f;
+    /* admissible range of the voxel coordinate x = u*N - 0.5 of a tap: its floor must stay inside the empty cells */
+    const float lox = fmaxf((float)(cx - d + 1) * cs, -0.5f) + eps, hix = fminf((float)(cx + d) * cs, k.nxf - 0.5f) - eps;
+    const float loy = fmaxf((float)(cy - d + 1) * cs, -0.5f) + eps, hiy = fminf((float)(cy + d) * cs, k.nyf - 0.5f) - eps;
+    const float loz = fmaxf((float)(cz - d + 1) * cs, -0.5f) + eps, hiz = fminf((float)(cz + d) * cs, k.nzf - 0.5f) - eps;
+    const float vx = s.dir.x * k.stepTs.x * k.nxf, vy = s.dir.y * k.stepTs.y * k.nyf, vz = s.dir.z * k.stepTs.z * k.nzf;
+    const float big = 1.0e9f;
+    const float tx = vx > 0.0f ? __fdividef(hix - x, vx) : (vx < 0.0f ? __fdividef(lox - x, vx) : big);
+    const float ty = vy > 0.0f ? __fdividef(hiy - y, vy) : (vy < 0.0f ? __fdividef(loy - y, vy) : big);
+    const float tz = vz > 0.0f ? __fdividef(hiz - z, vz) : (vz < 0.0f ? __fdividef(loz - z, vz) : big);
+    const float t = fminf(fminf(tx, ty), fminf(tz, 4096.0f));
+    if (t >= 1.0f) {
+        const float kf = floorf(t);
+        s.q.x = fmaf(kf * s.dir.x, k.stepTs.x, s.q.x);
+        s.q.y = fmaf(kf * s.dir.y, k.stepTs.y, s.q.y);
+        s.q.z = fmaf(kf * s.dir.z, k.stepTs.z, s.q.z);
+        nSteps += (uint32_t)kf;
+    }
+    return true;
+}
+
+template <bool SKIP>
+__device__ __forceinline__ int beginItemFast(const DevScene& sc, const FastConsts& k, const TraceJob& job, const float* sCdf,
+                                             const uint16_t* sGuide, unsigned long long idx, FastState& s, bool& valid)
+{
+    V3 o, d;
+    uint32_t val0, stream;
+    valid = true;
+    if (job.kind == JOB_RENDER) {
+        const unsigned long long sub = idx / job.itemsPerSubframe;
+        const uint32_t rem = (uint32_t)(idx - sub * job.itemsPerSubframe);
+        const uint32_t tile = rem >> 5, within = rem & 31u;
+        const uint32_t px = (tile % (uint32_t)job.tilesX) * 8u + (within & 7u);
+        const uint32_t py = (tile / (uint32_t)job.tilesX) * 4u + (within >> 3);
+        if (px >= (uint32_t)job.width || py >= (uint32_t)job.height) {
+            valid = false;
+            return ST_IDLE;
+        }
+        const float dx = (float)px / (float)job.width * 2.f - 1.f;
+        const float dy = (float)py / (float)job.height * 2.f - 1.f;
+        const V3 U = mk(job.U[0], job.U[1], job.U[2]), V = mk(job.V[0], job.V[1], job.V[2]), W = mk(job.W[0], job.W[1], job.W[2]);
+        o = mk(job.eye[0], job.eye[1], job.eye[2]);
+        d = normalize<true>(dx * U + dy * V + W);
+        val0 = px * 4096u + py;
+        stream = job.firstSubframe + (uint32_t)sub;
+        s.out = sub * (unsigned long long)job.width * job.height + (unsigned long long)py * job.width + px;
+    } else if (job.kind == JOB_POINT) {
+        const uint32_t t = (uint32_t)(idx / job.launches);
+        const uint32_t l = (uint32_t)(idx - (unsigned long long)t * job.launches);
+        const DsPointRadianceTask* task = job.tasks + t;
+        o = mk(task->position[0], task->position[1], task->position[2]);
+        d = mk(task->direction[0], task->direction[1], task->direction[2]);
+        val0 = t * 4096u;
+        stream = job.frame0 + l + 1u;
+        s.out = idx;
+    } else {
+        o = mk(job.origins[3 * idx], job.origins[3 * idx + 1], job.origins[3 * idx + 2]);
+        d = mk(job.dirs[3 * idx], job.dirs[3 * idx + 1], job.dirs[3 * idx + 2]);
+        val0 = job.seedVal0[idx];
+        stream = job.stream[idx];
+        s.out = idx;
+    }
+    s.rad = 0.0f;
+    const float tHit = intersectBox(sc, o, d);
+    if (tHit < 0.0f) return ST_DONE;
+    V3 hit = o + tHit * d;
+    hit = hit + 0.5f * sc.bbox;
+    s.q = hit * sc.texScale;
+    s.dir = normalize<true>(d);
+    s.seed = tea4(val0, stream);
+    s.depth = 0;
+    s.lastZero = true;
+    if (job.mode == DS_MODE_SUN_MULTIPLE_SCATTER) s.dir = newDirectionFast(sCdf, sGuide, s.seed, s.dir);
+    return loopTopFast(k, s);
+}
+
+__device__ __forceinline__ void writeResultFast(const DevScene& sc, const TraceJob& job, const FastState& s, uint32_t& nonfinite)
+{
+    const float scale = sc.lightIntensity * SUN_TO_SPHERE * s.rad;
+    const float r = sc.lightColor.x * scale, g = sc.lightColor.y * scale, b = sc.lightColor.z * scale;
+    if (!(fabsf(r + g + b) <= 3.0e38f)) nonfinite++;
+    if (job.kind == JOB_RENDER) {
+        job.staging[s.out] = make_float4(r, g, b, 1.0f);
+    } else if (job.kind == JOB_POINT) {
+        job.xOut[s.out] = r;
+    } else {
+        job.radianceOut[3 * s.out] = r;
+        job.radianceOut[3 * s.out + 1] = g;
+        job.radianceOut[3 * s.out + 2] = b;
+    }
+}
+
+template <bool SKIP>
+__global__ void __launch_bounds__(640, 2) k_trace_fast(const DevScene sc, const TraceJob job)
+{
+    extern __shared__ __align__(16) unsigned char smemRaw[];
+    float* sChopped = reinterpret_cast<float*>(smemRaw);
+    float* sCdf = sChopped + MIE_N;
+    uint16_t* sGuide = reinterpret_cast<uint16_t*>(sCdf + MIE_N);
+    uint32_t* sOcc = reinterpret_cast<uint32_t*>(sGuide + GUIDE_N + 2);
+    for (int i = threadIdx.x; i < MIE_N; i += blockDim.x) {
+        sChopped[i] = sc.chopped[i];
+        sCdf[i] = sc.cdf[i];
+    }
+    for (int i = threadIdx.x; i <= GUIDE_N; i += blockDim.x) sGuide[i] = sc.guide[i];
+    if (SKIP) {
+        for (int i = threadIdx.x; i < sc.occWords; i += blockDim.x) sOcc[i] = sc.occ[i];
+    }
+    __syncthreads();
+
+    FastConsts k;
+    k.stepTs = sc.texScale * sc.step;
+    k.half = mk(0.5f + 0.01f * sc.texScale.x, 0.5f + 0.01f * sc.texScale.y, 0.5f + 0.01f * sc.texScale.z);
+    k.c1 = sc.mult * sc.step;
+    k.nxf = (float)sc.nx;
+    k.nyf = (float)sc.ny;
+    k.nzf = (float)sc.nz;
+
+    const unsigned FULL = 0xffffffffu;
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned laneLt = (1u << lane) - 1u;
+
+    FastState s;
+    s.q = s.dir = mk(0.f, 0.f, 0.f);
+    s.rad = s.tau = s.tauStar = 0.f;
+    s.seed = 0;
+    s.depth = 0;
+    s.out = 0;
+    s.lastZero = true;
+    int st = ST_IDLE;
+    bool exhausted = false;
+    uint32_t nPaths = 0, nEvents = 0, nSteps = 0, nTaps = 0, nNonfinite = 0;
+    float lastDensity = 0.0f;
+
+    for (;;) {
+        /* ---- finish + regenerate ---- */
+        if (st == ST_DONE) {
+            writeResultFast(sc, job, s, nNonfinite);
+            st = ST_IDLE;
+        }
+        const unsigned need = __ballot_sync(FULL, st == ST_IDLE && !exhausted);
+        if (need) {
+            unsigned long long base = 0;
+            const int leader = __ffs(need) - 1;
+            if ((int)lane == leader) base = atomicAdd(job.queue, (unsigned long long)__popc(need));
+            base = __shfl_sync(FULL, base, leader);
+            if (st == ST_IDLE && !exhausted) {
+                const unsigned long long idx = base + __popc(need & laneLt);
+                if (idx >= job.total) {
+                    exhausted = true;
+                } else {
+                    bool valid;
+                    st = beginItemFast<SKIP>(sc, k, job, sCdf, sGuide, idx, s, valid);
+                    if (valid) nPaths++;
+                }
+            }
+        }
+        const unsigned alive = __ballot_sync(FULL, st != ST_IDLE);
+        if (alive == 0u) {
+            if (__all_sync(FULL, exhausted)) break;
+            continue;
+        }
+        const int nAlive = __popc(alive);
+
+        /* ---- march phase (CU/cloud.cuh:87-104) ---- */
+#pragma unroll 1
+        for (int it = 0; it < job.marchMaxIters; ++it) {
+            if (st == ST_MARCH) {
+                if (!inBoxTs(k, s.q)) {
+                    st = ST_DONE;
+                } else {
+                    s.q.x = fmaf(s.dir.x, k.stepTs.x, s.q.x);
+                    s.q.y = fmaf(s.dir.y, k.stepTs.y, s.q.y);
+                    s.q.z = fmaf(s.dir.z, k.stepTs.z, s.q.z);
+                    nSteps++;
+                    bool tap = true;
+                    if (SKIP && s.lastZero) tap = !skipEmpty(sc, k, sOcc, s, nSteps);
+                    if (tap) {
+                        nTaps++;
+                        lastDensity = tex3D<float>(sc.densityTex, s.q.x, s.q.y, s.q.z);
+                        s.lastZero = lastDensity == 0.0f;
+                        s.tau = fmaf(lastDensity, k.c1, s.tau);
+                        if (s.tau > s.tauStar) st = ST_EVENT;
+                    }
+                }
+            }
+            const int nMarch = __popc(__ballot_sync(FULL, st == ST_MARCH));
+            if (nMarch * 32 <= nAlive * job.marchKeep32) break;
+        }
+
+        /* ---- event phase (cloudRadianceMaterials.cu:49-61) ---- */
+        if (st == ST_EVENT) {
+            /* cloud.cuh:99: scatterPos = pos - dir * log(xi / T) / sigma, with log(xi / T) = tau - tauStar */
+            const float back = __fdividef(s.tau - s.tauStar, lastDensity * sc.mult);
+            s.q.x = fmaf(-back * s.dir.x, sc.texScale.x, s.q.x);
+            s.q.y = fmaf(-back * s.dir.y, sc.texScale.y, s.q.y);
+            s.q.z = fmaf(-back * s.dir.z, sc.texScale.z, s.q.z);
+            if (!inBoxTs(k, s.q)) {
+                st = ST_DONE;
+            } else {
+                const float cosLightAngle = -dot(sc.light, s.dir);
+                const bool choppedPhase = (job.mode == DS_MODE_SUN_AND_SKY_ALL_SCATTER) ? (s.depth != 1) : (job.mode == DS_MODE_SUN_MULTIPLE_SCATTER);
+                const float u = (cosLightAngle + 1.0f) * 0.5f;
+                const float phase = choppedPhase ? tex1dSoft(sChopped, u) : tex1dSoft(sc.mie, u);
+                const float tsun = tex3D<float>(sc.inscatterTex, s.q.x, s.q.y, s.q.z);
+                s.rad = fmaf(tsun, phase, s.rad);
+                nEvents++;
+                if (job.mode == DS_MODE_SUN_SINGLE_SCATTER) {
+                    st = ST_DONE;
+                } else {
+                    s.dir = newDirectionFast(sCdf, sGuide, s.seed, s.dir);
+                    st = loopTopFast(k, s);
+                }
+            }
+        }
+    }
+
+    unsigned long long c[5] = {nPaths, nEvents, nSteps, nTaps, nNonfinite};
+#pragma unroll
+    for (int i = 0; i < 5; i++) {
+        unsigned long long v = c[i];
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(FULL, v, o);
+        if (lane == 0 && v) atomicAdd(job.stats + i, v);
+    }
+}
+
+template <>
+cudaError_t KernelSet<true>::trace(const DevScene& sc, const TraceJob& job, const LaunchConfig& cfg, cudaStream_t st)
+{
+    if (cfg.variant == 1) return traceGeneric<true>(sc, job, cfg, st);
+    const size_t smem = (size_t)(2 * MIE_N) * 4 + (size_t)(GUIDE_N + 2) * 2 + (size_t)(cfg.skipEmpty ? sc.occWords : 0) * 4;
+    const int threads = cfg.blockThreads > 640 ? 640 : cfg.blockThreads;
+    const unsigned long long wantBlocks = (job.total + threads - 1) / threads;
+    const unsigned long long maxBlocks = (unsigned long long)cfg.smCount * cfg.blocksPerSm;
+    const int blocks = (int)(wantBlocks < maxBlocks ? (wantBlocks ? wantBlocks : 1) : maxBlocks);
+    cudaError_t e;
+    if (cfg.skipEmpty) {
+        e = cudaFuncSetAttribute(k_trace_fast<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        k_trace_fast<true><<<blocks, threads, smem, st>>>(sc, job);
+    } else {
+        e = cudaFuncSetAttribute(k_trace_fast<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        k_trace_fast<false><<<blocks, threads, smem, st>>>(sc, job);
+    }
+    return cudaGetLastError();
+}
 
 template struct KernelSet<true>;
 
