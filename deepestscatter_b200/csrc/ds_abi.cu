@@ -333,6 +333,10 @@ static int runTrace(DsContext* ctx, TraceJob& job)
     job.marchKeepQuarters = ctx->opt["march_keep_quarters"];
     job.marchMaxIters = ctx->opt["march_max_iters"];
     job.marchKeep32 = ctx->opt["march_keep32"];
+    job.regenMin = ctx->opt["regen_min"];
+    job.skipMin = ctx->opt["skip_min"];
+    job.skipKeep = ctx->opt["skip_keep"];
+    job.skipMaxIters = ctx->opt["skip_max_iters"];
     DS_CUDA(ctx, cudaMemsetAsync(ctx->queue, 0, sizeof(unsigned long long), ctx->stream));
     const LaunchConfig cfg = launchConfig(ctx);
     const bool prof = ctx->opt["profile_events"] != 0;
@@ -404,12 +408,16 @@ int ds_context_create(int device, DsContext** out)
     }
     ctx->opt["precision"] = DS_PRECISION_FAST;
     ctx->opt["variant"] = 0;
-    ctx->opt["block_threads"] = 512;
+    ctx->opt["block_threads"] = 640;
     ctx->opt["blocks_per_sm"] = 2;
     ctx->opt["skip_empty"] = 1;
     ctx->opt["march_keep_quarters"] = 2;
     ctx->opt["march_max_iters"] = 64;
-    ctx->opt["march_keep32"] = 6;
+    ctx->opt["march_keep32"] = 12;
+    ctx->opt["regen_min"] = 8;
+    ctx->opt["skip_min"] = 8;
+    ctx->opt["skip_keep"] = 4;
+    ctx->opt["skip_max_iters"] = 32;
     ctx->opt["staging_subframes"] = 16;
     ctx->opt["stream_offset"] = 0;
     ctx->opt["profile_events"] = 0;

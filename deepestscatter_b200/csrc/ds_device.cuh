@@ -104,7 +104,7 @@ struct DevScene {
     const uint16_t* guide;
 };
 
-constexpr int GUIDE_N = 1024;
+constexpr int GUIDE_N = 4096;
 
 /* ---- CU/random.cuh ---- */
 

@@ -26,6 +26,10 @@ struct TraceJob {
     int marchKeepQuarters;      /* generic kernel: leave the march phase when marching*4 <= alive*q */
     int marchKeep32;            /* fast kernel: leave the march phase when marching*32 <= alive*k */
     int marchMaxIters;
+    int regenMin;      /* fast kernel: regenerate when at least this many lanes of the warp are free */
+    int skipMin;       /* fast kernel: enter the empty-space phase with at least this many lanes */
+    int skipKeep;      /* ... and leave it when fewer remain (and other lanes have work) */
+    int skipMaxIters;
     /* JOB_RENDER: item = (subframe, 8x4 pixel tile, pixel in tile) */
     float eye[3], U[3], V[3], W[3];
     int width, height, tilesX;

@@ -9,8 +9,8 @@
  *   - the path marches in TEXTURE space (q = pos * textureScale), so a tap is one TEX instruction;
  *   - transmittance is carried as optical depth: tau += sigma*step and the collision test xi > exp(-tau)
  *     becomes tau > -ln(xi); one logarithm per free flight instead of one exponential per march step;
- *   - empty space: when the last tap returned exactly 0, the lane looks up the occupancy bit of its tap cell
- *     (shared memory) and, if the cell is empty, the Chebyshev distance to the nearest occupied cell; it
+ *   - empty space: a lane whose tap returned exactly 0 (and every new path) looks up the occupancy bit of its
+ *     tap cell (shared memory) and, if the cell is empty, the Chebyshev distance to the nearest occupied cell; it
  *     then advances k whole march steps at once, k chosen so that every skipped tap lies in cells that are
  *     known to be empty.  Skipped steps read density 0, i.e. tau and the collision test are unchanged;
  *     the step counter still advances by k (the reference algorithm performs those steps);
@@ -33,7 +33,6 @@ struct FastState {
     uint32_t seed;
     int depth;
     unsigned long long out;
-    bool lastZero; /* the previous density tap returned exactly 0 (or the flight has just started outside the cloud) */
 };
 
 struct FastConsts {
@@ -97,7 +96,7 @@ __device__ __forceinline__ int loopTopFast(const FastConsts& k, FastState& s)
     return ST_MARCH;
 }
 
-/* The tap at q is about to be taken and the previous one read 0.  If the tap cell is empty, skip the tap and
+/* The tap at q is about to be taken.  If the tap cell is empty, skip the tap and
  * advance as many whole steps as stay inside the cube of cells known to be empty.  Returns true when the tap
  * is skipped. */
 __device__ __forceinline__ bool skipEmpty(const DevScene& sc, const FastConsts& k, const uint32_t* sOcc, FastState& s, uint32_t& nSteps)
@@ -181,7 +180,6 @@ __device__ __forceinline__ int beginItemFast(const DevScene& sc, const FastConst
     s.dir = normalize<true>(d);
     s.seed = tea4(val0, stream);
     s.depth = 0;
-    s.lastZero = true;
     if (job.mode == DS_MODE_SUN_MULTIPLE_SCATTER) s.dir = newDirectionFast(sCdf, sGuide, s.seed, s.dir);
     return loopTopFast(k, s);
 }
@@ -202,6 +200,22 @@ __device__ __forceinline__ void writeResultFast(const DevScene& sc, const TraceJ
     }
 }
 
+/* lane states of k_trace_fast */
+enum FastLaneState { F_IDLE = 0, F_SKIP = 1, F_MARCH = 2, F_EVENT = 3, F_DONE = 4 };
+
+/*
+ * Warp-level schedule.  Each lane owns one path; a warp cycles through four phases and runs a phase only when
+ * enough of its lanes want it, so the (long, divergent) code of each phase executes with many lanes active:
+ *   A  retire + regenerate   lanes whose path ended write their sample and pull the next work item from the
+ *                            device queue (one warp-aggregated atomic); runs when >= regenMin lanes are free
+ *   B  empty-space phase     lanes travelling through empty cells (every new path starts here, and paths
+ *                            leaving the cloud return here): step, test the tap cell, jump; runs when >= skipMin
+ *                            lanes are in it
+ *   C  march phase           lanes inside the cloud: step + density tap + collision test
+ *   D  event phase           lanes that collided: next-event estimate + new direction
+ * A waiting lane costs nothing but its slot; a phase entered with two lanes costs the whole warp its full
+ * instruction stream, which is what the thresholds avoid.  Thresholds are ignored when nothing else can run.
+ */
 template <bool SKIP>
 __global__ void __launch_bounds__(640, 2) k_trace_fast(const DevScene sc, const TraceJob job)
 {
@@ -215,9 +229,7 @@ __global__ void __launch_bounds__(640, 2) k_trace_fast(const DevScene sc, const 
         sCdf[i] = sc.cdf[i];
     }
     for (int i = threadIdx.x; i <= GUIDE_N; i += blockDim.x) sGuide[i] = sc.guide[i];
-    if (SKIP) {
-        for (int i = threadIdx.x; i < sc.occWords; i += blockDim.x) sOcc[i] = sc.occ[i];
-    }
+    for (int i = threadIdx.x; i < sc.occWords; i += blockDim.x) sOcc[i] = sc.occ[i];
     __syncthreads();
 
     FastConsts k;
@@ -238,77 +250,115 @@ __global__ void __launch_bounds__(640, 2) k_trace_fast(const DevScene sc, const 
     s.seed = 0;
     s.depth = 0;
     s.out = 0;
-    s.lastZero = true;
-    int st = ST_IDLE;
+    int st = F_IDLE;
     bool exhausted = false;
     uint32_t nPaths = 0, nEvents = 0, nSteps = 0, nTaps = 0, nNonfinite = 0;
     float lastDensity = 0.0f;
 
     for (;;) {
-        /* ---- finish + regenerate ---- */
-        if (st == ST_DONE) {
-            writeResultFast(sc, job, s, nNonfinite);
-            st = ST_IDLE;
-        }
-        const unsigned need = __ballot_sync(FULL, st == ST_IDLE && !exhausted);
-        if (need) {
-            unsigned long long base = 0;
-            const int leader = __ffs(need) - 1;
-            if ((int)lane == leader) base = atomicAdd(job.queue, (unsigned long long)__popc(need));
-            base = __shfl_sync(FULL, base, leader);
-            if (st == ST_IDLE && !exhausted) {
-                const unsigned long long idx = base + __popc(need & laneLt);
-                if (idx >= job.total) {
-                    exhausted = true;
-                } else {
-                    bool valid;
-                    st = beginItemFast<SKIP>(sc, k, job, sCdf, sGuide, idx, s, valid);
-                    if (valid) nPaths++;
-                }
-            }
-        }
-        const unsigned alive = __ballot_sync(FULL, st != ST_IDLE);
-        if (alive == 0u) {
-            if (__all_sync(FULL, exhausted)) break;
-            continue;
-        }
-        const int nAlive = __popc(alive);
+        unsigned mBusy = __ballot_sync(FULL, st == F_MARCH || st == F_EVENT);
+        unsigned mSkip = __ballot_sync(FULL, st == F_SKIP);
+        unsigned mFree = __ballot_sync(FULL, st == F_DONE || (st == F_IDLE && !exhausted));
 
-        /* ---- march phase (CU/cloud.cuh:87-104) ---- */
+        /* ---- A: retire + regenerate ---- */
+        if (mFree && (__popc(mFree) >= job.regenMin || (mBusy == 0u && (mSkip == 0u || __popc(mSkip) < job.skipMin)))) {
 #pragma unroll 1
-        for (int it = 0; it < job.marchMaxIters; ++it) {
-            if (st == ST_MARCH) {
-                if (!inBoxTs(k, s.q)) {
-                    st = ST_DONE;
-                } else {
-                    s.q.x = fmaf(s.dir.x, k.stepTs.x, s.q.x);
-                    s.q.y = fmaf(s.dir.y, k.stepTs.y, s.q.y);
-                    s.q.z = fmaf(s.dir.z, k.stepTs.z, s.q.z);
-                    nSteps++;
-                    bool tap = true;
-                    if (SKIP && s.lastZero) tap = !skipEmpty(sc, k, sOcc, s, nSteps);
-                    if (tap) {
-                        nTaps++;
-                        lastDensity = tex3D<float>(sc.densityTex, s.q.x, s.q.y, s.q.z);
-                        s.lastZero = lastDensity == 0.0f;
-                        s.tau = fmaf(lastDensity, k.c1, s.tau);
-                        if (s.tau > s.tauStar) st = ST_EVENT;
+            for (int r = 0; r < 4; ++r) {
+                if (st == F_DONE) {
+                    writeResultFast(sc, job, s, nNonfinite);
+                    st = F_IDLE;
+                }
+                const unsigned need = __ballot_sync(FULL, st == F_IDLE && !exhausted);
+                if (need == 0u) break;
+                unsigned long long base = 0;
+                const int leader = __ffs(need) - 1;
+                if ((int)lane == leader) base = atomicAdd(job.queue, (unsigned long long)__popc(need));
+                base = __shfl_sync(FULL, base, leader);
+                if (st == F_IDLE && !exhausted) {
+                    const unsigned long long idx = base + __popc(need & laneLt);
+                    if (idx >= job.total) {
+                        exhausted = true;
+                    } else {
+                        bool valid;
+                        const int g = beginItemFast<SKIP>(sc, k, job, sCdf, sGuide, idx, s, valid);
+                        st = g == ST_MARCH ? (SKIP ? F_SKIP : F_MARCH) : (g == ST_DONE ? F_DONE : F_IDLE);
+                        if (valid) nPaths++;
                     }
                 }
+                mFree = __ballot_sync(FULL, st == F_DONE || (st == F_IDLE && !exhausted));
+                if (__popc(mFree) < job.regenMin) break;
             }
-            const int nMarch = __popc(__ballot_sync(FULL, st == ST_MARCH));
-            if (nMarch * 32 <= nAlive * job.marchKeep32) break;
+            mSkip = __ballot_sync(FULL, st == F_SKIP);
+            mBusy = __ballot_sync(FULL, st == F_MARCH || st == F_EVENT);
+            mFree = __ballot_sync(FULL, st == F_DONE || (st == F_IDLE && !exhausted));
+        }
+        if (mBusy == 0u && mSkip == 0u && mFree == 0u) break; /* every lane idle and the queue exhausted */
+
+        /* ---- B: empty-space phase ---- */
+        if (SKIP && mSkip && (__popc(mSkip) >= job.skipMin || mBusy == 0u)) {
+#pragma unroll 1
+            for (int it = 0; it < job.skipMaxIters; ++it) {
+                if (st == F_SKIP) {
+                    if (!inBoxTs(k, s.q)) {
+                        st = F_DONE;
+                    } else {
+                        s.q.x = fmaf(s.dir.x, k.stepTs.x, s.q.x);
+                        s.q.y = fmaf(s.dir.y, k.stepTs.y, s.q.y);
+                        s.q.z = fmaf(s.dir.z, k.stepTs.z, s.q.z);
+                        nSteps++;
+                        if (!skipEmpty(sc, k, sOcc, s, nSteps)) {
+                            nTaps++;
+                            lastDensity = tex3D<float>(sc.densityTex, s.q.x, s.q.y, s.q.z);
+                            if (lastDensity != 0.0f) {
+                                s.tau = fmaf(lastDensity, k.c1, s.tau);
+                                st = s.tau > s.tauStar ? F_EVENT : F_MARCH;
+                            }
+                        }
+                    }
+                }
+                const int nSkip = __popc(__ballot_sync(FULL, st == F_SKIP));
+                const bool busyNow = __any_sync(FULL, st == F_MARCH || st == F_EVENT);
+                if (nSkip == 0 || (busyNow && nSkip < job.skipKeep)) break;
+            }
         }
 
-        /* ---- event phase (cloudRadianceMaterials.cu:49-61) ---- */
-        if (st == ST_EVENT) {
+        /* ---- C: march phase (CU/cloud.cuh:87-104) ---- */
+        const int nBusy = __popc(__ballot_sync(FULL, st == F_MARCH || st == F_EVENT));
+        if (nBusy) {
+#pragma unroll 1
+            for (int it = 0; it < job.marchMaxIters; ++it) {
+                if (st == F_MARCH) {
+                    if (!inBoxTs(k, s.q)) {
+                        st = F_DONE;
+                    } else {
+                        s.q.x = fmaf(s.dir.x, k.stepTs.x, s.q.x);
+                        s.q.y = fmaf(s.dir.y, k.stepTs.y, s.q.y);
+                        s.q.z = fmaf(s.dir.z, k.stepTs.z, s.q.z);
+                        nSteps++;
+                        nTaps++;
+                        lastDensity = tex3D<float>(sc.densityTex, s.q.x, s.q.y, s.q.z);
+                        if (SKIP && lastDensity == 0.0f) {
+                            st = F_SKIP; /* left the cloud (or a hole in it): continue in the empty-space phase */
+                        } else {
+                            s.tau = fmaf(lastDensity, k.c1, s.tau);
+                            if (s.tau > s.tauStar) st = F_EVENT;
+                        }
+                    }
+                }
+                const int nMarch = __popc(__ballot_sync(FULL, st == F_MARCH));
+                if (nMarch * 32 <= nBusy * job.marchKeep32) break;
+            }
+        }
+
+        /* ---- D: event phase (cloudRadianceMaterials.cu:49-61) ---- */
+        if (st == F_EVENT) {
             /* cloud.cuh:99: scatterPos = pos - dir * log(xi / T) / sigma, with log(xi / T) = tau - tauStar */
             const float back = __fdividef(s.tau - s.tauStar, lastDensity * sc.mult);
             s.q.x = fmaf(-back * s.dir.x, sc.texScale.x, s.q.x);
             s.q.y = fmaf(-back * s.dir.y, sc.texScale.y, s.q.y);
             s.q.z = fmaf(-back * s.dir.z, sc.texScale.z, s.q.z);
             if (!inBoxTs(k, s.q)) {
-                st = ST_DONE;
+                st = F_DONE;
             } else {
                 const float cosLightAngle = -dot(sc.light, s.dir);
                 const bool choppedPhase = (job.mode == DS_MODE_SUN_AND_SKY_ALL_SCATTER) ? (s.depth != 1) : (job.mode == DS_MODE_SUN_MULTIPLE_SCATTER);
@@ -318,10 +368,11 @@ __global__ void __launch_bounds__(640, 2) k_trace_fast(const DevScene sc, const 
                 s.rad = fmaf(tsun, phase, s.rad);
                 nEvents++;
                 if (job.mode == DS_MODE_SUN_SINGLE_SCATTER) {
-                    st = ST_DONE;
+                    st = F_DONE;
                 } else {
                     s.dir = newDirectionFast(sCdf, sGuide, s.seed, s.dir);
-                    st = loopTopFast(k, s);
+                    const int g = loopTopFast(k, s);
+                    st = g == ST_MARCH ? F_MARCH : F_DONE;
                 }
             }
         }
@@ -340,7 +391,7 @@ template <>
 cudaError_t KernelSet<true>::trace(const DevScene& sc, const TraceJob& job, const LaunchConfig& cfg, cudaStream_t st)
 {
     if (cfg.variant == 1) return traceGeneric<true>(sc, job, cfg, st);
-    const size_t smem = (size_t)(2 * MIE_N) * 4 + (size_t)(GUIDE_N + 2) * 2 + (size_t)(cfg.skipEmpty ? sc.occWords : 0) * 4;
+    const size_t smem = (size_t)(2 * MIE_N) * 4 + (size_t)(GUIDE_N + 2) * 2 + (size_t)sc.occWords * 4;
     const int threads = cfg.blockThreads > 640 ? 640 : cfg.blockThreads;
     const unsigned long long wantBlocks = (job.total + threads - 1) / threads;
     const unsigned long long maxBlocks = (unsigned long long)cfg.smCount * cfg.blocksPerSm;
