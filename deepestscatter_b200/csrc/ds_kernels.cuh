@@ -245,7 +245,7 @@ template <bool FAST>
 cudaError_t traceGeneric(const DevScene& sc, const TraceJob& job, const LaunchConfig& cfg, cudaStream_t st)
 {
     const size_t smem = (size_t)(2 * MIE_N + (cfg.skipEmpty ? sc.occWords : 0)) * 4;
-    const int threads = cfg.blockThreads;
+    const int threads = cfg.blockThreads > 512 ? 512 : cfg.blockThreads; /* __launch_bounds__(512, 2) */
     unsigned long long wantBlocks = (job.total + threads - 1) / threads;
     const unsigned long long maxBlocks = (unsigned long long)cfg.smCount * cfg.blocksPerSm;
     const int blocks = (int)(wantBlocks < maxBlocks ? (wantBlocks ? wantBlocks : 1) : maxBlocks);

@@ -10,9 +10,9 @@
  *   - transmittance is carried as optical depth: tau += sigma*step and the collision test xi > exp(-tau)
  *     becomes tau > -ln(xi); one logarithm per free flight instead of one exponential per march step;
  *   - empty space: a lane whose tap returned exactly 0 (and every new path) looks up the occupancy bit of its
- *     tap cell (shared memory) and, if the cell is empty, the Chebyshev distance to the nearest occupied cell; it
- *     then advances k whole march steps at once, k chosen so that every skipped tap lies in cells that are
- *     known to be empty.  Skipped steps read density 0, i.e. tau and the collision test are unchanged;
+ *     tap cell (shared memory) and, if the cell is empty, walks the ray through the occupancy cells with a 3-D
+ *     DDA until the next occupied cell; it then advances k whole march steps at once, k chosen so that every
+ *     skipped tap lies in cells that are known to be empty.  Skipped steps read density 0, i.e. tau and the collision test are unchanged;
  *     the step counter still advances by k (the reference algorithm performs those steps);
  *   - the 16-step bisection of the chopped-Mie CDF (cloud.cuh:167-178) is replaced by the closed-form
  *     inverse of the same piecewise-linear CDF: guide table -> short binary search for the table cell ->
@@ -78,16 +78,28 @@ __device__ __forceinline__ V3 newDirectionFast(const float* sCdf, const uint16_t
     const float val = rnd(seed);
     const float cosTheta = invertCdf(sCdf, sGuide, val);
     const float phi = rnd(seed) * (PI_F * 2.0f);
-    const float sinTheta = sqrtf(fmaxf(1.0f - cosTheta * cosTheta, 0.0f));
+    const float s2 = fmaxf(fmaf(-cosTheta, cosTheta, 1.0f), 0.0f);
+    const float sinTheta = s2 * rsqrtf(fmaxf(s2, 1.0e-30f));
     float s, c;
     __sincosf(phi, &s, &c);
     V3 d = onbInverseTransform<true>(prev, mk(sinTheta * c, sinTheta * s, cosTheta));
     return d * rsqrtf(dot(d, d));
 }
 
+/* 4096-entry table, linear, clamp-to-edge, u in [0, 1] (tex1D semantics of the Mie samplers) */
+__device__ __forceinline__ float tableLerp(const float* table, float u)
+{
+    const float x = fminf(fmaxf(fmaf(u, (float)MIE_N, -0.5f), 0.0f), (float)(MIE_N - 1));
+    const int i = (int)x;
+    const float f = x - (float)i;
+    const float a = table[i], b = table[min(i + 1, MIE_N - 1)];
+    return fmaf(f, b - a, a);
+}
+
+template <bool CHECK_BOX>
 __device__ __forceinline__ int loopTopFast(const FastConsts& k, FastState& s)
 {
-    if (!inBoxTs(k, s.q)) return ST_DONE;
+    if (CHECK_BOX && !inBoxTs(k, s.q)) return ST_DONE;
     s.depth++;
     if (s.depth == MAX_DEPTH) return ST_DONE;
     const float xi = rnd(s.seed);
@@ -96,32 +108,68 @@ __device__ __forceinline__ int loopTopFast(const FastConsts& k, FastState& s)
     return ST_MARCH;
 }
 
-/* The tap at q is about to be taken.  If the tap cell is empty, skip the tap and
- * advance as many whole steps as stay inside the cube of cells known to be empty.  Returns true when the tap
- * is skipped. */
+/* The tap at q is about to be taken.  If its cell is empty the tap is skipped (it would read 0) and the lane
+ * walks the ray through the occupancy cells with a 3-D DDA until the next cell is occupied or the grid ends; it
+ * then advances the largest whole number of march steps whose taps all lie in the empty cells just walked.
+ * Coordinates: x = u*N - 0.5 is the voxel coordinate whose floor is the low corner of the trilinear footprint;
+ * the occupancy bit of cell c covers voxels [c*2^s, c*2^s + 2^s], i.e. every footprint with floor(x) in c.
+ * Returns true when the tap is skipped. */
 __device__ __forceinline__ bool skipEmpty(const DevScene& sc, const FastConsts& k, const uint32_t* sOcc, FastState& s, uint32_t& nSteps)
 {
     const float x = fmaf(s.q.x, k.nxf, -0.5f), y = fmaf(s.q.y, k.nyf, -0.5f), z = fmaf(s.q.z, k.nzf, -0.5f);
-    const int cx = min(max(__float2int_rd(x), 0), sc.nx - 1) >> sc.occShift;
-    const int cy = min(max(__float2int_rd(y), 0), sc.ny - 1) >> sc.occShift;
-    const int cz = min(max(__float2int_rd(z), 0), sc.nz - 1) >> sc.occShift;
-    const int cell = (cz * sc.ocy + cy) * sc.ocx + cx;
+    const int fx = __float2int_rd(x), fy = __float2int_rd(y), fz = __float2int_rd(z);
+    int cx = min(max(fx, 0), sc.nx - 1) >> sc.occShift;
+    int cy = min(max(fy, 0), sc.ny - 1) >> sc.occShift;
+    int cz = min(max(fz, 0), sc.nz - 1) >> sc.occShift;
+    int cell = (cz * sc.ocy + cy) * sc.ocx + cx;
     if ((sOcc[cell >> 5] >> (cell & 31)) & 1u) return false;
-    const int d = __ldg(sc.cellDist + cell); /* >= 1: every cell within Chebyshev distance d-1 is empty */
+    /* outside the grid the footprint is clamped to edge voxels: no walk, just skip this tap */
+    if ((unsigned)fx >= (unsigned)(sc.nx - 1) || (unsigned)fy >= (unsigned)(sc.ny - 1) || (unsigned)fz >= (unsigned)(sc.nz - 1)) return true;
     const float cs = (float)(1 << sc.occShift);
-    const float eps = 0.02f;
-    /* admissible range of the voxel coordinate x = u*N - 0.5 of a tap: its floor must stay inside the empty cells */
-    const float lox = fmaxf((float)(cx - d + 1) * cs, -0.5f) + eps, hix = fminf((float)(cx + d) * cs, k.nxf - 0.5f) - eps;
-    const float loy = fmaxf((float)(cy - d + 1) * cs, -0.5f) + eps, hiy = fminf((float)(cy + d) * cs, k.nyf - 0.5f) - eps;
-    const float loz = fmaxf((float)(cz - d + 1) * cs, -0.5f) + eps, hiz = fminf((float)(cz + d) * cs, k.nzf - 0.5f) - eps;
-    const float vx = s.dir.x * k.stepTs.x * k.nxf, vy = s.dir.y * k.stepTs.y * k.nyf, vz = s.dir.z * k.stepTs.z * k.nzf;
-    const float big = 1.0e9f;
-    const float tx = vx > 0.0f ? __fdividef(hix - x, vx) : (vx < 0.0f ? __fdividef(lox - x, vx) : big);
-    const float ty = vy > 0.0f ? __fdividef(hiy - y, vy) : (vy < 0.0f ? __fdividef(loy - y, vy) : big);
-    const float tz = vz > 0.0f ? __fdividef(hiz - z, vz) : (vz < 0.0f ? __fdividef(loz - z, vz) : big);
-    const float t = fminf(fminf(tx, ty), fminf(tz, 4096.0f));
-    if (t >= 1.0f) {
-        const float kf = floorf(t);
+    const float vx = s.dir.x * k.stepTs.x * k.nxf, vy = s.dir.y * k.stepTs.y * k.nyf, vz = s.dir.z * k.stepTs.z * k.nzf; /* voxels per step */
+    const float big = 3.0e38f;
+    const float ix = fabsf(vx) > 1e-12f ? __fdividef(1.0f, vx) : big, iy = fabsf(vy) > 1e-12f ? __fdividef(1.0f, vy) : big,
+                iz = fabsf(vz) > 1e-12f ? __fdividef(1.0f, vz) : big;
+    const int sx = vx > 0.0f ? 1 : -1, sy = vy > 0.0f ? 1 : -1, sz = vz > 0.0f ? 1 : -1;
+    /* steps until the ray crosses into the neighbouring cell along each axis, and per-cell increments */
+    float tx = fabsf(ix) >= big ? big : ((float)(cx + (sx > 0 ? 1 : 0)) * cs - x) * ix;
+    float ty = fabsf(iy) >= big ? big : ((float)(cy + (sy > 0 ? 1 : 0)) * cs - y) * iy;
+    float tz = fabsf(iz) >= big ? big : ((float)(cz + (sz > 0 ? 1 : 0)) * cs - z) * iz;
+    const float dtx = fabsf(ix) >= big ? 0.0f : cs * fabsf(ix), dty = fabsf(iy) >= big ? 0.0f : cs * fabsf(iy),
+                dtz = fabsf(iz) >= big ? 0.0f : cs * fabsf(iz);
+    const int strideY = sc.ocx, strideZ = sc.ocx * sc.ocy;
+    float t = 0.0f, margin = 0.0f;
+#pragma unroll 1
+    for (int it = 0; it < 256; ++it) {
+        const bool ax = tx <= ty && tx <= tz;
+        const bool ay = !ax && ty <= tz;
+        if (ax) {
+            t = tx;
+            margin = fabsf(ix);
+            tx += dtx;
+            cx += sx;
+            cell += sx;
+            if ((unsigned)cx >= (unsigned)sc.ocx) break;
+        } else if (ay) {
+            t = ty;
+            margin = fabsf(iy);
+            ty += dty;
+            cy += sy;
+            cell += sy * strideY;
+            if ((unsigned)cy >= (unsigned)sc.ocy) break;
+        } else {
+            t = tz;
+            margin = fabsf(iz);
+            tz += dtz;
+            cz += sz;
+            cell += sz * strideZ;
+            if ((unsigned)cz >= (unsigned)sc.ocz) break;
+        }
+        if ((sOcc[cell >> 5] >> (cell & 31)) & 1u) break;
+    }
+    /* stay 0.01 voxel short of the cell boundary that stopped the walk */
+    const float kf = floorf(fminf(t - 0.01f * margin, 8192.0f));
+    if (kf >= 1.0f) {
         s.q.x = fmaf(kf * s.dir.x, k.stepTs.x, s.q.x);
         s.q.y = fmaf(kf * s.dir.y, k.stepTs.y, s.q.y);
         s.q.z = fmaf(kf * s.dir.z, k.stepTs.z, s.q.z);
@@ -181,7 +229,7 @@ __device__ __forceinline__ int beginItemFast(const DevScene& sc, const FastConst
     s.seed = tea4(val0, stream);
     s.depth = 0;
     if (job.mode == DS_MODE_SUN_MULTIPLE_SCATTER) s.dir = newDirectionFast(sCdf, sGuide, s.seed, s.dir);
-    return loopTopFast(k, s);
+    return loopTopFast<true>(k, s);
 }
 
 __device__ __forceinline__ void writeResultFast(const DevScene& sc, const TraceJob& job, const FastState& s, uint32_t& nonfinite)
@@ -363,7 +411,7 @@ __global__ void __launch_bounds__(640, 2) k_trace_fast(const DevScene sc, const 
                 const float cosLightAngle = -dot(sc.light, s.dir);
                 const bool choppedPhase = (job.mode == DS_MODE_SUN_AND_SKY_ALL_SCATTER) ? (s.depth != 1) : (job.mode == DS_MODE_SUN_MULTIPLE_SCATTER);
                 const float u = (cosLightAngle + 1.0f) * 0.5f;
-                const float phase = choppedPhase ? tex1dSoft(sChopped, u) : tex1dSoft(sc.mie, u);
+                const float phase = choppedPhase ? tableLerp(sChopped, u) : tableLerp(sc.mie, u);
                 const float tsun = tex3D<float>(sc.inscatterTex, s.q.x, s.q.y, s.q.z);
                 s.rad = fmaf(tsun, phase, s.rad);
                 nEvents++;
@@ -371,7 +419,7 @@ __global__ void __launch_bounds__(640, 2) k_trace_fast(const DevScene sc, const 
                     st = F_DONE;
                 } else {
                     s.dir = newDirectionFast(sCdf, sGuide, s.seed, s.dir);
-                    const int g = loopTopFast(k, s);
+                    const int g = loopTopFast<false>(k, s); /* q is the scatter position just verified in-box */
                     st = g == ST_MARCH ? F_MARCH : F_DONE;
                 }
             }
