@@ -56,6 +56,15 @@ struct DsContext {
     float *columns = nullptr, *average = nullptr;
     uint32_t* unconv = nullptr;
 
+    /* primary-ray cache of the FAST flavour (k_primary_prepass): valid for one (volume, camera, frame size) */
+    uint32_t *entrySteps = nullptr, *hitList = nullptr;
+    unsigned long long* primaryCounts = nullptr; /* device: nHit, missSteps */
+    bool primaryValid = false;
+    DsCamera primaryCam{};
+    uint32_t nHit = 0;
+    unsigned long long missSteps = 0;
+    unsigned long long extraPaths = 0, extraSteps = 0; /* work of untraced (missing) pixels, added to the counters */
+
     /* counters + queue */
     unsigned long long* stats = nullptr; /* CNT_COUNT */
     unsigned long long* queue = nullptr;
@@ -138,6 +147,12 @@ static void freeFrame(DsContext* ctx)
     ctx->unconv = nullptr;
     ctx->stagingSubframes = 0;
     ctx->width = ctx->height = 0;
+    cudaFree(ctx->entrySteps);
+    cudaFree(ctx->hitList);
+    cudaFree(ctx->primaryCounts);
+    ctx->entrySteps = ctx->hitList = nullptr;
+    ctx->primaryCounts = nullptr;
+    ctx->primaryValid = false;
 }
 
 /* DG/Mie.cpp:8206-8282: phase samplers = table / mean(table); integral = running sum of table / sum(table) */
@@ -304,6 +319,7 @@ static int beginVolume(DsContext* ctx, int nx, int ny, int nz)
 {
     if (nx <= 0 || ny <= 0 || nz <= 0) DS_FAIL(ctx, DS_ERR_INVALID, "bad volume size %dx%dx%d", nx, ny, nz);
     freeVolume(ctx);
+    ctx->primaryValid = false;
     uint8_t* p = nullptr;
     DS_CUDA(ctx, cudaMalloc(&p, (size_t)nx * ny * nz));
     ctx->levels.push_back(p);
@@ -421,6 +437,7 @@ int ds_context_create(int device, DsContext** out)
     ctx->opt["staging_subframes"] = 16;
     ctx->opt["stream_offset"] = 0;
     ctx->opt["profile_events"] = 0;
+    ctx->opt["primary_cache"] = 1;
     ds_scene_params_default(&ctx->params);
     bool ok = cudaMalloc(&ctx->stats, CNT_COUNT * sizeof(unsigned long long)) == cudaSuccess &&
               cudaMalloc(&ctx->queue, sizeof(unsigned long long)) == cudaSuccess &&
@@ -523,9 +540,9 @@ int ds_get_counters(DsContext* ctx, DsCounters* out)
     unsigned long long h[CNT_COUNT];
     DS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     DS_CUDA(ctx, cudaMemcpy(h, ctx->stats, sizeof(h), cudaMemcpyDeviceToHost));
-    out->paths = h[CNT_PATHS];
+    out->paths = h[CNT_PATHS] + ctx->extraPaths;
     out->events = h[CNT_EVENTS];
-    out->steps = h[CNT_STEPS];
+    out->steps = h[CNT_STEPS] + ctx->extraSteps;
     out->density_taps = h[CNT_TAPS];
     out->nonfinite = h[CNT_NONFINITE];
     return DS_OK;
@@ -538,6 +555,7 @@ int ds_reset_counters(DsContext* ctx)
     DS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     ctx->launches = 0;
     ctx->traceEventsUsed = 0;
+    ctx->extraPaths = ctx->extraSteps = 0;
     return DS_OK;
 }
 
@@ -665,6 +683,7 @@ int ds_scene_set(DsContext* ctx, const DsSceneParams* p)
                               p->sample_step != ctx->params.sample_step;
     ctx->params = *p;
     ctx->sceneSet = true;
+    ctx->primaryValid = false; /* entry steps are counted in units of sample_step */
     if (lightChanged) ctx->baked = false;
     computeDerived(ctx);
     return DS_OK;
@@ -766,6 +785,9 @@ int ds_frame_create(DsContext* ctx, int width, int height)
     DS_CUDA(ctx, cudaMalloc(&ctx->columns, (size_t)width * sizeof(float)));
     DS_CUDA(ctx, cudaMalloc(&ctx->average, sizeof(float)));
     DS_CUDA(ctx, cudaMalloc(&ctx->unconv, sizeof(uint32_t)));
+    DS_CUDA(ctx, cudaMalloc(&ctx->entrySteps, px * sizeof(uint32_t)));
+    DS_CUDA(ctx, cudaMalloc(&ctx->hitList, px * sizeof(uint32_t)));
+    DS_CUDA(ctx, cudaMalloc(&ctx->primaryCounts, 2 * sizeof(unsigned long long)));
     ctx->width = width;
     ctx->height = height;
     return ds_frame_clear(ctx);
@@ -813,6 +835,54 @@ static void fillRenderJob(DsContext* ctx, TraceJob& job, const DsCamera* cam, Ds
     job.staging = ctx->staging;
 }
 
+/* The primary-ray cache applies to the optimised FAST kernel for estimators that follow the camera ray
+ * (all-order and single scatter; the multiple-scatter estimator resamples the direction first). */
+static bool usePrimaryCache(DsContext* ctx, DsMode mode)
+{
+    return ctx->opt["precision"] == DS_PRECISION_FAST && ctx->opt["variant"] == 0 && ctx->opt["skip_empty"] != 0 &&
+           ctx->opt["primary_cache"] != 0 && mode != DS_MODE_SUN_MULTIPLE_SCATTER;
+}
+
+static int ensurePrimary(DsContext* ctx, const DsCamera* cam)
+{
+    if (ctx->primaryValid && memcmp(&ctx->primaryCam, cam, sizeof(DsCamera)) == 0) return DS_OK;
+    DevScene sc;
+    fillDevScene(ctx, sc);
+    TraceJob job;
+    fillRenderJob(ctx, job, cam, DS_MODE_SUN_AND_SKY_ALL_SCATTER, 1, 1);
+    DS_CUDA(ctx, cudaMemsetAsync(ctx->primaryCounts, 0, 2 * sizeof(unsigned long long), ctx->stream));
+    DS_CUDA(ctx, KernelSet<true>::primaryPrepass(sc, job, ctx->entrySteps, ctx->hitList, ctx->primaryCounts, ctx->stream));
+    ctx->launches++;
+    unsigned long long h[2];
+    DS_CUDA(ctx, cudaMemcpyAsync(h, ctx->primaryCounts, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+    DS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->nHit = (uint32_t)h[0];
+    ctx->missSteps = h[1];
+    ctx->primaryCam = *cam;
+    ctx->primaryValid = true;
+    return DS_OK;
+}
+
+/* trace `n` subframes starting at `first` into the staging buffer */
+static int traceSubframes(DsContext* ctx, const DsCamera* cam, DsMode mode, uint32_t first, uint32_t n, bool* cached)
+{
+    TraceJob job;
+    fillRenderJob(ctx, job, cam, mode, first, n);
+    *cached = usePrimaryCache(ctx, mode);
+    if (*cached) {
+        int rc = ensurePrimary(ctx, cam);
+        if (rc) return rc;
+        job.hitList = ctx->hitList;
+        job.nHit = ctx->nHit;
+        job.entrySteps = ctx->entrySteps;
+        job.total = (unsigned long long)ctx->nHit * n;
+        ctx->extraPaths += ((unsigned long long)ctx->width * ctx->height - ctx->nHit) * n;
+        ctx->extraSteps += ctx->missSteps * n;
+        if (ctx->nHit == 0) return DS_OK;
+    }
+    return runTrace(ctx, job);
+}
+
 static int checkRender(DsContext* ctx, const DsCamera* cam, DsMode mode)
 {
     int rc = requireScene(ctx, true);
@@ -830,10 +900,13 @@ int ds_render_frame_result(DsContext* ctx, const DsCamera* cam, DsMode mode, uin
     if (rc) return rc;
     rc = ensureStaging(ctx, 1);
     if (rc) return rc;
-    TraceJob job;
-    fillRenderJob(ctx, job, cam, mode, subframe_id, 1);
-    rc = runTrace(ctx, job);
+    bool cached;
+    rc = traceSubframes(ctx, cam, mode, subframe_id, 1, &cached);
     if (rc) return rc;
+    if (cached) {
+        DS_CUDA(ctx, launchFillMissing(ctx->staging, ctx->entrySteps, (size_t)ctx->width * ctx->height, ctx->stream));
+        ctx->launches++;
+    }
     if (frame_result_out) {
         DS_CUDA(ctx, cudaMemcpyAsync(frame_result_out, ctx->staging, (size_t)ctx->width * ctx->height * sizeof(float4), cudaMemcpyDeviceToHost,
                                      ctx->stream));
@@ -854,11 +927,11 @@ int ds_render_subframes(DsContext* ctx, const DsCamera* cam, DsMode mode, uint32
     const size_t px = (size_t)ctx->width * ctx->height;
     for (uint32_t done = 0; done < n;) {
         const uint32_t chunk = std::min<uint32_t>(chunkMax, n - done);
-        TraceJob job;
-        fillRenderJob(ctx, job, cam, mode, first_subframe + done, chunk);
-        rc = runTrace(ctx, job);
+        bool cached;
+        rc = traceSubframes(ctx, cam, mode, first_subframe + done, chunk, &cached);
         if (rc) return rc;
-        DS_CUDA(ctx, launchUpdateFrame(ctx->staging, ctx->progressive, ctx->variance, px, first_subframe + done, chunk, ctx->stream));
+        DS_CUDA(ctx, launchUpdateFrame(ctx->staging, cached ? ctx->entrySteps : nullptr, ctx->progressive, ctx->variance, px,
+                                       first_subframe + done, chunk, ctx->stream));
         ctx->launches++;
         done += chunk;
     }

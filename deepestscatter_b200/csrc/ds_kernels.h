@@ -36,6 +36,11 @@ struct TraceJob {
     uint32_t firstSubframe;
     unsigned long long itemsPerSubframe;
     float4* staging; /* [n][H][W] */
+    /* primary-ray cache (FAST flavour): pixels whose camera ray reaches an occupied cell, and the
+     * number of march steps each of them spends in empty cells before that */
+    const uint32_t* hitList;
+    uint32_t nHit;
+    const uint32_t* entrySteps; /* [H*W], ENTRY_MISS for pixels that never reach an occupied cell */
     /* JOB_PATHS */
     const float* origins;
     const float* dirs;
@@ -48,6 +53,8 @@ struct TraceJob {
     uint32_t frame0;
     float* xOut; /* [threads][launches] */
 };
+
+constexpr uint32_t ENTRY_MISS = 0xffffffffu;
 
 struct LevelTable {
     const uint8_t* data[MAX_LEVELS];
@@ -72,6 +79,10 @@ struct LaunchConfig {
 template <bool FAST>
 struct KernelSet {
     static cudaError_t trace(const DevScene& sc, const TraceJob& job, const LaunchConfig& cfg, cudaStream_t st);
+    /* per pixel: entry steps / ENTRY_MISS, compacted list of hitting pixels; counts[0] = nHit, counts[1] = total march
+     * steps the reference algorithm spends on the missing pixels (per subframe) */
+    static cudaError_t primaryPrepass(const DevScene& sc, const TraceJob& cam, uint32_t* entrySteps, uint32_t* hitList,
+                                      unsigned long long* counts, cudaStream_t st);
     static cudaError_t bake(const DevScene& sc, uint8_t* out, int skipEmpty, cudaStream_t st);
     static cudaError_t generatePoints(const DevScene& sc, uint32_t firstIndex, uint32_t n, uint32_t stream, float* pos, float* dir,
                                       unsigned long long* stats, cudaStream_t st);
@@ -84,8 +95,9 @@ cudaError_t launchMip(const uint8_t* prev, int pnx, int pny, int pnz, uint8_t* c
 cudaError_t launchCellDistance(const uint32_t* occBits, int ocx, int ocy, int ocz, uint8_t* dist, uint8_t* tmp, cudaStream_t st);
 cudaError_t launchOccupancy(const uint8_t* density, int nx, int ny, int nz, int shift, int ocx, int ocy, int ocz, uint32_t* bits,
                             cudaStream_t st);
-cudaError_t launchUpdateFrame(const float4* staging, float4* progressive, float4* variance, size_t pixels, uint32_t firstSubframe,
-                              uint32_t n, cudaStream_t st);
+cudaError_t launchUpdateFrame(const float4* staging, const uint32_t* entrySteps, float4* progressive, float4* variance, size_t pixels,
+                              uint32_t firstSubframe, uint32_t n, cudaStream_t st);
+cudaError_t launchFillMissing(float4* staging, const uint32_t* entrySteps, size_t pixels, cudaStream_t st);
 cudaError_t launchTonemap(const float4* progressive, int w, int h, float exposure, float* columns, float* average, uchar4* screen,
                           cudaStream_t st);
 cudaError_t launchUnconverged(const float4* progressive, const float4* variance, size_t pixels, uint32_t subframeId, uint32_t* count,

@@ -15,6 +15,12 @@ cudaError_t KernelSet<false>::trace(const DevScene& sc, const TraceJob& job, con
     return traceGeneric<false>(sc, job, cfg, st);
 }
 
+template <>
+cudaError_t KernelSet<false>::primaryPrepass(const DevScene&, const TraceJob&, uint32_t*, uint32_t*, unsigned long long*, cudaStream_t)
+{
+    return cudaErrorNotSupported; /* the exact flavour marches every step like the reference */
+}
+
 template struct KernelSet<false>;
 
 /* ---- synthetic grid (include/ds_synth.h) ---- */
@@ -152,14 +158,17 @@ __device__ __forceinline__ void welford(float& mean, float& m2, float x, float w
     m2 = m2 + (x - previousMean) * (x - newMean);
 }
 
-__global__ void __launch_bounds__(256) k_update_frame(const float4* __restrict__ staging, float4* __restrict__ progressive,
-                                                      float4* __restrict__ variance, size_t pixels, uint32_t firstSubframe, uint32_t n)
+__global__ void __launch_bounds__(256) k_update_frame(const float4* __restrict__ staging, const uint32_t* __restrict__ entrySteps,
+                                                      float4* __restrict__ progressive, float4* __restrict__ variance, size_t pixels,
+                                                      uint32_t firstSubframe, uint32_t n)
 {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= pixels) return;
     float4 mean = progressive[i], m2 = variance[i];
+    /* pixels whose camera ray never reaches the cloud are not traced: their sample is (0, 0, 0, 1) */
+    const bool missing = entrySteps != nullptr && entrySteps[i] == ENTRY_MISS;
     for (uint32_t k = 0; k < n; k++) {
-        const float4 x = staging[(size_t)k * pixels + i];
+        const float4 x = missing ? make_float4(0.f, 0.f, 0.f, 1.f) : staging[(size_t)k * pixels + i];
         const float w = 1.0f / (float)(firstSubframe + k);
         welford(mean.x, m2.x, x.x, w);
         welford(mean.y, m2.y, x.y, w);
@@ -170,10 +179,22 @@ __global__ void __launch_bounds__(256) k_update_frame(const float4* __restrict__
     variance[i] = m2;
 }
 
-cudaError_t launchUpdateFrame(const float4* staging, float4* progressive, float4* variance, size_t pixels, uint32_t firstSubframe,
-                              uint32_t n, cudaStream_t st)
+cudaError_t launchUpdateFrame(const float4* staging, const uint32_t* entrySteps, float4* progressive, float4* variance, size_t pixels,
+                              uint32_t firstSubframe, uint32_t n, cudaStream_t st)
 {
-    k_update_frame<<<(unsigned)((pixels + 255) / 256), 256, 0, st>>>(staging, progressive, variance, pixels, firstSubframe, n);
+    k_update_frame<<<(unsigned)((pixels + 255) / 256), 256, 0, st>>>(staging, entrySteps, progressive, variance, pixels, firstSubframe, n);
+    return cudaGetLastError();
+}
+
+__global__ void __launch_bounds__(256) k_fill_missing(float4* __restrict__ staging, const uint32_t* __restrict__ entrySteps, size_t pixels)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < pixels && entrySteps[i] == ENTRY_MISS) staging[i] = make_float4(0.f, 0.f, 0.f, 1.f);
+}
+
+cudaError_t launchFillMissing(float4* staging, const uint32_t* entrySteps, size_t pixels, cudaStream_t st)
+{
+    k_fill_missing<<<(unsigned)((pixels + 255) / 256), 256, 0, st>>>(staging, entrySteps, pixels);
     return cudaGetLastError();
 }
 

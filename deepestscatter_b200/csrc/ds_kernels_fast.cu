@@ -9,11 +9,16 @@
  *   - the path marches in TEXTURE space (q = pos * textureScale), so a tap is one TEX instruction;
  *   - transmittance is carried as optical depth: tau += sigma*step and the collision test xi > exp(-tau)
  *     becomes tau > -ln(xi); one logarithm per free flight instead of one exponential per march step;
- *   - empty space: a lane whose tap returned exactly 0 (and every new path) looks up the occupancy bit of its
- *     tap cell (shared memory) and, if the cell is empty, walks the ray through the occupancy cells with a 3-D
- *     DDA until the next occupied cell; it then advances k whole march steps at once, k chosen so that every
- *     skipped tap lies in cells that are known to be empty.  Skipped steps read density 0, i.e. tau and the collision test are unchanged;
- *     the step counter still advances by k (the reference algorithm performs those steps);
+ *   - empty space: march steps whose trilinear footprint lies in all-zero occupancy cells read density 0 and
+ *     change nothing (tau, the collision test); they are skipped in bulk.  A lane in an empty cell reads the
+ *     cell's Chebyshev distance d to the nearest occupied cell, leaves the cube of (2d-1)^3 empty cells through
+ *     the face its ray exits ("leap DDA") and repeats until the next cell is occupied or the grid ends; it then
+ *     advances the whole number of march steps that fit.  The step counter advances by the same amount: the
+ *     reference algorithm performs those steps;
+ *   - primary rays do not depend on the subframe (no pixel jitter, CU/cameraCommon.cuh:22), so the empty-space
+ *     leg from the camera to the first occupied cell is walked ONCE per pixel by k_primary_prepass and cached:
+ *     pixels that never reach an occupied cell are not traced at all (their sample is exactly 0), the others
+ *     start at the cloud surface;
  *   - the 16-step bisection of the chopped-Mie CDF (cloud.cuh:167-178) is replaced by the closed-form
  *     inverse of the same piecewise-linear CDF: guide table -> short binary search for the table cell ->
  *     linear solve.  The bisection converges to that root within 2^-16;
@@ -41,6 +46,18 @@ struct FastConsts {
     float c1;   /* densityMultiplier * sampleStep */
     float nxf, nyf, nzf;
 };
+
+__device__ __forceinline__ FastConsts makeConsts(const DevScene& sc)
+{
+    FastConsts k;
+    k.stepTs = sc.texScale * sc.step;
+    k.half = mk(0.5f + 0.01f * sc.texScale.x, 0.5f + 0.01f * sc.texScale.y, 0.5f + 0.01f * sc.texScale.z);
+    k.c1 = sc.mult * sc.step;
+    k.nxf = (float)sc.nx;
+    k.nyf = (float)sc.ny;
+    k.nzf = (float)sc.nz;
+    return k;
+}
 
 __device__ __forceinline__ bool inBoxTs(const FastConsts& k, V3 q)
 {
@@ -96,104 +113,109 @@ __device__ __forceinline__ float tableLerp(const float* table, float u)
     return fmaf(f, b - a, a);
 }
 
+/* start of a free flight (cloudRadianceMaterials.cu:28-35, cloud.cuh:120) */
 template <bool CHECK_BOX>
-__device__ __forceinline__ int loopTopFast(const FastConsts& k, FastState& s)
+__device__ __forceinline__ bool beginFlight(const FastConsts& k, FastState& s)
 {
-    if (CHECK_BOX && !inBoxTs(k, s.q)) return ST_DONE;
+    if (CHECK_BOX && !inBoxTs(k, s.q)) return false;
     s.depth++;
-    if (s.depth == MAX_DEPTH) return ST_DONE;
+    if (s.depth == MAX_DEPTH) return false;
     const float xi = rnd(s.seed);
     s.tauStar = -__logf(xi); /* xi == 0 -> +inf: never collides, as `0 > T` in the reference */
     s.tau = 0.0f;
-    return ST_MARCH;
-}
-
-/* The tap at q is about to be taken.  If its cell is empty the tap is skipped (it would read 0) and the lane
- * walks the ray through the occupancy cells with a 3-D DDA until the next cell is occupied or the grid ends; it
- * then advances the largest whole number of march steps whose taps all lie in the empty cells just walked.
- * Coordinates: x = u*N - 0.5 is the voxel coordinate whose floor is the low corner of the trilinear footprint;
- * the occupancy bit of cell c covers voxels [c*2^s, c*2^s + 2^s], i.e. every footprint with floor(x) in c.
- * Returns true when the tap is skipped. */
-__device__ __forceinline__ bool skipEmpty(const DevScene& sc, const FastConsts& k, const uint32_t* sOcc, FastState& s, uint32_t& nSteps)
-{
-    const float x = fmaf(s.q.x, k.nxf, -0.5f), y = fmaf(s.q.y, k.nyf, -0.5f), z = fmaf(s.q.z, k.nzf, -0.5f);
-    const int fx = __float2int_rd(x), fy = __float2int_rd(y), fz = __float2int_rd(z);
-    int cx = min(max(fx, 0), sc.nx - 1) >> sc.occShift;
-    int cy = min(max(fy, 0), sc.ny - 1) >> sc.occShift;
-    int cz = min(max(fz, 0), sc.nz - 1) >> sc.occShift;
-    int cell = (cz * sc.ocy + cy) * sc.ocx + cx;
-    if ((sOcc[cell >> 5] >> (cell & 31)) & 1u) return false;
-    /* outside the grid the footprint is clamped to edge voxels: no walk, just skip this tap */
-    if ((unsigned)fx >= (unsigned)(sc.nx - 1) || (unsigned)fy >= (unsigned)(sc.ny - 1) || (unsigned)fz >= (unsigned)(sc.nz - 1)) return true;
-    const float cs = (float)(1 << sc.occShift);
-    const float vx = s.dir.x * k.stepTs.x * k.nxf, vy = s.dir.y * k.stepTs.y * k.nyf, vz = s.dir.z * k.stepTs.z * k.nzf; /* voxels per step */
-    const float big = 3.0e38f;
-    const float ix = fabsf(vx) > 1e-12f ? __fdividef(1.0f, vx) : big, iy = fabsf(vy) > 1e-12f ? __fdividef(1.0f, vy) : big,
-                iz = fabsf(vz) > 1e-12f ? __fdividef(1.0f, vz) : big;
-    const int sx = vx > 0.0f ? 1 : -1, sy = vy > 0.0f ? 1 : -1, sz = vz > 0.0f ? 1 : -1;
-    /* steps until the ray crosses into the neighbouring cell along each axis, and per-cell increments */
-    float tx = fabsf(ix) >= big ? big : ((float)(cx + (sx > 0 ? 1 : 0)) * cs - x) * ix;
-    float ty = fabsf(iy) >= big ? big : ((float)(cy + (sy > 0 ? 1 : 0)) * cs - y) * iy;
-    float tz = fabsf(iz) >= big ? big : ((float)(cz + (sz > 0 ? 1 : 0)) * cs - z) * iz;
-    const float dtx = fabsf(ix) >= big ? 0.0f : cs * fabsf(ix), dty = fabsf(iy) >= big ? 0.0f : cs * fabsf(iy),
-                dtz = fabsf(iz) >= big ? 0.0f : cs * fabsf(iz);
-    const int strideY = sc.ocx, strideZ = sc.ocx * sc.ocy;
-    float t = 0.0f, margin = 0.0f;
-#pragma unroll 1
-    for (int it = 0; it < 256; ++it) {
-        const bool ax = tx <= ty && tx <= tz;
-        const bool ay = !ax && ty <= tz;
-        if (ax) {
-            t = tx;
-            margin = fabsf(ix);
-            tx += dtx;
-            cx += sx;
-            cell += sx;
-            if ((unsigned)cx >= (unsigned)sc.ocx) break;
-        } else if (ay) {
-            t = ty;
-            margin = fabsf(iy);
-            ty += dty;
-            cy += sy;
-            cell += sy * strideY;
-            if ((unsigned)cy >= (unsigned)sc.ocy) break;
-        } else {
-            t = tz;
-            margin = fabsf(iz);
-            tz += dtz;
-            cz += sz;
-            cell += sz * strideZ;
-            if ((unsigned)cz >= (unsigned)sc.ocz) break;
-        }
-        if ((sOcc[cell >> 5] >> (cell & 31)) & 1u) break;
-    }
-    /* stay 0.01 voxel short of the cell boundary that stopped the walk */
-    const float kf = floorf(fminf(t - 0.01f * margin, 8192.0f));
-    if (kf >= 1.0f) {
-        s.q.x = fmaf(kf * s.dir.x, k.stepTs.x, s.q.x);
-        s.q.y = fmaf(kf * s.dir.y, k.stepTs.y, s.q.y);
-        s.q.z = fmaf(kf * s.dir.z, k.stepTs.z, s.q.z);
-        nSteps += (uint32_t)kf;
-    }
     return true;
 }
 
-template <bool SKIP>
-__device__ __forceinline__ int beginItemFast(const DevScene& sc, const FastConsts& k, const TraceJob& job, const float* sCdf,
-                                             const uint16_t* sGuide, unsigned long long idx, FastState& s, bool& valid)
+/* occupancy cell of the trilinear footprint at texture coordinate q; false if the cell is occupied */
+__device__ __forceinline__ bool tapCellEmpty(const DevScene& sc, const FastConsts& k, const uint32_t* occ, V3 q)
 {
-    V3 o, d;
-    uint32_t val0, stream;
-    valid = true;
+    const int fx = __float2int_rd(fmaf(q.x, k.nxf, -0.5f)), fy = __float2int_rd(fmaf(q.y, k.nyf, -0.5f)), fz = __float2int_rd(fmaf(q.z, k.nzf, -0.5f));
+    const int cx = min(max(fx, 0), sc.nx - 1) >> sc.occShift;
+    const int cy = min(max(fy, 0), sc.ny - 1) >> sc.occShift;
+    const int cz = min(max(fz, 0), sc.nz - 1) >> sc.occShift;
+    const int cell = (cz * sc.ocy + cy) * sc.ocx + cx;
+    return ((occ[cell >> 5] >> (cell & 31)) & 1u) == 0u;
+}
+
+/*
+ * Leap DDA.  The tap at q has just been found to lie in an EMPTY cell.  Walks the ray through empty cells and
+ * returns the whole number of further march steps whose taps are all guaranteed to read 0.
+ * Coordinates: x = u*N - 0.5 is the voxel coordinate whose floor is the low corner of the trilinear footprint;
+ * the occupancy bit of cell c covers voxels [c*2^s, c*2^s + 2^s], i.e. every footprint with floor(x) in c.
+ * A cell at Chebyshev distance d >= 1 from the nearest occupied cell is the centre of a cube of (2d-1)^3 empty
+ * cells; the ray leaves that cube through one face, lands in the adjacent cell and repeats.
+ */
+__device__ __forceinline__ float emptySteps(const DevScene& sc, const FastConsts& k, const uint32_t* occ, V3 q, V3 dir)
+{
+    const float x = fmaf(q.x, k.nxf, -0.5f), y = fmaf(q.y, k.nyf, -0.5f), z = fmaf(q.z, k.nzf, -0.5f);
+    const int fx = __float2int_rd(x), fy = __float2int_rd(y), fz = __float2int_rd(z);
+    /* outside the grid the footprint is clamped to edge voxels: no walk */
+    if ((unsigned)fx >= (unsigned)(sc.nx - 1) || (unsigned)fy >= (unsigned)(sc.ny - 1) || (unsigned)fz >= (unsigned)(sc.nz - 1)) return 0.0f;
+    const int sh = sc.occShift;
+    int cx = fx >> sh, cy = fy >> sh, cz = fz >> sh;
+    const float cs = (float)(1 << sh);
+    const float vx = dir.x * k.stepTs.x * k.nxf, vy = dir.y * k.stepTs.y * k.nyf, vz = dir.z * k.stepTs.z * k.nzf; /* voxels per step */
+    const float big = 1.0e30f;
+    const bool mx = fabsf(vx) > 1e-9f, my = fabsf(vy) > 1e-9f, mz = fabsf(vz) > 1e-9f;
+    const float ix = mx ? __fdividef(1.0f, vx) : 0.0f, iy = my ? __fdividef(1.0f, vy) : 0.0f, iz = mz ? __fdividef(1.0f, vz) : 0.0f;
+    const bool px = vx > 0.0f, py = vy > 0.0f, pz = vz > 0.0f;
+    float t = 0.0f, margin = 0.0f;
+#pragma unroll 1
+    for (int it = 0; it < 96; ++it) {
+        const int cell = (cz * sc.ocy + cy) * sc.ocx + cx;
+        const int r = (int)__ldg(sc.cellDist + cell) - 1; /* cells [c-r, c+r]^3 are empty */
+        /* exit planes of the cube along the direction of travel */
+        const float ex = (float)(px ? cx + r + 1 : cx - r) * cs, ey = (float)(py ? cy + r + 1 : cy - r) * cs, ez = (float)(pz ? cz + r + 1 : cz - r) * cs;
+        const float tx = mx ? (ex - x) * ix : big, ty = my ? (ey - y) * iy : big, tz = mz ? (ez - z) * iz : big;
+        t = fminf(tx, fminf(ty, tz));
+        /* cell the ray enters: the exit axis moves one cell past the cube face, the others follow the ray */
+        const bool ax = tx <= ty && tx <= tz, ay = !ax && ty <= tz;
+        int nx_ = __float2int_rd(fmaf(t, vx, x)) >> sh, ny_ = __float2int_rd(fmaf(t, vy, y)) >> sh, nz_ = __float2int_rd(fmaf(t, vz, z)) >> sh;
+        nx_ = min(max(nx_, cx - r), cx + r);
+        ny_ = min(max(ny_, cy - r), cy + r);
+        nz_ = min(max(nz_, cz - r), cz + r);
+        if (ax) {
+            nx_ = px ? cx + r + 1 : cx - r - 1;
+            margin = fabsf(ix);
+        } else if (ay) {
+            ny_ = py ? cy + r + 1 : cy - r - 1;
+            margin = fabsf(iy);
+        } else {
+            nz_ = pz ? cz + r + 1 : cz - r - 1;
+            margin = fabsf(iz);
+        }
+        if ((unsigned)nx_ >= (unsigned)sc.ocx || (unsigned)ny_ >= (unsigned)sc.ocy || (unsigned)nz_ >= (unsigned)sc.ocz) break;
+        cx = nx_;
+        cy = ny_;
+        cz = nz_;
+        const int ncell = (cz * sc.ocy + cy) * sc.ocx + cx;
+        if ((occ[ncell >> 5] >> (ncell & 31)) & 1u) break;
+    }
+    /* stay 0.01 voxel short of the plane that stopped the walk */
+    return fmaxf(floorf(fminf(t - 0.01f * margin, 65535.0f)), 0.0f);
+}
+
+/* ray of work item `idx` (CU/pathTracingCamera.cu:12-21, CU/cameraCommon.cuh:19-29, CU/pointEmissionCamera.cu:20-33) */
+__device__ __forceinline__ bool itemRay(const TraceJob& job, unsigned long long idx, V3& o, V3& d, uint32_t& val0, uint32_t& stream,
+                                        unsigned long long& out, uint32_t& pixel)
+{
+    pixel = 0;
     if (job.kind == JOB_RENDER) {
-        const unsigned long long sub = idx / job.itemsPerSubframe;
-        const uint32_t rem = (uint32_t)(idx - sub * job.itemsPerSubframe);
-        const uint32_t tile = rem >> 5, within = rem & 31u;
-        const uint32_t px = (tile % (uint32_t)job.tilesX) * 8u + (within & 7u);
-        const uint32_t py = (tile / (uint32_t)job.tilesX) * 4u + (within >> 3);
-        if (px >= (uint32_t)job.width || py >= (uint32_t)job.height) {
-            valid = false;
-            return ST_IDLE;
+        unsigned long long sub;
+        uint32_t px, py;
+        if (job.hitList) {
+            sub = idx / job.nHit;
+            pixel = job.hitList[(uint32_t)(idx - sub * job.nHit)];
+            px = pixel % (uint32_t)job.width;
+            py = pixel / (uint32_t)job.width;
+        } else {
+            sub = idx / job.itemsPerSubframe;
+            const uint32_t rem = (uint32_t)(idx - sub * job.itemsPerSubframe);
+            const uint32_t tile = rem >> 5, within = rem & 31u;
+            px = (tile % (uint32_t)job.tilesX) * 8u + (within & 7u);
+            py = (tile / (uint32_t)job.tilesX) * 4u + (within >> 3);
+            if (px >= (uint32_t)job.width || py >= (uint32_t)job.height) return false;
+            pixel = py * (uint32_t)job.width + px;
         }
         const float dx = (float)px / (float)job.width * 2.f - 1.f;
         const float dy = (float)py / (float)job.height * 2.f - 1.f;
@@ -202,7 +224,7 @@ __device__ __forceinline__ int beginItemFast(const DevScene& sc, const FastConst
         d = normalize<true>(dx * U + dy * V + W);
         val0 = px * 4096u + py;
         stream = job.firstSubframe + (uint32_t)sub;
-        s.out = sub * (unsigned long long)job.width * job.height + (unsigned long long)py * job.width + px;
+        out = sub * (unsigned long long)job.width * job.height + pixel;
     } else if (job.kind == JOB_POINT) {
         const uint32_t t = (uint32_t)(idx / job.launches);
         const uint32_t l = (uint32_t)(idx - (unsigned long long)t * job.launches);
@@ -211,17 +233,30 @@ __device__ __forceinline__ int beginItemFast(const DevScene& sc, const FastConst
         d = mk(task->direction[0], task->direction[1], task->direction[2]);
         val0 = t * 4096u;
         stream = job.frame0 + l + 1u;
-        s.out = idx;
+        out = idx;
     } else {
         o = mk(job.origins[3 * idx], job.origins[3 * idx + 1], job.origins[3 * idx + 2]);
         d = mk(job.dirs[3 * idx], job.dirs[3 * idx + 1], job.dirs[3 * idx + 2]);
         val0 = job.seedVal0[idx];
         stream = job.stream[idx];
-        s.out = idx;
+        out = idx;
     }
+    return true;
+}
+
+/* lane states of k_trace_fast */
+enum FastLaneState { F_IDLE = 0, F_SKIP = 1, F_MARCH = 2, F_EVENT = 3, F_DONE = 4 };
+
+__device__ __forceinline__ int beginItemFast(const DevScene& sc, const FastConsts& k, const TraceJob& job, const float* sCdf,
+                                             const uint16_t* sGuide, unsigned long long idx, FastState& s, bool& valid, uint32_t& nSteps)
+{
+    V3 o, d;
+    uint32_t val0, stream, pixel;
+    valid = itemRay(job, idx, o, d, val0, stream, s.out, pixel);
+    if (!valid) return F_IDLE;
     s.rad = 0.0f;
     const float tHit = intersectBox(sc, o, d);
-    if (tHit < 0.0f) return ST_DONE;
+    if (tHit < 0.0f) return F_DONE;
     V3 hit = o + tHit * d;
     hit = hit + 0.5f * sc.bbox;
     s.q = hit * sc.texScale;
@@ -229,7 +264,16 @@ __device__ __forceinline__ int beginItemFast(const DevScene& sc, const FastConst
     s.seed = tea4(val0, stream);
     s.depth = 0;
     if (job.mode == DS_MODE_SUN_MULTIPLE_SCATTER) s.dir = newDirectionFast(sCdf, sGuide, s.seed, s.dir);
-    return loopTopFast<true>(k, s);
+    if (!beginFlight<true>(k, s)) return F_DONE;
+    if (job.kind == JOB_RENDER && job.entrySteps) {
+        /* cached empty-space leg of the primary ray: start at the cloud surface */
+        const float kf = (float)job.entrySteps[pixel];
+        s.q.x = fmaf(kf * s.dir.x, k.stepTs.x, s.q.x);
+        s.q.y = fmaf(kf * s.dir.y, k.stepTs.y, s.q.y);
+        s.q.z = fmaf(kf * s.dir.z, k.stepTs.z, s.q.z);
+        nSteps += (uint32_t)kf;
+    }
+    return F_MARCH;
 }
 
 __device__ __forceinline__ void writeResultFast(const DevScene& sc, const TraceJob& job, const FastState& s, uint32_t& nonfinite)
@@ -248,17 +292,13 @@ __device__ __forceinline__ void writeResultFast(const DevScene& sc, const TraceJ
     }
 }
 
-/* lane states of k_trace_fast */
-enum FastLaneState { F_IDLE = 0, F_SKIP = 1, F_MARCH = 2, F_EVENT = 3, F_DONE = 4 };
-
 /*
  * Warp-level schedule.  Each lane owns one path; a warp cycles through four phases and runs a phase only when
  * enough of its lanes want it, so the (long, divergent) code of each phase executes with many lanes active:
  *   A  retire + regenerate   lanes whose path ended write their sample and pull the next work item from the
  *                            device queue (one warp-aggregated atomic); runs when >= regenMin lanes are free
- *   B  empty-space phase     lanes travelling through empty cells (every new path starts here, and paths
- *                            leaving the cloud return here): step, test the tap cell, jump; runs when >= skipMin
- *                            lanes are in it
+ *   B  empty-space phase     lanes whose tap fell into an empty cell (paths leaving the cloud, paths started in
+ *                            empty space): leap DDA, then continue marching; runs when >= skipMin lanes wait
  *   C  march phase           lanes inside the cloud: step + density tap + collision test
  *   D  event phase           lanes that collided: next-event estimate + new direction
  * A waiting lane costs nothing but its slot; a phase entered with two lanes costs the whole warp its full
@@ -280,14 +320,7 @@ __global__ void __launch_bounds__(640, 2) k_trace_fast(const DevScene sc, const 
     for (int i = threadIdx.x; i < sc.occWords; i += blockDim.x) sOcc[i] = sc.occ[i];
     __syncthreads();
 
-    FastConsts k;
-    k.stepTs = sc.texScale * sc.step;
-    k.half = mk(0.5f + 0.01f * sc.texScale.x, 0.5f + 0.01f * sc.texScale.y, 0.5f + 0.01f * sc.texScale.z);
-    k.c1 = sc.mult * sc.step;
-    k.nxf = (float)sc.nx;
-    k.nyf = (float)sc.ny;
-    k.nzf = (float)sc.nz;
-
+    const FastConsts k = makeConsts(sc);
     const unsigned FULL = 0xffffffffu;
     const unsigned lane = threadIdx.x & 31u;
     const unsigned laneLt = (1u << lane) - 1u;
@@ -328,8 +361,7 @@ __global__ void __launch_bounds__(640, 2) k_trace_fast(const DevScene sc, const 
                         exhausted = true;
                     } else {
                         bool valid;
-                        const int g = beginItemFast<SKIP>(sc, k, job, sCdf, sGuide, idx, s, valid);
-                        st = g == ST_MARCH ? (SKIP ? F_SKIP : F_MARCH) : (g == ST_DONE ? F_DONE : F_IDLE);
+                        st = beginItemFast(sc, k, job, sCdf, sGuide, idx, s, valid, nSteps);
                         if (valid) nPaths++;
                     }
                 }
@@ -342,31 +374,15 @@ __global__ void __launch_bounds__(640, 2) k_trace_fast(const DevScene sc, const 
         }
         if (mBusy == 0u && mSkip == 0u && mFree == 0u) break; /* every lane idle and the queue exhausted */
 
-        /* ---- B: empty-space phase ---- */
+        /* ---- B: empty-space phase: the tap at q fell into an empty cell ---- */
         if (SKIP && mSkip && (__popc(mSkip) >= job.skipMin || mBusy == 0u)) {
-#pragma unroll 1
-            for (int it = 0; it < job.skipMaxIters; ++it) {
-                if (st == F_SKIP) {
-                    if (!inBoxTs(k, s.q)) {
-                        st = F_DONE;
-                    } else {
-                        s.q.x = fmaf(s.dir.x, k.stepTs.x, s.q.x);
-                        s.q.y = fmaf(s.dir.y, k.stepTs.y, s.q.y);
-                        s.q.z = fmaf(s.dir.z, k.stepTs.z, s.q.z);
-                        nSteps++;
-                        if (!skipEmpty(sc, k, sOcc, s, nSteps)) {
-                            nTaps++;
-                            lastDensity = tex3D<float>(sc.densityTex, s.q.x, s.q.y, s.q.z);
-                            if (lastDensity != 0.0f) {
-                                s.tau = fmaf(lastDensity, k.c1, s.tau);
-                                st = s.tau > s.tauStar ? F_EVENT : F_MARCH;
-                            }
-                        }
-                    }
-                }
-                const int nSkip = __popc(__ballot_sync(FULL, st == F_SKIP));
-                const bool busyNow = __any_sync(FULL, st == F_MARCH || st == F_EVENT);
-                if (nSkip == 0 || (busyNow && nSkip < job.skipKeep)) break;
+            if (st == F_SKIP) {
+                const float kf = emptySteps(sc, k, sOcc, s.q, s.dir);
+                s.q.x = fmaf(kf * s.dir.x, k.stepTs.x, s.q.x);
+                s.q.y = fmaf(kf * s.dir.y, k.stepTs.y, s.q.y);
+                s.q.z = fmaf(kf * s.dir.z, k.stepTs.z, s.q.z);
+                nSteps += (uint32_t)kf;
+                st = F_MARCH;
             }
         }
 
@@ -385,8 +401,9 @@ __global__ void __launch_bounds__(640, 2) k_trace_fast(const DevScene sc, const 
                         nSteps++;
                         nTaps++;
                         lastDensity = tex3D<float>(sc.densityTex, s.q.x, s.q.y, s.q.z);
-                        if (SKIP && lastDensity == 0.0f) {
-                            st = F_SKIP; /* left the cloud (or a hole in it): continue in the empty-space phase */
+                        if (lastDensity == 0.0f) {
+                            /* left the cloud, or a hole inside an occupied cell */
+                            if (SKIP && tapCellEmpty(sc, k, sOcc, s.q)) st = F_SKIP;
                         } else {
                             s.tau = fmaf(lastDensity, k.c1, s.tau);
                             if (s.tau > s.tauStar) st = F_EVENT;
@@ -419,8 +436,7 @@ __global__ void __launch_bounds__(640, 2) k_trace_fast(const DevScene sc, const 
                     st = F_DONE;
                 } else {
                     s.dir = newDirectionFast(sCdf, sGuide, s.seed, s.dir);
-                    const int g = loopTopFast<false>(k, s); /* q is the scatter position just verified in-box */
-                    st = g == ST_MARCH ? F_MARCH : F_DONE;
+                    st = beginFlight<false>(k, s) ? F_MARCH : F_DONE; /* q is the scatter position just verified in-box */
                 }
             }
         }
@@ -454,6 +470,76 @@ cudaError_t KernelSet<true>::trace(const DevScene& sc, const TraceJob& job, cons
         if (e != cudaSuccess) return e;
         k_trace_fast<false><<<blocks, threads, smem, st>>>(sc, job);
     }
+    return cudaGetLastError();
+}
+
+/*
+ * Primary-ray pre-pass: one thread per pixel.  Walks the camera ray from the box entry through empty cells and
+ * records how many march steps precede the first tap that can be non-zero; pixels whose ray never reaches an
+ * occupied cell are marked ENTRY_MISS (their radiance sample is exactly 0 for every subframe) and the number of
+ * march steps the reference algorithm would spend on them is summed for the work counters.
+ */
+__global__ void __launch_bounds__(256) k_primary_prepass(const DevScene sc, const TraceJob job, uint32_t* __restrict__ entrySteps,
+                                                         uint32_t* __restrict__ hitList, unsigned long long* __restrict__ counts)
+{
+    const FastConsts k = makeConsts(sc);
+    const uint32_t rem = blockIdx.x * blockDim.x + threadIdx.x; /* tile-ordered pixel enumeration, 32 pixels per 8x4 tile */
+    const uint32_t tile = rem >> 5, within = rem & 31u;
+    const uint32_t px = (tile % (uint32_t)job.tilesX) * 8u + (within & 7u);
+    const uint32_t py = (tile / (uint32_t)job.tilesX) * 4u + (within >> 3);
+    const bool valid = rem < job.itemsPerSubframe && px < (uint32_t)job.width && py < (uint32_t)job.height;
+    bool hit = false;
+    uint32_t steps = 0;
+    const uint32_t pixel = py * (uint32_t)job.width + px;
+    if (valid) {
+        const float dx = (float)px / (float)job.width * 2.f - 1.f;
+        const float dy = (float)py / (float)job.height * 2.f - 1.f;
+        const V3 U = mk(job.U[0], job.U[1], job.U[2]), V = mk(job.V[0], job.V[1], job.V[2]), W = mk(job.W[0], job.W[1], job.W[2]);
+        const V3 o = mk(job.eye[0], job.eye[1], job.eye[2]);
+        const V3 d = normalize<true>(dx * U + dy * V + W);
+        const float tHit = intersectBox(sc, o, d);
+        if (tHit >= 0.0f) {
+            V3 hitp = o + tHit * d;
+            hitp = hitp + 0.5f * sc.bbox;
+            V3 q = hitp * sc.texScale;
+            const V3 dir = normalize<true>(d);
+            /* march like the reference (cloud.cuh:87-89) but only look at occupancy */
+            while (inBoxTs(k, q)) {
+                const V3 qn = mk(fmaf(dir.x, k.stepTs.x, q.x), fmaf(dir.y, k.stepTs.y, q.y), fmaf(dir.z, k.stepTs.z, q.z));
+                if (!tapCellEmpty(sc, k, sc.occ, qn)) {
+                    hit = true; /* the next step's tap may be non-zero: the traced path starts at q */
+                    break;
+                }
+                q = qn;
+                steps++;
+                const float kf = emptySteps(sc, k, sc.occ, q, dir);
+                q = mk(fmaf(kf * dir.x, k.stepTs.x, q.x), fmaf(kf * dir.y, k.stepTs.y, q.y), fmaf(kf * dir.z, k.stepTs.z, q.z));
+                steps += (uint32_t)kf;
+            }
+        }
+        entrySteps[pixel] = hit ? steps : ENTRY_MISS;
+    }
+    /* compact the hitting pixels, warp-aggregated, in tile order within a warp */
+    const unsigned m = __ballot_sync(0xffffffffu, hit);
+    const unsigned lane = threadIdx.x & 31u;
+    unsigned long long base = 0;
+    if (m) {
+        const int leader = __ffs(m) - 1;
+        if ((int)lane == leader) base = atomicAdd(counts, (unsigned long long)__popc(m));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (hit) hitList[base + __popc(m & ((1u << lane) - 1u))] = pixel;
+    }
+    unsigned long long missSteps = (valid && !hit) ? steps : 0ull;
+    for (int o = 16; o > 0; o >>= 1) missSteps += __shfl_down_sync(0xffffffffu, missSteps, o);
+    if (lane == 0 && missSteps) atomicAdd(counts + 1, missSteps);
+}
+
+template <>
+cudaError_t KernelSet<true>::primaryPrepass(const DevScene& sc, const TraceJob& cam, uint32_t* entrySteps, uint32_t* hitList,
+                                            unsigned long long* counts, cudaStream_t st)
+{
+    const unsigned long long items = cam.itemsPerSubframe;
+    k_primary_prepass<<<(unsigned)((items + 255) / 256), 256, 0, st>>>(sc, cam, entrySteps, hitList, counts);
     return cudaGetLastError();
 }
 

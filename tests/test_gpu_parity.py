@@ -242,6 +242,17 @@ def test_fast_flavour_is_deterministic_under_scheduling_knobs(built_library):
             for k, val in dict(regen_min=8, skip_min=8, skip_keep=4, march_keep32=12, march_max_iters=64, skip_max_iters=32,
                                block_threads=640, blocks_per_sm=2).items():
                 ctx.set_option(k, val)
+        # without the primary-ray cache every pixel is traced from the box face: same silhouette, same counters
+        ctx.set_option("primary_cache", 0)
+        ctx.counters_reset()
+        nocache = ctx.render_frame(cam, 0, 7)
+        c1 = ctx.counters()
+        ctx.set_option("primary_cache", 1)
+        assert np.array_equal(nocache[..., 0] == 0, base[..., 0] == 0)
+        assert np.all(nocache[..., 3] == 1) and np.all(base[..., 3] == 1)
+        assert c1["paths"] == c0["paths"] == w * h
+        assert abs(c1["steps"] - c0["steps"]) <= 0.02 * c0["steps"] and abs(c1["events"] - c0["events"]) <= 0.1 * c0["events"] + 50
+        assert abs(float(nocache[..., 0].mean()) - float(base[..., 0].mean())) < 0.25 * float(base[..., 0].mean())
         # the generic kernel (variant 1) and jump-free marching agree statistically, not bitwise
         ctx.set_option("skip_empty", 0)
         noskip = ctx.render_frame(cam, 0, 7)
