@@ -43,7 +43,7 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--spp", type=int, default=4, help="progressive subframes per step (per GPU)")
+    ap.add_argument("--spp", type=int, default=32, help="progressive subframes per step (per GPU)")
     ap.add_argument("--grid", type=int, default=GRID_N)
     ap.add_argument("--width", type=int, default=WIDTH)
     ap.add_argument("--height", type=int, default=HEIGHT)
@@ -244,7 +244,7 @@ def run_ours(a):
     for kv in a.opt:
         k, v = kv.split("=")
         ctx.set_option(k, int(v))
-    ctx.set_option("staging_subframes", max(1, min(16, a.spp)))
+    ctx.set_option("staging_subframes", max(1, min(64, a.spp)))
 
     # ---- inputs: resident in HBM before any timed region ----
     ctx.volume_synth(a.grid, GRID_KIND, GRID_SEED, True)
@@ -356,7 +356,8 @@ def run_ours(a):
         "config": {"workload": workload_name(a), "precision": a.precision, "grid_bytes": 2 * a.grid**3,
                    "l2": "inputs (density + sun-transmittance grids, 2*N^3 B) are larger than the 126 MB L2; no explicit flush",
                    "multi_gpu": "replicated grid, subframe ids split over ranks, one NCCL reduce of moment buffers" if distributed else "single GPU",
-                   "options": {k: ctx.get_option(k) for k in ("block_threads", "blocks_per_sm", "skip_empty", "march_keep_quarters", "march_max_iters", "staging_subframes")}},
+                   "options": {k: ctx.get_option(k) for k in ("variant", "block_threads", "blocks_per_sm", "skip_empty", "primary_cache", "regen_min", "skip_min",
+                                                               "skip_max_iters", "march_keep32", "march_max_iters", "staging_subframes")}},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": METRIC, "h2d_bytes_per_step": 2 * px * 16, "d2h_bytes_per_step": 2 * px * 16,
                 "api": "ds_render_subframes_host (progressive + variance float4 buffers in pinned host memory)", "checksum_mean_radiance": checksum},

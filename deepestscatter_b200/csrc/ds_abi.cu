@@ -40,6 +40,7 @@ struct DsContext {
     uint32_t* occ = nullptr;
     uint8_t* cellDist = nullptr;
     int occShift = 0, ocx = 0, ocy = 0, ocz = 0, occWords = 0;
+    int borderEmpty = 0;
 
     /* scene */
     DsSceneParams params{};
@@ -236,6 +237,7 @@ static void fillDevScene(DsContext* ctx, DevScene& sc)
     sc.occWords = ctx->occWords;
     sc.cellDist = ctx->cellDist;
     sc.guide = ctx->guide;
+    sc.borderEmpty = ctx->borderEmpty;
 }
 
 /* VDBCloud::setupVolumeVariables / setupVariables (VDBCloud.cpp:88-117) + Sun (SceneDescription.h:17-19) */
@@ -311,6 +313,17 @@ static int finishVolume(DsContext* ctx, int buildMips)
     DS_CUDA(ctx, cudaMalloc(&ctx->inscatter, (size_t)nx * ny * nz));
     DS_CUDA(ctx, cudaMemsetAsync(ctx->inscatter, 0, (size_t)nx * ny * nz, ctx->stream));
     computeDerived(ctx);
+    {
+        /* are all face voxels zero?  (decides whether clamped taps outside the grid can be skipped) */
+        int rcs = ensureScratch(ctx, 6, sizeof(uint32_t));
+        if (rcs) return rcs;
+        uint32_t h = 1;
+        DS_CUDA(ctx, cudaMemsetAsync(ctx->scratch[6], 0, sizeof(uint32_t), ctx->stream));
+        DS_CUDA(ctx, launchBorderCount(ctx->levels[0], nx, ny, nz, (uint32_t*)ctx->scratch[6], ctx->stream));
+        DS_CUDA(ctx, cudaMemcpyAsync(&h, ctx->scratch[6], sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+        DS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        ctx->borderEmpty = h == 0 ? 1 : 0;
+    }
     DS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return DS_OK;
 }
@@ -429,11 +442,11 @@ int ds_context_create(int device, DsContext** out)
     ctx->opt["skip_empty"] = 1;
     ctx->opt["march_keep_quarters"] = 2;
     ctx->opt["march_max_iters"] = 64;
-    ctx->opt["march_keep32"] = 12;
-    ctx->opt["regen_min"] = 8;
-    ctx->opt["skip_min"] = 8;
+    ctx->opt["march_keep32"] = 8;
+    ctx->opt["regen_min"] = 4;
+    ctx->opt["skip_min"] = 4;
     ctx->opt["skip_keep"] = 4;
-    ctx->opt["skip_max_iters"] = 32;
+    ctx->opt["skip_max_iters"] = 4;
     ctx->opt["staging_subframes"] = 16;
     ctx->opt["stream_offset"] = 0;
     ctx->opt["profile_events"] = 0;

@@ -102,6 +102,9 @@ struct DevScene {
     const uint8_t* cellDist;
     /* guide table of the chopped-Mie CDF: guide[k] = first index i with cdf[i] >= k / GUIDE_N, k = 0..GUIDE_N */
     const uint16_t* guide;
+    /* 1 when every voxel on the six faces of the grid is zero (VDB imports are padded by one voxel,
+     * Resources.cpp:97-101): clamped taps outside the grid then read 0 */
+    int borderEmpty;
 };
 
 constexpr int GUIDE_N = 4096;

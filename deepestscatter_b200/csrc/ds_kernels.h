@@ -93,6 +93,7 @@ cudaError_t launchSynth(uint8_t* out, int n, int kind, uint32_t seed, cudaStream
 cudaError_t launchQuantize(const float* in, size_t count, double maxDensity, uint8_t* out, cudaStream_t st);
 cudaError_t launchMip(const uint8_t* prev, int pnx, int pny, int pnz, uint8_t* cur, int cnx, int cny, int cnz, cudaStream_t st);
 cudaError_t launchCellDistance(const uint32_t* occBits, int ocx, int ocy, int ocz, uint8_t* dist, uint8_t* tmp, cudaStream_t st);
+cudaError_t launchBorderCount(const uint8_t* density, int nx, int ny, int nz, uint32_t* count, cudaStream_t st);
 cudaError_t launchOccupancy(const uint8_t* density, int nx, int ny, int nz, int shift, int ocx, int ocy, int ocz, uint32_t* bits,
                             cudaStream_t st);
 cudaError_t launchUpdateFrame(const float4* staging, const uint32_t* entrySteps, float4* progressive, float4* variance, size_t pixels,

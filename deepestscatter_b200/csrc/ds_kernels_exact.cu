@@ -108,6 +108,34 @@ cudaError_t launchOccupancy(const uint8_t* density, int nx, int ny, int nz, int 
     return cudaGetLastError();
 }
 
+/* ---- number of non-zero voxels on the six faces of the grid ---- */
+__global__ void __launch_bounds__(256) k_border_count(const uint8_t* __restrict__ density, int nx, int ny, int nz, uint32_t* count)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long nxy = (long long)nx * ny, nyz = (long long)ny * nz, nxz = (long long)nx * nz;
+    bool nonzero = false;
+    if (i < nxy) {
+        const int x = (int)(i % nx), y = (int)(i / nx);
+        nonzero = density[((size_t)0 * ny + y) * nx + x] || density[((size_t)(nz - 1) * ny + y) * nx + x];
+    } else if (i < nxy + nyz) {
+        const long long j = i - nxy;
+        const int y = (int)(j % ny), z = (int)(j / ny);
+        nonzero = density[((size_t)z * ny + y) * nx + 0] || density[((size_t)z * ny + y) * nx + (nx - 1)];
+    } else if (i < nxy + nyz + nxz) {
+        const long long j = i - nxy - nyz;
+        const int x = (int)(j % nx), z = (int)(j / nx);
+        nonzero = density[((size_t)z * ny + 0) * nx + x] || density[((size_t)z * ny + (ny - 1)) * nx + x];
+    }
+    if (nonzero) atomicAdd(count, 1u);
+}
+
+cudaError_t launchBorderCount(const uint8_t* density, int nx, int ny, int nz, uint32_t* count, cudaStream_t st)
+{
+    const long long total = (long long)nx * ny + (long long)ny * nz + (long long)nx * nz;
+    k_border_count<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(density, nx, ny, nz, count);
+    return cudaGetLastError();
+}
+
 /* ---- Chebyshev distance transform over occupancy cells (iterated 26-neighbour relaxation) ---- */
 __global__ void __launch_bounds__(128) k_cell_dist_init(const uint32_t* __restrict__ bits, int cells, uint8_t* dist)
 {

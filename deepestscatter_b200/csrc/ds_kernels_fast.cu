@@ -68,13 +68,14 @@ __device__ __forceinline__ bool inBoxTs(const FastConsts& k, V3 q)
 __device__ __forceinline__ float invertCdf(const float* sCdf, const uint16_t* sGuide, float val)
 {
     const int k = min((int)(val * (float)GUIDE_N), GUIDE_N - 1);
-    int lo = sGuide[k], hi = sGuide[k + 1];
-    while (lo < hi) { /* first index with cdf[i] >= val */
-        const int mid = (lo + hi) >> 1;
-        if (sCdf[mid] < val)
-            lo = mid + 1;
-        else
-            hi = mid;
+    /* lower bound of val in cdf[lo, lo + n): n <= 31 (GUIDE_N = 4096), five branch-free halvings */
+    int lo = sGuide[k], n = (int)sGuide[k + 1] - lo;
+#pragma unroll
+    for (int i = 0; i < 5; i++) {
+        const int half = n >> 1;
+        const bool right = n > 0 && sCdf[min(lo + half, MIE_N - 1)] < val;
+        lo = right ? lo + half + 1 : lo;
+        n = right ? n - half - 1 : half;
     }
     float u;
     if (lo == 0) {
@@ -137,20 +138,35 @@ __device__ __forceinline__ bool tapCellEmpty(const DevScene& sc, const FastConst
     return ((occ[cell >> 5] >> (cell & 31)) & 1u) == 0u;
 }
 
+/* whole march steps until the position leaves the in-box slab (the reference's `while (isInBox(pos))`) */
+__device__ __forceinline__ float stepsToLeaveBox(const FastConsts& k, V3 q, V3 dir)
+{
+    const float dx = dir.x * k.stepTs.x, dy = dir.y * k.stepTs.y, dz = dir.z * k.stepTs.z;
+    const float big = 1.0e30f;
+    const float tx = fabsf(dx) > 1e-12f ? __fdividef((dx > 0.0f ? 0.5f + k.half.x : 0.5f - k.half.x) - q.x, dx) : big;
+    const float ty = fabsf(dy) > 1e-12f ? __fdividef((dy > 0.0f ? 0.5f + k.half.y : 0.5f - k.half.y) - q.y, dy) : big;
+    const float tz = fabsf(dz) > 1e-12f ? __fdividef((dz > 0.0f ? 0.5f + k.half.z : 0.5f - k.half.z) - q.z, dz) : big;
+    return fmaxf(floorf(fminf(fminf(tx, ty), fminf(tz, 65534.0f))) + 1.0f, 0.0f);
+}
+
 /*
  * Leap DDA.  The tap at q has just been found to lie in an EMPTY cell.  Walks the ray through empty cells and
- * returns the whole number of further march steps whose taps are all guaranteed to read 0.
+ * returns the whole number of further march steps whose taps are all guaranteed to read 0; `more` is set when
+ * the walk was cut short after `maxLeaps` leaps and the landing position is still in an empty cell.
  * Coordinates: x = u*N - 0.5 is the voxel coordinate whose floor is the low corner of the trilinear footprint;
  * the occupancy bit of cell c covers voxels [c*2^s, c*2^s + 2^s], i.e. every footprint with floor(x) in c.
  * A cell at Chebyshev distance d >= 1 from the nearest occupied cell is the centre of a cube of (2d-1)^3 empty
- * cells; the ray leaves that cube through one face, lands in the adjacent cell and repeats.
+ * cells; the ray leaves that cube through one face, lands in the adjacent cell and repeats.  When the ray leaves
+ * the grid and all face voxels are zero (borderEmpty), the rest of its way out of the box reads 0 as well.
  */
-__device__ __forceinline__ float emptySteps(const DevScene& sc, const FastConsts& k, const uint32_t* occ, V3 q, V3 dir)
+__device__ __forceinline__ float emptySteps(const DevScene& sc, const FastConsts& k, const uint32_t* occ, V3 q, V3 dir, int maxLeaps, bool& more)
 {
+    more = false;
     const float x = fmaf(q.x, k.nxf, -0.5f), y = fmaf(q.y, k.nyf, -0.5f), z = fmaf(q.z, k.nzf, -0.5f);
     const int fx = __float2int_rd(x), fy = __float2int_rd(y), fz = __float2int_rd(z);
-    /* outside the grid the footprint is clamped to edge voxels: no walk */
-    if ((unsigned)fx >= (unsigned)(sc.nx - 1) || (unsigned)fy >= (unsigned)(sc.ny - 1) || (unsigned)fz >= (unsigned)(sc.nz - 1)) return 0.0f;
+    /* outside the grid the footprint is clamped to edge voxels */
+    if ((unsigned)fx >= (unsigned)(sc.nx - 1) || (unsigned)fy >= (unsigned)(sc.ny - 1) || (unsigned)fz >= (unsigned)(sc.nz - 1))
+        return sc.borderEmpty ? stepsToLeaveBox(k, q, dir) : 0.0f;
     const int sh = sc.occShift;
     int cx = fx >> sh, cy = fy >> sh, cz = fz >> sh;
     const float cs = (float)(1 << sh);
@@ -159,13 +175,20 @@ __device__ __forceinline__ float emptySteps(const DevScene& sc, const FastConsts
     const bool mx = fabsf(vx) > 1e-9f, my = fabsf(vy) > 1e-9f, mz = fabsf(vz) > 1e-9f;
     const float ix = mx ? __fdividef(1.0f, vx) : 0.0f, iy = my ? __fdividef(1.0f, vy) : 0.0f, iz = mz ? __fdividef(1.0f, vz) : 0.0f;
     const bool px = vx > 0.0f, py = vy > 0.0f, pz = vz > 0.0f;
+    /* the walk stays where floor(x) <= N-2, i.e. inside the region the test above calls "inside the grid" */
+    const float gx = px ? k.nxf - 1.0f : 0.0f, gy = py ? k.nyf - 1.0f : 0.0f, gz = pz ? k.nzf - 1.0f : 0.0f;
     float t = 0.0f, margin = 0.0f;
+    bool leftGrid = false, blocked = false;
 #pragma unroll 1
-    for (int it = 0; it < 96; ++it) {
+    for (int it = 0; it < maxLeaps; ++it) {
         const int cell = (cz * sc.ocy + cy) * sc.ocx + cx;
         const int r = (int)__ldg(sc.cellDist + cell) - 1; /* cells [c-r, c+r]^3 are empty */
-        /* exit planes of the cube along the direction of travel */
-        const float ex = (float)(px ? cx + r + 1 : cx - r) * cs, ey = (float)(py ? cy + r + 1 : cy - r) * cs, ez = (float)(pz ? cz + r + 1 : cz - r) * cs;
+        /* exit planes of the cube along the direction of travel, clamped to the grid */
+        float ex = (float)(px ? cx + r + 1 : cx - r) * cs, ey = (float)(py ? cy + r + 1 : cy - r) * cs, ez = (float)(pz ? cz + r + 1 : cz - r) * cs;
+        const bool cxg = px ? ex >= gx : ex <= gx, cyg = py ? ey >= gy : ey <= gy, czg = pz ? ez >= gz : ez <= gz;
+        ex = cxg ? gx : ex;
+        ey = cyg ? gy : ey;
+        ez = czg ? gz : ez;
         const float tx = mx ? (ex - x) * ix : big, ty = my ? (ey - y) * iy : big, tz = mz ? (ez - z) * iz : big;
         t = fminf(tx, fminf(ty, tz));
         /* cell the ray enters: the exit axis moves one cell past the cube face, the others follow the ray */
@@ -177,20 +200,27 @@ __device__ __forceinline__ float emptySteps(const DevScene& sc, const FastConsts
         if (ax) {
             nx_ = px ? cx + r + 1 : cx - r - 1;
             margin = fabsf(ix);
+            leftGrid = cxg;
         } else if (ay) {
             ny_ = py ? cy + r + 1 : cy - r - 1;
             margin = fabsf(iy);
+            leftGrid = cyg;
         } else {
             nz_ = pz ? cz + r + 1 : cz - r - 1;
             margin = fabsf(iz);
+            leftGrid = czg;
         }
-        if ((unsigned)nx_ >= (unsigned)sc.ocx || (unsigned)ny_ >= (unsigned)sc.ocy || (unsigned)nz_ >= (unsigned)sc.ocz) break;
+        leftGrid = leftGrid || (unsigned)nx_ >= (unsigned)sc.ocx || (unsigned)ny_ >= (unsigned)sc.ocy || (unsigned)nz_ >= (unsigned)sc.ocz;
+        if (leftGrid) break;
         cx = nx_;
         cy = ny_;
         cz = nz_;
         const int ncell = (cz * sc.ocy + cy) * sc.ocx + cx;
-        if ((occ[ncell >> 5] >> (ncell & 31)) & 1u) break;
+        blocked = ((occ[ncell >> 5] >> (ncell & 31)) & 1u) != 0u;
+        if (blocked) break;
     }
+    if (leftGrid && sc.borderEmpty) return stepsToLeaveBox(k, q, dir);
+    more = !leftGrid && !blocked;
     /* stay 0.01 voxel short of the plane that stopped the walk */
     return fmaxf(floorf(fminf(t - 0.01f * margin, 65535.0f)), 0.0f);
 }
@@ -304,8 +334,8 @@ __device__ __forceinline__ void writeResultFast(const DevScene& sc, const TraceJ
  * A waiting lane costs nothing but its slot; a phase entered with two lanes costs the whole warp its full
  * instruction stream, which is what the thresholds avoid.  Thresholds are ignored when nothing else can run.
  */
-template <bool SKIP>
-__global__ void __launch_bounds__(640, 2) k_trace_fast(const DevScene sc, const TraceJob job)
+template <bool SKIP, int MAXT>
+__global__ void __launch_bounds__(MAXT, 2) k_trace_fast(const DevScene sc, const TraceJob job)
 {
     extern __shared__ __align__(16) unsigned char smemRaw[];
     float* sChopped = reinterpret_cast<float*>(smemRaw);
@@ -377,12 +407,15 @@ __global__ void __launch_bounds__(640, 2) k_trace_fast(const DevScene sc, const 
         /* ---- B: empty-space phase: the tap at q fell into an empty cell ---- */
         if (SKIP && mSkip && (__popc(mSkip) >= job.skipMin || mBusy == 0u)) {
             if (st == F_SKIP) {
-                const float kf = emptySteps(sc, k, sOcc, s.q, s.dir);
+                bool more;
+                const float kf = emptySteps(sc, k, sOcc, s.q, s.dir, job.skipMaxIters, more);
                 s.q.x = fmaf(kf * s.dir.x, k.stepTs.x, s.q.x);
                 s.q.y = fmaf(kf * s.dir.y, k.stepTs.y, s.q.y);
                 s.q.z = fmaf(kf * s.dir.z, k.stepTs.z, s.q.z);
                 nSteps += (uint32_t)kf;
-                st = F_MARCH;
+                /* a walk cut short lands in an empty cell and continues next round; otherwise march on (the
+                 * in-box test of the march phase retires paths that left the box) */
+                st = (more && kf >= 1.0f) ? F_SKIP : F_MARCH;
             }
         }
 
@@ -460,16 +493,29 @@ cudaError_t KernelSet<true>::trace(const DevScene& sc, const TraceJob& job, cons
     const unsigned long long wantBlocks = (job.total + threads - 1) / threads;
     const unsigned long long maxBlocks = (unsigned long long)cfg.smCount * cfg.blocksPerSm;
     const int blocks = (int)(wantBlocks < maxBlocks ? (wantBlocks ? wantBlocks : 1) : maxBlocks);
-    cudaError_t e;
+    /* register budget follows the block size: 64 regs up to 512 threads, 56 up to 576, 48 up to 640 (2 blocks/SM) */
+#define DS_LAUNCH_FAST(SK, MT)                                                                                                 \
+    do {                                                                                                                       \
+        cudaError_t e = cudaFuncSetAttribute(k_trace_fast<SK, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        if (e != cudaSuccess) return e;                                                                                        \
+        k_trace_fast<SK, MT><<<blocks, threads, smem, st>>>(sc, job);                                                          \
+    } while (0)
     if (cfg.skipEmpty) {
-        e = cudaFuncSetAttribute(k_trace_fast<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        k_trace_fast<true><<<blocks, threads, smem, st>>>(sc, job);
+        if (threads <= 512)
+            DS_LAUNCH_FAST(true, 512);
+        else if (threads <= 576)
+            DS_LAUNCH_FAST(true, 576);
+        else
+            DS_LAUNCH_FAST(true, 640);
     } else {
-        e = cudaFuncSetAttribute(k_trace_fast<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        k_trace_fast<false><<<blocks, threads, smem, st>>>(sc, job);
+        if (threads <= 512)
+            DS_LAUNCH_FAST(false, 512);
+        else if (threads <= 576)
+            DS_LAUNCH_FAST(false, 576);
+        else
+            DS_LAUNCH_FAST(false, 640);
     }
+#undef DS_LAUNCH_FAST
     return cudaGetLastError();
 }
 
@@ -512,7 +558,8 @@ __global__ void __launch_bounds__(256) k_primary_prepass(const DevScene sc, cons
                 }
                 q = qn;
                 steps++;
-                const float kf = emptySteps(sc, k, sc.occ, q, dir);
+                bool more;
+                const float kf = emptySteps(sc, k, sc.occ, q, dir, 256, more);
                 q = mk(fmaf(kf * dir.x, k.stepTs.x, q.x), fmaf(kf * dir.y, k.stepTs.y, q.y), fmaf(kf * dir.z, k.stepTs.z, q.z));
                 steps += (uint32_t)kf;
             }
