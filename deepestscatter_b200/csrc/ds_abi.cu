@@ -366,6 +366,7 @@ static int runTrace(DsContext* ctx, TraceJob& job)
     job.skipMin = ctx->opt["skip_min"];
     job.skipKeep = ctx->opt["skip_keep"];
     job.skipMaxIters = ctx->opt["skip_max_iters"];
+    job.skipOpenDist = ctx->opt["skip_open_dist"];
     DS_CUDA(ctx, cudaMemsetAsync(ctx->queue, 0, sizeof(unsigned long long), ctx->stream));
     const LaunchConfig cfg = launchConfig(ctx);
     const bool prof = ctx->opt["profile_events"] != 0;
@@ -437,7 +438,7 @@ int ds_context_create(int device, DsContext** out)
     }
     ctx->opt["precision"] = DS_PRECISION_FAST;
     ctx->opt["variant"] = 0;
-    ctx->opt["block_threads"] = 640;
+    ctx->opt["block_threads"] = 576;
     ctx->opt["blocks_per_sm"] = 2;
     ctx->opt["skip_empty"] = 1;
     ctx->opt["march_keep_quarters"] = 2;
@@ -446,7 +447,8 @@ int ds_context_create(int device, DsContext** out)
     ctx->opt["regen_min"] = 4;
     ctx->opt["skip_min"] = 4;
     ctx->opt["skip_keep"] = 4;
-    ctx->opt["skip_max_iters"] = 4;
+    ctx->opt["skip_max_iters"] = 8;
+    ctx->opt["skip_open_dist"] = 2;
     ctx->opt["staging_subframes"] = 16;
     ctx->opt["stream_offset"] = 0;
     ctx->opt["profile_events"] = 0;
@@ -532,6 +534,7 @@ int ds_set_option(DsContext* ctx, const char* name, int value)
     if (n == "block_threads" && (value < 32 || value > 1024 || value % 32)) DS_FAIL(ctx, DS_ERR_INVALID, "block_threads must be 32..1024, multiple of 32");
     if (n == "blocks_per_sm" && (value < 1 || value > 32)) DS_FAIL(ctx, DS_ERR_INVALID, "blocks_per_sm must be 1..32");
     if (n == "precision" && value != DS_PRECISION_EXACT && value != DS_PRECISION_FAST) DS_FAIL(ctx, DS_ERR_INVALID, "precision must be 0 or 1");
+    if (n == "skip_open_dist" && value < 1) DS_FAIL(ctx, DS_ERR_INVALID, "skip_open_dist must be >= 1 (0 would leap out of occupied cells)");
     if (n == "staging_subframes" && value < 1) DS_FAIL(ctx, DS_ERR_INVALID, "staging_subframes must be >= 1");
     if (n == "march_max_iters" && value < 1) DS_FAIL(ctx, DS_ERR_INVALID, "march_max_iters must be >= 1");
     ctx->opt[n] = value;

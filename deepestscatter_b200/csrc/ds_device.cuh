@@ -107,7 +107,7 @@ struct DevScene {
     int borderEmpty;
 };
 
-constexpr int GUIDE_N = 4096;
+constexpr int GUIDE_N = 16384;
 
 /* ---- CU/random.cuh ---- */
 

@@ -30,6 +30,7 @@ struct TraceJob {
     int skipMin;       /* fast kernel: enter the empty-space phase with at least this many lanes */
     int skipKeep;      /* ... and leave it when fewer remain (and other lanes have work) */
     int skipMaxIters;
+    int skipOpenDist;  /* fast kernel: leave the march phase for the empty-space phase when the tap cell is at least this far (cells) from the cloud */
     /* JOB_RENDER: item = (subframe, 8x4 pixel tile, pixel in tile) */
     float eye[3], U[3], V[3], W[3];
     int width, height, tilesX;

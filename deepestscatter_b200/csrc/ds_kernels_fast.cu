@@ -68,14 +68,14 @@ __device__ __forceinline__ bool inBoxTs(const FastConsts& k, V3 q)
 __device__ __forceinline__ float invertCdf(const float* sCdf, const uint16_t* sGuide, float val)
 {
     const int k = min((int)(val * (float)GUIDE_N), GUIDE_N - 1);
-    /* lower bound of val in cdf[lo, lo + n): n <= 31 (GUIDE_N = 4096), five branch-free halvings */
-    int lo = sGuide[k], n = (int)sGuide[k + 1] - lo;
-#pragma unroll
-    for (int i = 0; i < 5; i++) {
-        const int half = n >> 1;
-        const bool right = n > 0 && sCdf[min(lo + half, MIE_N - 1)] < val;
-        lo = right ? lo + half + 1 : lo;
-        n = right ? n - half - 1 : half;
+    /* first index with cdf[i] >= val; with GUIDE_N = 16384 85 % of the buckets hold no table knot at all */
+    int lo = sGuide[k], hi = sGuide[k + 1];
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (sCdf[mid] < val)
+            lo = mid + 1;
+        else
+            hi = mid;
     }
     float u;
     if (lo == 0) {
@@ -138,6 +138,16 @@ __device__ __forceinline__ bool tapCellEmpty(const DevScene& sc, const FastConst
     return ((occ[cell >> 5] >> (cell & 31)) & 1u) == 0u;
 }
 
+/* Chebyshev distance (cells) from the tap cell of q to the nearest occupied cell; 0 = the cell is occupied */
+__device__ __forceinline__ int tapCellDistance(const DevScene& sc, const FastConsts& k, V3 q)
+{
+    const int fx = __float2int_rd(fmaf(q.x, k.nxf, -0.5f)), fy = __float2int_rd(fmaf(q.y, k.nyf, -0.5f)), fz = __float2int_rd(fmaf(q.z, k.nzf, -0.5f));
+    const int cx = min(max(fx, 0), sc.nx - 1) >> sc.occShift;
+    const int cy = min(max(fy, 0), sc.ny - 1) >> sc.occShift;
+    const int cz = min(max(fz, 0), sc.nz - 1) >> sc.occShift;
+    return (int)__ldg(sc.cellDist + (cz * sc.ocy + cy) * sc.ocx + cx);
+}
+
 /* whole march steps until the position leaves the in-box slab (the reference's `while (isInBox(pos))`) */
 __device__ __forceinline__ float stepsToLeaveBox(const FastConsts& k, V3 q, V3 dir)
 {
@@ -147,6 +157,33 @@ __device__ __forceinline__ float stepsToLeaveBox(const FastConsts& k, V3 q, V3 d
     const float ty = fabsf(dy) > 1e-12f ? __fdividef((dy > 0.0f ? 0.5f + k.half.y : 0.5f - k.half.y) - q.y, dy) : big;
     const float tz = fabsf(dz) > 1e-12f ? __fdividef((dz > 0.0f ? 0.5f + k.half.z : 0.5f - k.half.z) - q.z, dz) : big;
     return fmaxf(floorf(fminf(fminf(tx, ty), fminf(tz, 65534.0f))) + 1.0f, 0.0f);
+}
+
+/* The footprint at q is outside the grid and all face voxels are zero: every tap reads 0 until the ray enters the
+ * region floor(x) in [0, N-2] (slab test), or until it leaves the box if it never does. */
+__device__ __forceinline__ float outsideGridSteps(const FastConsts& k, V3 q, V3 dir, float x, float y, float z)
+{
+    const float vx = dir.x * k.stepTs.x * k.nxf, vy = dir.y * k.stepTs.y * k.nyf, vz = dir.z * k.stepTs.z * k.nzf;
+    const float big = 1.0e30f;
+    float tn = -big, tf = big, margin = 0.0f;
+    const float v[3] = {vx, vy, vz}, p[3] = {x, y, z}, hi[3] = {k.nxf - 1.0f, k.nyf - 1.0f, k.nzf - 1.0f};
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+        if (fabsf(v[a]) > 1e-9f) {
+            const float inv = __fdividef(1.0f, v[a]);
+            const float t0 = (0.0f - p[a]) * inv, t1 = (hi[a] - p[a]) * inv;
+            const float lo_ = fminf(t0, t1), hi_ = fmaxf(t0, t1);
+            if (lo_ > tn) {
+                tn = lo_;
+                margin = fabsf(inv);
+            }
+            tf = fminf(tf, hi_);
+        } else if (p[a] < 0.0f || p[a] >= hi[a]) {
+            tn = big; /* parallel to the slab and outside it */
+        }
+    }
+    if (tn < tf && tf > 0.0f) return fmaxf(floorf(fminf(tn - 0.01f * margin, 65535.0f)), 0.0f); /* enters the grid */
+    return stepsToLeaveBox(k, q, dir);
 }
 
 /*
@@ -166,7 +203,7 @@ __device__ __forceinline__ float emptySteps(const DevScene& sc, const FastConsts
     const int fx = __float2int_rd(x), fy = __float2int_rd(y), fz = __float2int_rd(z);
     /* outside the grid the footprint is clamped to edge voxels */
     if ((unsigned)fx >= (unsigned)(sc.nx - 1) || (unsigned)fy >= (unsigned)(sc.ny - 1) || (unsigned)fz >= (unsigned)(sc.nz - 1))
-        return sc.borderEmpty ? stepsToLeaveBox(k, q, dir) : 0.0f;
+        return sc.borderEmpty ? outsideGridSteps(k, q, dir, x, y, z) : 0.0f;
     const int sh = sc.occShift;
     int cx = fx >> sh, cy = fy >> sh, cz = fz >> sh;
     const float cs = (float)(1 << sh);
@@ -435,8 +472,9 @@ __global__ void __launch_bounds__(MAXT, 2) k_trace_fast(const DevScene sc, const
                         nTaps++;
                         lastDensity = tex3D<float>(sc.densityTex, s.q.x, s.q.y, s.q.z);
                         if (lastDensity == 0.0f) {
-                            /* left the cloud, or a hole inside an occupied cell */
-                            if (SKIP && tapCellEmpty(sc, k, sOcc, s.q)) st = F_SKIP;
+                            /* left the cloud, or a hole in it: leap only in open space (no occupied cell among the 26
+                             * neighbours); pockets next to the cloud are cheaper to march through */
+                            if (SKIP && tapCellDistance(sc, k, s.q) >= job.skipOpenDist) st = F_SKIP;
                         } else {
                             s.tau = fmaf(lastDensity, k.c1, s.tau);
                             if (s.tau > s.tauStar) st = F_EVENT;

@@ -240,7 +240,7 @@ def test_fast_flavour_is_deterministic_under_scheduling_knobs(built_library):
             assert np.array_equal(again.view(np.uint32), base.view(np.uint32)), opts
             assert c == c0, opts
             for k, val in dict(regen_min=8, skip_min=8, skip_keep=4, march_keep32=12, march_max_iters=64, skip_max_iters=32,
-                               block_threads=640, blocks_per_sm=2).items():
+                               block_threads=576, blocks_per_sm=2).items():
                 ctx.set_option(k, val)
         # without the primary-ray cache every pixel is traced from the box face: same silhouette, same counters
         ctx.set_option("primary_cache", 0)
