@@ -236,7 +236,8 @@ static void fillDevScene(DsContext* ctx, DevScene& sc)
     sc.ocz = ctx->ocz;
     sc.occWords = ctx->occWords;
     sc.cellDist = ctx->cellDist;
-    sc.guide = ctx->guide;
+    sc.guideN = ctx->opt["guide_n"] == GUIDE_MAX ? GUIDE_MAX : 4096;
+    sc.guide = sc.guideN == 4096 ? ctx->guide : ctx->guide + 4097;
     sc.borderEmpty = ctx->borderEmpty;
 }
 
@@ -448,7 +449,8 @@ int ds_context_create(int device, DsContext** out)
     ctx->opt["skip_min"] = 4;
     ctx->opt["skip_keep"] = 4;
     ctx->opt["skip_max_iters"] = 8;
-    ctx->opt["skip_open_dist"] = 2;
+    ctx->opt["skip_open_dist"] = 1;
+    ctx->opt["guide_n"] = 4096;
     ctx->opt["staging_subframes"] = 16;
     ctx->opt["stream_offset"] = 0;
     ctx->opt["profile_events"] = 0;
@@ -467,14 +469,19 @@ int ds_context_create(int device, DsContext** out)
             memcpy(raw.data(), ds_mie_blob, raw.size() * sizeof(float));
             buildMieSamplers(raw.data(), raw.data() + MIE_N, samplers.data());
             ok = cudaMemcpy(ctx->mie, samplers.data(), samplers.size() * sizeof(float), cudaMemcpyHostToDevice) == cudaSuccess;
-            /* guide[k] = first index with cdf[i] >= k / GUIDE_N (binary-search bounds for the fast CDF inversion) */
-            std::vector<uint16_t> guide(GUIDE_N + 1);
+            /* guide[k] = first index with cdf[i] >= k / N (binary-search bounds for the fast CDF inversion); two
+             * resolutions are kept, option "guide_n" picks one */
+            std::vector<uint16_t> guide((4096 + 1) + (GUIDE_MAX + 1));
             const float* cdf = samplers.data() + 2 * MIE_N;
-            int idx = 0;
-            for (int k = 0; k <= GUIDE_N; k++) {
-                const float v = (float)k / (float)GUIDE_N;
-                while (idx < MIE_N && cdf[idx] < v) idx++;
-                guide[k] = (uint16_t)idx;
+            size_t off = 0;
+            for (int n : {4096, GUIDE_MAX}) {
+                int idx = 0;
+                for (int k = 0; k <= n; k++) {
+                    const float v = (float)k / (float)n;
+                    while (idx < MIE_N && cdf[idx] < v) idx++;
+                    guide[off + k] = (uint16_t)idx;
+                }
+                off += n + 1;
             }
             ok = ok && cudaMalloc(&ctx->guide, guide.size() * sizeof(uint16_t)) == cudaSuccess &&
                  cudaMemcpy(ctx->guide, guide.data(), guide.size() * sizeof(uint16_t), cudaMemcpyHostToDevice) == cudaSuccess;
@@ -534,6 +541,7 @@ int ds_set_option(DsContext* ctx, const char* name, int value)
     if (n == "block_threads" && (value < 32 || value > 1024 || value % 32)) DS_FAIL(ctx, DS_ERR_INVALID, "block_threads must be 32..1024, multiple of 32");
     if (n == "blocks_per_sm" && (value < 1 || value > 32)) DS_FAIL(ctx, DS_ERR_INVALID, "blocks_per_sm must be 1..32");
     if (n == "precision" && value != DS_PRECISION_EXACT && value != DS_PRECISION_FAST) DS_FAIL(ctx, DS_ERR_INVALID, "precision must be 0 or 1");
+    if (n == "guide_n" && value != 4096 && value != GUIDE_MAX) DS_FAIL(ctx, DS_ERR_INVALID, "guide_n must be 4096 or 16384");
     if (n == "skip_open_dist" && value < 1) DS_FAIL(ctx, DS_ERR_INVALID, "skip_open_dist must be >= 1 (0 would leap out of occupied cells)");
     if (n == "staging_subframes" && value < 1) DS_FAIL(ctx, DS_ERR_INVALID, "staging_subframes must be >= 1");
     if (n == "march_max_iters" && value < 1) DS_FAIL(ctx, DS_ERR_INVALID, "march_max_iters must be >= 1");

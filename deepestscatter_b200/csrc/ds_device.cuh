@@ -100,14 +100,15 @@ struct DevScene {
     int occWords;
     /* Chebyshev distance (in cells, saturated at 255) from each cell to the nearest occupied cell; 0 = occupied */
     const uint8_t* cellDist;
-    /* guide table of the chopped-Mie CDF: guide[k] = first index i with cdf[i] >= k / GUIDE_N, k = 0..GUIDE_N */
+    /* guide table of the chopped-Mie CDF: guide[k] = first index i with cdf[i] >= k / guideN, k = 0..guideN */
     const uint16_t* guide;
+    int guideN;
     /* 1 when every voxel on the six faces of the grid is zero (VDB imports are padded by one voxel,
      * Resources.cpp:97-101): clamped taps outside the grid then read 0 */
     int borderEmpty;
 };
 
-constexpr int GUIDE_N = 16384;
+constexpr int GUIDE_MAX = 16384;
 
 /* ---- CU/random.cuh ---- */
 

@@ -65,10 +65,10 @@ __device__ __forceinline__ bool inBoxTs(const FastConsts& k, V3 q)
 }
 
 /* closed-form inverse of the piecewise-linear CDF that cloud.cuh:167-178 bisects */
-__device__ __forceinline__ float invertCdf(const float* sCdf, const uint16_t* sGuide, float val)
+__device__ __forceinline__ float invertCdf(const float* sCdf, const uint16_t* sGuide, int guideN, float val)
 {
-    const int k = min((int)(val * (float)GUIDE_N), GUIDE_N - 1);
-    /* first index with cdf[i] >= val; with GUIDE_N = 16384 85 % of the buckets hold no table knot at all */
+    const int k = min((int)(val * (float)guideN), guideN - 1);
+    /* first index with cdf[i] >= val; most guide buckets hold no table knot at all (66 % at 4096, 85 % at 16384) */
     int lo = sGuide[k], hi = sGuide[k + 1];
     while (lo < hi) {
         const int mid = (lo + hi) >> 1;
@@ -91,10 +91,10 @@ __device__ __forceinline__ float invertCdf(const float* sCdf, const uint16_t* sG
 }
 
 /* CU/cloud.cuh:160-188 */
-__device__ __forceinline__ V3 newDirectionFast(const float* sCdf, const uint16_t* sGuide, uint32_t& seed, V3 prev)
+__device__ __forceinline__ V3 newDirectionFast(const float* sCdf, const uint16_t* sGuide, int guideN, uint32_t& seed, V3 prev)
 {
     const float val = rnd(seed);
-    const float cosTheta = invertCdf(sCdf, sGuide, val);
+    const float cosTheta = invertCdf(sCdf, sGuide, guideN, val);
     const float phi = rnd(seed) * (PI_F * 2.0f);
     const float s2 = fmaxf(fmaf(-cosTheta, cosTheta, 1.0f), 0.0f);
     const float sinTheta = s2 * rsqrtf(fmaxf(s2, 1.0e-30f));
@@ -330,7 +330,7 @@ __device__ __forceinline__ int beginItemFast(const DevScene& sc, const FastConst
     s.dir = normalize<true>(d);
     s.seed = tea4(val0, stream);
     s.depth = 0;
-    if (job.mode == DS_MODE_SUN_MULTIPLE_SCATTER) s.dir = newDirectionFast(sCdf, sGuide, s.seed, s.dir);
+    if (job.mode == DS_MODE_SUN_MULTIPLE_SCATTER) s.dir = newDirectionFast(sCdf, sGuide, sc.guideN, s.seed, s.dir);
     if (!beginFlight<true>(k, s)) return F_DONE;
     if (job.kind == JOB_RENDER && job.entrySteps) {
         /* cached empty-space leg of the primary ray: start at the cloud surface */
@@ -378,12 +378,12 @@ __global__ void __launch_bounds__(MAXT, 2) k_trace_fast(const DevScene sc, const
     float* sChopped = reinterpret_cast<float*>(smemRaw);
     float* sCdf = sChopped + MIE_N;
     uint16_t* sGuide = reinterpret_cast<uint16_t*>(sCdf + MIE_N);
-    uint32_t* sOcc = reinterpret_cast<uint32_t*>(sGuide + GUIDE_N + 2);
+    uint32_t* sOcc = reinterpret_cast<uint32_t*>(sGuide + sc.guideN + 2);
     for (int i = threadIdx.x; i < MIE_N; i += blockDim.x) {
         sChopped[i] = sc.chopped[i];
         sCdf[i] = sc.cdf[i];
     }
-    for (int i = threadIdx.x; i <= GUIDE_N; i += blockDim.x) sGuide[i] = sc.guide[i];
+    for (int i = threadIdx.x; i <= sc.guideN; i += blockDim.x) sGuide[i] = sc.guide[i];
     for (int i = threadIdx.x; i < sc.occWords; i += blockDim.x) sOcc[i] = sc.occ[i];
     __syncthreads();
 
@@ -506,7 +506,7 @@ __global__ void __launch_bounds__(MAXT, 2) k_trace_fast(const DevScene sc, const
                 if (job.mode == DS_MODE_SUN_SINGLE_SCATTER) {
                     st = F_DONE;
                 } else {
-                    s.dir = newDirectionFast(sCdf, sGuide, s.seed, s.dir);
+                    s.dir = newDirectionFast(sCdf, sGuide, sc.guideN, s.seed, s.dir);
                     st = beginFlight<false>(k, s) ? F_MARCH : F_DONE; /* q is the scatter position just verified in-box */
                 }
             }
@@ -526,7 +526,7 @@ template <>
 cudaError_t KernelSet<true>::trace(const DevScene& sc, const TraceJob& job, const LaunchConfig& cfg, cudaStream_t st)
 {
     if (cfg.variant == 1) return traceGeneric<true>(sc, job, cfg, st);
-    const size_t smem = (size_t)(2 * MIE_N) * 4 + (size_t)(GUIDE_N + 2) * 2 + (size_t)sc.occWords * 4;
+    const size_t smem = (size_t)(2 * MIE_N) * 4 + (size_t)(sc.guideN + 2) * 2 + (size_t)sc.occWords * 4;
     const int threads = cfg.blockThreads > 640 ? 640 : cfg.blockThreads;
     const unsigned long long wantBlocks = (job.total + threads - 1) / threads;
     const unsigned long long maxBlocks = (unsigned long long)cfg.smCount * cfg.blocksPerSm;

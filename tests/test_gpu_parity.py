@@ -231,15 +231,17 @@ def test_fast_flavour_is_deterministic_under_scheduling_knobs(built_library):
         base = ctx.render_frame(cam, 0, 7)
         c0 = ctx.counters()
         for opts in (dict(regen_min=1, skip_min=1, skip_keep=1), dict(regen_min=32, skip_min=32, skip_keep=16), dict(march_keep32=0),
-                     dict(march_keep32=31, march_max_iters=2, skip_max_iters=1), dict(block_threads=64, blocks_per_sm=1)):
+                     dict(march_keep32=31, march_max_iters=2, skip_max_iters=1), dict(block_threads=64, blocks_per_sm=1),
+                     dict(guide_n=16384, skip_open_dist=3)):
             for k, val in opts.items():
                 ctx.set_option(k, val)
             ctx.counters_reset()
             again = ctx.render_frame(cam, 0, 7)
             c = ctx.counters()
             assert np.array_equal(again.view(np.uint32), base.view(np.uint32)), opts
-            assert c == c0, opts
-            for k, val in dict(regen_min=8, skip_min=8, skip_keep=4, march_keep32=12, march_max_iters=64, skip_max_iters=32,
+            # taps may differ (a leap cut short re-taps a known-empty cell); the reference-algorithm counts may not
+            assert (c["paths"], c["events"], c["steps"]) == (c0["paths"], c0["events"], c0["steps"]), opts
+            for k, val in dict(regen_min=4, skip_min=4, skip_keep=4, march_keep32=8, march_max_iters=64, skip_max_iters=8, guide_n=4096, skip_open_dist=1,
                                block_threads=576, blocks_per_sm=2).items():
                 ctx.set_option(k, val)
         # without the primary-ray cache every pixel is traced from the box face: same silhouette, same counters
