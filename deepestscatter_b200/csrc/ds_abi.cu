@@ -444,11 +444,11 @@ int ds_context_create(int device, DsContext** out)
     ctx->opt["skip_empty"] = 1;
     ctx->opt["march_keep_quarters"] = 2;
     ctx->opt["march_max_iters"] = 64;
-    ctx->opt["march_keep32"] = 8;
-    ctx->opt["regen_min"] = 4;
-    ctx->opt["skip_min"] = 4;
+    ctx->opt["march_keep32"] = 12;
+    ctx->opt["regen_min"] = 2;
+    ctx->opt["skip_min"] = 8;
     ctx->opt["skip_keep"] = 4;
-    ctx->opt["skip_max_iters"] = 8;
+    ctx->opt["skip_max_iters"] = 32;
     ctx->opt["skip_open_dist"] = 1;
     ctx->opt["guide_n"] = 4096;
     ctx->opt["staging_subframes"] = 16;
