@@ -51,8 +51,8 @@ def parse_args():
     ap.add_argument("--opt", action="append", default=[], help="library option name=value (tuning)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU work for the cpu_baseline sample")
-    ap.add_argument("--ref-width", type=int, default=240)
-    ap.add_argument("--ref-height", type=int, default=135)
+    ap.add_argument("--ref-width", type=int, default=480)
+    ap.add_argument("--ref-height", type=int, default=270)
     return ap.parse_args()
 
 
@@ -223,6 +223,7 @@ def run_ours(a):
     import torch.distributed as dist
 
     import deepestscatter_b200 as ds
+    from deepestscatter_b200 import multigpu
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -290,7 +291,7 @@ def run_ours(a):
         if distributed:
             # the single NCCL reduce of the per-GPU accumulation buffers (as mergeable moments)
             ctx.export_moments(sub - 1, moments.data_ptr())
-            dist.reduce(moments, dst=0, op=dist.ReduceOp.SUM)
+            multigpu.reduce_moments(moments, dst=0)
             if rank == 0:
                 ctx.import_moments((sub - 1) * world, moments.data_ptr())
         ev1.record(stream)

@@ -232,7 +232,7 @@ def test_fast_flavour_is_deterministic_under_scheduling_knobs(built_library):
         c0 = ctx.counters()
         for opts in (dict(regen_min=1, skip_min=1, skip_keep=1), dict(regen_min=32, skip_min=32, skip_keep=16), dict(march_keep32=0),
                      dict(march_keep32=31, march_max_iters=2), dict(block_threads=64, blocks_per_sm=1),
-                     dict(guide_n=16384, skip_open_dist=3)):
+                     dict(guide_n=16384)):
             for k, val in opts.items():
                 ctx.set_option(k, val)
             ctx.counters_reset()
@@ -247,8 +247,10 @@ def test_fast_flavour_is_deterministic_under_scheduling_knobs(built_library):
         # cutting leap walks short splits one jump into several (different fp rounding of the landing point): same
         # silhouette and statistics, not the same bits
         ctx.set_option("skip_max_iters", 1)
+        ctx.set_option("skip_open_dist", 3)
         cut = ctx.render_frame(cam, 0, 7)
         ctx.set_option("skip_max_iters", 32)
+        ctx.set_option("skip_open_dist", 1)
         assert np.array_equal(cut[..., 0] == 0, base[..., 0] == 0)
         assert abs(float(cut[..., 0].mean()) - float(base[..., 0].mean())) < 0.25 * float(base[..., 0].mean())
         # without the primary-ray cache every pixel is traced from the box face: same silhouette, same counters
