@@ -24,12 +24,14 @@ def main():
     ap.add_argument("--size", type=float, default=7000.0)
     ap.add_argument("--sun", default="-0.586,-0.766,-0.271")
     ap.add_argument("--mode", type=int, default=0)
+    ap.add_argument("--kind", type=int, default=0)
+    ap.add_argument("--tag", default="")
     ap.add_argument("--out", default=None)
     ap.add_argument("--set", action="append", default=[], help="name=v1,v2,... (cartesian product)")
     a = ap.parse_args()
     sun = tuple(float(x) for x in a.sun.split(","))
     ctx = ds.Context(0)
-    ctx.volume_synth(a.grid, 0, 1234, True)
+    ctx.volume_synth(a.grid, a.kind, 1234, True)
     ctx.scene_set(a.size, sun)
     baked = {}
     ctx.frame_create(a.width, a.height)
@@ -62,7 +64,7 @@ def main():
         c = ctx.counters()
         ls = ctx.launch_stats()
         p, _ = ctx.frame_download()
-        rec = dict(opts=opts, precision=prec, mpaths_s=c["paths"] / dt / 1e6, gevents_s=c["events"] / dt / 1e9, gsteps_s=c["steps"] / dt / 1e9,
+        rec = dict(tag=a.tag, opts=opts, nonfinite=c['nonfinite'], precision=prec, mpaths_s=c["paths"] / dt / 1e6, gevents_s=c["events"] / dt / 1e9, gsteps_s=c["steps"] / dt / 1e9,
                    gtaps_s=c["density_taps"] / dt / 1e9, events_per_path=c["events"] / c["paths"], steps_per_path=c["steps"] / c["paths"],
                    trace_ms=ls["trace_ms_total"] / max(1, ls["trace_launches_timed"]), wall_s=dt, bake_s=bake_s,
                    alg_gbs=(8 * c["steps"] + 8 * c["events"]) / (ls["trace_ms_total"] * 1e-3) / 1e9, mean=float(p[..., 0].mean()))
