@@ -1,0 +1,8 @@
+#!/bin/bash
+# profile session for the current k_trace_fast: gpu tests, default bench, ncu launch list of the same command, one --set full capture
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests -m gpu -q --timeout 300 --timeout-method thread > gpurun_out/pytest_gpu_l.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/pytest_gpu_l.log
+timeout 900 python bench.py > gpurun_out/bench_l.log 2>&1; echo "bench rc=$?"; tail -c 2500 gpurun_out/bench_l.log
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_r1l.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_launches_l.log 2>&1; echo "ncu list rc=$?"
+timeout 1200 ncu --set full --clock-control none --import-source on -k regex:k_trace_fast -s 1 -c 1 -o gpurun_out/prof_trace_r1l python bench.py --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_full_l.log 2>&1; echo "ncu full rc=$?"
+ls -la gpurun_out
