@@ -37,6 +37,9 @@ struct DsContext {
     bool baked = false;
     cudaArray_t densityArr = nullptr, inscatterArr = nullptr;
     cudaTextureObject_t densityTex = 0, inscatterTex = 0;
+    /* texture layout 1 (k_trace_fast): 2-D layered RG8 z-pair copies of both volumes */
+    cudaArray_t densityPairArr = nullptr, inscatterPairArr = nullptr;
+    cudaTextureObject_t densityPairTex = 0, inscatterPairTex = 0;
     uint32_t* occ = nullptr;
     uint8_t* cellDist = nullptr;
     int occShift = 0, ocx = 0, ocy = 0, ocz = 0, occWords = 0;
@@ -47,7 +50,7 @@ struct DsContext {
     bool sceneSet = false;
     float derived[12] = {0};
     float* mie = nullptr;     /* 3 * 4096 floats: mie, chopped, cdf */
-    uint16_t* guide = nullptr; /* GUIDE_N + 1 entries */
+    uint16_t* guide = nullptr; /* GUIDE_A_N + GUIDE_B_N packed entries (DevScene::guideA / guideB) */
 
     /* frame */
     int width = 0, height = 0;
@@ -127,6 +130,12 @@ static void freeVolume(DsContext* ctx)
     if (ctx->densityArr) cudaFreeArray(ctx->densityArr);
     if (ctx->inscatterArr) cudaFreeArray(ctx->inscatterArr);
     ctx->densityArr = ctx->inscatterArr = nullptr;
+    if (ctx->densityPairTex) cudaDestroyTextureObject(ctx->densityPairTex);
+    if (ctx->inscatterPairTex) cudaDestroyTextureObject(ctx->inscatterPairTex);
+    ctx->densityPairTex = ctx->inscatterPairTex = 0;
+    if (ctx->densityPairArr) cudaFreeArray(ctx->densityPairArr);
+    if (ctx->inscatterPairArr) cudaFreeArray(ctx->inscatterPairArr);
+    ctx->densityPairArr = ctx->inscatterPairArr = nullptr;
     if (ctx->occ) cudaFree(ctx->occ);
     ctx->occ = nullptr;
     if (ctx->cellDist) cudaFree(ctx->cellDist);
@@ -205,6 +214,37 @@ static int makeTexture(DsContext* ctx, const uint8_t* linear, int nx, int ny, in
     return DS_OK;
 }
 
+/* z-pair layout: a 2-D layered RG8 array, layer z = {v[z], v[min(z + 1, nz - 1)]}, bilinear within a layer.
+ * Skipped (texture object left 0 -> the 3-D layout is used) when the volume exceeds the layered-texture limits. */
+static int makePairTexture(DsContext* ctx, const uint8_t* linear, int nx, int ny, int nz, cudaArray_t* arr, cudaTextureObject_t* tex)
+{
+    if (*tex) {
+        cudaDestroyTextureObject(*tex);
+        *tex = 0;
+    }
+    if (nx > ctx->prop.maxTexture2DLayered[0] || ny > ctx->prop.maxTexture2DLayered[1] || nz > ctx->prop.maxTexture2DLayered[2]) return DS_OK;
+    if (!*arr) {
+        cudaChannelFormatDesc cd = cudaCreateChannelDesc<uchar2>();
+        DS_CUDA(ctx, cudaMalloc3DArray(arr, &cd, make_cudaExtent(nx, ny, nz), cudaArrayLayered | cudaArraySurfaceLoadStore));
+    }
+    cudaResourceDesc rd = {};
+    rd.resType = cudaResourceTypeArray;
+    rd.res.array.array = *arr;
+    cudaSurfaceObject_t surf = 0;
+    DS_CUDA(ctx, cudaCreateSurfaceObject(&surf, &rd));
+    cudaError_t e = launchPackZPair(linear, nx, ny, nz, surf, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaDestroySurfaceObject(surf);
+    DS_CUDA(ctx, e);
+    cudaTextureDesc td = {};
+    td.addressMode[0] = td.addressMode[1] = td.addressMode[2] = cudaAddressModeClamp;
+    td.filterMode = cudaFilterModeLinear;
+    td.readMode = cudaReadModeNormalizedFloat;
+    td.normalizedCoords = 1;
+    DS_CUDA(ctx, cudaCreateTextureObject(tex, &rd, &td, nullptr));
+    return DS_OK;
+}
+
 static void fillDevScene(DsContext* ctx, DevScene& sc)
 {
     memset(&sc, 0, sizeof(sc));
@@ -236,8 +276,10 @@ static void fillDevScene(DsContext* ctx, DevScene& sc)
     sc.ocz = ctx->ocz;
     sc.occWords = ctx->occWords;
     sc.cellDist = ctx->cellDist;
-    sc.guideN = ctx->opt["guide_n"] == GUIDE_MAX ? GUIDE_MAX : 4096;
-    sc.guide = sc.guideN == 4096 ? ctx->guide : ctx->guide + 4097;
+    sc.guideA = ctx->guide;
+    sc.guideB = ctx->guide + GUIDE_A_N;
+    sc.densityPairTex = ctx->densityPairTex;
+    sc.inscatterPairTex = ctx->inscatterPairTex;
     sc.borderEmpty = ctx->borderEmpty;
 }
 
@@ -311,6 +353,8 @@ static int finishVolume(DsContext* ctx, int buildMips)
     }
     int rc = makeTexture(ctx, ctx->levels[0], nx, ny, nz, &ctx->densityArr, &ctx->densityTex);
     if (rc) return rc;
+    rc = makePairTexture(ctx, ctx->levels[0], nx, ny, nz, &ctx->densityPairArr, &ctx->densityPairTex);
+    if (rc) return rc;
     DS_CUDA(ctx, cudaMalloc(&ctx->inscatter, (size_t)nx * ny * nz));
     DS_CUDA(ctx, cudaMemsetAsync(ctx->inscatter, 0, (size_t)nx * ny * nz, ctx->stream));
     computeDerived(ctx);
@@ -351,6 +395,8 @@ static LaunchConfig launchConfig(DsContext* ctx)
     cfg.smCount = ctx->prop.multiProcessorCount;
     cfg.skipEmpty = ctx->opt["skip_empty"];
     cfg.variant = ctx->opt["variant"];
+    cfg.texLayout = ctx->opt["tex_layout"];
+    cfg.marchUnroll = ctx->opt["march_unroll"];
     return cfg;
 }
 
@@ -365,7 +411,6 @@ static int runTrace(DsContext* ctx, TraceJob& job)
     job.marchKeep32 = ctx->opt["march_keep32"];
     job.regenMin = ctx->opt["regen_min"];
     job.skipMin = ctx->opt["skip_min"];
-    job.skipKeep = ctx->opt["skip_keep"];
     job.skipMaxIters = ctx->opt["skip_max_iters"];
     job.skipOpenDist = ctx->opt["skip_open_dist"];
     DS_CUDA(ctx, cudaMemsetAsync(ctx->queue, 0, sizeof(unsigned long long), ctx->stream));
@@ -447,10 +492,10 @@ int ds_context_create(int device, DsContext** out)
     ctx->opt["march_keep32"] = 12;
     ctx->opt["regen_min"] = 2;
     ctx->opt["skip_min"] = 8;
-    ctx->opt["skip_keep"] = 4;
     ctx->opt["skip_max_iters"] = 32;
     ctx->opt["skip_open_dist"] = 1;
-    ctx->opt["guide_n"] = 4096;
+    ctx->opt["tex_layout"] = 1;
+    ctx->opt["march_unroll"] = 1;
     ctx->opt["staging_subframes"] = 16;
     ctx->opt["stream_offset"] = 0;
     ctx->opt["profile_events"] = 0;
@@ -469,19 +514,30 @@ int ds_context_create(int device, DsContext** out)
             memcpy(raw.data(), ds_mie_blob, raw.size() * sizeof(float));
             buildMieSamplers(raw.data(), raw.data() + MIE_N, samplers.data());
             ok = cudaMemcpy(ctx->mie, samplers.data(), samplers.size() * sizeof(float), cudaMemcpyHostToDevice) == cudaSuccess;
-            /* guide[k] = first index with cdf[i] >= k / N (binary-search bounds for the fast CDF inversion); two
-             * resolutions are kept, option "guide_n" picks one */
-            std::vector<uint16_t> guide((4096 + 1) + (GUIDE_MAX + 1));
+            /* two-level guide of the CDF inversion (DevScene::guideA / guideB): entry = lo | n << 13 */
+            std::vector<uint16_t> guide(GUIDE_A_N + GUIDE_B_N);
             const float* cdf = samplers.data() + 2 * MIE_N;
-            size_t off = 0;
-            for (int n : {4096, GUIDE_MAX}) {
-                int idx = 0;
-                for (int k = 0; k <= n; k++) {
-                    const float v = (float)k / (float)n;
+            auto fill = [&](uint16_t* dst, int buckets, float limit) {
+                int idx = 0, maxKnots = 0;
+                std::vector<int> first(buckets + 1);
+                for (int k = 0; k <= buckets; k++) {
+                    const float v = (float)k / (float)buckets * limit; /* exact: powers of two */
                     while (idx < MIE_N && cdf[idx] < v) idx++;
-                    guide[off + k] = (uint16_t)idx;
+                    first[k] = idx;
                 }
-                off += n + 1;
+                for (int k = 0; k < buckets; k++) {
+                    /* buckets of guideA below the limit are never looked up (guideB serves them) */
+                    const int n = first[k + 1] - first[k];
+                    const bool used = limit < 1.0f || (float)(k + 1) / (float)buckets > GUIDE_B_LIMIT;
+                    if (used) maxKnots = std::max(maxKnots, n);
+                    dst[k] = (uint16_t)(first[k] | (std::min(n, 3) << 13));
+                }
+                return maxKnots;
+            };
+            const int mA = fill(guide.data(), GUIDE_A_N, 1.0f), mB = fill(guide.data() + GUIDE_A_N, GUIDE_B_N, GUIDE_B_LIMIT);
+            if (mA > 2 || mB > 2 || !(cdf[MIE_N - 1] >= 1.0f)) {
+                g_createError = "chopped-Mie CDF does not fit the two-level guide (more than 2 knots in a bucket)";
+                ok = false;
             }
             ok = ok && cudaMalloc(&ctx->guide, guide.size() * sizeof(uint16_t)) == cudaSuccess &&
                  cudaMemcpy(ctx->guide, guide.data(), guide.size() * sizeof(uint16_t), cudaMemcpyHostToDevice) == cudaSuccess;
@@ -541,7 +597,8 @@ int ds_set_option(DsContext* ctx, const char* name, int value)
     if (n == "block_threads" && (value < 32 || value > 1024 || value % 32)) DS_FAIL(ctx, DS_ERR_INVALID, "block_threads must be 32..1024, multiple of 32");
     if (n == "blocks_per_sm" && (value < 1 || value > 32)) DS_FAIL(ctx, DS_ERR_INVALID, "blocks_per_sm must be 1..32");
     if (n == "precision" && value != DS_PRECISION_EXACT && value != DS_PRECISION_FAST) DS_FAIL(ctx, DS_ERR_INVALID, "precision must be 0 or 1");
-    if (n == "guide_n" && value != 4096 && value != GUIDE_MAX) DS_FAIL(ctx, DS_ERR_INVALID, "guide_n must be 4096 or 16384");
+    if (n == "tex_layout" && value != 0 && value != 1) DS_FAIL(ctx, DS_ERR_INVALID, "tex_layout must be 0 (3-D R8) or 1 (2-D layered RG8 z pairs)");
+    if (n == "march_unroll" && value != 1 && value != 2) DS_FAIL(ctx, DS_ERR_INVALID, "march_unroll must be 1 or 2");
     if (n == "skip_open_dist" && value < 1) DS_FAIL(ctx, DS_ERR_INVALID, "skip_open_dist must be >= 1 (0 would leap out of occupied cells)");
     if (n == "staging_subframes" && value < 1) DS_FAIL(ctx, DS_ERR_INVALID, "staging_subframes must be >= 1");
     if (n == "march_max_iters" && value < 1) DS_FAIL(ctx, DS_ERR_INVALID, "march_max_iters must be >= 1");
@@ -733,6 +790,8 @@ int ds_bake_sun_transmittance(DsContext* ctx)
         DS_CUDA(ctx, KernelSet<false>::bake(sc, ctx->inscatter, ctx->opt["skip_empty"], ctx->stream));
     rc = makeTexture(ctx, ctx->inscatter, ctx->lnx[0], ctx->lny[0], ctx->lnz[0], &ctx->inscatterArr, &ctx->inscatterTex);
     if (rc) return rc;
+    rc = makePairTexture(ctx, ctx->inscatter, ctx->lnx[0], ctx->lny[0], ctx->lnz[0], &ctx->inscatterPairArr, &ctx->inscatterPairTex);
+    if (rc) return rc;
     ctx->baked = true;
     return DS_OK;
 }
@@ -752,6 +811,8 @@ int ds_inscatter_upload(DsContext* ctx, const uint8_t* in)
     if (ctx->levels.empty() || !in) DS_FAIL(ctx, DS_ERR_STATE, "no volume");
     DS_CUDA(ctx, cudaMemcpyAsync(ctx->inscatter, in, (size_t)ctx->lnx[0] * ctx->lny[0] * ctx->lnz[0], cudaMemcpyHostToDevice, ctx->stream));
     int rc = makeTexture(ctx, ctx->inscatter, ctx->lnx[0], ctx->lny[0], ctx->lnz[0], &ctx->inscatterArr, &ctx->inscatterTex);
+    if (rc) return rc;
+    rc = makePairTexture(ctx, ctx->inscatter, ctx->lnx[0], ctx->lny[0], ctx->lnz[0], &ctx->inscatterPairArr, &ctx->inscatterPairTex);
     if (rc) return rc;
     ctx->baked = true;
     return DS_OK;
@@ -830,6 +891,8 @@ int ds_frame_clear(DsContext* ctx)
 static int ensureStaging(DsContext* ctx, size_t subframes)
 {
     if (ctx->stagingSubframes >= subframes) return DS_OK;
+    if (subframes * (size_t)ctx->width * ctx->height >= (1ull << 32))
+        DS_FAIL(ctx, DS_ERR_INVALID, "staging_subframes x width x height must stay below 2^32 samples");
     cudaFree(ctx->staging);
     ctx->staging = nullptr;
     ctx->stagingSubframes = 0;
@@ -1207,6 +1270,8 @@ int ds_point_radiance_run(DsContext* ctx, const float* positions, const float* d
     if (!positions || !directions || !tasks_out || !converged_out) DS_FAIL(ctx, DS_ERR_INVALID, "NULL argument");
     if (cfg.max_thread_count < n) DS_FAIL(ctx, DS_ERR_INVALID, "taskRepeatCount would be 0 (RadianceCollector.cpp:179): max_thread_count < n");
     if (cfg.launches_per_update == 0) DS_FAIL(ctx, DS_ERR_INVALID, "launches_per_update must be > 0");
+    if ((unsigned long long)cfg.max_thread_count * cfg.launches_per_update >= (1ull << 32))
+        DS_FAIL(ctx, DS_ERR_INVALID, "max_thread_count x launches_per_update must stay below 2^32");
 
     /* RadianceCollector::init (:27-47) */
     std::vector<DsPointRadianceTask> todo(n);

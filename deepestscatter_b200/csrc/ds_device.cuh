@@ -100,15 +100,24 @@ struct DevScene {
     int occWords;
     /* Chebyshev distance (in cells, saturated at 255) from each cell to the nearest occupied cell; 0 = occupied */
     const uint8_t* cellDist;
-    /* guide table of the chopped-Mie CDF: guide[k] = first index i with cdf[i] >= k / guideN, k = 0..guideN */
-    const uint16_t* guide;
-    int guideN;
+    /* two-level guide of the chopped-Mie CDF (k_trace_fast): bucket k of guideA covers val in [k, k+1) / GUIDE_A_N,
+     * bucket k of guideB covers val in [k, k+1) * GUIDE_B_LIMIT / GUIDE_B_N (val < GUIDE_B_LIMIT, where the CDF is flat
+     * and its knots are dense).  Entry = lo | n << 13: lo = first index i with cdf[i] >= bucket start, n <= 2 = number
+     * of knots inside the bucket. */
+    const uint16_t* guideA;
+    const uint16_t* guideB;
+    /* FAST flavour, texture layout 1: 2-D layered RG8 arrays, texel (x, y, layer z) = {v[z], v[min(z + 1, nz - 1)]} */
+    cudaTextureObject_t densityPairTex;
+    cudaTextureObject_t inscatterPairTex;
     /* 1 when every voxel on the six faces of the grid is zero (VDB imports are padded by one voxel,
      * Resources.cpp:97-101): clamped taps outside the grid then read 0 */
     int borderEmpty;
 };
 
-constexpr int GUIDE_MAX = 16384;
+constexpr int GUIDE_A_N = 4096;
+constexpr int GUIDE_B_N = 8192;
+constexpr float GUIDE_B_LIMIT = 0.125f;
+constexpr int CDF_PAD_N = MIE_N + 4; /* k_trace_fast keeps the CDF in shared memory as {0, cdf[0..4095], +inf x3} */
 
 /* ---- CU/random.cuh ---- */
 

@@ -30,20 +30,24 @@
 namespace dsk {
 
 struct FastState {
-    V3 q;   /* position in texture coordinates */
-    V3 dir; /* unit direction (world / box-local axes) */
+    V3 q0;    /* origin of the current free flight, texture coordinates */
+    V3 sv;    /* march step in texture space: dir * textureScale * sampleStep */
+    float nf; /* march steps taken in this flight; the marching position is q0 + nf * sv */
     float rad;
     float tau;     /* optical depth accumulated in the current free flight */
     float tauStar; /* -ln(xi) */
     uint32_t seed;
     int depth;
-    unsigned long long out;
+    uint32_t out;
 };
 
 struct FastConsts {
-    V3 stepTs;  /* sampleStep * textureScale */
-    V3 half;    /* 0.5 + 0.01 * textureScale: half extent of the in-box slab in texture space */
-    float c1;   /* densityMultiplier * sampleStep */
+    V3 stepTs;    /* sampleStep * textureScale */
+    V3 invStepTs; /* 1 / stepTs: dir = sv * invStepTs */
+    V3 half;      /* 0.5 + 0.01 * textureScale: half extent of the in-box slab in texture space */
+    V3 lightTs;   /* lightDirection * invStepTs: dot(light, dir) = dot(lightTs, sv) */
+    float c1;     /* densityMultiplier * sampleStep */
+    float invStep;
     float nxf, nyf, nzf;
 };
 
@@ -51,8 +55,11 @@ __device__ __forceinline__ FastConsts makeConsts(const DevScene& sc)
 {
     FastConsts k;
     k.stepTs = sc.texScale * sc.step;
+    k.invStepTs = mk(1.0f / k.stepTs.x, 1.0f / k.stepTs.y, 1.0f / k.stepTs.z);
     k.half = mk(0.5f + 0.01f * sc.texScale.x, 0.5f + 0.01f * sc.texScale.y, 0.5f + 0.01f * sc.texScale.z);
+    k.lightTs = sc.light * k.invStepTs;
     k.c1 = sc.mult * sc.step;
+    k.invStep = 1.0f / sc.step;
     k.nxf = (float)sc.nx;
     k.nyf = (float)sc.ny;
     k.nzf = (float)sc.nz;
@@ -64,37 +71,44 @@ __device__ __forceinline__ bool inBoxTs(const FastConsts& k, V3 q)
     return fabsf(q.x - 0.5f) <= k.half.x && fabsf(q.y - 0.5f) <= k.half.y && fabsf(q.z - 0.5f) <= k.half.z;
 }
 
-/* closed-form inverse of the piecewise-linear CDF that cloud.cuh:167-178 bisects */
-__device__ __forceinline__ float invertCdf(const float* sCdf, const uint16_t* sGuide, int guideN, float val)
+/* marching position after n steps of the current flight.  Positions are a function of the step INDEX, never of
+ * how the steps were grouped into march iterations and leaps, so a path's arithmetic does not depend on the
+ * warp schedule. */
+__device__ __forceinline__ V3 posAt(const FastState& s, float n)
 {
-    const int k = min((int)(val * (float)guideN), guideN - 1);
-    /* first index with cdf[i] >= val; most guide buckets hold no table knot at all (66 % at 4096, 85 % at 16384) */
-    int lo = sGuide[k], hi = sGuide[k + 1];
-    while (lo < hi) {
-        const int mid = (lo + hi) >> 1;
-        if (sCdf[mid] < val)
-            lo = mid + 1;
-        else
-            hi = mid;
-    }
-    float u;
-    if (lo == 0) {
-        u = 0.0f;
-    } else if (lo >= MIE_N) {
-        u = 1.0f;
-    } else {
-        const float a = sCdf[lo - 1], b = sCdf[lo];
-        const float t = __fdividef(val - a, b - a);
-        u = ((float)lo - 0.5f + t) * (1.0f / (float)MIE_N);
-    }
-    return 2.0f * u - 1.0f;
+    return mk(fmaf(n, s.sv.x, s.q0.x), fmaf(n, s.sv.y, s.q0.y), fmaf(n, s.sv.z, s.q0.z));
+}
+
+/*
+ * Closed-form inverse of the piecewise-linear CDF that cloud.cuh:167-178 bisects.  sCdfPad[i + 1] = cdf[i],
+ * sCdfPad[0] = 0 (the value "left of" knot 0), two +inf entries at the end.  The two-level guide (DevScene) gives
+ * the first candidate knot `lo` and the number n <= 2 of knots inside the bucket, so the search is two
+ * predicated compares: no loop, no divergence.
+ */
+__device__ __forceinline__ float invertCdf(const float* sCdfPad, const uint16_t* sGuideA, const uint16_t* sGuideB, float val)
+{
+    const bool low = val < GUIDE_B_LIMIT;
+    const int kb = (int)(val * (low ? (float)GUIDE_B_N / GUIDE_B_LIMIT : (float)GUIDE_A_N));
+    const uint32_t e = low ? sGuideB[kb] : sGuideA[kb];
+    const int lo = (int)(e & 0x1fffu), n = (int)(e >> 13);
+    const float* c = sCdfPad + lo; /* c[0] = cdf[lo - 1], c[1] = cdf[lo], ... */
+    const float cm1 = c[0], c0 = c[1], c1 = c[2], c2 = c[3];
+    const bool p0 = n >= 1 && c0 < val; /* first index with cdf[i] >= val is beyond lo */
+    const bool p1 = n >= 2 && c1 < val; /* ... beyond lo + 1 (cdf is non-decreasing: p1 implies p0) */
+    const float a = p1 ? c1 : (p0 ? c0 : cm1);
+    const float b = p1 ? c2 : (p0 ? c1 : c0);
+    const int i = lo + (p0 ? 1 : 0) + (p1 ? 1 : 0);
+    const float t = __fdividef(val - a, b - a);
+    /* tex1D clamps below the first texel centre: every val <= cdf[0] bisects to u = 0 */
+    const float u = i == 0 ? 0.0f : ((float)i - 0.5f + t) * (1.0f / (float)MIE_N);
+    return 2.0f * fminf(u, 1.0f) - 1.0f;
 }
 
 /* CU/cloud.cuh:160-188 */
-__device__ __forceinline__ V3 newDirectionFast(const float* sCdf, const uint16_t* sGuide, int guideN, uint32_t& seed, V3 prev)
+__device__ __forceinline__ V3 newDirectionFast(const float* sCdfPad, const uint16_t* sGuideA, const uint16_t* sGuideB, uint32_t& seed, V3 prev)
 {
     const float val = rnd(seed);
-    const float cosTheta = invertCdf(sCdf, sGuide, guideN, val);
+    const float cosTheta = invertCdf(sCdfPad, sGuideA, sGuideB, val);
     const float phi = rnd(seed) * (PI_F * 2.0f);
     const float s2 = fmaxf(fmaf(-cosTheta, cosTheta, 1.0f), 0.0f);
     const float sinTheta = s2 * rsqrtf(fmaxf(s2, 1.0e-30f));
@@ -114,16 +128,35 @@ __device__ __forceinline__ float tableLerp(const float* table, float u)
     return fmaf(f, b - a, a);
 }
 
-/* start of a free flight (cloudRadianceMaterials.cu:28-35, cloud.cuh:120) */
+/*
+ * One trilinear fetch of a u8 volume at texture coordinate q.
+ *   ZPAIR = false: hardware 3-D filtering of the block-linear R8 array (what rtTex3D does, cloud.cuh:61).
+ *   ZPAIR = true:  the volume is also stored as a 2-D LAYERED RG8 array whose texel (x, y, layer z) holds
+ *                  {v[z], v[min(z + 1, nz - 1)]}: one bilinear fetch of layer floor(z) returns both z slices, the z
+ *                  interpolation is one fp32 lerp.  The footprint of a tap is 2x2 texels of one layer instead of
+ *                  2x2x2 texels of two slices: about half the 32-byte sectors per tap through L1TEX/L2.
+ */
+template <bool ZPAIR>
+__device__ __forceinline__ float tapVolume(cudaTextureObject_t tex3, cudaTextureObject_t texPair, const FastConsts& k, V3 q)
+{
+    if (!ZPAIR) return tex3D<float>(tex3, q.x, q.y, q.z);
+    const float zf = fminf(fmaxf(fmaf(q.z, k.nzf, -0.5f), 0.0f), k.nzf - 1.0f); /* clamp-to-edge in z */
+    const float fl = floorf(zf);
+    const float2 v = tex2DLayered<float2>(texPair, q.x, q.y, (int)fl);
+    return fmaf(zf - fl, v.y - v.x, v.x);
+}
+
+/* start of a free flight (cloudRadianceMaterials.cu:28-35, cloud.cuh:120); the flight origin is s.q0 */
 template <bool CHECK_BOX>
 __device__ __forceinline__ bool beginFlight(const FastConsts& k, FastState& s)
 {
-    if (CHECK_BOX && !inBoxTs(k, s.q)) return false;
+    if (CHECK_BOX && !inBoxTs(k, s.q0)) return false;
     s.depth++;
     if (s.depth == MAX_DEPTH) return false;
     const float xi = rnd(s.seed);
     s.tauStar = -__logf(xi); /* xi == 0 -> +inf: never collides, as `0 > T` in the reference */
     s.tau = 0.0f;
+    s.nf = 0.0f;
     return true;
 }
 
@@ -149,9 +182,9 @@ __device__ __forceinline__ int tapCellDistance(const DevScene& sc, const FastCon
 }
 
 /* whole march steps until the position leaves the in-box slab (the reference's `while (isInBox(pos))`) */
-__device__ __forceinline__ float stepsToLeaveBox(const FastConsts& k, V3 q, V3 dir)
+__device__ __forceinline__ float stepsToLeaveBox(const FastConsts& k, V3 q, V3 sv)
 {
-    const float dx = dir.x * k.stepTs.x, dy = dir.y * k.stepTs.y, dz = dir.z * k.stepTs.z;
+    const float dx = sv.x, dy = sv.y, dz = sv.z;
     const float big = 1.0e30f;
     const float tx = fabsf(dx) > 1e-12f ? __fdividef((dx > 0.0f ? 0.5f + k.half.x : 0.5f - k.half.x) - q.x, dx) : big;
     const float ty = fabsf(dy) > 1e-12f ? __fdividef((dy > 0.0f ? 0.5f + k.half.y : 0.5f - k.half.y) - q.y, dy) : big;
@@ -161,9 +194,9 @@ __device__ __forceinline__ float stepsToLeaveBox(const FastConsts& k, V3 q, V3 d
 
 /* The footprint at q is outside the grid and all face voxels are zero: every tap reads 0 until the ray enters the
  * region floor(x) in [0, N-2] (slab test), or until it leaves the box if it never does. */
-__device__ __forceinline__ float outsideGridSteps(const FastConsts& k, V3 q, V3 dir, float x, float y, float z)
+__device__ __forceinline__ float outsideGridSteps(const FastConsts& k, V3 q, V3 sv, float x, float y, float z)
 {
-    const float vx = dir.x * k.stepTs.x * k.nxf, vy = dir.y * k.stepTs.y * k.nyf, vz = dir.z * k.stepTs.z * k.nzf;
+    const float vx = sv.x * k.nxf, vy = sv.y * k.nyf, vz = sv.z * k.nzf;
     const float big = 1.0e30f;
     float tn = -big, tf = big, margin = 0.0f;
     const float v[3] = {vx, vy, vz}, p[3] = {x, y, z}, hi[3] = {k.nxf - 1.0f, k.nyf - 1.0f, k.nzf - 1.0f};
@@ -183,31 +216,33 @@ __device__ __forceinline__ float outsideGridSteps(const FastConsts& k, V3 q, V3 
         }
     }
     if (tn < tf && tf > 0.0f) return fmaxf(floorf(fminf(tn - 0.01f * margin, 65535.0f)), 0.0f); /* enters the grid */
-    return stepsToLeaveBox(k, q, dir);
+    return stepsToLeaveBox(k, q, sv);
 }
 
 /*
- * Leap DDA.  The tap at q has just been found to lie in an EMPTY cell.  Walks the ray through empty cells and
- * returns the whole number of further march steps whose taps are all guaranteed to read 0; `more` is set when
- * the walk was cut short after `maxLeaps` leaps and the landing position is still in an empty cell.
+ * Leap DDA.  Walks the ray from the tap at q through EMPTY cells and returns the whole number of further march
+ * steps whose taps are all guaranteed to read 0 (0 when the tap cell is occupied); `more` is set when the walk was
+ * cut short after `maxLeaps` leaps and the landing position is still in an empty cell.
  * Coordinates: x = u*N - 0.5 is the voxel coordinate whose floor is the low corner of the trilinear footprint;
- * the occupancy bit of cell c covers voxels [c*2^s, c*2^s + 2^s], i.e. every footprint with floor(x) in c.
+ * the occupancy of cell c covers voxels [c*2^s, c*2^s + 2^s], i.e. every footprint with floor(x) in c.
  * A cell at Chebyshev distance d >= 1 from the nearest occupied cell is the centre of a cube of (2d-1)^3 empty
  * cells; the ray leaves that cube through one face, lands in the adjacent cell and repeats.  When the ray leaves
  * the grid and all face voxels are zero (borderEmpty), the rest of its way out of the box reads 0 as well.
  */
-__device__ __forceinline__ float emptySteps(const DevScene& sc, const FastConsts& k, const uint32_t* occ, V3 q, V3 dir, int maxLeaps, bool& more)
+__device__ __forceinline__ float emptySteps(const DevScene& sc, const FastConsts& k, V3 q, V3 sv, int maxLeaps, bool& more)
 {
     more = false;
     const float x = fmaf(q.x, k.nxf, -0.5f), y = fmaf(q.y, k.nyf, -0.5f), z = fmaf(q.z, k.nzf, -0.5f);
     const int fx = __float2int_rd(x), fy = __float2int_rd(y), fz = __float2int_rd(z);
     /* outside the grid the footprint is clamped to edge voxels */
     if ((unsigned)fx >= (unsigned)(sc.nx - 1) || (unsigned)fy >= (unsigned)(sc.ny - 1) || (unsigned)fz >= (unsigned)(sc.nz - 1))
-        return sc.borderEmpty ? outsideGridSteps(k, q, dir, x, y, z) : 0.0f;
+        return sc.borderEmpty ? outsideGridSteps(k, q, sv, x, y, z) : 0.0f;
     const int sh = sc.occShift;
     int cx = fx >> sh, cy = fy >> sh, cz = fz >> sh;
+    int dist = (int)__ldg(sc.cellDist + (cz * sc.ocy + cy) * sc.ocx + cx);
+    if (dist == 0) return 0.0f; /* the tap cell is occupied */
     const float cs = (float)(1 << sh);
-    const float vx = dir.x * k.stepTs.x * k.nxf, vy = dir.y * k.stepTs.y * k.nyf, vz = dir.z * k.stepTs.z * k.nzf; /* voxels per step */
+    const float vx = sv.x * k.nxf, vy = sv.y * k.nyf, vz = sv.z * k.nzf; /* voxels per step */
     const float big = 1.0e30f;
     const bool mx = fabsf(vx) > 1e-9f, my = fabsf(vy) > 1e-9f, mz = fabsf(vz) > 1e-9f;
     const float ix = mx ? __fdividef(1.0f, vx) : 0.0f, iy = my ? __fdividef(1.0f, vy) : 0.0f, iz = mz ? __fdividef(1.0f, vz) : 0.0f;
@@ -218,8 +253,7 @@ __device__ __forceinline__ float emptySteps(const DevScene& sc, const FastConsts
     bool leftGrid = false, blocked = false;
 #pragma unroll 1
     for (int it = 0; it < maxLeaps; ++it) {
-        const int cell = (cz * sc.ocy + cy) * sc.ocx + cx;
-        const int r = (int)__ldg(sc.cellDist + cell) - 1; /* cells [c-r, c+r]^3 are empty */
+        const int r = dist - 1; /* cells [c-r, c+r]^3 are empty */
         /* exit planes of the cube along the direction of travel, clamped to the grid */
         float ex = (float)(px ? cx + r + 1 : cx - r) * cs, ey = (float)(py ? cy + r + 1 : cy - r) * cs, ez = (float)(pz ? cz + r + 1 : cz - r) * cs;
         const bool cxg = px ? ex >= gx : ex <= gx, cyg = py ? ey >= gy : ey <= gy, czg = pz ? ez >= gz : ez <= gz;
@@ -252,11 +286,11 @@ __device__ __forceinline__ float emptySteps(const DevScene& sc, const FastConsts
         cx = nx_;
         cy = ny_;
         cz = nz_;
-        const int ncell = (cz * sc.ocy + cy) * sc.ocx + cx;
-        blocked = ((occ[ncell >> 5] >> (ncell & 31)) & 1u) != 0u;
+        dist = (int)__ldg(sc.cellDist + (cz * sc.ocy + cy) * sc.ocx + cx);
+        blocked = dist == 0;
         if (blocked) break;
     }
-    if (leftGrid && sc.borderEmpty) return stepsToLeaveBox(k, q, dir);
+    if (leftGrid && sc.borderEmpty) return stepsToLeaveBox(k, q, sv);
     more = !leftGrid && !blocked;
     /* stay 0.01 voxel short of the plane that stopped the walk */
     return fmaxf(floorf(fminf(t - 0.01f * margin, 65535.0f)), 0.0f);
@@ -264,7 +298,7 @@ __device__ __forceinline__ float emptySteps(const DevScene& sc, const FastConsts
 
 /* ray of work item `idx` (CU/pathTracingCamera.cu:12-21, CU/cameraCommon.cuh:19-29, CU/pointEmissionCamera.cu:20-33) */
 __device__ __forceinline__ bool itemRay(const TraceJob& job, unsigned long long idx, V3& o, V3& d, uint32_t& val0, uint32_t& stream,
-                                        unsigned long long& out, uint32_t& pixel)
+                                        uint32_t& out, uint32_t& pixel)
 {
     pixel = 0;
     if (job.kind == JOB_RENDER) {
@@ -291,7 +325,7 @@ __device__ __forceinline__ bool itemRay(const TraceJob& job, unsigned long long 
         d = normalize<true>(dx * U + dy * V + W);
         val0 = px * 4096u + py;
         stream = job.firstSubframe + (uint32_t)sub;
-        out = sub * (unsigned long long)job.width * job.height + pixel;
+        out = (uint32_t)sub * (uint32_t)(job.width * job.height) + pixel; /* the host keeps the staging buffer below 2^32 slots */
     } else if (job.kind == JOB_POINT) {
         const uint32_t t = (uint32_t)(idx / job.launches);
         const uint32_t l = (uint32_t)(idx - (unsigned long long)t * job.launches);
@@ -300,13 +334,13 @@ __device__ __forceinline__ bool itemRay(const TraceJob& job, unsigned long long 
         d = mk(task->direction[0], task->direction[1], task->direction[2]);
         val0 = t * 4096u;
         stream = job.frame0 + l + 1u;
-        out = idx;
+        out = (uint32_t)idx;
     } else {
         o = mk(job.origins[3 * idx], job.origins[3 * idx + 1], job.origins[3 * idx + 2]);
         d = mk(job.dirs[3 * idx], job.dirs[3 * idx + 1], job.dirs[3 * idx + 2]);
         val0 = job.seedVal0[idx];
         stream = job.stream[idx];
-        out = idx;
+        out = (uint32_t)idx;
     }
     return true;
 }
@@ -314,8 +348,8 @@ __device__ __forceinline__ bool itemRay(const TraceJob& job, unsigned long long 
 /* lane states of k_trace_fast */
 enum FastLaneState { F_IDLE = 0, F_SKIP = 1, F_MARCH = 2, F_EVENT = 3, F_DONE = 4 };
 
-__device__ __forceinline__ int beginItemFast(const DevScene& sc, const FastConsts& k, const TraceJob& job, const float* sCdf,
-                                             const uint16_t* sGuide, unsigned long long idx, FastState& s, bool& valid, uint32_t& nSteps)
+__device__ __forceinline__ int beginItemFast(const DevScene& sc, const FastConsts& k, const TraceJob& job, const float* sCdfPad,
+                                             const uint16_t* sGuideA, const uint16_t* sGuideB, unsigned long long idx, FastState& s, bool& valid)
 {
     V3 o, d;
     uint32_t val0, stream, pixel;
@@ -326,20 +360,15 @@ __device__ __forceinline__ int beginItemFast(const DevScene& sc, const FastConst
     if (tHit < 0.0f) return F_DONE;
     V3 hit = o + tHit * d;
     hit = hit + 0.5f * sc.bbox;
-    s.q = hit * sc.texScale;
-    s.dir = normalize<true>(d);
+    s.q0 = hit * sc.texScale;
+    V3 dir = normalize<true>(d);
     s.seed = tea4(val0, stream);
     s.depth = 0;
-    if (job.mode == DS_MODE_SUN_MULTIPLE_SCATTER) s.dir = newDirectionFast(sCdf, sGuide, sc.guideN, s.seed, s.dir);
+    if (job.mode == DS_MODE_SUN_MULTIPLE_SCATTER) dir = newDirectionFast(sCdfPad, sGuideA, sGuideB, s.seed, dir);
+    s.sv = dir * k.stepTs;
     if (!beginFlight<true>(k, s)) return F_DONE;
-    if (job.kind == JOB_RENDER && job.entrySteps) {
-        /* cached empty-space leg of the primary ray: start at the cloud surface */
-        const float kf = (float)job.entrySteps[pixel];
-        s.q.x = fmaf(kf * s.dir.x, k.stepTs.x, s.q.x);
-        s.q.y = fmaf(kf * s.dir.y, k.stepTs.y, s.q.y);
-        s.q.z = fmaf(kf * s.dir.z, k.stepTs.z, s.q.z);
-        nSteps += (uint32_t)kf;
-    }
+    /* cached empty-space leg of the primary ray: the first taps that can be non-zero follow step entrySteps[pixel] */
+    if (job.kind == JOB_RENDER && job.entrySteps) s.nf = (float)job.entrySteps[pixel];
     return F_MARCH;
 }
 
@@ -353,9 +382,9 @@ __device__ __forceinline__ void writeResultFast(const DevScene& sc, const TraceJ
     } else if (job.kind == JOB_POINT) {
         job.xOut[s.out] = r;
     } else {
-        job.radianceOut[3 * s.out] = r;
-        job.radianceOut[3 * s.out + 1] = g;
-        job.radianceOut[3 * s.out + 2] = b;
+        job.radianceOut[3 * (size_t)s.out] = r;
+        job.radianceOut[3 * (size_t)s.out + 1] = g;
+        job.radianceOut[3 * (size_t)s.out + 2] = b;
     }
 }
 
@@ -366,25 +395,34 @@ __device__ __forceinline__ void writeResultFast(const DevScene& sc, const TraceJ
  *                            device queue (one warp-aggregated atomic); runs when >= regenMin lanes are free
  *   B  empty-space phase     lanes whose tap fell into an empty cell (paths leaving the cloud, paths started in
  *                            empty space): leap DDA, then continue marching; runs when >= skipMin lanes wait
- *   C  march phase           lanes inside the cloud: step + density tap + collision test
+ *   C  march phase           step + density tap + collision test, UNROLL steps per vote.  The loop body is the
+ *                            bare minimum: a zero tap changes nothing, so lanes in a hole or past the cloud just
+ *                            keep stepping; whether they left the box (all face voxels are zero, so taps outside
+ *                            the box read 0 as well) or may leap through empty space is looked at ONCE per round,
+ *                            after the loop, and the number of steps the reference would have taken is recovered
+ *                            exactly from the step index.  Grids with non-zero faces (BOXTEST) test the box per step.
  *   D  event phase           lanes that collided: next-event estimate + new direction
  * A waiting lane costs nothing but its slot; a phase entered with two lanes costs the whole warp its full
  * instruction stream, which is what the thresholds avoid.  Thresholds are ignored when nothing else can run.
  */
-template <bool SKIP, int MAXT>
+template <bool SKIP, bool ZPAIR, bool BOXTEST, int UNROLL, int MAXT>
 __global__ void __launch_bounds__(MAXT, 2) k_trace_fast(const DevScene sc, const TraceJob job)
 {
     extern __shared__ __align__(16) unsigned char smemRaw[];
     float* sChopped = reinterpret_cast<float*>(smemRaw);
-    float* sCdf = sChopped + MIE_N;
-    uint16_t* sGuide = reinterpret_cast<uint16_t*>(sCdf + MIE_N);
-    uint32_t* sOcc = reinterpret_cast<uint32_t*>(sGuide + sc.guideN + 2);
+    float* sCdfPad = sChopped + MIE_N;
+    uint16_t* sGuideA = reinterpret_cast<uint16_t*>(sCdfPad + CDF_PAD_N);
+    uint16_t* sGuideB = sGuideA + GUIDE_A_N;
     for (int i = threadIdx.x; i < MIE_N; i += blockDim.x) {
         sChopped[i] = sc.chopped[i];
-        sCdf[i] = sc.cdf[i];
+        sCdfPad[i + 1] = sc.cdf[i];
     }
-    for (int i = threadIdx.x; i <= sc.guideN; i += blockDim.x) sGuide[i] = sc.guide[i];
-    for (int i = threadIdx.x; i < sc.occWords; i += blockDim.x) sOcc[i] = sc.occ[i];
+    if (threadIdx.x == 0) {
+        sCdfPad[0] = 0.0f;
+        sCdfPad[MIE_N + 1] = sCdfPad[MIE_N + 2] = sCdfPad[MIE_N + 3] = 3.0e38f;
+    }
+    for (int i = threadIdx.x; i < GUIDE_A_N; i += blockDim.x) sGuideA[i] = sc.guideA[i];
+    for (int i = threadIdx.x; i < GUIDE_B_N; i += blockDim.x) sGuideB[i] = sc.guideB[i];
     __syncthreads();
 
     const FastConsts k = makeConsts(sc);
@@ -393,8 +431,8 @@ __global__ void __launch_bounds__(MAXT, 2) k_trace_fast(const DevScene sc, const
     const unsigned laneLt = (1u << lane) - 1u;
 
     FastState s;
-    s.q = s.dir = mk(0.f, 0.f, 0.f);
-    s.rad = s.tau = s.tauStar = 0.f;
+    s.q0 = s.sv = mk(0.f, 0.f, 0.f);
+    s.nf = s.rad = s.tau = s.tauStar = 0.f;
     s.seed = 0;
     s.depth = 0;
     s.out = 0;
@@ -428,7 +466,7 @@ __global__ void __launch_bounds__(MAXT, 2) k_trace_fast(const DevScene sc, const
                         exhausted = true;
                     } else {
                         bool valid;
-                        st = beginItemFast(sc, k, job, sCdf, sGuide, idx, s, valid, nSteps);
+                        st = beginItemFast(sc, k, job, sCdfPad, sGuideA, sGuideB, idx, s, valid);
                         if (valid) nPaths++;
                     }
                 }
@@ -441,17 +479,13 @@ __global__ void __launch_bounds__(MAXT, 2) k_trace_fast(const DevScene sc, const
         }
         if (mBusy == 0u && mSkip == 0u && mFree == 0u) break; /* every lane idle and the queue exhausted */
 
-        /* ---- B: empty-space phase: the tap at q fell into an empty cell ---- */
+        /* ---- B: empty-space phase: the tap at the current position fell into an empty cell ---- */
         if (SKIP && mSkip && (__popc(mSkip) >= job.skipMin || mBusy == 0u)) {
             if (st == F_SKIP) {
                 bool more;
-                const float kf = emptySteps(sc, k, sOcc, s.q, s.dir, job.skipMaxIters, more);
-                s.q.x = fmaf(kf * s.dir.x, k.stepTs.x, s.q.x);
-                s.q.y = fmaf(kf * s.dir.y, k.stepTs.y, s.q.y);
-                s.q.z = fmaf(kf * s.dir.z, k.stepTs.z, s.q.z);
-                nSteps += (uint32_t)kf;
-                /* a walk cut short lands in an empty cell and continues next round; otherwise march on (the
-                 * in-box test of the march phase retires paths that left the box) */
+                const float kf = emptySteps(sc, k, posAt(s, s.nf), s.sv, job.skipMaxIters, more);
+                s.nf += kf;
+                /* a walk cut short lands in an empty cell and continues next round; otherwise march on */
                 st = (more && kf >= 1.0f) ? F_SKIP : F_MARCH;
             }
         }
@@ -459,55 +493,68 @@ __global__ void __launch_bounds__(MAXT, 2) k_trace_fast(const DevScene sc, const
         /* ---- C: march phase (CU/cloud.cuh:87-104) ---- */
         const int nBusy = __popc(__ballot_sync(FULL, st == F_MARCH || st == F_EVENT));
         if (nBusy) {
+            const float nfStart = s.nf;
+            const int keep = (nBusy * job.marchKeep32) >> 5; /* leave when at most this many lanes still march */
 #pragma unroll 1
-            for (int it = 0; it < job.marchMaxIters; ++it) {
-                if (st == F_MARCH) {
-                    if (!inBoxTs(k, s.q)) {
-                        st = F_DONE;
-                    } else {
-                        s.q.x = fmaf(s.dir.x, k.stepTs.x, s.q.x);
-                        s.q.y = fmaf(s.dir.y, k.stepTs.y, s.q.y);
-                        s.q.z = fmaf(s.dir.z, k.stepTs.z, s.q.z);
-                        nSteps++;
-                        nTaps++;
-                        lastDensity = tex3D<float>(sc.densityTex, s.q.x, s.q.y, s.q.z);
-                        if (lastDensity == 0.0f) {
-                            /* left the cloud, or a hole in it: leap only in open space (no occupied cell among the 26
-                             * neighbours); pockets next to the cloud are cheaper to march through */
-                            if (SKIP && tapCellDistance(sc, k, s.q) >= job.skipOpenDist) st = F_SKIP;
+            for (int it = 0; it < job.marchMaxIters; it += UNROLL) {
+#pragma unroll
+                for (int u = 0; u < UNROLL; ++u) {
+                    if (st == F_MARCH) {
+                        if (BOXTEST && !inBoxTs(k, posAt(s, s.nf))) {
+                            nSteps += (uint32_t)s.nf;
+                            st = F_DONE;
                         } else {
+                            s.nf += 1.0f;
+                            lastDensity = tapVolume<ZPAIR>(sc.densityTex, sc.densityPairTex, k, posAt(s, s.nf));
                             s.tau = fmaf(lastDensity, k.c1, s.tau);
                             if (s.tau > s.tauStar) st = F_EVENT;
                         }
                     }
                 }
-                const int nMarch = __popc(__ballot_sync(FULL, st == F_MARCH));
-                if (nMarch * 32 <= nBusy * job.marchKeep32) break;
+                if (__popc(__ballot_sync(FULL, st == F_MARCH)) <= keep) break;
+            }
+            nTaps += (uint32_t)(s.nf - nfStart);
+
+            /* once per round: lanes whose last tap read 0 */
+            if (st == F_MARCH && lastDensity == 0.0f) {
+                const V3 q = posAt(s, s.nf);
+                if (!BOXTEST && !inBoxTs(k, q)) {
+                    /* left the box: the reference stops at the first position outside it (its taps beyond read 0 too) */
+                    float n = s.nf;
+#pragma unroll 1
+                    while (n >= 2.0f && !inBoxTs(k, posAt(s, n - 1.0f))) n -= 1.0f;
+                    nSteps += (uint32_t)n;
+                    st = F_DONE;
+                } else if (SKIP && tapCellDistance(sc, k, q) >= job.skipOpenDist) {
+                    /* open space (no occupied cell within skipOpenDist - 1 cells): leap; pockets next to the cloud
+                     * are cheaper to march through */
+                    st = F_SKIP;
+                }
             }
         }
 
         /* ---- D: event phase (cloudRadianceMaterials.cu:49-61) ---- */
         if (st == F_EVENT) {
+            nSteps += (uint32_t)s.nf;
             /* cloud.cuh:99: scatterPos = pos - dir * log(xi / T) / sigma, with log(xi / T) = tau - tauStar */
             const float back = __fdividef(s.tau - s.tauStar, lastDensity * sc.mult);
-            s.q.x = fmaf(-back * s.dir.x, sc.texScale.x, s.q.x);
-            s.q.y = fmaf(-back * s.dir.y, sc.texScale.y, s.q.y);
-            s.q.z = fmaf(-back * s.dir.z, sc.texScale.z, s.q.z);
-            if (!inBoxTs(k, s.q)) {
+            s.q0 = posAt(s, fmaf(-back, k.invStep, s.nf));
+            if (!inBoxTs(k, s.q0)) {
                 st = F_DONE;
             } else {
-                const float cosLightAngle = -dot(sc.light, s.dir);
+                const float cosLightAngle = -dot(k.lightTs, s.sv);
                 const bool choppedPhase = (job.mode == DS_MODE_SUN_AND_SKY_ALL_SCATTER) ? (s.depth != 1) : (job.mode == DS_MODE_SUN_MULTIPLE_SCATTER);
                 const float u = (cosLightAngle + 1.0f) * 0.5f;
                 const float phase = choppedPhase ? tableLerp(sChopped, u) : tableLerp(sc.mie, u);
-                const float tsun = tex3D<float>(sc.inscatterTex, s.q.x, s.q.y, s.q.z);
+                const float tsun = tapVolume<ZPAIR>(sc.inscatterTex, sc.inscatterPairTex, k, s.q0);
                 s.rad = fmaf(tsun, phase, s.rad);
                 nEvents++;
                 if (job.mode == DS_MODE_SUN_SINGLE_SCATTER) {
                     st = F_DONE;
                 } else {
-                    s.dir = newDirectionFast(sCdf, sGuide, sc.guideN, s.seed, s.dir);
-                    st = beginFlight<false>(k, s) ? F_MARCH : F_DONE; /* q is the scatter position just verified in-box */
+                    const V3 dir = newDirectionFast(sCdfPad, sGuideA, sGuideB, s.seed, s.sv * k.invStepTs);
+                    s.sv = dir * k.stepTs;
+                    st = beginFlight<false>(k, s) ? F_MARCH : F_DONE; /* q0 is the scatter position just verified in-box */
                 }
             }
         }
@@ -522,39 +569,44 @@ __global__ void __launch_bounds__(MAXT, 2) k_trace_fast(const DevScene sc, const
     }
 }
 
+template <bool SKIP, bool ZPAIR, bool BOXTEST, int UNROLL, int MAXT>
+static cudaError_t launchFast(const DevScene& sc, const TraceJob& job, int blocks, int threads, size_t smem, cudaStream_t st)
+{
+    cudaError_t e = cudaFuncSetAttribute(k_trace_fast<SKIP, ZPAIR, BOXTEST, UNROLL, MAXT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    k_trace_fast<SKIP, ZPAIR, BOXTEST, UNROLL, MAXT><<<blocks, threads, smem, st>>>(sc, job);
+    return cudaGetLastError();
+}
+
 template <>
 cudaError_t KernelSet<true>::trace(const DevScene& sc, const TraceJob& job, const LaunchConfig& cfg, cudaStream_t st)
 {
     if (cfg.variant == 1) return traceGeneric<true>(sc, job, cfg, st);
-    const size_t smem = (size_t)(2 * MIE_N) * 4 + (size_t)(sc.guideN + 2) * 2 + (size_t)sc.occWords * 4;
+    const size_t smem = (size_t)(MIE_N + CDF_PAD_N) * 4 + (size_t)(GUIDE_A_N + GUIDE_B_N) * 2;
     const int threads = cfg.blockThreads > 640 ? 640 : cfg.blockThreads;
     const unsigned long long wantBlocks = (job.total + threads - 1) / threads;
     const unsigned long long maxBlocks = (unsigned long long)cfg.smCount * cfg.blocksPerSm;
     const int blocks = (int)(wantBlocks < maxBlocks ? (wantBlocks ? wantBlocks : 1) : maxBlocks);
+    const bool zpair = cfg.texLayout == 1 && sc.densityPairTex != 0 && sc.inscatterPairTex != 0;
+    const bool boxtest = sc.borderEmpty == 0;
     /* register budget follows the block size: 64 regs up to 512 threads, 56 up to 576, 48 up to 640 (2 blocks/SM) */
-#define DS_LAUNCH_FAST(SK, MT)                                                                                                 \
-    do {                                                                                                                       \
-        cudaError_t e = cudaFuncSetAttribute(k_trace_fast<SK, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-        if (e != cudaSuccess) return e;                                                                                        \
-        k_trace_fast<SK, MT><<<blocks, threads, smem, st>>>(sc, job);                                                          \
-    } while (0)
-    if (cfg.skipEmpty) {
-        if (threads <= 512)
-            DS_LAUNCH_FAST(true, 512);
-        else if (threads <= 576)
-            DS_LAUNCH_FAST(true, 576);
-        else
-            DS_LAUNCH_FAST(true, 640);
-    } else {
-        if (threads <= 512)
-            DS_LAUNCH_FAST(false, 512);
-        else if (threads <= 576)
-            DS_LAUNCH_FAST(false, 576);
-        else
-            DS_LAUNCH_FAST(false, 640);
+    if (!cfg.skipEmpty || boxtest) {
+        /* uncommon configurations: one instantiation each */
+        if (cfg.skipEmpty) return launchFast<true, false, true, 1, 512>(sc, job, blocks, threads > 512 ? 512 : threads, smem, st);
+        if (boxtest) return launchFast<false, false, true, 1, 512>(sc, job, blocks, threads > 512 ? 512 : threads, smem, st);
+        return launchFast<false, false, false, 1, 512>(sc, job, blocks, threads > 512 ? 512 : threads, smem, st);
     }
-#undef DS_LAUNCH_FAST
-    return cudaGetLastError();
+    const bool u2 = cfg.marchUnroll >= 2;
+    if (threads <= 512) {
+        if (zpair) return u2 ? launchFast<true, true, false, 2, 512>(sc, job, blocks, threads, smem, st) : launchFast<true, true, false, 1, 512>(sc, job, blocks, threads, smem, st);
+        return u2 ? launchFast<true, false, false, 2, 512>(sc, job, blocks, threads, smem, st) : launchFast<true, false, false, 1, 512>(sc, job, blocks, threads, smem, st);
+    }
+    if (threads <= 576) {
+        if (zpair) return u2 ? launchFast<true, true, false, 2, 576>(sc, job, blocks, threads, smem, st) : launchFast<true, true, false, 1, 576>(sc, job, blocks, threads, smem, st);
+        return u2 ? launchFast<true, false, false, 2, 576>(sc, job, blocks, threads, smem, st) : launchFast<true, false, false, 1, 576>(sc, job, blocks, threads, smem, st);
+    }
+    if (zpair) return u2 ? launchFast<true, true, false, 2, 640>(sc, job, blocks, threads, smem, st) : launchFast<true, true, false, 1, 640>(sc, job, blocks, threads, smem, st);
+    return u2 ? launchFast<true, false, false, 2, 640>(sc, job, blocks, threads, smem, st) : launchFast<true, false, false, 1, 640>(sc, job, blocks, threads, smem, st);
 }
 
 /*
@@ -585,22 +637,24 @@ __global__ void __launch_bounds__(256) k_primary_prepass(const DevScene sc, cons
         if (tHit >= 0.0f) {
             V3 hitp = o + tHit * d;
             hitp = hitp + 0.5f * sc.bbox;
-            V3 q = hitp * sc.texScale;
-            const V3 dir = normalize<true>(d);
-            /* march like the reference (cloud.cuh:87-89) but only look at occupancy */
-            while (inBoxTs(k, q)) {
-                const V3 qn = mk(fmaf(dir.x, k.stepTs.x, q.x), fmaf(dir.y, k.stepTs.y, q.y), fmaf(dir.z, k.stepTs.z, q.z));
-                if (!tapCellEmpty(sc, k, sc.occ, qn)) {
-                    hit = true; /* the next step's tap may be non-zero: the traced path starts at q */
+            FastState f;
+            f.q0 = hitp * sc.texScale;
+            f.sv = normalize<true>(d) * k.stepTs;
+            /* march like the reference (cloud.cuh:87-89) but only look at occupancy; positions by step index, exactly
+             * as k_trace_fast computes them */
+            float n = 0.0f;
+            while (inBoxTs(k, posAt(f, n))) {
+                if (!tapCellEmpty(sc, k, sc.occ, posAt(f, n + 1.0f))) {
+                    hit = true; /* the next step's tap may be non-zero: the traced path starts at step n */
                     break;
                 }
-                q = qn;
-                steps++;
+                n += 1.0f;
                 bool more;
-                const float kf = emptySteps(sc, k, sc.occ, q, dir, 256, more);
-                q = mk(fmaf(kf * dir.x, k.stepTs.x, q.x), fmaf(kf * dir.y, k.stepTs.y, q.y), fmaf(kf * dir.z, k.stepTs.z, q.z));
-                steps += (uint32_t)kf;
+                n += emptySteps(sc, k, posAt(f, n), f.sv, 256, more);
             }
+            /* a ray that leaves the box: the reference stops at the first position outside it */
+            while (!hit && n >= 2.0f && !inBoxTs(k, posAt(f, n - 1.0f))) n -= 1.0f;
+            steps = (uint32_t)n;
         }
         entrySteps[pixel] = hit ? steps : ENTRY_MISS;
     }

@@ -230,46 +230,51 @@ def test_fast_flavour_is_deterministic_under_scheduling_knobs(built_library):
         ctx.counters_reset()
         base = ctx.render_frame(cam, 0, 7)
         c0 = ctx.counters()
-        for opts in (dict(regen_min=1, skip_min=1, skip_keep=1), dict(regen_min=32, skip_min=32, skip_keep=16), dict(march_keep32=0),
-                     dict(march_keep32=31, march_max_iters=2), dict(block_threads=64, blocks_per_sm=1),
-                     dict(guide_n=16384)):
+        defaults = dict(regen_min=2, skip_min=8, march_keep32=12, march_max_iters=64, skip_open_dist=1, skip_max_iters=32, march_unroll=1,
+                        block_threads=576, blocks_per_sm=2)
+        # positions are a function of the step index (q0 + n * sv), so neither the phase votes, nor how leaps are cut,
+        # nor the number of march steps per vote can change a single bit of a path
+        for opts in (dict(regen_min=1, skip_min=1), dict(regen_min=32, skip_min=32), dict(march_keep32=0),
+                     dict(march_keep32=31, march_max_iters=2), dict(block_threads=64, blocks_per_sm=1), dict(march_unroll=2),
+                     dict(skip_max_iters=1, skip_open_dist=3), dict(block_threads=512), dict(block_threads=640, march_unroll=2)):
             for k, val in opts.items():
                 ctx.set_option(k, val)
             ctx.counters_reset()
             again = ctx.render_frame(cam, 0, 7)
             c = ctx.counters()
             assert np.array_equal(again.view(np.uint32), base.view(np.uint32)), opts
-            # taps may differ (a leap cut short re-taps a known-empty cell); the reference-algorithm counts may not
+            # taps may differ (a lane past the cloud keeps tapping zeros until the end of its march round); the
+            # reference-algorithm counts may not
             assert (c["paths"], c["events"], c["steps"]) == (c0["paths"], c0["events"], c0["steps"]), opts
-            for k, val in dict(regen_min=2, skip_min=8, skip_keep=4, march_keep32=12, march_max_iters=64, guide_n=4096, skip_open_dist=1,
-                               block_threads=576, blocks_per_sm=2).items():
+            for k, val in defaults.items():
                 ctx.set_option(k, val)
-        # cutting leap walks short splits one jump into several (different fp rounding of the landing point): same
-        # silhouette and statistics, not the same bits
-        ctx.set_option("skip_max_iters", 1)
-        ctx.set_option("skip_open_dist", 3)
-        cut = ctx.render_frame(cam, 0, 7)
-        ctx.set_option("skip_max_iters", 32)
-        ctx.set_option("skip_open_dist", 1)
-        assert np.array_equal(cut[..., 0] == 0, base[..., 0] == 0)
-        assert abs(float(cut[..., 0].mean()) - float(base[..., 0].mean())) < 0.25 * float(base[..., 0].mean())
-        # without the primary-ray cache every pixel is traced from the box face: same silhouette, same counters
+        # without the primary-ray cache every pixel is traced from the box face: same bits, same counters
         ctx.set_option("primary_cache", 0)
         ctx.counters_reset()
         nocache = ctx.render_frame(cam, 0, 7)
         c1 = ctx.counters()
         ctx.set_option("primary_cache", 1)
-        assert np.array_equal(nocache[..., 0] == 0, base[..., 0] == 0)
-        assert np.all(nocache[..., 3] == 1) and np.all(base[..., 3] == 1)
-        assert c1["paths"] == c0["paths"] == w * h
-        assert abs(c1["steps"] - c0["steps"]) <= 0.02 * c0["steps"] and abs(c1["events"] - c0["events"]) <= 0.1 * c0["events"] + 50
-        assert abs(float(nocache[..., 0].mean()) - float(base[..., 0].mean())) < 0.25 * float(base[..., 0].mean())
-        # the generic kernel (variant 1) and jump-free marching agree statistically, not bitwise
+        assert np.array_equal(nocache.view(np.uint32), base.view(np.uint32))
+        assert (c1["paths"], c1["events"], c1["steps"]) == (c0["paths"], c0["events"], c0["steps"])
+        assert c1["paths"] == w * h
+        # the two texture layouts filter differently in z (8-bit hardware weight vs fp32 lerp): statistics agree, bits do not
+        ctx.set_option("tex_layout", 0)
+        ctx.counters_reset()
+        base3d = ctx.render_frame(cam, 0, 7)
+        c3 = ctx.counters()
+        assert ((base3d[..., 0] == 0) != (base[..., 0] == 0)).mean() < 0.02
+        assert abs(float(base3d[..., 0].mean()) - float(base[..., 0].mean())) < 0.25 * float(base[..., 0].mean())
+        assert c3["paths"] == c0["paths"] and abs(c3["steps"] - c0["steps"]) <= 0.02 * c0["steps"]
+        # jump-free marching takes every tap: same bits as the leaping kernel of the same texture layout
         ctx.set_option("skip_empty", 0)
+        ctx.counters_reset()
         noskip = ctx.render_frame(cam, 0, 7)
+        c2 = ctx.counters()
         ctx.set_option("skip_empty", 1)
-        assert abs(float(noskip[..., 0].mean()) - float(base[..., 0].mean())) < 0.25 * float(base[..., 0].mean())
-        assert np.array_equal(noskip[..., 0] == 0, base[..., 0] == 0) or ((noskip[..., 0] == 0) != (base[..., 0] == 0)).mean() < 0.02
+        ctx.set_option("tex_layout", 1)
+        assert np.array_equal(noskip.view(np.uint32), base3d.view(np.uint32))
+        assert (c2["paths"], c2["events"], c2["steps"]) == (c3["paths"], c3["events"], c3["steps"])
+        assert c2["density_taps"] >= c2["steps"]
 
 
 # ---------------------------------------------------------------- dataset generation
