@@ -494,8 +494,8 @@ int ds_context_create(int device, DsContext** out)
     ctx->opt["skip_min"] = 8;
     ctx->opt["skip_max_iters"] = 32;
     ctx->opt["skip_open_dist"] = 1;
-    ctx->opt["tex_layout"] = 1;
-    ctx->opt["march_unroll"] = 1;
+    ctx->opt["tex_layout"] = 0;
+    ctx->opt["march_unroll"] = 2;
     ctx->opt["staging_subframes"] = 16;
     ctx->opt["stream_offset"] = 0;
     ctx->opt["profile_events"] = 0;
