@@ -4,6 +4,8 @@ The product is the C-ABI shared library `libdeepestscatter_b200.so` (include/ds_
 deepestscatter_b200/csrc/ for sm_100a).  This package only loads it and marshals numpy / torch buffers.
 """
 from ._lib import LIB_PATH, build_library, load
+from . import lmdb_compat
+from .dataset import Dataset
 from .context import (
     MODE_ALL_SCATTER,
     MODE_MULTIPLE_SCATTER,
@@ -24,5 +26,5 @@ from .context import (
 __all__ = [
     "LIB_PATH", "build_library", "load", "Context", "DsError", "camera_look_at", "camera_array",
     "MODE_ALL_SCATTER", "MODE_MULTIPLE_SCATTER", "MODE_SINGLE_SCATTER", "PRECISION_EXACT", "PRECISION_FAST", "TASK_DTYPE",
-    "record_scatter_sample", "record_disney_descriptor", "record_result", "record_scene_setup",
+    "record_scatter_sample", "record_disney_descriptor", "record_result", "record_scene_setup", "Dataset", "lmdb_compat",
 ]

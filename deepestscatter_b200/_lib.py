@@ -117,6 +117,19 @@ SIGNATURES = {
     "ds_record_disney_descriptor": (_i, [_vp, _sz, _vp, _sz]),
     "ds_record_result": (_i, [_f, _i, _vp, _sz]),
     "ds_record_scene_setup": (_i, [C.c_char_p, _f, _pf, _vp, _sz]),
+    "ds_dataset_open": (_i, [C.c_char_p, C.POINTER(_vp)]),
+    "ds_dataset_close": (_i, [_vp]),
+    "ds_dataset_last_error": (C.c_char_p, [_vp]),
+    "ds_dataset_commit": (_i, [_vp]),
+    "ds_dataset_put": (_i, [_vp, C.c_char_p, C.c_int32, _vp, _sz]),
+    "ds_dataset_get": (C.c_longlong, [_vp, C.c_char_p, C.c_int32, _vp, _sz]),
+    "ds_dataset_count": (C.c_longlong, [_vp, C.c_char_p]),
+    "ds_dataset_drop": (_i, [_vp, C.c_char_p]),
+    "ds_dataset_merge": (_i, [_vp, C.c_char_p]),
+    "ds_dataset_append_scene_setup": (_i, [_vp, C.c_int32, C.c_char_p, _f, _pf]),
+    "ds_dataset_append_scatter_samples": (_i, [_vp, C.c_int32, _u32, _vp, _vp]),
+    "ds_dataset_append_descriptors": (_i, [_vp, C.c_int32, _u32, _vp, _sz]),
+    "ds_dataset_append_results": (_i, [_vp, C.c_int32, _u32, _vp, _vp]),
 }
 
 

@@ -37,9 +37,6 @@ struct DsContext {
     bool baked = false;
     cudaArray_t densityArr = nullptr, inscatterArr = nullptr;
     cudaTextureObject_t densityTex = 0, inscatterTex = 0;
-    /* texture layout 1 (k_trace_fast): 2-D layered RG8 z-pair copies of both volumes */
-    cudaArray_t densityPairArr = nullptr, inscatterPairArr = nullptr;
-    cudaTextureObject_t densityPairTex = 0, inscatterPairTex = 0;
     uint32_t* occ = nullptr;
     uint8_t* cellDist = nullptr;
     int occShift = 0, ocx = 0, ocy = 0, ocz = 0, occWords = 0;
@@ -130,12 +127,6 @@ static void freeVolume(DsContext* ctx)
     if (ctx->densityArr) cudaFreeArray(ctx->densityArr);
     if (ctx->inscatterArr) cudaFreeArray(ctx->inscatterArr);
     ctx->densityArr = ctx->inscatterArr = nullptr;
-    if (ctx->densityPairTex) cudaDestroyTextureObject(ctx->densityPairTex);
-    if (ctx->inscatterPairTex) cudaDestroyTextureObject(ctx->inscatterPairTex);
-    ctx->densityPairTex = ctx->inscatterPairTex = 0;
-    if (ctx->densityPairArr) cudaFreeArray(ctx->densityPairArr);
-    if (ctx->inscatterPairArr) cudaFreeArray(ctx->inscatterPairArr);
-    ctx->densityPairArr = ctx->inscatterPairArr = nullptr;
     if (ctx->occ) cudaFree(ctx->occ);
     ctx->occ = nullptr;
     if (ctx->cellDist) cudaFree(ctx->cellDist);
@@ -214,37 +205,6 @@ static int makeTexture(DsContext* ctx, const uint8_t* linear, int nx, int ny, in
     return DS_OK;
 }
 
-/* z-pair layout: a 2-D layered RG8 array, layer z = {v[z], v[min(z + 1, nz - 1)]}, bilinear within a layer.
- * Skipped (texture object left 0 -> the 3-D layout is used) when the volume exceeds the layered-texture limits. */
-static int makePairTexture(DsContext* ctx, const uint8_t* linear, int nx, int ny, int nz, cudaArray_t* arr, cudaTextureObject_t* tex)
-{
-    if (*tex) {
-        cudaDestroyTextureObject(*tex);
-        *tex = 0;
-    }
-    if (nx > ctx->prop.maxTexture2DLayered[0] || ny > ctx->prop.maxTexture2DLayered[1] || nz > ctx->prop.maxTexture2DLayered[2]) return DS_OK;
-    if (!*arr) {
-        cudaChannelFormatDesc cd = cudaCreateChannelDesc<uchar2>();
-        DS_CUDA(ctx, cudaMalloc3DArray(arr, &cd, make_cudaExtent(nx, ny, nz), cudaArrayLayered | cudaArraySurfaceLoadStore));
-    }
-    cudaResourceDesc rd = {};
-    rd.resType = cudaResourceTypeArray;
-    rd.res.array.array = *arr;
-    cudaSurfaceObject_t surf = 0;
-    DS_CUDA(ctx, cudaCreateSurfaceObject(&surf, &rd));
-    cudaError_t e = launchPackZPair(linear, nx, ny, nz, surf, ctx->stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-    cudaDestroySurfaceObject(surf);
-    DS_CUDA(ctx, e);
-    cudaTextureDesc td = {};
-    td.addressMode[0] = td.addressMode[1] = td.addressMode[2] = cudaAddressModeClamp;
-    td.filterMode = cudaFilterModeLinear;
-    td.readMode = cudaReadModeNormalizedFloat;
-    td.normalizedCoords = 1;
-    DS_CUDA(ctx, cudaCreateTextureObject(tex, &rd, &td, nullptr));
-    return DS_OK;
-}
-
 static void fillDevScene(DsContext* ctx, DevScene& sc)
 {
     memset(&sc, 0, sizeof(sc));
@@ -278,8 +238,6 @@ static void fillDevScene(DsContext* ctx, DevScene& sc)
     sc.cellDist = ctx->cellDist;
     sc.guideA = ctx->guide;
     sc.guideB = ctx->guide + GUIDE_A_N;
-    sc.densityPairTex = ctx->densityPairTex;
-    sc.inscatterPairTex = ctx->inscatterPairTex;
     sc.borderEmpty = ctx->borderEmpty;
 }
 
@@ -353,8 +311,6 @@ static int finishVolume(DsContext* ctx, int buildMips)
     }
     int rc = makeTexture(ctx, ctx->levels[0], nx, ny, nz, &ctx->densityArr, &ctx->densityTex);
     if (rc) return rc;
-    rc = makePairTexture(ctx, ctx->levels[0], nx, ny, nz, &ctx->densityPairArr, &ctx->densityPairTex);
-    if (rc) return rc;
     DS_CUDA(ctx, cudaMalloc(&ctx->inscatter, (size_t)nx * ny * nz));
     DS_CUDA(ctx, cudaMemsetAsync(ctx->inscatter, 0, (size_t)nx * ny * nz, ctx->stream));
     computeDerived(ctx);
@@ -395,7 +351,6 @@ static LaunchConfig launchConfig(DsContext* ctx)
     cfg.smCount = ctx->prop.multiProcessorCount;
     cfg.skipEmpty = ctx->opt["skip_empty"];
     cfg.variant = ctx->opt["variant"];
-    cfg.texLayout = ctx->opt["tex_layout"];
     cfg.marchUnroll = ctx->opt["march_unroll"];
     return cfg;
 }
@@ -413,6 +368,7 @@ static int runTrace(DsContext* ctx, TraceJob& job)
     job.skipMin = ctx->opt["skip_min"];
     job.skipMaxIters = ctx->opt["skip_max_iters"];
     job.skipOpenDist = ctx->opt["skip_open_dist"];
+    job.zeroCheckMin = ctx->opt["zero_check_min"];
     DS_CUDA(ctx, cudaMemsetAsync(ctx->queue, 0, sizeof(unsigned long long), ctx->stream));
     const LaunchConfig cfg = launchConfig(ctx);
     const bool prof = ctx->opt["profile_events"] != 0;
@@ -484,17 +440,17 @@ int ds_context_create(int device, DsContext** out)
     }
     ctx->opt["precision"] = DS_PRECISION_FAST;
     ctx->opt["variant"] = 0;
-    ctx->opt["block_threads"] = 576;
+    ctx->opt["block_threads"] = 512;
     ctx->opt["blocks_per_sm"] = 2;
     ctx->opt["skip_empty"] = 1;
     ctx->opt["march_keep_quarters"] = 2;
     ctx->opt["march_max_iters"] = 64;
-    ctx->opt["march_keep32"] = 12;
+    ctx->opt["march_keep32"] = 14;
     ctx->opt["regen_min"] = 2;
     ctx->opt["skip_min"] = 8;
     ctx->opt["skip_max_iters"] = 32;
     ctx->opt["skip_open_dist"] = 1;
-    ctx->opt["tex_layout"] = 0;
+    ctx->opt["zero_check_min"] = 2;
     ctx->opt["march_unroll"] = 2;
     ctx->opt["staging_subframes"] = 16;
     ctx->opt["stream_offset"] = 0;
@@ -597,7 +553,6 @@ int ds_set_option(DsContext* ctx, const char* name, int value)
     if (n == "block_threads" && (value < 32 || value > 1024 || value % 32)) DS_FAIL(ctx, DS_ERR_INVALID, "block_threads must be 32..1024, multiple of 32");
     if (n == "blocks_per_sm" && (value < 1 || value > 32)) DS_FAIL(ctx, DS_ERR_INVALID, "blocks_per_sm must be 1..32");
     if (n == "precision" && value != DS_PRECISION_EXACT && value != DS_PRECISION_FAST) DS_FAIL(ctx, DS_ERR_INVALID, "precision must be 0 or 1");
-    if (n == "tex_layout" && value != 0 && value != 1) DS_FAIL(ctx, DS_ERR_INVALID, "tex_layout must be 0 (3-D R8) or 1 (2-D layered RG8 z pairs)");
     if (n == "march_unroll" && value != 1 && value != 2) DS_FAIL(ctx, DS_ERR_INVALID, "march_unroll must be 1 or 2");
     if (n == "skip_open_dist" && value < 1) DS_FAIL(ctx, DS_ERR_INVALID, "skip_open_dist must be >= 1 (0 would leap out of occupied cells)");
     if (n == "staging_subframes" && value < 1) DS_FAIL(ctx, DS_ERR_INVALID, "staging_subframes must be >= 1");
@@ -790,8 +745,6 @@ int ds_bake_sun_transmittance(DsContext* ctx)
         DS_CUDA(ctx, KernelSet<false>::bake(sc, ctx->inscatter, ctx->opt["skip_empty"], ctx->stream));
     rc = makeTexture(ctx, ctx->inscatter, ctx->lnx[0], ctx->lny[0], ctx->lnz[0], &ctx->inscatterArr, &ctx->inscatterTex);
     if (rc) return rc;
-    rc = makePairTexture(ctx, ctx->inscatter, ctx->lnx[0], ctx->lny[0], ctx->lnz[0], &ctx->inscatterPairArr, &ctx->inscatterPairTex);
-    if (rc) return rc;
     ctx->baked = true;
     return DS_OK;
 }
@@ -811,8 +764,6 @@ int ds_inscatter_upload(DsContext* ctx, const uint8_t* in)
     if (ctx->levels.empty() || !in) DS_FAIL(ctx, DS_ERR_STATE, "no volume");
     DS_CUDA(ctx, cudaMemcpyAsync(ctx->inscatter, in, (size_t)ctx->lnx[0] * ctx->lny[0] * ctx->lnz[0], cudaMemcpyHostToDevice, ctx->stream));
     int rc = makeTexture(ctx, ctx->inscatter, ctx->lnx[0], ctx->lny[0], ctx->lnz[0], &ctx->inscatterArr, &ctx->inscatterTex);
-    if (rc) return rc;
-    rc = makePairTexture(ctx, ctx->inscatter, ctx->lnx[0], ctx->lny[0], ctx->lnz[0], &ctx->inscatterPairArr, &ctx->inscatterPairTex);
     if (rc) return rc;
     ctx->baked = true;
     return DS_OK;

@@ -106,9 +106,6 @@ struct DevScene {
      * of knots inside the bucket. */
     const uint16_t* guideA;
     const uint16_t* guideB;
-    /* FAST flavour, texture layout 1: 2-D layered RG8 arrays, texel (x, y, layer z) = {v[z], v[min(z + 1, nz - 1)]} */
-    cudaTextureObject_t densityPairTex;
-    cudaTextureObject_t inscatterPairTex;
     /* 1 when every voxel on the six faces of the grid is zero (VDB imports are padded by one voxel,
      * Resources.cpp:97-101): clamped taps outside the grid then read 0 */
     int borderEmpty;

@@ -29,6 +29,7 @@ struct TraceJob {
     int regenMin;      /* fast kernel: regenerate when at least this many lanes of the warp are free */
     int skipMin;       /* fast kernel: enter the empty-space phase with at least this many lanes */
     int skipMaxIters;
+    int zeroCheckMin;  /* fast kernel: look at lanes marching through zero density (box exit / open space) when at least this many wait */
     int skipOpenDist;  /* fast kernel: leave the march phase for the empty-space phase when the tap cell is at least this far (cells) from the cloud */
     /* JOB_RENDER: item = (subframe, 8x4 pixel tile, pixel in tile) */
     float eye[3], U[3], V[3], W[3];
@@ -74,8 +75,7 @@ struct LaunchConfig {
     int smCount;
     int skipEmpty;
     int variant; /* FAST flavour: 0 = optimised k_trace_fast, 1 = generic k_trace<true, SKIP> (round-1 baseline) */
-    int texLayout;   /* k_trace_fast: 0 = 3-D R8 textures, 1 = 2-D layered RG8 z-pair textures */
-    int marchUnroll; /* k_trace_fast: march steps per vote (1 or 2) */
+    int marchUnroll; /* k_trace_fast: march steps per vote (1, or 2 = the taps of two steps in flight together) */
 };
 
 template <bool FAST>
@@ -95,8 +95,6 @@ cudaError_t launchSynth(uint8_t* out, int n, int kind, uint32_t seed, cudaStream
 cudaError_t launchQuantize(const float* in, size_t count, double maxDensity, uint8_t* out, cudaStream_t st);
 cudaError_t launchMip(const uint8_t* prev, int pnx, int pny, int pnz, uint8_t* cur, int cnx, int cny, int cnz, cudaStream_t st);
 cudaError_t launchCellDistance(const uint32_t* occBits, int ocx, int ocy, int ocz, uint8_t* dist, uint8_t* tmp, cudaStream_t st);
-/* 2-D layered RG8 copy of a u8 volume: texel (x, y, layer z) = {v[z], v[min(z + 1, nz - 1)]} */
-cudaError_t launchPackZPair(const uint8_t* volume, int nx, int ny, int nz, cudaSurfaceObject_t surf, cudaStream_t st);
 cudaError_t launchBorderCount(const uint8_t* density, int nx, int ny, int nz, uint32_t* count, cudaStream_t st);
 cudaError_t launchOccupancy(const uint8_t* density, int nx, int ny, int nz, int shift, int ocx, int ocy, int ocz, uint32_t* bits,
                             cudaStream_t st);

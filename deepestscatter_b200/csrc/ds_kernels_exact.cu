@@ -108,24 +108,6 @@ cudaError_t launchOccupancy(const uint8_t* density, int nx, int ny, int nz, int 
     return cudaGetLastError();
 }
 
-/* ---- z-pair copy of a u8 volume into a 2-D layered RG8 array (texture layout 1 of k_trace_fast) ---- */
-__global__ void __launch_bounds__(256) k_pack_zpair(const uint8_t* __restrict__ v, int nx, int ny, int nz, cudaSurfaceObject_t surf)
-{
-    const int x = blockIdx.x * blockDim.x + threadIdx.x;
-    const int y = blockIdx.y, z = blockIdx.z;
-    if (x >= nx) return;
-    const size_t slice = (size_t)nx * ny, row = (size_t)y * nx + x;
-    const uint8_t a = v[(size_t)z * slice + row];
-    const uint8_t b = v[(size_t)min(z + 1, nz - 1) * slice + row];
-    surf2DLayeredwrite(make_uchar2(a, b), surf, x * (int)sizeof(uchar2), y, z);
-}
-
-cudaError_t launchPackZPair(const uint8_t* volume, int nx, int ny, int nz, cudaSurfaceObject_t surf, cudaStream_t st)
-{
-    k_pack_zpair<<<dim3((nx + 255) / 256, ny, nz), 256, 0, st>>>(volume, nx, ny, nz, surf);
-    return cudaGetLastError();
-}
-
 /* ---- number of non-zero voxels on the six faces of the grid ---- */
 __global__ void __launch_bounds__(256) k_border_count(const uint8_t* __restrict__ density, int nx, int ny, int nz, uint32_t* count)
 {

@@ -34,12 +34,16 @@ struct FastState {
     V3 sv;    /* march step in texture space: dir * textureScale * sampleStep */
     float nf; /* march steps taken in this flight; the marching position is q0 + nf * sv */
     float rad;
+    float pendT, pendP; /* sun transmittance and phase of the latest event: rad += pendT * pendP is applied at the NEXT event (or
+                           when the sample is written), so the texture fetch behind pendT has a whole march phase to land */
     float tau;     /* optical depth accumulated in the current free flight */
     float tauStar; /* -ln(xi) */
     uint32_t seed;
     int depth;
     uint32_t out;
 };
+
+constexpr int FAST_MAX_THREADS = 576; /* 2 blocks per SM at 56 registers */
 
 struct FastConsts {
     V3 stepTs;    /* sampleStep * textureScale */
@@ -49,20 +53,24 @@ struct FastConsts {
     float c1;     /* densityMultiplier * sampleStep */
     float invStep;
     float nxf, nyf, nzf;
+    float backScale; /* 1 / (densityMultiplier * sampleStep): march steps per unit of optical depth at density 1 */
 };
 
-__device__ __forceinline__ FastConsts makeConsts(const DevScene& sc)
+/* computed once on the host and passed as a kernel parameter: the values sit in the constant bank and are used as
+ * instruction operands, instead of being re-derived (and kept in registers) by every thread */
+static FastConsts makeConsts(const DevScene& sc)
 {
     FastConsts k;
-    k.stepTs = sc.texScale * sc.step;
-    k.invStepTs = mk(1.0f / k.stepTs.x, 1.0f / k.stepTs.y, 1.0f / k.stepTs.z);
-    k.half = mk(0.5f + 0.01f * sc.texScale.x, 0.5f + 0.01f * sc.texScale.y, 0.5f + 0.01f * sc.texScale.z);
-    k.lightTs = sc.light * k.invStepTs;
+    k.stepTs = V3{sc.texScale.x * sc.step, sc.texScale.y * sc.step, sc.texScale.z * sc.step};
+    k.invStepTs = V3{1.0f / k.stepTs.x, 1.0f / k.stepTs.y, 1.0f / k.stepTs.z};
+    k.half = V3{0.5f + 0.01f * sc.texScale.x, 0.5f + 0.01f * sc.texScale.y, 0.5f + 0.01f * sc.texScale.z};
+    k.lightTs = V3{sc.light.x * k.invStepTs.x, sc.light.y * k.invStepTs.y, sc.light.z * k.invStepTs.z};
     k.c1 = sc.mult * sc.step;
     k.invStep = 1.0f / sc.step;
     k.nxf = (float)sc.nx;
     k.nyf = (float)sc.ny;
     k.nzf = (float)sc.nz;
+    k.backScale = 1.0f / (sc.mult * sc.step);
     return k;
 }
 
@@ -128,23 +136,9 @@ __device__ __forceinline__ float tableLerp(const float* table, float u)
     return fmaf(f, b - a, a);
 }
 
-/*
- * One trilinear fetch of a u8 volume at texture coordinate q.
- *   ZPAIR = false: hardware 3-D filtering of the block-linear R8 array (what rtTex3D does, cloud.cuh:61).
- *   ZPAIR = true:  the volume is also stored as a 2-D LAYERED RG8 array whose texel (x, y, layer z) holds
- *                  {v[z], v[min(z + 1, nz - 1)]}: one bilinear fetch of layer floor(z) returns both z slices, the z
- *                  interpolation is one fp32 lerp.  The footprint of a tap is 2x2 texels of one layer instead of
- *                  2x2x2 texels of two slices: about half the 32-byte sectors per tap through L1TEX/L2.
- */
-template <bool ZPAIR>
-__device__ __forceinline__ float tapVolume(cudaTextureObject_t tex3, cudaTextureObject_t texPair, const FastConsts& k, V3 q)
-{
-    if (!ZPAIR) return tex3D<float>(tex3, q.x, q.y, q.z);
-    const float zf = fminf(fmaxf(fmaf(q.z, k.nzf, -0.5f), 0.0f), k.nzf - 1.0f); /* clamp-to-edge in z */
-    const float fl = floorf(zf);
-    const float2 v = tex2DLayered<float2>(texPair, q.x, q.y, (int)fl);
-    return fmaf(zf - fl, v.y - v.x, v.x);
-}
+/* one trilinear fetch of a u8 volume at texture coordinate q: hardware 3-D filtering of the block-linear R8 array,
+ * what rtTex3D does (cloud.cuh:61) */
+__device__ __forceinline__ float tapVolume(cudaTextureObject_t tex3, V3 q) { return tex3D<float>(tex3, q.x, q.y, q.z); }
 
 /* start of a free flight (cloudRadianceMaterials.cu:28-35, cloud.cuh:120); the flight origin is s.q0 */
 template <bool CHECK_BOX>
@@ -345,9 +339,17 @@ __device__ __forceinline__ bool itemRay(const TraceJob& job, unsigned long long 
     return true;
 }
 
-/* lane states of k_trace_fast */
-enum FastLaneState { F_IDLE = 0, F_SKIP = 1, F_MARCH = 2, F_EVENT = 3, F_DONE = 4 };
+/* lane states of k_trace_fast, one bit each so that a warp vote over a set of states is one LOP + VOTE */
+enum FastLaneState {
+    F_IDLE = 1,   /* wants a work item */
+    F_SKIP = 2,   /* the tap at the current position fell into an empty cell */
+    F_MARCH = 4,  /* marching */
+    F_EVENT = 8,  /* collided: next-event estimate + new direction pending */
+    F_DONE = 16,  /* path ended, sample not yet written */
+    F_OFF = 32    /* idle and the queue is exhausted */
+};
 
+template <int MODE>
 __device__ __forceinline__ int beginItemFast(const DevScene& sc, const FastConsts& k, const TraceJob& job, const float* sCdfPad,
                                              const uint16_t* sGuideA, const uint16_t* sGuideB, unsigned long long idx, FastState& s, bool& valid)
 {
@@ -355,7 +357,7 @@ __device__ __forceinline__ int beginItemFast(const DevScene& sc, const FastConst
     uint32_t val0, stream, pixel;
     valid = itemRay(job, idx, o, d, val0, stream, s.out, pixel);
     if (!valid) return F_IDLE;
-    s.rad = 0.0f;
+    s.rad = s.pendT = s.pendP = 0.0f;
     const float tHit = intersectBox(sc, o, d);
     if (tHit < 0.0f) return F_DONE;
     V3 hit = o + tHit * d;
@@ -364,7 +366,8 @@ __device__ __forceinline__ int beginItemFast(const DevScene& sc, const FastConst
     V3 dir = normalize<true>(d);
     s.seed = tea4(val0, stream);
     s.depth = 0;
-    if (job.mode == DS_MODE_SUN_MULTIPLE_SCATTER) dir = newDirectionFast(sCdfPad, sGuideA, sGuideB, s.seed, dir);
+    const int mode = MODE >= 0 ? MODE : job.mode;
+    if (mode == DS_MODE_SUN_MULTIPLE_SCATTER) dir = newDirectionFast(sCdfPad, sGuideA, sGuideB, s.seed, dir);
     s.sv = dir * k.stepTs;
     if (!beginFlight<true>(k, s)) return F_DONE;
     /* cached empty-space leg of the primary ray: the first taps that can be non-zero follow step entrySteps[pixel] */
@@ -374,7 +377,7 @@ __device__ __forceinline__ int beginItemFast(const DevScene& sc, const FastConst
 
 __device__ __forceinline__ void writeResultFast(const DevScene& sc, const TraceJob& job, const FastState& s, uint32_t& nonfinite)
 {
-    const float scale = sc.lightIntensity * SUN_TO_SPHERE * s.rad;
+    const float scale = sc.lightIntensity * SUN_TO_SPHERE * fmaf(s.pendT, s.pendP, s.rad);
     const float r = sc.lightColor.x * scale, g = sc.lightColor.y * scale, b = sc.lightColor.z * scale;
     if (!(fabsf(r + g + b) <= 3.0e38f)) nonfinite++;
     if (job.kind == JOB_RENDER) {
@@ -395,18 +398,24 @@ __device__ __forceinline__ void writeResultFast(const DevScene& sc, const TraceJ
  *                            device queue (one warp-aggregated atomic); runs when >= regenMin lanes are free
  *   B  empty-space phase     lanes whose tap fell into an empty cell (paths leaving the cloud, paths started in
  *                            empty space): leap DDA, then continue marching; runs when >= skipMin lanes wait
- *   C  march phase           step + density tap + collision test, UNROLL steps per vote.  The loop body is the
- *                            bare minimum: a zero tap changes nothing, so lanes in a hole or past the cloud just
- *                            keep stepping; whether they left the box (all face voxels are zero, so taps outside
- *                            the box read 0 as well) or may leap through empty space is looked at ONCE per round,
- *                            after the loop, and the number of steps the reference would have taken is recovered
- *                            exactly from the step index.  Grids with non-zero faces (BOXTEST) test the box per step.
- *   D  event phase           lanes that collided: next-event estimate + new direction
+ *   C  march phase           step + density tap + collision test.  With UNROLL = 2 the taps of the next TWO steps are
+ *                            issued back to back and then consumed in order (the second is speculative: it is wasted
+ *                            when the first step collides), which halves the exposed texture latency per step.
+ *                            The loop body is the bare minimum: a zero tap changes nothing, so lanes in a hole or
+ *                            past the cloud just keep stepping; whether they left the box (all face voxels are zero,
+ *                            so taps outside the box read 0 as well) or may leap through empty space is looked at
+ *                            ONCE per round, after the loop, and the number of steps the reference would have taken
+ *                            is recovered exactly from the step index.  Grids with non-zero faces (BOXTEST) test the
+ *                            box per step.
+ *   D  event phase           lanes that collided: next-event estimate + new direction.  The sun-transmittance tap is
+ *                            issued first and consumed last.
  * A waiting lane costs nothing but its slot; a phase entered with two lanes costs the whole warp its full
  * instruction stream, which is what the thresholds avoid.  Thresholds are ignored when nothing else can run.
+ * MODE >= 0 fixes the estimator at compile time (DsMode); MODE = -1 reads job.mode.
  */
-template <bool SKIP, bool ZPAIR, bool BOXTEST, int UNROLL, int MAXT>
-__global__ void __launch_bounds__(MAXT, 2) k_trace_fast(const DevScene sc, const TraceJob job)
+template <bool SKIP, bool BOXTEST, int UNROLL, int MODE>
+__global__ void __launch_bounds__(FAST_MAX_THREADS, 2)
+    k_trace_fast(const __grid_constant__ DevScene sc, const __grid_constant__ TraceJob job, const __grid_constant__ FastConsts k)
 {
     extern __shared__ __align__(16) unsigned char smemRaw[];
     float* sChopped = reinterpret_cast<float*>(smemRaw);
@@ -425,26 +434,26 @@ __global__ void __launch_bounds__(MAXT, 2) k_trace_fast(const DevScene sc, const
     for (int i = threadIdx.x; i < GUIDE_B_N; i += blockDim.x) sGuideB[i] = sc.guideB[i];
     __syncthreads();
 
-    const FastConsts k = makeConsts(sc);
+    const int mode = MODE >= 0 ? MODE : job.mode;
     const unsigned FULL = 0xffffffffu;
     const unsigned lane = threadIdx.x & 31u;
     const unsigned laneLt = (1u << lane) - 1u;
 
     FastState s;
     s.q0 = s.sv = mk(0.f, 0.f, 0.f);
-    s.nf = s.rad = s.tau = s.tauStar = 0.f;
+    s.nf = s.rad = s.tau = s.tauStar = s.pendT = s.pendP = 0.f;
     s.seed = 0;
     s.depth = 0;
     s.out = 0;
     int st = F_IDLE;
-    bool exhausted = false;
     uint32_t nPaths = 0, nEvents = 0, nSteps = 0, nTaps = 0, nNonfinite = 0;
     float lastDensity = 0.0f;
+    unsigned roundIdx = 0;
 
     for (;;) {
-        unsigned mBusy = __ballot_sync(FULL, st == F_MARCH || st == F_EVENT);
-        unsigned mSkip = __ballot_sync(FULL, st == F_SKIP);
-        unsigned mFree = __ballot_sync(FULL, st == F_DONE || (st == F_IDLE && !exhausted));
+        unsigned mBusy = __ballot_sync(FULL, (st & (F_MARCH | F_EVENT)) != 0);
+        unsigned mSkip = __ballot_sync(FULL, (st & F_SKIP) != 0);
+        unsigned mFree = __ballot_sync(FULL, (st & (F_IDLE | F_DONE)) != 0);
 
         /* ---- A: retire + regenerate ---- */
         if (mFree && (__popc(mFree) >= job.regenMin || (mBusy == 0u && (mSkip == 0u || __popc(mSkip) < job.skipMin)))) {
@@ -454,30 +463,29 @@ __global__ void __launch_bounds__(MAXT, 2) k_trace_fast(const DevScene sc, const
                     writeResultFast(sc, job, s, nNonfinite);
                     st = F_IDLE;
                 }
-                const unsigned need = __ballot_sync(FULL, st == F_IDLE && !exhausted);
+                const unsigned need = __ballot_sync(FULL, st == F_IDLE);
                 if (need == 0u) break;
                 unsigned long long base = 0;
                 const int leader = __ffs(need) - 1;
                 if ((int)lane == leader) base = atomicAdd(job.queue, (unsigned long long)__popc(need));
                 base = __shfl_sync(FULL, base, leader);
-                if (st == F_IDLE && !exhausted) {
+                if (st == F_IDLE) {
                     const unsigned long long idx = base + __popc(need & laneLt);
                     if (idx >= job.total) {
-                        exhausted = true;
+                        st = F_OFF;
                     } else {
                         bool valid;
-                        st = beginItemFast(sc, k, job, sCdfPad, sGuideA, sGuideB, idx, s, valid);
+                        st = beginItemFast<MODE>(sc, k, job, sCdfPad, sGuideA, sGuideB, idx, s, valid);
                         if (valid) nPaths++;
                     }
                 }
-                mFree = __ballot_sync(FULL, st == F_DONE || (st == F_IDLE && !exhausted));
+                mFree = __ballot_sync(FULL, (st & (F_IDLE | F_DONE)) != 0);
                 if (__popc(mFree) < job.regenMin) break;
             }
-            mSkip = __ballot_sync(FULL, st == F_SKIP);
-            mBusy = __ballot_sync(FULL, st == F_MARCH || st == F_EVENT);
-            mFree = __ballot_sync(FULL, st == F_DONE || (st == F_IDLE && !exhausted));
+            mSkip = __ballot_sync(FULL, (st & F_SKIP) != 0);
+            mBusy = __ballot_sync(FULL, (st & (F_MARCH | F_EVENT)) != 0);
         }
-        if (mBusy == 0u && mSkip == 0u && mFree == 0u) break; /* every lane idle and the queue exhausted */
+        if ((mBusy | mSkip | mFree) == 0u) break; /* every lane off: the queue is exhausted */
 
         /* ---- B: empty-space phase: the tap at the current position fell into an empty cell ---- */
         if (SKIP && mSkip && (__popc(mSkip) >= job.skipMin || mBusy == 0u)) {
@@ -488,68 +496,97 @@ __global__ void __launch_bounds__(MAXT, 2) k_trace_fast(const DevScene sc, const
                 /* a walk cut short lands in an empty cell and continues next round; otherwise march on */
                 st = (more && kf >= 1.0f) ? F_SKIP : F_MARCH;
             }
+            mBusy = __ballot_sync(FULL, (st & (F_MARCH | F_EVENT)) != 0);
         }
 
         /* ---- C: march phase (CU/cloud.cuh:87-104) ---- */
-        const int nBusy = __popc(__ballot_sync(FULL, st == F_MARCH || st == F_EVENT));
-        if (nBusy) {
-            const float nfStart = s.nf;
-            const int keep = (nBusy * job.marchKeep32) >> 5; /* leave when at most this many lanes still march */
+        if (mBusy) {
+            const int keep = (__popc(mBusy) * job.marchKeep32) >> 5; /* leave when at most this many lanes still march */
 #pragma unroll 1
             for (int it = 0; it < job.marchMaxIters; it += UNROLL) {
-#pragma unroll
-                for (int u = 0; u < UNROLL; ++u) {
+                if (!BOXTEST && UNROLL == 2) {
                     if (st == F_MARCH) {
-                        if (BOXTEST && !inBoxTs(k, posAt(s, s.nf))) {
-                            nSteps += (uint32_t)s.nf;
-                            st = F_DONE;
-                        } else {
-                            s.nf += 1.0f;
-                            lastDensity = tapVolume<ZPAIR>(sc.densityTex, sc.densityPairTex, k, posAt(s, s.nf));
-                            s.tau = fmaf(lastDensity, k.c1, s.tau);
-                            if (s.tau > s.tauStar) st = F_EVENT;
+                        const float n1 = s.nf + 1.0f, n2 = s.nf + 2.0f;
+                        const float d1 = tapVolume(sc.densityTex, posAt(s, n1));
+                        const float d2 = tapVolume(sc.densityTex, posAt(s, n2));
+                        const float t1 = fmaf(d1, k.c1, s.tau);
+                        const float t2 = fmaf(d2, k.c1, t1); /* d2 >= 0: t2 >= t1 */
+                        const bool hit1 = t1 > s.tauStar;
+                        s.nf = hit1 ? n1 : n2;
+                        s.tau = hit1 ? t1 : t2;
+                        lastDensity = hit1 ? d1 : d2;
+                        if (t2 > s.tauStar) st = F_EVENT;
+                        nTaps += 2u;
+                    }
+                } else {
+#pragma unroll
+                    for (int u = 0; u < UNROLL; ++u) {
+                        if (st == F_MARCH) {
+                            if (BOXTEST && !inBoxTs(k, posAt(s, s.nf))) {
+                                nSteps += (uint32_t)s.nf;
+                                st = F_DONE;
+                            } else {
+                                s.nf += 1.0f;
+                                lastDensity = tapVolume(sc.densityTex, posAt(s, s.nf));
+                                s.tau = fmaf(lastDensity, k.c1, s.tau);
+                                if (s.tau > s.tauStar) st = F_EVENT;
+                                nTaps++;
+                            }
                         }
                     }
                 }
                 if (__popc(__ballot_sync(FULL, st == F_MARCH)) <= keep) break;
             }
-            nTaps += (uint32_t)(s.nf - nfStart);
 
             /* once per round: lanes whose last tap read 0 */
-            if (st == F_MARCH && lastDensity == 0.0f) {
-                const V3 q = posAt(s, s.nf);
-                if (!BOXTEST && !inBoxTs(k, q)) {
-                    /* left the box: the reference stops at the first position outside it (its taps beyond read 0 too) */
-                    float n = s.nf;
+            /* (with zeroCheckMin > 1 the look is postponed until that many lanes wait, but never beyond 4 rounds and
+             * never when every marching lane waits: a lane past the cloud only wastes zero taps meanwhile) */
+            const bool zero = st == F_MARCH && lastDensity == 0.0f;
+            bool look = job.zeroCheckMin <= 1 || (++roundIdx & 3u) == 0u;
+            if (!look) {
+                const int nZero = __popc(__ballot_sync(FULL, zero));
+                look = nZero >= job.zeroCheckMin || (nZero > 0 && nZero == __popc(__ballot_sync(FULL, st == F_MARCH)));
+            }
+            if (look) {
+                if (zero) {
+                    const V3 q = posAt(s, s.nf);
+                    if (!BOXTEST && !inBoxTs(k, q)) {
+                        /* left the box: the reference stops at the first position outside it (its taps beyond read 0 too) */
+                        float n = s.nf;
 #pragma unroll 1
-                    while (n >= 2.0f && !inBoxTs(k, posAt(s, n - 1.0f))) n -= 1.0f;
-                    nSteps += (uint32_t)n;
-                    st = F_DONE;
-                } else if (SKIP && tapCellDistance(sc, k, q) >= job.skipOpenDist) {
-                    /* open space (no occupied cell within skipOpenDist - 1 cells): leap; pockets next to the cloud
-                     * are cheaper to march through */
-                    st = F_SKIP;
+                        while (n >= 2.0f && !inBoxTs(k, posAt(s, n - 1.0f))) n -= 1.0f;
+                        nSteps += (uint32_t)n;
+                        st = F_DONE;
+                    } else if (SKIP && tapCellDistance(sc, k, q) >= job.skipOpenDist) {
+                        /* open space (no occupied cell within skipOpenDist - 1 cells): leap; pockets next to the cloud
+                         * are cheaper to march through */
+                        st = F_SKIP;
+                    }
                 }
             }
         }
 
         /* ---- D: event phase (cloudRadianceMaterials.cu:49-61) ---- */
         if (st == F_EVENT) {
+            s.rad = fmaf(s.pendT, s.pendP, s.rad); /* the previous event's estimate */
+            s.pendT = s.pendP = 0.0f;
             nSteps += (uint32_t)s.nf;
-            /* cloud.cuh:99: scatterPos = pos - dir * log(xi / T) / sigma, with log(xi / T) = tau - tauStar */
-            const float back = __fdividef(s.tau - s.tauStar, lastDensity * sc.mult);
-            s.q0 = posAt(s, fmaf(-back, k.invStep, s.nf));
+            /* cloud.cuh:99: scatterPos = pos - dir * log(xi / T) / sigma, with log(xi / T) = tau - tauStar; in march
+             * steps: (tau - tauStar) / (density * mult * step) */
+            const float back = __fdividef((s.tau - s.tauStar) * k.backScale, lastDensity);
+            s.q0 = posAt(s, s.nf - back);
             if (!inBoxTs(k, s.q0)) {
                 st = F_DONE;
             } else {
+                s.pendT = tapVolume(sc.inscatterTex, s.q0); /* consumed at the next event */
                 const float cosLightAngle = -dot(k.lightTs, s.sv);
-                const bool choppedPhase = (job.mode == DS_MODE_SUN_AND_SKY_ALL_SCATTER) ? (s.depth != 1) : (job.mode == DS_MODE_SUN_MULTIPLE_SCATTER);
                 const float u = (cosLightAngle + 1.0f) * 0.5f;
-                const float phase = choppedPhase ? tableLerp(sChopped, u) : tableLerp(sc.mie, u);
-                const float tsun = tapVolume<ZPAIR>(sc.inscatterTex, sc.inscatterPairTex, k, s.q0);
-                s.rad = fmaf(tsun, phase, s.rad);
+                if (mode == DS_MODE_SUN_MULTIPLE_SCATTER || (mode == DS_MODE_SUN_AND_SKY_ALL_SCATTER && s.depth != 1))
+                    s.pendP = tableLerp(sChopped, u);
+                else
+                    s.pendP = tableLerp(sc.mie, u);
                 nEvents++;
-                if (job.mode == DS_MODE_SUN_SINGLE_SCATTER) {
+                if (mode == DS_MODE_SUN_SINGLE_SCATTER) {
                     st = F_DONE;
                 } else {
                     const V3 dir = newDirectionFast(sCdfPad, sGuideA, sGuideB, s.seed, s.sv * k.invStepTs);
@@ -569,12 +606,12 @@ __global__ void __launch_bounds__(MAXT, 2) k_trace_fast(const DevScene sc, const
     }
 }
 
-template <bool SKIP, bool ZPAIR, bool BOXTEST, int UNROLL, int MAXT>
+template <bool SKIP, bool BOXTEST, int UNROLL, int MODE>
 static cudaError_t launchFast(const DevScene& sc, const TraceJob& job, int blocks, int threads, size_t smem, cudaStream_t st)
 {
-    cudaError_t e = cudaFuncSetAttribute(k_trace_fast<SKIP, ZPAIR, BOXTEST, UNROLL, MAXT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(k_trace_fast<SKIP, BOXTEST, UNROLL, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    k_trace_fast<SKIP, ZPAIR, BOXTEST, UNROLL, MAXT><<<blocks, threads, smem, st>>>(sc, job);
+    k_trace_fast<SKIP, BOXTEST, UNROLL, MODE><<<blocks, threads, smem, st>>>(sc, job, makeConsts(sc));
     return cudaGetLastError();
 }
 
@@ -583,30 +620,29 @@ cudaError_t KernelSet<true>::trace(const DevScene& sc, const TraceJob& job, cons
 {
     if (cfg.variant == 1) return traceGeneric<true>(sc, job, cfg, st);
     const size_t smem = (size_t)(MIE_N + CDF_PAD_N) * 4 + (size_t)(GUIDE_A_N + GUIDE_B_N) * 2;
-    const int threads = cfg.blockThreads > 640 ? 640 : cfg.blockThreads;
+    const int threads = cfg.blockThreads > FAST_MAX_THREADS ? FAST_MAX_THREADS : cfg.blockThreads;
     const unsigned long long wantBlocks = (job.total + threads - 1) / threads;
     const unsigned long long maxBlocks = (unsigned long long)cfg.smCount * cfg.blocksPerSm;
     const int blocks = (int)(wantBlocks < maxBlocks ? (wantBlocks ? wantBlocks : 1) : maxBlocks);
-    const bool zpair = cfg.texLayout == 1 && sc.densityPairTex != 0 && sc.inscatterPairTex != 0;
     const bool boxtest = sc.borderEmpty == 0;
-    /* register budget follows the block size: 64 regs up to 512 threads, 56 up to 576, 48 up to 640 (2 blocks/SM) */
     if (!cfg.skipEmpty || boxtest) {
-        /* uncommon configurations: one instantiation each */
-        if (cfg.skipEmpty) return launchFast<true, false, true, 1, 512>(sc, job, blocks, threads > 512 ? 512 : threads, smem, st);
-        if (boxtest) return launchFast<false, false, true, 1, 512>(sc, job, blocks, threads > 512 ? 512 : threads, smem, st);
-        return launchFast<false, false, false, 1, 512>(sc, job, blocks, threads > 512 ? 512 : threads, smem, st);
+        /* uncommon configurations (grids with non-zero faces, empty-space skipping switched off): estimator read at run time */
+        if (cfg.skipEmpty) return launchFast<true, true, 1, -1>(sc, job, blocks, threads, smem, st);
+        if (boxtest) return launchFast<false, true, 1, -1>(sc, job, blocks, threads, smem, st);
+        return launchFast<false, false, 1, -1>(sc, job, blocks, threads, smem, st);
     }
     const bool u2 = cfg.marchUnroll >= 2;
-    if (threads <= 512) {
-        if (zpair) return u2 ? launchFast<true, true, false, 2, 512>(sc, job, blocks, threads, smem, st) : launchFast<true, true, false, 1, 512>(sc, job, blocks, threads, smem, st);
-        return u2 ? launchFast<true, false, false, 2, 512>(sc, job, blocks, threads, smem, st) : launchFast<true, false, false, 1, 512>(sc, job, blocks, threads, smem, st);
+    switch (job.mode) {
+    case DS_MODE_SUN_AND_SKY_ALL_SCATTER:
+        return u2 ? launchFast<true, false, 2, DS_MODE_SUN_AND_SKY_ALL_SCATTER>(sc, job, blocks, threads, smem, st)
+                  : launchFast<true, false, 1, DS_MODE_SUN_AND_SKY_ALL_SCATTER>(sc, job, blocks, threads, smem, st);
+    case DS_MODE_SUN_MULTIPLE_SCATTER:
+        return u2 ? launchFast<true, false, 2, DS_MODE_SUN_MULTIPLE_SCATTER>(sc, job, blocks, threads, smem, st)
+                  : launchFast<true, false, 1, DS_MODE_SUN_MULTIPLE_SCATTER>(sc, job, blocks, threads, smem, st);
+    default:
+        return u2 ? launchFast<true, false, 2, DS_MODE_SUN_SINGLE_SCATTER>(sc, job, blocks, threads, smem, st)
+                  : launchFast<true, false, 1, DS_MODE_SUN_SINGLE_SCATTER>(sc, job, blocks, threads, smem, st);
     }
-    if (threads <= 576) {
-        if (zpair) return u2 ? launchFast<true, true, false, 2, 576>(sc, job, blocks, threads, smem, st) : launchFast<true, true, false, 1, 576>(sc, job, blocks, threads, smem, st);
-        return u2 ? launchFast<true, false, false, 2, 576>(sc, job, blocks, threads, smem, st) : launchFast<true, false, false, 1, 576>(sc, job, blocks, threads, smem, st);
-    }
-    if (zpair) return u2 ? launchFast<true, true, false, 2, 640>(sc, job, blocks, threads, smem, st) : launchFast<true, true, false, 1, 640>(sc, job, blocks, threads, smem, st);
-    return u2 ? launchFast<true, false, false, 2, 640>(sc, job, blocks, threads, smem, st) : launchFast<true, false, false, 1, 640>(sc, job, blocks, threads, smem, st);
 }
 
 /*
@@ -615,10 +651,9 @@ cudaError_t KernelSet<true>::trace(const DevScene& sc, const TraceJob& job, cons
  * occupied cell are marked ENTRY_MISS (their radiance sample is exactly 0 for every subframe) and the number of
  * march steps the reference algorithm would spend on them is summed for the work counters.
  */
-__global__ void __launch_bounds__(256) k_primary_prepass(const DevScene sc, const TraceJob job, uint32_t* __restrict__ entrySteps,
+__global__ void __launch_bounds__(256) k_primary_prepass(const DevScene sc, const TraceJob job, const FastConsts k, uint32_t* __restrict__ entrySteps,
                                                          uint32_t* __restrict__ hitList, unsigned long long* __restrict__ counts)
 {
-    const FastConsts k = makeConsts(sc);
     const uint32_t rem = blockIdx.x * blockDim.x + threadIdx.x; /* tile-ordered pixel enumeration, 32 pixels per 8x4 tile */
     const uint32_t tile = rem >> 5, within = rem & 31u;
     const uint32_t px = (tile % (uint32_t)job.tilesX) * 8u + (within & 7u);
@@ -678,7 +713,7 @@ cudaError_t KernelSet<true>::primaryPrepass(const DevScene& sc, const TraceJob& 
                                             unsigned long long* counts, cudaStream_t st)
 {
     const unsigned long long items = cam.itemsPerSubframe;
-    k_primary_prepass<<<(unsigned)((items + 255) / 256), 256, 0, st>>>(sc, cam, entrySteps, hitList, counts);
+    k_primary_prepass<<<(unsigned)((items + 255) / 256), 256, 0, st>>>(sc, cam, makeConsts(sc), entrySteps, hitList, counts);
     return cudaGetLastError();
 }
 

@@ -3,9 +3,10 @@
  *
  * Mirrors the interface of the reference's DeepestScatter::Dataset (DG/Util/Dataset/Dataset.h:87-232,
  * Dataset.cpp): tables named after the protobuf message (`T::descriptor()->name()`), keys are int32 record ids,
- * values are the proto3 wire bytes.  The reference keeps them in one LMDB environment; liblmdb does not exist in
- * this environment, so the store is an append-only record log (`*.dsrec`) with the same table / key / value
- * contract, resumable (`CollectMode::Continue`, Tasks.h:65-68) and mergeable by concatenation (one shard per GPU).
+ * values are the proto3 wire bytes, all in one LMDB data file that DeepestScatter_Train/LmdbDataset.py opens
+ * unchanged.  liblmdb does not exist in this environment; the file format is written by host/LmdbFile.hpp.
+ * Resumable (`CollectMode::Continue`, Tasks.h:65-68: an existing file is loaded and appended to) and mergeable
+ * (one shard per GPU, mergeFrom).
  *
  * Record messages (DeepestScatter_Train/Protocols/*.proto) are plain structs whose serialize() goes through the
  * C-ABI encoders (ds_record_*), i.e. the exact bytes the reference's generated protobuf code writes.
@@ -21,6 +22,7 @@
 #include <vector>
 
 #include "../../include/ds_abi.h"
+#include "LmdbFile.hpp"
 
 namespace Persistance {
 
@@ -233,7 +235,12 @@ struct Result {
 
 namespace DeepestScatter {
 
-/* Dataset (DG/Util/Dataset/Dataset.h): tables by message name, int32 keys, proto3 values. */
+/*
+ * Dataset (DG/Util/Dataset/Dataset.h:87-232, Dataset.cpp): tables by message name, int32 keys, proto3 values, kept in
+ * one LMDB data file (MDB_NOSUBDIR, sub-databases MDB_INTEGERKEY | MDB_CREATE) written by host/LmdbFile.hpp.
+ * A batchAppend is the reference's one-transaction-per-batch; the B+tree pages are written by commit() (destructor,
+ * or explicitly after every N batches for crash safety).
+ */
 class Dataset {
 public:
     struct Settings {
@@ -242,20 +249,10 @@ public:
     };
     using TableName = std::string;
 
-    explicit Dataset(const Settings& settings) : path(settings.path)
+    explicit Dataset(const Settings& settings) : file(settings.path, /*create=*/true)
     {
-        /* "Opening Dataset..." (Dataset.cpp:10): load the index of an existing log */
-        FILE* f = fopen(path.c_str(), "rb");
-        if (f) {
-            load(f);
-            fclose(f);
-        }
-        file = fopen(path.c_str(), "ab");
-        if (!file) throw std::runtime_error("cannot open dataset " + path);
-    }
-    ~Dataset()
-    {
-        if (file) fclose(file);
+        /* "Opening Dataset..." (Dataset.cpp:10) */
+        for (const auto& t : file.tables()) nextIds[t.first] = t.second.empty() ? 0 : (int32_t)t.second.rbegin()->first + 1;
     }
     Dataset(const Dataset&) = delete;
     Dataset& operator=(const Dataset&) = delete;
@@ -263,39 +260,33 @@ public:
     template <class T>
     size_t getRecordsCount()
     {
-        return tables[T::name()].size();
+        file.createTable(T::name()); /* getTable opens with MDB_CREATE (Dataset.cpp:78-90) */
+        return file.count(T::name());
     }
 
     template <class T>
     T getRecord(int32_t recordId)
     {
-        const auto& table = tables[T::name()];
-        const auto it = table.find(recordId);
-        if (it == table.end()) throw std::runtime_error(std::string("MDB_NOTFOUND: no record ") + std::to_string(recordId) + " in table " + T::name());
-        return T::parse(it->second.data(), it->second.size());
+        std::vector<uint8_t> bytes;
+        if (!file.get(T::name(), (uint32_t)recordId, bytes))
+            throw std::runtime_error(std::string("MDB_NOTFOUND: no record ") + std::to_string(recordId) + " in table " + T::name());
+        return T::parse(bytes.data(), bytes.size());
     }
-
-    /* raw bytes, for tests and the LMDB exporter */
-    const std::map<TableName, std::map<int32_t, std::vector<uint8_t>>>& allTables() const { return tables; }
 
     template <class T>
     void dropTable()
     {
-        put(T::name(), DROP_KEY, nullptr, 0);
-        tables[T::name()].clear();
+        file.drop(T::name());
         nextIds[T::name()] = 0;
-        fflush(file);
     }
 
     template <class T>
     void append(const T& example)
     {
-        const int32_t id = nextIds[T::name()];
+        const int32_t id = nextIds[T::name()]; /* zero if not initialised (Dataset.h:150-151) */
         const std::vector<uint8_t> bytes = example.serialize();
-        put(T::name(), id, bytes.data(), bytes.size());
-        tables[T::name()][id] = bytes;
+        file.put(T::name(), (uint32_t)id, bytes.data(), bytes.size());
         nextIds[T::name()] = id + 1;
-        fflush(file);
     }
 
     /* one transaction per batch (Dataset.h:203-232) */
@@ -305,65 +296,39 @@ public:
         int32_t id = startId;
         for (const T& e : examples) {
             const std::vector<uint8_t> bytes = e.serialize();
-            put(T::name(), id, bytes.data(), bytes.size());
-            tables[T::name()][id] = bytes;
+            file.put(T::name(), (uint32_t)id, bytes.data(), bytes.size());
             id++;
         }
         nextIds[T::name()] = startId + (int32_t)examples.size();
-        fflush(file);
     }
 
-    /* append every record of another store (shard merge) */
-    void mergeFrom(const Dataset& other)
+    /* raw bytes (already encoded records) */
+    void putRaw(const TableName& table, int32_t id, const uint8_t* data, size_t n)
     {
-        for (const auto& t : other.tables)
+        file.put(table, (uint32_t)id, data, n);
+        nextIds[table] = std::max(nextIds[table], id + 1);
+    }
+
+    /* copy every record of another dataset (merging the shards written by different GPUs) */
+    void mergeFrom(Dataset& other)
+    {
+        std::vector<uint8_t> bytes;
+        for (const auto& t : other.file.tables()) {
+            file.createTable(t.first);
             for (const auto& kv : t.second) {
-                put(t.first, kv.first, kv.second.data(), kv.second.size());
-                tables[t.first][kv.first] = kv.second;
-            }
-        fflush(file);
-    }
-
-private:
-    static constexpr int32_t DROP_KEY = INT32_MIN; /* log entry that empties a table */
-    static constexpr uint32_t MAGIC = 0x43525344u; /* "DSRC" */
-
-    void put(const TableName& table, int32_t key, const uint8_t* data, size_t n)
-    {
-        const uint32_t magic = MAGIC, len = (uint32_t)n;
-        const uint8_t nameLen = (uint8_t)table.size();
-        if (fwrite(&magic, 4, 1, file) != 1 || fwrite(&nameLen, 1, 1, file) != 1 || fwrite(table.data(), 1, nameLen, file) != nameLen ||
-            fwrite(&key, 4, 1, file) != 1 || fwrite(&len, 4, 1, file) != 1 || (n && fwrite(data, 1, n, file) != n))
-            throw std::runtime_error("dataset write failed: " + path);
-    }
-
-    void load(FILE* f)
-    {
-        for (;;) {
-            uint32_t magic, len;
-            uint8_t nameLen;
-            int32_t key;
-            char name[256];
-            if (fread(&magic, 4, 1, f) != 1) break;
-            if (magic != MAGIC || fread(&nameLen, 1, 1, f) != 1 || fread(name, 1, nameLen, f) != nameLen || fread(&key, 4, 1, f) != 1 ||
-                fread(&len, 4, 1, f) != 1)
-                break; /* truncated tail of an interrupted batch: ignore */
-            std::vector<uint8_t> bytes(len);
-            if (len && fread(bytes.data(), 1, len, f) != len) break;
-            const std::string table(name, nameLen);
-            if (key == DROP_KEY) {
-                tables[table].clear();
-                nextIds[table] = 0;
-            } else {
-                tables[table][key] = std::move(bytes);
-                nextIds[table] = std::max(nextIds[table], key + 1);
+                other.file.get(t.first, kv.first, bytes);
+                putRaw(t.first, (int32_t)kv.first, bytes.data(), bytes.size());
             }
         }
     }
 
-    std::string path;
-    FILE* file = nullptr;
-    std::map<TableName, std::map<int32_t, std::vector<uint8_t>>> tables;
+    /* mdb_txn_commit: make everything appended so far durable and visible to readers */
+    void commit() { file.commit(); }
+
+    dslmdb::LmdbFile& lmdb() { return file; }
+
+private:
+    dslmdb::LmdbFile file;
     std::map<TableName, int32_t> nextIds;
 };
 

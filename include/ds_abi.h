@@ -225,6 +225,42 @@ int ds_record_result(float light_intensity, int is_converged, uint8_t* out, size
 /* Persistance::SceneSetup (DG/ExecutionLoop/Tasks.cpp:77-85) */
 int ds_record_scene_setup(const char* cloud_path, float cloud_size_m, const float light_direction[3], uint8_t* out, size_t cap);
 
+/* ---------------------------------------------------------------- dataset store (LMDB data file, host only) */
+
+/* DeepestScatter::Dataset (DG/Util/Dataset/Dataset.h:87-232, Dataset.cpp:8-18): one LMDB environment opened
+ * MDB_NOSUBDIR, one MDB_INTEGERKEY sub-database per record type named after the protobuf message, key = int32 record
+ * id (native little endian), value = proto3 bytes.  The file is written in LMDB 0.9's on-disk format by this library
+ * itself (no liblmdb dependency; deepestscatter_b200/host/LmdbFile.hpp) and is what
+ * DeepestScatter_Train/LmdbDataset.py opens.  An existing file is loaded and appended to (CollectMode::Continue,
+ * DG/ExecutionLoop/Tasks.h:65-68). */
+typedef struct DsDataset DsDataset;
+int ds_dataset_open(const char* path, DsDataset** out);
+/* commits and closes (Dataset::~Dataset, Dataset.cpp:20-36) */
+int ds_dataset_close(DsDataset* ds);
+/* message of the last failing call (ds may be NULL for open / close failures) */
+const char* ds_dataset_last_error(DsDataset* ds);
+/* mdb_txn_commit: write the B+tree pages and flip the meta page; records appended since the previous commit become
+ * durable and visible to readers.  The reference commits once per batch (Dataset.h:203-232). */
+int ds_dataset_commit(DsDataset* ds);
+/* mdb_put of already encoded record bytes (Dataset::tryAppend, Dataset.h:170-200) */
+int ds_dataset_put(DsDataset* ds, const char* table, int32_t id, const uint8_t* data, size_t n);
+/* mdb_get (Dataset::getRecord, Dataset.h:96-118): returns the record length (copied to out when cap suffices) or a negative error */
+long long ds_dataset_get(DsDataset* ds, const char* table, int32_t id, uint8_t* out, size_t cap);
+/* mdb_stat ms_entries (Dataset::getRecordsCount, Dataset.h:80-93) */
+long long ds_dataset_count(DsDataset* ds, const char* table);
+/* mdb_drop(dbi, 0) (Dataset::dropTable, Dataset.h:120-152, without the console confirmation) */
+int ds_dataset_drop(DsDataset* ds, const char* table);
+/* copy every record of another dataset file into this one (merging per-GPU shards) */
+int ds_dataset_merge(DsDataset* ds, const char* other_path);
+/* SceneSetup record of scene `scene_id` (DG/ExecutionLoop/Tasks.cpp:77-85) */
+int ds_dataset_append_scene_setup(DsDataset* ds, int32_t scene_id, const char* cloud_path, float cloud_size_m, const float light_direction[3]);
+/* ScatterSampleCollector::collect record loop (ScatterSampleCollector.cpp:42-61): ids start_id .. start_id + n - 1 */
+int ds_dataset_append_scatter_samples(DsDataset* ds, int32_t start_id, uint32_t n, const float* positions, const float* directions);
+/* DisneyDescriptorCollector::recordToDataset (DisneyDescriptorCollector.cpp:76-103): n descriptors of descriptor_bytes (2250) each */
+int ds_dataset_append_descriptors(DsDataset* ds, int32_t start_id, uint32_t n, const uint8_t* descriptors, size_t descriptor_bytes);
+/* RadianceCollector::recordToDataset (RadianceCollector.cpp:148-169) */
+int ds_dataset_append_results(DsDataset* ds, int32_t start_id, uint32_t n, const float* light_intensity, const uint8_t* is_converged);
+
 #ifdef __cplusplus
 }
 #endif

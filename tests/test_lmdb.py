@@ -1,0 +1,228 @@
+"""Dataset store: the LMDB data file written by ds_dataset_* (deepestscatter_b200/host/LmdbFile.hpp) read back through an
+independent pure-Python parser with py-lmdb's API (deepestscatter_b200/lmdb_compat.py), the way
+DeepestScatter_Train/LmdbDataset.py:24-66 reads the reference's datasets.  No GPU needed.
+
+FORMAT PARITY IS UNPINNED against liblmdb (neither liblmdb nor py-lmdb exists here): these tests pin the writer against
+the restated format, the record bytes against the golden vectors, and the structural invariants mdb.c relies on."""
+import json
+import struct
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+GOLDEN = json.loads((Path(__file__).parent / "golden" / "records.json").read_text())
+BATCH_SIZE = 2048
+
+
+class LmdbDatasetMirror:
+    """DeepestScatter_Train/LmdbDataset.py, with lmdb -> lmdb_compat and protobuf messages -> raw bytes."""
+
+    def __init__(self, ds, path):
+        self.env = ds.lmdb_compat.Environment(str(path), map_size=3e9, subdir=False, max_dbs=64, mode=0, create=False, readonly=True)
+        self.dbs = {}
+
+    def db(self, name):
+        if name not in self.dbs:
+            self.dbs[name] = self.env.open_db(name.encode("ascii"), integerkey=True, create=False)
+        return self.dbs[name]
+
+    def getCountOf(self, name):
+        with self.env.begin() as transaction:
+            return transaction.stat(self.db(name))["entries"]
+
+    def get(self, name, id, buffers=False):
+        db = self.db(name)
+        with self.env.begin(db=db, buffers=buffers) as transaction:
+            return transaction.get(id.to_bytes(4, "little"), db=db)
+
+
+def parse_vector3(b):
+    v = [0.0, 0.0, 0.0]
+    i = 0
+    while i < len(b):
+        tag = b[i]
+        i += 1
+        assert tag & 7 == 5
+        v[(tag >> 3) - 1] = struct.unpack_from("<f", b, i)[0]
+        i += 4
+    return v
+
+
+def parse_scatter_sample(b):
+    out = {}
+    i = 0
+    while i < len(b):
+        tag = b[i]
+        n = b[i + 1]
+        out[tag >> 3] = parse_vector3(b[i + 2: i + 2 + n])
+        i += 2 + n
+    return out[2], out[3]
+
+
+def synth(n, seed):
+    rng = np.random.default_rng(seed)
+    pos = rng.uniform(-0.5, 0.5, (n, 3)).astype(np.float32)
+    d = rng.normal(size=(n, 3)).astype(np.float32)
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    desc = rng.integers(0, 256, (n, 2250), dtype=np.uint8)
+    rad = rng.uniform(0, 3, n).astype(np.float32)
+    rad[::17] = 0.0
+    return pos, d, desc, rad
+
+
+def test_dataset_written_here_reads_like_the_reference_reader(built_library, tmp_path):
+    ds = built_library
+    path = tmp_path / "Train.lmdb"
+    n = 3 * BATCH_SIZE
+    pos, d, desc, rad = synth(n, 1)
+    with ds.Dataset(path) as w:
+        for scene in range(3):
+            w.append_scene_setup(scene, f"Clouds/cloud{scene}.vdb", 7000.0 + scene, (-0.03, -0.25, 0.8))
+            s = slice(scene * BATCH_SIZE, (scene + 1) * BATCH_SIZE)
+            w.append_scatter_samples(scene * BATCH_SIZE, pos[s], d[s])
+            w.append_descriptors(scene * BATCH_SIZE, desc[s])
+            w.append_results(scene * BATCH_SIZE, rad[s], np.ones(BATCH_SIZE, np.uint8))
+            w.commit()  # one transaction per batch, Dataset.h:203-232
+        assert w.count("ScatterSample") == n and w.count("SceneSetup") == 3
+
+    report = ds.lmdb_compat.check(str(path))
+    assert report["pages_leaked"] == 0
+    assert report["tables"]["DisneyDescriptor"]["overflow_pages"] == n  # 2253-byte values: one overflow page each
+    r = LmdbDatasetMirror(ds, path)
+    assert r.getCountOf("ScatterSample") == n and r.getCountOf("DisneyDescriptor") == n and r.getCountOf("Result") == n
+    assert r.getCountOf("SceneSetup") == 3
+    for i in (0, 1, 2047, 2048, 4095, n - 1, 777, 5000):
+        p, v = parse_scatter_sample(r.get("ScatterSample", i))
+        assert np.array_equal(np.float32(p), pos[i]) and np.array_equal(np.float32(v), d[i])
+        g = r.get("DisneyDescriptor", i, buffers=True)
+        assert len(g) == 2253 and bytes(g[:3]) == b"\x0a\xca\x11"
+        # DisneyDataset.py:26-28: bytes / 256 viewed (10, -1)
+        grid = np.frombuffer(g, np.uint8, offset=3).astype(np.float32) / 256
+        assert grid.reshape(10, -1).shape == (10, 225) and np.array_equal(np.frombuffer(g, np.uint8, offset=3), desc[i])
+        assert r.get("Result", i) == ds.record_result(float(rad[i]), True)
+        scene = r.get("SceneSetup", i // BATCH_SIZE)  # BaseDataset.py:32
+        assert scene == ds.record_scene_setup(f"Clouds/cloud{i // BATCH_SIZE}.vdb", 7000.0 + i // BATCH_SIZE, (-0.03, -0.25, 0.8))
+    assert r.get("Result", n) is None and r.get("Result", 2**31 - 1) is None
+    with pytest.raises(ds.lmdb_compat.Error):
+        r.env.open_db(b"BakedInterpolationSet", integerkey=True)  # MDB_NOTFOUND with create=False
+    # cursor order = key order (LmdbDataset.getCountBeforeLastFlatCloud iterates SceneSetup)
+    with r.env.begin() as t:
+        keys = [int.from_bytes(k, "little") for k, _ in t.cursor(r.db("SceneSetup"))]
+    assert keys == [0, 1, 2]
+
+
+def test_golden_record_bytes_survive_the_store(built_library, tmp_path):
+    ds = built_library
+    path = tmp_path / "g.lmdb"
+    with ds.Dataset(path) as w:
+        for i, g in enumerate(GOLDEN["scatter_sample"]):
+            w.append_scatter_samples(i, [g["point"]], [g["view_direction"]])
+        for i, g in enumerate(GOLDEN["result"]):
+            w.append_results(i, [g["light_intensity"]], [1 if g["is_converged"] else 0])
+    r = LmdbDatasetMirror(ds, path)
+    for i, g in enumerate(GOLDEN["scatter_sample"]):
+        assert r.get("ScatterSample", i).hex() == g["hex"]
+    for i, g in enumerate(GOLDEN["result"]):
+        assert r.get("Result", i).hex() == g["hex"]
+
+
+def test_meta_page_bytes(built_library, tmp_path):
+    """mdb_env_init_meta / mdb_env_write_meta layout at fixed offsets."""
+    ds = built_library
+    path = tmp_path / "m.lmdb"
+    ds.Dataset(path).close()  # nothing appended: both metas still txn 0
+    raw = path.read_bytes()
+    assert len(raw) == 2 * 4096
+    for i in range(2):
+        page = raw[i * 4096:(i + 1) * 4096]
+        assert struct.unpack_from("<QHH", page, 0) == (i, 0, 0x08)  # pgno, pad, P_META
+        magic, version, address, mapsize = struct.unpack_from("<IIQQ", page, 16)
+        assert (magic, version, address, mapsize) == (0xBEEFC0DE, 1, 0, 1048576)
+        psize, flags, depth = struct.unpack_from("<IHH", page, 40)
+        assert psize == 4096 and flags == 0x4008 and depth == 0  # MDB_NOSUBDIR | MDB_INTEGERKEY on the free DB
+        assert struct.unpack_from("<Q", page, 40 + 40)[0] == 2**64 - 1  # free root P_INVALID
+        assert struct.unpack_from("<Q", page, 88 + 40)[0] == 2**64 - 1  # main root P_INVALID
+        assert struct.unpack_from("<QQ", page, 136) == (1, 0)  # last_pg, txnid
+    assert ds.lmdb_compat.check(str(path))["tables"] == {}
+    with ds.Dataset(path) as w:
+        w.put("Result", 0, b"\x10\x01")
+    raw = path.read_bytes()
+    assert struct.unpack_from("<Q", raw, 4096 + 144)[0] == 1  # the first commit goes to meta page 1
+    assert struct.unpack_from("<Q", raw, 144)[0] == 0
+
+
+def test_continue_mode_appends_and_frees_old_tree_pages(built_library, tmp_path):
+    ds = built_library
+    path = tmp_path / "c.lmdb"
+    pos, d, desc, rad = synth(5000, 2)
+    with ds.Dataset(path) as w:
+        w.append_scatter_samples(0, pos[:3000], d[:3000])
+        w.append_descriptors(0, desc[:100])
+    first = ds.lmdb_compat.check(str(path))
+    assert first["txnid"] == 1 and first["pages_free"] == 0
+    with ds.Dataset(path) as w:  # CollectMode::Continue
+        assert w.count("ScatterSample") == 3000
+        w.append_scatter_samples(3000, pos[3000:], d[3000:])
+        w.append_descriptors(100, desc[100:200])
+        w.put("DisneyDescriptor", 5, ds.record_disney_descriptor(bytes(desc[4999])))  # replace a big value
+    second = ds.lmdb_compat.check(str(path))
+    assert second["txnid"] == 2 and second["pages_free"] > 0 and second["pages_leaked"] == 0
+    assert second["tables"]["ScatterSample"]["entries"] == 5000 and second["tables"]["DisneyDescriptor"]["entries"] == 200
+    r = LmdbDatasetMirror(ds, path)
+    assert np.array_equal(np.frombuffer(r.get("DisneyDescriptor", 5), np.uint8, offset=3), desc[4999])
+    assert np.array_equal(np.frombuffer(r.get("DisneyDescriptor", 150), np.uint8, offset=3), desc[150])
+    p, v = parse_scatter_sample(r.get("ScatterSample", 4999))
+    assert np.array_equal(np.float32(p), pos[4999])
+    with ds.Dataset(path) as w:
+        w.drop("DisneyDescriptor")  # mdb_drop(dbi, 0): empty, not deleted
+        assert w.count("DisneyDescriptor") == 0
+    third = ds.lmdb_compat.check(str(path))
+    assert third["tables"]["DisneyDescriptor"]["entries"] == 0 and third["pages_leaked"] == 0
+    assert third["pages_free"] >= second["pages_free"] + 200
+    with ds.Dataset(path) as w:  # a session that writes nothing leaves the file alone
+        pass
+    assert ds.lmdb_compat.check(str(path))["txnid"] == third["txnid"]
+
+
+def test_three_level_tree_and_shard_merge(built_library, tmp_path):
+    ds = built_library
+    n = 120_000
+    rng = np.random.default_rng(3)
+    rad = rng.uniform(0, 2, n).astype(np.float32)
+    a, b, m = tmp_path / "rank0.lmdb", tmp_path / "rank1.lmdb", tmp_path / "merged.lmdb"
+    with ds.Dataset(a) as w:
+        w.append_results(0, rad[: n // 2], np.ones(n // 2, np.uint8))
+    with ds.Dataset(b) as w:
+        w.append_results(n // 2, rad[n // 2:], np.ones(n - n // 2, np.uint8))
+    with ds.Dataset(m) as w:
+        w.merge(str(b))  # shards may arrive in any order
+        w.merge(str(a))
+    rep = ds.lmdb_compat.check(str(m))
+    assert rep["tables"]["Result"]["entries"] == n and rep["tables"]["Result"]["depth"] == 3
+    r = LmdbDatasetMirror(ds, m)
+    for i in list(range(0, n, 997)) + [n - 1, n // 2 - 1, n // 2]:
+        assert r.get("Result", i) == ds.record_result(float(rad[i]), True), i
+    with r.env.begin() as t:
+        keys = np.fromiter((int.from_bytes(k, "little") for k, _ in t.cursor(r.db("Result"))), np.int64)
+    assert np.array_equal(keys, np.arange(n))
+
+
+def test_error_paths(built_library, tmp_path):
+    ds = built_library
+    bad = tmp_path / "bad.lmdb"
+    bad.write_bytes(b"not an lmdb file" * 1000)
+    with pytest.raises(ds.DsError) as e:
+        ds.Dataset(bad)
+    assert "MDB_INVALID" in str(e.value)
+    with pytest.raises(ds.lmdb_compat.Error):
+        ds.lmdb_compat.Environment(str(bad), subdir=False, readonly=True)
+    with pytest.raises(ds.DsError):
+        ds.Dataset(tmp_path / "no_such_dir" / "x.lmdb")
+    with ds.Dataset(tmp_path / "e.lmdb") as w:
+        with pytest.raises(ds.DsError) as e:
+            w.get("Result", 3)
+        assert "MDB_NOTFOUND" in str(e.value)
+        assert w.count("Nothing") == 0
+    with pytest.raises(ds.lmdb_compat.Error):
+        ds.lmdb_compat.Environment(str(tmp_path / "e.lmdb"), subdir=False, readonly=False)
