@@ -17,6 +17,7 @@ from .context import (
     DsError,
     camera_array,
     camera_look_at,
+    cloud_crop_active,
     record_disney_descriptor,
     record_result,
     record_scatter_sample,
@@ -26,5 +27,5 @@ from .context import (
 __all__ = [
     "LIB_PATH", "build_library", "load", "Context", "DsError", "camera_look_at", "camera_array",
     "MODE_ALL_SCATTER", "MODE_MULTIPLE_SCATTER", "MODE_SINGLE_SCATTER", "PRECISION_EXACT", "PRECISION_FAST", "TASK_DTYPE",
-    "record_scatter_sample", "record_disney_descriptor", "record_result", "record_scene_setup", "Dataset", "lmdb_compat",
+    "record_scatter_sample", "record_disney_descriptor", "record_result", "record_scene_setup", "Dataset", "lmdb_compat", "cloud_crop_active",
 ]

@@ -117,6 +117,10 @@ SIGNATURES = {
     "ds_record_disney_descriptor": (_i, [_vp, _sz, _vp, _sz]),
     "ds_record_result": (_i, [_f, _i, _vp, _sz]),
     "ds_record_scene_setup": (_i, [C.c_char_p, _f, _pf, _vp, _sz]),
+    "ds_cloud_load": (_i, [_vp, C.c_char_p, _i, C.POINTER(_i)]),
+    "ds_cloud_forget": (None, [_vp]),
+    "ds_cloud_last_error": (C.c_char_p, []),
+    "ds_cloud_crop_active": (_i, [_vp, _i, _i, _i, _vp, _sz, C.POINTER(_i), C.POINTER(C.c_double)]),
     "ds_dataset_open": (_i, [C.c_char_p, C.POINTER(_vp)]),
     "ds_dataset_close": (_i, [_vp]),
     "ds_dataset_last_error": (C.c_char_p, [_vp]),

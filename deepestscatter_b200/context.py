@@ -142,6 +142,14 @@ class Context:
     def volume_synth(self, n: int, kind: int = 0, seed: int = 1234, build_mips: bool = True):
         self._ck(self.lib.ds_volume_synth(self.h, n, kind, seed, int(build_mips)))
 
+    def cloud_load(self, path: str, build_mips: bool = True):
+        """Resources::loadVolumeBuffer front end: dense .npy grid or synth:<n> spec; returns (nx, ny, nz)."""
+        size = (C.c_int * 3)()
+        rc = self.lib.ds_cloud_load(self.h, str(path).encode(), 1 if build_mips else 0, size)
+        if rc != 0:
+            raise DsError(rc, (self.lib.ds_cloud_last_error() or b"").decode())
+        return tuple(size)
+
     def level_count(self) -> int:
         v = C.c_int()
         self._ck(self.lib.ds_volume_level_count(self.h, C.byref(v)))
@@ -290,6 +298,23 @@ class Context:
         upd = C.c_uint32()
         self._ck(self.lib.ds_point_radiance_run(self.h, _ptr(p), _ptr(d), n, C.byref(s), _ptr(tasks), _ptr(conv), C.byref(upd)))
         return tasks, conv.astype(bool), int(conv.sum()), upd.value
+
+
+def cloud_crop_active(dense: np.ndarray):
+    """Active bounding box expanded by one voxel (Resources.cpp:97-101) of a dense (nz, ny, nx) float grid; host only."""
+    lib = _lib.load()
+    g = np.ascontiguousarray(dense, dtype=np.float32)
+    nz, ny, nx = g.shape
+    dims = (C.c_int * 3)()
+    mx = C.c_double()
+    rc = lib.ds_cloud_crop_active(_ptr(g), nx, ny, nz, None, 0, dims, C.byref(mx))
+    if rc != 0:
+        raise DsError(rc, (lib.ds_cloud_last_error() or b"").decode())
+    out = np.empty((dims[2], dims[1], dims[0]), dtype=np.float32)
+    rc = lib.ds_cloud_crop_active(_ptr(g), nx, ny, nz, _ptr(out), out.size, dims, C.byref(mx))
+    if rc != 0:
+        raise DsError(rc, (lib.ds_cloud_last_error() or b"").decode())
+    return out, mx.value
 
 
 # ---- records (host only; usable without a GPU) ----

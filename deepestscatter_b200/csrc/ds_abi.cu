@@ -334,6 +334,7 @@ static int beginVolume(DsContext* ctx, int nx, int ny, int nz)
     if (nx <= 0 || ny <= 0 || nz <= 0) DS_FAIL(ctx, DS_ERR_INVALID, "bad volume size %dx%dx%d", nx, ny, nz);
     freeVolume(ctx);
     ctx->primaryValid = false;
+    ctx->opt["volume_generation"]++; /* read by the importer's cache (host/CloudImporter.hpp) */
     uint8_t* p = nullptr;
     DS_CUDA(ctx, cudaMalloc(&p, (size_t)nx * ny * nz));
     ctx->levels.push_back(p);
@@ -440,17 +441,20 @@ int ds_context_create(int device, DsContext** out)
     }
     ctx->opt["precision"] = DS_PRECISION_FAST;
     ctx->opt["variant"] = 0;
-    ctx->opt["block_threads"] = 512;
-    ctx->opt["blocks_per_sm"] = 2;
+    ctx->opt["block_threads"] = 896;
+    ctx->opt["blocks_per_sm"] = 1;
     ctx->opt["skip_empty"] = 1;
     ctx->opt["march_keep_quarters"] = 2;
     ctx->opt["march_max_iters"] = 64;
     ctx->opt["march_keep32"] = 14;
-    ctx->opt["regen_min"] = 2;
+    ctx->opt["regen_min"] = 4;
     ctx->opt["skip_min"] = 8;
     ctx->opt["skip_max_iters"] = 32;
     ctx->opt["skip_open_dist"] = 1;
     ctx->opt["zero_check_min"] = 2;
+    ctx->opt["radiance_scheduler"] = 1;
+    ctx->opt["volume_generation"] = 0;
+    ctx->opt["radiance_quota"] = 256;
     ctx->opt["march_unroll"] = 2;
     ctx->opt["staging_subframes"] = 16;
     ctx->opt["stream_offset"] = 0;
@@ -510,6 +514,7 @@ int ds_context_create(int device, DsContext** out)
 
 int ds_context_destroy(DsContext* ctx)
 {
+    ds_cloud_forget(ctx); /* the importer's cache entry dies with the context */
     if (!ctx) return DS_ERR_INVALID;
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
@@ -1223,6 +1228,72 @@ int ds_point_radiance_run(DsContext* ctx, const float* positions, const float* d
     if (cfg.launches_per_update == 0) DS_FAIL(ctx, DS_ERR_INVALID, "launches_per_update must be > 0");
     if ((unsigned long long)cfg.max_thread_count * cfg.launches_per_update >= (1ull << 32))
         DS_FAIL(ctx, DS_ERR_INVALID, "max_thread_count x launches_per_update must stay below 2^32");
+
+    /* FAST flavour, option "radiance_scheduler" = 1 (default): the device-resident collector (AdaptiveCollector,
+     * ds_kernels.h) -- one launch for the whole batch, same convergence rule, no host round trips.  The reference
+     * schedule below stays available (option = 0) and is what the EXACT flavour always runs (bit-exact with the oracle). */
+    if (ctx->opt["precision"] == DS_PRECISION_FAST && ctx->opt["radiance_scheduler"] == 1 && ctx->borderEmpty && ctx->opt["skip_empty"] &&
+        ctx->opt["variant"] == 0) {
+        const uint32_t repeat = cfg.max_thread_count / n;
+        const size_t perSample = 8 + 8 + 8 + 4 + 4;
+        const size_t stateBytes = (size_t)n * perSample + 64;
+        if ((rc = ensureScratch(ctx, 5, (size_t)n * sizeof(DsPointRadianceTask))) || (rc = ensureScratch(ctx, 6, stateBytes))) return rc;
+        std::vector<DsPointRadianceTask> samples(n);
+        for (uint32_t i = 0; i < n; i++) {
+            DsPointRadianceTask t{};
+            t.id = (int32_t)i;
+            memcpy(t.position, positions + 3 * i, 12);
+            memcpy(t.direction, directions + 3 * i, 12);
+            samples[i] = t;
+        }
+        DsPointRadianceTask* dTasks = (DsPointRadianceTask*)ctx->scratch[5];
+        uint8_t* state = (uint8_t*)ctx->scratch[6];
+        DS_CUDA(ctx, cudaMemcpyAsync(dTasks, samples.data(), (size_t)n * sizeof(DsPointRadianceTask), cudaMemcpyHostToDevice, ctx->stream));
+        DS_CUDA(ctx, cudaMemsetAsync(state, 0, stateBytes, ctx->stream));
+        TraceJob job;
+        memset(&job, 0, sizeof(job));
+        job.kind = JOB_ADAPTIVE;
+        job.mode = DS_MODE_SUN_MULTIPLE_SCATTER; /* Tasks.cpp:134 */
+        job.tasks = dTasks;
+        job.total = ~0ull >> 1;
+        AdaptiveCollector& ad = job.ad;
+        ad.sum = (double*)state;
+        ad.sumSq = ad.sum + n;
+        ad.count = (unsigned long long*)(ad.sumSq + n);
+        ad.issued = (uint32_t*)(ad.count + n);
+        ad.flag = ad.issued + n;
+        ad.closed = ad.flag + n;
+        ad.ticket = (unsigned long long*)(state + (((size_t)n * perSample + 8 + 7) & ~(size_t)7));
+        ad.nSamples = n;
+        ad.quota = (uint32_t)std::max(1, ctx->opt["radiance_quota"]);
+        /* the reference's first convergence test sees repeat x launches_per_update experiments per sample */
+        ad.minExperiments = repeat * cfg.launches_per_update;
+        ad.maxExperiments = cfg.max_updates ? (uint32_t)std::min<unsigned long long>(0xffffffffull, (unsigned long long)cfg.max_updates * ad.minExperiments) : 0u;
+        ad.zeroMin = cfg.zero_radiance_min_experiments;
+        ad.relCI = cfg.relative_ci;
+        ad.absCI = cfg.absolute_ci;
+        rc = runTrace(ctx, job);
+        if (rc) return rc;
+        std::vector<uint8_t> host(stateBytes);
+        DS_CUDA(ctx, cudaMemcpyAsync(host.data(), state, stateBytes, cudaMemcpyDeviceToHost, ctx->stream));
+        DS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        const double* hSum = (const double*)host.data();
+        const double* hSq = hSum + n;
+        const unsigned long long* hCount = (const unsigned long long*)(hSq + n);
+        const uint32_t* hFlag = (const uint32_t*)(hCount + n) + n;
+        for (uint32_t i = 0; i < n; i++) {
+            DsPointRadianceTask t = samples[i];
+            const double N = (double)hCount[i];
+            const double mean = N > 0 ? hSum[i] / N : 0.0;
+            t.experiment_count = (uint32_t)std::min<unsigned long long>(hCount[i], 0xffffffffull);
+            t.radiance = (float)mean;
+            t.running_variance = (float)std::max(hSq[i] - N * mean * mean, 0.0);
+            tasks_out[i] = t;
+            converged_out[i] = hFlag[i] == 1u ? 1 : 0;
+        }
+        if (updates_out) *updates_out = 1;
+        return DS_OK;
+    }
 
     /* RadianceCollector::init (:27-47) */
     std::vector<DsPointRadianceTask> todo(n);

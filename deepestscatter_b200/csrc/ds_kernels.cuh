@@ -247,7 +247,9 @@ cudaError_t traceGeneric(const DevScene& sc, const TraceJob& job, const LaunchCo
     const size_t smem = (size_t)(2 * MIE_N + (cfg.skipEmpty ? sc.occWords : 0)) * 4;
     const int threads = cfg.blockThreads > 512 ? 512 : cfg.blockThreads; /* __launch_bounds__(512, 2) */
     unsigned long long wantBlocks = (job.total + threads - 1) / threads;
-    const unsigned long long maxBlocks = (unsigned long long)cfg.smCount * cfg.blocksPerSm;
+    /* the options describe threads per SM (block_threads x blocks_per_sm, tuned for k_trace_fast); keep that many resident here */
+    const int perSm = (cfg.blockThreads * cfg.blocksPerSm + threads - 1) / threads;
+    const unsigned long long maxBlocks = (unsigned long long)cfg.smCount * (perSm < 1 ? 1 : perSm > 2 ? 2 : perSm);
     const int blocks = (int)(wantBlocks < maxBlocks ? (wantBlocks ? wantBlocks : 1) : maxBlocks);
     cudaError_t e;
     if (cfg.skipEmpty) {

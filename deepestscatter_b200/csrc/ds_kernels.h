@@ -11,7 +11,27 @@
 
 namespace dsk {
 
-enum JobKind { JOB_RENDER = 0, JOB_PATHS = 1, JOB_POINT = 2 };
+enum JobKind { JOB_RENDER = 0, JOB_PATHS = 1, JOB_POINT = 2, JOB_ADAPTIVE = 3 };
+
+/* JOB_ADAPTIVE: device-resident radiance collector of the FAST flavour.  One launch per batch of samples:
+ * warps draw tickets (sample, `quota` experiment ids), lanes run the experiments, finished paths are summed into the
+ * sample's accumulators and the lane that commits applies the reference's convergence rule (RadianceCollector.cpp:108-118,
+ * PointRadianceTask.h:23-36); a converged sample is closed and receives no more tickets. */
+struct AdaptiveCollector {
+    double* sum;               /* [n] sum of the radiance samples */
+    double* sumSq;             /* [n] sum of their squares */
+    unsigned long long* count; /* [n] experiments accumulated */
+    uint32_t* issued;          /* [n] experiment ids handed out */
+    uint32_t* flag;            /* [n] 0 = open, 1 = converged, 2 = closed by the experiment cap */
+    uint32_t* closed;          /* number of samples with flag != 0 */
+    unsigned long long* ticket;
+    uint32_t nSamples;
+    uint32_t quota;            /* experiments per ticket */
+    uint32_t minExperiments;   /* no convergence test before this many (the reference's first test comes after repeat x 100) */
+    uint32_t maxExperiments;   /* 0 = unlimited */
+    uint32_t zeroMin;          /* zero-radiance samples need more than this many experiments */
+    float relCI, absCI;
+};
 
 /* index of the 64-bit work counters on the device */
 enum { CNT_PATHS = 0, CNT_EVENTS = 1, CNT_STEPS = 2, CNT_TAPS = 3, CNT_NONFINITE = 4, CNT_COUNT = 8 };
@@ -53,6 +73,8 @@ struct TraceJob {
     uint32_t launches;
     uint32_t frame0;
     float* xOut; /* [threads][launches] */
+    /* JOB_ADAPTIVE: sample i = tasks[i].position / direction */
+    AdaptiveCollector ad;
 };
 
 constexpr uint32_t ENTRY_MISS = 0xffffffffu;

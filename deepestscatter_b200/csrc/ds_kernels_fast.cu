@@ -43,7 +43,7 @@ struct FastState {
     uint32_t out;
 };
 
-constexpr int FAST_MAX_THREADS = 576; /* 2 blocks per SM at 56 registers */
+constexpr int FAST_MAX_THREADS = 1024; /* 64 registers: one block of 1024 threads or two of 512 per SM */
 
 struct FastConsts {
     V3 stepTs;    /* sampleStep * textureScale */
@@ -349,14 +349,11 @@ enum FastLaneState {
     F_OFF = 32    /* idle and the queue is exhausted */
 };
 
+/* start of the path of one radiance ray (closest-hit entry, cloudRadianceMaterials.cu:9-27 / 72-90) */
 template <int MODE>
-__device__ __forceinline__ int beginItemFast(const DevScene& sc, const FastConsts& k, const TraceJob& job, const float* sCdfPad,
-                                             const uint16_t* sGuideA, const uint16_t* sGuideB, unsigned long long idx, FastState& s, bool& valid)
+__device__ __forceinline__ int beginPathFast(const DevScene& sc, const FastConsts& k, const TraceJob& job, const float* sCdfPad, const uint16_t* sGuideA,
+                                             const uint16_t* sGuideB, V3 o, V3 d, uint32_t val0, uint32_t stream, FastState& s)
 {
-    V3 o, d;
-    uint32_t val0, stream, pixel;
-    valid = itemRay(job, idx, o, d, val0, stream, s.out, pixel);
-    if (!valid) return F_IDLE;
     s.rad = s.pendT = s.pendP = 0.0f;
     const float tHit = intersectBox(sc, o, d);
     if (tHit < 0.0f) return F_DONE;
@@ -370,9 +367,64 @@ __device__ __forceinline__ int beginItemFast(const DevScene& sc, const FastConst
     if (mode == DS_MODE_SUN_MULTIPLE_SCATTER) dir = newDirectionFast(sCdfPad, sGuideA, sGuideB, s.seed, dir);
     s.sv = dir * k.stepTs;
     if (!beginFlight<true>(k, s)) return F_DONE;
-    /* cached empty-space leg of the primary ray: the first taps that can be non-zero follow step entrySteps[pixel] */
-    if (job.kind == JOB_RENDER && job.entrySteps) s.nf = (float)job.entrySteps[pixel];
     return F_MARCH;
+}
+
+template <int MODE>
+__device__ __forceinline__ int beginItemFast(const DevScene& sc, const FastConsts& k, const TraceJob& job, const float* sCdfPad,
+                                             const uint16_t* sGuideA, const uint16_t* sGuideB, unsigned long long idx, FastState& s, bool& valid)
+{
+    V3 o, d;
+    uint32_t val0, stream, pixel;
+    valid = itemRay(job, idx, o, d, val0, stream, s.out, pixel);
+    if (!valid) return F_IDLE;
+    const int st = beginPathFast<MODE>(sc, k, job, sCdfPad, sGuideA, sGuideB, o, d, val0, stream, s);
+    /* cached empty-space leg of the primary ray: the first taps that can be non-zero follow step entrySteps[pixel] */
+    if (st == F_MARCH && job.kind == JOB_RENDER && job.entrySteps) s.nf = (float)job.entrySteps[pixel];
+    return st;
+}
+
+/* ---- JOB_ADAPTIVE: device-resident radiance collector ---- */
+constexpr uint32_t AD_NONE = 0xffffffffu, AD_ALLDONE = 0xfffffffeu;
+
+/* add c experiments (sum dx, sum of squares dxx) to sample sid and apply the convergence rule of
+ * RadianceCollector.cpp:108-118 with the confidence intervals of PointRadianceTask.h:23-36 */
+__device__ __forceinline__ void adaptiveCommit(const AdaptiveCollector& ad, uint32_t sid, double dx, double dxx, unsigned c)
+{
+    const unsigned long long c0 = atomicAdd(ad.count + sid, (unsigned long long)c);
+    const double s0 = atomicAdd(ad.sum + sid, dx);
+    const double q0 = atomicAdd(ad.sumSq + sid, dxx);
+    const double N = (double)(c0 + c);
+    /* test at the reference's cadence -- once per `minExperiments` new experiments of the sample (its update adds
+     * repeat x 100 per sample between two tests) -- not after every commit: testing a running confidence interval more
+     * often stops earlier on an under-estimated variance */
+    if ((c0 + c) / ad.minExperiments == c0 / ad.minExperiments) return;
+    const double mean = (s0 + dx) / N;
+    const double m2 = fmax((q0 + dxx) - N * mean * mean, 0.0);
+    const float Nf = (float)N;
+    const float sigma = sqrtf((float)m2 / Nf);
+    const float absoluteCI = 1.96f * sigma / sqrtf(Nf);
+    const float relativeCI = absoluteCI / ((float)mean + 1.1920929e-07f);
+    bool converged = relativeCI < ad.relCI || absoluteCI < ad.absCI;
+    if ((float)mean < 1.1920929e-07f) converged = N > (double)ad.zeroMin;
+    if (converged) {
+        if (atomicCAS(ad.flag + sid, 0u, 1u) == 0u) atomicAdd(ad.closed, 1u);
+    } else if (ad.maxExperiments && N >= (double)ad.maxExperiments) {
+        if (atomicCAS(ad.flag + sid, 0u, 2u) == 0u) atomicAdd(ad.closed, 1u); /* experiment cap (max_updates) */
+    }
+}
+
+/* lane 0: next open sample and the first of `quota` fresh experiment ids for it */
+__device__ __forceinline__ uint32_t adaptiveTicket(const AdaptiveCollector& ad, uint32_t& base)
+{
+    for (int tries = 0; tries < 32; ++tries) {
+        if (*(volatile uint32_t*)ad.closed >= ad.nSamples) return AD_ALLDONE;
+        const uint32_t sid = (uint32_t)(atomicAdd(ad.ticket, 1ull) % ad.nSamples);
+        if (*(volatile uint32_t*)(ad.flag + sid) != 0u) continue;
+        base = atomicAdd(ad.issued + sid, ad.quota);
+        return sid;
+    }
+    return AD_NONE;
 }
 
 __device__ __forceinline__ void writeResultFast(const DevScene& sc, const TraceJob& job, const FastState& s, uint32_t& nonfinite)
@@ -413,8 +465,8 @@ __device__ __forceinline__ void writeResultFast(const DevScene& sc, const TraceJ
  * instruction stream, which is what the thresholds avoid.  Thresholds are ignored when nothing else can run.
  * MODE >= 0 fixes the estimator at compile time (DsMode); MODE = -1 reads job.mode.
  */
-template <bool SKIP, bool BOXTEST, int UNROLL, int MODE>
-__global__ void __launch_bounds__(FAST_MAX_THREADS, 2)
+template <bool SKIP, bool BOXTEST, int UNROLL, int MODE, bool ADAPT>
+__global__ void __launch_bounds__(FAST_MAX_THREADS, 1)
     k_trace_fast(const __grid_constant__ DevScene sc, const __grid_constant__ TraceJob job, const __grid_constant__ FastConsts k)
 {
     extern __shared__ __align__(16) unsigned char smemRaw[];
@@ -448,7 +500,13 @@ __global__ void __launch_bounds__(FAST_MAX_THREADS, 2)
     int st = F_IDLE;
     uint32_t nPaths = 0, nEvents = 0, nSteps = 0, nTaps = 0, nNonfinite = 0;
     float lastDensity = 0.0f;
+    /* PIPE: every lane in F_MARCH holds the densities of its next two steps (nf + 1, nf + 2), fetched when the lane
+     * ENTERED that state -- at the end of the event phase, of the empty-space phase or of regeneration -- so the
+     * texture latency of the first march iteration of a round hides behind the rest of the previous round */
+    constexpr bool PIPE = !BOXTEST && UNROLL == 2;
+    float pd1 = 0.0f, pd2 = 0.0f;
     unsigned roundIdx = 0;
+    uint32_t wSample = 0, wNext = 0, wQuota = 0; /* ADAPT: the warp's current ticket (uniform across lanes) */
 
     for (;;) {
         unsigned mBusy = __ballot_sync(FULL, (st & (F_MARCH | F_EVENT)) != 0);
@@ -456,7 +514,75 @@ __global__ void __launch_bounds__(FAST_MAX_THREADS, 2)
         unsigned mFree = __ballot_sync(FULL, (st & (F_IDLE | F_DONE)) != 0);
 
         /* ---- A: retire + regenerate ---- */
-        if (mFree && (__popc(mFree) >= job.regenMin || (mBusy == 0u && (mSkip == 0u || __popc(mSkip) < job.skipMin)))) {
+        if (ADAPT && mFree && (__popc(mFree) >= job.regenMin || (mBusy == 0u && (mSkip == 0u || __popc(mSkip) < job.skipMin)))) {
+            /* retire: finished paths are summed per sample (lanes of a warp mostly share one) and committed by one lane */
+            const bool isDone = st == F_DONE;
+            unsigned rem = __ballot_sync(FULL, isDone);
+            float x = 0.0f;
+            if (isDone) {
+                x = sc.lightColor.x * (sc.lightIntensity * SUN_TO_SPHERE * fmaf(s.pendT, s.pendP, s.rad)); /* pointEmissionCamera.cu:32: result.x */
+                if (!(fabsf(x) <= 3.0e38f)) {
+                    nNonfinite++;
+                    x = 0.0f;
+                }
+                st = F_IDLE;
+            }
+#pragma unroll 1
+            while (rem) {
+                const int l0 = __ffs(rem) - 1;
+                const uint32_t sid0 = __shfl_sync(FULL, s.out, l0);
+                const bool mine = isDone && s.out == sid0;
+                const unsigned same = __ballot_sync(FULL, mine);
+                double dx = mine ? (double)x : 0.0, dxx = dx * dx;
+                for (int o = 16; o > 0; o >>= 1) {
+                    dx += __shfl_xor_sync(FULL, dx, o);
+                    dxx += __shfl_xor_sync(FULL, dxx, o);
+                }
+                if ((int)lane == l0) adaptiveCommit(job.ad, sid0, dx, dxx, (unsigned)__popc(same));
+                rem &= ~same;
+            }
+            /* regenerate: free lanes take the next experiments of the warp's ticket */
+#pragma unroll 1
+            for (int r = 0; r < 4; ++r) {
+                const unsigned need = __ballot_sync(FULL, st == F_IDLE);
+                if (need == 0u) break;
+                if (wQuota == 0u) {
+                    uint32_t sidNew = AD_NONE, base = 0;
+                    if (lane == 0) sidNew = adaptiveTicket(job.ad, base);
+                    sidNew = __shfl_sync(FULL, sidNew, 0);
+                    base = __shfl_sync(FULL, base, 0);
+                    if (sidNew == AD_ALLDONE) {
+                        if (st == F_IDLE) st = F_OFF;
+                        break;
+                    }
+                    if (sidNew == AD_NONE) break; /* every ticket drawn was a closed sample: try again next round */
+                    wSample = sidNew;
+                    wNext = base;
+                    wQuota = job.ad.quota;
+                }
+                const unsigned take = min((unsigned)__popc(need), wQuota);
+                const unsigned rank = (unsigned)__popc(need & laneLt);
+                if (st == F_IDLE && rank < take) {
+                    const DsPointRadianceTask* task = job.tasks + wSample;
+                    const V3 o = mk(task->position[0], task->position[1], task->position[2]);
+                    const V3 d = mk(task->direction[0], task->direction[1], task->direction[2]);
+                    s.out = wSample;
+                    st = beginPathFast<MODE>(sc, k, job, sCdfPad, sGuideA, sGuideB, o, d, wSample * 4096u, wNext + rank + 1u, s);
+                    nPaths++;
+                    if (PIPE && st == F_MARCH) {
+                        pd1 = tapVolume(sc.densityTex, posAt(s, s.nf + 1.0f));
+                        pd2 = tapVolume(sc.densityTex, posAt(s, s.nf + 2.0f));
+                        nTaps += 2u;
+                    }
+                }
+                wNext += take;
+                wQuota -= take;
+            }
+            mFree = __ballot_sync(FULL, (st & (F_IDLE | F_DONE)) != 0);
+            mSkip = __ballot_sync(FULL, (st & F_SKIP) != 0);
+            mBusy = __ballot_sync(FULL, (st & (F_MARCH | F_EVENT)) != 0);
+        }
+        if (!ADAPT && mFree && (__popc(mFree) >= job.regenMin || (mBusy == 0u && (mSkip == 0u || __popc(mSkip) < job.skipMin)))) {
 #pragma unroll 1
             for (int r = 0; r < 4; ++r) {
                 if (st == F_DONE) {
@@ -477,6 +603,11 @@ __global__ void __launch_bounds__(FAST_MAX_THREADS, 2)
                         bool valid;
                         st = beginItemFast<MODE>(sc, k, job, sCdfPad, sGuideA, sGuideB, idx, s, valid);
                         if (valid) nPaths++;
+                        if (PIPE && st == F_MARCH) {
+                            pd1 = tapVolume(sc.densityTex, posAt(s, s.nf + 1.0f));
+                            pd2 = tapVolume(sc.densityTex, posAt(s, s.nf + 2.0f));
+                            nTaps += 2u;
+                        }
                     }
                 }
                 mFree = __ballot_sync(FULL, (st & (F_IDLE | F_DONE)) != 0);
@@ -495,6 +626,11 @@ __global__ void __launch_bounds__(FAST_MAX_THREADS, 2)
                 s.nf += kf;
                 /* a walk cut short lands in an empty cell and continues next round; otherwise march on */
                 st = (more && kf >= 1.0f) ? F_SKIP : F_MARCH;
+                if (PIPE && st == F_MARCH) {
+                    pd1 = tapVolume(sc.densityTex, posAt(s, s.nf + 1.0f));
+                    pd2 = tapVolume(sc.densityTex, posAt(s, s.nf + 2.0f));
+                    nTaps += 2u;
+                }
             }
             mBusy = __ballot_sync(FULL, (st & (F_MARCH | F_EVENT)) != 0);
         }
@@ -504,19 +640,22 @@ __global__ void __launch_bounds__(FAST_MAX_THREADS, 2)
             const int keep = (__popc(mBusy) * job.marchKeep32) >> 5; /* leave when at most this many lanes still march */
 #pragma unroll 1
             for (int it = 0; it < job.marchMaxIters; it += UNROLL) {
-                if (!BOXTEST && UNROLL == 2) {
+                if (PIPE) {
                     if (st == F_MARCH) {
                         const float n1 = s.nf + 1.0f, n2 = s.nf + 2.0f;
-                        const float d1 = tapVolume(sc.densityTex, posAt(s, n1));
-                        const float d2 = tapVolume(sc.densityTex, posAt(s, n2));
-                        const float t1 = fmaf(d1, k.c1, s.tau);
-                        const float t2 = fmaf(d2, k.c1, t1); /* d2 >= 0: t2 >= t1 */
+                        const float t1 = fmaf(pd1, k.c1, s.tau);
+                        const float t2 = fmaf(pd2, k.c1, t1); /* pd2 >= 0: t2 >= t1 */
                         const bool hit1 = t1 > s.tauStar;
                         s.nf = hit1 ? n1 : n2;
                         s.tau = hit1 ? t1 : t2;
-                        lastDensity = hit1 ? d1 : d2;
-                        if (t2 > s.tauStar) st = F_EVENT;
-                        nTaps += 2u;
+                        lastDensity = hit1 ? pd1 : pd2;
+                        if (t2 > s.tauStar) {
+                            st = F_EVENT;
+                        } else {
+                            pd1 = tapVolume(sc.densityTex, posAt(s, n2 + 1.0f));
+                            pd2 = tapVolume(sc.densityTex, posAt(s, n2 + 2.0f));
+                            nTaps += 2u;
+                        }
                     }
                 } else {
 #pragma unroll
@@ -592,6 +731,11 @@ __global__ void __launch_bounds__(FAST_MAX_THREADS, 2)
                     const V3 dir = newDirectionFast(sCdfPad, sGuideA, sGuideB, s.seed, s.sv * k.invStepTs);
                     s.sv = dir * k.stepTs;
                     st = beginFlight<false>(k, s) ? F_MARCH : F_DONE; /* q0 is the scatter position just verified in-box */
+                    if (PIPE && st == F_MARCH) {
+                        pd1 = tapVolume(sc.densityTex, posAt(s, 1.0f));
+                        pd2 = tapVolume(sc.densityTex, posAt(s, 2.0f));
+                        nTaps += 2u;
+                    }
                 }
             }
         }
@@ -606,12 +750,12 @@ __global__ void __launch_bounds__(FAST_MAX_THREADS, 2)
     }
 }
 
-template <bool SKIP, bool BOXTEST, int UNROLL, int MODE>
+template <bool SKIP, bool BOXTEST, int UNROLL, int MODE, bool ADAPT = false>
 static cudaError_t launchFast(const DevScene& sc, const TraceJob& job, int blocks, int threads, size_t smem, cudaStream_t st)
 {
-    cudaError_t e = cudaFuncSetAttribute(k_trace_fast<SKIP, BOXTEST, UNROLL, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(k_trace_fast<SKIP, BOXTEST, UNROLL, MODE, ADAPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    k_trace_fast<SKIP, BOXTEST, UNROLL, MODE><<<blocks, threads, smem, st>>>(sc, job, makeConsts(sc));
+    k_trace_fast<SKIP, BOXTEST, UNROLL, MODE, ADAPT><<<blocks, threads, smem, st>>>(sc, job, makeConsts(sc));
     return cudaGetLastError();
 }
 
@@ -625,6 +769,12 @@ cudaError_t KernelSet<true>::trace(const DevScene& sc, const TraceJob& job, cons
     const unsigned long long maxBlocks = (unsigned long long)cfg.smCount * cfg.blocksPerSm;
     const int blocks = (int)(wantBlocks < maxBlocks ? (wantBlocks ? wantBlocks : 1) : maxBlocks);
     const bool boxtest = sc.borderEmpty == 0;
+    if (job.kind == JOB_ADAPTIVE) {
+        /* the collector always runs multipleScatterSunRadiance (Tasks.cpp:134); the host falls back to the update loop for
+         * grids with non-zero faces */
+        if (boxtest || !cfg.skipEmpty || job.mode != DS_MODE_SUN_MULTIPLE_SCATTER) return cudaErrorInvalidValue;
+        return launchFast<true, false, 2, DS_MODE_SUN_MULTIPLE_SCATTER, true>(sc, job, (int)maxBlocks, threads, smem, st);
+    }
     if (!cfg.skipEmpty || boxtest) {
         /* uncommon configurations (grids with non-zero faces, empty-space skipping switched off): estimator read at run time */
         if (cfg.skipEmpty) return launchFast<true, true, 1, -1>(sc, job, blocks, threads, smem, st);

@@ -167,7 +167,7 @@ public:
     /* Resources::loadVolumeBuffer(path, createMipmaps): returns the grid size in voxels */
     void load(const std::string& path, bool createMipmaps, int sizeOut[3])
     {
-        if (path == cachedPath && createMipmaps == cachedMips) { /* "Using cached." (Resources.cpp:73-78) */
+        if (path == cachedPath && createMipmaps == cachedMips && generation() == cachedGeneration) { /* "Using cached." (Resources.cpp:73-78) */
             memcpy(sizeOut, cachedSize, sizeof(cachedSize));
             return;
         }
@@ -192,6 +192,7 @@ public:
         }
         cachedPath = path;
         cachedMips = createMipmaps;
+        cachedGeneration = generation();
         memcpy(sizeOut, cachedSize, sizeof(cachedSize));
     }
 
@@ -200,7 +201,15 @@ private:
     {
         if (rc != DS_OK) throw std::runtime_error(ds_last_error(ctx));
     }
+    /* bumped by every volume upload of the context: a volume replaced behind the importer's back invalidates the cache */
+    int generation() const
+    {
+        int g = 0;
+        ds_get_option(ctx, "volume_generation", &g);
+        return g;
+    }
     DsContext* ctx;
+    int cachedGeneration = -1;
     std::string cachedPath;
     bool cachedMips = false;
     int cachedSize[3] = {0, 0, 0};

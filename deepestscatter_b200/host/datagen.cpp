@@ -7,7 +7,7 @@
  *   datagen scenes <db> --clouds a.npy,b.npy,... [--scenes-per-cloud 30] [--seed 566]
  *       DeepestScatter_Train/Utils/GenerateSceneSetups.py: SceneSetup records (size log-uniform 1..12 km, sun uniform on the sphere)
  *   datagen collect <db> --what samples|descriptors|results|all [--cloud-root DIR] [--mode continue|reset]
- *                   [--batch-size 2048] [--shard r/R] [--device D] [--max-threads N] [--launches N]
+ *                   [--batch-size 2048] [--shard r/R] [--device D] [--max-threads N] [--launches N] [--opt name=value,...]
  *       Tasks::collect<T> (Tasks.h:43-71): one task per scene; --shard writes only scenes with id % R == r
  *   datagen merge <out-db> <shard-db>...      copy the records of per-GPU shards into one dataset
  *   datagen stat <db>                         record counts per table
@@ -123,6 +123,11 @@ int cmdCollect(const Args& a)
     if (sscanf(shard.c_str(), "%d/%d", &cs.shard, &cs.shards) != 2 || cs.shards < 1 || cs.shard < 0 || cs.shard >= cs.shards) throw std::runtime_error("bad --shard r/R");
     cs.radiance.max_thread_count = (uint32_t)a.num("max-threads", cs.radiance.max_thread_count);
     cs.radiance.launches_per_update = (uint32_t)a.num("launches", cs.radiance.launches_per_update);
+    for (const std::string& kv : split(a.get("opt", ""), ',')) { /* library tuning options, name=value[,name=value...] */
+        const size_t eq = kv.find('=');
+        if (eq == std::string::npos) throw std::runtime_error("bad --opt " + kv);
+        dsCheck(device->ctx, ds_set_option(device->ctx, kv.substr(0, eq).c_str(), atoi(kv.c_str() + eq + 1)));
+    }
     const Tasks::CollectMode mode = a.get("mode", "continue") == "reset" ? Tasks::CollectMode::Reset : Tasks::CollectMode::Continue;
     const std::string root = a.get("cloud-root", ".");
     const std::string what = a.get("what", "all");

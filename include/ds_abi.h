@@ -225,6 +225,22 @@ int ds_record_result(float light_intensity, int is_converged, uint8_t* out, size
 /* Persistance::SceneSetup (DG/ExecutionLoop/Tasks.cpp:77-85) */
 int ds_record_scene_setup(const char* cloud_path, float cloud_size_m, const float light_direction[3], uint8_t* out, size_t cap);
 
+/* ---------------------------------------------------------------- cloud importer front end (host side) */
+
+/* Resources::loadVolumeBuffer (DG/Util/Resources.cpp:68-155) for what can be read without OpenVDB: `path` is a dense NumPy
+ * array file (<file>.npy, C order, shape (nz, ny, nx), float32 / float64 / uint8) or "synth:<n>[:<kind>[:<seed>]]".  The
+ * grid is cropped to the bounding box of its non-zero ("active") voxels expanded by one voxel (Resources.cpp:97-101),
+ * quantised uint8(v / max * 255) on the device (Resources.cpp:137) and mip-mapped (Resources.cpp:169-209).  The last cloud
+ * of a context is kept (Resources::volumeCache, Resources.cpp:22,73-78): loading the same path again is free.
+ * size_out (may be NULL) receives the grid size in voxels.  Errors: DS_ERR_IO with ds_cloud_last_error(). */
+int ds_cloud_load(DsContext* ctx, const char* path, int build_mips, int size_out[3]);
+/* drop the importer's cache entry of a context (ds_context_destroy does it as well) */
+void ds_cloud_forget(DsContext* ctx);
+const char* ds_cloud_last_error(void);
+/* the crop step alone, on the host: active bounding box + one voxel of zero padding.  dims_out = cropped size; when `out`
+ * is not NULL it receives the cropped grid (out_capacity in floats). */
+int ds_cloud_crop_active(const float* dense, int nx, int ny, int nz, float* out, size_t out_capacity, int dims_out[3], double* max_density_out);
+
 /* ---------------------------------------------------------------- dataset store (LMDB data file, host only) */
 
 /* DeepestScatter::Dataset (DG/Util/Dataset/Dataset.h:87-232, Dataset.cpp:8-18): one LMDB environment opened

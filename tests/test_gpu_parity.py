@@ -315,6 +315,46 @@ def test_point_radiance_collector_bit_exact(gpu_small, oracle_small):
 
 # ---------------------------------------------------------------- tone map, moments
 
+def test_device_resident_collector_agrees_with_the_reference_schedule(built_library):
+    """FAST flavour: the one-launch adaptive collector applies the same convergence rule as RadianceCollector's update
+    loop; the two estimates of every sample agree within their confidence intervals."""
+    ds = built_library
+    with ds.Context(0) as ctx:
+        ctx.volume_synth(SCENE_SMALL["n"], SCENE_SMALL["kind"], SCENE_SMALL["seed"])
+        ctx.scene_set(SCENE_SMALL["cloud_size_m"], SCENE_SMALL["light_dir"])
+        ctx.bake()
+        pos, dirs = ctx.generate_points(0, 96, stream=3)
+        kw = dict(max_threads=96 * 20, launches_per_update=50, max_updates=1500)
+        ctx.set_option("radiance_scheduler", 0)
+        ref, ref_conv, _, ref_updates = ctx.point_radiance(pos, dirs, **kw)
+        ctx.set_option("radiance_scheduler", 1)
+        ctx.counters_reset()
+        ad, ad_conv, _, ad_updates = ctx.point_radiance(pos, dirs, **kw)
+        c = ctx.counters()
+    assert ad_updates == 1 and ref_updates > 1
+    assert c["nonfinite"] == 0 and c["paths"] >= int(ad["experimentCount"].astype(np.int64).sum())
+    assert np.all(ad["experimentCount"] >= 20 * 50)  # never tested before the reference's first test
+    both = ref_conv & ad_conv
+    assert both.mean() > 0.6  # the rest needs more than the 1.5 M experiments this test allows per sample
+    assert np.all(ad["experimentCount"][~ad_conv] >= 1500 * 20 * 50)  # closed by the cap, not dropped
+
+    def ci(t):
+        n = t["experimentCount"].astype(np.float64)
+        return 1.96 * np.sqrt(t["runningVariance"] / n) / np.sqrt(n)
+
+    # converged samples satisfy the rule they were closed by (2 % relative or 1e-4 absolute; zero radiance: > 100000 experiments)
+    a = ad[ad_conv]
+    rel = ci(a) / (a["radiance"] + np.finfo(np.float32).eps)
+    # (paths still in flight when a sample closes are added afterwards and heavy-tailed samples move the variance: some slack)
+    ok = (rel < 0.02 * 1.3) | (ci(a) < 1e-4 * 1.3) | ((a["radiance"] < np.finfo(np.float32).eps) & (a["experimentCount"] > 100000))
+    assert ok.mean() > 0.97, float(ok.mean())
+    # the two schedules estimate the same radiance: differences within the combined 95 % intervals (4 sigma slack)
+    diff = np.abs(ad["radiance"][both].astype(np.float64) - ref["radiance"][both])
+    tol = 2.1 * (ci(ad[both]) + ci(ref[both])) + 1e-6
+    assert (diff <= tol).mean() > 0.97, float((diff <= tol).mean())
+    assert abs(ad["radiance"][both].mean() - ref["radiance"][both].mean()) < 0.01 * ref["radiance"][both].mean() + 1e-5
+
+
 def test_tonemap_matches_reinhard_oracle(gpu_small, oracle_small, built_library):
     cam, cam_np = cam_pair(built_library, W, H)
     gpu_small.frame_create(W, H)
