@@ -353,6 +353,12 @@ static LaunchConfig launchConfig(DsContext* ctx)
     cfg.skipEmpty = ctx->opt["skip_empty"];
     cfg.variant = ctx->opt["variant"];
     cfg.marchUnroll = ctx->opt["march_unroll"];
+    if (cfg.marchUnroll == 0) {
+        /* auto: speculative tap pairs pay while the taps are L2 hits (C2: 268 MB of volumes, 99 % L2 hit rate); once the
+         * volumes dwarf the L2 every wasted tap is a DRAM transaction (C4, 2.1 GB: 449 vs 372 Mpaths/s, profiles/r01z_*) */
+        const size_t volumeBytes = ctx->levels.empty() ? 0 : 2 * (size_t)ctx->lnx[0] * ctx->lny[0] * ctx->lnz[0];
+        cfg.marchUnroll = volumeBytes > 4 * (size_t)ctx->prop.l2CacheSize ? 1 : 2;
+    }
     return cfg;
 }
 
@@ -455,7 +461,7 @@ int ds_context_create(int device, DsContext** out)
     ctx->opt["radiance_scheduler"] = 1;
     ctx->opt["volume_generation"] = 0;
     ctx->opt["radiance_quota"] = 256;
-    ctx->opt["march_unroll"] = 2;
+    ctx->opt["march_unroll"] = 0; /* auto */
     ctx->opt["staging_subframes"] = 16;
     ctx->opt["stream_offset"] = 0;
     ctx->opt["profile_events"] = 0;
@@ -558,7 +564,7 @@ int ds_set_option(DsContext* ctx, const char* name, int value)
     if (n == "block_threads" && (value < 32 || value > 1024 || value % 32)) DS_FAIL(ctx, DS_ERR_INVALID, "block_threads must be 32..1024, multiple of 32");
     if (n == "blocks_per_sm" && (value < 1 || value > 32)) DS_FAIL(ctx, DS_ERR_INVALID, "blocks_per_sm must be 1..32");
     if (n == "precision" && value != DS_PRECISION_EXACT && value != DS_PRECISION_FAST) DS_FAIL(ctx, DS_ERR_INVALID, "precision must be 0 or 1");
-    if (n == "march_unroll" && value != 1 && value != 2) DS_FAIL(ctx, DS_ERR_INVALID, "march_unroll must be 1 or 2");
+    if (n == "march_unroll" && (value < 0 || value > 2)) DS_FAIL(ctx, DS_ERR_INVALID, "march_unroll must be 0 (auto), 1 or 2");
     if (n == "skip_open_dist" && value < 1) DS_FAIL(ctx, DS_ERR_INVALID, "skip_open_dist must be >= 1 (0 would leap out of occupied cells)");
     if (n == "staging_subframes" && value < 1) DS_FAIL(ctx, DS_ERR_INVALID, "staging_subframes must be >= 1");
     if (n == "march_max_iters" && value < 1) DS_FAIL(ctx, DS_ERR_INVALID, "march_max_iters must be >= 1");
