@@ -12,7 +12,9 @@ from .context import (
     MODE_SINGLE_SCATTER,
     PRECISION_EXACT,
     PRECISION_FAST,
+    INFO_DTYPE,
     TASK_DTYPE,
+    blit_predicted,
     Context,
     DsError,
     camera_array,
@@ -27,5 +29,5 @@ from .context import (
 __all__ = [
     "LIB_PATH", "build_library", "load", "Context", "DsError", "camera_look_at", "camera_array",
     "MODE_ALL_SCATTER", "MODE_MULTIPLE_SCATTER", "MODE_SINGLE_SCATTER", "PRECISION_EXACT", "PRECISION_FAST", "TASK_DTYPE",
-    "record_scatter_sample", "record_disney_descriptor", "record_result", "record_scene_setup", "Dataset", "lmdb_compat", "cloud_crop_active",
+    "record_scatter_sample", "record_disney_descriptor", "record_result", "record_scene_setup", "Dataset", "lmdb_compat", "cloud_crop_active", "INFO_DTYPE", "blit_predicted",
 ]

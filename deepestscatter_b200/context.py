@@ -31,6 +31,22 @@ TASK_DTYPE = np.dtype(
 )
 
 
+INFO_DTYPE = np.dtype([("radiance", "<f4", 3), ("transmittance", "<f4"), ("hasScattered", "<u4")])  # IntersectionInfo, rayData.cuh:28-33
+
+
+def blit_predicted(frame_result: np.ndarray, rect, predicted: np.ndarray, info: np.ndarray):
+    """copyToFrameResult (disneyCamera.cu:38-46) into a float4 [H][W] image, in place."""
+    lib = _lib.load()
+    hgt, wid = frame_result.shape[:2]
+    x, y, w, h = rect
+    pr = np.ascontiguousarray(predicted, dtype=np.float32).reshape(h, w)
+    inf = np.ascontiguousarray(info, dtype=INFO_DTYPE).reshape(h, w)
+    assert frame_result.dtype == np.float32 and frame_result.flags.c_contiguous and frame_result.shape[2] == 4
+    rc = lib.ds_blit_predicted(wid, hgt, x, y, w, h, _ptr(pr), _ptr(inf), _ptr(frame_result))
+    if rc != 0:
+        raise DsError(rc, "ds_blit_predicted: bad rectangle")
+
+
 class DsError(RuntimeError):
     def __init__(self, code: int, message: str):
         super().__init__(f"[{code}] {message}")
@@ -284,6 +300,14 @@ class Context:
         idx = np.empty((n, 10, 225, 4), dtype=np.int32) if want_index else None
         self._ck(self.lib.ds_collect_descriptors_float(self.h, _ptr(p), _ptr(d), n, _ptr(out), _ptr(idx) if want_index else None))
         return (out, idx) if want_index else out
+
+    def network_input(self, cam: DsCamera, frame_w: int, frame_h: int, rect, stream: int = 0):
+        """DisneyRenderer::renderRect launch 0: returns (network input [h][w][10][226] float32, info [h][w] INFO_DTYPE)."""
+        x, y, w, h = rect
+        inp = np.empty((h, w, 10, 226), dtype=np.float32)
+        info = np.empty((h, w), dtype=INFO_DTYPE)
+        self._ck(self.lib.ds_render_network_input(self.h, C.byref(cam), frame_w, frame_h, x, y, w, h, stream, _ptr(inp), _ptr(info)))
+        return inp, info
 
     def point_radiance(self, pos, dirs, max_threads: int = 20480, launches_per_update: int = 100, max_updates: int = 0):
         p, d = _f32(pos).reshape(-1, 3), _f32(dirs).reshape(-1, 3)

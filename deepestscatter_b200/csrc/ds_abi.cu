@@ -1128,6 +1128,28 @@ int ds_generate_points(DsContext* ctx, uint32_t first_index, uint32_t n, uint32_
     return DS_OK;
 }
 
+static void fillDescriptorTables(DsContext* ctx, LevelTable& lv, DescriptorLayers& layers)
+{
+    memset(&lv, 0, sizeof(lv));
+    lv.count = (int)ctx->levels.size();
+    for (int l = 0; l < lv.count; l++) {
+        lv.data[l] = ctx->levels[l];
+        lv.nx[l] = ctx->lnx[l];
+        lv.ny[l] = ctx->lny[l];
+        lv.nz[l] = ctx->lnz[l];
+    }
+    /* DisneyDescriptor.cuh:81-88,109-110: per-layer scale, mip level and mip voxel size */
+    float scale = 0.5f / ctx->derived[6];
+    float mipmapLevel = -ds_log2f(ctx->derived[8]) - 1;
+    for (int l = 0; l < 10; l++) {
+        layers.scale[l] = scale;
+        layers.lod[l] = fmaxf(0.0f, mipmapLevel);
+        layers.mipVoxelSize[l] = ds_exp2f(mipmapLevel) * ctx->derived[7] / ctx->params.cloud_size_m;
+        scale *= 2;
+        mipmapLevel++;
+    }
+}
+
 static int collectDescriptors(DsContext* ctx, const float* positions, const float* directions, uint32_t n, uint8_t* outU8, float* outF32,
                               int32_t* tapIndex)
 {
@@ -1145,25 +1167,8 @@ static int collectDescriptors(DsContext* ctx, const float* positions, const floa
     DevScene sc;
     fillDevScene(ctx, sc);
     LevelTable lv;
-    memset(&lv, 0, sizeof(lv));
-    lv.count = (int)ctx->levels.size();
-    for (int l = 0; l < lv.count; l++) {
-        lv.data[l] = ctx->levels[l];
-        lv.nx[l] = ctx->lnx[l];
-        lv.ny[l] = ctx->lny[l];
-        lv.nz[l] = ctx->lnz[l];
-    }
-    /* DisneyDescriptor.cuh:81-88,109-110: per-layer scale, mip level and mip voxel size */
     DescriptorLayers layers;
-    float scale = 0.5f / ctx->derived[6];
-    float mipmapLevel = -ds_log2f(ctx->derived[8]) - 1;
-    for (int l = 0; l < 10; l++) {
-        layers.scale[l] = scale;
-        layers.lod[l] = fmaxf(0.0f, mipmapLevel);
-        layers.mipVoxelSize[l] = ds_exp2f(mipmapLevel) * ctx->derived[7] / ctx->params.cloud_size_m;
-        scale *= 2;
-        mipmapLevel++;
-    }
+    fillDescriptorTables(ctx, lv, layers);
     DS_CUDA(ctx, launchDescriptors(sc, lv, layers, (const float*)ctx->scratch[0], (const float*)ctx->scratch[1], n,
                                    outU8 ? (uint8_t*)ctx->scratch[2] : nullptr, outF32 ? (float*)ctx->scratch[3] : nullptr,
                                    tapIndex ? (int32_t*)ctx->scratch[4] : nullptr, ctx->stream));
@@ -1186,6 +1191,73 @@ int ds_collect_descriptors_float(DsContext* ctx, const float* positions, const f
     DS_CHECK_CTX(ctx);
     if (!out && n) DS_FAIL(ctx, DS_ERR_INVALID, "NULL argument");
     return collectDescriptors(ctx, positions, directions, n, nullptr, out, tap_index_out);
+}
+
+int ds_render_network_input(DsContext* ctx, const DsCamera* cam, uint32_t frame_width, uint32_t frame_height, uint32_t rect_x, uint32_t rect_y,
+                            uint32_t rect_w, uint32_t rect_h, uint32_t stream, float* network_input_out, DsIntersectionInfo* info_out)
+{
+    DS_CHECK_CTX(ctx);
+    int rc = requireScene(ctx, true);
+    if (rc) return rc;
+    if (!cam || !network_input_out || !info_out) DS_FAIL(ctx, DS_ERR_INVALID, "NULL argument");
+    if (frame_width == 0 || frame_height == 0 || rect_w == 0 || rect_h == 0 || (unsigned long long)rect_w * rect_h > (1u << 24))
+        DS_FAIL(ctx, DS_ERR_INVALID, "bad frame / rectangle size");
+    const size_t n = (size_t)rect_w * rect_h;
+    if ((rc = ensureScratch(ctx, 0, n * 3 * sizeof(float))) || (rc = ensureScratch(ctx, 1, n * 3 * sizeof(float))) ||
+        (rc = ensureScratch(ctx, 2, n * (sizeof(float) + 1))) || (rc = ensureScratch(ctx, 3, n * 2260 * sizeof(float))) ||
+        (rc = ensureScratch(ctx, 4, n * 5 * sizeof(float))))
+        return rc;
+    float* dPos = (float*)ctx->scratch[0];
+    float* dDir = (float*)ctx->scratch[1];
+    float* dAngle = (float*)ctx->scratch[2];
+    uint8_t* dActive = (uint8_t*)(dAngle + n);
+    float* dInput = (float*)ctx->scratch[3];
+    float* dInfo = (float*)ctx->scratch[4];
+    TraceJob job;
+    memset(&job, 0, sizeof(job));
+    memcpy(job.eye, cam->eye, 12);
+    memcpy(job.U, cam->U, 12);
+    memcpy(job.V, cam->V, 12);
+    memcpy(job.W, cam->W, 12);
+    job.width = (int)frame_width;
+    job.height = (int)frame_height;
+    DevScene sc;
+    fillDevScene(ctx, sc);
+    if (ctx->opt["precision"] == DS_PRECISION_FAST)
+        DS_CUDA(ctx, KernelSet<true>::networkInfo(sc, job, (int)rect_x, (int)rect_y, (int)rect_w, (int)rect_h, stream, dInfo, dPos, dDir, dAngle, dActive,
+                                                  ctx->stats, ctx->stream));
+    else
+        DS_CUDA(ctx, KernelSet<false>::networkInfo(sc, job, (int)rect_x, (int)rect_y, (int)rect_w, (int)rect_h, stream, dInfo, dPos, dDir, dAngle, dActive,
+                                                   ctx->stats, ctx->stream));
+    LevelTable lv;
+    DescriptorLayers layers;
+    fillDescriptorTables(ctx, lv, layers);
+    DS_CUDA(ctx, launchDescriptors(sc, lv, layers, dPos, dDir, (uint32_t)n, nullptr, dInput, nullptr, ctx->stream, 226, dAngle, dActive));
+    ctx->launches += 2;
+    DS_CUDA(ctx, cudaMemcpyAsync(network_input_out, dInput, n * 2260 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    DS_CUDA(ctx, cudaMemcpyAsync(info_out, dInfo, n * 5 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    DS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return DS_OK;
+}
+
+int ds_blit_predicted(uint32_t frame_width, uint32_t frame_height, uint32_t rect_x, uint32_t rect_y, uint32_t rect_w, uint32_t rect_h,
+                      const float* predicted, const DsIntersectionInfo* info, float* frame_result_inout)
+{
+    if (!predicted || !info || !frame_result_inout) return DS_ERR_INVALID;
+    if ((unsigned long long)rect_x + rect_w > frame_width || (unsigned long long)rect_y + rect_h > frame_height) return DS_ERR_INVALID;
+    for (uint32_t y = 0; y < rect_h; y++)
+        for (uint32_t x = 0; x < rect_w; x++) {
+            const size_t i = (size_t)y * rect_w + x;
+            if (!info[i].has_scattered) continue;
+            float* px = frame_result_inout + 4 * ((size_t)(y + rect_y) * frame_width + (x + rect_x));
+            const float w = 1 - info[i].transmittance;
+            /* (make_float4(predicted) + make_float4(radiance)) * (1 - transmittance): make_float4(float3) sets w = 0 */
+            px[0] = (predicted[i] + info[i].radiance[0]) * w;
+            px[1] = (predicted[i] + info[i].radiance[1]) * w;
+            px[2] = (predicted[i] + info[i].radiance[2]) * w;
+            px[3] = (predicted[i] + 0.0f) * w;
+        }
+    return DS_OK;
 }
 
 void ds_radiance_settings_default(DsRadianceSettings* s)

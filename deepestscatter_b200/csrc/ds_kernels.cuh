@@ -367,4 +367,104 @@ cudaError_t KernelSet<FAST>::generatePoints(const DevScene& sc, uint32_t firstIn
     return cudaGetLastError();
 }
 
+/* ---- CU/disneyCamera.cu:20-36 (pinholeCamera) + CU/disneyDescriptorMaterial.cu:14-46 (sampleDisneyDescriptor) ----
+ * one thread per pixel of the rectangle: transmittance of the whole ray, a collision forced inside the cloud, the direct
+ * sun radiance there; the float descriptor of the scattered pixels is gathered by k_descriptors afterwards */
+template <bool FAST>
+__global__ void __launch_bounds__(128) k_network_info(const DevScene sc, const TraceJob cam, int rectX, int rectY, int rectW, int rectH, uint32_t stream,
+                                                      float* __restrict__ info, float* __restrict__ pos, float* __restrict__ dir,
+                                                      float* __restrict__ angleOut, uint8_t* __restrict__ active, unsigned long long* stats)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (uint32_t)(rectW * rectH)) return;
+    const uint32_t lx = i % (uint32_t)rectW, ly = i / (uint32_t)rectW;
+    const uint32_t px = lx + (uint32_t)rectX, py = ly + (uint32_t)rectY;
+    const float dx = (float)px / (float)cam.width * 2.f - 1.f;
+    const float dy = (float)py / (float)cam.height * 2.f - 1.f;
+    const V3 U = mk(cam.U[0], cam.U[1], cam.U[2]), V = mk(cam.V[0], cam.V[1], cam.V[2]), W = mk(cam.W[0], cam.W[1], cam.W[2]);
+    const V3 o = mk(cam.eye[0], cam.eye[1], cam.eye[2]);
+    const V3 rayDirection = normalize<FAST>(dx * U + dy * V + W);
+    angleOut[i] = acosf(dot(sc.light, rayDirection)); /* disneyCamera.cu:31 */
+    float r = 0.f, g = 0.f, b = 0.f, transmittance = 1.0f;
+    bool has = false;
+    V3 world = mk(0.f, 0.f, 0.f), d = rayDirection;
+    unsigned long long steps = 0, events = 0;
+    const float tHit = intersectBox(sc, o, rayDirection);
+    if (tHit >= 0.0f) {
+        V3 hit = o + tHit * rayDirection;
+        hit = hit + 0.5f * sc.bbox;
+        d = normalize<FAST>(rayDirection);
+        uint32_t seed = tea4(lx * 4096u + ly, stream);
+        /* getNextScatteringEvent(seed, pos, direction, false).transmittance (cloud.cuh:77-122): the march does not stop */
+        {
+            const float xi = rnd(seed);
+            (void)xi; /* the scatter position of this pass is not used */
+            V3 p = hit;
+            float T = 1.0f;
+            while (isInBox(sc, p)) {
+                p = p + d * sc.step;
+                steps++;
+                const float density = sampleCloud<FAST>(sc, p) * sc.mult;
+                T *= expNeg<FAST>(-(density * sc.step));
+            }
+            transmittance = T;
+        }
+        /* getNextScatteringEvent(1 - rnd(seed) * (1 - transmittance), pos, direction) */
+        const float xi = 1 - rnd(seed) * (1 - transmittance);
+        V3 p = hit;
+        float T = 1.0f;
+        bool scattered = false;
+        while (isInBox(sc, p)) {
+            p = p + d * sc.step;
+            steps++;
+            const float density = sampleCloud<FAST>(sc, p) * sc.mult;
+            T *= expNeg<FAST>(-(density * sc.step));
+            if (xi > T) {
+                const float lg = logPos<FAST>(xi / T);
+                const float inv = 1.0f / density;
+                p = p - (d * lg) * inv;
+                scattered = true;
+                break;
+            }
+        }
+        if (scattered && isInBox(sc, p)) {
+            has = true;
+            const float cosLightAngle = dot(-sc.light, d);
+            const float phase = tex1dSoft(sc.mie, (cosLightAngle + 1) / 2); /* full Mie phase: getInScattering(scatter, direction, false) */
+            const float tsun = sampleInScatter<FAST>(sc, p);
+            const V3 li = sc.lightColor * sc.lightIntensity * tsun * phase * SUN_TO_SPHERE;
+            r = li.x;
+            g = li.y;
+            b = li.z;
+            events++;
+            world = p - 0.5f * sc.bbox;
+        }
+    }
+    info[5 * (size_t)i] = r;
+    info[5 * (size_t)i + 1] = g;
+    info[5 * (size_t)i + 2] = b;
+    info[5 * (size_t)i + 3] = transmittance;
+    info[5 * (size_t)i + 4] = __uint_as_float(has ? 1u : 0u); /* IntersectionInfo::hasScattered: a bool in a 4-byte slot (rayData.cuh:28-33) */
+    active[i] = has ? 1 : 0;
+    pos[3 * (size_t)i] = world.x;
+    pos[3 * (size_t)i + 1] = world.y;
+    pos[3 * (size_t)i + 2] = world.z;
+    dir[3 * (size_t)i] = d.x;
+    dir[3 * (size_t)i + 1] = d.y;
+    dir[3 * (size_t)i + 2] = d.z;
+    atomicAdd(stats + CNT_PATHS, 1ull);
+    if (steps) atomicAdd(stats + CNT_STEPS, steps);
+    if (events) atomicAdd(stats + CNT_EVENTS, events);
+}
+
+template <bool FAST>
+cudaError_t KernelSet<FAST>::networkInfo(const DevScene& sc, const TraceJob& cam, int rectX, int rectY, int rectW, int rectH, uint32_t stream, float* info,
+                                         float* pos, float* dir, float* angle, uint8_t* active, unsigned long long* stats, cudaStream_t st)
+{
+    const int n = rectW * rectH;
+    if (n <= 0) return cudaSuccess;
+    k_network_info<FAST><<<(n + 127) / 128, 128, 0, st>>>(sc, cam, rectX, rectY, rectW, rectH, stream, info, pos, dir, angle, active, stats);
+    return cudaGetLastError();
+}
+
 } // namespace dsk

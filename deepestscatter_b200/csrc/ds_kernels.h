@@ -108,6 +108,11 @@ struct KernelSet {
     static cudaError_t primaryPrepass(const DevScene& sc, const TraceJob& cam, uint32_t* entrySteps, uint32_t* hitList,
                                       unsigned long long* counts, cudaStream_t st);
     static cudaError_t bake(const DevScene& sc, uint8_t* out, int skipEmpty, cudaStream_t st);
+    /* first half of the neural renderers' frame (disneyCamera.cu pinholeCamera + disneyDescriptorMaterial.cu): per pixel of the
+     * rectangle info = {radiance rgb, transmittance, hasScattered}, the collision point (centred) and view direction, the
+     * light / view angle and the hasScattered byte */
+    static cudaError_t networkInfo(const DevScene& sc, const TraceJob& cam, int rectX, int rectY, int rectW, int rectH, uint32_t stream, float* info,
+                                   float* pos, float* dir, float* angle, uint8_t* active, unsigned long long* stats, cudaStream_t st);
     static cudaError_t generatePoints(const DevScene& sc, uint32_t firstIndex, uint32_t n, uint32_t stream, float* pos, float* dir,
                                       unsigned long long* stats, cudaStream_t st);
 };
@@ -129,8 +134,11 @@ cudaError_t launchUnconverged(const float4* progressive, const float4* variance,
                               cudaStream_t st);
 cudaError_t launchExportMoments(const float4* progressive, const float4* variance, size_t pixels, uint32_t n, double* out, cudaStream_t st);
 cudaError_t launchImportMoments(const double* in, size_t pixels, uint32_t nTotal, float4* progressive, float4* variance, cudaStream_t st);
+/* layerStride 225: DisneyDescriptor layout [n][10][225]; 226: DisneyNetworkInput layout [n][10][226] whose last element per layer is
+ * angle[i] (may be NULL) -- samples with active[i] == 0 (active may be NULL) get all-zero densities */
 cudaError_t launchDescriptors(const DevScene& sc, const LevelTable& lv, const DescriptorLayers& layers, const float* pos, const float* dir,
-                              uint32_t n, uint8_t* outU8, float* outF32, int32_t* tapIndex, cudaStream_t st);
+                              uint32_t n, uint8_t* outU8, float* outF32, int32_t* tapIndex, cudaStream_t st, int layerStride = 225,
+                              const float* angle = nullptr, const uint8_t* active = nullptr);
 cudaError_t launchTaskWelford(DsPointRadianceTask* tasks, const float* x, uint32_t nThreads, uint32_t launches, cudaStream_t st);
 
 } // namespace dsk

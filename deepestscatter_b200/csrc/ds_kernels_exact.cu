@@ -380,11 +380,19 @@ __device__ __forceinline__ float distanceToBox(const DevScene& sc, V3 pos, float
  * reference's sampleId (z outermost, x innermost, DisneyDescriptor.cuh:89-93); 10 layers per thread */
 __global__ void __launch_bounds__(256) k_descriptors(const DevScene sc, const LevelTable lv, const DescriptorLayers layers,
                                                      const float* __restrict__ positions, const float* __restrict__ directions, uint32_t n,
-                                                     uint8_t* __restrict__ outU8, float* __restrict__ outF32, int32_t* __restrict__ tapIndex)
+                                                     uint8_t* __restrict__ outU8, float* __restrict__ outF32, int32_t* __restrict__ tapIndex,
+                                                     int layerStride, const float* __restrict__ angle, const uint8_t* __restrict__ active)
 {
     const uint32_t i = blockIdx.x;
     const int t = threadIdx.x;
     if (i >= n || t >= 225) return;
+    const size_t sampleStride = (size_t)layerStride * 10;
+    if (angle && outF32 && t < 10) outF32[(size_t)i * sampleStride + (size_t)t * layerStride + 225] = angle[i]; /* disneyCamera.cu:32-35 */
+    if (active && !active[i]) {
+        if (outF32)
+            for (int layer = 0; layer < 10; layer++) outF32[(size_t)i * sampleStride + (size_t)layer * layerStride + t] = 0.0f;
+        return;
+    }
     const V3 worldPos = mk(positions[3 * i], positions[3 * i + 1], positions[3 * i + 2]);
     const V3 viewDirection = mk(directions[3 * i], directions[3 * i + 1], directions[3 * i + 2]);
     const V3 eZ = normalize<false>(-sc.light);
@@ -405,7 +413,7 @@ __global__ void __launch_bounds__(256) k_descriptors(const DevScene sc, const Le
         density = density + tt * (0.0f - density); /* lerp(density, 0, t) */
         const size_t o = (size_t)i * 2250 + (size_t)layer * 225 + t;
         if (outU8) outU8[o] = (uint8_t)(density * 255.0f); /* TFromFloat<uint8_t>, DisneyDescriptor.cuh:66-69 */
-        if (outF32) outF32[o] = density;
+        if (outF32) outF32[(size_t)i * sampleStride + (size_t)layer * layerStride + t] = density;
         if (tapIndex) {
             const int nx = lv.nx[l0], ny = lv.ny[l0], nz = lv.nz[l0];
             tapIndex[4 * o + 0] = (int)fminf(fmaxf(floorf(uvw.x * (float)nx - 0.5f), -2.0f), (float)nx + 1.0f);
@@ -417,10 +425,11 @@ __global__ void __launch_bounds__(256) k_descriptors(const DevScene sc, const Le
 }
 
 cudaError_t launchDescriptors(const DevScene& sc, const LevelTable& lv, const DescriptorLayers& layers, const float* pos, const float* dir,
-                              uint32_t n, uint8_t* outU8, float* outF32, int32_t* tapIndex, cudaStream_t st)
+                              uint32_t n, uint8_t* outU8, float* outF32, int32_t* tapIndex, cudaStream_t st, int layerStride, const float* angle,
+                              const uint8_t* active)
 {
     if (n == 0) return cudaSuccess;
-    k_descriptors<<<n, 256, 0, st>>>(sc, lv, layers, pos, dir, n, outU8, outF32, tapIndex);
+    k_descriptors<<<n, 256, 0, st>>>(sc, lv, layers, pos, dir, n, outU8, outF32, tapIndex, layerStride, angle, active);
     return cudaGetLastError();
 }
 

@@ -205,6 +205,26 @@ int ds_collect_descriptors(DsContext* ctx, const float* positions, const float* 
  * addresses {x, y, z, level} per tap for index parity */
 int ds_collect_descriptors_float(DsContext* ctx, const float* positions, const float* directions, uint32_t n, float* out,
                                  int32_t* tap_index_out);
+/* IntersectionInfo (CU/rayData.cuh:28-33): float3 radiance, float transmittance, bool hasScattered (4-byte slot), 20 bytes */
+typedef struct DsIntersectionInfo {
+    float radiance[3];
+    float transmittance;
+    uint32_t has_scattered;
+} DsIntersectionInfo;
+/* First launch of the neural renderers' renderRect (DG/Scene/Cameras/DisneyRenderer.cpp:84-88): CU/disneyCamera.cu:20-36
+ * (pinholeCamera for pixel launchID + rectOrigin) with CU/disneyDescriptorMaterial.cu:14-46 (sampleDisneyDescriptor) as
+ * closest hit.  Per pixel of the rectangle: the transmittance of the whole ray, a collision forced inside the cloud
+ * (xi = 1 - rnd * (1 - T)), the direct sun radiance there with the full Mie phase, and DisneyNetworkInput = 10 layers of
+ * 225 float densities + the light / view angle (CU/DisneyDescriptor.h) -- the tensor the reference hands to its TorchScript
+ * model (DisneyRenderer.cpp:30-36).  network_input_out: [rect_h][rect_w][10][226] floats (densities zero where nothing
+ * scattered); info_out: [rect_h][rect_w].  The RNG seed is tea<4>(launchID.x * 4096 + launchID.y, stream) with the
+ * rectangle-local launch index, as in the reference (clock() -> stream).  The model itself is the caller's. */
+int ds_render_network_input(DsContext* ctx, const DsCamera* cam, uint32_t frame_width, uint32_t frame_height, uint32_t rect_x, uint32_t rect_y,
+                            uint32_t rect_w, uint32_t rect_h, uint32_t stream, float* network_input_out, DsIntersectionInfo* info_out);
+/* copyToFrameResult (CU/disneyCamera.cu:38-46), host side: frameResult[pixel] = (predicted + radiance) * (1 - transmittance) for
+ * the pixels that scattered; frame_result_inout is float4 [frame_height][frame_width] */
+int ds_blit_predicted(uint32_t frame_width, uint32_t frame_height, uint32_t rect_x, uint32_t rect_y, uint32_t rect_w, uint32_t rect_h,
+                      const float* predicted, const DsIntersectionInfo* info, float* frame_result_inout);
 void ds_radiance_settings_default(DsRadianceSettings* s);
 /* RadianceCollector::init/update loop until all samples converge (RadianceCollector.cpp:19-54,73-141,176-192;
  * CU/pointEmissionCamera.cu:20-33; CU/PointRadianceTask.h).  tasks_out[i] is the merged representative of

@@ -1031,6 +1031,59 @@ void orc_descriptors(void* h, const float* positions, const float* directions, i
     }
 }
 
+/*
+ * First half of the neural renderers' frame (DG/Scene/Cameras/DisneyRenderer.cpp:84-88, launch 0): for every pixel of a
+ * rectangle of the frame, CU/disneyCamera.cu:20-36 (pinholeCamera: ray through pixel launchID + rectOrigin, angle between
+ * light and view direction) and CU/disneyDescriptorMaterial.cu:14-46 (sampleDisneyDescriptor: transmittance of the whole
+ * ray, a collision forced inside the cloud with xi = 1 - rnd * (1 - T), direct sun radiance with the full Mie phase, float
+ * descriptor at the collision).  The seed is tea<4>(launchID.x * 4096 + launchID.y, stream) with the RECT-LOCAL launch
+ * index, as in the reference; clock() -> stream.
+ *   input: [rectH][rectW][10][226] floats (DisneyNetworkInput: 225 densities + angle per layer), zero where nothing scattered
+ *   info:  [rectH][rectW][5] floats: radiance r, g, b; transmittance (1 where the ray misses the box); hasScattered (0 / 1)
+ */
+void orc_network_input(void* h, const float* cam, int frameW, int frameH, int rectX, int rectY, int rectW, int rectH, uint32_t stream, float* input,
+                       float* info)
+{
+    Scene& s = *(Scene*)h;
+    std::vector<float> layer(2250);
+    for (int ly = 0; ly < rectH; ly++)
+        for (int lx = 0; lx < rectW; lx++) {
+            const size_t pix = (size_t)ly * rectW + lx;
+            float* in = input + pix * 2260;
+            float* out = info + pix * 5;
+            for (int k = 0; k < 2260; k++) in[k] = 0.0f;
+            out[0] = out[1] = out[2] = 0.0f;
+            out[3] = 1.0f;
+            out[4] = 0.0f;
+            const f3 origin = mk(cam[0], cam[1], cam[2]);
+            const f3 rayDirection = cameraDirection(cam, (uint32_t)(lx + rectX), (uint32_t)(ly + rectY), (uint32_t)frameW, (uint32_t)frameH);
+            const float angle = acosf(dot(s.lightDirection, rayDirection)); /* disneyCamera.cu:31 */
+            const float tHit = intersectBox(s, origin, rayDirection);
+            if (tHit >= 0.0f) {
+                f3 hitPoint = origin + tHit * rayDirection;
+                hitPoint = hitPoint + 0.5f * s.bboxSize;
+                const f3 direction = normalize(rayDirection);
+                uint32_t seed = tea4((uint32_t)lx * 4096u + (uint32_t)ly, stream);
+                const float transmittance = getNextScatteringEvent(s, rnd(seed), hitPoint, direction, false).transmittance;
+                const ScatteringEvent scatter = getNextScatteringEvent(s, 1 - rnd(seed) * (1 - transmittance), hitPoint, direction);
+                out[3] = transmittance;
+                if (scatter.hasScattered && isInBox(s, scatter.scatterPos)) {
+                    const f3 radiance = getInScattering(s, scatter, direction, false);
+                    out[0] = radiance.x;
+                    out[1] = radiance.y;
+                    out[2] = radiance.z;
+                    out[4] = 1.0f;
+                    const f3 world = scatter.scatterPos - 0.5f * s.bboxSize;
+                    const float p[3] = {world.x, world.y, world.z}, d[3] = {direction.x, direction.y, direction.z};
+                    orc_descriptors(h, p, d, 1, 1, layer.data(), nullptr);
+                    for (int l = 0; l < 10; l++)
+                        for (int t = 0; t < 225; t++) in[l * 226 + t] = layer[l * 225 + t];
+                }
+            }
+            for (int l = 0; l < 10; l++) in[l * 226 + 225] = angle; /* disneyCamera.cu:32-35: written for every pixel */
+        }
+}
+
 /* CU/PointRadianceTask.h:70-77 layout, 40 bytes */
 struct OrcTask {
     int32_t id;

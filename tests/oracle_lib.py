@@ -61,6 +61,7 @@ def lib() -> C.CDLL:
         L.orc_volume_level_count.argtypes = [C.c_void_p]
         L.orc_volume_level_dims.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int)]
         L.orc_volume_level_get.argtypes = [C.c_void_p, C.c_int, _u8p]
+        L.orc_network_input.argtypes = [C.c_void_p, _f32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint32, _f32p, _f32p]
         L.orc_scene_set.argtypes = [C.c_void_p, C.c_float, C.c_float, C.c_float, _f32p, _f32p, C.c_float]
         L.orc_scene_get_derived.argtypes = [C.c_void_p, _f32p]
         L.orc_bake_inscatter.argtypes = [C.c_void_p]
@@ -229,6 +230,14 @@ class Oracle:
         self.L.orc_descriptors(self.h, p.reshape(-1), d.reshape(-1), n, int(as_float), out.ctypes.data_as(C.c_void_p),
                                idx.ctypes.data_as(C.c_void_p) if want_index else None)
         return (out, idx) if want_index else out
+
+    def network_input(self, cam, frame_w, frame_h, rect, stream=0):
+        """orc_network_input: (input [h][w][10][226] float32, info [h][w][5] float32: r, g, b, transmittance, hasScattered)."""
+        x, y, w, h = rect
+        inp = np.empty((h, w, 10, 226), dtype=np.float32)
+        info = np.empty((h, w, 5), dtype=np.float32)
+        self.L.orc_network_input(self.h, f32(cam).reshape(-1), frame_w, frame_h, x, y, w, h, stream, inp.reshape(-1), info.reshape(-1))
+        return inp, info
 
     def point_radiance(self, pos, dirs, max_threads=20480, launches_per_update=100, max_updates=1000):
         p, d = f32(pos).reshape(-1, 3), f32(dirs).reshape(-1, 3)

@@ -356,6 +356,59 @@ def test_device_resident_collector_agrees_with_the_reference_schedule(built_libr
     assert abs(ad["radiance"][both].mean() - ref["radiance"][both].mean()) < 0.01 * ref["radiance"][both].mean() + 1e-5
 
 
+def test_network_input_pass_matches_oracle(gpu_small, oracle_small, built_library):
+    """DisneyRenderer's first launch (disneyCamera.cu pinholeCamera + disneyDescriptorMaterial.cu): EXACT flavour bit-exact on the
+    direct radiance / transmittance / hasScattered, descriptor densities and the angle within 1e-6."""
+    ds = built_library
+    w, h = 64, 36
+    cam, cam_arr = cam_pair(ds, w, h)
+    rect = (8, 6, 40, 24)
+    ref_in, ref_info = oracle_small.network_input(cam_arr, w, h, rect, stream=5)
+    got_in, got_info = gpu_small.network_input(cam, w, h, rect, stream=5)
+    has = ref_info[..., 4] > 0
+    assert 0.2 < has.mean() < 1.0  # the rectangle straddles the silhouette
+    assert np.array_equal(got_info["hasScattered"] != 0, has)
+    assert np.array_equal(got_info["radiance"].view(np.uint32), ref_info[..., :3].copy().view(np.uint32))
+    assert np.array_equal(got_info["transmittance"].view(np.uint32), ref_info[..., 3].copy().view(np.uint32))
+    assert np.all(got_info["transmittance"][~has] > 0)
+    # descriptor: densities as the float descriptor test (<= 1e-6), zero where nothing scattered; angle (device acosf vs libm) 1e-6
+    assert np.all(got_in[~has][:, :, :225] == 0) and np.all(ref_in[~has][:, :, :225] == 0)
+    assert np.abs(got_in[..., :225] - ref_in[..., :225]).max() <= 1e-6
+    assert np.abs(got_in[..., 225] - ref_in[..., 225]).max() <= 1e-6 and got_in[..., 225].min() > 0
+    assert (got_in[has][:, 0, :225].max(axis=1) > 0).all()  # a collision point sits in the cloud: layer 0 sees density
+    # the same seeds in every rectangle (rect-local launch index, as in the reference): a shifted rectangle differs
+    other_in, other_info = gpu_small.network_input(cam, w, h, (9, 6, 40, 24), stream=5)
+    assert not np.array_equal(other_info["radiance"][:, :-1], got_info["radiance"][:, 1:])
+    # copyToFrameResult
+    frame = np.zeros((h, w, 4), np.float32)
+    predicted = np.full((rect[3], rect[2]), 0.25, np.float32)
+    ds.blit_predicted(frame, rect, predicted, got_info)
+    sub = frame[rect[1]:rect[1] + rect[3], rect[0]:rect[0] + rect[2]]
+    want = (0.25 + ref_info[..., :3]) * (1 - ref_info[..., 3:4])
+    assert np.array_equal(sub[..., :3][has], want[has].astype(np.float32)) and np.all(sub[~has] == 0)
+    assert frame.sum() == sub.sum()
+
+
+def test_network_input_pass_fast_flavour(built_library, oracle_small):
+    """FAST flavour of the same pass: same silhouette, transmittance within texture-filter precision."""
+    ds = built_library
+    w, h = 64, 36
+    cam, cam_arr = cam_pair(ds, w, h)
+    rect = (0, 0, w, h)
+    ref_in, ref_info = oracle_small.network_input(cam_arr, w, h, rect, stream=2)
+    with ds.Context(0) as ctx:
+        ctx.volume_synth(SCENE_SMALL["n"], SCENE_SMALL["kind"], SCENE_SMALL["seed"])
+        ctx.scene_set(SCENE_SMALL["cloud_size_m"], SCENE_SMALL["light_dir"])
+        ctx.bake()
+        got_in, got_info = ctx.network_input(cam, w, h, rect, stream=2)
+    has = ref_info[..., 4] > 0
+    assert ((got_info["hasScattered"] != 0) != has).mean() < 0.01
+    assert np.abs(got_info["transmittance"] - ref_info[..., 3]).max() < 0.02
+    both = has & (got_info["hasScattered"] != 0)
+    assert abs(got_info["radiance"][both].mean() - ref_info[..., :3][both].mean()) < 0.03 * ref_info[..., :3][both].mean()
+    assert np.abs(got_in[..., 225] - ref_in[..., 225]).max() <= 1e-5
+
+
 def test_tonemap_matches_reinhard_oracle(gpu_small, oracle_small, built_library):
     cam, cam_np = cam_pair(built_library, W, H)
     gpu_small.frame_create(W, H)
