@@ -45,3 +45,28 @@ def reduce_moments(moments, dst: int = 0):
 
     dist.reduce(moments, dst=dst, op=dist.ReduceOp.SUM)
     return moments
+
+
+class SceneQueue:
+    """Dynamic assignment of dataset scenes to ranks (dataset generation shards by scene, no data-path collective).
+
+    Scene costs differ by an order of magnitude (a 1 km cloud needs far more experiments per sample than a 12 km one), so a
+    static round-robin leaves ranks idle at the end.  Every rank draws the next scene id from ONE shared counter kept in the
+    process group's key-value store (`store.add`, an atomic fetch-and-add served by rank 0's TCPStore -- control plane only;
+    works the same under gloo and NCCL).  `scenes` may be a list of ids (e.g. the ones a resumed run still has to do).
+    """
+
+    def __init__(self, store, scenes, key: str = "ds_next_scene"):
+        self.store, self.scenes, self.key = store, list(scenes), key
+
+    def __iter__(self):
+        while True:
+            ticket = self.store.add(self.key, 1) - 1  # add returns the value after the increment
+            if ticket >= len(self.scenes):
+                return
+            yield self.scenes[ticket]
+
+
+def static_scenes(rank: int, world: int, scenes):
+    """Round-robin split (what `datagen collect --shard r/R` does)."""
+    return [s for i, s in enumerate(scenes) if i % world == rank]

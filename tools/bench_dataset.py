@@ -53,6 +53,7 @@ def main():
     ap.add_argument("--out", default="/tmp/ds_c3")
     ap.add_argument("--opt", action="append", default=[])
     ap.add_argument("--keep", action="store_true")
+    ap.add_argument("--static", action="store_true", help="round-robin scene split instead of the shared scene counter")
     a = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -67,7 +68,12 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     total = a.scenes_per_gpu * world if a.scenes_per_gpu else a.scenes
     setups = scene_setups(total)
-    mine = [i for i in range(total) if i % world == rank]
+    from deepestscatter_b200.multigpu import SceneQueue, static_scenes
+
+    if dist is not None and not a.static:
+        mine = SceneQueue(dist.distributed_c10d._get_default_store(), range(total))  # dynamic: next scene from a shared counter
+    else:
+        mine = static_scenes(rank, world, range(total))
 
     out_dir = Path(a.out)
     out_dir.mkdir(parents=True, exist_ok=True)
@@ -133,7 +139,8 @@ def main():
             "metric": "samples/s", "value": stats["samples"] / elapsed, "unit": "samples/s", "n_gpus": world,
             "config": {"workload": f"C3: dataset generation, {total} scenes x {a.batch} samples, {a.grid}^3 synthetic cumulus, sizes 1-12 km log-uniform, "
                                    f"sun uniform on the sphere (seed 566); radiance to the reference CI rule (2 % relative / 1e-4 absolute)",
-                       "max_thread_count": a.max_threads, "launches_per_update": a.launches},
+                       "max_thread_count": a.max_threads, "launches_per_update": a.launches,
+                       "scene_assignment": "static round-robin" if (a.static or world == 1) else "dynamic (shared counter in the process group's store)"},
             "seconds": elapsed, "scenes": total, **stats, "mpaths_per_s": c["paths"] / elapsed / 1e6, "events_per_s": c["events"] / elapsed,
             "steps_per_s": c["steps"] / elapsed, "seconds_per_stage_per_rank": t,
             "shard0": {"pages": rep["pages_total"], "leaked": rep["pages_leaked"], "tables": {k: v["entries"] for k, v in rep["tables"].items()}},
