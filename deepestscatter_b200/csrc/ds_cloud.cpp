@@ -11,6 +11,7 @@
 
 #include "../../include/ds_abi.h"
 #include "../host/CloudImporter.hpp"
+#include "../host/ExrWriter.hpp"
 
 namespace {
 std::mutex g_mutex;
@@ -71,6 +72,18 @@ int ds_cloud_crop_active(const float* dense, int nx, int ny, int nz, float* out,
     } catch (const std::exception& e) {
         g_error = e.what();
         return DS_ERR_INVALID;
+    }
+}
+
+int ds_write_exr(const char* path, uint32_t width, uint32_t height, const float* rgba)
+{
+    if (!path || !rgba) return DS_ERR_INVALID;
+    try {
+        DeepestScatter::writeExrRGB(path, width, height, rgba, true);
+        return DS_OK;
+    } catch (const std::exception& e) {
+        g_error = e.what();
+        return DS_ERR_IO;
     }
 }
 

@@ -22,6 +22,7 @@
 #include "../../include/ds_abi.h"
 #include "CloudImporter.hpp"
 #include "Dataset.hpp"
+#include "ExrWriter.hpp"
 
 namespace DeepestScatter {
 
@@ -154,7 +155,7 @@ class Camera : public SceneItem {
 public:
     struct Settings {
         uint32_t width, height;
-        std::string outputFile;     /* linear image (the reference writes an EXR; here a PFM, bottom row first like the buffer) */
+        std::string outputFile;     /* linear image: scanline EXR, R G B float, DECREASING_Y (Camera.cpp:149-175) */
         uint32_t maxSubframes = 0;  /* 0: until converged (Camera.cpp:232-268) */
         uint32_t subframesPerUpdate = 10; /* Camera.cpp:186 */
     };
@@ -193,16 +194,11 @@ public:
     {
         if (settings.outputFile.empty()) return;
         const size_t pixels = (size_t)settings.width * settings.height;
-        std::vector<float> rgba(pixels * 4), rgb(pixels * 3);
+        std::vector<float> rgba(pixels * 4);
         dsCheck(device->ctx, ds_frame_download(device->ctx, rgba.data(), nullptr));
-        for (size_t i = 0; i < pixels; i++)
-            for (int c = 0; c < 3; c++) rgb[3 * i + c] = rgba[4 * i + c];
         std::cout << rgba[4 * (pixels / 2 + settings.width / 2)] << std::endl; /* Camera.cpp:161 */
-        FILE* f = fopen(settings.outputFile.c_str(), "wb");
-        if (!f) throw std::runtime_error("cannot write " + settings.outputFile);
-        fprintf(f, "PF\n%u %u\n-1.0\n", settings.width, settings.height); /* little endian, rows bottom to top */
-        fwrite(rgb.data(), sizeof(float), rgb.size(), f);
-        fclose(f);
+        writeExrRGB(settings.outputFile, settings.width, settings.height, rgba.data(), /*decreasingY=*/true); /* Camera.cpp:154-174 */
+        FILE* f;
         /* the display image (reinhard.cu) next to it */
         std::vector<uint8_t> screen(pixels * 4);
         dsCheck(device->ctx, ds_tonemap(device->ctx, exposure, screen.data(), nullptr));
@@ -467,7 +463,7 @@ public:
                 if (c == ':') c = '_';
             const size_t dot = base.find_last_of('.');
             if (dot != std::string::npos) base = base.substr(0, dot);
-            Camera::Settings cs{rs.width, rs.height, rs.outputDir + "/" + base + "." + toString(light) + ".PathTracing.pfm", rs.maxSubframes};
+            Camera::Settings cs{rs.width, rs.height, rs.outputDir + "/" + base + "." + toString(light) + ".PathTracing.exr", rs.maxSubframes};
             auto renderer = std::make_shared<PathTracingRenderer>(device, rs.mode);
             std::vector<std::shared_ptr<SceneItem>> items{std::make_shared<VDBCloud>(device, scene), std::make_shared<Camera>(device, renderer, cs)};
             return std::make_shared<Scene>(items);

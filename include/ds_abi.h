@@ -261,6 +261,12 @@ const char* ds_cloud_last_error(void);
  * is not NULL it receives the cropped grid (out_capacity in floats). */
 int ds_cloud_crop_active(const float* dense, int nx, int ny, int nz, float* out, size_t out_capacity, int dims_out[3], double* max_density_out);
 
+/* Camera::saveToDisk (DG/Scene/Cameras/Camera.cpp:149-175), host only: the float4 [height][width] progressive buffer as a
+ * single-part scanline OpenEXR file with FLOAT channels R, G, B, lineOrder DECREASING_Y, scanline y = buffer row y
+ * (uncompressed; written without the OpenEXR library, deepestscatter_b200/host/ExrWriter.hpp).  Errors: DS_ERR_IO with
+ * ds_cloud_last_error(). */
+int ds_write_exr(const char* path, uint32_t width, uint32_t height, const float* rgba);
+
 /* ---------------------------------------------------------------- dataset store (LMDB data file, host only) */
 
 /* DeepestScatter::Dataset (DG/Util/Dataset/Dataset.h:87-232, Dataset.cpp:8-18): one LMDB environment opened

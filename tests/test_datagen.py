@@ -111,11 +111,12 @@ def test_render_task_writes_the_progressive_image(built_library, tmp_path):
     ds = built_library
     run("render", "synth:48", "--width", 64, "--height", 32, "--spp", 20, "--out", tmp_path, "--size", 7000)
     files = sorted(p.name for p in tmp_path.iterdir())
-    assert files == ["synth_48.Back.PathTracing.pfm", "synth_48.Back.PathTracing.pfm.ppm", "synth_48.Side.PathTracing.pfm", "synth_48.Side.PathTracing.pfm.ppm"]
-    raw = (tmp_path / "synth_48.Side.PathTracing.pfm").read_bytes()
-    header = b"PF\n64 32\n-1.0\n"
-    assert raw.startswith(header)
-    img = np.frombuffer(raw, np.float32, offset=len(header)).reshape(32, 64, 3)
+    assert files == ["synth_48.Back.PathTracing.exr", "synth_48.Back.PathTracing.exr.ppm", "synth_48.Side.PathTracing.exr", "synth_48.Side.PathTracing.exr.ppm"]
+    from exr_reader import read_exr
+
+    e = read_exr(tmp_path / "synth_48.Side.PathTracing.exr")
+    assert (e["width"], e["height"], e["line_order"]) == (64, 32, 1)
+    img = np.stack([e["image"][c] for c in "RGB"], axis=-1)
     with ds.Context(0) as ctx:
         ctx.volume_synth(48, 0, 1234)
         ctx.scene_set(7000.0, (-0.03, -0.25, 0.8))
