@@ -352,6 +352,7 @@ static LaunchConfig launchConfig(DsContext* ctx)
     cfg.smCount = ctx->prop.multiProcessorCount;
     cfg.skipEmpty = ctx->opt["skip_empty"];
     cfg.variant = ctx->opt["variant"];
+    cfg.smemCarveout = ctx->opt["smem_carveout"];
     cfg.marchUnroll = ctx->opt["march_unroll"];
     if (cfg.marchUnroll == 0) {
         /* auto: speculative tap pairs pay while the taps are L2 hits (C2: 268 MB of volumes, 99 % L2 hit rate); once the
@@ -459,6 +460,7 @@ int ds_context_create(int device, DsContext** out)
     ctx->opt["skip_open_dist"] = 1;
     ctx->opt["zero_check_min"] = 2;
     ctx->opt["radiance_scheduler"] = 1;
+    ctx->opt["smem_carveout"] = -1;
     ctx->opt["volume_generation"] = 0;
     ctx->opt["radiance_quota"] = 256;
     ctx->opt["march_unroll"] = 0; /* auto */

@@ -97,6 +97,7 @@ struct LaunchConfig {
     int smCount;
     int skipEmpty;
     int variant; /* FAST flavour: 0 = optimised k_trace_fast, 1 = generic k_trace<true, SKIP> (round-1 baseline) */
+    int smemCarveout; /* k_trace_fast: cudaFuncAttributePreferredSharedMemoryCarveout in percent, -1 = leave the driver default */
     int marchUnroll; /* k_trace_fast: march steps per vote (1, or 2 = the taps of two steps in flight together) */
 };
 

@@ -751,10 +751,14 @@ __global__ void __launch_bounds__(FAST_MAX_THREADS, 1)
 }
 
 template <bool SKIP, bool BOXTEST, int UNROLL, int MODE, bool ADAPT = false>
-static cudaError_t launchFast(const DevScene& sc, const TraceJob& job, int blocks, int threads, size_t smem, cudaStream_t st)
+static cudaError_t launchFast(const DevScene& sc, const TraceJob& job, int blocks, int threads, size_t smem, cudaStream_t st, int carveout = -1)
 {
     cudaError_t e = cudaFuncSetAttribute(k_trace_fast<SKIP, BOXTEST, UNROLL, MODE, ADAPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
+    if (carveout >= 0) {
+        e = cudaFuncSetAttribute(k_trace_fast<SKIP, BOXTEST, UNROLL, MODE, ADAPT>, cudaFuncAttributePreferredSharedMemoryCarveout, carveout);
+        if (e != cudaSuccess) return e;
+    }
     k_trace_fast<SKIP, BOXTEST, UNROLL, MODE, ADAPT><<<blocks, threads, smem, st>>>(sc, job, makeConsts(sc));
     return cudaGetLastError();
 }
@@ -784,14 +788,14 @@ cudaError_t KernelSet<true>::trace(const DevScene& sc, const TraceJob& job, cons
     const bool u2 = cfg.marchUnroll >= 2;
     switch (job.mode) {
     case DS_MODE_SUN_AND_SKY_ALL_SCATTER:
-        return u2 ? launchFast<true, false, 2, DS_MODE_SUN_AND_SKY_ALL_SCATTER>(sc, job, blocks, threads, smem, st)
-                  : launchFast<true, false, 1, DS_MODE_SUN_AND_SKY_ALL_SCATTER>(sc, job, blocks, threads, smem, st);
+        return u2 ? launchFast<true, false, 2, DS_MODE_SUN_AND_SKY_ALL_SCATTER>(sc, job, blocks, threads, smem, st, cfg.smemCarveout)
+                  : launchFast<true, false, 1, DS_MODE_SUN_AND_SKY_ALL_SCATTER>(sc, job, blocks, threads, smem, st, cfg.smemCarveout);
     case DS_MODE_SUN_MULTIPLE_SCATTER:
-        return u2 ? launchFast<true, false, 2, DS_MODE_SUN_MULTIPLE_SCATTER>(sc, job, blocks, threads, smem, st)
-                  : launchFast<true, false, 1, DS_MODE_SUN_MULTIPLE_SCATTER>(sc, job, blocks, threads, smem, st);
+        return u2 ? launchFast<true, false, 2, DS_MODE_SUN_MULTIPLE_SCATTER>(sc, job, blocks, threads, smem, st, cfg.smemCarveout)
+                  : launchFast<true, false, 1, DS_MODE_SUN_MULTIPLE_SCATTER>(sc, job, blocks, threads, smem, st, cfg.smemCarveout);
     default:
-        return u2 ? launchFast<true, false, 2, DS_MODE_SUN_SINGLE_SCATTER>(sc, job, blocks, threads, smem, st)
-                  : launchFast<true, false, 1, DS_MODE_SUN_SINGLE_SCATTER>(sc, job, blocks, threads, smem, st);
+        return u2 ? launchFast<true, false, 2, DS_MODE_SUN_SINGLE_SCATTER>(sc, job, blocks, threads, smem, st, cfg.smemCarveout)
+                  : launchFast<true, false, 1, DS_MODE_SUN_SINGLE_SCATTER>(sc, job, blocks, threads, smem, st, cfg.smemCarveout);
     }
 }
 

@@ -217,6 +217,39 @@ def test_fast_flavour_matches_oracle_statistically(built_library, oracle_small):
     assert abs(a.mean() - b.mean()) / b.mean() < 0.005 + 3 * np.sqrt((sigma**2).sum()) / a.size / b.mean()
 
 
+def test_converged_images_agree_within_half_a_percent_rmse(built_library):
+    """north_star's radiance bar at convergence: the FAST flavour (hardware trilinear taps, MUFU transcendentals) against the
+    EXACT flavour (bit-identical to the oracle, see the *_bit_exact tests) at 2 M spp per pixel: every pixel within 3 sigma and
+    image-wide relative RMSE below 0.5 %."""
+    ds = built_library
+    w, h, spp, chunk = 32, 18, 1 << 21, 1 << 13
+    cam, _ = cam_pair(ds, w, h)
+    res = {}
+    with ds.Context(0) as ctx:
+        ctx.set_option("staging_subframes", chunk)
+        ctx.volume_synth(SCENE_SMALL["n"], SCENE_SMALL["kind"], SCENE_SMALL["seed"])
+        ctx.scene_set(SCENE_SMALL["cloud_size_m"], SCENE_SMALL["light_dir"])
+        for flavour in (ds.PRECISION_EXACT, ds.PRECISION_FAST):
+            ctx.set_option("precision", flavour)
+            ctx.bake()
+            ctx.frame_create(w, h)
+            for first in range(1, spp + 1, chunk):
+                ctx.render_subframes(cam, ds.MODE_ALL_SCATTER, first, chunk)
+            p, v = ctx.frame_download()
+            assert ctx.counters()["nonfinite"] == 0
+            res[flavour] = (p[..., 0].astype(np.float64), v[..., 0].astype(np.float64) / (spp - 1))
+    (a, va), (b, vb) = res[ds.PRECISION_FAST], res[ds.PRECISION_EXACT]
+    assert ((a == 0) != (b == 0)).mean() < 0.01  # silhouette: a grazing pixel may see density in one filter and not the other
+    lit = (a > 0) & (b > 0)
+    sigma = np.sqrt((va + vb) / spp)
+    z = np.abs(a - b)[lit] / sigma[lit]
+    rmse = np.sqrt(np.mean((a - b) ** 2)) / b.mean()
+    print(f"converged FAST vs EXACT: relative RMSE {rmse:.5f}, max z {z.max():.2f}, mean ratio {a.mean() / b.mean():.6f}")
+    assert rmse < 0.005, rmse
+    assert (z < 3).mean() > 0.98 and z.max() < 5, (float((z < 3).mean()), float(z.max()))
+    assert abs(a.mean() / b.mean() - 1) < 0.002
+
+
 def test_fast_flavour_is_deterministic_under_scheduling_knobs(built_library):
     """k_trace_fast: a path's arithmetic never depends on which lane runs it or on the warp's phase votes."""
     ds = built_library
