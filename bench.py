@@ -43,7 +43,7 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--spp", type=int, default=32, help="progressive subframes per step (per GPU)")
+    ap.add_argument("--spp", type=int, default=64, help="progressive subframes per step (per GPU)")
     ap.add_argument("--grid", type=int, default=GRID_N)
     ap.add_argument("--width", type=int, default=WIDTH)
     ap.add_argument("--height", type=int, default=HEIGHT)
