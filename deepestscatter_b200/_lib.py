@@ -113,6 +113,11 @@ SIGNATURES = {
     "ds_collect_descriptors_float": (_i, [_vp, _vp, _vp, _u32, _vp, _vp]),
     "ds_render_network_input": (_i, [_vp, C.POINTER(DsCamera), _u32, _u32, _u32, _u32, _u32, _u32, _u32, _vp, _vp]),
     "ds_blit_predicted": (_i, [_u32, _u32, _u32, _u32, _u32, _u32, _vp, _vp, _vp]),
+    "ds_disney_model_weight_count": (_sz, []),
+    "ds_disney_model_load": (_i, [_vp, _vp, _sz]),
+    "ds_disney_model_pack": (_i, [_vp, _sz, _vp, _sz, _vp, _sz, C.POINTER(_sz), C.POINTER(_sz)]),
+    "ds_disney_model_forward": (_i, [_vp, _vp, _u32, _vp]),
+    "ds_render_disney": (_i, [_vp, C.POINTER(DsCamera), _u32, _u32, _u32, _vp]),
     "ds_radiance_settings_default": (None, [C.POINTER(DsRadianceSettings)]),
     "ds_point_radiance_run": (_i, [_vp, _vp, _vp, _u32, C.POINTER(DsRadianceSettings), _vp, _vp, C.POINTER(_u32)]),
     "ds_record_scatter_sample": (_i, [_pf, _pf, _vp, _sz]),

@@ -309,6 +309,24 @@ class Context:
         self._ck(self.lib.ds_render_network_input(self.h, C.byref(cam), frame_w, frame_h, x, y, w, h, stream, _ptr(inp), _ptr(info)))
         return inp, info
 
+    def disney_model_load(self, weights):
+        """Load DisneyModel.state_dict() as one flat float32 array (deepestscatter_b200.disney_model.flatten_state_dict)."""
+        w = _f32(weights).reshape(-1)
+        self._ck(self.lib.ds_disney_model_load(self.h, _ptr(w), w.size))
+
+    def disney_model_forward(self, network_input) -> np.ndarray:
+        """module->forward (DisneyRenderer.cpp:104): [n][10][226] -> [n] predicted radiance."""
+        x = _f32(network_input).reshape(-1, 10, 226)
+        out = np.empty(len(x), dtype=np.float32)
+        self._ck(self.lib.ds_disney_model_forward(self.h, _ptr(x), len(x), _ptr(out)))
+        return out
+
+    def render_disney(self, cam: DsCamera, frame_w: int, frame_h: int, stream: int = 0) -> np.ndarray:
+        """DisneyRenderer::render: the neural renderer's frameResultBuffer, float4 [h][w]."""
+        out = np.empty((frame_h, frame_w, 4), dtype=np.float32)
+        self._ck(self.lib.ds_render_disney(self.h, C.byref(cam), frame_w, frame_h, stream, _ptr(out)))
+        return out
+
     def point_radiance(self, pos, dirs, max_threads: int = 20480, launches_per_update: int = 100, max_updates: int = 0):
         p, d = _f32(pos).reshape(-1, 3), _f32(dirs).reshape(-1, 3)
         n = len(p)

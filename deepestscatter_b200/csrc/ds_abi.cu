@@ -13,6 +13,7 @@
 #include <vector>
 
 #include "ds_kernels.h"
+#include "ds_mlp.h"
 
 extern "C" {
 extern const unsigned char ds_mie_blob[];     /* deepestscatter_b200/data/mie_tables.f32 (ds_mie_blob.S) */
@@ -78,6 +79,11 @@ struct DsContext {
     /* scratch */
     void* scratch[8] = {nullptr};
     size_t scratchSize[8] = {0};
+
+    /* radiance-predicting network of the neural renderer (ds_disney_model_load) */
+    DisneyModelDev model;
+    void* mlpScratch[4] = {nullptr}; /* network-input upload, predictions, compacted row indices + count, frame result */
+    size_t mlpScratchSize[4] = {0};
 };
 
 static thread_local std::string g_createError;
@@ -109,6 +115,29 @@ static int ensureScratch(DsContext* ctx, int slot, size_t bytes)
     DS_CUDA(ctx, cudaMalloc(&ctx->scratch[slot], bytes));
     ctx->scratchSize[slot] = bytes;
     return DS_OK;
+}
+
+static int ensureMlpScratch(DsContext* ctx, int slot, size_t bytes)
+{
+    if (ctx->mlpScratchSize[slot] >= bytes) return DS_OK;
+    if (ctx->mlpScratch[slot]) cudaFree(ctx->mlpScratch[slot]);
+    ctx->mlpScratch[slot] = nullptr;
+    ctx->mlpScratchSize[slot] = 0;
+    DS_CUDA(ctx, cudaMalloc(&ctx->mlpScratch[slot], bytes));
+    ctx->mlpScratchSize[slot] = bytes;
+    return DS_OK;
+}
+
+static void freeDisneyModel(DsContext* ctx)
+{
+    DisneyModelDev& m = ctx->model;
+    cudaFree(m.wT);
+    cudaFree(m.bias);
+    cudaFree(m.w4b4);
+    cudaFree(m.stream);
+    cudaFree(m.chunks);
+    cudaFree(m.error);
+    m = DisneyModelDev();
 }
 
 static void freeVolume(DsContext* ctx)
@@ -468,6 +497,7 @@ int ds_context_create(int device, DsContext** out)
     ctx->opt["stream_offset"] = 0;
     ctx->opt["profile_events"] = 0;
     ctx->opt["primary_cache"] = 1;
+    ctx->opt["mlp_last_us"] = 0; /* read-only: device time of the last model launch when profile_events is on */
     ds_scene_params_default(&ctx->params);
     bool ok = cudaMalloc(&ctx->stats, CNT_COUNT * sizeof(unsigned long long)) == cudaSuccess &&
               cudaMalloc(&ctx->queue, sizeof(unsigned long long)) == cudaSuccess &&
@@ -533,6 +563,8 @@ int ds_context_destroy(DsContext* ctx)
     cudaFree(ctx->mie);
     cudaFree(ctx->guide);
     for (int i = 0; i < 8; i++) cudaFree(ctx->scratch[i]);
+    for (int i = 0; i < 4; i++) cudaFree(ctx->mlpScratch[i]);
+    freeDisneyModel(ctx);
     for (cudaEvent_t e : ctx->traceEvents) cudaEventDestroy(e);
     if (ctx->ownStream && ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -1195,15 +1227,12 @@ int ds_collect_descriptors_float(DsContext* ctx, const float* positions, const f
     return collectDescriptors(ctx, positions, directions, n, nullptr, out, tap_index_out);
 }
 
-int ds_render_network_input(DsContext* ctx, const DsCamera* cam, uint32_t frame_width, uint32_t frame_height, uint32_t rect_x, uint32_t rect_y,
-                            uint32_t rect_w, uint32_t rect_h, uint32_t stream, float* network_input_out, DsIntersectionInfo* info_out)
+/* device side of the first launch of renderRect: fills scratch[3] (network input [n][10][226]), scratch[4] (DsIntersectionInfo [n]) and
+ * scratch[2] (angle [n] + hasScattered bytes [n]) for the rectangle */
+static int networkInputDevice(DsContext* ctx, const DsCamera* cam, uint32_t frame_width, uint32_t frame_height, uint32_t rect_x, uint32_t rect_y,
+                              uint32_t rect_w, uint32_t rect_h, uint32_t stream)
 {
-    DS_CHECK_CTX(ctx);
-    int rc = requireScene(ctx, true);
-    if (rc) return rc;
-    if (!cam || !network_input_out || !info_out) DS_FAIL(ctx, DS_ERR_INVALID, "NULL argument");
-    if (frame_width == 0 || frame_height == 0 || rect_w == 0 || rect_h == 0 || (unsigned long long)rect_w * rect_h > (1u << 24))
-        DS_FAIL(ctx, DS_ERR_INVALID, "bad frame / rectangle size");
+    int rc;
     const size_t n = (size_t)rect_w * rect_h;
     if ((rc = ensureScratch(ctx, 0, n * 3 * sizeof(float))) || (rc = ensureScratch(ctx, 1, n * 3 * sizeof(float))) ||
         (rc = ensureScratch(ctx, 2, n * (sizeof(float) + 1))) || (rc = ensureScratch(ctx, 3, n * 2260 * sizeof(float))) ||
@@ -1236,10 +1265,174 @@ int ds_render_network_input(DsContext* ctx, const DsCamera* cam, uint32_t frame_
     fillDescriptorTables(ctx, lv, layers);
     DS_CUDA(ctx, launchDescriptors(sc, lv, layers, dPos, dDir, (uint32_t)n, nullptr, dInput, nullptr, ctx->stream, 226, dAngle, dActive));
     ctx->launches += 2;
-    DS_CUDA(ctx, cudaMemcpyAsync(network_input_out, dInput, n * 2260 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
-    DS_CUDA(ctx, cudaMemcpyAsync(info_out, dInfo, n * 5 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    return DS_OK;
+}
+
+int ds_render_network_input(DsContext* ctx, const DsCamera* cam, uint32_t frame_width, uint32_t frame_height, uint32_t rect_x, uint32_t rect_y,
+                            uint32_t rect_w, uint32_t rect_h, uint32_t stream, float* network_input_out, DsIntersectionInfo* info_out)
+{
+    DS_CHECK_CTX(ctx);
+    int rc = requireScene(ctx, true);
+    if (rc) return rc;
+    if (!cam || !network_input_out || !info_out) DS_FAIL(ctx, DS_ERR_INVALID, "NULL argument");
+    if (frame_width == 0 || frame_height == 0 || rect_w == 0 || rect_h == 0 || (unsigned long long)rect_w * rect_h > (1u << 24))
+        DS_FAIL(ctx, DS_ERR_INVALID, "bad frame / rectangle size");
+    const size_t n = (size_t)rect_w * rect_h;
+    if ((rc = networkInputDevice(ctx, cam, frame_width, frame_height, rect_x, rect_y, rect_w, rect_h, stream))) return rc;
+    DS_CUDA(ctx, cudaMemcpyAsync(network_input_out, ctx->scratch[3], n * 2260 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    DS_CUDA(ctx, cudaMemcpyAsync(info_out, ctx->scratch[4], n * 5 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
     DS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return DS_OK;
+}
+
+/* ---- the radiance-predicting network (DeepestScatter_Train/Disney/DisneyModel.py) ---- */
+
+size_t ds_disney_model_weight_count(void) { return MLP_WEIGHT_COUNT; }
+
+int ds_disney_model_pack(const float* weights, size_t count, void* stream_out, size_t stream_capacity, void* chunks_out, size_t chunks_capacity,
+                         size_t* stream_bytes, size_t* chunk_count)
+{
+    if (!weights || count != MLP_WEIGHT_COUNT || !stream_bytes || !chunk_count) return DS_ERR_INVALID;
+    DisneyModelHost h;
+    packDisneyModel(weights, h);
+    *stream_bytes = h.stream.size();
+    *chunk_count = h.chunks.size();
+    if (stream_out) {
+        if (stream_capacity < h.stream.size()) return DS_ERR_INVALID;
+        memcpy(stream_out, h.stream.data(), h.stream.size());
+    }
+    if (chunks_out) {
+        if (chunks_capacity < h.chunks.size() * sizeof(MlpChunk)) return DS_ERR_INVALID;
+        memcpy(chunks_out, h.chunks.data(), h.chunks.size() * sizeof(MlpChunk));
+    }
+    return DS_OK;
+}
+
+int ds_disney_model_load(DsContext* ctx, const float* weights, size_t count)
+{
+    DS_CHECK_CTX(ctx);
+    if (!weights) DS_FAIL(ctx, DS_ERR_INVALID, "NULL weights");
+    if (count != MLP_WEIGHT_COUNT)
+        DS_FAIL(ctx, DS_ERR_INVALID, "DisneyModel state_dict has %zu floats, got %zu", (size_t)MLP_WEIGHT_COUNT, count);
+    for (size_t i = 0; i < count; ++i)
+        if (!std::isfinite(weights[i])) DS_FAIL(ctx, DS_ERR_INVALID, "weight %zu is not finite", i);
+    DisneyModelHost h;
+    packDisneyModel(weights, h);
+    DS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    freeDisneyModel(ctx);
+    DisneyModelDev& m = ctx->model;
+    DS_CUDA(ctx, cudaMalloc(&m.wT, h.wT.size() * sizeof(float)));
+    DS_CUDA(ctx, cudaMalloc(&m.bias, h.bias.size() * sizeof(float)));
+    DS_CUDA(ctx, cudaMalloc(&m.w4b4, h.w4b4.size() * sizeof(float)));
+    DS_CUDA(ctx, cudaMalloc(&m.stream, h.stream.size()));
+    DS_CUDA(ctx, cudaMalloc(&m.chunks, h.chunks.size() * sizeof(MlpChunk)));
+    DS_CUDA(ctx, cudaMalloc(&m.error, sizeof(uint32_t)));
+    DS_CUDA(ctx, cudaMemcpy(m.wT, h.wT.data(), h.wT.size() * sizeof(float), cudaMemcpyHostToDevice));
+    DS_CUDA(ctx, cudaMemcpy(m.bias, h.bias.data(), h.bias.size() * sizeof(float), cudaMemcpyHostToDevice));
+    DS_CUDA(ctx, cudaMemcpy(m.w4b4, h.w4b4.data(), h.w4b4.size() * sizeof(float), cudaMemcpyHostToDevice));
+    DS_CUDA(ctx, cudaMemcpy(m.stream, h.stream.data(), h.stream.size(), cudaMemcpyHostToDevice));
+    DS_CUDA(ctx, cudaMemcpy(m.chunks, h.chunks.data(), h.chunks.size() * sizeof(MlpChunk), cudaMemcpyHostToDevice));
+    DS_CUDA(ctx, cudaMemset(m.error, 0, sizeof(uint32_t)));
+    m.nChunks = (int)h.chunks.size();
+    m.loaded = true;
+    return DS_OK;
+}
+
+/* evaluates the loaded model on device rows; EXACT flavour: fp32 FMA kernel, FAST flavour: tcgen05 tf32 kernel */
+static int disneyForwardDevice(DsContext* ctx, const float* dIn, const uint32_t* dRowIndex, uint32_t nRows, float* dOut)
+{
+    if (!ctx->model.loaded) DS_FAIL(ctx, DS_ERR_STATE, "no model loaded (ds_disney_model_load)");
+    const bool prof = ctx->opt["profile_events"] != 0;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (prof) {
+        DS_CUDA(ctx, cudaEventCreate(&e0));
+        DS_CUDA(ctx, cudaEventCreate(&e1));
+        DS_CUDA(ctx, cudaEventRecord(e0, ctx->stream));
+    }
+    if (ctx->opt["precision"] == DS_PRECISION_FAST)
+        DS_CUDA(ctx, launchDisneyMlpTc(ctx->model, dIn, dRowIndex, nRows, dOut, ctx->stream));
+    else
+        DS_CUDA(ctx, launchDisneyMlpF32(ctx->model, dIn, dRowIndex, nRows, dOut, ctx->stream));
+    ctx->launches += 1;
+    if (prof) {
+        float ms = 0.0f;
+        DS_CUDA(ctx, cudaEventRecord(e1, ctx->stream));
+        DS_CUDA(ctx, cudaEventSynchronize(e1));
+        DS_CUDA(ctx, cudaEventElapsedTime(&ms, e0, e1));
+        ctx->opt["mlp_last_us"] = (int)(ms * 1000.0f + 0.5f);
+        cudaEventDestroy(e0);
+        cudaEventDestroy(e1);
+    }
+    return DS_OK;
+}
+
+static int disneyCheckError(DsContext* ctx)
+{
+    uint32_t err = 0;
+    DS_CUDA(ctx, cudaMemcpyAsync(&err, ctx->model.error, sizeof(err), cudaMemcpyDeviceToHost, ctx->stream));
+    DS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (err) {
+        cudaMemset(ctx->model.error, 0, sizeof(uint32_t));
+        DS_FAIL(ctx, DS_ERR_CUDA, "k_disney_mlp_tc: barrier wait timed out in block %u", err - 1u);
+    }
+    return DS_OK;
+}
+
+int ds_disney_model_forward(DsContext* ctx, const float* network_input, uint32_t n, float* predicted_out)
+{
+    DS_CHECK_CTX(ctx);
+    if (!network_input || !predicted_out) DS_FAIL(ctx, DS_ERR_INVALID, "NULL argument");
+    if (!ctx->model.loaded) DS_FAIL(ctx, DS_ERR_STATE, "no model loaded (ds_disney_model_load)");
+    if (n == 0) return DS_OK;
+    int rc;
+    if ((rc = ensureMlpScratch(ctx, 0, (size_t)n * 2260 * sizeof(float))) || (rc = ensureMlpScratch(ctx, 1, (size_t)n * sizeof(float)))) return rc;
+    DS_CUDA(ctx, cudaMemcpyAsync(ctx->mlpScratch[0], network_input, (size_t)n * 2260 * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    if ((rc = disneyForwardDevice(ctx, (const float*)ctx->mlpScratch[0], nullptr, n, (float*)ctx->mlpScratch[1]))) return rc;
+    DS_CUDA(ctx, cudaMemcpyAsync(predicted_out, ctx->mlpScratch[1], (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    return disneyCheckError(ctx);
+}
+
+/* DisneyRenderer::render (DG/Scene/Cameras/DisneyRenderer.cpp:58-110): for every 128 x 128 rectangle (x outer, y inner) the
+ * network-input launch, the model on the pixels that scattered (the reference skips the rectangle when none did, :91-99),
+ * copyToFrameResult.  Everything stays on the device; one copy of the frame result at the end. */
+int ds_render_disney(DsContext* ctx, const DsCamera* cam, uint32_t frame_width, uint32_t frame_height, uint32_t stream, float* frame_result_out)
+{
+    DS_CHECK_CTX(ctx);
+    int rc = requireScene(ctx, true);
+    if (rc) return rc;
+    if (!cam || !frame_result_out) DS_FAIL(ctx, DS_ERR_INVALID, "NULL argument");
+    if (frame_width == 0 || frame_height == 0 || (unsigned long long)frame_width * frame_height > (1ull << 28))
+        DS_FAIL(ctx, DS_ERR_INVALID, "bad frame size");
+    if (!ctx->model.loaded) DS_FAIL(ctx, DS_ERR_STATE, "no model loaded (ds_disney_model_load)");
+    const uint32_t RECT = 128; /* DisneyRenderer.cpp:10 */
+    const size_t pixels = (size_t)frame_width * frame_height;
+    if ((rc = ensureMlpScratch(ctx, 1, (size_t)RECT * RECT * sizeof(float))) ||
+        (rc = ensureMlpScratch(ctx, 2, ((size_t)RECT * RECT + 1) * sizeof(uint32_t))) || (rc = ensureMlpScratch(ctx, 3, pixels * sizeof(float4))))
+        return rc;
+    float* dPred = (float*)ctx->mlpScratch[1];
+    uint32_t* dIdx = (uint32_t*)ctx->mlpScratch[2];
+    uint32_t* dCount = dIdx + (size_t)RECT * RECT;
+    float4* dFrame = (float4*)ctx->mlpScratch[3];
+    DS_CUDA(ctx, cudaMemsetAsync(dFrame, 0, pixels * sizeof(float4), ctx->stream));
+    uint32_t ordinal = 0;
+    for (uint32_t x = 0; x < frame_width; x += RECT)
+        for (uint32_t y = 0; y < frame_height; y += RECT, ++ordinal) {
+            const uint32_t rw = std::min(RECT, frame_width - x), rh = std::min(RECT, frame_height - y);
+            const uint32_t n = rw * rh;
+            if ((rc = networkInputDevice(ctx, cam, frame_width, frame_height, x, y, rw, rh, stream + ordinal))) return rc;
+            const uint8_t* dActive = (const uint8_t*)((float*)ctx->scratch[2] + n);
+            DS_CUDA(ctx, launchCompactActive(dActive, n, dIdx, dCount, ctx->stream));
+            uint32_t nActive = 0;
+            DS_CUDA(ctx, cudaMemcpyAsync(&nActive, dCount, sizeof(nActive), cudaMemcpyDeviceToHost, ctx->stream));
+            DS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            ctx->launches += 1;
+            if (nActive == 0) continue; /* DisneyRenderer.cpp:96-99 */
+            if ((rc = disneyForwardDevice(ctx, (const float*)ctx->scratch[3], dIdx, nActive, dPred))) return rc;
+            DS_CUDA(ctx, launchBlitPredicted(dPred, (const float*)ctx->scratch[4], frame_width, frame_height, x, y, rw, rh, dFrame, ctx->stream));
+            ctx->launches += 1;
+        }
+    DS_CUDA(ctx, cudaMemcpyAsync(frame_result_out, dFrame, pixels * sizeof(float4), cudaMemcpyDeviceToHost, ctx->stream));
+    return disneyCheckError(ctx);
 }
 
 int ds_blit_predicted(uint32_t frame_width, uint32_t frame_height, uint32_t rect_x, uint32_t rect_y, uint32_t rect_w, uint32_t rect_h,

@@ -1,0 +1,626 @@
+/*
+ * ds_mlp.cu -- the radiance-predicting network of the neural renderer on sm_100a (see ds_mlp.h).
+ *
+ *   k_disney_mlp_tc   FAST flavour: tcgen05.mma kind::tf32, M = 128 rows per CTA, N = 208, fp32 accumulators in
+ *                     tensor memory, weights streamed by 1-D bulk TMA, activations never leave the SM;
+ *   k_disney_mlp_f32  EXACT flavour: plain fp32 FMA in a fixed summation order (register-tiled, shared-memory staged).
+ *
+ * Both are checked against oracle/ds_oracle_mlp.cpp, which is pinned to the reference's own DisneyModel.py through
+ * tests/golden/disney_mlp.json.
+ */
+#include <cstring>
+
+#include "ds_mlp.h"
+
+namespace dsk {
+
+/* ------------------------------------------------------------------------------------------------ host packing */
+
+namespace {
+
+struct BlockPtrs {
+    const float *f1zW, *f1zB, *f1oW, *f1oB, *f2W, *f2B;
+};
+
+/* tf32 = fp32 with 10 mantissa bits; round to nearest, ties away (what cvt.rna.tf32.f32 does) */
+float roundTf32(float x)
+{
+    uint32_t u;
+    memcpy(&u, &x, 4);
+    if ((u & 0x7f800000u) == 0x7f800000u) return x;
+    u = (u + 0x1000u) & 0xffffe000u;
+    memcpy(&x, &u, 4);
+    return x;
+}
+
+constexpr uint32_t B_LBO = MLP_NPAD / 8 * 128; /* bytes between the two 4-float K groups of one MMA step: all 26 row groups */
+
+/* one K chunk of W [200][ld] (torch Linear layout), k in [k0, k0 + 8 * k8), zero beyond kValid and beyond row 200, in the
+ * UMMA canonical K-major no-swizzle layout: 8 x 16-byte core matrices, row groups 128 B apart, K groups B_LBO apart */
+void appendWeightChunk(std::vector<uint8_t>& stream, const float* W, int ld, int k0, int k8, int kValid)
+{
+    const size_t base = stream.size();
+    const int kc = 8 * k8;
+    stream.resize(base + (size_t)(kc / 4) * B_LBO, 0);
+    for (int kk = 0; kk < kc; ++kk)
+        for (int n = 0; n < MLP_D; ++n) {
+            const int k = k0 + kk;
+            const float v = k < kValid ? roundTf32(W[(size_t)n * ld + k]) : 0.0f;
+            const size_t off = base + (size_t)(kk / 4) * B_LBO + (size_t)(n / 8) * 128 + (size_t)(n % 8) * 16 + (size_t)(kk % 4) * 4;
+            memcpy(&stream[off], &v, 4);
+        }
+}
+
+/* the chunks of one GEMM operand of K values (padded to a multiple of 8): 32 at a time, then the rest */
+void appendGemmPart(DisneyModelHost& out, const float* W, int ld, int K, uint8_t src, uint8_t layer, uint8_t dst, uint8_t gemm, bool first,
+                    bool waitAct, bool last, uint8_t epilogue)
+{
+    const int kPad = (K + 7) / 8 * 8;
+    for (int k0 = 0; k0 < kPad; k0 += 32) {
+        const int k8 = (kPad - k0 >= 32 ? 32 : kPad - k0) / 8;
+        MlpChunk c{};
+        c.wOffset = (uint32_t)out.stream.size();
+        appendWeightChunk(out.stream, W, ld, k0, k8, K);
+        c.wBytes = (uint32_t)out.stream.size() - c.wOffset;
+        c.k8 = (uint16_t)k8;
+        c.aKGroup = (uint16_t)(src == 0 ? k0 / 4 : k0);
+        c.src = src;
+        c.layer = layer;
+        c.dst = dst;
+        c.gemm = gemm;
+        c.flags = 0;
+        if (k0 == 0 && first) c.flags |= MLP_FIRST;
+        if (k0 == 0 && waitAct) c.flags |= MLP_WAIT_ACT;
+        if (k0 + 32 >= kPad && last) {
+            c.flags |= MLP_LAST;
+            c.epilogue = epilogue;
+        }
+        out.chunks.push_back(c);
+    }
+}
+
+} // namespace
+
+void packDisneyModel(const float* w, DisneyModelHost& out)
+{
+    BlockPtrs blk[MLP_NB];
+    for (int i = 0; i < MLP_NB; ++i) {
+        blk[i].f1zW = w;
+        blk[i].f1zB = blk[i].f1zW + MLP_D * MLP_ZD;
+        blk[i].f1oW = blk[i].f1zB + MLP_D;
+        blk[i].f1oB = blk[i].f1oW + MLP_D * MLP_D;
+        blk[i].f2W = blk[i].f1oB + MLP_D;
+        blk[i].f2B = blk[i].f2W + MLP_D * MLP_D;
+        w = blk[i].f2B + MLP_D;
+    }
+    const float* fc0W = w;
+    const float* fc0B = fc0W + MLP_D * MLP_D;
+    const float* fc2W = fc0B + MLP_D;
+    const float* fc2B = fc2W + MLP_D * MLP_D;
+    const float* fc4W = fc2B + MLP_D;
+    const float* fc4B = fc4W + MLP_D;
+
+    /* fp32 kernel: W^T per GEMM, [K][200] */
+    out.wT.clear();
+    out.bias.assign((size_t)MLP_GEMMS * MLP_NPAD, 0.0f);
+    auto appendT = [&](const float* W, int K) {
+        const size_t base = out.wT.size();
+        out.wT.resize(base + (size_t)K * MLP_D);
+        for (int k = 0; k < K; ++k)
+            for (int c = 0; c < MLP_D; ++c) out.wT[base + (size_t)k * MLP_D + c] = W[(size_t)c * K + k];
+    };
+    for (int i = 0; i < MLP_NB; ++i) {
+        appendT(blk[i].f1oW, MLP_D);
+        appendT(blk[i].f1zW, MLP_ZD);
+        appendT(blk[i].f2W, MLP_D);
+        for (int c = 0; c < MLP_D; ++c) {
+            out.bias[(size_t)(2 * i) * MLP_NPAD + c] = blk[i].f1oB[c] + blk[i].f1zB[c];
+            out.bias[(size_t)(2 * i + 1) * MLP_NPAD + c] = blk[i].f2B[c];
+        }
+    }
+    appendT(fc0W, MLP_D);
+    appendT(fc2W, MLP_D);
+    for (int c = 0; c < MLP_D; ++c) {
+        out.bias[(size_t)20 * MLP_NPAD + c] = fc0B[c];
+        out.bias[(size_t)21 * MLP_NPAD + c] = fc2B[c];
+    }
+    out.w4b4.assign(fc4W, fc4W + MLP_D);
+    out.w4b4.push_back(fc4B[0]);
+
+    /* tensor-core kernel: the program */
+    out.stream.clear();
+    out.chunks.clear();
+    for (int i = 0; i < MLP_NB; ++i) {
+        /* h = relu(o . f1o^T + z_i . f1z^T + b); o = 0 in block 0 (DisneyModel.py:34): that part is skipped */
+        if (i > 0) appendGemmPart(out, blk[i].f1oW, MLP_D, MLP_D, 0, 0, 0, (uint8_t)(2 * i), true, true, false, 0);
+        appendGemmPart(out, blk[i].f1zW, MLP_ZD, MLP_ZD, 1, (uint8_t)i, 0, (uint8_t)(2 * i), i == 0, false, true, MLP_EPI_H);
+        /* o = relu(h . f2^T + b + o): D2 still holds o, the MMAs accumulate on top of it */
+        appendGemmPart(out, blk[i].f2W, MLP_D, MLP_D, 0, 0, 1, (uint8_t)(2 * i + 1), i == 0, true, true, MLP_EPI_O);
+    }
+    appendGemmPart(out, fc0W, MLP_D, MLP_D, 0, 0, 0, 20, true, true, true, MLP_EPI_H);
+    appendGemmPart(out, fc2W, MLP_D, MLP_D, 0, 0, 0, 21, true, true, true, MLP_EPI_OUT);
+}
+
+/* ------------------------------------------------------------------------------------------------ fp32 kernel */
+
+constexpr int F32_TM = 64;       /* rows per CTA */
+constexpr int F32_KC = 32;       /* K rows of W^T staged at a time */
+constexpr int F32_THREADS = 200; /* 8 row groups x 25 column groups, 8 x 8 outputs per thread */
+constexpr size_t F32_SMEM = (size_t)(2 * MLP_D * F32_TM + MLP_ZD * F32_TM + F32_KC * MLP_D) * sizeof(float);
+
+/* acc[i][j] += sum_k A[k][ty*8 + i] * W^T[k][tx*8 + j]; A = A0 (K0 rows) followed by A1 (K1 rows), both [k][64] in shared memory */
+__device__ __forceinline__ void gemmF32(const float* A0, int K0, const float* A1, int K1, const float* __restrict__ Wg, float* wS, int ty, int tx,
+                                        float (&acc)[8][8])
+{
+    const int K = K0 + K1;
+    for (int k0 = 0; k0 < K; k0 += F32_KC) {
+        const int kc = min(F32_KC, K - k0);
+        __syncthreads(); /* the previous chunk has been consumed */
+        const float4* src = reinterpret_cast<const float4*>(Wg + (size_t)k0 * MLP_D);
+        for (int i = threadIdx.x; i < kc * (MLP_D / 4); i += F32_THREADS) reinterpret_cast<float4*>(wS)[i] = __ldg(src + i);
+        __syncthreads();
+        for (int kk = 0; kk < kc; ++kk) {
+            const int k = k0 + kk;
+            const float* arow = k < K0 ? A0 + k * F32_TM : A1 + (k - K0) * F32_TM;
+            const float4 a0 = *reinterpret_cast<const float4*>(arow + ty * 8), a1 = *reinterpret_cast<const float4*>(arow + ty * 8 + 4);
+            const float4 w0 = *reinterpret_cast<const float4*>(wS + kk * MLP_D + tx * 8), w1 = *reinterpret_cast<const float4*>(wS + kk * MLP_D + tx * 8 + 4);
+            const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+            const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], wv[j], acc[i][j]);
+        }
+    }
+}
+
+/* dst[c][r] = relu(acc + bias[c] (+ res[c][r])) for the thread's 8 x 8 outputs; dst may alias res (same element, same thread) */
+__device__ __forceinline__ void epilogueF32(const float (&acc)[8][8], const float* __restrict__ bias, const float* res, float* dst, int ty, int tx)
+{
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int c = tx * 8 + j;
+        const float b = __ldg(bias + c);
+        float v[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            float x = acc[i][j] + b;
+            if (res) x += res[c * F32_TM + ty * 8 + i];
+            v[i] = fmaxf(x, 0.0f);
+        }
+        *reinterpret_cast<float4*>(dst + c * F32_TM + ty * 8) = make_float4(v[0], v[1], v[2], v[3]);
+        *reinterpret_cast<float4*>(dst + c * F32_TM + ty * 8 + 4) = make_float4(v[4], v[5], v[6], v[7]);
+    }
+}
+
+__global__ void __launch_bounds__(F32_THREADS, 1)
+    k_disney_mlp_f32(const float* __restrict__ in, const uint32_t* __restrict__ rowIndex, uint32_t nRows, const float* __restrict__ wT,
+                     const float* __restrict__ bias, const float* __restrict__ w4b4, float* __restrict__ out)
+{
+    extern __shared__ __align__(16) unsigned char smemRaw[];
+    float* actO = reinterpret_cast<float*>(smemRaw); /* [200][64]: element (k, row) */
+    float* actH = actO + MLP_D * F32_TM;
+    float* actZ = actH + MLP_D * F32_TM; /* [226][64] */
+    float* wS = actZ + MLP_ZD * F32_TM;  /* [32][200] */
+    const int ty = threadIdx.x / 25, tx = threadIdx.x % 25;
+    const uint32_t row0 = blockIdx.x * F32_TM;
+    for (int i = threadIdx.x; i < MLP_D * F32_TM; i += F32_THREADS) actO[i] = 0.0f; /* DisneyModel.py:34 */
+
+    const float* wg = wT;
+    float acc[8][8];
+    for (int blk = 0; blk < MLP_NB; ++blk) {
+        __syncthreads(); /* actZ of the previous block has been consumed */
+        /* descriptor layer blk of the tile's rows, transposed to [k][row] (lane <-> row: conflict-free stores) */
+        for (int i = threadIdx.x; i < MLP_ZD * F32_TM; i += F32_THREADS) {
+            const int k = i / F32_TM, r = i % F32_TM;
+            float v = 0.0f;
+            if (row0 + r < nRows) {
+                const size_t src = rowIndex ? rowIndex[row0 + r] : row0 + r;
+                v = __ldg(in + (src * MLP_NB + blk) * MLP_ZD + k);
+            }
+            actZ[i] = v;
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[i][j] = 0.0f;
+        gemmF32(actO, MLP_D, actZ, MLP_ZD, wg, wS, ty, tx, acc); /* first syncs, so actZ is complete */
+        wg += (size_t)(MLP_D + MLP_ZD) * MLP_D;
+        epilogueF32(acc, bias + (size_t)(2 * blk) * MLP_NPAD, nullptr, actH, ty, tx);
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[i][j] = 0.0f;
+        gemmF32(actH, MLP_D, nullptr, 0, wg, wS, ty, tx, acc);
+        wg += (size_t)MLP_D * MLP_D;
+        epilogueF32(acc, bias + (size_t)(2 * blk + 1) * MLP_NPAD, actO, actO, ty, tx);
+    }
+    /* fullyConnected */
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = 0.0f;
+    gemmF32(actO, MLP_D, nullptr, 0, wg, wS, ty, tx, acc);
+    wg += (size_t)MLP_D * MLP_D;
+    epilogueF32(acc, bias + (size_t)20 * MLP_NPAD, nullptr, actH, ty, tx);
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = 0.0f;
+    gemmF32(actH, MLP_D, nullptr, 0, wg, wS, ty, tx, acc);
+    __syncthreads(); /* every thread is done reading actO's predecessor chain before it is overwritten */
+    epilogueF32(acc, bias + (size_t)21 * MLP_NPAD, nullptr, actO, ty, tx);
+    __syncthreads();
+    if (threadIdx.x < F32_TM && row0 + threadIdx.x < nRows) {
+        float y = __ldg(w4b4 + MLP_D);
+        for (int k = 0; k < MLP_D; ++k) y = fmaf(actO[k * F32_TM + threadIdx.x], __ldg(w4b4 + k), y);
+        const size_t dst = rowIndex ? rowIndex[row0 + threadIdx.x] : row0 + threadIdx.x;
+        out[dst] = y > 0.0f ? y : 0.01f * y; /* torch.nn.LeakyReLU default slope */
+    }
+}
+
+cudaError_t launchDisneyMlpF32(const DisneyModelDev& m, const float* in, const uint32_t* rowIndex, uint32_t nRows, float* out, cudaStream_t st)
+{
+    if (nRows == 0) return cudaSuccess;
+    cudaError_t e = cudaFuncSetAttribute(k_disney_mlp_f32, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)F32_SMEM);
+    if (e != cudaSuccess) return e;
+    k_disney_mlp_f32<<<(nRows + F32_TM - 1) / F32_TM, F32_THREADS, F32_SMEM, st>>>(in, rowIndex, nRows, m.wT, m.bias, m.w4b4, out);
+    return cudaGetLastError();
+}
+
+/* ------------------------------------------------------------------------------------------------ tcgen05 kernel */
+
+constexpr int TC_M = 128;          /* rows per CTA = UMMA M = TMEM lanes */
+constexpr int TC_WORKERS = 128;    /* warps 0-3: thread t owns row t (TMEM lane t) */
+constexpr int TC_THREADS = 160;    /* warp 4: TMEM allocation, weight producer and MMA issuer (one lane) */
+constexpr int TC_WSTAGES = 3, TC_ZSTAGES = 2;
+constexpr uint32_t TC_A_LBO = TC_M / 8 * 128;          /* 2048: bytes between 4-float K groups of the activations (all 16 row groups) */
+constexpr uint32_t TC_SBO = 128;                       /* bytes between 8-row groups */
+constexpr uint32_t TC_ACT_BYTES = MLP_D / 4 * TC_A_LBO; /* 102400 */
+constexpr uint32_t TC_WSTAGE_BYTES = 8 * B_LBO;        /* 26624: K = 32 */
+constexpr uint32_t TC_ZSTAGE_BYTES = 8 * TC_A_LBO;     /* 16384 */
+constexpr int TC_MAX_CHUNKS = 256;
+constexpr uint32_t TC_OFF_W = TC_ACT_BYTES;
+constexpr uint32_t TC_OFF_Z = TC_OFF_W + TC_WSTAGES * TC_WSTAGE_BYTES;
+constexpr uint32_t TC_OFF_CHUNKS = TC_OFF_Z + TC_ZSTAGES * TC_ZSTAGE_BYTES;
+constexpr uint32_t TC_OFF_BAR = TC_OFF_CHUNKS + TC_MAX_CHUNKS * sizeof(MlpChunk);
+constexpr uint32_t TC_SMEM = TC_OFF_BAR + 256;
+static_assert(sizeof(MlpChunk) == 20 || sizeof(MlpChunk) == 24, "MlpChunk layout");
+static_assert(TC_SMEM <= 232448, "shared memory budget");
+constexpr uint32_t TC_TMEM_COLS = 512, TC_D2_COL = 256;
+/* instruction descriptor (cute/arch/mma_sm100_desc.hpp InstrDescriptor): D = F32 (bits 4-5 = 1), A = B = TF32 (bits 7-9, 10-12 = 2),
+ * both K-major (bits 15, 16 = 0), N >> 3 at bits 17-22, M >> 4 at bits 24-28 */
+constexpr uint32_t TC_IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(MLP_NPAD >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
+
+/* barrier slots (8 bytes each) */
+enum { BAR_WFULL = 0, BAR_WFREE = 3, BAR_ZFULL = 6, BAR_ZFREE = 8, BAR_GEMM = 10, BAR_ACT = 11, BAR_COUNT = 12 };
+
+__device__ __forceinline__ uint32_t smemAddr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbarInit(uint32_t bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count)); }
+__device__ __forceinline__ void mbarArrive(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
+__device__ __forceinline__ void mbarExpectTx(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbarTry(uint32_t bar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+/* bounded wait: a protocol error must end the kernel with an error code, never hang the GPU */
+__device__ __forceinline__ bool mbarWait(uint32_t bar, uint32_t parity, volatile uint32_t* abortFlag)
+{
+    if (mbarTry(bar, parity)) return true;
+    const long long t0 = clock64();
+    for (;;) {
+        if (mbarTry(bar, parity)) return true;
+        if (*abortFlag) return false;
+        if (clock64() - t0 > 2000000000ll) { /* ~1 s */
+            *abortFlag = 1u;
+            return false;
+        }
+    }
+}
+
+__device__ __forceinline__ uint64_t ummaDesc(uint32_t saddr, uint32_t lbo)
+{
+    /* cute/arch/mma_sm100_desc.hpp SmemDescriptor: start >> 4 at bits 0-13, leading byte offset >> 4 at 16-29, stride byte offset >> 4
+     * at 32-45, version 1 at 46-47, layout type 0 (no swizzle) at 61-63 */
+    return (uint64_t)((saddr & 0x3ffffu) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(TC_SBO >> 4) << 32) | (1ull << 46);
+}
+
+__device__ __forceinline__ void ummaTf32(uint32_t tmemD, uint64_t descA, uint64_t descB, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmemD), "l"(descA), "l"(descB), "r"(TC_IDESC), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void ummaCommit(uint32_t bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+__device__ __forceinline__ void tmemLoad16(uint32_t taddr, uint32_t (&v)[16])
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]),
+          "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmemStore16(uint32_t taddr, const uint32_t (&v)[16])
+{
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+        "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]),
+        "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+        : "memory");
+}
+
+__device__ __forceinline__ float toTf32(float x)
+{
+    uint32_t u;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+    return __uint_as_float(u);
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+    k_disney_mlp_tc(const float* __restrict__ in, const uint32_t* __restrict__ rowIndex, uint32_t nRows, const uint8_t* __restrict__ stream,
+                    const MlpChunk* __restrict__ chunksG, int nChunks, const float* __restrict__ bias, const float* __restrict__ w4b4,
+                    float* __restrict__ out, uint32_t* __restrict__ errorOut)
+{
+    extern __shared__ __align__(1024) unsigned char smem[];
+    unsigned char* actS = smem;
+    MlpChunk* chunks = reinterpret_cast<MlpChunk*>(smem + TC_OFF_CHUNKS);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + TC_OFF_BAR);
+    uint32_t* tmemSlot = reinterpret_cast<uint32_t*>(bars + BAR_COUNT);
+    volatile uint32_t* abortFlag = tmemSlot + 1;
+    const uint32_t barBase = smemAddr(bars);
+    const uint32_t actAddr = smemAddr(actS);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    for (int i = threadIdx.x; i < nChunks; i += TC_THREADS) chunks[i] = chunksG[i];
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < TC_WSTAGES; ++s) {
+            mbarInit(barBase + 8 * (BAR_WFULL + s), 1);
+            mbarInit(barBase + 8 * (BAR_WFREE + s), 1);
+        }
+        for (int s = 0; s < TC_ZSTAGES; ++s) {
+            mbarInit(barBase + 8 * (BAR_ZFULL + s), TC_WORKERS);
+            mbarInit(barBase + 8 * (BAR_ZFREE + s), 1);
+        }
+        mbarInit(barBase + 8 * BAR_GEMM, 1);
+        mbarInit(barBase + 8 * BAR_ACT, TC_WORKERS);
+        *abortFlag = 0u;
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 4) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smemAddr(tmemSlot)), "r"(TC_TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmemBase = *tmemSlot;
+
+    if (warp == 4) {
+        /* ===== weight producer + MMA issuer: one thread ===== */
+        if (lane == 0) {
+            auto loadWeights = [&](int c) {
+                const MlpChunk& ch = chunks[c];
+                const uint32_t bar = barBase + 8 * (BAR_WFULL + c % TC_WSTAGES);
+                mbarExpectTx(bar, ch.wBytes);
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                                 actAddr + TC_OFF_W + (uint32_t)(c % TC_WSTAGES) * TC_WSTAGE_BYTES),
+                             "l"(stream + ch.wOffset), "r"(ch.wBytes), "r"(bar)
+                             : "memory");
+            };
+            for (int c = 0; c < TC_WSTAGES - 1 && c < nChunks; ++c) loadWeights(c);
+            uint32_t actWaits = 0, zUses = 0;
+            bool ok = true;
+            for (int c = 0; c < nChunks && ok; ++c) {
+                const MlpChunk ch = chunks[c];
+                const int ws = c % TC_WSTAGES;
+                if (ch.flags & MLP_WAIT_ACT) {
+                    ok = mbarWait(barBase + 8 * BAR_ACT, actWaits & 1u, abortFlag);
+                    actWaits++;
+                }
+                const int zs = (int)(zUses % TC_ZSTAGES);
+                if (ok && ch.src == 1) ok = mbarWait(barBase + 8 * (BAR_ZFULL + zs), (zUses / TC_ZSTAGES) & 1u, abortFlag);
+                if (ok) ok = mbarWait(barBase + 8 * (BAR_WFULL + ws), (uint32_t)(c / TC_WSTAGES) & 1u, abortFlag);
+                if (!ok) break;
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t aBase = ch.src == 1 ? actAddr + TC_OFF_Z + (uint32_t)zs * TC_ZSTAGE_BYTES : actAddr + (uint32_t)ch.aKGroup * TC_A_LBO;
+                const uint32_t bBase = actAddr + TC_OFF_W + (uint32_t)ws * TC_WSTAGE_BYTES;
+                const uint32_t d = tmemBase + (ch.dst ? TC_D2_COL : 0u);
+                for (int j = 0; j < ch.k8; ++j)
+                    ummaTf32(d, ummaDesc(aBase + (uint32_t)j * 2u * TC_A_LBO, TC_A_LBO), ummaDesc(bBase + (uint32_t)j * 2u * B_LBO, B_LBO),
+                             ((ch.flags & MLP_FIRST) && j == 0) ? 0u : 1u);
+                ummaCommit(barBase + 8 * (BAR_WFREE + ws));
+                if (ch.src == 1) {
+                    ummaCommit(barBase + 8 * (BAR_ZFREE + zs));
+                    zUses++;
+                }
+                if (ch.flags & MLP_LAST) ummaCommit(barBase + 8 * BAR_GEMM);
+                /* refill the stage chunk c - 1 used with chunk c + 2 */
+                const int p = c + TC_WSTAGES - 1;
+                if (p < nChunks) {
+                    if (p >= TC_WSTAGES) ok = mbarWait(barBase + 8 * (BAR_WFREE + p % TC_WSTAGES), (uint32_t)(p / TC_WSTAGES - 1) & 1u, abortFlag);
+                    if (ok) loadWeights(p);
+                }
+            }
+            if (!ok) *abortFlag = 1u;
+        }
+    } else {
+        /* ===== workers: stage descriptor layers, run the epilogues ===== */
+        const int t = threadIdx.x;
+        const uint32_t row = blockIdx.x * TC_M + t;
+        const bool valid = row < nRows;
+        const size_t srcRow = valid ? (rowIndex ? (size_t)rowIndex[row] : (size_t)row) : 0;
+        const float* inRow = in + srcRow * (MLP_NB * MLP_ZD);
+        const uint32_t rowOff = (uint32_t)(t / 8) * TC_SBO + (uint32_t)(t % 8) * 16u; /* the row's 16 bytes inside a K group */
+        const uint32_t tmemRow = tmemBase + ((uint32_t)(warp * 32) << 16);
+        uint32_t zFills = 0, gemmWaits = 0;
+        bool ok = true;
+        for (int c = 0; c < nChunks && ok; ++c) {
+            const MlpChunk ch = chunks[c];
+            if (ch.src == 1) {
+                const int zs = (int)(zFills % TC_ZSTAGES);
+                bool mine = true;
+                if (zFills >= TC_ZSTAGES) mine = mbarWait(barBase + 8 * (BAR_ZFREE + zs), (zFills / TC_ZSTAGES - 1) & 1u, abortFlag);
+                ok = __all_sync(0xffffffffu, mine);
+                if (!ok) break;
+                unsigned char* zst = smem + TC_OFF_Z + (uint32_t)zs * TC_ZSTAGE_BYTES + rowOff;
+                const float* src = inRow + (int)ch.layer * MLP_ZD + (int)ch.aKGroup;
+                for (int kg = 0; kg < 2 * ch.k8; ++kg) {
+                    const int k = (int)ch.aKGroup + 4 * kg;
+                    float2 lo = make_float2(0.f, 0.f), hi = make_float2(0.f, 0.f);
+                    if (valid && k < MLP_ZD) lo = __ldg(reinterpret_cast<const float2*>(src + 4 * kg));
+                    if (valid && k + 2 < MLP_ZD) hi = __ldg(reinterpret_cast<const float2*>(src + 4 * kg + 2));
+                    *reinterpret_cast<float4*>(zst + (uint32_t)kg * TC_A_LBO) = make_float4(toTf32(lo.x), toTf32(lo.y), toTf32(hi.x), toTf32(hi.y));
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); /* generic-proxy stores -> the tensor core's async-proxy reads */
+                mbarArrive(barBase + 8 * (BAR_ZFULL + zs));
+                zFills++;
+            }
+            if (ch.flags & MLP_LAST) {
+                const bool mine = mbarWait(barBase + 8 * BAR_GEMM, gemmWaits & 1u, abortFlag);
+                gemmWaits++;
+                ok = __all_sync(0xffffffffu, mine);
+                if (!ok) break;
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t tacc = tmemRow + (ch.dst ? TC_D2_COL : 0u);
+                const float* b = bias + (size_t)ch.gemm * MLP_NPAD;
+                float y = 0.0f;
+#pragma unroll 1
+                for (int g = 0; g < MLP_NPAD / 16; ++g) {
+                    uint32_t v[16];
+                    tmemLoad16(tacc + (uint32_t)g * 16u, v);
+                    float x[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) x[j] = fmaxf(__uint_as_float(v[j]) + __ldg(b + g * 16 + j), 0.0f);
+                    if (ch.epilogue == MLP_EPI_OUT) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j)
+                            if (g * 16 + j < MLP_D) y = fmaf(x[j], __ldg(w4b4 + g * 16 + j), y);
+                    } else {
+                        if (ch.epilogue == MLP_EPI_O) {
+                            /* the post-activation value is the residual of the next block: the next MMAs accumulate on top of it */
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) v[j] = __float_as_uint(x[j]);
+                            tmemStore16(tacc + (uint32_t)g * 16u, v);
+                        }
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const int kg = g * 4 + q;
+                            if (kg < MLP_D / 4)
+                                *reinterpret_cast<float4*>(actS + (uint32_t)kg * TC_A_LBO + rowOff) =
+                                    make_float4(toTf32(x[4 * q]), toTf32(x[4 * q + 1]), toTf32(x[4 * q + 2]), toTf32(x[4 * q + 3]));
+                        }
+                    }
+                }
+                if (ch.epilogue == MLP_EPI_OUT) {
+                    y += __ldg(w4b4 + MLP_D);
+                    if (valid) out[srcRow] = y > 0.0f ? y : 0.01f * y; /* torch.nn.LeakyReLU default slope */
+                } else {
+                    if (ch.epilogue == MLP_EPI_O) asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                    mbarArrive(barBase + 8 * BAR_ACT);
+                }
+            }
+        }
+        if (!ok) *abortFlag = 1u;
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (threadIdx.x == 0 && *abortFlag) atomicExch(errorOut, 1u + blockIdx.x);
+    if (warp == 4) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmemBase), "r"(TC_TMEM_COLS) : "memory");
+    }
+}
+
+cudaError_t launchDisneyMlpTc(const DisneyModelDev& m, const float* in, const uint32_t* rowIndex, uint32_t nRows, float* out, cudaStream_t st)
+{
+    if (nRows == 0) return cudaSuccess;
+    if (m.nChunks > TC_MAX_CHUNKS) return cudaErrorInvalidValue;
+    cudaError_t e = cudaFuncSetAttribute(k_disney_mlp_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM);
+    if (e != cudaSuccess) return e;
+    k_disney_mlp_tc<<<(nRows + TC_M - 1) / TC_M, TC_THREADS, TC_SMEM, st>>>(in, rowIndex, nRows, m.stream, m.chunks, m.nChunks, m.bias, m.w4b4, out,
+                                                                          m.error);
+    return cudaGetLastError();
+}
+
+/* ------------------------------------------------------------------------------------------------ renderRect glue */
+
+/* one block: ordered compaction of the rows with active[i] != 0 */
+__global__ void __launch_bounds__(1024) k_compact_active(const uint8_t* __restrict__ active, uint32_t n, uint32_t* __restrict__ idx,
+                                                         uint32_t* __restrict__ count)
+{
+    __shared__ uint32_t warpSum[32];
+    __shared__ uint32_t base;
+    if (threadIdx.x == 0) base = 0;
+    __syncthreads();
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    for (uint32_t i0 = 0; i0 < n; i0 += blockDim.x) {
+        const uint32_t i = i0 + threadIdx.x;
+        const bool a = i < n && active[i] != 0;
+        const unsigned m = __ballot_sync(0xffffffffu, a);
+        if (lane == 0) warpSum[warp] = (uint32_t)__popc(m);
+        __syncthreads();
+        uint32_t before = 0, total = 0;
+        for (unsigned w = 0; w < (blockDim.x >> 5); ++w) {
+            if (w < warp) before += warpSum[w];
+            total += warpSum[w];
+        }
+        if (a) idx[base + before + (uint32_t)__popc(m & ((1u << lane) - 1u))] = i;
+        __syncthreads();
+        if (threadIdx.x == 0) base += total;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *count = base;
+}
+
+cudaError_t launchCompactActive(const uint8_t* active, uint32_t n, uint32_t* idx, uint32_t* count, cudaStream_t st)
+{
+    k_compact_active<<<1, 1024, 0, st>>>(active, n, idx, count);
+    return cudaGetLastError();
+}
+
+/* CU/disneyCamera.cu:38-46: frameResult[pixel] = (make_float4(predicted) + make_float4(radiance)) * (1 - transmittance) */
+__global__ void k_blit_predicted(const float* __restrict__ predicted, const float* __restrict__ info, uint32_t frameW, uint32_t rectX, uint32_t rectY,
+                                 uint32_t rectW, uint32_t n, float4* __restrict__ frameResult)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float* f = info + (size_t)i * 5; /* DsIntersectionInfo: radiance rgb, transmittance, hasScattered */
+    if (__float_as_uint(f[4]) == 0u) return;
+    const uint32_t x = i % rectW, y = i / rectW;
+    const float w = 1.0f - f[3], p = predicted[i];
+    frameResult[(size_t)(y + rectY) * frameW + (x + rectX)] = make_float4((p + f[0]) * w, (p + f[1]) * w, (p + f[2]) * w, (p + 0.0f) * w);
+}
+
+cudaError_t launchBlitPredicted(const float* predicted, const float* info, uint32_t frameW, uint32_t frameH, uint32_t rectX, uint32_t rectY, uint32_t rectW,
+                                uint32_t rectH, float4* frameResult, cudaStream_t st)
+{
+    (void)frameH;
+    const uint32_t n = rectW * rectH;
+    k_blit_predicted<<<(n + 255) / 256, 256, 0, st>>>(predicted, info, frameW, rectX, rectY, rectW, n, frameResult);
+    return cudaGetLastError();
+}
+
+} // namespace dsk

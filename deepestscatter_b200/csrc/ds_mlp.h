@@ -1,0 +1,76 @@
+/*
+ * ds_mlp.h -- the radiance-predicting network of the neural renderer (DeepestScatter_Train/Disney/DisneyModel.py,
+ * DisneyBlock.py; evaluated by DisneyRenderer::renderRect, DG/Scene/Cameras/DisneyRenderer.cpp:104) as sm_100a kernels.
+ * Internal to the library.
+ *
+ * The network is a chain of 22 GEMMs over the rows (pixels) of a batch, all of width 200:
+ *   block i (x10):  h = relu([o | z_i] . [f1o.W | f1z.W]^T + f1o.b + f1z.b)     K = 200 + 226      (DisneyBlock.py:25-26)
+ *                   o = relu(h . f2.W^T + f2.b + o)                              K = 200            (:28-30)
+ *   fullyConnected: relu(Linear), relu(Linear), leaky_relu(Linear 200 -> 1)                          (DisneyModel.py:52-59)
+ * Rows never interact, so a CTA carries a tile of rows through the whole chain with the activations on chip.
+ */
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <vector>
+
+namespace dsk {
+
+constexpr int MLP_D = 200;      /* DisneyModel.BLOCK_DIMENSION */
+constexpr int MLP_NB = 10;      /* DisneyModel.BLOCK_COUNT */
+constexpr int MLP_ZD = 226;     /* DESCRIPTOR_LAYER_WITH_ANGLE_DIMENSION */
+constexpr int MLP_NPAD = 208;   /* output width padded to a multiple of 16 (UMMA N for M = 128) */
+constexpr int MLP_GEMMS = 22;   /* 2 per block + fullyConnected.0 + fullyConnected.2 */
+constexpr size_t MLP_WEIGHT_COUNT = (size_t)MLP_NB * (MLP_D * MLP_ZD + MLP_D + 2 * (MLP_D * MLP_D + MLP_D)) + 2 * (MLP_D * MLP_D + MLP_D) + MLP_D + 1;
+
+/* one step of the tensor-core kernel's program: a K-chunk of one GEMM */
+struct MlpChunk {
+    uint32_t wOffset;  /* byte offset of the chunk's weights in the packed stream */
+    uint32_t wBytes;   /* (k8 * 2) * MLP_NPAD * 16 */
+    uint16_t k8;       /* number of K = 8 MMA steps in the chunk (1..4) */
+    uint16_t aKGroup;  /* src 0: first 4-float K group of the activation buffer; src 1: first k of the descriptor layer */
+    uint8_t src;       /* 0 = activation buffer, 1 = descriptor layer (z) */
+    uint8_t layer;     /* src 1: descriptor layer index */
+    uint8_t dst;       /* accumulator: 0 = D1 (h), 1 = D2 (o, carries the residual) */
+    uint8_t flags;     /* MLP_FIRST | MLP_LAST | MLP_WAIT_ACT */
+    uint8_t epilogue;  /* MLP_LAST: which epilogue follows */
+    uint8_t gemm;      /* bias row */
+    uint8_t pad[2];
+};
+enum { MLP_FIRST = 1 /* first MMA overwrites the accumulator */, MLP_LAST = 2 /* last chunk of its GEMM */,
+       MLP_WAIT_ACT = 4 /* first chunk that reads what the previous epilogue wrote */ };
+enum { MLP_EPI_H = 1 /* relu -> activation buffer */, MLP_EPI_O = 2 /* relu -> activation buffer and back into D2 */,
+       MLP_EPI_OUT = 3 /* relu, dot with fullyConnected.4, leaky relu -> out */ };
+
+struct DisneyModelDev {
+    float* wT = nullptr;       /* fp32 kernel: per GEMM W^T [K][200] (K = 426 for the first GEMM of a block: o rows, then z rows) */
+    float* bias = nullptr;     /* [22][208]; the two biases of a block's first GEMM are pre-summed */
+    float* w4b4 = nullptr;     /* fullyConnected.4: 200 weights + bias */
+    uint8_t* stream = nullptr; /* tensor-core kernel: weights in UMMA canonical K-major layout, in consumption order */
+    MlpChunk* chunks = nullptr;
+    int nChunks = 0;
+    uint32_t* error = nullptr; /* device word: non-zero if a barrier wait of the tensor-core kernel timed out */
+    bool loaded = false;
+};
+
+/* host-side packing of the flat state_dict array (include/ds_abi.h: ds_disney_model_load) */
+struct DisneyModelHost {
+    std::vector<float> wT, bias, w4b4;
+    std::vector<uint8_t> stream;
+    std::vector<MlpChunk> chunks;
+};
+void packDisneyModel(const float* weights, DisneyModelHost& out);
+
+/* in: [nRowsTotal][10][226] floats on the device; rowIndex (may be NULL): the nRows input rows to evaluate (gather);
+ * out[rowIndex[i]] (or out[i]) receives the prediction */
+cudaError_t launchDisneyMlpF32(const DisneyModelDev& m, const float* in, const uint32_t* rowIndex, uint32_t nRows, float* out, cudaStream_t st);
+cudaError_t launchDisneyMlpTc(const DisneyModelDev& m, const float* in, const uint32_t* rowIndex, uint32_t nRows, float* out, cudaStream_t st);
+/* rows of the rectangle that scattered, compacted in order: idx[0..*count) */
+cudaError_t launchCompactActive(const uint8_t* active, uint32_t n, uint32_t* idx, uint32_t* count, cudaStream_t st);
+/* copyToFrameResult (CU/disneyCamera.cu:38-46) on the device */
+cudaError_t launchBlitPredicted(const float* predicted, const float* info, uint32_t frameW, uint32_t frameH, uint32_t rectX, uint32_t rectY,
+                                uint32_t rectW, uint32_t rectH, float4* frameResult, cudaStream_t st);
+
+} // namespace dsk

@@ -225,6 +225,33 @@ int ds_render_network_input(DsContext* ctx, const DsCamera* cam, uint32_t frame_
  * the pixels that scattered; frame_result_inout is float4 [frame_height][frame_width] */
 int ds_blit_predicted(uint32_t frame_width, uint32_t frame_height, uint32_t rect_x, uint32_t rect_y, uint32_t rect_w, uint32_t rect_h,
                       const float* predicted, const DsIntersectionInfo* info, float* frame_result_inout);
+/* ---- the radiance-predicting network of the neural renderer ----
+ * DisneyRenderer::init loads a TorchScript export of DeepestScatter_Train/Disney/DisneyModel.py (DisneyRenderer.cpp:19-22) and
+ * renderRect evaluates it on the rectangle's network inputs (:104).  Here the model is ONE flat float32 array: the tensors of
+ * DisneyModel().state_dict() in their own order, row-major as torch stores them --
+ *   for i in 0..9: blocks.i.f1z.weight [200][226], .f1z.bias [200], .f1o.weight [200][200], .f1o.bias [200], .f2.weight [200][200],
+ *   .f2.bias [200] (DisneyBlock.py:13-15); fullyConnected.0.weight [200][200], .0.bias [200], .2.weight [200][200], .2.bias [200],
+ *   .4.weight [1][200], .4.bias [1] (DisneyModel.py:52-59)
+ * = ds_disney_model_weight_count() = 1 338 601 floats (deepestscatter_b200/disney_model.py: flatten_state_dict). */
+size_t ds_disney_model_weight_count(void);
+int ds_disney_model_load(DsContext* ctx, const float* weights, size_t count);
+/* Introspection, host only (no device needed): the program the tensor-core kernel runs for these weights -- the weight stream in
+ * UMMA canonical K-major layout (8-row x 16-byte core matrices; row groups 128 B apart, 4-float K groups 26 * 128 B apart; 208 rows,
+ * tf32-rounded) and the chunk table (20-byte records: u32 stream offset, u32 bytes, u16 K/8, u16 first K group (activations) or first k
+ * (descriptor layer), u8 source, u8 layer, u8 accumulator, u8 flags 1 = overwrite / 2 = last of its GEMM / 4 = waits for the previous
+ * epilogue, u8 epilogue 1 = relu -> activations / 2 = same + residual kept in tensor memory / 3 = output, u8 GEMM index, 2 pad).
+ * Either output pointer may be NULL to query the sizes. */
+int ds_disney_model_pack(const float* weights, size_t count, void* stream_out, size_t stream_capacity, void* chunks_out, size_t chunks_capacity,
+                         size_t* stream_bytes, size_t* chunk_count);
+/* module->forward (DisneyRenderer.cpp:104; DisneyModel.forward, DisneyModel.py:16-29): network_input [n][10][226] floats ->
+ * predicted_out [n] (radiance for a sun of 1e6).  DS_PRECISION_EXACT: fp32 FMA kernel; DS_PRECISION_FAST: tcgen05 kind::tf32 tensor-core
+ * kernel (inputs and activations rounded to tf32, fp32 accumulation and residual path) */
+int ds_disney_model_forward(DsContext* ctx, const float* network_input, uint32_t n, float* predicted_out);
+/* DisneyRenderer::render (DisneyRenderer.cpp:58-110): every 128 x 128 rectangle of the frame (x outer, y inner; clipped at the frame
+ * edge) -> network-input launch, the model on the pixels that scattered, copyToFrameResult.  Rectangle k uses RNG stream
+ * `stream + k` (clock() in the reference).  frame_result_out: float4 [frame_height][frame_width], zero where nothing scattered;
+ * what ARenderer::render leaves in frameResultBuffer, ready for the progressive accumulation (ds_frame_* / Camera.cpp:195-199). */
+int ds_render_disney(DsContext* ctx, const DsCamera* cam, uint32_t frame_width, uint32_t frame_height, uint32_t stream, float* frame_result_out);
 void ds_radiance_settings_default(DsRadianceSettings* s);
 /* RadianceCollector::init/update loop until all samples converge (RadianceCollector.cpp:19-54,73-141,176-192;
  * CU/pointEmissionCamera.cu:20-33; CU/PointRadianceTask.h).  tasks_out[i] is the merged representative of

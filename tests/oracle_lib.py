@@ -37,7 +37,7 @@ assert TASK_DTYPE.itemsize == 40
 
 
 def build_oracle(force: bool = False) -> Path:
-    srcs = [ORACLE_DIR / "ds_oracle.cpp", ROOT / "include" / "ds_detmath.h", ROOT / "include" / "ds_synth.h"]
+    srcs = [ORACLE_DIR / "ds_oracle.cpp", ORACLE_DIR / "ds_oracle_mlp.cpp", ROOT / "include" / "ds_detmath.h", ROOT / "include" / "ds_synth.h"]
     if force or not ORACLE_SO.exists() or any(s.stat().st_mtime > ORACLE_SO.stat().st_mtime for s in srcs):
         subprocess.run(["make", "-C", str(ORACLE_DIR)], check=True, capture_output=True)
     return ORACLE_SO
@@ -62,6 +62,8 @@ def lib() -> C.CDLL:
         L.orc_volume_level_dims.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int)]
         L.orc_volume_level_get.argtypes = [C.c_void_p, C.c_int, _u8p]
         L.orc_network_input.argtypes = [C.c_void_p, _f32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint32, _f32p, _f32p]
+        L.orc_disney_weight_count.restype = C.c_size_t
+        L.orc_disney_forward.argtypes = [_f32p, _f32p, C.c_int, _f32p, C.c_void_p]
         L.orc_scene_set.argtypes = [C.c_void_p, C.c_float, C.c_float, C.c_float, _f32p, _f32p, C.c_float]
         L.orc_scene_get_derived.argtypes = [C.c_void_p, _f32p]
         L.orc_bake_inscatter.argtypes = [C.c_void_p]
@@ -270,3 +272,16 @@ def tonemap(progressive: np.ndarray, exposure: float = 0.4):
     out = np.empty((h, w, 4), dtype=np.uint8)
     avg = lib().orc_tonemap(f32(progressive).reshape(-1), w, h, exposure, out.reshape(-1))
     return out, avg
+
+
+def disney_forward(weights: np.ndarray, inputs: np.ndarray, want_hidden: bool = False):
+    """Oracle restatement of the reference's DisneyModel.forward (oracle/ds_oracle_mlp.cpp): inputs [n][10][226] -> [n]."""
+    L = lib()
+    w = np.ascontiguousarray(weights, np.float32)
+    x = np.ascontiguousarray(inputs, np.float32)
+    assert w.size == L.orc_disney_weight_count() and x.shape[1:] == (10, 226)
+    n = x.shape[0]
+    out = np.zeros(n, np.float32)
+    hidden = np.zeros((n, 200), np.float32) if want_hidden else None
+    L.orc_disney_forward(w, x, n, out, hidden.ctypes.data if want_hidden else None)
+    return (out, hidden) if want_hidden else out

@@ -1,0 +1,248 @@
+"""The radiance-predicting network of the neural renderer (second half).
+
+Chain of evidence: the reference's own DisneyModel.py (torch) -> tests/golden/disney_mlp.json (tools/make_golden_disney_mlp.py)
+-> oracle/ds_oracle_mlp.cpp (CPU tests below) -> the two CUDA kernels through the C ABI (GPU tests below).
+
+Tolerances (written here as the task asks):
+  oracle vs reference float64 outputs      1e-6 relative (double accumulation against torch float64)
+  oracle vs reference float32 outputs      2e-6 relative (torch's own float32 rounding)
+  EXACT flavour (fp32 FMA kernel) vs oracle   1e-5 relative
+  FAST flavour (tcgen05 kind::tf32) vs oracle 5e-3 relative: operands carry 10 mantissa bits (2^-11 relative rounding) through 23
+      layers with fp32 accumulation and an fp32 residual path
+"""
+import json
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+import oracle_lib as ol
+from conftest import SCENE_SMALL
+from deepestscatter_b200 import disney_model as dm
+
+GOLDEN = json.loads((Path(__file__).resolve().parent / "golden" / "disney_mlp.json").read_text())
+
+
+@pytest.fixture(scope="module")
+def weights():
+    w = dm.synthetic_weights(GOLDEN["weight_seed"])
+    assert [float(v) for v in w[:4]] == GOLDEN["weights_sha_head"]  # numpy's legacy stream is frozen
+    return w
+
+
+@pytest.fixture(scope="module")
+def inputs():
+    x = dm.synthetic_inputs(GOLDEN["n"], GOLDEN["input_seed"])
+    assert [float(v) for v in x.reshape(-1)[:4]] == GOLDEN["inputs_head"]
+    return x
+
+
+def rel(a, b):
+    return float(np.max(np.abs(np.asarray(a, np.float64) - np.asarray(b, np.float64)) / (np.abs(np.asarray(b, np.float64)) + 1e-6)))
+
+
+def test_weight_layout_matches_state_dict_order():
+    assert dm.WEIGHT_COUNT == 1338601 == ol.lib().orc_disney_weight_count()
+    names = [n for n, _ in dm.tensor_shapes()]
+    assert names[:6] == ["blocks.0.f1z.weight", "blocks.0.f1z.bias", "blocks.0.f1o.weight", "blocks.0.f1o.bias", "blocks.0.f2.weight", "blocks.0.f2.bias"]
+    assert names[-6:] == ["fullyConnected.0.weight", "fullyConnected.0.bias", "fullyConnected.2.weight", "fullyConnected.2.bias",
+                          "fullyConnected.4.weight", "fullyConnected.4.bias"]
+    w = dm.synthetic_weights(3)
+    assert np.array_equal(dm.flatten_state_dict(dm.unflatten(w)), w)
+
+
+def test_oracle_matches_reference_model_outputs(weights, inputs):
+    """The oracle restatement against outputs of the reference's own DisneyModel.py (committed golden vectors)."""
+    y, hidden = ol.disney_forward(weights, inputs, want_hidden=True)
+    assert rel(y, GOLDEN["output_f64"]) <= 1e-6
+    assert rel(y, GOLDEN["output_f32"]) <= 2e-6
+    h_ref = np.array(GOLDEN["hidden_after_blocks_f64_rows0to3"])
+    assert np.abs(hidden[:4] - h_ref).max() <= 1e-6 and (h_ref > 0).mean() > 0.5
+
+
+def test_oracle_block_zero_ignores_previous_output(weights):
+    """o = zeros entering block 0 (DisneyModel.py:34): f1o contributes its bias only; rows are independent."""
+    x = dm.synthetic_inputs(5, 11)
+    y = ol.disney_forward(weights, x)
+    y_rev = ol.disney_forward(weights, x[::-1].copy())
+    assert np.array_equal(y, y_rev[::-1])
+
+
+# ---------------------------------------------------------------- GPU parity, through the C ABI
+
+
+@pytest.fixture(scope="module")
+def gpu_ctx(built_library, weights):
+    ctx = built_library.Context(0)
+    ctx.disney_model_load(weights)
+    yield ctx
+    ctx.close()
+
+
+@pytest.mark.gpu
+def test_forward_requires_a_model_and_checks_the_blob(built_library, weights):
+    ds = built_library
+    with ds.Context(0) as ctx:
+        with pytest.raises(ds.DsError) as e:
+            ctx.disney_model_forward(dm.synthetic_inputs(1))
+        assert e.value.code == -3 and "no model loaded" in str(e.value)
+        with pytest.raises(ds.DsError) as e:
+            ctx.disney_model_load(weights[:-1])
+        assert e.value.code == -1
+        bad = weights.copy()
+        bad[12345] = np.nan
+        with pytest.raises(ds.DsError):
+            ctx.disney_model_load(bad)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n", [1, 63, 160, 1000])
+def test_exact_flavour_matches_oracle(gpu_ctx, built_library, weights, inputs, n):
+    ds = built_library
+    x = inputs[:n] if n <= len(inputs) else dm.synthetic_inputs(n, 21)
+    gpu_ctx.set_option("precision", ds.PRECISION_EXACT)
+    got = gpu_ctx.disney_model_forward(x)
+    ref = ol.disney_forward(weights, x)
+    assert rel(got, ref) <= 1e-5
+    if n == 160:
+        assert rel(got, GOLDEN["output_f64"]) <= 1e-5  # and straight against the reference's outputs
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n", [1, 127, 160, 1000])
+def test_tensor_core_flavour_matches_oracle(gpu_ctx, built_library, weights, inputs, n):
+    ds = built_library
+    x = inputs[:n] if n <= len(inputs) else dm.synthetic_inputs(n, 21)
+    gpu_ctx.set_option("precision", ds.PRECISION_FAST)
+    got = gpu_ctx.disney_model_forward(x)
+    ref = ol.disney_forward(weights, x)
+    assert np.isfinite(got).all()
+    assert rel(got, ref) <= 5e-3
+    assert np.array_equal(got, gpu_ctx.disney_model_forward(x))  # deterministic
+    if n == 160:
+        assert rel(got, GOLDEN["output_f64"]) <= 5e-3
+
+
+@pytest.mark.gpu
+def test_tensor_core_flavour_full_rectangle_and_zero_input(gpu_ctx, built_library, weights):
+    """128 x 128 rows (one rectangle of DisneyRenderer, 128 CTAs) and the all-zero descriptor (a pixel outside the cloud)."""
+    ds = built_library
+    x = dm.synthetic_inputs(128 * 128, 33)
+    x[5] = 0.0
+    gpu_ctx.set_option("precision", ds.PRECISION_FAST)
+    got = gpu_ctx.disney_model_forward(x)
+    gpu_ctx.set_option("precision", ds.PRECISION_EXACT)
+    exact = gpu_ctx.disney_model_forward(x)
+    assert rel(got, exact) <= 5e-3
+    sel = np.r_[0:64, 5000:5064, 16320:16384]
+    assert rel(exact[sel], ol.disney_forward(weights, x[sel])) <= 1e-5
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("precision", ["exact", "fast"])
+def test_render_disney_composes_the_reference_frame(built_library, oracle_small, weights, precision):
+    """DisneyRenderer::render: network-input launch + model on the scattering pixels + copyToFrameResult per rectangle.  The frame is
+    wider than one rectangle, so the second rectangle is clipped and uses stream + 1."""
+    ds = built_library
+    w, h = 160, 40
+    cam = ds.camera_look_at(aspect=w / h)
+    cam_arr = ds.camera_array(cam)
+    want = np.zeros((h, w, 4), np.float32)
+    for k, (x0, rw) in enumerate([(0, 128), (128, 32)]):
+        inp, info = oracle_small.network_input(cam_arr, w, h, (x0, 0, rw, h), stream=9 + k)
+        has = info[..., 4] > 0
+        pred = np.zeros((h, rw), np.float32)
+        if has.any():
+            pred[has] = ol.disney_forward(weights, inp[has])
+        wgt = (1 - info[..., 3:4])
+        rect = np.concatenate([(pred[..., None] + info[..., :3]) * wgt, pred[..., None] * wgt], axis=-1)
+        want[:, x0:x0 + rw][has] = rect[has]
+    with ds.Context(0) as ctx:
+        ctx.set_option("precision", ds.PRECISION_EXACT if precision == "exact" else ds.PRECISION_FAST)
+        ctx.volume_synth(SCENE_SMALL["n"], SCENE_SMALL["kind"], SCENE_SMALL["seed"])
+        ctx.scene_set(SCENE_SMALL["cloud_size_m"], SCENE_SMALL["light_dir"])
+        ctx.bake()
+        ctx.disney_model_load(weights)
+        got = ctx.render_disney(cam, w, h, stream=9)
+    lit = want[..., 3] != 0
+    assert 0.05 < lit.mean() < 1.0
+    if precision == "exact":
+        assert np.array_equal(got[..., 3] != 0, lit)
+        assert np.abs(got - want).max() <= 1e-5 * np.abs(want).max()
+    else:
+        # FAST: hardware-filtered taps move a few silhouette pixels; compare where both scattered
+        both = lit & (got[..., 3] != 0)
+        assert both.sum() > 0.97 * lit.sum()
+        assert abs(float(got[..., 3][both].mean()) / float(want[..., 3][both].mean()) - 1) < 0.02
+
+
+# ---------------------------------------------------------------- the tensor-core kernel's program, emulated on the CPU
+
+CHUNK_DTYPE = np.dtype([("wOffset", "<u4"), ("wBytes", "<u4"), ("k8", "<u2"), ("aK", "<u2"), ("src", "u1"), ("layer", "u1"), ("dst", "u1"),
+                        ("flags", "u1"), ("epilogue", "u1"), ("gemm", "u1"), ("pad", "u1", 2)])
+
+
+def packed_program(built_library, weights):
+    import ctypes as C
+
+    lib = built_library.load()
+    nb, nc = C.c_size_t(), C.c_size_t()
+    w = np.ascontiguousarray(weights, np.float32)
+    assert lib.ds_disney_model_pack(w.ctypes.data, w.size, None, 0, None, 0, C.byref(nb), C.byref(nc)) == 0
+    stream = np.zeros(nb.value, np.uint8)
+    chunks = np.zeros(nc.value, CHUNK_DTYPE)
+    assert lib.ds_disney_model_pack(w.ctypes.data, w.size, stream.ctypes.data, stream.size, chunks.ctypes.data, chunks.nbytes, C.byref(nb), C.byref(nc)) == 0
+    return stream, chunks
+
+
+def test_tensor_core_program_emulated_on_cpu(built_library, weights, inputs):
+    """Runs the chunk program of k_disney_mlp_tc in numpy (float64 accumulators): decodes every weight chunk from the canonical
+    core-matrix layout, follows the overwrite / accumulate / residual-in-accumulator / epilogue flags, and must land on the oracle
+    within the tf32 rounding of the weights (activations are not rounded here)."""
+    assert CHUNK_DTYPE.itemsize == 20
+    stream, chunks = packed_program(built_library, weights)
+    assert len(chunks) <= 256 and chunks["wOffset"][0] == 0 and np.all(chunks["wBytes"] == chunks["k8"].astype(np.uint32) * 2 * 26 * 128)
+    assert np.all(np.diff(chunks["wOffset"].astype(np.int64)) == chunks["wBytes"][:-1])  # consumption order, no gaps
+    assert chunks["wOffset"][-1] + chunks["wBytes"][-1] == stream.size and np.all(chunks["wOffset"] % 16 == 0)
+    n = 24
+    x = inputs[:n].astype(np.float64)
+    words = stream.view(np.float32)
+    act = np.zeros((n, 200))
+    D = [np.zeros((n, 208)), np.zeros((n, 208))]
+    unflat = dm.unflatten(weights)
+    out = None
+    nn, kk = np.meshgrid(np.arange(208), np.arange(32), indexing="ij")
+    for ch in chunks:
+        kc = int(ch["k8"]) * 8
+        off = (kk[:, :kc] // 4) * (26 * 128) + (nn[:, :kc] // 8) * 128 + (nn[:, :kc] % 8) * 16 + (kk[:, :kc] % 4) * 4
+        W = words[(int(ch["wOffset"]) + off) // 4].astype(np.float64)  # [208][kc]
+        assert np.all(W[200:] == 0)
+        if ch["src"] == 1:
+            A = np.zeros((n, kc))
+            k0 = int(ch["aK"])
+            hi = min(226, k0 + kc)
+            A[:, : hi - k0] = x[:, int(ch["layer"]), k0:hi]
+        else:
+            k0 = int(ch["aK"]) * 4
+            assert k0 + kc <= 200
+            A = act[:, k0 : k0 + kc]
+        d = int(ch["dst"])
+        D[d] = A @ W.T if ch["flags"] & 1 else D[d] + A @ W.T
+        if ch["flags"] & 2:
+            g = int(ch["gemm"])
+            if g < 20:
+                pre = f"blocks.{g // 2}."
+                bias = (unflat[pre + "f1o.bias"] + unflat[pre + "f1z.bias"]) if g % 2 == 0 else unflat[pre + "f2.bias"]
+            else:
+                bias = unflat["fullyConnected.0.bias"] if g == 20 else unflat["fullyConnected.2.bias"]
+            v = np.maximum(D[d][:, :200] + bias.astype(np.float64), 0.0)
+            if ch["epilogue"] == 3:
+                y = v @ unflat["fullyConnected.4.weight"][0].astype(np.float64) + float(unflat["fullyConnected.4.bias"][0])
+                out = np.where(y > 0, y, 0.01 * y)
+            else:
+                act = v
+                if ch["epilogue"] == 2:
+                    D[d][:, :200] = v  # the residual of the next block stays in the accumulator
+    assert out is not None
+    ref = ol.disney_forward(weights, inputs[:n])
+    assert rel(out, ref) <= 2e-3
