@@ -321,6 +321,14 @@ class Context:
         self._ck(self.lib.ds_disney_model_forward(self.h, _ptr(x), len(x), _ptr(out)))
         return out
 
+    def disney_model_profile(self) -> dict:
+        """Cycle accounting of block 0 of the last tensor-core model launch (needs option profile_events = 1)."""
+        c = (C.c_uint64 * 16)()
+        self._ck(self.lib.ds_disney_model_profile(self.h, c))
+        return {"issuer_total": c[0], "issuer_wait_weight_stage": c[1], "issuer_wait_epilogue": c[2], "issuer_wait_descriptor": c[3],
+                "issuer_wait_weights": c[4], "worker_total": c[8], "worker_wait_descriptor_stage": c[9], "worker_wait_gemm": c[10],
+                "worker_epilogues": c[11], "worker_staging": c[12]}
+
     def render_disney(self, cam: DsCamera, frame_w: int, frame_h: int, stream: int = 0) -> np.ndarray:
         """DisneyRenderer::render: the neural renderer's frameResultBuffer, float4 [h][w]."""
         out = np.empty((frame_h, frame_w, 4), dtype=np.float32)

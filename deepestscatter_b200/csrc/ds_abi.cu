@@ -137,6 +137,7 @@ static void freeDisneyModel(DsContext* ctx)
     cudaFree(m.stream);
     cudaFree(m.chunks);
     cudaFree(m.error);
+    cudaFree(m.prof);
     m = DisneyModelDev();
 }
 
@@ -1327,6 +1328,8 @@ int ds_disney_model_load(DsContext* ctx, const float* weights, size_t count)
     DS_CUDA(ctx, cudaMalloc(&m.stream, h.stream.size()));
     DS_CUDA(ctx, cudaMalloc(&m.chunks, h.chunks.size() * sizeof(MlpChunk)));
     DS_CUDA(ctx, cudaMalloc(&m.error, sizeof(uint32_t)));
+    DS_CUDA(ctx, cudaMalloc(&m.prof, 16 * sizeof(unsigned long long)));
+    DS_CUDA(ctx, cudaMemset(m.prof, 0, 16 * sizeof(unsigned long long)));
     DS_CUDA(ctx, cudaMemcpy(m.wT, h.wT.data(), h.wT.size() * sizeof(float), cudaMemcpyHostToDevice));
     DS_CUDA(ctx, cudaMemcpy(m.bias, h.bias.data(), h.bias.size() * sizeof(float), cudaMemcpyHostToDevice));
     DS_CUDA(ctx, cudaMemcpy(m.w4b4, h.w4b4.data(), h.w4b4.size() * sizeof(float), cudaMemcpyHostToDevice));
@@ -1350,7 +1353,7 @@ static int disneyForwardDevice(DsContext* ctx, const float* dIn, const uint32_t*
         DS_CUDA(ctx, cudaEventRecord(e0, ctx->stream));
     }
     if (ctx->opt["precision"] == DS_PRECISION_FAST)
-        DS_CUDA(ctx, launchDisneyMlpTc(ctx->model, dIn, dRowIndex, nRows, dOut, ctx->stream));
+        DS_CUDA(ctx, launchDisneyMlpTc(ctx->model, dIn, dRowIndex, nRows, dOut, ctx->stream, ctx->opt["profile_events"] >= 2 ? ctx->model.prof : nullptr));
     else
         DS_CUDA(ctx, launchDisneyMlpF32(ctx->model, dIn, dRowIndex, nRows, dOut, ctx->stream));
     ctx->launches += 1;
@@ -1378,6 +1381,16 @@ static int disneyCheckError(DsContext* ctx)
     return DS_OK;
 }
 
+int ds_disney_model_profile(DsContext* ctx, uint64_t* cycles16)
+{
+    DS_CHECK_CTX(ctx);
+    if (!cycles16) DS_FAIL(ctx, DS_ERR_INVALID, "NULL argument");
+    if (!ctx->model.loaded) DS_FAIL(ctx, DS_ERR_STATE, "no model loaded (ds_disney_model_load)");
+    DS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    DS_CUDA(ctx, cudaMemcpy(cycles16, ctx->model.prof, 16 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+    return DS_OK;
+}
+
 int ds_disney_model_forward(DsContext* ctx, const float* network_input, uint32_t n, float* predicted_out)
 {
     DS_CHECK_CTX(ctx);
@@ -1392,45 +1405,72 @@ int ds_disney_model_forward(DsContext* ctx, const float* network_input, uint32_t
     return disneyCheckError(ctx);
 }
 
-/* DisneyRenderer::render (DG/Scene/Cameras/DisneyRenderer.cpp:58-110): for every 128 x 128 rectangle (x outer, y inner) the
- * network-input launch, the model on the pixels that scattered (the reference skips the rectangle when none did, :91-99),
- * copyToFrameResult.  Everything stays on the device; one copy of the frame result at the end. */
+/* DisneyRenderer::render (DG/Scene/Cameras/DisneyRenderer.cpp:58-110).  The reference walks the frame in 128 x 128 rectangles because its
+ * network-input tensor holds one rectangle; per rectangle: the network-input launch, the model (skipped when nothing scattered, :91-99),
+ * copyToFrameResult.  Pixels do not interact, so here the WHOLE frame goes through each stage in one launch -- every pixel with the seed and
+ * stream of its own rectangle, so the result is the reference's pixel for pixel -- and only the pixels that scattered reach the descriptor
+ * gather and the model, compacted, in batches sized for HBM (2.4 GB of network input per batch):
+ *   k_network_info (frame) -> k_compact_active -> per batch: k_descriptors (gather) -> model -> k_blit_predicted (scatter) */
 int ds_render_disney(DsContext* ctx, const DsCamera* cam, uint32_t frame_width, uint32_t frame_height, uint32_t stream, float* frame_result_out)
 {
     DS_CHECK_CTX(ctx);
     int rc = requireScene(ctx, true);
     if (rc) return rc;
     if (!cam || !frame_result_out) DS_FAIL(ctx, DS_ERR_INVALID, "NULL argument");
-    if (frame_width == 0 || frame_height == 0 || (unsigned long long)frame_width * frame_height > (1ull << 28))
+    if (frame_width == 0 || frame_height == 0 || (unsigned long long)frame_width * frame_height > (1ull << 26))
         DS_FAIL(ctx, DS_ERR_INVALID, "bad frame size");
     if (!ctx->model.loaded) DS_FAIL(ctx, DS_ERR_STATE, "no model loaded (ds_disney_model_load)");
-    const uint32_t RECT = 128; /* DisneyRenderer.cpp:10 */
+    const int RECT = 128;            /* DisneyRenderer.cpp:10 */
+    const uint32_t BATCH = 1u << 18; /* rows of network input resident at a time */
     const size_t pixels = (size_t)frame_width * frame_height;
-    if ((rc = ensureMlpScratch(ctx, 1, (size_t)RECT * RECT * sizeof(float))) ||
-        (rc = ensureMlpScratch(ctx, 2, ((size_t)RECT * RECT + 1) * sizeof(uint32_t))) || (rc = ensureMlpScratch(ctx, 3, pixels * sizeof(float4))))
+    const size_t batchRows = std::min<size_t>(BATCH, pixels);
+    if ((rc = ensureScratch(ctx, 0, pixels * 3 * sizeof(float))) || (rc = ensureScratch(ctx, 1, pixels * 3 * sizeof(float))) ||
+        (rc = ensureScratch(ctx, 2, pixels * (sizeof(float) + 1))) || (rc = ensureScratch(ctx, 3, batchRows * 2260 * sizeof(float))) ||
+        (rc = ensureScratch(ctx, 4, pixels * 5 * sizeof(float))) || (rc = ensureMlpScratch(ctx, 1, batchRows * sizeof(float))) ||
+        (rc = ensureMlpScratch(ctx, 2, (pixels + 1) * sizeof(uint32_t))) || (rc = ensureMlpScratch(ctx, 3, pixels * sizeof(float4))))
         return rc;
+    float* dPos = (float*)ctx->scratch[0];
+    float* dDir = (float*)ctx->scratch[1];
+    float* dAngle = (float*)ctx->scratch[2];
+    uint8_t* dActive = (uint8_t*)(dAngle + pixels);
+    float* dInput = (float*)ctx->scratch[3];
+    float* dInfo = (float*)ctx->scratch[4];
     float* dPred = (float*)ctx->mlpScratch[1];
     uint32_t* dIdx = (uint32_t*)ctx->mlpScratch[2];
-    uint32_t* dCount = dIdx + (size_t)RECT * RECT;
+    uint32_t* dCount = dIdx + pixels;
     float4* dFrame = (float4*)ctx->mlpScratch[3];
     DS_CUDA(ctx, cudaMemsetAsync(dFrame, 0, pixels * sizeof(float4), ctx->stream));
-    uint32_t ordinal = 0;
-    for (uint32_t x = 0; x < frame_width; x += RECT)
-        for (uint32_t y = 0; y < frame_height; y += RECT, ++ordinal) {
-            const uint32_t rw = std::min(RECT, frame_width - x), rh = std::min(RECT, frame_height - y);
-            const uint32_t n = rw * rh;
-            if ((rc = networkInputDevice(ctx, cam, frame_width, frame_height, x, y, rw, rh, stream + ordinal))) return rc;
-            const uint8_t* dActive = (const uint8_t*)((float*)ctx->scratch[2] + n);
-            DS_CUDA(ctx, launchCompactActive(dActive, n, dIdx, dCount, ctx->stream));
-            uint32_t nActive = 0;
-            DS_CUDA(ctx, cudaMemcpyAsync(&nActive, dCount, sizeof(nActive), cudaMemcpyDeviceToHost, ctx->stream));
-            DS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-            ctx->launches += 1;
-            if (nActive == 0) continue; /* DisneyRenderer.cpp:96-99 */
-            if ((rc = disneyForwardDevice(ctx, (const float*)ctx->scratch[3], dIdx, nActive, dPred))) return rc;
-            DS_CUDA(ctx, launchBlitPredicted(dPred, (const float*)ctx->scratch[4], frame_width, frame_height, x, y, rw, rh, dFrame, ctx->stream));
-            ctx->launches += 1;
-        }
+    TraceJob job;
+    memset(&job, 0, sizeof(job));
+    memcpy(job.eye, cam->eye, 12);
+    memcpy(job.U, cam->U, 12);
+    memcpy(job.V, cam->V, 12);
+    memcpy(job.W, cam->W, 12);
+    job.width = (int)frame_width;
+    job.height = (int)frame_height;
+    DevScene sc;
+    fillDevScene(ctx, sc);
+    if (ctx->opt["precision"] == DS_PRECISION_FAST)
+        DS_CUDA(ctx, KernelSet<true>::networkInfo(sc, job, 0, 0, (int)frame_width, (int)frame_height, stream, dInfo, dPos, dDir, dAngle, dActive,
+                                                  ctx->stats, ctx->stream, RECT));
+    else
+        DS_CUDA(ctx, KernelSet<false>::networkInfo(sc, job, 0, 0, (int)frame_width, (int)frame_height, stream, dInfo, dPos, dDir, dAngle, dActive,
+                                                   ctx->stats, ctx->stream, RECT));
+    DS_CUDA(ctx, launchCompactActive(dActive, (uint32_t)pixels, dIdx, dCount, ctx->stream));
+    uint32_t nActive = 0;
+    DS_CUDA(ctx, cudaMemcpyAsync(&nActive, dCount, sizeof(nActive), cudaMemcpyDeviceToHost, ctx->stream));
+    DS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->launches += 2;
+    LevelTable lv;
+    DescriptorLayers layers;
+    fillDescriptorTables(ctx, lv, layers);
+    for (uint32_t first = 0; first < nActive; first += BATCH) {
+        const uint32_t n = std::min(BATCH, nActive - first);
+        DS_CUDA(ctx, launchDescriptors(sc, lv, layers, dPos, dDir, n, nullptr, dInput, nullptr, ctx->stream, 226, dAngle, nullptr, dIdx + first));
+        if ((rc = disneyForwardDevice(ctx, dInput, nullptr, n, dPred))) return rc;
+        DS_CUDA(ctx, launchBlitPredicted(dPred, dInfo, dIdx + first, n, dFrame, ctx->stream));
+        ctx->launches += 2;
+    }
     DS_CUDA(ctx, cudaMemcpyAsync(frame_result_out, dFrame, pixels * sizeof(float4), cudaMemcpyDeviceToHost, ctx->stream));
     return disneyCheckError(ctx);
 }

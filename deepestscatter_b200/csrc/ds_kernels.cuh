@@ -372,13 +372,25 @@ cudaError_t KernelSet<FAST>::generatePoints(const DevScene& sc, uint32_t firstIn
  * sun radiance there; the float descriptor of the scattered pixels is gathered by k_descriptors afterwards */
 template <bool FAST>
 __global__ void __launch_bounds__(128) k_network_info(const DevScene sc, const TraceJob cam, int rectX, int rectY, int rectW, int rectH, uint32_t stream,
-                                                      float* __restrict__ info, float* __restrict__ pos, float* __restrict__ dir,
+                                                      int tile, float* __restrict__ info, float* __restrict__ pos, float* __restrict__ dir,
                                                       float* __restrict__ angleOut, uint8_t* __restrict__ active, unsigned long long* stats)
 {
+    /* tile == 0: one rectangle of renderRect, outputs indexed by the rectangle-local pixel;
+     * tile  > 0: the whole frame in one launch (rectW x rectH = frame, rectX = rectY = 0), outputs indexed by the frame pixel; every pixel
+     *            behaves as in the launch of its own tile x tile rectangle: rectangle-local launch index in the seed and the stream of
+     *            rectangle k = (px / tile) * rectsY + py / tile, the order DisneyRenderer::render visits them (DisneyRenderer.cpp:72-78) */
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= (uint32_t)(rectW * rectH)) return;
-    const uint32_t lx = i % (uint32_t)rectW, ly = i / (uint32_t)rectW;
+    const bool inRange = i < (uint32_t)(rectW * rectH);
+    uint32_t lx = inRange ? i % (uint32_t)rectW : 0u, ly = inRange ? i / (uint32_t)rectW : 0u;
     const uint32_t px = lx + (uint32_t)rectX, py = ly + (uint32_t)rectY;
+    if (tile > 0) {
+        const uint32_t rectsY = ((uint32_t)rectH + (uint32_t)tile - 1u) / (uint32_t)tile;
+        stream += (px / (uint32_t)tile) * rectsY + py / (uint32_t)tile;
+        lx = px % (uint32_t)tile;
+        ly = py % (uint32_t)tile;
+    }
+    unsigned long long steps = 0, events = 0;
+    if (inRange) {
     const float dx = (float)px / (float)cam.width * 2.f - 1.f;
     const float dy = (float)py / (float)cam.height * 2.f - 1.f;
     const V3 U = mk(cam.U[0], cam.U[1], cam.U[2]), V = mk(cam.V[0], cam.V[1], cam.V[2]), W = mk(cam.W[0], cam.W[1], cam.W[2]);
@@ -388,7 +400,6 @@ __global__ void __launch_bounds__(128) k_network_info(const DevScene sc, const T
     float r = 0.f, g = 0.f, b = 0.f, transmittance = 1.0f;
     bool has = false;
     V3 world = mk(0.f, 0.f, 0.f), d = rayDirection;
-    unsigned long long steps = 0, events = 0;
     const float tHit = intersectBox(sc, o, rayDirection);
     if (tHit >= 0.0f) {
         V3 hit = o + tHit * rayDirection;
@@ -452,18 +463,28 @@ __global__ void __launch_bounds__(128) k_network_info(const DevScene sc, const T
     dir[3 * (size_t)i] = d.x;
     dir[3 * (size_t)i + 1] = d.y;
     dir[3 * (size_t)i + 2] = d.z;
-    atomicAdd(stats + CNT_PATHS, 1ull);
-    if (steps) atomicAdd(stats + CNT_STEPS, steps);
-    if (events) atomicAdd(stats + CNT_EVENTS, events);
+    }
+    /* work counters: one atomic per warp and counter */
+    unsigned long long paths = inRange ? 1ull : 0ull;
+    for (int o = 16; o > 0; o >>= 1) {
+        paths += __shfl_down_sync(0xffffffffu, paths, o);
+        steps += __shfl_down_sync(0xffffffffu, steps, o);
+        events += __shfl_down_sync(0xffffffffu, events, o);
+    }
+    if ((threadIdx.x & 31u) == 0u) {
+        if (paths) atomicAdd(stats + CNT_PATHS, paths);
+        if (steps) atomicAdd(stats + CNT_STEPS, steps);
+        if (events) atomicAdd(stats + CNT_EVENTS, events);
+    }
 }
 
 template <bool FAST>
 cudaError_t KernelSet<FAST>::networkInfo(const DevScene& sc, const TraceJob& cam, int rectX, int rectY, int rectW, int rectH, uint32_t stream, float* info,
-                                         float* pos, float* dir, float* angle, uint8_t* active, unsigned long long* stats, cudaStream_t st)
+                                         float* pos, float* dir, float* angle, uint8_t* active, unsigned long long* stats, cudaStream_t st, int tile)
 {
     const int n = rectW * rectH;
     if (n <= 0) return cudaSuccess;
-    k_network_info<FAST><<<(n + 127) / 128, 128, 0, st>>>(sc, cam, rectX, rectY, rectW, rectH, stream, info, pos, dir, angle, active, stats);
+    k_network_info<FAST><<<(n + 127) / 128, 128, 0, st>>>(sc, cam, rectX, rectY, rectW, rectH, stream, tile, info, pos, dir, angle, active, stats);
     return cudaGetLastError();
 }
 

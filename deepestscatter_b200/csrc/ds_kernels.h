@@ -113,7 +113,7 @@ struct KernelSet {
      * rectangle info = {radiance rgb, transmittance, hasScattered}, the collision point (centred) and view direction, the
      * light / view angle and the hasScattered byte */
     static cudaError_t networkInfo(const DevScene& sc, const TraceJob& cam, int rectX, int rectY, int rectW, int rectH, uint32_t stream, float* info,
-                                   float* pos, float* dir, float* angle, uint8_t* active, unsigned long long* stats, cudaStream_t st);
+                                   float* pos, float* dir, float* angle, uint8_t* active, unsigned long long* stats, cudaStream_t st, int tile = 0);
     static cudaError_t generatePoints(const DevScene& sc, uint32_t firstIndex, uint32_t n, uint32_t stream, float* pos, float* dir,
                                       unsigned long long* stats, cudaStream_t st);
 };
@@ -136,10 +136,11 @@ cudaError_t launchUnconverged(const float4* progressive, const float4* variance,
 cudaError_t launchExportMoments(const float4* progressive, const float4* variance, size_t pixels, uint32_t n, double* out, cudaStream_t st);
 cudaError_t launchImportMoments(const double* in, size_t pixels, uint32_t nTotal, float4* progressive, float4* variance, cudaStream_t st);
 /* layerStride 225: DisneyDescriptor layout [n][10][225]; 226: DisneyNetworkInput layout [n][10][226] whose last element per layer is
- * angle[i] (may be NULL) -- samples with active[i] == 0 (active may be NULL) get all-zero densities */
+ * angle[i] (may be NULL) -- samples with active[i] == 0 (active may be NULL) get all-zero densities; gather (may be NULL): output row i
+ * is computed from input sample gather[i] */
 cudaError_t launchDescriptors(const DevScene& sc, const LevelTable& lv, const DescriptorLayers& layers, const float* pos, const float* dir,
                               uint32_t n, uint8_t* outU8, float* outF32, int32_t* tapIndex, cudaStream_t st, int layerStride = 225,
-                              const float* angle = nullptr, const uint8_t* active = nullptr);
+                              const float* angle = nullptr, const uint8_t* active = nullptr, const uint32_t* gather = nullptr);
 cudaError_t launchTaskWelford(DsPointRadianceTask* tasks, const float* x, uint32_t nThreads, uint32_t launches, cudaStream_t st);
 
 } // namespace dsk

@@ -381,20 +381,22 @@ __device__ __forceinline__ float distanceToBox(const DevScene& sc, V3 pos, float
 __global__ void __launch_bounds__(256) k_descriptors(const DevScene sc, const LevelTable lv, const DescriptorLayers layers,
                                                      const float* __restrict__ positions, const float* __restrict__ directions, uint32_t n,
                                                      uint8_t* __restrict__ outU8, float* __restrict__ outF32, int32_t* __restrict__ tapIndex,
-                                                     int layerStride, const float* __restrict__ angle, const uint8_t* __restrict__ active)
+                                                     int layerStride, const float* __restrict__ angle, const uint8_t* __restrict__ active,
+                                                     const uint32_t* __restrict__ gather)
 {
     const uint32_t i = blockIdx.x;
     const int t = threadIdx.x;
     if (i >= n || t >= 225) return;
+    const uint32_t src = gather ? gather[i] : i; /* input sample of output row i */
     const size_t sampleStride = (size_t)layerStride * 10;
-    if (angle && outF32 && t < 10) outF32[(size_t)i * sampleStride + (size_t)t * layerStride + 225] = angle[i]; /* disneyCamera.cu:32-35 */
-    if (active && !active[i]) {
+    if (angle && outF32 && t < 10) outF32[(size_t)i * sampleStride + (size_t)t * layerStride + 225] = angle[src]; /* disneyCamera.cu:32-35 */
+    if (active && !active[src]) {
         if (outF32)
             for (int layer = 0; layer < 10; layer++) outF32[(size_t)i * sampleStride + (size_t)layer * layerStride + t] = 0.0f;
         return;
     }
-    const V3 worldPos = mk(positions[3 * i], positions[3 * i + 1], positions[3 * i + 2]);
-    const V3 viewDirection = mk(directions[3 * i], directions[3 * i + 1], directions[3 * i + 2]);
+    const V3 worldPos = mk(positions[3 * (size_t)src], positions[3 * (size_t)src + 1], positions[3 * (size_t)src + 2]);
+    const V3 viewDirection = mk(directions[3 * (size_t)src], directions[3 * (size_t)src + 1], directions[3 * (size_t)src + 2]);
     const V3 eZ = normalize<false>(-sc.light);
     const V3 eX = normalize<false>(cross(eZ, viewDirection));
     const V3 eY = cross(eX, eZ);
@@ -405,12 +407,17 @@ __global__ void __launch_bounds__(256) k_descriptors(const DevScene sc, const Le
         const V3 offset = (eX * x + eY * y + eZ * z) * layers.scale[layer];
         const V3 pos = origin + offset;
         const V3 uvw = pos * sc.texScale;
-        int l0;
-        float density = tex3dLod(lv, uvw.x, uvw.y, uvw.z, layers.lod[layer], l0);
+        int l0 = 0;
         const float mipVoxelSize = layers.mipVoxelSize[layer];
         const float distance = distanceToBox(sc, pos, mipVoxelSize);
         const float tt = fminf(fmaxf(distance / mipVoxelSize, 0.0f), 1.0f);
-        density = density + tt * (0.0f - density); /* lerp(density, 0, t) */
+        /* a tap more than one mip voxel outside the box fades to exactly zero: lerp(d, 0, 1) = d + 1 * (0 - d) = +0 for every finite d,
+         * so its (up to 16) texel reads are skipped -- most taps of the outer layers */
+        float density = 0.0f;
+        if (tt < 1.0f || tapIndex) {
+            density = tex3dLod(lv, uvw.x, uvw.y, uvw.z, layers.lod[layer], l0);
+            density = density + tt * (0.0f - density); /* lerp(density, 0, t) */
+        }
         const size_t o = (size_t)i * 2250 + (size_t)layer * 225 + t;
         if (outU8) outU8[o] = (uint8_t)(density * 255.0f); /* TFromFloat<uint8_t>, DisneyDescriptor.cuh:66-69 */
         if (outF32) outF32[(size_t)i * sampleStride + (size_t)layer * layerStride + t] = density;
@@ -426,10 +433,10 @@ __global__ void __launch_bounds__(256) k_descriptors(const DevScene sc, const Le
 
 cudaError_t launchDescriptors(const DevScene& sc, const LevelTable& lv, const DescriptorLayers& layers, const float* pos, const float* dir,
                               uint32_t n, uint8_t* outU8, float* outF32, int32_t* tapIndex, cudaStream_t st, int layerStride, const float* angle,
-                              const uint8_t* active)
+                              const uint8_t* active, const uint32_t* gather)
 {
     if (n == 0) return cudaSuccess;
-    k_descriptors<<<n, 256, 0, st>>>(sc, lv, layers, pos, dir, n, outU8, outF32, tapIndex, layerStride, angle, active);
+    k_descriptors<<<n, 256, 0, st>>>(sc, lv, layers, pos, dir, n, outU8, outF32, tapIndex, layerStride, angle, active, gather);
     return cudaGetLastError();
 }
 

@@ -35,9 +35,10 @@ float roundTf32(float x)
 
 constexpr uint32_t B_LBO = MLP_NPAD / 8 * 128; /* bytes between the two 4-float K groups of one MMA step: all 26 row groups */
 
-/* one K chunk of W [200][ld] (torch Linear layout), k in [k0, k0 + 8 * k8), zero beyond kValid and beyond row 200, in the
- * UMMA canonical K-major no-swizzle layout: 8 x 16-byte core matrices, row groups 128 B apart, K groups B_LBO apart */
-void appendWeightChunk(std::vector<uint8_t>& stream, const float* W, int ld, int k0, int k8, int kValid)
+/* one K chunk of W [200][ld] (torch Linear layout), k in [k0, k0 + 8 * k8), zero beyond row 200, in the UMMA canonical K-major no-swizzle
+ * layout: 8 x 16-byte core matrices, row groups 128 B apart, K groups B_LBO apart.  Columns kValid and kValid + 1 (when bias != NULL)
+ * carry the bias split into two tf32 values: the A operand holds 1.0 there, so the MMA adds the bias at nearly fp32 precision */
+void appendWeightChunk(std::vector<uint8_t>& stream, const float* W, int ld, int k0, int k8, int kValid, const float* bias)
 {
     const size_t base = stream.size();
     const int kc = 8 * k8;
@@ -45,22 +46,29 @@ void appendWeightChunk(std::vector<uint8_t>& stream, const float* W, int ld, int
     for (int kk = 0; kk < kc; ++kk)
         for (int n = 0; n < MLP_D; ++n) {
             const int k = k0 + kk;
-            const float v = k < kValid ? roundTf32(W[(size_t)n * ld + k]) : 0.0f;
+            float v = 0.0f;
+            if (k < kValid)
+                v = roundTf32(W[(size_t)n * ld + k]);
+            else if (bias && k == kValid)
+                v = roundTf32(bias[n]);
+            else if (bias && k == kValid + 1)
+                v = roundTf32(bias[n] - roundTf32(bias[n]));
             const size_t off = base + (size_t)(kk / 4) * B_LBO + (size_t)(n / 8) * 128 + (size_t)(n % 8) * 16 + (size_t)(kk % 4) * 4;
             memcpy(&stream[off], &v, 4);
         }
 }
 
-/* the chunks of one GEMM operand of K values (padded to a multiple of 8): 32 at a time, then the rest */
-void appendGemmPart(DisneyModelHost& out, const float* W, int ld, int K, uint8_t src, uint8_t layer, uint8_t dst, uint8_t gemm, bool first,
-                    bool waitAct, bool last, uint8_t epilogue)
+/* the chunks of one GEMM operand of K values (+ 2 bias columns when bias != NULL; padded to a multiple of 8): MLP_TC_KCHUNK at a time,
+ * then the rest */
+void appendGemmPart(DisneyModelHost& out, const float* W, int ld, int K, const float* bias, uint8_t src, uint8_t layer, uint8_t dst, uint8_t gemm,
+                    bool first, bool waitAct, bool last, uint8_t epilogue)
 {
-    const int kPad = (K + 7) / 8 * 8;
-    for (int k0 = 0; k0 < kPad; k0 += 32) {
-        const int k8 = (kPad - k0 >= 32 ? 32 : kPad - k0) / 8;
+    const int kPad = (K + (bias ? 2 : 0) + 7) / 8 * 8;
+    for (int k0 = 0; k0 < kPad; k0 += MLP_TC_KCHUNK) {
+        const int k8 = (kPad - k0 >= MLP_TC_KCHUNK ? MLP_TC_KCHUNK : kPad - k0) / 8;
         MlpChunk c{};
         c.wOffset = (uint32_t)out.stream.size();
-        appendWeightChunk(out.stream, W, ld, k0, k8, K);
+        appendWeightChunk(out.stream, W, ld, k0, k8, K, bias);
         c.wBytes = (uint32_t)out.stream.size() - c.wOffset;
         c.k8 = (uint16_t)k8;
         c.aKGroup = (uint16_t)(src == 0 ? k0 / 4 : k0);
@@ -71,7 +79,7 @@ void appendGemmPart(DisneyModelHost& out, const float* W, int ld, int K, uint8_t
         c.flags = 0;
         if (k0 == 0 && first) c.flags |= MLP_FIRST;
         if (k0 == 0 && waitAct) c.flags |= MLP_WAIT_ACT;
-        if (k0 + 32 >= kPad && last) {
+        if (k0 + MLP_TC_KCHUNK >= kPad && last) {
             c.flags |= MLP_LAST;
             c.epilogue = epilogue;
         }
@@ -124,21 +132,24 @@ void packDisneyModel(const float* w, DisneyModelHost& out)
         out.bias[(size_t)20 * MLP_NPAD + c] = fc0B[c];
         out.bias[(size_t)21 * MLP_NPAD + c] = fc2B[c];
     }
-    out.w4b4.assign(fc4W, fc4W + MLP_D);
-    out.w4b4.push_back(fc4B[0]);
+    out.w4b4.assign(MLP_NPAD + 1, 0.0f); /* 200 weights, zero padding to 208, bias */
+    for (int c = 0; c < MLP_D; ++c) out.w4b4[c] = fc4W[c];
+    out.w4b4[MLP_NPAD] = fc4B[0];
 
-    /* tensor-core kernel: the program */
+    /* tensor-core kernel: the program.  Biases ride in the GEMMs: the descriptor layer is staged with z[226] = z[227] = 1 and the
+     * activation buffer holds 1 in columns 200 and 201 */
     out.stream.clear();
     out.chunks.clear();
     for (int i = 0; i < MLP_NB; ++i) {
         /* h = relu(o . f1o^T + z_i . f1z^T + b); o = 0 in block 0 (DisneyModel.py:34): that part is skipped */
-        if (i > 0) appendGemmPart(out, blk[i].f1oW, MLP_D, MLP_D, 0, 0, 0, (uint8_t)(2 * i), true, true, false, 0);
-        appendGemmPart(out, blk[i].f1zW, MLP_ZD, MLP_ZD, 1, (uint8_t)i, 0, (uint8_t)(2 * i), i == 0, false, true, MLP_EPI_H);
+        if (i > 0) appendGemmPart(out, blk[i].f1oW, MLP_D, MLP_D, nullptr, 0, 0, 0, (uint8_t)(2 * i), true, true, false, 0);
+        appendGemmPart(out, blk[i].f1zW, MLP_ZD, MLP_ZD, &out.bias[(size_t)(2 * i) * MLP_NPAD], 1, (uint8_t)i, 0, (uint8_t)(2 * i), i == 0, false, true,
+                       MLP_EPI_H);
         /* o = relu(h . f2^T + b + o): D2 still holds o, the MMAs accumulate on top of it */
-        appendGemmPart(out, blk[i].f2W, MLP_D, MLP_D, 0, 0, 1, (uint8_t)(2 * i + 1), i == 0, true, true, MLP_EPI_O);
+        appendGemmPart(out, blk[i].f2W, MLP_D, MLP_D, blk[i].f2B, 0, 0, 1, (uint8_t)(2 * i + 1), i == 0, true, true, MLP_EPI_O);
     }
-    appendGemmPart(out, fc0W, MLP_D, MLP_D, 0, 0, 0, 20, true, true, true, MLP_EPI_H);
-    appendGemmPart(out, fc2W, MLP_D, MLP_D, 0, 0, 0, 21, true, true, true, MLP_EPI_OUT);
+    appendGemmPart(out, fc0W, MLP_D, MLP_D, fc0B, 0, 0, 0, 20, true, true, true, MLP_EPI_H);
+    appendGemmPart(out, fc2W, MLP_D, MLP_D, fc2B, 0, 0, 0, 21, true, true, true, MLP_EPI_OUT);
 }
 
 /* ------------------------------------------------------------------------------------------------ fp32 kernel */
@@ -252,7 +263,7 @@ __global__ void __launch_bounds__(F32_THREADS, 1)
     epilogueF32(acc, bias + (size_t)21 * MLP_NPAD, nullptr, actO, ty, tx);
     __syncthreads();
     if (threadIdx.x < F32_TM && row0 + threadIdx.x < nRows) {
-        float y = __ldg(w4b4 + MLP_D);
+        float y = __ldg(w4b4 + MLP_NPAD);
         for (int k = 0; k < MLP_D; ++k) y = fmaf(actO[k * F32_TM + threadIdx.x], __ldg(w4b4 + k), y);
         const size_t dst = rowIndex ? rowIndex[row0 + threadIdx.x] : row0 + threadIdx.x;
         out[dst] = y > 0.0f ? y : 0.01f * y; /* torch.nn.LeakyReLU default slope */
@@ -271,29 +282,38 @@ cudaError_t launchDisneyMlpF32(const DisneyModelDev& m, const float* in, const u
 /* ------------------------------------------------------------------------------------------------ tcgen05 kernel */
 
 constexpr int TC_M = 128;          /* rows per CTA = UMMA M = TMEM lanes */
-constexpr int TC_WORKERS = 128;    /* warps 0-3: thread t owns row t (TMEM lane t) */
-constexpr int TC_THREADS = 160;    /* warp 4: TMEM allocation, weight producer and MMA issuer (one lane) */
+constexpr int TC_WORKERS = 256;    /* warps 0-7: threads t and t + 128 share row t (TMEM lane t): each stages half of a descriptor chunk and
+                                      runs the epilogue on half of the columns (a warp reaches the TMEM lanes of quadrant warp % 4) */
+constexpr int TC_ISSUER_WARP = TC_WORKERS / 32;     /* TMEM allocation and MMA issue (one lane) */
+constexpr int TC_PRODUCER_WARP = TC_ISSUER_WARP + 1; /* weight stream: bulk copies (one lane) */
+constexpr int TC_THREADS = TC_WORKERS + 64;
+constexpr int TC_HALF_COLS = 112;  /* epilogue: columns [0, 112) for the first half of the workers, [112, 208) for the second */
 constexpr int TC_WSTAGES = 3, TC_ZSTAGES = 2;
-constexpr uint32_t TC_A_LBO = TC_M / 8 * 128;          /* 2048: bytes between 4-float K groups of the activations (all 16 row groups) */
-constexpr uint32_t TC_SBO = 128;                       /* bytes between 8-row groups */
-constexpr uint32_t TC_ACT_BYTES = MLP_D / 4 * TC_A_LBO; /* 102400 */
-constexpr uint32_t TC_WSTAGE_BYTES = 8 * B_LBO;        /* 26624: K = 32 */
-constexpr uint32_t TC_ZSTAGE_BYTES = 8 * TC_A_LBO;     /* 16384 */
-constexpr int TC_MAX_CHUNKS = 256;
+constexpr int TC_MAX_CHUNKS = 232;
+constexpr uint32_t TC_A_LBO = TC_M / 8 * 128;           /* 2048: bytes between 4-float K groups of the activations (all 16 row groups) */
+constexpr uint32_t TC_SBO = 128;                        /* bytes between 8-row groups */
+constexpr uint32_t TC_ACT_KGROUPS = MLP_NPAD / 4;       /* 200 activations, the two constant-one columns, padding to 208 */
+constexpr uint32_t TC_ACT_BYTES = TC_ACT_KGROUPS * TC_A_LBO; /* 106496 */
+constexpr uint32_t TC_WSTAGE_BYTES = MLP_TC_KCHUNK / 4 * B_LBO;    /* 26624 */
+constexpr uint32_t TC_ZSTAGE_BYTES = MLP_TC_KCHUNK / 4 * TC_A_LBO; /* 16384 */
 constexpr uint32_t TC_OFF_W = TC_ACT_BYTES;
 constexpr uint32_t TC_OFF_Z = TC_OFF_W + TC_WSTAGES * TC_WSTAGE_BYTES;
 constexpr uint32_t TC_OFF_CHUNKS = TC_OFF_Z + TC_ZSTAGES * TC_ZSTAGE_BYTES;
 constexpr uint32_t TC_OFF_BAR = TC_OFF_CHUNKS + TC_MAX_CHUNKS * sizeof(MlpChunk);
 constexpr uint32_t TC_SMEM = TC_OFF_BAR + 256;
-static_assert(sizeof(MlpChunk) == 20 || sizeof(MlpChunk) == 24, "MlpChunk layout");
+static_assert(sizeof(MlpChunk) == 20, "MlpChunk layout (include/ds_abi.h documents it)");
 static_assert(TC_SMEM <= 232448, "shared memory budget");
+static_assert(MLP_TC_KCHUNK % 8 == 0 && MLP_TC_KCHUNK <= 32, "chunk size");
+static_assert(((TC_ACT_BYTES + TC_WSTAGES * TC_WSTAGE_BYTES + TC_ZSTAGES * TC_ZSTAGE_BYTES) >> 4) + 3 * (2 * 3328 >> 4) < 0x4000, "descriptor start field");
 constexpr uint32_t TC_TMEM_COLS = 512, TC_D2_COL = 256;
 /* instruction descriptor (cute/arch/mma_sm100_desc.hpp InstrDescriptor): D = F32 (bits 4-5 = 1), A = B = TF32 (bits 7-9, 10-12 = 2),
  * both K-major (bits 15, 16 = 0), N >> 3 at bits 17-22, M >> 4 at bits 24-28 */
 constexpr uint32_t TC_IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(MLP_NPAD >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
 
 /* barrier slots (8 bytes each) */
-enum { BAR_WFULL = 0, BAR_WFREE = 3, BAR_ZFULL = 6, BAR_ZFREE = 8, BAR_GEMM = 10, BAR_ACT = 11, BAR_COUNT = 12 };
+enum { BAR_WFULL = 0, BAR_WFREE = BAR_WFULL + TC_WSTAGES, BAR_ZFULL = BAR_WFREE + TC_WSTAGES, BAR_ZFREE = BAR_ZFULL + TC_ZSTAGES,
+       BAR_GEMM = BAR_ZFREE + TC_ZSTAGES, BAR_ACT, BAR_COUNT };
+static_assert(BAR_COUNT * 8 + 8 <= 256, "barrier area");
 
 __device__ __forceinline__ uint32_t smemAddr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -316,12 +336,16 @@ __device__ __forceinline__ bool mbarTry(uint32_t bar, uint32_t parity)
     return ok != 0;
 }
 /* bounded wait: a protocol error must end the kernel with an error code, never hang the GPU */
-__device__ __forceinline__ bool mbarWait(uint32_t bar, uint32_t parity, volatile uint32_t* abortFlag)
+template <bool PROFILE>
+__device__ __forceinline__ bool mbarWait(uint32_t bar, uint32_t parity, volatile uint32_t* abortFlag, long long& waited)
 {
-    if (mbarTry(bar, parity)) return true;
-    const long long t0 = clock64();
+    if (!PROFILE && mbarTry(bar, parity)) return true;
+    const long long t0 = clock64(); /* try_wait itself may block for a while before it answers */
     for (;;) {
-        if (mbarTry(bar, parity)) return true;
+        if (mbarTry(bar, parity)) {
+            if (PROFILE) waited += clock64() - t0;
+            return true;
+        }
         if (*abortFlag) return false;
         if (clock64() - t0 > 2000000000ll) { /* ~1 s */
             *abortFlag = 1u;
@@ -330,20 +354,21 @@ __device__ __forceinline__ bool mbarWait(uint32_t bar, uint32_t parity, volatile
     }
 }
 
-__device__ __forceinline__ uint64_t ummaDesc(uint32_t saddr, uint32_t lbo)
-{
-    /* cute/arch/mma_sm100_desc.hpp SmemDescriptor: start >> 4 at bits 0-13, leading byte offset >> 4 at 16-29, stride byte offset >> 4
-     * at 32-45, version 1 at 46-47, layout type 0 (no swizzle) at 61-63 */
-    return (uint64_t)((saddr & 0x3ffffu) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(TC_SBO >> 4) << 32) | (1ull << 46);
-}
+/* shared-memory matrix descriptor (cute/arch/mma_sm100_desc.hpp SmemDescriptor): low word = start >> 4 at bits 0-13 and leading byte offset
+ * >> 4 at bits 16-29; high word = stride byte offset >> 4 at bits 0-13 (32-45 of the descriptor), version 1 at bit 14 (46); layout type 0
+ * (no swizzle) at bits 29-31 (61-63) */
+__device__ __forceinline__ uint32_t ummaDescLo(uint32_t saddr, uint32_t lbo) { return ((saddr & 0x3ffffu) >> 4) | ((lbo >> 4) << 16); }
+constexpr uint32_t TC_DESC_HI = (TC_SBO >> 4) | (1u << 14);
 
-__device__ __forceinline__ void ummaTf32(uint32_t tmemD, uint64_t descA, uint64_t descB, uint32_t accumulate)
+__device__ __forceinline__ void ummaTf32(uint32_t tmemD, uint32_t descALo, uint32_t descBLo, uint32_t accumulate)
 {
     asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(tmemD), "l"(descA), "l"(descB), "r"(TC_IDESC), "r"(accumulate)
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+        "mov.b64 da, {%1, %3};\n\t"
+        "mov.b64 db, {%2, %3};\n\t"
+        "setp.ne.b32 p, %5, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %4, p;\n\t}"
+        ::"r"(tmemD), "r"(descALo), "r"(descBLo), "r"(TC_DESC_HI), "r"(TC_IDESC), "r"(accumulate)
         : "memory");
 }
 __device__ __forceinline__ void ummaCommit(uint32_t bar)
@@ -351,7 +376,7 @@ __device__ __forceinline__ void ummaCommit(uint32_t bar)
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
 
-__device__ __forceinline__ void tmemLoad16(uint32_t taddr, uint32_t (&v)[16])
+__device__ __forceinline__ void tmemLoad(uint32_t taddr, uint32_t (&v)[16])
 {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
@@ -359,14 +384,35 @@ __device__ __forceinline__ void tmemLoad16(uint32_t taddr, uint32_t (&v)[16])
           "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
         : "r"(taddr)
         : "memory");
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
-__device__ __forceinline__ void tmemStore16(uint32_t taddr, const uint32_t (&v)[16])
+__device__ __forceinline__ void tmemLoad(uint32_t taddr, uint32_t (&v)[32])
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, "
+        "%21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]),
+          "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]),
+          "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]),
+          "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmemStore(uint32_t taddr, const uint32_t (&v)[16])
 {
     asm volatile(
         "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
         "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]),
         "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+        : "memory");
+}
+__device__ __forceinline__ void tmemStore(uint32_t taddr, const uint32_t (&v)[32])
+{
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, "
+        "%21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+        "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]),
+        "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]), "r"(v[18]), "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]),
+        "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
         : "memory");
 }
 
@@ -377,13 +423,47 @@ __device__ __forceinline__ float toTf32(float x)
     return __uint_as_float(u);
 }
 
+/* one piece of an epilogue: N accumulator columns of the thread's row, starting at col0 (a multiple of 16).  The bias is already in the
+ * accumulator (it rides in the GEMM), so this is relu + the write-back */
+template <int N>
+__device__ __forceinline__ void epiloguePiece(uint32_t tacc, int col0, int epilogue, unsigned char* actRow, const float* __restrict__ w4, float& y)
+{
+    uint32_t v[N];
+    tmemLoad(tacc + (uint32_t)col0, v);
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int q = 0; q < N / 4; ++q) {
+        const int col = col0 + 4 * q;
+        const float x0 = fmaxf(__uint_as_float(v[4 * q]), 0.0f), x1 = fmaxf(__uint_as_float(v[4 * q + 1]), 0.0f);
+        const float x2 = fmaxf(__uint_as_float(v[4 * q + 2]), 0.0f), x3 = fmaxf(__uint_as_float(v[4 * q + 3]), 0.0f);
+        if (epilogue == MLP_EPI_OUT) {
+            const float4 ww = __ldg(reinterpret_cast<const float4*>(w4 + col)); /* zero beyond column 200 */
+            y = fmaf(x0, ww.x, y);
+            y = fmaf(x1, ww.y, y);
+            y = fmaf(x2, ww.z, y);
+            y = fmaf(x3, ww.w, y);
+        } else {
+            v[4 * q] = __float_as_uint(x0);
+            v[4 * q + 1] = __float_as_uint(x1);
+            v[4 * q + 2] = __float_as_uint(x2);
+            v[4 * q + 3] = __float_as_uint(x3);
+            if (col < MLP_D)
+                *reinterpret_cast<float4*>(actRow + (uint32_t)(col / 4) * TC_A_LBO) = make_float4(toTf32(x0), toTf32(x1), toTf32(x2), toTf32(x3));
+        }
+    }
+    /* the post-activation value is the residual of the next block: the next MMAs accumulate on top of it */
+    if (epilogue == MLP_EPI_O) tmemStore(tacc + (uint32_t)col0, v);
+}
+
+template <bool PROFILE>
 __global__ void __launch_bounds__(TC_THREADS, 1)
     k_disney_mlp_tc(const float* __restrict__ in, const uint32_t* __restrict__ rowIndex, uint32_t nRows, const uint8_t* __restrict__ stream,
-                    const MlpChunk* __restrict__ chunksG, int nChunks, const float* __restrict__ bias, const float* __restrict__ w4b4,
-                    float* __restrict__ out, uint32_t* __restrict__ errorOut)
+                    const MlpChunk* __restrict__ chunksG, int nChunks, const float* __restrict__ w4b4, float* __restrict__ out,
+                    uint32_t* __restrict__ errorOut, unsigned long long* __restrict__ prof)
 {
     extern __shared__ __align__(1024) unsigned char smem[];
     unsigned char* actS = smem;
+    const long long tStart = clock64();
     MlpChunk* chunks = reinterpret_cast<MlpChunk*>(smem + TC_OFF_CHUNKS);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + TC_OFF_BAR);
     uint32_t* tmemSlot = reinterpret_cast<uint32_t*>(bars + BAR_COUNT);
@@ -392,7 +472,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     const uint32_t actAddr = smemAddr(actS);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-    for (int i = threadIdx.x; i < nChunks; i += TC_THREADS) chunks[i] = chunksG[i];
+    {
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(chunksG);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(chunks);
+        for (int i = threadIdx.x; i < nChunks * (int)(sizeof(MlpChunk) / 4); i += TC_THREADS) dst[i] = __ldg(src + i);
+    }
     if (threadIdx.x == 0) {
         for (int s = 0; s < TC_WSTAGES; ++s) {
             mbarInit(barBase + 8 * (BAR_WFULL + s), 1);
@@ -407,7 +491,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         *abortFlag = 0u;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 4) {
+    if (warp == TC_ISSUER_WARP) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smemAddr(tmemSlot)), "r"(TC_TMEM_COLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
@@ -416,210 +500,254 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmemBase = *tmemSlot;
 
-    if (warp == 4) {
-        /* ===== weight producer + MMA issuer: one thread ===== */
+    if (warp == TC_PRODUCER_WARP) {
+        /* ===== weight stream: one thread keeps every free stage filled ===== */
         if (lane == 0) {
-            auto loadWeights = [&](int c) {
-                const MlpChunk& ch = chunks[c];
-                const uint32_t bar = barBase + 8 * (BAR_WFULL + c % TC_WSTAGES);
-                mbarExpectTx(bar, ch.wBytes);
+            long long wFree = 0;
+            bool ok = true;
+            for (int c = 0; c < nChunks && ok; ++c) {
+                const int ws = c % TC_WSTAGES;
+                if (c >= TC_WSTAGES) ok = mbarWait<PROFILE>(barBase + 8 * (BAR_WFREE + ws), (uint32_t)(c / TC_WSTAGES - 1) & 1u, abortFlag, wFree);
+                if (!ok) break;
+                const uint32_t wOffset = chunks[c].wOffset, wBytes = chunks[c].wBytes;
+                const uint32_t bar = barBase + 8 * (BAR_WFULL + ws);
+                mbarExpectTx(bar, wBytes);
                 asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                                 actAddr + TC_OFF_W + (uint32_t)(c % TC_WSTAGES) * TC_WSTAGE_BYTES),
-                             "l"(stream + ch.wOffset), "r"(ch.wBytes), "r"(bar)
+                                 actAddr + TC_OFF_W + (uint32_t)ws * TC_WSTAGE_BYTES),
+                             "l"(stream + wOffset), "r"(wBytes), "r"(bar)
                              : "memory");
-            };
-            for (int c = 0; c < TC_WSTAGES - 1 && c < nChunks; ++c) loadWeights(c);
+            }
+            if (!ok) *abortFlag = 1u;
+            if (PROFILE && prof && blockIdx.x == 0) prof[1] = (unsigned long long)wFree; /* producer: waiting for a free weight stage */
+        }
+    } else if (warp == TC_ISSUER_WARP) {
+        /* ===== MMA issuer: one thread ===== */
+        if (lane == 0) {
             uint32_t actWaits = 0, zUses = 0;
             bool ok = true;
+            long long wAct = 0, wZ = 0, wW = 0; /* cycles spent waiting, by cause (PROFILE) */
             for (int c = 0; c < nChunks && ok; ++c) {
                 const MlpChunk ch = chunks[c];
                 const int ws = c % TC_WSTAGES;
                 if (ch.flags & MLP_WAIT_ACT) {
-                    ok = mbarWait(barBase + 8 * BAR_ACT, actWaits & 1u, abortFlag);
+                    ok = mbarWait<PROFILE>(barBase + 8 * BAR_ACT, actWaits & 1u, abortFlag, wAct);
                     actWaits++;
                 }
                 const int zs = (int)(zUses % TC_ZSTAGES);
-                if (ok && ch.src == 1) ok = mbarWait(barBase + 8 * (BAR_ZFULL + zs), (zUses / TC_ZSTAGES) & 1u, abortFlag);
-                if (ok) ok = mbarWait(barBase + 8 * (BAR_WFULL + ws), (uint32_t)(c / TC_WSTAGES) & 1u, abortFlag);
+                if (ok && ch.src == 1) ok = mbarWait<PROFILE>(barBase + 8 * (BAR_ZFULL + zs), (zUses / TC_ZSTAGES) & 1u, abortFlag, wZ);
+                if (ok) ok = mbarWait<PROFILE>(barBase + 8 * (BAR_WFULL + ws), (uint32_t)(c / TC_WSTAGES) & 1u, abortFlag, wW);
                 if (!ok) break;
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t aBase = ch.src == 1 ? actAddr + TC_OFF_Z + (uint32_t)zs * TC_ZSTAGE_BYTES : actAddr + (uint32_t)ch.aKGroup * TC_A_LBO;
-                const uint32_t bBase = actAddr + TC_OFF_W + (uint32_t)ws * TC_WSTAGE_BYTES;
+                const uint32_t aLo = ummaDescLo(ch.src == 1 ? actAddr + TC_OFF_Z + (uint32_t)zs * TC_ZSTAGE_BYTES : actAddr + (uint32_t)ch.aKGroup * TC_A_LBO, TC_A_LBO);
+                const uint32_t bLo = ummaDescLo(actAddr + TC_OFF_W + (uint32_t)ws * TC_WSTAGE_BYTES, B_LBO);
                 const uint32_t d = tmemBase + (ch.dst ? TC_D2_COL : 0u);
-                for (int j = 0; j < ch.k8; ++j)
-                    ummaTf32(d, ummaDesc(aBase + (uint32_t)j * 2u * TC_A_LBO, TC_A_LBO), ummaDesc(bBase + (uint32_t)j * 2u * B_LBO, B_LBO),
-                             ((ch.flags & MLP_FIRST) && j == 0) ? 0u : 1u);
+                const int k8 = ch.k8;
+                /* one MMA per 8 k values: two 4-float K groups of each operand, i.e. 2 * LBO bytes further per step */
+                ummaTf32(d, aLo, bLo, (ch.flags & MLP_FIRST) ? 0u : 1u);
+                if (k8 > 1) ummaTf32(d, aLo + (2u * TC_A_LBO >> 4), bLo + (2u * B_LBO >> 4), 1u);
+                if (k8 > 2) ummaTf32(d, aLo + 2u * (2u * TC_A_LBO >> 4), bLo + 2u * (2u * B_LBO >> 4), 1u);
+                if (k8 > 3) ummaTf32(d, aLo + 3u * (2u * TC_A_LBO >> 4), bLo + 3u * (2u * B_LBO >> 4), 1u);
                 ummaCommit(barBase + 8 * (BAR_WFREE + ws));
                 if (ch.src == 1) {
                     ummaCommit(barBase + 8 * (BAR_ZFREE + zs));
                     zUses++;
                 }
                 if (ch.flags & MLP_LAST) ummaCommit(barBase + 8 * BAR_GEMM);
-                /* refill the stage chunk c - 1 used with chunk c + 2 */
-                const int p = c + TC_WSTAGES - 1;
-                if (p < nChunks) {
-                    if (p >= TC_WSTAGES) ok = mbarWait(barBase + 8 * (BAR_WFREE + p % TC_WSTAGES), (uint32_t)(p / TC_WSTAGES - 1) & 1u, abortFlag);
-                    if (ok) loadWeights(p);
-                }
             }
             if (!ok) *abortFlag = 1u;
+            if (PROFILE && prof && blockIdx.x == 0) {
+                prof[0] = (unsigned long long)(clock64() - tStart); /* issuer: total, then waits for the previous epilogue, a staged */
+                prof[2] = (unsigned long long)wAct;                 /* descriptor chunk, a landed weight chunk */
+                prof[3] = (unsigned long long)wZ;
+                prof[4] = (unsigned long long)wW;
+            }
         }
     } else {
         /* ===== workers: stage descriptor layers, run the epilogues ===== */
-        const int t = threadIdx.x;
+        const int t = threadIdx.x & (TC_M - 1), half = threadIdx.x / TC_M;
         const uint32_t row = blockIdx.x * TC_M + t;
         const bool valid = row < nRows;
         const size_t srcRow = valid ? (rowIndex ? (size_t)rowIndex[row] : (size_t)row) : 0;
         const float* inRow = in + srcRow * (MLP_NB * MLP_ZD);
         const uint32_t rowOff = (uint32_t)(t / 8) * TC_SBO + (uint32_t)(t % 8) * 16u; /* the row's 16 bytes inside a K group */
-        const uint32_t tmemRow = tmemBase + ((uint32_t)(warp * 32) << 16);
+        const uint32_t tmemRow = tmemBase + ((uint32_t)((warp & 3) * 32) << 16);
+        /* the constant-one columns 200, 201 that carry the biases through the GEMMs; 202..207 are padding */
+        if (half == 0) {
+            *reinterpret_cast<float4*>(actS + (uint32_t)(MLP_D / 4) * TC_A_LBO + rowOff) = make_float4(1.0f, 1.0f, 0.0f, 0.0f);
+            *reinterpret_cast<float4*>(actS + (uint32_t)(MLP_D / 4 + 1) * TC_A_LBO + rowOff) = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        }
         uint32_t zFills = 0, gemmWaits = 0;
         bool ok = true;
+        long long wZFree = 0, wGemm = 0, tEpi = 0, tFill = 0;
+        /* descriptor chunks of this row are fetched into registers three chunks ahead of their staging step (zA is the next one to stage,
+         * zB and zC follow), and the row's next layer is pulled into L2 a whole block ahead: the global-memory latency hides behind the MMAs,
+         * the epilogues and two other staging steps */
+        constexpr int ZH = MLP_TC_KCHUNK / 2; /* k values of a chunk per worker half */
+        float2 zA[ZH / 2], zB[ZH / 2], zC[ZH / 2];
+        int zCursor = 0; /* first chunk of the table not yet looked at by fetchZ */
+        auto fetchZ = [&](float2 (&zr)[ZH / 2]) {
+            int c = zCursor;
+            while (c < nChunks && chunks[c].src != 1) ++c;
+            zCursor = c + 1;
+            if (c >= nChunks) return;
+            const int k0 = (int)chunks[c].aKGroup + half * ZH, layer = (int)chunks[c].layer;
+            const float* src = inRow + layer * MLP_ZD + k0;
+#pragma unroll
+            for (int i = 0; i < ZH / 2; ++i) {
+                const int k = k0 + 2 * i;
+                zr[i] = make_float2(0.f, 0.f);
+                if (k == MLP_ZD) zr[i] = make_float2(1.0f, 1.0f); /* z[226] = z[227] = 1: the bias columns */
+                if (valid && k < MLP_ZD) zr[i] = __ldg(reinterpret_cast<const float2*>(src + 2 * i));
+            }
+            if (valid && half == 0 && chunks[c].aKGroup == 0 && layer + 1 < MLP_NB) {
+                const char* nextLayer = reinterpret_cast<const char*>(inRow + (layer + 1) * MLP_ZD);
+#pragma unroll
+                for (int off = 0; off < MLP_ZD * 4 + 128; off += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(nextLayer + off));
+            }
+        };
+        fetchZ(zA);
+        fetchZ(zB);
+        fetchZ(zC);
         for (int c = 0; c < nChunks && ok; ++c) {
             const MlpChunk ch = chunks[c];
             if (ch.src == 1) {
                 const int zs = (int)(zFills % TC_ZSTAGES);
                 bool mine = true;
-                if (zFills >= TC_ZSTAGES) mine = mbarWait(barBase + 8 * (BAR_ZFREE + zs), (zFills / TC_ZSTAGES - 1) & 1u, abortFlag);
+                if (zFills >= TC_ZSTAGES) mine = mbarWait<PROFILE>(barBase + 8 * (BAR_ZFREE + zs), (zFills / TC_ZSTAGES - 1) & 1u, abortFlag, wZFree);
+                const long long tf0 = PROFILE ? clock64() : 0;
                 ok = __all_sync(0xffffffffu, mine);
                 if (!ok) break;
-                unsigned char* zst = smem + TC_OFF_Z + (uint32_t)zs * TC_ZSTAGE_BYTES + rowOff;
-                const float* src = inRow + (int)ch.layer * MLP_ZD + (int)ch.aKGroup;
-                for (int kg = 0; kg < 2 * ch.k8; ++kg) {
-                    const int k = (int)ch.aKGroup + 4 * kg;
-                    float2 lo = make_float2(0.f, 0.f), hi = make_float2(0.f, 0.f);
-                    if (valid && k < MLP_ZD) lo = __ldg(reinterpret_cast<const float2*>(src + 4 * kg));
-                    if (valid && k + 2 < MLP_ZD) hi = __ldg(reinterpret_cast<const float2*>(src + 4 * kg + 2));
-                    *reinterpret_cast<float4*>(zst + (uint32_t)kg * TC_A_LBO) = make_float4(toTf32(lo.x), toTf32(lo.y), toTf32(hi.x), toTf32(hi.y));
-                }
+                unsigned char* zst = smem + TC_OFF_Z + (uint32_t)zs * TC_ZSTAGE_BYTES + rowOff + (uint32_t)(half * (ZH / 4)) * TC_A_LBO;
+#pragma unroll
+                for (int kg = 0; kg < ZH / 4; ++kg)
+                    if (half * (ZH / 4) + kg < 2 * ch.k8)
+                        *reinterpret_cast<float4*>(zst + (uint32_t)kg * TC_A_LBO) =
+                            make_float4(toTf32(zA[2 * kg].x), toTf32(zA[2 * kg].y), toTf32(zA[2 * kg + 1].x), toTf32(zA[2 * kg + 1].y));
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); /* generic-proxy stores -> the tensor core's async-proxy reads */
                 mbarArrive(barBase + 8 * (BAR_ZFULL + zs));
                 zFills++;
+#pragma unroll
+                for (int i = 0; i < ZH / 2; ++i) {
+                    zA[i] = zB[i];
+                    zB[i] = zC[i];
+                }
+                fetchZ(zC);
+                if (PROFILE) tFill += clock64() - tf0;
             }
             if (ch.flags & MLP_LAST) {
-                const bool mine = mbarWait(barBase + 8 * BAR_GEMM, gemmWaits & 1u, abortFlag);
+                const bool mine = mbarWait<PROFILE>(barBase + 8 * BAR_GEMM, gemmWaits & 1u, abortFlag, wGemm);
+                const long long te0 = PROFILE ? clock64() : 0;
                 gemmWaits++;
                 ok = __all_sync(0xffffffffu, mine);
                 if (!ok) break;
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t tacc = tmemRow + (ch.dst ? TC_D2_COL : 0u);
-                const float* b = bias + (size_t)ch.gemm * MLP_NPAD;
+                const int epilogue = ch.epilogue;
                 float y = 0.0f;
+                const int colBegin = half * TC_HALF_COLS;
 #pragma unroll 1
-                for (int g = 0; g < MLP_NPAD / 16; ++g) {
-                    uint32_t v[16];
-                    tmemLoad16(tacc + (uint32_t)g * 16u, v);
-                    float x[16];
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) x[j] = fmaxf(__uint_as_float(v[j]) + __ldg(b + g * 16 + j), 0.0f);
-                    if (ch.epilogue == MLP_EPI_OUT) {
-#pragma unroll
-                        for (int j = 0; j < 16; ++j)
-                            if (g * 16 + j < MLP_D) y = fmaf(x[j], __ldg(w4b4 + g * 16 + j), y);
-                    } else {
-                        if (ch.epilogue == MLP_EPI_O) {
-                            /* the post-activation value is the residual of the next block: the next MMAs accumulate on top of it */
-#pragma unroll
-                            for (int j = 0; j < 16; ++j) v[j] = __float_as_uint(x[j]);
-                            tmemStore16(tacc + (uint32_t)g * 16u, v);
-                        }
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            const int kg = g * 4 + q;
-                            if (kg < MLP_D / 4)
-                                *reinterpret_cast<float4*>(actS + (uint32_t)kg * TC_A_LBO + rowOff) =
-                                    make_float4(toTf32(x[4 * q]), toTf32(x[4 * q + 1]), toTf32(x[4 * q + 2]), toTf32(x[4 * q + 3]));
-                        }
+                for (int p = 0; p < 3; ++p) epiloguePiece<32>(tacc, colBegin + 32 * p, epilogue, actS + rowOff, w4b4, y);
+                if (half == 0) epiloguePiece<16>(tacc, 96, epilogue, actS + rowOff, w4b4, y);
+                if (epilogue == MLP_EPI_OUT) {
+                    /* the two halves of a row meet in shared memory (the descriptor stages are idle by now) */
+                    float* partial = reinterpret_cast<float*>(smem + TC_OFF_Z);
+                    if (half == 1) partial[t] = y;
+                    asm volatile("bar.sync 1, %0;" ::"n"(TC_WORKERS) : "memory");
+                    if (half == 0) {
+                        y += partial[t] + __ldg(w4b4 + MLP_NPAD);
+                        if (valid) out[srcRow] = y > 0.0f ? y : 0.01f * y; /* torch.nn.LeakyReLU default slope */
                     }
-                }
-                if (ch.epilogue == MLP_EPI_OUT) {
-                    y += __ldg(w4b4 + MLP_D);
-                    if (valid) out[srcRow] = y > 0.0f ? y : 0.01f * y; /* torch.nn.LeakyReLU default slope */
                 } else {
-                    if (ch.epilogue == MLP_EPI_O) asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                    if (epilogue == MLP_EPI_O) asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                     mbarArrive(barBase + 8 * BAR_ACT);
                 }
+                if (PROFILE) tEpi += clock64() - te0;
             }
         }
         if (!ok) *abortFlag = 1u;
+        if (PROFILE && prof && blockIdx.x == 0 && threadIdx.x == 0) {
+            prof[8] = (unsigned long long)(clock64() - tStart); /* worker 0: total, waits for a free descriptor stage and for a GEMM, */
+            prof[9] = (unsigned long long)wZFree;               /* time inside the epilogues and inside the descriptor staging */
+            prof[10] = (unsigned long long)wGemm;
+            prof[11] = (unsigned long long)tEpi;
+            prof[12] = (unsigned long long)tFill;
+        }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (threadIdx.x == 0 && *abortFlag) atomicExch(errorOut, 1u + blockIdx.x);
-    if (warp == 4) {
+    if (warp == TC_ISSUER_WARP) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmemBase), "r"(TC_TMEM_COLS) : "memory");
     }
 }
 
-cudaError_t launchDisneyMlpTc(const DisneyModelDev& m, const float* in, const uint32_t* rowIndex, uint32_t nRows, float* out, cudaStream_t st)
+cudaError_t launchDisneyMlpTc(const DisneyModelDev& m, const float* in, const uint32_t* rowIndex, uint32_t nRows, float* out, cudaStream_t st,
+                              unsigned long long* prof)
 {
     if (nRows == 0) return cudaSuccess;
     if (m.nChunks > TC_MAX_CHUNKS) return cudaErrorInvalidValue;
-    cudaError_t e = cudaFuncSetAttribute(k_disney_mlp_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM);
-    if (e != cudaSuccess) return e;
-    k_disney_mlp_tc<<<(nRows + TC_M - 1) / TC_M, TC_THREADS, TC_SMEM, st>>>(in, rowIndex, nRows, m.stream, m.chunks, m.nChunks, m.bias, m.w4b4, out,
-                                                                          m.error);
+    const unsigned blocks = (nRows + TC_M - 1) / TC_M;
+    cudaError_t e;
+    if (prof) {
+        e = cudaFuncSetAttribute(k_disney_mlp_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM);
+        if (e != cudaSuccess) return e;
+        k_disney_mlp_tc<true><<<blocks, TC_THREADS, TC_SMEM, st>>>(in, rowIndex, nRows, m.stream, m.chunks, m.nChunks, m.w4b4, out, m.error, prof);
+    } else {
+        e = cudaFuncSetAttribute(k_disney_mlp_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM);
+        if (e != cudaSuccess) return e;
+        k_disney_mlp_tc<false><<<blocks, TC_THREADS, TC_SMEM, st>>>(in, rowIndex, nRows, m.stream, m.chunks, m.nChunks, m.w4b4, out, m.error, nullptr);
+    }
     return cudaGetLastError();
 }
 
 /* ------------------------------------------------------------------------------------------------ renderRect glue */
 
-/* one block: ordered compaction of the rows with active[i] != 0 */
-__global__ void __launch_bounds__(1024) k_compact_active(const uint8_t* __restrict__ active, uint32_t n, uint32_t* __restrict__ idx,
-                                                         uint32_t* __restrict__ count)
+/* compaction of the rows with active[i] != 0: idx[0..*count) (count zeroed by the caller).  One warp-aggregated atomic per warp:
+ * the order of idx depends on scheduling, the set does not (and the model's rows are independent of each other) */
+__global__ void __launch_bounds__(256) k_compact_active(const uint8_t* __restrict__ active, uint32_t n, uint32_t* __restrict__ idx,
+                                                        uint32_t* __restrict__ count)
 {
-    __shared__ uint32_t warpSum[32];
-    __shared__ uint32_t base;
-    if (threadIdx.x == 0) base = 0;
-    __syncthreads();
-    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-    for (uint32_t i0 = 0; i0 < n; i0 += blockDim.x) {
-        const uint32_t i = i0 + threadIdx.x;
-        const bool a = i < n && active[i] != 0;
-        const unsigned m = __ballot_sync(0xffffffffu, a);
-        if (lane == 0) warpSum[warp] = (uint32_t)__popc(m);
-        __syncthreads();
-        uint32_t before = 0, total = 0;
-        for (unsigned w = 0; w < (blockDim.x >> 5); ++w) {
-            if (w < warp) before += warpSum[w];
-            total += warpSum[w];
-        }
-        if (a) idx[base + before + (uint32_t)__popc(m & ((1u << lane) - 1u))] = i;
-        __syncthreads();
-        if (threadIdx.x == 0) base += total;
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) *count = base;
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool a = i < n && active[i] != 0;
+    const unsigned m = __ballot_sync(0xffffffffu, a);
+    if (m == 0u) return;
+    const unsigned lane = threadIdx.x & 31u;
+    const int leader = __ffs(m) - 1;
+    uint32_t base = 0;
+    if ((int)lane == leader) base = atomicAdd(count, (uint32_t)__popc(m));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (a) idx[base + (uint32_t)__popc(m & ((1u << lane) - 1u))] = i;
 }
 
 cudaError_t launchCompactActive(const uint8_t* active, uint32_t n, uint32_t* idx, uint32_t* count, cudaStream_t st)
 {
-    k_compact_active<<<1, 1024, 0, st>>>(active, n, idx, count);
+    cudaError_t e = cudaMemsetAsync(count, 0, sizeof(uint32_t), st);
+    if (e != cudaSuccess) return e;
+    if (n == 0) return cudaSuccess;
+    k_compact_active<<<(n + 255) / 256, 256, 0, st>>>(active, n, idx, count);
     return cudaGetLastError();
 }
 
-/* CU/disneyCamera.cu:38-46: frameResult[pixel] = (make_float4(predicted) + make_float4(radiance)) * (1 - transmittance) */
-__global__ void k_blit_predicted(const float* __restrict__ predicted, const float* __restrict__ info, uint32_t frameW, uint32_t rectX, uint32_t rectY,
-                                 uint32_t rectW, uint32_t n, float4* __restrict__ frameResult)
+/* CU/disneyCamera.cu:38-46: frameResult[pixel] = (make_float4(predicted) + make_float4(radiance)) * (1 - transmittance) for the n compacted
+ * rows; row i is frame pixel idx[i], info is indexed by the frame pixel */
+__global__ void k_blit_predicted(const float* __restrict__ predicted, const float* __restrict__ info, const uint32_t* __restrict__ idx, uint32_t n,
+                                 float4* __restrict__ frameResult)
 {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const float* f = info + (size_t)i * 5; /* DsIntersectionInfo: radiance rgb, transmittance, hasScattered */
-    if (__float_as_uint(f[4]) == 0u) return;
-    const uint32_t x = i % rectW, y = i / rectW;
+    const uint32_t pixel = idx[i];
+    const float* f = info + (size_t)pixel * 5; /* DsIntersectionInfo: radiance rgb, transmittance, hasScattered */
     const float w = 1.0f - f[3], p = predicted[i];
-    frameResult[(size_t)(y + rectY) * frameW + (x + rectX)] = make_float4((p + f[0]) * w, (p + f[1]) * w, (p + f[2]) * w, (p + 0.0f) * w);
+    frameResult[pixel] = make_float4((p + f[0]) * w, (p + f[1]) * w, (p + f[2]) * w, (p + 0.0f) * w);
 }
 
-cudaError_t launchBlitPredicted(const float* predicted, const float* info, uint32_t frameW, uint32_t frameH, uint32_t rectX, uint32_t rectY, uint32_t rectW,
-                                uint32_t rectH, float4* frameResult, cudaStream_t st)
+cudaError_t launchBlitPredicted(const float* predicted, const float* info, const uint32_t* idx, uint32_t n, float4* frameResult, cudaStream_t st)
 {
-    (void)frameH;
-    const uint32_t n = rectW * rectH;
-    k_blit_predicted<<<(n + 255) / 256, 256, 0, st>>>(predicted, info, frameW, rectX, rectY, rectW, n, frameResult);
+    if (n == 0) return cudaSuccess;
+    k_blit_predicted<<<(n + 255) / 256, 256, 0, st>>>(predicted, info, idx, n, frameResult);
     return cudaGetLastError();
 }
 

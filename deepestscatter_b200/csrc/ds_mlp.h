@@ -22,6 +22,7 @@ constexpr int MLP_D = 200;      /* DisneyModel.BLOCK_DIMENSION */
 constexpr int MLP_NB = 10;      /* DisneyModel.BLOCK_COUNT */
 constexpr int MLP_ZD = 226;     /* DESCRIPTOR_LAYER_WITH_ANGLE_DIMENSION */
 constexpr int MLP_NPAD = 208;   /* output width padded to a multiple of 16 (UMMA N for M = 128) */
+constexpr int MLP_TC_KCHUNK = 32; /* K values per weight chunk of the tensor-core kernel's stream (four MMA steps) */
 constexpr int MLP_GEMMS = 22;   /* 2 per block + fullyConnected.0 + fullyConnected.2 */
 constexpr size_t MLP_WEIGHT_COUNT = (size_t)MLP_NB * (MLP_D * MLP_ZD + MLP_D + 2 * (MLP_D * MLP_D + MLP_D)) + 2 * (MLP_D * MLP_D + MLP_D) + MLP_D + 1;
 
@@ -29,7 +30,7 @@ constexpr size_t MLP_WEIGHT_COUNT = (size_t)MLP_NB * (MLP_D * MLP_ZD + MLP_D + 2
 struct MlpChunk {
     uint32_t wOffset;  /* byte offset of the chunk's weights in the packed stream */
     uint32_t wBytes;   /* (k8 * 2) * MLP_NPAD * 16 */
-    uint16_t k8;       /* number of K = 8 MMA steps in the chunk (1..4) */
+    uint16_t k8;       /* number of K = 8 MMA steps in the chunk (1..MLP_TC_KCHUNK / 8) */
     uint16_t aKGroup;  /* src 0: first 4-float K group of the activation buffer; src 1: first k of the descriptor layer */
     uint8_t src;       /* 0 = activation buffer, 1 = descriptor layer (z) */
     uint8_t layer;     /* src 1: descriptor layer index */
@@ -47,11 +48,12 @@ enum { MLP_EPI_H = 1 /* relu -> activation buffer */, MLP_EPI_O = 2 /* relu -> a
 struct DisneyModelDev {
     float* wT = nullptr;       /* fp32 kernel: per GEMM W^T [K][200] (K = 426 for the first GEMM of a block: o rows, then z rows) */
     float* bias = nullptr;     /* [22][208]; the two biases of a block's first GEMM are pre-summed */
-    float* w4b4 = nullptr;     /* fullyConnected.4: 200 weights + bias */
+    float* w4b4 = nullptr;     /* fullyConnected.4: 200 weights, zero padding to 208, bias at [208] */
     uint8_t* stream = nullptr; /* tensor-core kernel: weights in UMMA canonical K-major layout, in consumption order */
     MlpChunk* chunks = nullptr;
     int nChunks = 0;
     uint32_t* error = nullptr; /* device word: non-zero if a barrier wait of the tensor-core kernel timed out */
+    unsigned long long* prof = nullptr; /* 16 words: cycle accounting of block 0 of the last tensor-core launch (profile_events) */
     bool loaded = false;
 };
 
@@ -66,11 +68,13 @@ void packDisneyModel(const float* weights, DisneyModelHost& out);
 /* in: [nRowsTotal][10][226] floats on the device; rowIndex (may be NULL): the nRows input rows to evaluate (gather);
  * out[rowIndex[i]] (or out[i]) receives the prediction */
 cudaError_t launchDisneyMlpF32(const DisneyModelDev& m, const float* in, const uint32_t* rowIndex, uint32_t nRows, float* out, cudaStream_t st);
-cudaError_t launchDisneyMlpTc(const DisneyModelDev& m, const float* in, const uint32_t* rowIndex, uint32_t nRows, float* out, cudaStream_t st);
-/* rows of the rectangle that scattered, compacted in order: idx[0..*count) */
+/* prof (may be NULL): 16 device words; block 0 leaves its cycle accounting there (issuer: [0] total, [1..4] waits; worker 0: [8] total,
+ * [9..12] waits / epilogue / staging) */
+cudaError_t launchDisneyMlpTc(const DisneyModelDev& m, const float* in, const uint32_t* rowIndex, uint32_t nRows, float* out, cudaStream_t st,
+                              unsigned long long* prof = nullptr);
+/* indices of the rows with active[i] != 0: idx[0..*count), unordered */
 cudaError_t launchCompactActive(const uint8_t* active, uint32_t n, uint32_t* idx, uint32_t* count, cudaStream_t st);
-/* copyToFrameResult (CU/disneyCamera.cu:38-46) on the device */
-cudaError_t launchBlitPredicted(const float* predicted, const float* info, uint32_t frameW, uint32_t frameH, uint32_t rectX, uint32_t rectY,
-                                uint32_t rectW, uint32_t rectH, float4* frameResult, cudaStream_t st);
+/* copyToFrameResult (CU/disneyCamera.cu:38-46) on the device for n compacted rows: row i is frame pixel idx[i] */
+cudaError_t launchBlitPredicted(const float* predicted, const float* info, const uint32_t* idx, uint32_t n, float4* frameResult, cudaStream_t st);
 
 } // namespace dsk

@@ -247,6 +247,12 @@ int ds_disney_model_pack(const float* weights, size_t count, void* stream_out, s
  * predicted_out [n] (radiance for a sun of 1e6).  DS_PRECISION_EXACT: fp32 FMA kernel; DS_PRECISION_FAST: tcgen05 kind::tf32 tensor-core
  * kernel (inputs and activations rounded to tf32, fp32 accumulation and residual path) */
 int ds_disney_model_forward(DsContext* ctx, const float* network_input, uint32_t n, float* predicted_out);
+/* Introspection: cycle accounting of block 0 of the last tensor-core model launch made with option "profile_events" = 2 (an instrumented
+ * build of the kernel) -- SM clock cycles; [0] MMA-issuing thread: total, [1] weight producer: waiting for a free weight stage, [2] issuer
+ * waiting for the previous epilogue, [3] for a staged descriptor
+ * chunk, [4] for a weight chunk to land; [8] worker thread 0: total, [9] waiting for a free descriptor stage, [10] for a GEMM to finish,
+ * [11] inside the epilogues, [12] inside the descriptor staging; the rest 0. */
+int ds_disney_model_profile(DsContext* ctx, uint64_t* cycles16);
 /* DisneyRenderer::render (DisneyRenderer.cpp:58-110): every 128 x 128 rectangle of the frame (x outer, y inner; clipped at the frame
  * edge) -> network-input launch, the model on the pixels that scattered, copyToFrameResult.  Rectangle k uses RNG stream
  * `stream + k` (clock() in the reference).  frame_result_out: float4 [frame_height][frame_width], zero where nothing scattered;

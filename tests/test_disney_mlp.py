@@ -201,13 +201,16 @@ def test_tensor_core_program_emulated_on_cpu(built_library, weights, inputs):
     within the tf32 rounding of the weights (activations are not rounded here)."""
     assert CHUNK_DTYPE.itemsize == 20
     stream, chunks = packed_program(built_library, weights)
-    assert len(chunks) <= 256 and chunks["wOffset"][0] == 0 and np.all(chunks["wBytes"] == chunks["k8"].astype(np.uint32) * 2 * 26 * 128)
+    assert len(chunks) <= 1024 and chunks["wOffset"][0] == 0 and np.all(chunks["wBytes"] == chunks["k8"].astype(np.uint32) * 2 * 26 * 128)
     assert np.all(np.diff(chunks["wOffset"].astype(np.int64)) == chunks["wBytes"][:-1])  # consumption order, no gaps
     assert chunks["wOffset"][-1] + chunks["wBytes"][-1] == stream.size and np.all(chunks["wOffset"] % 16 == 0)
     n = 24
-    x = inputs[:n].astype(np.float64)
+    x = np.zeros((n, 10, 232))
+    x[:, :, :226] = inputs[:n]
+    x[:, :, 226:228] = 1.0  # the kernel stages z[226] = z[227] = 1: the bias columns of a block's first GEMM
     words = stream.view(np.float32)
-    act = np.zeros((n, 200))
+    act = np.zeros((n, 208))
+    act[:, 200:202] = 1.0  # the constant-one columns of the activation buffer
     D = [np.zeros((n, 208)), np.zeros((n, 208))]
     unflat = dm.unflatten(weights)
     out = None
@@ -218,29 +221,22 @@ def test_tensor_core_program_emulated_on_cpu(built_library, weights, inputs):
         W = words[(int(ch["wOffset"]) + off) // 4].astype(np.float64)  # [208][kc]
         assert np.all(W[200:] == 0)
         if ch["src"] == 1:
-            A = np.zeros((n, kc))
             k0 = int(ch["aK"])
-            hi = min(226, k0 + kc)
-            A[:, : hi - k0] = x[:, int(ch["layer"]), k0:hi]
+            assert k0 + kc <= 232
+            A = x[:, int(ch["layer"]), k0 : k0 + kc]
         else:
             k0 = int(ch["aK"]) * 4
-            assert k0 + kc <= 200
+            assert k0 + kc <= 208
             A = act[:, k0 : k0 + kc]
         d = int(ch["dst"])
         D[d] = A @ W.T if ch["flags"] & 1 else D[d] + A @ W.T
         if ch["flags"] & 2:
-            g = int(ch["gemm"])
-            if g < 20:
-                pre = f"blocks.{g // 2}."
-                bias = (unflat[pre + "f1o.bias"] + unflat[pre + "f1z.bias"]) if g % 2 == 0 else unflat[pre + "f2.bias"]
-            else:
-                bias = unflat["fullyConnected.0.bias"] if g == 20 else unflat["fullyConnected.2.bias"]
-            v = np.maximum(D[d][:, :200] + bias.astype(np.float64), 0.0)
+            v = np.maximum(D[d][:, :200], 0.0)  # the bias is already in the accumulator
             if ch["epilogue"] == 3:
                 y = v @ unflat["fullyConnected.4.weight"][0].astype(np.float64) + float(unflat["fullyConnected.4.bias"][0])
                 out = np.where(y > 0, y, 0.01 * y)
             else:
-                act = v
+                act[:, :200] = v
                 if ch["epilogue"] == 2:
                     D[d][:, :200] = v  # the residual of the next block stays in the accumulator
     assert out is not None

@@ -34,6 +34,11 @@ def main():
             best = min(us[1:])
             print(json.dumps({"kernel": name, "rows": n, "us": us, "best_us": best, "tflops": 2 * MACS_PER_ROW * n / (best * 1e-6) / 1e12,
                               "rows_per_s": n / (best * 1e-6)}), flush=True)
+            if prec == ds.PRECISION_FAST:
+                ctx.set_option("profile_events", 2)  # instrumented kernel: where block 0 spends its cycles
+                ctx.disney_model_forward(x)
+                print(json.dumps({"block0_cycles": ctx.disney_model_profile(), "instrumented_us": ctx.get_option("mlp_last_us")}), flush=True)
+                ctx.set_option("profile_events", 1)
         a, b = outs["exact_f32_fma"], outs["fast_tcgen05_tf32"]
         print(json.dumps({"max_rel_diff_fast_vs_exact": float(np.max(np.abs(a - b) / (np.abs(a) + 1e-6)))}))
 
