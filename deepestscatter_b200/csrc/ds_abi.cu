@@ -38,6 +38,8 @@ struct DsContext {
     bool baked = false;
     cudaArray_t densityArr = nullptr, inscatterArr = nullptr;
     cudaTextureObject_t densityTex = 0, inscatterTex = 0;
+    cudaMipmappedArray_t densityMip = nullptr; /* the whole mip chain as one mip-mapped array (FAST descriptor gather of the neural renderer) */
+    cudaTextureObject_t densityMipTex = 0;
     uint32_t* occ = nullptr;
     uint8_t* cellDist = nullptr;
     int occShift = 0, ocx = 0, ocy = 0, ocz = 0, occWords = 0;
@@ -154,6 +156,10 @@ static void freeVolume(DsContext* ctx)
     if (ctx->densityTex) cudaDestroyTextureObject(ctx->densityTex);
     if (ctx->inscatterTex) cudaDestroyTextureObject(ctx->inscatterTex);
     ctx->densityTex = ctx->inscatterTex = 0;
+    if (ctx->densityMipTex) cudaDestroyTextureObject(ctx->densityMipTex);
+    ctx->densityMipTex = 0;
+    if (ctx->densityMip) cudaFreeMipmappedArray(ctx->densityMip);
+    ctx->densityMip = nullptr;
     if (ctx->densityArr) cudaFreeArray(ctx->densityArr);
     if (ctx->inscatterArr) cudaFreeArray(ctx->inscatterArr);
     ctx->densityArr = ctx->inscatterArr = nullptr;
@@ -232,6 +238,61 @@ static int makeTexture(DsContext* ctx, const uint8_t* linear, int nx, int ny, in
     td.readMode = cudaReadModeNormalizedFloat;
     td.normalizedCoords = 1;
     DS_CUDA(ctx, cudaCreateTextureObject(tex, &rd, &td, nullptr));
+    return DS_OK;
+}
+
+/* rtTex3DLod's texture (DisneyDescriptor.cuh:38-42; sampler of VDBCloud.cpp:119-137 with the mip chain of Resources.cpp:169-209): the u8 levels
+ * this library built, copied into one mip-mapped array; trilinear within a level, linear between levels, clamp, normalised.  Built on first
+ * use, dropped with the volume. */
+static int ensureMipTexture(DsContext* ctx)
+{
+    if (ctx->densityMipTex) return DS_OK;
+    const int count = (int)ctx->levels.size();
+    if (count < 1) DS_FAIL(ctx, DS_ERR_STATE, "no volume");
+    cudaChannelFormatDesc cd = cudaCreateChannelDesc<unsigned char>();
+    DS_CUDA(ctx, cudaMallocMipmappedArray(&ctx->densityMip, &cd, make_cudaExtent(ctx->lnx[0], ctx->lny[0], ctx->lnz[0]), (unsigned)count));
+    for (int l = 0; l < count; ++l) {
+        cudaArray_t level = nullptr;
+        DS_CUDA(ctx, cudaGetMipmappedArrayLevel(&level, ctx->densityMip, (unsigned)l));
+        cudaExtent ext{};
+        cudaChannelFormatDesc got{};
+        DS_CUDA(ctx, cudaArrayGetInfo(&got, &ext, nullptr, level));
+        if ((int)ext.width != ctx->lnx[l] || (int)std::max<size_t>(ext.height, 1) != ctx->lny[l] || (int)std::max<size_t>(ext.depth, 1) != ctx->lnz[l])
+            DS_FAIL(ctx, DS_ERR_CUDA, "mip level %d: array is %zux%zux%zu, expected %dx%dx%d", l, ext.width, ext.height, ext.depth, ctx->lnx[l], ctx->lny[l],
+                    ctx->lnz[l]);
+        cudaMemcpy3DParms cp = {};
+        cp.srcPtr = make_cudaPitchedPtr((void*)ctx->levels[l], (size_t)ctx->lnx[l], (size_t)ctx->lnx[l], (size_t)ctx->lny[l]);
+        cp.dstArray = level;
+        cp.extent = make_cudaExtent(ctx->lnx[l], ctx->lny[l], ctx->lnz[l]);
+        cp.kind = cudaMemcpyDeviceToDevice;
+        DS_CUDA(ctx, cudaMemcpy3DAsync(&cp, ctx->stream));
+    }
+    cudaResourceDesc rd = {};
+    rd.resType = cudaResourceTypeMipmappedArray;
+    rd.res.mipmap.mipmap = ctx->densityMip;
+    cudaTextureDesc td = {};
+    td.addressMode[0] = td.addressMode[1] = td.addressMode[2] = cudaAddressModeClamp;
+    td.filterMode = cudaFilterModeLinear;
+    td.mipmapFilterMode = cudaFilterModeLinear;
+    td.readMode = cudaReadModeNormalizedFloat;
+    td.normalizedCoords = 1;
+    td.minMipmapLevelClamp = 0.0f;
+    td.maxMipmapLevelClamp = (float)(count - 1);
+    DS_CUDA(ctx, cudaCreateTextureObject(&ctx->densityMipTex, &rd, &td, nullptr));
+    return DS_OK;
+}
+
+/* the descriptor gather of the neural renderer runs on the texture units in the FAST flavour (what the reference's rtTex3DLod does); the
+ * dataset collectors always use the exact software fetch.  Option descriptor_hw: -1 = that rule, 0 = never, 1 = also the float collector */
+static int descriptorTexture(DsContext* ctx, bool networkInput, cudaTextureObject_t* tex)
+{
+    *tex = 0;
+    const int opt = ctx->opt["descriptor_hw"];
+    const bool want = opt == 1 || (opt < 0 && networkInput && ctx->opt["precision"] == DS_PRECISION_FAST);
+    if (!want || ctx->levels.size() < 2) return DS_OK;
+    int rc = ensureMipTexture(ctx);
+    if (rc) return rc;
+    *tex = ctx->densityMipTex;
     return DS_OK;
 }
 
@@ -498,6 +559,7 @@ int ds_context_create(int device, DsContext** out)
     ctx->opt["stream_offset"] = 0;
     ctx->opt["profile_events"] = 0;
     ctx->opt["primary_cache"] = 1;
+    ctx->opt["descriptor_hw"] = -1;
     ctx->opt["mlp_last_us"] = 0; /* read-only: device time of the last model launch when profile_events is on */
     ds_scene_params_default(&ctx->params);
     bool ok = cudaMalloc(&ctx->stats, CNT_COUNT * sizeof(unsigned long long)) == cudaSuccess &&
@@ -1204,9 +1266,11 @@ static int collectDescriptors(DsContext* ctx, const float* positions, const floa
     LevelTable lv;
     DescriptorLayers layers;
     fillDescriptorTables(ctx, lv, layers);
+    cudaTextureObject_t mipTex = 0; /* the collectors use the exact software fetch unless option descriptor_hw = 1 asks for the float one */
+    if (outF32 && !outU8 && !tapIndex && (rc = descriptorTexture(ctx, false, &mipTex))) return rc;
     DS_CUDA(ctx, launchDescriptors(sc, lv, layers, (const float*)ctx->scratch[0], (const float*)ctx->scratch[1], n,
                                    outU8 ? (uint8_t*)ctx->scratch[2] : nullptr, outF32 ? (float*)ctx->scratch[3] : nullptr,
-                                   tapIndex ? (int32_t*)ctx->scratch[4] : nullptr, ctx->stream));
+                                   tapIndex ? (int32_t*)ctx->scratch[4] : nullptr, ctx->stream, 225, nullptr, nullptr, nullptr, mipTex));
     if (outU8) DS_CUDA(ctx, cudaMemcpyAsync(outU8, ctx->scratch[2], taps, cudaMemcpyDeviceToHost, ctx->stream));
     if (outF32) DS_CUDA(ctx, cudaMemcpyAsync(outF32, ctx->scratch[3], taps * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
     if (tapIndex) DS_CUDA(ctx, cudaMemcpyAsync(tapIndex, ctx->scratch[4], taps * 4 * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
@@ -1264,7 +1328,9 @@ static int networkInputDevice(DsContext* ctx, const DsCamera* cam, uint32_t fram
     LevelTable lv;
     DescriptorLayers layers;
     fillDescriptorTables(ctx, lv, layers);
-    DS_CUDA(ctx, launchDescriptors(sc, lv, layers, dPos, dDir, (uint32_t)n, nullptr, dInput, nullptr, ctx->stream, 226, dAngle, dActive));
+    cudaTextureObject_t mipTex = 0;
+    if ((rc = descriptorTexture(ctx, true, &mipTex))) return rc;
+    DS_CUDA(ctx, launchDescriptors(sc, lv, layers, dPos, dDir, (uint32_t)n, nullptr, dInput, nullptr, ctx->stream, 226, dAngle, dActive, nullptr, mipTex));
     ctx->launches += 2;
     return DS_OK;
 }
@@ -1464,9 +1530,11 @@ int ds_render_disney(DsContext* ctx, const DsCamera* cam, uint32_t frame_width, 
     LevelTable lv;
     DescriptorLayers layers;
     fillDescriptorTables(ctx, lv, layers);
+    cudaTextureObject_t mipTex = 0;
+    if ((rc = descriptorTexture(ctx, true, &mipTex))) return rc;
     for (uint32_t first = 0; first < nActive; first += BATCH) {
         const uint32_t n = std::min(BATCH, nActive - first);
-        DS_CUDA(ctx, launchDescriptors(sc, lv, layers, dPos, dDir, n, nullptr, dInput, nullptr, ctx->stream, 226, dAngle, nullptr, dIdx + first));
+        DS_CUDA(ctx, launchDescriptors(sc, lv, layers, dPos, dDir, n, nullptr, dInput, nullptr, ctx->stream, 226, dAngle, nullptr, dIdx + first, mipTex));
         if ((rc = disneyForwardDevice(ctx, dInput, nullptr, n, dPred))) return rc;
         DS_CUDA(ctx, launchBlitPredicted(dPred, dInfo, dIdx + first, n, dFrame, ctx->stream));
         ctx->launches += 2;

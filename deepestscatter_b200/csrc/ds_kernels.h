@@ -137,10 +137,12 @@ cudaError_t launchExportMoments(const float4* progressive, const float4* varianc
 cudaError_t launchImportMoments(const double* in, size_t pixels, uint32_t nTotal, float4* progressive, float4* variance, cudaStream_t st);
 /* layerStride 225: DisneyDescriptor layout [n][10][225]; 226: DisneyNetworkInput layout [n][10][226] whose last element per layer is
  * angle[i] (may be NULL) -- samples with active[i] == 0 (active may be NULL) get all-zero densities; gather (may be NULL): output row i
- * is computed from input sample gather[i] */
+ * is computed from input sample gather[i]; mipTex (0 = none): mip-mapped density texture, the taps then run on the texture units (what the
+ * reference's rtTex3DLod does) instead of the exact software fetch */
 cudaError_t launchDescriptors(const DevScene& sc, const LevelTable& lv, const DescriptorLayers& layers, const float* pos, const float* dir,
                               uint32_t n, uint8_t* outU8, float* outF32, int32_t* tapIndex, cudaStream_t st, int layerStride = 225,
-                              const float* angle = nullptr, const uint8_t* active = nullptr, const uint32_t* gather = nullptr);
+                              const float* angle = nullptr, const uint8_t* active = nullptr, const uint32_t* gather = nullptr,
+                              cudaTextureObject_t mipTex = 0);
 cudaError_t launchTaskWelford(DsPointRadianceTask* tasks, const float* x, uint32_t nThreads, uint32_t launches, cudaStream_t st);
 
 } // namespace dsk

@@ -382,7 +382,7 @@ __global__ void __launch_bounds__(256) k_descriptors(const DevScene sc, const Le
                                                      const float* __restrict__ positions, const float* __restrict__ directions, uint32_t n,
                                                      uint8_t* __restrict__ outU8, float* __restrict__ outF32, int32_t* __restrict__ tapIndex,
                                                      int layerStride, const float* __restrict__ angle, const uint8_t* __restrict__ active,
-                                                     const uint32_t* __restrict__ gather)
+                                                     const uint32_t* __restrict__ gather, cudaTextureObject_t mipTex)
 {
     const uint32_t i = blockIdx.x;
     const int t = threadIdx.x;
@@ -415,7 +415,10 @@ __global__ void __launch_bounds__(256) k_descriptors(const DevScene sc, const Le
          * so its (up to 16) texel reads are skipped -- most taps of the outer layers */
         float density = 0.0f;
         if (tt < 1.0f || tapIndex) {
-            density = tex3dLod(lv, uvw.x, uvw.y, uvw.z, layers.lod[layer], l0);
+            if (mipTex)
+                density = tex3DLod<float>(mipTex, uvw.x, uvw.y, uvw.z, layers.lod[layer]); /* rtTex3DLod, DisneyDescriptor.cuh:41 */
+            else
+                density = tex3dLod(lv, uvw.x, uvw.y, uvw.z, layers.lod[layer], l0);
             density = density + tt * (0.0f - density); /* lerp(density, 0, t) */
         }
         const size_t o = (size_t)i * 2250 + (size_t)layer * 225 + t;
@@ -433,10 +436,10 @@ __global__ void __launch_bounds__(256) k_descriptors(const DevScene sc, const Le
 
 cudaError_t launchDescriptors(const DevScene& sc, const LevelTable& lv, const DescriptorLayers& layers, const float* pos, const float* dir,
                               uint32_t n, uint8_t* outU8, float* outF32, int32_t* tapIndex, cudaStream_t st, int layerStride, const float* angle,
-                              const uint8_t* active, const uint32_t* gather)
+                              const uint8_t* active, const uint32_t* gather, cudaTextureObject_t mipTex)
 {
     if (n == 0) return cudaSuccess;
-    k_descriptors<<<n, 256, 0, st>>>(sc, lv, layers, pos, dir, n, outU8, outF32, tapIndex, layerStride, angle, active, gather);
+    k_descriptors<<<n, 256, 0, st>>>(sc, lv, layers, pos, dir, n, outU8, outF32, tapIndex, layerStride, angle, active, gather, mipTex);
     return cudaGetLastError();
 }
 

@@ -335,6 +335,32 @@ def test_descriptors_u8_and_indices_bit_exact_floats_1e6(built_library, size_m):
     assert got_u8.max() > 0
 
 
+@pytest.mark.parametrize("size_m", [1000.0, 7000.0])
+def test_descriptors_on_the_texture_units_match_within_filter_precision(built_library, size_m):
+    """FAST flavour of the neural renderer's descriptor gather: the same taps through a mip-mapped hardware texture (rtTex3DLod in the
+    reference).  The texture unit quantises the trilinear and the mip weights to 8 fractional bits: each of the three lerps inside a
+    level and the one between levels is off by at most 2^-9 of the local value range, so |hw - exact| <= 4 * 2^-9 in normalised density."""
+    ds = built_library
+    o = ol.Oracle()
+    o.volume_synth(64, 0, 1234, True)
+    o.scene_set(size_m, (0.3, -0.8, 0.52))
+    with ds.Context(0) as ctx:
+        ctx.volume_synth(64, 0, 1234, True)
+        ctx.scene_set(size_m, (0.3, -0.8, 0.52))
+        p, d = ctx.generate_points(0, 96, 0)
+        p[:4] = [[0.49, 0.0, 0.0], [-0.5, -0.5, -0.5], [0.0, 0.499, 0.3], [0.2, -0.1, -0.5]]
+        soft = ctx.descriptors(p, d, as_float=True)
+        ctx.set_option("descriptor_hw", 1)
+        hw = ctx.descriptors(p, d, as_float=True)
+        assert ctx.descriptors(p, d).dtype == np.uint8  # the byte collector never takes the hardware path
+    ref = o.descriptors(p, d, as_float=True)
+    assert np.abs(soft - ref).max() <= 1e-6
+    assert not np.array_equal(hw, soft)  # it really went through the texture units
+    assert np.abs(hw - ref).max() <= 4.0 / 512.0
+    assert np.abs(hw - ref).mean() <= 1e-3
+    assert np.array_equal(hw == 0, ref == 0) or (np.abs(hw - ref)[(hw == 0) != (ref == 0)].max() <= 4.0 / 512.0)
+
+
 def test_point_radiance_collector_bit_exact(gpu_small, oracle_small):
     p, d = oracle_small.generate_points(0, 6)
     rt, rc, rn, ru = oracle_small.point_radiance(p, d, max_threads=48, launches_per_update=20, max_updates=3)
