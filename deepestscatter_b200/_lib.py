@@ -119,6 +119,7 @@ SIGNATURES = {
     "ds_disney_model_profile": (_i, [_vp, C.POINTER(C.c_uint64)]),
     "ds_disney_model_forward": (_i, [_vp, _vp, _u32, _vp]),
     "ds_render_disney": (_i, [_vp, C.POINTER(DsCamera), _u32, _u32, _u32, _vp]),
+    "ds_render_disney_subframes": (_i, [_vp, C.POINTER(DsCamera), _u32, _u32]),
     "ds_radiance_settings_default": (None, [C.POINTER(DsRadianceSettings)]),
     "ds_point_radiance_run": (_i, [_vp, _vp, _vp, _u32, C.POINTER(DsRadianceSettings), _vp, _vp, C.POINTER(_u32)]),
     "ds_record_scatter_sample": (_i, [_pf, _pf, _vp, _sz]),

@@ -335,6 +335,10 @@ class Context:
         self._ck(self.lib.ds_render_disney(self.h, C.byref(cam), frame_w, frame_h, stream, _ptr(out)))
         return out
 
+    def render_disney_subframes(self, cam: DsCamera, first_subframe: int, n: int):
+        """Camera::render with DisneyRenderer: n neural subframes accumulated into the progressive / variance buffers."""
+        self._ck(self.lib.ds_render_disney_subframes(self.h, C.byref(cam), first_subframe, n))
+
     def point_radiance(self, pos, dirs, max_threads: int = 20480, launches_per_update: int = 100, max_updates: int = 0):
         p, d = _f32(pos).reshape(-1, 3), _f32(dirs).reshape(-1, 3)
         n = len(p)

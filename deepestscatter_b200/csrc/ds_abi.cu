@@ -1477,12 +1477,11 @@ int ds_disney_model_forward(DsContext* ctx, const float* network_input, uint32_t
  * stream of its own rectangle, so the result is the reference's pixel for pixel -- and only the pixels that scattered reach the descriptor
  * gather and the model, compacted, in batches sized for HBM (2.4 GB of network input per batch):
  *   k_network_info (frame) -> k_compact_active -> per batch: k_descriptors (gather) -> model -> k_blit_predicted (scatter) */
-int ds_render_disney(DsContext* ctx, const DsCamera* cam, uint32_t frame_width, uint32_t frame_height, uint32_t stream, float* frame_result_out)
+static int renderDisneyDevice(DsContext* ctx, const DsCamera* cam, uint32_t frame_width, uint32_t frame_height, uint32_t stream, float4** frame_out)
 {
-    DS_CHECK_CTX(ctx);
     int rc = requireScene(ctx, true);
     if (rc) return rc;
-    if (!cam || !frame_result_out) DS_FAIL(ctx, DS_ERR_INVALID, "NULL argument");
+    if (!cam) DS_FAIL(ctx, DS_ERR_INVALID, "NULL argument");
     if (frame_width == 0 || frame_height == 0 || (unsigned long long)frame_width * frame_height > (1ull << 26))
         DS_FAIL(ctx, DS_ERR_INVALID, "bad frame size");
     if (!ctx->model.loaded) DS_FAIL(ctx, DS_ERR_STATE, "no model loaded (ds_disney_model_load)");
@@ -1539,7 +1538,36 @@ int ds_render_disney(DsContext* ctx, const DsCamera* cam, uint32_t frame_width, 
         DS_CUDA(ctx, launchBlitPredicted(dPred, dInfo, dIdx + first, n, dFrame, ctx->stream));
         ctx->launches += 2;
     }
-    DS_CUDA(ctx, cudaMemcpyAsync(frame_result_out, dFrame, pixels * sizeof(float4), cudaMemcpyDeviceToHost, ctx->stream));
+    *frame_out = dFrame;
+    return DS_OK;
+}
+
+int ds_render_disney(DsContext* ctx, const DsCamera* cam, uint32_t frame_width, uint32_t frame_height, uint32_t stream, float* frame_result_out)
+{
+    DS_CHECK_CTX(ctx);
+    if (!frame_result_out) DS_FAIL(ctx, DS_ERR_INVALID, "NULL argument");
+    float4* dFrame = nullptr;
+    int rc = renderDisneyDevice(ctx, cam, frame_width, frame_height, stream, &dFrame);
+    if (rc) return rc;
+    DS_CUDA(ctx, cudaMemcpyAsync(frame_result_out, dFrame, (size_t)frame_width * frame_height * sizeof(float4), cudaMemcpyDeviceToHost, ctx->stream));
+    return disneyCheckError(ctx);
+}
+
+/* Camera::render with DisneyRenderer as the ARenderer (Camera.cpp:189-199): per subframe the neural frame, then updateFrameResult into the
+ * progressive / variance buffers of the context's frame -- all on the device.  Subframe s uses stream s * 4096 (+ rectangle ordinal). */
+int ds_render_disney_subframes(DsContext* ctx, const DsCamera* cam, uint32_t first_subframe, uint32_t n)
+{
+    DS_CHECK_CTX(ctx);
+    if (!ctx->progressive) DS_FAIL(ctx, DS_ERR_STATE, "no frame (ds_frame_create)");
+    if (first_subframe == 0) DS_FAIL(ctx, DS_ERR_INVALID, "subframe ids are 1-based (Camera.cpp:191)");
+    const size_t px = (size_t)ctx->width * ctx->height;
+    for (uint32_t k = 0; k < n; ++k) {
+        float4* dFrame = nullptr;
+        int rc = renderDisneyDevice(ctx, cam, (uint32_t)ctx->width, (uint32_t)ctx->height, (first_subframe + k) * 4096u, &dFrame);
+        if (rc) return rc;
+        DS_CUDA(ctx, launchUpdateFrame(dFrame, nullptr, ctx->progressive, ctx->variance, px, first_subframe + k, 1, ctx->stream));
+        ctx->launches += 1;
+    }
     return disneyCheckError(ctx);
 }
 

@@ -13,6 +13,7 @@
 #include <cmath>
 #include <cstdio>
 #include <functional>
+#include <fstream>
 #include <iostream>
 #include <memory>
 #include <queue>
@@ -141,6 +142,31 @@ public:
 private:
     std::shared_ptr<Device> device;
     Cloud::Rendering::Mode mode;
+};
+
+/* DisneyRenderer.cpp:17-110: the neural renderer.  init() loads the model -- here the flat float32 export of DisneyModel.state_dict()
+ * (deepestscatter_b200/disney_model.py) instead of the TorchScript file of DisneyRenderer.cpp:19-22 -- and render() runs the network-input
+ * launch, the model and copyToFrameResult for the whole frame, then the accumulation, on the device */
+class DisneyRenderer : public ARenderer {
+public:
+    static constexpr const char* NAME = "Disney";
+    DisneyRenderer(std::shared_ptr<Device> device, std::string modelPath) : device(std::move(device)), modelPath(std::move(modelPath)) {}
+    void init() override
+    {
+        std::vector<float> w(ds_disney_model_weight_count());
+        std::ifstream f(modelPath, std::ios::binary);
+        if (!f.read(reinterpret_cast<char*>(w.data()), (std::streamsize)(w.size() * sizeof(float))))
+            throw std::runtime_error("cannot read " + std::to_string(w.size()) + " float32 weights from " + modelPath);
+        dsCheck(device->ctx, ds_disney_model_load(device->ctx, w.data(), w.size()));
+    }
+    void render(const DsCamera& camera, uint32_t firstSubframe, uint32_t count) override
+    {
+        dsCheck(device->ctx, ds_render_disney_subframes(device->ctx, &camera, firstSubframe, count));
+    }
+
+private:
+    std::shared_ptr<Device> device;
+    std::string modelPath;
 };
 
 /* EmptyRenderer (dataset tasks register it: Tasks.cpp:139): renders nothing */
@@ -442,6 +468,7 @@ public:
         uint32_t maxSubframes = 0;
         Cloud::Rendering::Mode mode = Cloud::Rendering::Mode::SunAndSkyAllScatter;
         std::string outputDir = ".";
+        std::string disneyModel; /* non-empty: `using TRenderer = DisneyRenderer` (Tasks.cpp:86) with this weight file */
     };
 
     /* renderCloudSingleTask (Tasks.cpp:68-106) with the path-tracing renderer */
@@ -463,8 +490,14 @@ public:
                 if (c == ':') c = '_';
             const size_t dot = base.find_last_of('.');
             if (dot != std::string::npos) base = base.substr(0, dot);
-            Camera::Settings cs{rs.width, rs.height, rs.outputDir + "/" + base + "." + toString(light) + ".PathTracing.exr", rs.maxSubframes};
-            auto renderer = std::make_shared<PathTracingRenderer>(device, rs.mode);
+            const bool neural = !rs.disneyModel.empty();
+            Camera::Settings cs{rs.width, rs.height, rs.outputDir + "/" + base + "." + toString(light) + "." + (neural ? DisneyRenderer::NAME : "PathTracing") + ".exr",
+                                rs.maxSubframes};
+            std::shared_ptr<ARenderer> renderer;
+            if (neural)
+                renderer = std::make_shared<DisneyRenderer>(device, rs.disneyModel);
+            else
+                renderer = std::make_shared<PathTracingRenderer>(device, rs.mode);
             std::vector<std::shared_ptr<SceneItem>> items{std::make_shared<VDBCloud>(device, scene), std::make_shared<Camera>(device, renderer, cs)};
             return std::make_shared<Scene>(items);
         };

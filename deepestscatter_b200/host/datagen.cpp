@@ -3,6 +3,7 @@
  * Scattering dataset through libdeepestscatter_b200.so.  See host/DataGen.hpp for the class layer it drives.
  *
  *   datagen render <cloud> [--size M] [--width W --height H] [--spp N] [--mode all|multi|single] [--out DIR]
+ *                  [--renderer pathtracing|disney --model WEIGHTS.f32]   (the reference's `using TRenderer = ...`, Tasks.cpp:86)
  *       Tasks::renderCloud (Tasks.cpp:108-116): sun "Side", then "Back"; linear image as PFM + tone-mapped PPM
  *   datagen scenes <db> --clouds a.npy,b.npy,... [--scenes-per-cloud 30] [--seed 566]
  *       DeepestScatter_Train/Utils/GenerateSceneSetups.py: SceneSetup records (size log-uniform 1..12 km, sun uniform on the sphere)
@@ -80,6 +81,10 @@ int cmdRender(const Args& a)
     rs.height = (uint32_t)a.num("height", rs.height);
     rs.maxSubframes = (uint32_t)a.num("spp", 0);
     rs.outputDir = a.get("out", ".");
+    if (a.get("renderer", "pathtracing") == "disney") {
+        rs.disneyModel = a.get("model", "");
+        if (rs.disneyModel.empty()) throw std::runtime_error("--renderer disney needs --model <flat float32 state_dict>");
+    }
     const std::string mode = a.get("mode", "all");
     rs.mode = mode == "single" ? Cloud::Rendering::Mode::SunSingleScatter : mode == "multi" ? Cloud::Rendering::Mode::SunMultipleScatter
                                                                                            : Cloud::Rendering::Mode::SunAndSkyAllScatter;

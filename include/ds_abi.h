@@ -258,6 +258,10 @@ int ds_disney_model_profile(DsContext* ctx, uint64_t* cycles16);
  * `stream + k` (clock() in the reference).  frame_result_out: float4 [frame_height][frame_width], zero where nothing scattered;
  * what ARenderer::render leaves in frameResultBuffer, ready for the progressive accumulation (ds_frame_* / Camera.cpp:195-199). */
 int ds_render_disney(DsContext* ctx, const DsCamera* cam, uint32_t frame_width, uint32_t frame_height, uint32_t stream, float* frame_result_out);
+/* Camera::render with DisneyRenderer registered as the ARenderer (Tasks.cpp:87, Camera.cpp:189-199): n subframes of the neural renderer,
+ * each followed by updateFrameResult into the context's progressive / variance buffers (ds_frame_create); nothing leaves the device.
+ * Subframe s draws its forced collisions from stream s * 4096 (+ rectangle ordinal). */
+int ds_render_disney_subframes(DsContext* ctx, const DsCamera* cam, uint32_t first_subframe, uint32_t n);
 void ds_radiance_settings_default(DsRadianceSettings* s);
 /* RadianceCollector::init/update loop until all samples converge (RadianceCollector.cpp:19-54,73-141,176-192;
  * CU/pointEmissionCamera.cu:20-33; CU/PointRadianceTask.h).  tasks_out[i] is the merged representative of

@@ -125,3 +125,38 @@ def test_render_task_writes_the_progressive_image(built_library, tmp_path):
         ctx.render_subframes(ds.camera_look_at(aspect=2.0), ds.MODE_ALL_SCATTER, 1, 20)
         p, _ = ctx.frame_download()
     assert np.array_equal(img, p[..., :3])
+
+
+@pytest.mark.gpu
+def test_render_task_with_the_neural_renderer(built_library, tmp_path):
+    """`using TRenderer = DisneyRenderer` (Tasks.cpp:86): the C++ driver loads the flat weight file and accumulates neural subframes;
+    the EXR equals the same subframes driven through the Python binding."""
+    ds = built_library
+    from deepestscatter_b200 import disney_model as dm
+
+    w = dm.synthetic_weights(566)
+    model = tmp_path / "DisneyModel.f32"
+    w.tofile(model)
+    run("render", "synth:48", "--width", 160, "--height", 40, "--spp", 3, "--out", tmp_path, "--size", 7000, "--renderer", "disney", "--model", model)
+    assert (tmp_path / "synth_48.Side.Disney.exr").exists() and (tmp_path / "synth_48.Back.Disney.exr").exists()
+    from exr_reader import read_exr
+
+    e = read_exr(tmp_path / "synth_48.Side.Disney.exr")
+    img = np.stack([e["image"][c] for c in "RGB"], axis=-1)
+    cam = ds.camera_look_at(aspect=4.0)
+    with ds.Context(0) as ctx:
+        ctx.volume_synth(48, 0, 1234)
+        ctx.scene_set(7000.0, (-0.03, -0.25, 0.8))
+        ctx.bake()
+        ctx.disney_model_load(w)
+        ctx.frame_create(160, 40)
+        ctx.render_disney_subframes(cam, 1, 3)
+        p, v = ctx.frame_download()
+        # the accumulation is Welford over the three neural frames (subframe s draws from stream s * 4096)
+        frames = [ctx.render_disney(cam, 160, 40, stream=s * 4096) for s in (1, 2, 3)]
+    assert np.array_equal(img, p[..., :3]) and img.max() > 0
+    mean = np.zeros_like(frames[0])
+    for k, f in enumerate(frames, start=1):
+        mean = mean + (f - mean) * np.float32(1.0 / k)
+    assert np.abs(mean - p).max() <= 1e-6 * max(1.0, float(np.abs(p).max()))
+    assert run("render", "synth:48", "--renderer", "disney", check=False).returncode == 1  # no --model
