@@ -564,3 +564,94 @@ def test_full_size_frame_properties(built_library):
         again = ctx.render_frame(cam, 0, 1)
         again2 = ctx.render_frame(cam, 0, 1)
         assert np.array_equal(again, again2)
+
+
+# ---------------------------------------------------------------- edge cases of the estimator
+
+
+def _edge_grid(shape, seed):
+    """A lumpy cloud in a non-cubic (nz, ny, nx) grid with a zero border voxel (what the importer produces, Resources.cpp:97-101)."""
+    rs = np.random.RandomState(seed)
+    nz, ny, nx = shape
+    z, y, x = np.meshgrid(np.linspace(-1, 1, nz), np.linspace(-1, 1, ny), np.linspace(-1, 1, nx), indexing="ij")
+    d = np.clip(1.3 - np.sqrt(x * x + (1.4 * y) ** 2 + z * z) * 1.5 + 0.5 * rs.uniform(-1, 1, size=shape), 0, 1)
+    g = (d * 255).astype(np.uint8)
+    g[0] = g[-1] = 0
+    g[:, 0] = g[:, -1] = 0
+    g[:, :, 0] = g[:, :, -1] = 0
+    return g
+
+
+EDGE_CASES = {
+    # name: (grid shape (nz, ny, nx), cloud size m, sun, eye)
+    "non_cubic_grid": ((40, 24, 56), 7000.0, (-0.586, -0.766, -0.271), (2.5, -0.4, 0.0)),
+    "camera_inside_the_cloud": ((32, 32, 32), 3000.0, (0.3, -0.8, 0.52), (0.05, 0.02, -0.03)),  # intersect reports t = 1e-6 (cloudBBox.cu:31)
+    "axis_aligned_sun_thick_cloud": ((24, 48, 24), 12000.0, (0.0, -1.0, 0.0), (0.0, 0.3, 2.2)),
+    "grazing_sun": ((32, 32, 48), 7000.0, (0.995, -0.0998, 0.0), (2.5, -0.4, 0.0)),  # the C4 sun
+}
+
+
+@pytest.mark.parametrize("name", sorted(EDGE_CASES))
+def test_edge_cases_exact_bit_exact_and_fast_consistent(built_library, name):
+    """Grids that are not cubes (per-axis texture scale, occupancy cells), a camera inside the box, an axis-aligned sun (Onb branch) and a
+    grazing one: EXACT equals the oracle bit for bit, FAST agrees with it statistically and keeps the silhouette."""
+    ds = built_library
+    shape, size_m, sun, eye = EDGE_CASES[name]
+    grid = _edge_grid(shape, 5)
+    w, h, spp = 36, 20, 24
+    cam = ds.camera_look_at(eye=eye, aspect=w / h)
+    cam_np = ds.camera_array(cam)
+    o = ol.Oracle()
+    o.volume_upload(grid, True)
+    o.scene_set(size_m, sun)
+    o.bake()
+    rp, rv = o.render_accumulate(cam_np, w, h, 0, 1, spp)
+    assert rp[..., 0].max() > 0
+    with ds.Context(0) as ctx:
+        ctx.set_option("precision", ds.PRECISION_EXACT)
+        ctx.volume_upload(grid, True)
+        ctx.scene_set(size_m, sun)
+        ctx.bake()
+        assert np.array_equal(ctx.inscatter(), o.inscatter())
+        ctx.frame_create(w, h)
+        ctx.render_subframes(cam, 0, 1, spp)
+        p, v = ctx.frame_download()
+        assert np.array_equal(p, rp) and np.array_equal(v, rv)
+        ctx.set_option("precision", ds.PRECISION_FAST)
+        ctx.bake()
+        ctx.frame_clear()
+        ctx.counters_reset()
+        ctx.render_subframes(cam, 0, 1, spp)
+        pf, vf = ctx.frame_download()
+        c = ctx.counters()
+    assert c["nonfinite"] == 0 and np.isfinite(pf).all() and c["paths"] == w * h * spp
+    a, b = pf[..., 0].astype(np.float64), rp[..., 0].astype(np.float64)
+    sigma = np.sqrt((vf[..., 0].astype(np.float64) + rv[..., 0].astype(np.float64)) / (spp - 1) / spp)
+    lit = sigma > 0
+    assert (np.abs(a - b)[lit] / sigma[lit] < 3).mean() > 0.98
+    # same silhouette; pixels in deep shadow (the u8 sun transmittance truncates to 0 there) may flip between exactly 0 and a tiny value
+    flipped = (a == 0) != (b == 0)
+    assert flipped.mean() < 0.05 and (flipped.sum() == 0 or np.maximum(a, b)[flipped].max() < 0.05 * b.max())
+    assert abs(a.mean() - b.mean()) < 0.01 * b.mean() + 3 * np.sqrt((sigma**2).sum()) / a.size
+
+
+def test_empty_cloud_renders_black_and_terminates(built_library):
+    """An all-zero grid: every tap reads 0, nothing scatters, the bake is fully transparent; both flavours, all three estimators."""
+    ds = built_library
+    grid = np.zeros((16, 20, 12), np.uint8)
+    cam = ds.camera_look_at(aspect=2.0)
+    for prec in (ds.PRECISION_EXACT, ds.PRECISION_FAST):
+        with ds.Context(0) as ctx:
+            ctx.set_option("precision", prec)
+            ctx.volume_upload(grid, True)
+            ctx.scene_set(7000.0, (-0.03, -0.25, 0.8))
+            ctx.bake()
+            assert ctx.inscatter().min() == 255
+            ctx.frame_create(32, 16)
+            for mode in (0, 1, 2):
+                ctx.frame_clear()
+                ctx.render_subframes(cam, mode, 1, 3)
+                p, v = ctx.frame_download()
+                assert np.all(p[..., :3] == 0) and np.all(v == 0) and np.all(p[..., 3] == 1)
+            c = ctx.counters()
+            assert c["events"] == 0 and c["nonfinite"] == 0
