@@ -84,8 +84,8 @@ struct DsContext {
 
     /* radiance-predicting network of the neural renderer (ds_disney_model_load) */
     DisneyModelDev model;
-    void* mlpScratch[4] = {nullptr}; /* network-input upload, predictions, compacted row indices + count, frame result */
-    size_t mlpScratchSize[4] = {0};
+    void* mlpScratch[5] = {nullptr}; /* network-input upload, predictions, compacted row indices + count, frame result, network-input tiles */
+    size_t mlpScratchSize[5] = {0};
 };
 
 static thread_local std::string g_createError;
@@ -626,7 +626,7 @@ int ds_context_destroy(DsContext* ctx)
     cudaFree(ctx->mie);
     cudaFree(ctx->guide);
     for (int i = 0; i < 8; i++) cudaFree(ctx->scratch[i]);
-    for (int i = 0; i < 4; i++) cudaFree(ctx->mlpScratch[i]);
+    for (int i = 0; i < 5; i++) cudaFree(ctx->mlpScratch[i]);
     freeDisneyModel(ctx);
     for (cudaEvent_t e : ctx->traceEvents) cudaEventDestroy(e);
     if (ctx->ownStream && ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -1407,11 +1407,14 @@ int ds_disney_model_load(DsContext* ctx, const float* weights, size_t count)
     return DS_OK;
 }
 
-/* evaluates the loaded model on device rows; EXACT flavour: fp32 FMA kernel, FAST flavour: tcgen05 tf32 kernel */
-static int disneyForwardDevice(DsContext* ctx, const float* dIn, const uint32_t* dRowIndex, uint32_t nRows, float* dOut)
+static size_t networkTileBytes(size_t rows) { return (rows + 127) / 128 * NETWORK_TILE_FLOATS * sizeof(float); }
+
+/* evaluates the loaded model on device rows.  FAST flavour: tcgen05 tf32 kernel, dIn = 128-row tiles (NETWORK_TILE_FLOATS); EXACT flavour: fp32
+ * FMA kernel, dIn = DisneyNetworkInput rows [n][10][226] */
+static int disneyForwardDevice(DsContext* ctx, const float* dIn, uint32_t nRows, float* dOut)
 {
     if (!ctx->model.loaded) DS_FAIL(ctx, DS_ERR_STATE, "no model loaded (ds_disney_model_load)");
-    const bool prof = ctx->opt["profile_events"] != 0;
+    const int prof = ctx->opt["profile_events"];
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (prof) {
         DS_CUDA(ctx, cudaEventCreate(&e0));
@@ -1419,9 +1422,9 @@ static int disneyForwardDevice(DsContext* ctx, const float* dIn, const uint32_t*
         DS_CUDA(ctx, cudaEventRecord(e0, ctx->stream));
     }
     if (ctx->opt["precision"] == DS_PRECISION_FAST)
-        DS_CUDA(ctx, launchDisneyMlpTc(ctx->model, dIn, dRowIndex, nRows, dOut, ctx->stream, ctx->opt["profile_events"] >= 2 ? ctx->model.prof : nullptr));
+        DS_CUDA(ctx, launchDisneyMlpTc(ctx->model, dIn, nRows, dOut, ctx->stream, prof >= 2 ? ctx->model.prof : nullptr));
     else
-        DS_CUDA(ctx, launchDisneyMlpF32(ctx->model, dIn, dRowIndex, nRows, dOut, ctx->stream));
+        DS_CUDA(ctx, launchDisneyMlpF32(ctx->model, dIn, nullptr, nRows, dOut, ctx->stream));
     ctx->launches += 1;
     if (prof) {
         float ms = 0.0f;
@@ -1466,7 +1469,15 @@ int ds_disney_model_forward(DsContext* ctx, const float* network_input, uint32_t
     int rc;
     if ((rc = ensureMlpScratch(ctx, 0, (size_t)n * 2260 * sizeof(float))) || (rc = ensureMlpScratch(ctx, 1, (size_t)n * sizeof(float)))) return rc;
     DS_CUDA(ctx, cudaMemcpyAsync(ctx->mlpScratch[0], network_input, (size_t)n * 2260 * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
-    if ((rc = disneyForwardDevice(ctx, (const float*)ctx->mlpScratch[0], nullptr, n, (float*)ctx->mlpScratch[1]))) return rc;
+    const float* dIn = (const float*)ctx->mlpScratch[0];
+    if (ctx->opt["precision"] == DS_PRECISION_FAST) {
+        /* rows -> the tiles the tensor-core kernel reads (the renderer's descriptor gather writes tiles directly) */
+        if ((rc = ensureMlpScratch(ctx, 4, networkTileBytes(n)))) return rc;
+        DS_CUDA(ctx, launchNetworkInputToTiles(dIn, n, (float*)ctx->mlpScratch[4], ctx->stream));
+        ctx->launches += 1;
+        dIn = (const float*)ctx->mlpScratch[4];
+    }
+    if ((rc = disneyForwardDevice(ctx, dIn, n, (float*)ctx->mlpScratch[1]))) return rc;
     DS_CUDA(ctx, cudaMemcpyAsync(predicted_out, ctx->mlpScratch[1], (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
     return disneyCheckError(ctx);
 }
@@ -1489,8 +1500,11 @@ static int renderDisneyDevice(DsContext* ctx, const DsCamera* cam, uint32_t fram
     const uint32_t BATCH = 1u << 18; /* rows of network input resident at a time */
     const size_t pixels = (size_t)frame_width * frame_height;
     const size_t batchRows = std::min<size_t>(BATCH, pixels);
+    /* FAST: the descriptor gather writes the tiles the tensor-core kernel reads; EXACT: DisneyNetworkInput rows for the fp32 kernel */
+    const bool tiled = ctx->opt["precision"] == DS_PRECISION_FAST;
     if ((rc = ensureScratch(ctx, 0, pixels * 3 * sizeof(float))) || (rc = ensureScratch(ctx, 1, pixels * 3 * sizeof(float))) ||
-        (rc = ensureScratch(ctx, 2, pixels * (sizeof(float) + 1))) || (rc = ensureScratch(ctx, 3, batchRows * 2260 * sizeof(float))) ||
+        (rc = ensureScratch(ctx, 2, pixels * (sizeof(float) + 1))) ||
+        (rc = ensureScratch(ctx, 3, tiled ? networkTileBytes(batchRows) : batchRows * 2260 * sizeof(float))) ||
         (rc = ensureScratch(ctx, 4, pixels * 5 * sizeof(float))) || (rc = ensureMlpScratch(ctx, 1, batchRows * sizeof(float))) ||
         (rc = ensureMlpScratch(ctx, 2, (pixels + 1) * sizeof(uint32_t))) || (rc = ensureMlpScratch(ctx, 3, pixels * sizeof(float4))))
         return rc;
@@ -1533,8 +1547,9 @@ static int renderDisneyDevice(DsContext* ctx, const DsCamera* cam, uint32_t fram
     if ((rc = descriptorTexture(ctx, true, &mipTex))) return rc;
     for (uint32_t first = 0; first < nActive; first += BATCH) {
         const uint32_t n = std::min(BATCH, nActive - first);
-        DS_CUDA(ctx, launchDescriptors(sc, lv, layers, dPos, dDir, n, nullptr, dInput, nullptr, ctx->stream, 226, dAngle, nullptr, dIdx + first, mipTex));
-        if ((rc = disneyForwardDevice(ctx, dInput, nullptr, n, dPred))) return rc;
+        DS_CUDA(ctx, launchDescriptors(sc, lv, layers, dPos, dDir, n, nullptr, dInput, nullptr, ctx->stream, tiled ? 0 : 226, dAngle, nullptr, dIdx + first,
+                                       mipTex));
+        if ((rc = disneyForwardDevice(ctx, dInput, n, dPred))) return rc;
         DS_CUDA(ctx, launchBlitPredicted(dPred, dInfo, dIdx + first, n, dFrame, ctx->stream));
         ctx->launches += 2;
     }

@@ -135,9 +135,14 @@ cudaError_t launchUnconverged(const float4* progressive, const float4* variance,
                               cudaStream_t st);
 cudaError_t launchExportMoments(const float4* progressive, const float4* variance, size_t pixels, uint32_t n, double* out, cudaStream_t st);
 cudaError_t launchImportMoments(const double* in, size_t pixels, uint32_t nTotal, float4* progressive, float4* variance, cudaStream_t st);
+/* one 128-row tile of network input in the layout the tensor-core model kernel consumes (ds_mlp.h): [layer 10][K group 58][row 128][4 floats],
+ * k = 0..224 densities, 225 the angle, 226 and 227 the constant 1 that carries the biases, 228..231 zero */
+constexpr size_t NETWORK_TILE_FLOATS = (size_t)10 * 58 * 128 * 4;
+
 /* layerStride 225: DisneyDescriptor layout [n][10][225]; 226: DisneyNetworkInput layout [n][10][226] whose last element per layer is
  * angle[i] (may be NULL) -- samples with active[i] == 0 (active may be NULL) get all-zero densities; gather (may be NULL): output row i
- * is computed from input sample gather[i]; mipTex (0 = none): mip-mapped density texture, the taps then run on the texture units (what the
+ * is computed from input sample gather[i]; layerStride 0: outF32 is written as tf32-rounded 128-row tiles (NETWORK_TILE_FLOATS each, the rows
+ * that pad the last tile zeroed); mipTex (0 = none): mip-mapped density texture, the taps then run on the texture units (what the
  * reference's rtTex3DLod does) instead of the exact software fetch */
 cudaError_t launchDescriptors(const DevScene& sc, const LevelTable& lv, const DescriptorLayers& layers, const float* pos, const float* dir,
                               uint32_t n, uint8_t* outU8, float* outF32, int32_t* tapIndex, cudaStream_t st, int layerStride = 225,

@@ -386,13 +386,36 @@ __global__ void __launch_bounds__(256) k_descriptors(const DevScene sc, const Le
 {
     const uint32_t i = blockIdx.x;
     const int t = threadIdx.x;
+    const bool tiled = layerStride == 0;
+    if (tiled) {
+        /* constants of the tile layout, and the rows that pad the last tile */
+        float* tile = outF32 + (size_t)(i >> 7) * NETWORK_TILE_FLOATS + (size_t)(i & 127u) * 4;
+        if (i >= n) {
+            for (int g = t; g < 10 * 58; g += blockDim.x) *reinterpret_cast<float4*>(tile + (size_t)g * 512) = make_float4(0.f, 0.f, 0.f, 0.f);
+            return;
+        }
+        if (t >= 225 && t < 235) {
+            const int layer = t - 225;
+            float* p = tile + (size_t)(layer * 58 + 56) * 512; /* K group 56 = k 224..227, group 57 = k 228..231 */
+            p[2] = 1.0f;
+            p[3] = 1.0f;
+            *reinterpret_cast<float4*>(p + 512) = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    }
     if (i >= n || t >= 225) return;
     const uint32_t src = gather ? gather[i] : i; /* input sample of output row i */
     const size_t sampleStride = (size_t)layerStride * 10;
-    if (angle && outF32 && t < 10) outF32[(size_t)i * sampleStride + (size_t)t * layerStride + 225] = angle[src]; /* disneyCamera.cu:32-35 */
+    /* index of element k of layer `layer` of output row i in outF32 */
+    auto f32At = [&](int layer, int k) -> size_t {
+        if (!tiled) return (size_t)i * sampleStride + (size_t)layer * layerStride + k;
+        return (size_t)(i >> 7) * NETWORK_TILE_FLOATS + ((size_t)(layer * 58 + (k >> 2)) * 128 + (i & 127u)) * 4 + (k & 3);
+    };
+    /* tf32 (10 mantissa bits), round to nearest: the tensor core would otherwise truncate */
+    auto tf32If = [&](float v) -> float { return tiled ? __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xffffe000u) : v; };
+    if (angle && outF32 && t < 10) outF32[f32At(t, 225)] = tf32If(angle[src]); /* disneyCamera.cu:32-35 */
     if (active && !active[src]) {
         if (outF32)
-            for (int layer = 0; layer < 10; layer++) outF32[(size_t)i * sampleStride + (size_t)layer * layerStride + t] = 0.0f;
+            for (int layer = 0; layer < 10; layer++) outF32[f32At(layer, t)] = 0.0f;
         return;
     }
     const V3 worldPos = mk(positions[3 * (size_t)src], positions[3 * (size_t)src + 1], positions[3 * (size_t)src + 2]);
@@ -423,7 +446,7 @@ __global__ void __launch_bounds__(256) k_descriptors(const DevScene sc, const Le
         }
         const size_t o = (size_t)i * 2250 + (size_t)layer * 225 + t;
         if (outU8) outU8[o] = (uint8_t)(density * 255.0f); /* TFromFloat<uint8_t>, DisneyDescriptor.cuh:66-69 */
-        if (outF32) outF32[(size_t)i * sampleStride + (size_t)layer * layerStride + t] = density;
+        if (outF32) outF32[f32At(layer, t)] = tf32If(density);
         if (tapIndex) {
             const int nx = lv.nx[l0], ny = lv.ny[l0], nz = lv.nz[l0];
             tapIndex[4 * o + 0] = (int)fminf(fmaxf(floorf(uvw.x * (float)nx - 0.5f), -2.0f), (float)nx + 1.0f);
@@ -439,7 +462,8 @@ cudaError_t launchDescriptors(const DevScene& sc, const LevelTable& lv, const De
                               const uint8_t* active, const uint32_t* gather, cudaTextureObject_t mipTex)
 {
     if (n == 0) return cudaSuccess;
-    k_descriptors<<<n, 256, 0, st>>>(sc, lv, layers, pos, dir, n, outU8, outF32, tapIndex, layerStride, angle, active, gather, mipTex);
+    const uint32_t blocks = layerStride == 0 ? (n + 127u) / 128u * 128u : n; /* tiled output: whole tiles */
+    k_descriptors<<<blocks, 256, 0, st>>>(sc, lv, layers, pos, dir, n, outU8, outF32, tapIndex, layerStride, angle, active, gather, mipTex);
     return cudaGetLastError();
 }
 

@@ -11,6 +11,7 @@
 #include <cstring>
 
 #include "ds_mlp.h"
+#include "ds_kernels.h"
 
 namespace dsk {
 
@@ -457,9 +458,9 @@ __device__ __forceinline__ void epiloguePiece(uint32_t tacc, int col0, int epilo
 
 template <bool PROFILE>
 __global__ void __launch_bounds__(TC_THREADS, 1)
-    k_disney_mlp_tc(const float* __restrict__ in, const uint32_t* __restrict__ rowIndex, uint32_t nRows, const uint8_t* __restrict__ stream,
-                    const MlpChunk* __restrict__ chunksG, int nChunks, const float* __restrict__ w4b4, float* __restrict__ out,
-                    uint32_t* __restrict__ errorOut, unsigned long long* __restrict__ prof)
+    k_disney_mlp_tc(const float* __restrict__ tiles, uint32_t nRows, const uint8_t* __restrict__ stream, const MlpChunk* __restrict__ chunksG,
+                    int nChunks, const float* __restrict__ w4b4, float* __restrict__ out, uint32_t* __restrict__ errorOut,
+                    unsigned long long* __restrict__ prof)
 {
     extern __shared__ __align__(1024) unsigned char smem[];
     unsigned char* actS = smem;
@@ -483,7 +484,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
             mbarInit(barBase + 8 * (BAR_WFREE + s), 1);
         }
         for (int s = 0; s < TC_ZSTAGES; ++s) {
-            mbarInit(barBase + 8 * (BAR_ZFULL + s), TC_WORKERS);
+            mbarInit(barBase + 8 * (BAR_ZFULL + s), 1);
             mbarInit(barBase + 8 * (BAR_ZFREE + s), 1);
         }
         mbarInit(barBase + 8 * BAR_GEMM, 1);
@@ -501,24 +502,48 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     const uint32_t tmemBase = *tmemSlot;
 
     if (warp == TC_PRODUCER_WARP) {
-        /* ===== weight stream: one thread keeps every free stage filled ===== */
+        /* ===== operand streams: one thread keeps every free weight stage and descriptor stage filled with bulk copies ===== */
         if (lane == 0) {
-            long long wFree = 0;
+            long long wFree = 0, zFree = 0;
             bool ok = true;
+            const char* tile = reinterpret_cast<const char*>(tiles + (size_t)blockIdx.x * NETWORK_TILE_FLOATS);
+            constexpr uint32_t LAYER_BYTES = 58u * 128u * 16u; /* one descriptor layer of the tile: 58 K groups x 128 rows x 4 floats */
+            uint32_t zFills = 0;
+            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(tile), "r"(LAYER_BYTES) : "memory");
             for (int c = 0; c < nChunks && ok; ++c) {
+                const MlpChunk ch = chunks[c];
                 const int ws = c % TC_WSTAGES;
                 if (c >= TC_WSTAGES) ok = mbarWait<PROFILE>(barBase + 8 * (BAR_WFREE + ws), (uint32_t)(c / TC_WSTAGES - 1) & 1u, abortFlag, wFree);
                 if (!ok) break;
-                const uint32_t wOffset = chunks[c].wOffset, wBytes = chunks[c].wBytes;
                 const uint32_t bar = barBase + 8 * (BAR_WFULL + ws);
-                mbarExpectTx(bar, wBytes);
+                mbarExpectTx(bar, ch.wBytes);
                 asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
                                  actAddr + TC_OFF_W + (uint32_t)ws * TC_WSTAGE_BYTES),
-                             "l"(stream + wOffset), "r"(wBytes), "r"(bar)
+                             "l"(stream + ch.wOffset), "r"(ch.wBytes), "r"(bar)
                              : "memory");
+                if (ch.src == 1) {
+                    /* the chunk's K groups are contiguous in the tile: [layer][K group][row][4] */
+                    const int zs = (int)(zFills % TC_ZSTAGES);
+                    if (zFills >= TC_ZSTAGES) ok = mbarWait<PROFILE>(barBase + 8 * (BAR_ZFREE + zs), (zFills / TC_ZSTAGES - 1) & 1u, abortFlag, zFree);
+                    if (!ok) break;
+                    const uint32_t zBytes = (uint32_t)ch.k8 * 2u * TC_A_LBO;
+                    const uint32_t zbar = barBase + 8 * (BAR_ZFULL + zs);
+                    mbarExpectTx(zbar, zBytes);
+                    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                                     actAddr + TC_OFF_Z + (uint32_t)zs * TC_ZSTAGE_BYTES),
+                                 "l"(tile + (size_t)ch.layer * LAYER_BYTES + (size_t)(ch.aKGroup / 4) * TC_A_LBO), "r"(zBytes), "r"(zbar)
+                                 : "memory");
+                    zFills++;
+                    /* the next layer of the tile starts its way into L2 a whole block ahead */
+                    if (ch.aKGroup == 0 && ch.layer + 1 < MLP_NB)
+                        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(tile + (size_t)(ch.layer + 1) * LAYER_BYTES), "r"(LAYER_BYTES) : "memory");
+                }
             }
             if (!ok) *abortFlag = 1u;
-            if (PROFILE && prof && blockIdx.x == 0) prof[1] = (unsigned long long)wFree; /* producer: waiting for a free weight stage */
+            if (PROFILE && prof && blockIdx.x == 0) {
+                prof[1] = (unsigned long long)wFree; /* producer: waiting for a free weight stage, for a free descriptor stage */
+                prof[9] = (unsigned long long)zFree;
+            }
         }
     } else if (warp == TC_ISSUER_WARP) {
         /* ===== MMA issuer: one thread ===== */
@@ -563,12 +588,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
             }
         }
     } else {
-        /* ===== workers: stage descriptor layers, run the epilogues ===== */
+        /* ===== workers: the epilogues ===== */
         const int t = threadIdx.x & (TC_M - 1), half = threadIdx.x / TC_M;
         const uint32_t row = blockIdx.x * TC_M + t;
         const bool valid = row < nRows;
-        const size_t srcRow = valid ? (rowIndex ? (size_t)rowIndex[row] : (size_t)row) : 0;
-        const float* inRow = in + srcRow * (MLP_NB * MLP_ZD);
         const uint32_t rowOff = (uint32_t)(t / 8) * TC_SBO + (uint32_t)(t % 8) * 16u; /* the row's 16 bytes inside a K group */
         const uint32_t tmemRow = tmemBase + ((uint32_t)((warp & 3) * 32) << 16);
         /* the constant-one columns 200, 201 that carry the biases through the GEMMs; 202..207 are padding */
@@ -576,64 +599,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
             *reinterpret_cast<float4*>(actS + (uint32_t)(MLP_D / 4) * TC_A_LBO + rowOff) = make_float4(1.0f, 1.0f, 0.0f, 0.0f);
             *reinterpret_cast<float4*>(actS + (uint32_t)(MLP_D / 4 + 1) * TC_A_LBO + rowOff) = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
         }
-        uint32_t zFills = 0, gemmWaits = 0;
+        uint32_t gemmWaits = 0;
         bool ok = true;
-        long long wZFree = 0, wGemm = 0, tEpi = 0, tFill = 0;
-        /* descriptor chunks of this row are fetched into registers three chunks ahead of their staging step (zA is the next one to stage,
-         * zB and zC follow), and the row's next layer is pulled into L2 a whole block ahead: the global-memory latency hides behind the MMAs,
-         * the epilogues and two other staging steps */
-        constexpr int ZH = MLP_TC_KCHUNK / 2; /* k values of a chunk per worker half */
-        float2 zA[ZH / 2], zB[ZH / 2], zC[ZH / 2];
-        int zCursor = 0; /* first chunk of the table not yet looked at by fetchZ */
-        auto fetchZ = [&](float2 (&zr)[ZH / 2]) {
-            int c = zCursor;
-            while (c < nChunks && chunks[c].src != 1) ++c;
-            zCursor = c + 1;
-            if (c >= nChunks) return;
-            const int k0 = (int)chunks[c].aKGroup + half * ZH, layer = (int)chunks[c].layer;
-            const float* src = inRow + layer * MLP_ZD + k0;
-#pragma unroll
-            for (int i = 0; i < ZH / 2; ++i) {
-                const int k = k0 + 2 * i;
-                zr[i] = make_float2(0.f, 0.f);
-                if (k == MLP_ZD) zr[i] = make_float2(1.0f, 1.0f); /* z[226] = z[227] = 1: the bias columns */
-                if (valid && k < MLP_ZD) zr[i] = __ldg(reinterpret_cast<const float2*>(src + 2 * i));
-            }
-            if (valid && half == 0 && chunks[c].aKGroup == 0 && layer + 1 < MLP_NB) {
-                const char* nextLayer = reinterpret_cast<const char*>(inRow + (layer + 1) * MLP_ZD);
-#pragma unroll
-                for (int off = 0; off < MLP_ZD * 4 + 128; off += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(nextLayer + off));
-            }
-        };
-        fetchZ(zA);
-        fetchZ(zB);
-        fetchZ(zC);
+        long long wGemm = 0, tEpi = 0;
         for (int c = 0; c < nChunks && ok; ++c) {
             const MlpChunk ch = chunks[c];
-            if (ch.src == 1) {
-                const int zs = (int)(zFills % TC_ZSTAGES);
-                bool mine = true;
-                if (zFills >= TC_ZSTAGES) mine = mbarWait<PROFILE>(barBase + 8 * (BAR_ZFREE + zs), (zFills / TC_ZSTAGES - 1) & 1u, abortFlag, wZFree);
-                const long long tf0 = PROFILE ? clock64() : 0;
-                ok = __all_sync(0xffffffffu, mine);
-                if (!ok) break;
-                unsigned char* zst = smem + TC_OFF_Z + (uint32_t)zs * TC_ZSTAGE_BYTES + rowOff + (uint32_t)(half * (ZH / 4)) * TC_A_LBO;
-#pragma unroll
-                for (int kg = 0; kg < ZH / 4; ++kg)
-                    if (half * (ZH / 4) + kg < 2 * ch.k8)
-                        *reinterpret_cast<float4*>(zst + (uint32_t)kg * TC_A_LBO) =
-                            make_float4(toTf32(zA[2 * kg].x), toTf32(zA[2 * kg].y), toTf32(zA[2 * kg + 1].x), toTf32(zA[2 * kg + 1].y));
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); /* generic-proxy stores -> the tensor core's async-proxy reads */
-                mbarArrive(barBase + 8 * (BAR_ZFULL + zs));
-                zFills++;
-#pragma unroll
-                for (int i = 0; i < ZH / 2; ++i) {
-                    zA[i] = zB[i];
-                    zB[i] = zC[i];
-                }
-                fetchZ(zC);
-                if (PROFILE) tFill += clock64() - tf0;
-            }
             if (ch.flags & MLP_LAST) {
                 const bool mine = mbarWait<PROFILE>(barBase + 8 * BAR_GEMM, gemmWaits & 1u, abortFlag, wGemm);
                 const long long te0 = PROFILE ? clock64() : 0;
@@ -655,7 +625,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
                     asm volatile("bar.sync 1, %0;" ::"n"(TC_WORKERS) : "memory");
                     if (half == 0) {
                         y += partial[t] + __ldg(w4b4 + MLP_NPAD);
-                        if (valid) out[srcRow] = y > 0.0f ? y : 0.01f * y; /* torch.nn.LeakyReLU default slope */
+                        if (valid) out[row] = y > 0.0f ? y : 0.01f * y; /* torch.nn.LeakyReLU default slope */
                     }
                 } else {
                     if (epilogue == MLP_EPI_O) asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
@@ -668,11 +638,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         }
         if (!ok) *abortFlag = 1u;
         if (PROFILE && prof && blockIdx.x == 0 && threadIdx.x == 0) {
-            prof[8] = (unsigned long long)(clock64() - tStart); /* worker 0: total, waits for a free descriptor stage and for a GEMM, */
-            prof[9] = (unsigned long long)wZFree;               /* time inside the epilogues and inside the descriptor staging */
+            prof[8] = (unsigned long long)(clock64() - tStart); /* worker 0: total, waiting for a GEMM, inside the epilogues */
             prof[10] = (unsigned long long)wGemm;
             prof[11] = (unsigned long long)tEpi;
-            prof[12] = (unsigned long long)tFill;
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -684,8 +652,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     }
 }
 
-cudaError_t launchDisneyMlpTc(const DisneyModelDev& m, const float* in, const uint32_t* rowIndex, uint32_t nRows, float* out, cudaStream_t st,
-                              unsigned long long* prof)
+cudaError_t launchDisneyMlpTc(const DisneyModelDev& m, const float* tiles, uint32_t nRows, float* out, cudaStream_t st, unsigned long long* prof)
 {
     if (nRows == 0) return cudaSuccess;
     if (m.nChunks > TC_MAX_CHUNKS) return cudaErrorInvalidValue;
@@ -694,12 +661,45 @@ cudaError_t launchDisneyMlpTc(const DisneyModelDev& m, const float* in, const ui
     if (prof) {
         e = cudaFuncSetAttribute(k_disney_mlp_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM);
         if (e != cudaSuccess) return e;
-        k_disney_mlp_tc<true><<<blocks, TC_THREADS, TC_SMEM, st>>>(in, rowIndex, nRows, m.stream, m.chunks, m.nChunks, m.w4b4, out, m.error, prof);
+        k_disney_mlp_tc<true><<<blocks, TC_THREADS, TC_SMEM, st>>>(tiles, nRows, m.stream, m.chunks, m.nChunks, m.w4b4, out, m.error, prof);
     } else {
         e = cudaFuncSetAttribute(k_disney_mlp_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM);
         if (e != cudaSuccess) return e;
-        k_disney_mlp_tc<false><<<blocks, TC_THREADS, TC_SMEM, st>>>(in, rowIndex, nRows, m.stream, m.chunks, m.nChunks, m.w4b4, out, m.error, nullptr);
+        k_disney_mlp_tc<false><<<blocks, TC_THREADS, TC_SMEM, st>>>(tiles, nRows, m.stream, m.chunks, m.nChunks, m.w4b4, out, m.error, nullptr);
     }
+    return cudaGetLastError();
+}
+
+/* DisneyNetworkInput rows [n][10][226] -> the tiles the tensor-core kernel consumes (tf32-rounded; k 226, 227 = 1; padding rows zero):
+ * one thread per (row, layer, K group) */
+__global__ void __launch_bounds__(256) k_network_input_to_tiles(const float* __restrict__ in, uint32_t nRows, uint32_t nPadded, float* __restrict__ tiles)
+{
+    const size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= (size_t)nPadded * 580) return;
+    const uint32_t row = (uint32_t)(g / 580);
+    const uint32_t lk = (uint32_t)(g - (size_t)row * 580); /* layer * 58 + K group */
+    const uint32_t layer = lk / 58, kg = lk % 58;
+    float v[4] = {0.f, 0.f, 0.f, 0.f};
+    if (row < nRows) {
+        const float* src = in + ((size_t)row * MLP_NB + layer) * MLP_ZD;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const uint32_t k = kg * 4 + e;
+            if (k < (uint32_t)MLP_ZD)
+                v[e] = __uint_as_float((__float_as_uint(__ldg(src + k)) + 0x1000u) & 0xffffe000u); /* tf32, round to nearest */
+            else if (k < (uint32_t)MLP_ZD + 2)
+                v[e] = 1.0f;
+        }
+    }
+    *reinterpret_cast<float4*>(tiles + (size_t)(row >> 7) * NETWORK_TILE_FLOATS + ((size_t)lk * 128 + (row & 127u)) * 4) = make_float4(v[0], v[1], v[2], v[3]);
+}
+
+cudaError_t launchNetworkInputToTiles(const float* in, uint32_t nRows, float* tiles, cudaStream_t st)
+{
+    if (nRows == 0) return cudaSuccess;
+    const uint32_t nPadded = (nRows + 127u) / 128u * 128u;
+    const size_t total = (size_t)nPadded * 580;
+    k_network_input_to_tiles<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(in, nRows, nPadded, tiles);
     return cudaGetLastError();
 }
 

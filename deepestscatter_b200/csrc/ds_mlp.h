@@ -65,13 +65,15 @@ struct DisneyModelHost {
 };
 void packDisneyModel(const float* weights, DisneyModelHost& out);
 
-/* in: [nRowsTotal][10][226] floats on the device; rowIndex (may be NULL): the nRows input rows to evaluate (gather);
+/* fp32 kernel: in = [nRowsTotal][10][226] floats on the device; rowIndex (may be NULL): the nRows input rows to evaluate (gather);
  * out[rowIndex[i]] (or out[i]) receives the prediction */
 cudaError_t launchDisneyMlpF32(const DisneyModelDev& m, const float* in, const uint32_t* rowIndex, uint32_t nRows, float* out, cudaStream_t st);
-/* prof (may be NULL): 16 device words; block 0 leaves its cycle accounting there (issuer: [0] total, [1..4] waits; worker 0: [8] total,
- * [9..12] waits / epilogue / staging) */
-cudaError_t launchDisneyMlpTc(const DisneyModelDev& m, const float* in, const uint32_t* rowIndex, uint32_t nRows, float* out, cudaStream_t st,
-                              unsigned long long* prof = nullptr);
+/* tensor-core kernel: the rows come as 128-row tiles in the layout its MMAs read straight from shared memory (ds_kernels.h
+ * NETWORK_TILE_FLOATS: [layer][K group][row][4], so that the K chunk of a layer is one contiguous block a bulk copy can fetch); out[i] for
+ * i < nRows.  prof (may be NULL): 16 device words; block 0 leaves its cycle accounting there */
+cudaError_t launchDisneyMlpTc(const DisneyModelDev& m, const float* tiles, uint32_t nRows, float* out, cudaStream_t st, unsigned long long* prof = nullptr);
+/* [nRows][10][226] -> ceil(nRows / 128) tiles */
+cudaError_t launchNetworkInputToTiles(const float* in, uint32_t nRows, float* tiles, cudaStream_t st);
 /* indices of the rows with active[i] != 0: idx[0..*count), unordered */
 cudaError_t launchCompactActive(const uint8_t* active, uint32_t n, uint32_t* idx, uint32_t* count, cudaStream_t st);
 /* copyToFrameResult (CU/disneyCamera.cu:38-46) on the device for n compacted rows: row i is frame pixel idx[i] */
