@@ -278,6 +278,7 @@ static int ensureMipTexture(DsContext* ctx)
     td.normalizedCoords = 1;
     td.minMipmapLevelClamp = 0.0f;
     td.maxMipmapLevelClamp = (float)(count - 1);
+    td.disableTrilinearOptimization = 1; /* the full linear blend between levels for every LOD fraction (and the same one in every process) */
     DS_CUDA(ctx, cudaCreateTextureObject(&ctx->densityMipTex, &rd, &td, nullptr));
     return DS_OK;
 }
@@ -560,6 +561,7 @@ int ds_context_create(int device, DsContext** out)
     ctx->opt["profile_events"] = 0;
     ctx->opt["primary_cache"] = 1;
     ctx->opt["descriptor_hw"] = -1;
+    ctx->opt["compact_reverse"] = 0; /* test hook: neural renderer processes the scattering pixels in the opposite order */
     ctx->opt["mlp_last_us"] = 0; /* read-only: device time of the last model launch when profile_events is on */
     ds_scene_params_default(&ctx->params);
     bool ok = cudaMalloc(&ctx->stats, CNT_COUNT * sizeof(unsigned long long)) == cudaSuccess &&
@@ -1540,6 +1542,7 @@ static int renderDisneyDevice(DsContext* ctx, const DsCamera* cam, uint32_t fram
     DS_CUDA(ctx, cudaMemcpyAsync(&nActive, dCount, sizeof(nActive), cudaMemcpyDeviceToHost, ctx->stream));
     DS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     ctx->launches += 2;
+    if (ctx->opt["compact_reverse"]) DS_CUDA(ctx, launchReverse(dIdx, nActive, ctx->stream));
     LevelTable lv;
     DescriptorLayers layers;
     fillDescriptorTables(ctx, lv, layers);

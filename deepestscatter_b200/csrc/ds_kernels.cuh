@@ -488,4 +488,127 @@ cudaError_t KernelSet<FAST>::networkInfo(const DevScene& sc, const TraceJob& cam
     return cudaGetLastError();
 }
 
+/* ---- CU/DisneyDescriptor.cuh:38-112 + CU/disneyDescriptorCollector.cu:22-29 ---- */
+
+/* rtTex3DLod: clamp lod to [0, L-1], trilinear in floor(lod) and floor(lod)+1, lerp */
+__device__ __forceinline__ float tex3dLod(const LevelTable& lv, float u, float v, float w, float lod, int& l0Out)
+{
+    const int last = lv.count - 1;
+    const float l = fminf(fmaxf(lod, 0.0f), (float)last);
+    const float lf = floorf(l);
+    const int l0 = (int)lf;
+    const float t = l - lf;
+    l0Out = l0;
+    const float a = tex3dSoft(lv.data[l0], lv.nx[l0], lv.ny[l0], lv.nz[l0], u, v, w);
+    if (l0 >= last || t == 0.0f) return a;
+    const float b = tex3dSoft(lv.data[l0 + 1], lv.nx[l0 + 1], lv.ny[l0 + 1], lv.nz[l0 + 1], u, v, w);
+    return fmaf(t, b - a, a);
+}
+
+/* DisneyDescriptor.cuh:48-55 */
+__device__ __forceinline__ float distanceToBox(const DevScene& sc, V3 pos, float voxelSize)
+{
+    V3 dist = pos - sc.bbox * 0.5f;
+    dist = mk(fabsf(dist.x), fabsf(dist.y), fabsf(dist.z));
+    const V3 c = sc.bbox * 0.5f - mk(voxelSize, voxelSize, voxelSize) * 0.5f;
+    const V3 boxCorner = mk(fmaxf(c.x, 0.0f), fmaxf(c.y, 0.0f), fmaxf(c.z, 0.0f));
+    dist = dist - boxCorner;
+    dist = mk(fmaxf(dist.x, 0.0f), fmaxf(dist.y, 0.0f), fmaxf(dist.z, 0.0f));
+    return sqrtf(dot(dist, dist));
+}
+
+/* one block per sample; thread t < 225 is stencil tap (x, y, z) = (t%5-2, (t/5)%5-2, t/25-2), i.e. the
+ * reference's sampleId (z outermost, x innermost, DisneyDescriptor.cuh:89-93); 10 layers per thread */
+template <bool FAST>
+__global__ void __launch_bounds__(256) k_descriptors(const DevScene sc, const LevelTable lv, const DescriptorLayers layers,
+                                                     const float* __restrict__ positions, const float* __restrict__ directions, uint32_t n,
+                                                     uint8_t* __restrict__ outU8, float* __restrict__ outF32, int32_t* __restrict__ tapIndex,
+                                                     int layerStride, const float* __restrict__ angle, const uint8_t* __restrict__ active,
+                                                     const uint32_t* __restrict__ gather, cudaTextureObject_t mipTex)
+{
+    const uint32_t i = blockIdx.x;
+    const int t = threadIdx.x;
+    const bool tiled = layerStride == 0;
+    if (tiled) {
+        /* constants of the tile layout, and the rows that pad the last tile */
+        float* tile = outF32 + (size_t)(i >> 7) * NETWORK_TILE_FLOATS + (size_t)(i & 127u) * 4;
+        if (i >= n) {
+            for (int g = t; g < 10 * 58; g += blockDim.x) *reinterpret_cast<float4*>(tile + (size_t)g * 512) = make_float4(0.f, 0.f, 0.f, 0.f);
+            return;
+        }
+        if (t >= 225 && t < 235) {
+            const int layer = t - 225;
+            float* p = tile + (size_t)(layer * 58 + 56) * 512; /* K group 56 = k 224..227, group 57 = k 228..231 */
+            p[2] = 1.0f;
+            p[3] = 1.0f;
+            *reinterpret_cast<float4*>(p + 512) = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    }
+    if (i >= n || t >= 225) return;
+    const uint32_t src = gather ? gather[i] : i; /* input sample of output row i */
+    const size_t sampleStride = (size_t)layerStride * 10;
+    /* index of element k of layer `layer` of output row i in outF32 */
+    auto f32At = [&](int layer, int k) -> size_t {
+        if (!tiled) return (size_t)i * sampleStride + (size_t)layer * layerStride + k;
+        return (size_t)(i >> 7) * NETWORK_TILE_FLOATS + ((size_t)(layer * 58 + (k >> 2)) * 128 + (i & 127u)) * 4 + (k & 3);
+    };
+    /* tf32 (10 mantissa bits), round to nearest: the tensor core would otherwise truncate */
+    auto tf32If = [&](float v) -> float { return tiled ? __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xffffe000u) : v; };
+    if (angle && outF32 && t < 10) outF32[f32At(t, 225)] = tf32If(angle[src]); /* disneyCamera.cu:32-35 */
+    if (active && !active[src]) {
+        if (outF32)
+            for (int layer = 0; layer < 10; layer++) outF32[f32At(layer, t)] = 0.0f;
+        return;
+    }
+    const V3 worldPos = mk(positions[3 * (size_t)src], positions[3 * (size_t)src + 1], positions[3 * (size_t)src + 2]);
+    const V3 viewDirection = mk(directions[3 * (size_t)src], directions[3 * (size_t)src + 1], directions[3 * (size_t)src + 2]);
+    const V3 eZ = normalize<false>(-sc.light);
+    const V3 eX = normalize<false>(cross(eZ, viewDirection));
+    const V3 eY = cross(eX, eZ);
+    const V3 origin = worldPos + 0.5f * sc.bbox;
+    const float x = (float)(t % 5 - 2), y = (float)((t / 5) % 5 - 2), z = (float)(t / 25 - 2);
+#pragma unroll 1
+    for (int layer = 0; layer < 10; layer++) {
+        const V3 offset = (eX * x + eY * y + eZ * z) * layers.scale[layer];
+        const V3 pos = origin + offset;
+        const V3 uvw = pos * sc.texScale;
+        int l0 = 0;
+        const float mipVoxelSize = layers.mipVoxelSize[layer];
+        const float distance = distanceToBox(sc, pos, mipVoxelSize);
+        const float tt = fminf(fmaxf(distance / mipVoxelSize, 0.0f), 1.0f);
+        /* a tap more than one mip voxel outside the box fades to exactly zero: lerp(d, 0, 1) = d + 1 * (0 - d) = +0 for every finite d,
+         * so its (up to 16) texel reads are skipped -- most taps of the outer layers */
+        float density = 0.0f;
+        if (tt < 1.0f || tapIndex) {
+            if (FAST)
+                density = tex3DLod<float>(mipTex, uvw.x, uvw.y, uvw.z, layers.lod[layer]); /* rtTex3DLod, DisneyDescriptor.cuh:41 */
+            else
+                density = tex3dLod(lv, uvw.x, uvw.y, uvw.z, layers.lod[layer], l0);
+            density = density + tt * (0.0f - density); /* lerp(density, 0, t) */
+        }
+        const size_t o = (size_t)i * 2250 + (size_t)layer * 225 + t;
+        if (outU8) outU8[o] = (uint8_t)(density * 255.0f); /* TFromFloat<uint8_t>, DisneyDescriptor.cuh:66-69 */
+        if (outF32) outF32[f32At(layer, t)] = tf32If(density);
+        if (tapIndex) {
+            const int nx = lv.nx[l0], ny = lv.ny[l0], nz = lv.nz[l0];
+            tapIndex[4 * o + 0] = (int)fminf(fmaxf(floorf(uvw.x * (float)nx - 0.5f), -2.0f), (float)nx + 1.0f);
+            tapIndex[4 * o + 1] = (int)fminf(fmaxf(floorf(uvw.y * (float)ny - 0.5f), -2.0f), (float)ny + 1.0f);
+            tapIndex[4 * o + 2] = (int)fminf(fmaxf(floorf(uvw.z * (float)nz - 0.5f), -2.0f), (float)nz + 1.0f);
+            tapIndex[4 * o + 3] = l0;
+        }
+    }
+}
+
+template <bool FAST>
+cudaError_t KernelSet<FAST>::descriptors(const DevScene& sc, const LevelTable& lv, const DescriptorLayers& layers, const float* pos, const float* dir,
+                                         uint32_t n, uint8_t* outU8, float* outF32, int32_t* tapIndex, cudaStream_t st, int layerStride, const float* angle,
+                                         const uint8_t* active, const uint32_t* gather, cudaTextureObject_t mipTex)
+{
+    if (n == 0) return cudaSuccess;
+    if (FAST && !mipTex) return cudaErrorInvalidValue; /* the FAST instantiation samples the mip-mapped texture */
+    const uint32_t blocks = layerStride == 0 ? (n + 127u) / 128u * 128u : n; /* tiled output: whole tiles */
+    k_descriptors<FAST><<<blocks, 256, 0, st>>>(sc, lv, layers, pos, dir, n, outU8, outF32, tapIndex, layerStride, angle, active, gather, mipTex);
+    return cudaGetLastError();
+}
+
 } // namespace dsk

@@ -114,6 +114,10 @@ struct KernelSet {
      * light / view angle and the hasScattered byte */
     static cudaError_t networkInfo(const DevScene& sc, const TraceJob& cam, int rectX, int rectY, int rectW, int rectH, uint32_t stream, float* info,
                                    float* pos, float* dir, float* angle, uint8_t* active, unsigned long long* stats, cudaStream_t st, int tile = 0);
+    /* the hierarchical stencil descriptor (launchDescriptors below picks the instantiation) */
+    static cudaError_t descriptors(const DevScene& sc, const struct LevelTable& lv, const struct DescriptorLayers& layers, const float* pos, const float* dir,
+                                   uint32_t n, uint8_t* outU8, float* outF32, int32_t* tapIndex, cudaStream_t st, int layerStride, const float* angle,
+                                   const uint8_t* active, const uint32_t* gather, cudaTextureObject_t mipTex);
     static cudaError_t generatePoints(const DevScene& sc, uint32_t firstIndex, uint32_t n, uint32_t stream, float* pos, float* dir,
                                       unsigned long long* stats, cudaStream_t st);
 };

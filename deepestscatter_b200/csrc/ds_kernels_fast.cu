@@ -29,6 +29,9 @@
 
 namespace dsk {
 
+/* the EXACT instantiations live in ds_kernels_exact.cu (see there) */
+extern template struct KernelSet<false>;
+
 struct FastState {
     V3 q0;    /* origin of the current free flight, texture coordinates */
     V3 sv;    /* march step in texture space: dir * textureScale * sampleStep */

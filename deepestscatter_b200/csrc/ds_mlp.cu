@@ -731,6 +731,23 @@ cudaError_t launchCompactActive(const uint8_t* active, uint32_t n, uint32_t* idx
     return cudaGetLastError();
 }
 
+/* test hook (option compact_reverse): the same set of rows in the opposite order -- results must not depend on where a row lands */
+__global__ void k_reverse_u32(uint32_t* a, uint32_t n)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n / 2) {
+        const uint32_t x = a[i], y = a[n - 1 - i];
+        a[i] = y;
+        a[n - 1 - i] = x;
+    }
+}
+cudaError_t launchReverse(uint32_t* a, uint32_t n, cudaStream_t st)
+{
+    if (n < 2) return cudaSuccess;
+    k_reverse_u32<<<(n / 2 + 255) / 256, 256, 0, st>>>(a, n);
+    return cudaGetLastError();
+}
+
 /* CU/disneyCamera.cu:38-46: frameResult[pixel] = (make_float4(predicted) + make_float4(radiance)) * (1 - transmittance) for the n compacted
  * rows; row i is frame pixel idx[i], info is indexed by the frame pixel */
 __global__ void k_blit_predicted(const float* __restrict__ predicted, const float* __restrict__ info, const uint32_t* __restrict__ idx, uint32_t n,

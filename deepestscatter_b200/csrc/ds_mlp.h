@@ -76,6 +76,7 @@ cudaError_t launchDisneyMlpTc(const DisneyModelDev& m, const float* tiles, uint3
 cudaError_t launchNetworkInputToTiles(const float* in, uint32_t nRows, float* tiles, cudaStream_t st);
 /* indices of the rows with active[i] != 0: idx[0..*count), unordered */
 cudaError_t launchCompactActive(const uint8_t* active, uint32_t n, uint32_t* idx, uint32_t* count, cudaStream_t st);
+cudaError_t launchReverse(uint32_t* a, uint32_t n, cudaStream_t st); /* test hook: reverse the compacted order */
 /* copyToFrameResult (CU/disneyCamera.cu:38-46) on the device for n compacted rows: row i is frame pixel idx[i] */
 cudaError_t launchBlitPredicted(const float* predicted, const float* info, const uint32_t* idx, uint32_t n, float4* frameResult, cudaStream_t st);
 

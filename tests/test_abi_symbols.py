@@ -60,3 +60,19 @@ def test_no_cpu_fallback_context_creation_fails_loudly(built_library):
     with pytest.raises(ds.DsError) as e:
         ds.Context(0)
     assert "no CPU fallback" in str(e.value)
+
+
+def test_no_kernel_is_compiled_in_two_translation_units(built_library):
+    """The exact and the fast translation units are built with different arithmetic flags; a kernel template instantiated in both would be
+    an ODR violation (which copy a launch gets is then decided per process).  The ptxas logs of the build list every entry function."""
+    obj = ROOT / "deepestscatter_b200" / "csrc" / "_obj"
+    logs = sorted(obj.glob("ptxas_*.log"))
+    if len(logs) < 3:
+        built_library.build_library(force=True)
+        logs = sorted(obj.glob("ptxas_*.log"))
+    seen = {}
+    for log in logs:
+        for name in set(re.findall(r"Compiling entry function '(\w+)'", log.read_text())):
+            assert name not in seen, f"kernel {name} is compiled in {seen[name]} and in {log.name}"
+            seen[name] = log.name
+    assert len(seen) > 20

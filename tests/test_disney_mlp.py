@@ -242,3 +242,20 @@ def test_tensor_core_program_emulated_on_cpu(built_library, weights, inputs):
     assert out is not None
     ref = ol.disney_forward(weights, inputs[:n])
     assert rel(out, ref) <= 2e-3
+
+
+@pytest.mark.gpu
+def test_neural_frame_does_not_depend_on_the_compaction_order(built_library, weights):
+    """The scattering pixels are compacted with warp-aggregated atomics, so their order -- and with it the tile and the TMEM lane a pixel
+    lands in -- varies; the frame must not.  Option compact_reverse processes them in the opposite order."""
+    ds = built_library
+    cam = ds.camera_look_at(aspect=4.0)
+    with ds.Context(0) as ctx:
+        ctx.volume_synth(SCENE_SMALL["n"], SCENE_SMALL["kind"], SCENE_SMALL["seed"])
+        ctx.scene_set(SCENE_SMALL["cloud_size_m"], SCENE_SMALL["light_dir"])
+        ctx.bake()
+        ctx.disney_model_load(weights)
+        a = ctx.render_disney(cam, 160, 40, stream=3)
+        ctx.set_option("compact_reverse", 1)
+        b = ctx.render_disney(cam, 160, 40, stream=3)
+    assert (a[..., 3] != 0).sum() > 1000 and np.array_equal(a, b)
