@@ -50,6 +50,7 @@ def parse_args():
     ap.add_argument("--precision", default="fast", choices=["fast", "exact"])
     ap.add_argument("--opt", action="append", default=[], help="library option name=value (tuning)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the neural-renderer numbers reported next to the main line")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU work for the cpu_baseline sample")
     ap.add_argument("--ref-width", type=int, default=480)
     ap.add_argument("--ref-height", type=int, default=270)
@@ -399,6 +400,36 @@ def run_ours(a):
             }
         except Exception as exc:  # the baseline is reporting only; never lose the GPU line
             line["cpu_baseline"] = {"value": None, "unit": METRIC, "cores": host_threads(), "kind": "port", "sample": f"failed: {exc}"}
+
+    # ---- secondary numbers of the same build (rank 0, N = 1 only; never in the timed region, never able to lose the main line):
+    # the neural renderer end to end on the same cloud and frame, and its network alone ----
+    if rank == 0 and world == 1 and not a.no_secondary:
+        try:
+            from deepestscatter_b200 import disney_model as dm
+
+            ctx.disney_model_load(dm.synthetic_weights(566))
+            ctx.render_disney(cam, a.width, a.height, stream=1)  # warm-up (scratch allocation, mip-mapped texture)
+            times = []
+            for rep in range(3):
+                t0 = time.perf_counter()
+                frame = ctx.render_disney(cam, a.width, a.height, stream=2 + rep)
+                times.append(time.perf_counter() - t0)
+            rows = 1 << 17
+            x = dm.synthetic_inputs(1024, 33)
+            x = np.ascontiguousarray(np.tile(x, (rows // 1024, 1, 1)))
+            ctx.set_option("profile_events", 1)
+            ctx.disney_model_forward(x)
+            ctx.disney_model_forward(x)
+            us = ctx.get_option("mlp_last_us")
+            macs = 10 * (226 * 200 + 2 * 200 * 200) - 200 * 200 + 2 * 200 * 200 + 200
+            line["secondary"] = {
+                "neural_renderer_ms_per_frame": min(times) * 1e3, "neural_renderer_scattering_pixels": int((frame[..., 3] != 0).sum()),
+                "neural_renderer_api": "ds_render_disney (DisneyRenderer::render; host frame buffer out), synthetic weights",
+                "model_kernel": "k_disney_mlp_tc (tcgen05 kind::tf32)", "model_rows": rows, "model_us": us,
+                "model_tflops_tf32": 2 * macs * rows / (us * 1e-6) / 1e12 if us else None,
+            }
+        except Exception as exc:  # reporting only
+            line["secondary"] = {"failed": str(exc)}
 
     if rank == 0:
         print(json.dumps(line))

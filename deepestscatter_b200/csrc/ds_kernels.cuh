@@ -520,7 +520,8 @@ __device__ __forceinline__ float distanceToBox(const DevScene& sc, V3 pos, float
 /* one block per sample; thread t < 225 is stencil tap (x, y, z) = (t%5-2, (t/5)%5-2, t/25-2), i.e. the
  * reference's sampleId (z outermost, x innermost, DisneyDescriptor.cuh:89-93); 10 layers per thread */
 template <bool FAST>
-__global__ void __launch_bounds__(256) k_descriptors(const DevScene sc, const LevelTable lv, const DescriptorLayers layers,
+__global__ void __launch_bounds__(256) k_descriptors(const __grid_constant__ DevScene sc, const __grid_constant__ LevelTable lv,
+                                                     const __grid_constant__ DescriptorLayers layers,
                                                      const float* __restrict__ positions, const float* __restrict__ directions, uint32_t n,
                                                      uint8_t* __restrict__ outU8, float* __restrict__ outF32, int32_t* __restrict__ tapIndex,
                                                      int layerStride, const float* __restrict__ angle, const uint8_t* __restrict__ active,
@@ -567,7 +568,8 @@ __global__ void __launch_bounds__(256) k_descriptors(const DevScene sc, const Le
     const V3 eY = cross(eX, eZ);
     const V3 origin = worldPos + 0.5f * sc.bbox;
     const float x = (float)(t % 5 - 2), y = (float)((t / 5) % 5 - 2), z = (float)(t / 25 - 2);
-#pragma unroll 1
+    /* FAST: the ten layers are independent texture fetches -- unrolled so that they are all in flight together */
+#pragma unroll(FAST ? 10 : 1)
     for (int layer = 0; layer < 10; layer++) {
         const V3 offset = (eX * x + eY * y + eZ * z) * layers.scale[layer];
         const V3 pos = origin + offset;
