@@ -218,7 +218,7 @@ typedef struct DsIntersectionInfo {
  * 225 float densities + the light / view angle (CU/DisneyDescriptor.h) -- the tensor the reference hands to its TorchScript
  * model (DisneyRenderer.cpp:30-36).  network_input_out: [rect_h][rect_w][10][226] floats (densities zero where nothing
  * scattered); info_out: [rect_h][rect_w].  The RNG seed is tea<4>(launchID.x * 4096 + launchID.y, stream) with the
- * rectangle-local launch index, as in the reference (clock() -> stream).  The model itself is the caller's. */
+ * rectangle-local launch index, as in the reference (clock() -> stream).  The model: ds_disney_model_forward below, or the caller's own. */
 int ds_render_network_input(DsContext* ctx, const DsCamera* cam, uint32_t frame_width, uint32_t frame_height, uint32_t rect_x, uint32_t rect_y,
                             uint32_t rect_w, uint32_t rect_h, uint32_t stream, float* network_input_out, DsIntersectionInfo* info_out);
 /* copyToFrameResult (CU/disneyCamera.cu:38-46), host side: frameResult[pixel] = (predicted + radiance) * (1 - transmittance) for
