@@ -84,8 +84,12 @@ struct DsContext {
 
     /* radiance-predicting network of the neural renderer (ds_disney_model_load) */
     DisneyModelDev model;
-    void* mlpScratch[5] = {nullptr}; /* network-input upload, predictions, compacted row indices + count, frame result, network-input tiles */
-    size_t mlpScratchSize[5] = {0};
+    void* mlpScratch[7] = {nullptr}; /* network-input upload, predictions, compacted row indices + count, frame result, network-input tiles,
+                                        entry steps + hit list of the neural renderer's primary-ray cache */
+    size_t mlpScratchSize[7] = {0};
+    bool disneyPrimaryValid = false; /* entry steps valid for (disneyPrimaryCam, disneyPrimaryW x H, the current volume and scene) */
+    DsCamera disneyPrimaryCam{};
+    uint32_t disneyPrimaryW = 0, disneyPrimaryH = 0;
 };
 
 static thread_local std::string g_createError;
@@ -426,6 +430,7 @@ static int beginVolume(DsContext* ctx, int nx, int ny, int nz)
     if (nx <= 0 || ny <= 0 || nz <= 0) DS_FAIL(ctx, DS_ERR_INVALID, "bad volume size %dx%dx%d", nx, ny, nz);
     freeVolume(ctx);
     ctx->primaryValid = false;
+    ctx->disneyPrimaryValid = false;
     ctx->opt["volume_generation"]++; /* read by the importer's cache (host/CloudImporter.hpp) */
     uint8_t* p = nullptr;
     DS_CUDA(ctx, cudaMalloc(&p, (size_t)nx * ny * nz));
@@ -628,7 +633,7 @@ int ds_context_destroy(DsContext* ctx)
     cudaFree(ctx->mie);
     cudaFree(ctx->guide);
     for (int i = 0; i < 8; i++) cudaFree(ctx->scratch[i]);
-    for (int i = 0; i < 5; i++) cudaFree(ctx->mlpScratch[i]);
+    for (int i = 0; i < 7; i++) cudaFree(ctx->mlpScratch[i]);
     freeDisneyModel(ctx);
     for (cudaEvent_t e : ctx->traceEvents) cudaEventDestroy(e);
     if (ctx->ownStream && ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -830,6 +835,7 @@ int ds_scene_set(DsContext* ctx, const DsSceneParams* p)
     ctx->params = *p;
     ctx->sceneSet = true;
     ctx->primaryValid = false; /* entry steps are counted in units of sample_step */
+    ctx->disneyPrimaryValid = false;
     if (lightChanged) ctx->baked = false;
     computeDerived(ctx);
     return DS_OK;
@@ -1531,9 +1537,32 @@ static int renderDisneyDevice(DsContext* ctx, const DsCamera* cam, uint32_t fram
     job.height = (int)frame_height;
     DevScene sc;
     fillDevScene(ctx, sc);
+    /* FAST: the empty-space leg of every camera ray, walked once per (camera, frame size, volume) by k_primary_prepass as for the path
+     * tracer -- pixels that never reach an occupied cell have transmittance 1 and do not scatter; the others start at the cloud */
+    const uint32_t* dEntry = nullptr;
+    if (tiled && ctx->opt["skip_empty"] != 0 && ctx->opt["primary_cache"] != 0) {
+        if ((rc = ensureMlpScratch(ctx, 5, pixels * sizeof(uint32_t))) || (rc = ensureMlpScratch(ctx, 6, (pixels + 8) * sizeof(uint32_t)))) return rc;
+        uint32_t* entry = (uint32_t*)ctx->mlpScratch[5];
+        if (!ctx->disneyPrimaryValid || ctx->disneyPrimaryW != frame_width || ctx->disneyPrimaryH != frame_height ||
+            memcmp(&ctx->disneyPrimaryCam, cam, sizeof(DsCamera)) != 0) {
+            TraceJob pj = job;
+            pj.tilesX = ((int)frame_width + 7) / 8;
+            pj.itemsPerSubframe = (unsigned long long)pj.tilesX * (((int)frame_height + 3) / 4) * 32ull;
+            uint32_t* hitList = (uint32_t*)ctx->mlpScratch[6];
+            unsigned long long* counts = (unsigned long long*)(hitList + ((pixels + 1) & ~(size_t)1)); /* 8-byte aligned tail of slot 6 */
+            DS_CUDA(ctx, cudaMemsetAsync(counts, 0, 2 * sizeof(unsigned long long), ctx->stream));
+            DS_CUDA(ctx, KernelSet<true>::primaryPrepass(sc, pj, entry, hitList, counts, ctx->stream));
+            ctx->launches++;
+            ctx->disneyPrimaryCam = *cam;
+            ctx->disneyPrimaryW = frame_width;
+            ctx->disneyPrimaryH = frame_height;
+            ctx->disneyPrimaryValid = true;
+        }
+        dEntry = entry;
+    }
     if (ctx->opt["precision"] == DS_PRECISION_FAST)
         DS_CUDA(ctx, KernelSet<true>::networkInfo(sc, job, 0, 0, (int)frame_width, (int)frame_height, stream, dInfo, dPos, dDir, dAngle, dActive,
-                                                  ctx->stats, ctx->stream, RECT));
+                                                  ctx->stats, ctx->stream, RECT, dEntry));
     else
         DS_CUDA(ctx, KernelSet<false>::networkInfo(sc, job, 0, 0, (int)frame_width, (int)frame_height, stream, dInfo, dPos, dDir, dAngle, dActive,
                                                    ctx->stats, ctx->stream, RECT));

@@ -372,8 +372,9 @@ cudaError_t KernelSet<FAST>::generatePoints(const DevScene& sc, uint32_t firstIn
  * sun radiance there; the float descriptor of the scattered pixels is gathered by k_descriptors afterwards */
 template <bool FAST>
 __global__ void __launch_bounds__(128) k_network_info(const DevScene sc, const TraceJob cam, int rectX, int rectY, int rectW, int rectH, uint32_t stream,
-                                                      int tile, float* __restrict__ info, float* __restrict__ pos, float* __restrict__ dir,
-                                                      float* __restrict__ angleOut, uint8_t* __restrict__ active, unsigned long long* stats)
+                                                      int tile, const uint32_t* __restrict__ entrySteps, float* __restrict__ info,
+                                                      float* __restrict__ pos, float* __restrict__ dir, float* __restrict__ angleOut,
+                                                      uint8_t* __restrict__ active, unsigned long long* stats)
 {
     /* tile == 0: one rectangle of renderRect, outputs indexed by the rectangle-local pixel;
      * tile  > 0: the whole frame in one launch (rectW x rectH = frame, rectX = rectY = 0), outputs indexed by the frame pixel; every pixel
@@ -401,10 +402,15 @@ __global__ void __launch_bounds__(128) k_network_info(const DevScene sc, const T
     bool has = false;
     V3 world = mk(0.f, 0.f, 0.f), d = rayDirection;
     const float tHit = intersectBox(sc, o, rayDirection);
-    if (tHit >= 0.0f) {
+    /* entrySteps (frame-wide launches of the FAST flavour): march steps of the camera ray whose taps are known to read 0 (k_primary_prepass);
+     * ENTRY_MISS = the ray never reaches an occupied cell: transmittance 1, nothing scatters */
+    const uint32_t entry = entrySteps ? entrySteps[i] : 0u;
+    if (tHit >= 0.0f && entry != ENTRY_MISS) {
         V3 hit = o + tHit * rayDirection;
         hit = hit + 0.5f * sc.bbox;
         d = normalize<FAST>(rayDirection);
+        hit = hit + d * (sc.step * (float)entry); /* zero-density steps change neither the transmittance nor the collision */
+        steps += entry + entry;                   /* both marches below would have taken them */
         uint32_t seed = tea4(lx * 4096u + ly, stream);
         /* getNextScatteringEvent(seed, pos, direction, false).transmittance (cloud.cuh:77-122): the march does not stop */
         {
@@ -480,11 +486,12 @@ __global__ void __launch_bounds__(128) k_network_info(const DevScene sc, const T
 
 template <bool FAST>
 cudaError_t KernelSet<FAST>::networkInfo(const DevScene& sc, const TraceJob& cam, int rectX, int rectY, int rectW, int rectH, uint32_t stream, float* info,
-                                         float* pos, float* dir, float* angle, uint8_t* active, unsigned long long* stats, cudaStream_t st, int tile)
+                                         float* pos, float* dir, float* angle, uint8_t* active, unsigned long long* stats, cudaStream_t st, int tile,
+                                         const uint32_t* entrySteps)
 {
     const int n = rectW * rectH;
     if (n <= 0) return cudaSuccess;
-    k_network_info<FAST><<<(n + 127) / 128, 128, 0, st>>>(sc, cam, rectX, rectY, rectW, rectH, stream, tile, info, pos, dir, angle, active, stats);
+    k_network_info<FAST><<<(n + 127) / 128, 128, 0, st>>>(sc, cam, rectX, rectY, rectW, rectH, stream, tile, entrySteps, info, pos, dir, angle, active, stats);
     return cudaGetLastError();
 }
 

@@ -113,7 +113,8 @@ struct KernelSet {
      * rectangle info = {radiance rgb, transmittance, hasScattered}, the collision point (centred) and view direction, the
      * light / view angle and the hasScattered byte */
     static cudaError_t networkInfo(const DevScene& sc, const TraceJob& cam, int rectX, int rectY, int rectW, int rectH, uint32_t stream, float* info,
-                                   float* pos, float* dir, float* angle, uint8_t* active, unsigned long long* stats, cudaStream_t st, int tile = 0);
+                                   float* pos, float* dir, float* angle, uint8_t* active, unsigned long long* stats, cudaStream_t st, int tile = 0,
+                                   const uint32_t* entrySteps = nullptr);
     /* the hierarchical stencil descriptor (launchDescriptors below picks the instantiation) */
     static cudaError_t descriptors(const DevScene& sc, const struct LevelTable& lv, const struct DescriptorLayers& layers, const float* pos, const float* dir,
                                    uint32_t n, uint8_t* outU8, float* outF32, int32_t* tapIndex, cudaStream_t st, int layerStride, const float* angle,

@@ -259,3 +259,33 @@ def test_neural_frame_does_not_depend_on_the_compaction_order(built_library, wei
         ctx.set_option("compact_reverse", 1)
         b = ctx.render_disney(cam, 160, 40, stream=3)
     assert (a[..., 3] != 0).sum() > 1000 and np.array_equal(a, b)
+
+
+@pytest.mark.gpu
+def test_primary_ray_cache_does_not_change_the_neural_frame_beyond_rounding(built_library, weights):
+    """FAST flavour: the network-input pass starts every camera ray at the first occupied cell (k_primary_prepass).  The skipped steps read
+    zero density, so transmittance and collisions are the same up to the rounding of the start position; silhouette and mean must agree,
+    and a changed camera must invalidate the cache."""
+    ds = built_library
+    with ds.Context(0) as ctx:
+        ctx.volume_synth(SCENE_SMALL["n"], SCENE_SMALL["kind"], SCENE_SMALL["seed"])
+        ctx.scene_set(SCENE_SMALL["cloud_size_m"], SCENE_SMALL["light_dir"])
+        ctx.bake()
+        ctx.disney_model_load(weights)
+        cam = ds.camera_look_at(aspect=4.0)
+        with_cache = ctx.render_disney(cam, 160, 40, stream=3)
+        again = ctx.render_disney(cam, 160, 40, stream=3)
+        ctx.set_option("primary_cache", 0)
+        without = ctx.render_disney(cam, 160, 40, stream=3)
+        ctx.set_option("primary_cache", 1)
+        cam2 = ds.camera_look_at(eye=(2.2, 0.5, 0.4), aspect=4.0)
+        moved = ctx.render_disney(cam2, 160, 40, stream=3)
+        ctx.set_option("primary_cache", 0)
+        moved_ref = ctx.render_disney(cam2, 160, 40, stream=3)
+    assert np.array_equal(with_cache, again)
+    for a, b in ((with_cache, without), (moved, moved_ref)):
+        la, lb = a[..., 3] != 0, b[..., 3] != 0
+        assert lb.sum() > 1000 and (la != lb).mean() < 0.002
+        both = la & lb
+        assert abs(float(a[both].mean()) / float(b[both].mean()) - 1) < 0.01
+    assert not np.array_equal(moved, with_cache)
