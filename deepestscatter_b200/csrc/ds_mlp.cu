@@ -142,15 +142,17 @@ void packDisneyModel(const float* w, DisneyModelHost& out)
     out.stream.clear();
     out.chunks.clear();
     for (int i = 0; i < MLP_NB; ++i) {
-        /* h = relu(o . f1o^T + z_i . f1z^T + b); o = 0 in block 0 (DisneyModel.py:34): that part is skipped */
-        if (i > 0) appendGemmPart(out, blk[i].f1oW, MLP_D, MLP_D, nullptr, 0, 0, 0, (uint8_t)(2 * i), true, true, false, 0);
-        appendGemmPart(out, blk[i].f1zW, MLP_ZD, MLP_ZD, &out.bias[(size_t)(2 * i) * MLP_NPAD], 1, (uint8_t)i, 0, (uint8_t)(2 * i), i == 0, false, true,
+        /* h = relu(z_i . f1z^T + o . f1o^T + b).  The descriptor part goes first: it does not depend on the previous block's epilogue, so its
+         * MMAs run while the workers are still writing o; o = 0 in block 0 (DisneyModel.py:34), whose f1o part is skipped */
+        appendGemmPart(out, blk[i].f1zW, MLP_ZD, MLP_ZD, &out.bias[(size_t)(2 * i) * MLP_NPAD], 1, (uint8_t)i, 0, (uint8_t)(2 * i), true, false, i == 0,
                        MLP_EPI_H);
+        if (i > 0) appendGemmPart(out, blk[i].f1oW, MLP_D, MLP_D, nullptr, 0, 0, 0, (uint8_t)(2 * i), false, true, true, MLP_EPI_H);
         /* o = relu(h . f2^T + b + o): D2 still holds o, the MMAs accumulate on top of it */
         appendGemmPart(out, blk[i].f2W, MLP_D, MLP_D, blk[i].f2B, 0, 0, 1, (uint8_t)(2 * i + 1), i == 0, true, true, MLP_EPI_O);
     }
     appendGemmPart(out, fc0W, MLP_D, MLP_D, fc0B, 0, 0, 0, 20, true, true, true, MLP_EPI_H);
-    appendGemmPart(out, fc2W, MLP_D, MLP_D, fc2B, 0, 0, 0, 21, true, true, true, MLP_EPI_OUT);
+    /* into D2 (the residual is no longer needed): its first MMAs start while the epilogue of the layer before is still reading D1 */
+    appendGemmPart(out, fc2W, MLP_D, MLP_D, fc2B, 0, 0, 1, 21, true, true, true, MLP_EPI_OUT);
 }
 
 /* ------------------------------------------------------------------------------------------------ fp32 kernel */
@@ -288,7 +290,8 @@ constexpr int TC_WORKERS = 256;    /* warps 0-7: threads t and t + 128 share row
 constexpr int TC_ISSUER_WARP = TC_WORKERS / 32;     /* TMEM allocation and MMA issue (one lane) */
 constexpr int TC_PRODUCER_WARP = TC_ISSUER_WARP + 1; /* weight stream: bulk copies (one lane) */
 constexpr int TC_THREADS = TC_WORKERS + 64;
-constexpr int TC_HALF_COLS = 112;  /* epilogue: columns [0, 112) for the first half of the workers, [112, 208) for the second */
+constexpr int TC_PIECES = 7;       /* epilogue pieces = K chunks of the next GEMM: 32 columns each (the last one 16); pieces 0-3 belong to the
+                                      first half of the workers, 4-6 to the second */
 constexpr int TC_WSTAGES = 3, TC_ZSTAGES = 2;
 constexpr int TC_MAX_CHUNKS = 232;
 constexpr uint32_t TC_A_LBO = TC_M / 8 * 128;           /* 2048: bytes between 4-float K groups of the activations (all 16 row groups) */
@@ -304,7 +307,7 @@ constexpr uint32_t TC_OFF_BAR = TC_OFF_CHUNKS + TC_MAX_CHUNKS * sizeof(MlpChunk)
 constexpr uint32_t TC_SMEM = TC_OFF_BAR + 256;
 static_assert(sizeof(MlpChunk) == 20, "MlpChunk layout (include/ds_abi.h documents it)");
 static_assert(TC_SMEM <= 232448, "shared memory budget");
-static_assert(MLP_TC_KCHUNK % 8 == 0 && MLP_TC_KCHUNK <= 32, "chunk size");
+static_assert(MLP_TC_KCHUNK == 32, "the epilogue pieces are the K chunks of the next GEMM");
 static_assert(((TC_ACT_BYTES + TC_WSTAGES * TC_WSTAGE_BYTES + TC_ZSTAGES * TC_ZSTAGE_BYTES) >> 4) + 3 * (2 * 3328 >> 4) < 0x4000, "descriptor start field");
 constexpr uint32_t TC_TMEM_COLS = 512, TC_D2_COL = 256;
 /* instruction descriptor (cute/arch/mma_sm100_desc.hpp InstrDescriptor): D = F32 (bits 4-5 = 1), A = B = TF32 (bits 7-9, 10-12 = 2),
@@ -313,7 +316,7 @@ constexpr uint32_t TC_IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(M
 
 /* barrier slots (8 bytes each) */
 enum { BAR_WFULL = 0, BAR_WFREE = BAR_WFULL + TC_WSTAGES, BAR_ZFULL = BAR_WFREE + TC_WSTAGES, BAR_ZFREE = BAR_ZFULL + TC_ZSTAGES,
-       BAR_GEMM = BAR_ZFREE + TC_ZSTAGES, BAR_ACT, BAR_COUNT };
+       BAR_GEMM = BAR_ZFREE + TC_ZSTAGES, BAR_ACT /* one per epilogue piece */, BAR_COUNT = BAR_ACT + TC_PIECES };
 static_assert(BAR_COUNT * 8 + 8 <= 256, "barrier area");
 
 __device__ __forceinline__ uint32_t smemAddr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -488,7 +491,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
             mbarInit(barBase + 8 * (BAR_ZFREE + s), 1);
         }
         mbarInit(barBase + 8 * BAR_GEMM, 1);
-        mbarInit(barBase + 8 * BAR_ACT, TC_WORKERS);
+        for (int p = 0; p < TC_PIECES; ++p) mbarInit(barBase + 8 * (BAR_ACT + p), TC_WORKERS / 2);
         *abortFlag = 0u;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -554,10 +557,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
             for (int c = 0; c < nChunks && ok; ++c) {
                 const MlpChunk ch = chunks[c];
                 const int ws = c % TC_WSTAGES;
-                if (ch.flags & MLP_WAIT_ACT) {
-                    ok = mbarWait<PROFILE>(barBase + 8 * BAR_ACT, actWaits & 1u, abortFlag, wAct);
-                    actWaits++;
-                }
+                /* a chunk that reads the activation buffer needs only ITS 32 columns from the epilogue before it: the GEMM starts while the
+                 * workers are still writing the later pieces */
+                if (ch.flags & MLP_WAIT_ACT) actWaits++;
+                if (ch.src == 0) ok = mbarWait<PROFILE>(barBase + 8 * (BAR_ACT + ch.aKGroup / 8), (actWaits - 1u) & 1u, abortFlag, wAct);
                 const int zs = (int)(zUses % TC_ZSTAGES);
                 if (ok && ch.src == 1) ok = mbarWait<PROFILE>(barBase + 8 * (BAR_ZFULL + zs), (zUses / TC_ZSTAGES) & 1u, abortFlag, wZ);
                 if (ok) ok = mbarWait<PROFILE>(barBase + 8 * (BAR_WFULL + ws), (uint32_t)(c / TC_WSTAGES) & 1u, abortFlag, wW);
@@ -614,10 +617,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
                 const uint32_t tacc = tmemRow + (ch.dst ? TC_D2_COL : 0u);
                 const int epilogue = ch.epilogue;
                 float y = 0.0f;
-                const int colBegin = half * TC_HALF_COLS;
+                const int pieceBegin = half ? 4 : 0, pieceEnd = half ? TC_PIECES : 4;
 #pragma unroll 1
-                for (int p = 0; p < 3; ++p) epiloguePiece<32>(tacc, colBegin + 32 * p, epilogue, actS + rowOff, w4b4, y);
-                if (half == 0) epiloguePiece<16>(tacc, 96, epilogue, actS + rowOff, w4b4, y);
+                for (int p = pieceBegin; p < pieceEnd; ++p) {
+                    if (p < TC_PIECES - 1)
+                        epiloguePiece<32>(tacc, 32 * p, epilogue, actS + rowOff, w4b4, y);
+                    else
+                        epiloguePiece<16>(tacc, 32 * p, epilogue, actS + rowOff, w4b4, y);
+                    if (epilogue != MLP_EPI_OUT) {
+                        /* hand the piece over: TMEM store done, shared-memory stores visible to the tensor core's async proxy */
+                        if (epilogue == MLP_EPI_O) asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                        mbarArrive(barBase + 8 * (BAR_ACT + p));
+                    }
+                }
                 if (epilogue == MLP_EPI_OUT) {
                     /* the two halves of a row meet in shared memory (the descriptor stages are idle by now) */
                     float* partial = reinterpret_cast<float*>(smem + TC_OFF_Z);
@@ -627,11 +641,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
                         y += partial[t] + __ldg(w4b4 + MLP_NPAD);
                         if (valid) out[row] = y > 0.0f ? y : 0.01f * y; /* torch.nn.LeakyReLU default slope */
                     }
-                } else {
-                    if (epilogue == MLP_EPI_O) asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                    mbarArrive(barBase + 8 * BAR_ACT);
                 }
                 if (PROFILE) tEpi += clock64() - te0;
             }
