@@ -141,7 +141,7 @@ static void freeDisneyModel(DsContext* ctx)
     cudaFree(m.bias);
     cudaFree(m.w4b4);
     cudaFree(m.stream);
-    cudaFree(m.chunks);
+    freeMlpProgram(m.program);
     cudaFree(m.error);
     cudaFree(m.prof);
     m = DisneyModelDev();
@@ -1400,7 +1400,6 @@ int ds_disney_model_load(DsContext* ctx, const float* weights, size_t count)
     DS_CUDA(ctx, cudaMalloc(&m.bias, h.bias.size() * sizeof(float)));
     DS_CUDA(ctx, cudaMalloc(&m.w4b4, h.w4b4.size() * sizeof(float)));
     DS_CUDA(ctx, cudaMalloc(&m.stream, h.stream.size()));
-    DS_CUDA(ctx, cudaMalloc(&m.chunks, h.chunks.size() * sizeof(MlpChunk)));
     DS_CUDA(ctx, cudaMalloc(&m.error, sizeof(uint32_t)));
     DS_CUDA(ctx, cudaMalloc(&m.prof, 16 * sizeof(unsigned long long)));
     DS_CUDA(ctx, cudaMemset(m.prof, 0, 16 * sizeof(unsigned long long)));
@@ -1408,7 +1407,8 @@ int ds_disney_model_load(DsContext* ctx, const float* weights, size_t count)
     DS_CUDA(ctx, cudaMemcpy(m.bias, h.bias.data(), h.bias.size() * sizeof(float), cudaMemcpyHostToDevice));
     DS_CUDA(ctx, cudaMemcpy(m.w4b4, h.w4b4.data(), h.w4b4.size() * sizeof(float), cudaMemcpyHostToDevice));
     DS_CUDA(ctx, cudaMemcpy(m.stream, h.stream.data(), h.stream.size(), cudaMemcpyHostToDevice));
-    DS_CUDA(ctx, cudaMemcpy(m.chunks, h.chunks.data(), h.chunks.size() * sizeof(MlpChunk), cudaMemcpyHostToDevice));
+    m.program = makeMlpProgram(h.chunks);
+    if (!m.program) DS_FAIL(ctx, DS_ERR_INVALID, "model program has %zu chunks", h.chunks.size());
     DS_CUDA(ctx, cudaMemset(m.error, 0, sizeof(uint32_t)));
     m.nChunks = (int)h.chunks.size();
     m.loaded = true;

@@ -294,6 +294,12 @@ constexpr int TC_PIECES = 7;       /* epilogue pieces = K chunks of the next GEM
                                       first half of the workers, 4-6 to the second */
 constexpr int TC_WSTAGES = 3, TC_ZSTAGES = 2;
 constexpr int TC_MAX_CHUNKS = 232;
+/* the program every warp follows, as a kernel parameter: it sits in the constant bank, so a chunk's fields are uniform-register operands for
+ * the warp that issues the MMAs (no per-thread registers, no shared-memory copy) */
+struct MlpProgram {
+    int nChunks;
+    MlpChunk chunks[TC_MAX_CHUNKS];
+};
 constexpr uint32_t TC_A_LBO = TC_M / 8 * 128;           /* 2048: bytes between 4-float K groups of the activations (all 16 row groups) */
 constexpr uint32_t TC_SBO = 128;                        /* bytes between 8-row groups */
 constexpr uint32_t TC_ACT_KGROUPS = MLP_NPAD / 4;       /* 200 activations, the two constant-one columns, padding to 208 */
@@ -302,8 +308,7 @@ constexpr uint32_t TC_WSTAGE_BYTES = MLP_TC_KCHUNK / 4 * B_LBO;    /* 26624 */
 constexpr uint32_t TC_ZSTAGE_BYTES = MLP_TC_KCHUNK / 4 * TC_A_LBO; /* 16384 */
 constexpr uint32_t TC_OFF_W = TC_ACT_BYTES;
 constexpr uint32_t TC_OFF_Z = TC_OFF_W + TC_WSTAGES * TC_WSTAGE_BYTES;
-constexpr uint32_t TC_OFF_CHUNKS = TC_OFF_Z + TC_ZSTAGES * TC_ZSTAGE_BYTES;
-constexpr uint32_t TC_OFF_BAR = TC_OFF_CHUNKS + TC_MAX_CHUNKS * sizeof(MlpChunk);
+constexpr uint32_t TC_OFF_BAR = TC_OFF_Z + TC_ZSTAGES * TC_ZSTAGE_BYTES;
 constexpr uint32_t TC_SMEM = TC_OFF_BAR + 256;
 static_assert(sizeof(MlpChunk) == 20, "MlpChunk layout (include/ds_abi.h documents it)");
 static_assert(TC_SMEM <= 232448, "shared memory budget");
@@ -375,6 +380,14 @@ __device__ __forceinline__ void ummaTf32(uint32_t tmemD, uint32_t descALo, uint3
         ::"r"(tmemD), "r"(descALo), "r"(descBLo), "r"(TC_DESC_HI), "r"(TC_IDESC), "r"(accumulate)
         : "memory");
 }
+/* elect.sync: one lane of the (converged) warp */
+__device__ __forceinline__ bool electOne()
+{
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+
 __device__ __forceinline__ void ummaCommit(uint32_t bar)
 {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
@@ -461,14 +474,14 @@ __device__ __forceinline__ void epiloguePiece(uint32_t tacc, int col0, int epilo
 
 template <bool PROFILE>
 __global__ void __launch_bounds__(TC_THREADS, 1)
-    k_disney_mlp_tc(const float* __restrict__ tiles, uint32_t nRows, const uint8_t* __restrict__ stream, const MlpChunk* __restrict__ chunksG,
-                    int nChunks, const float* __restrict__ w4b4, float* __restrict__ out, uint32_t* __restrict__ errorOut,
-                    unsigned long long* __restrict__ prof)
+    k_disney_mlp_tc(const __grid_constant__ MlpProgram prog, const float* __restrict__ tiles, uint32_t nRows, const uint8_t* __restrict__ stream,
+                    const float* __restrict__ w4b4, float* __restrict__ out, uint32_t* __restrict__ errorOut, unsigned long long* __restrict__ prof)
 {
     extern __shared__ __align__(1024) unsigned char smem[];
     unsigned char* actS = smem;
     const long long tStart = clock64();
-    MlpChunk* chunks = reinterpret_cast<MlpChunk*>(smem + TC_OFF_CHUNKS);
+    const MlpChunk* chunks = prog.chunks;
+    const int nChunks = prog.nChunks;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + TC_OFF_BAR);
     uint32_t* tmemSlot = reinterpret_cast<uint32_t*>(bars + BAR_COUNT);
     volatile uint32_t* abortFlag = tmemSlot + 1;
@@ -476,11 +489,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     const uint32_t actAddr = smemAddr(actS);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-    {
-        const uint32_t* src = reinterpret_cast<const uint32_t*>(chunksG);
-        uint32_t* dst = reinterpret_cast<uint32_t*>(chunks);
-        for (int i = threadIdx.x; i < nChunks * (int)(sizeof(MlpChunk) / 4); i += TC_THREADS) dst[i] = __ldg(src + i);
-    }
     if (threadIdx.x == 0) {
         for (int s = 0; s < TC_WSTAGES; ++s) {
             mbarInit(barBase + 8 * (BAR_WFULL + s), 1);
@@ -549,13 +557,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
             }
         }
     } else if (warp == TC_ISSUER_WARP) {
-        /* ===== MMA issuer: one thread ===== */
-        if (lane == 0) {
+        /* ===== MMA issuer: the whole warp walks the program (uniform control flow, operands in uniform registers), one elected lane issues ===== */
+        {
             uint32_t actWaits = 0, zUses = 0;
             bool ok = true;
             long long wAct = 0, wZ = 0, wW = 0; /* cycles spent waiting, by cause (PROFILE) */
-            for (int c = 0; c < nChunks && ok; ++c) {
-                const MlpChunk ch = chunks[c];
+            for (int c = 0; c < nChunks; ++c) {
+                const MlpChunk& ch = chunks[c];
                 const int ws = c % TC_WSTAGES;
                 /* a chunk that reads the activation buffer needs only ITS 32 columns from the epilogue before it: the GEMM starts while the
                  * workers are still writing the later pieces */
@@ -564,26 +572,28 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
                 const int zs = (int)(zUses % TC_ZSTAGES);
                 if (ok && ch.src == 1) ok = mbarWait<PROFILE>(barBase + 8 * (BAR_ZFULL + zs), (zUses / TC_ZSTAGES) & 1u, abortFlag, wZ);
                 if (ok) ok = mbarWait<PROFILE>(barBase + 8 * (BAR_WFULL + ws), (uint32_t)(c / TC_WSTAGES) & 1u, abortFlag, wW);
+                ok = __all_sync(0xffffffffu, ok);
                 if (!ok) break;
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t aLo = ummaDescLo(ch.src == 1 ? actAddr + TC_OFF_Z + (uint32_t)zs * TC_ZSTAGE_BYTES : actAddr + (uint32_t)ch.aKGroup * TC_A_LBO, TC_A_LBO);
                 const uint32_t bLo = ummaDescLo(actAddr + TC_OFF_W + (uint32_t)ws * TC_WSTAGE_BYTES, B_LBO);
                 const uint32_t d = tmemBase + (ch.dst ? TC_D2_COL : 0u);
                 const int k8 = ch.k8;
-                /* one MMA per 8 k values: two 4-float K groups of each operand, i.e. 2 * LBO bytes further per step */
-                ummaTf32(d, aLo, bLo, (ch.flags & MLP_FIRST) ? 0u : 1u);
-                if (k8 > 1) ummaTf32(d, aLo + (2u * TC_A_LBO >> 4), bLo + (2u * B_LBO >> 4), 1u);
-                if (k8 > 2) ummaTf32(d, aLo + 2u * (2u * TC_A_LBO >> 4), bLo + 2u * (2u * B_LBO >> 4), 1u);
-                if (k8 > 3) ummaTf32(d, aLo + 3u * (2u * TC_A_LBO >> 4), bLo + 3u * (2u * B_LBO >> 4), 1u);
-                ummaCommit(barBase + 8 * (BAR_WFREE + ws));
-                if (ch.src == 1) {
-                    ummaCommit(barBase + 8 * (BAR_ZFREE + zs));
-                    zUses++;
+                if (electOne()) {
+                    /* one MMA per 8 k values: two 4-float K groups of each operand, i.e. 2 * LBO bytes further per step */
+                    ummaTf32(d, aLo, bLo, (ch.flags & MLP_FIRST) ? 0u : 1u);
+                    if (k8 > 1) ummaTf32(d, aLo + (2u * TC_A_LBO >> 4), bLo + (2u * B_LBO >> 4), 1u);
+                    if (k8 > 2) ummaTf32(d, aLo + 2u * (2u * TC_A_LBO >> 4), bLo + 2u * (2u * B_LBO >> 4), 1u);
+                    if (k8 > 3) ummaTf32(d, aLo + 3u * (2u * TC_A_LBO >> 4), bLo + 3u * (2u * B_LBO >> 4), 1u);
+                    ummaCommit(barBase + 8 * (BAR_WFREE + ws));
+                    if (ch.src == 1) ummaCommit(barBase + 8 * (BAR_ZFREE + zs));
+                    if (ch.flags & MLP_LAST) ummaCommit(barBase + 8 * BAR_GEMM);
                 }
-                if (ch.flags & MLP_LAST) ummaCommit(barBase + 8 * BAR_GEMM);
+                __syncwarp();
+                if (ch.src == 1) zUses++;
             }
             if (!ok) *abortFlag = 1u;
-            if (PROFILE && prof && blockIdx.x == 0) {
+            if (PROFILE && prof && blockIdx.x == 0 && lane == 0) {
                 prof[0] = (unsigned long long)(clock64() - tStart); /* issuer: total, then waits for the previous epilogue, a staged */
                 prof[2] = (unsigned long long)wAct;                 /* descriptor chunk, a landed weight chunk */
                 prof[3] = (unsigned long long)wZ;
@@ -664,20 +674,32 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
 cudaError_t launchDisneyMlpTc(const DisneyModelDev& m, const float* tiles, uint32_t nRows, float* out, cudaStream_t st, unsigned long long* prof)
 {
     if (nRows == 0) return cudaSuccess;
-    if (m.nChunks > TC_MAX_CHUNKS) return cudaErrorInvalidValue;
+    if (!m.program) return cudaErrorInvalidValue;
     const unsigned blocks = (nRows + TC_M - 1) / TC_M;
     cudaError_t e;
     if (prof) {
         e = cudaFuncSetAttribute(k_disney_mlp_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM);
         if (e != cudaSuccess) return e;
-        k_disney_mlp_tc<true><<<blocks, TC_THREADS, TC_SMEM, st>>>(tiles, nRows, m.stream, m.chunks, m.nChunks, m.w4b4, out, m.error, prof);
+        k_disney_mlp_tc<true><<<blocks, TC_THREADS, TC_SMEM, st>>>(*m.program, tiles, nRows, m.stream, m.w4b4, out, m.error, prof);
     } else {
         e = cudaFuncSetAttribute(k_disney_mlp_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM);
         if (e != cudaSuccess) return e;
-        k_disney_mlp_tc<false><<<blocks, TC_THREADS, TC_SMEM, st>>>(tiles, nRows, m.stream, m.chunks, m.nChunks, m.w4b4, out, m.error, nullptr);
+        k_disney_mlp_tc<false><<<blocks, TC_THREADS, TC_SMEM, st>>>(*m.program, tiles, nRows, m.stream, m.w4b4, out, m.error, nullptr);
     }
     return cudaGetLastError();
 }
+
+/* the chunk table as the kernel-parameter block (host memory, owned by the model) */
+MlpProgram* makeMlpProgram(const std::vector<MlpChunk>& chunks)
+{
+    if ((int)chunks.size() > TC_MAX_CHUNKS) return nullptr;
+    MlpProgram* p = new MlpProgram();
+    memset(p, 0, sizeof(*p));
+    p->nChunks = (int)chunks.size();
+    memcpy(p->chunks, chunks.data(), chunks.size() * sizeof(MlpChunk));
+    return p;
+}
+void freeMlpProgram(MlpProgram* p) { delete p; }
 
 /* DisneyNetworkInput rows [n][10][226] -> the tiles the tensor-core kernel consumes (tf32-rounded; k 226, 227 = 1; padding rows zero):
  * one thread per (row, layer, K group) */

@@ -50,7 +50,7 @@ struct DisneyModelDev {
     float* bias = nullptr;     /* [22][208]; the two biases of a block's first GEMM are pre-summed */
     float* w4b4 = nullptr;     /* fullyConnected.4: 200 weights, zero padding to 208, bias at [208] */
     uint8_t* stream = nullptr; /* tensor-core kernel: weights in UMMA canonical K-major layout, in consumption order */
-    MlpChunk* chunks = nullptr;
+    struct MlpProgram* program = nullptr; /* host: the chunk table, passed to the kernel as its (grid-constant) parameter block */
     int nChunks = 0;
     uint32_t* error = nullptr; /* device word: non-zero if a barrier wait of the tensor-core kernel timed out */
     unsigned long long* prof = nullptr; /* 16 words: cycle accounting of block 0 of the last tensor-core launch (profile_events) */
@@ -64,6 +64,8 @@ struct DisneyModelHost {
     std::vector<MlpChunk> chunks;
 };
 void packDisneyModel(const float* weights, DisneyModelHost& out);
+struct MlpProgram* makeMlpProgram(const std::vector<MlpChunk>& chunks); /* NULL if the table is too long */
+void freeMlpProgram(struct MlpProgram* p);
 
 /* fp32 kernel: in = [nRowsTotal][10][226] floats on the device; rowIndex (may be NULL): the nRows input rows to evaluate (gather);
  * out[rowIndex[i]] (or out[i]) receives the prediction */
