@@ -142,6 +142,8 @@ static void freeDisneyModel(DsContext* ctx)
     cudaFree(m.w4b4);
     cudaFree(m.stream);
     freeMlpProgram(m.program);
+    freeMlpProgram(m.programBf16);
+    cudaFree(m.streamBf16);
     cudaFree(m.error);
     cudaFree(m.prof);
     m = DisneyModelDev();
@@ -566,6 +568,7 @@ int ds_context_create(int device, DsContext** out)
     ctx->opt["profile_events"] = 0;
     ctx->opt["primary_cache"] = 1;
     ctx->opt["descriptor_hw"] = -1;
+    ctx->opt["mlp_bf16"] = 0; /* FAST flavour of the model: 0 = tf32 operands (default), 1 = bf16 operands (twice the MMA rate, half the operand bytes) */
     ctx->opt["compact_reverse"] = 0; /* test hook: neural renderer processes the scattering pixels in the opposite order */
     ctx->opt["mlp_last_us"] = 0; /* read-only: device time of the last model launch when profile_events is on */
     ds_scene_params_default(&ctx->params);
@@ -1364,21 +1367,23 @@ int ds_render_network_input(DsContext* ctx, const DsCamera* cam, uint32_t frame_
 
 size_t ds_disney_model_weight_count(void) { return MLP_WEIGHT_COUNT; }
 
-int ds_disney_model_pack(const float* weights, size_t count, void* stream_out, size_t stream_capacity, void* chunks_out, size_t chunks_capacity,
+int ds_disney_model_pack(const float* weights, size_t count, int bf16, void* stream_out, size_t stream_capacity, void* chunks_out, size_t chunks_capacity,
                          size_t* stream_bytes, size_t* chunk_count)
 {
     if (!weights || count != MLP_WEIGHT_COUNT || !stream_bytes || !chunk_count) return DS_ERR_INVALID;
     DisneyModelHost h;
     packDisneyModel(weights, h);
-    *stream_bytes = h.stream.size();
-    *chunk_count = h.chunks.size();
+    const std::vector<uint8_t>& stream = bf16 ? h.streamBf16 : h.stream;
+    const std::vector<MlpChunk>& chunks = bf16 ? h.chunksBf16 : h.chunks;
+    *stream_bytes = stream.size();
+    *chunk_count = chunks.size();
     if (stream_out) {
-        if (stream_capacity < h.stream.size()) return DS_ERR_INVALID;
-        memcpy(stream_out, h.stream.data(), h.stream.size());
+        if (stream_capacity < stream.size()) return DS_ERR_INVALID;
+        memcpy(stream_out, stream.data(), stream.size());
     }
     if (chunks_out) {
-        if (chunks_capacity < h.chunks.size() * sizeof(MlpChunk)) return DS_ERR_INVALID;
-        memcpy(chunks_out, h.chunks.data(), h.chunks.size() * sizeof(MlpChunk));
+        if (chunks_capacity < chunks.size() * sizeof(MlpChunk)) return DS_ERR_INVALID;
+        memcpy(chunks_out, chunks.data(), chunks.size() * sizeof(MlpChunk));
     }
     return DS_OK;
 }
@@ -1400,6 +1405,7 @@ int ds_disney_model_load(DsContext* ctx, const float* weights, size_t count)
     DS_CUDA(ctx, cudaMalloc(&m.bias, h.bias.size() * sizeof(float)));
     DS_CUDA(ctx, cudaMalloc(&m.w4b4, h.w4b4.size() * sizeof(float)));
     DS_CUDA(ctx, cudaMalloc(&m.stream, h.stream.size()));
+    DS_CUDA(ctx, cudaMalloc(&m.streamBf16, h.streamBf16.size()));
     DS_CUDA(ctx, cudaMalloc(&m.error, sizeof(uint32_t)));
     DS_CUDA(ctx, cudaMalloc(&m.prof, 16 * sizeof(unsigned long long)));
     DS_CUDA(ctx, cudaMemset(m.prof, 0, 16 * sizeof(unsigned long long)));
@@ -1407,15 +1413,17 @@ int ds_disney_model_load(DsContext* ctx, const float* weights, size_t count)
     DS_CUDA(ctx, cudaMemcpy(m.bias, h.bias.data(), h.bias.size() * sizeof(float), cudaMemcpyHostToDevice));
     DS_CUDA(ctx, cudaMemcpy(m.w4b4, h.w4b4.data(), h.w4b4.size() * sizeof(float), cudaMemcpyHostToDevice));
     DS_CUDA(ctx, cudaMemcpy(m.stream, h.stream.data(), h.stream.size(), cudaMemcpyHostToDevice));
+    DS_CUDA(ctx, cudaMemcpy(m.streamBf16, h.streamBf16.data(), h.streamBf16.size(), cudaMemcpyHostToDevice));
     m.program = makeMlpProgram(h.chunks);
-    if (!m.program) DS_FAIL(ctx, DS_ERR_INVALID, "model program has %zu chunks", h.chunks.size());
+    m.programBf16 = makeMlpProgram(h.chunksBf16);
+    if (!m.program || !m.programBf16) DS_FAIL(ctx, DS_ERR_INVALID, "model program has %zu chunks", h.chunks.size());
     DS_CUDA(ctx, cudaMemset(m.error, 0, sizeof(uint32_t)));
     m.nChunks = (int)h.chunks.size();
     m.loaded = true;
     return DS_OK;
 }
 
-static size_t networkTileBytes(size_t rows) { return (rows + 127) / 128 * NETWORK_TILE_FLOATS * sizeof(float); }
+static size_t networkTileBytes(DsContext* ctx, size_t rows) { return (rows + 127) / 128 * networkTileBytesOf(ctx->opt["mlp_bf16"] != 0); }
 
 /* evaluates the loaded model on device rows.  FAST flavour: tcgen05 tf32 kernel, dIn = 128-row tiles (NETWORK_TILE_FLOATS); EXACT flavour: fp32
  * FMA kernel, dIn = DisneyNetworkInput rows [n][10][226] */
@@ -1430,7 +1438,7 @@ static int disneyForwardDevice(DsContext* ctx, const float* dIn, uint32_t nRows,
         DS_CUDA(ctx, cudaEventRecord(e0, ctx->stream));
     }
     if (ctx->opt["precision"] == DS_PRECISION_FAST)
-        DS_CUDA(ctx, launchDisneyMlpTc(ctx->model, dIn, nRows, dOut, ctx->stream, prof >= 2 ? ctx->model.prof : nullptr));
+        DS_CUDA(ctx, launchDisneyMlpTc(ctx->model, dIn, nRows, dOut, ctx->stream, prof >= 2 ? ctx->model.prof : nullptr, ctx->opt["mlp_bf16"] != 0));
     else
         DS_CUDA(ctx, launchDisneyMlpF32(ctx->model, dIn, nullptr, nRows, dOut, ctx->stream));
     ctx->launches += 1;
@@ -1480,8 +1488,8 @@ int ds_disney_model_forward(DsContext* ctx, const float* network_input, uint32_t
     const float* dIn = (const float*)ctx->mlpScratch[0];
     if (ctx->opt["precision"] == DS_PRECISION_FAST) {
         /* rows -> the tiles the tensor-core kernel reads (the renderer's descriptor gather writes tiles directly) */
-        if ((rc = ensureMlpScratch(ctx, 4, networkTileBytes(n)))) return rc;
-        DS_CUDA(ctx, launchNetworkInputToTiles(dIn, n, (float*)ctx->mlpScratch[4], ctx->stream));
+        if ((rc = ensureMlpScratch(ctx, 4, networkTileBytes(ctx, n)))) return rc;
+        DS_CUDA(ctx, launchNetworkInputToTiles(dIn, n, ctx->mlpScratch[4], ctx->stream, ctx->opt["mlp_bf16"] != 0));
         ctx->launches += 1;
         dIn = (const float*)ctx->mlpScratch[4];
     }
@@ -1512,7 +1520,7 @@ static int renderDisneyDevice(DsContext* ctx, const DsCamera* cam, uint32_t fram
     const bool tiled = ctx->opt["precision"] == DS_PRECISION_FAST;
     if ((rc = ensureScratch(ctx, 0, pixels * 3 * sizeof(float))) || (rc = ensureScratch(ctx, 1, pixels * 3 * sizeof(float))) ||
         (rc = ensureScratch(ctx, 2, pixels * (sizeof(float) + 1))) ||
-        (rc = ensureScratch(ctx, 3, tiled ? networkTileBytes(batchRows) : batchRows * 2260 * sizeof(float))) ||
+        (rc = ensureScratch(ctx, 3, tiled ? networkTileBytes(ctx, batchRows) : batchRows * 2260 * sizeof(float))) ||
         (rc = ensureScratch(ctx, 4, pixels * 5 * sizeof(float))) || (rc = ensureMlpScratch(ctx, 1, batchRows * sizeof(float))) ||
         (rc = ensureMlpScratch(ctx, 2, (pixels + 1) * sizeof(uint32_t))) || (rc = ensureMlpScratch(ctx, 3, pixels * sizeof(float4))))
         return rc;
@@ -1579,7 +1587,7 @@ static int renderDisneyDevice(DsContext* ctx, const DsCamera* cam, uint32_t fram
     if ((rc = descriptorTexture(ctx, true, &mipTex))) return rc;
     for (uint32_t first = 0; first < nActive; first += BATCH) {
         const uint32_t n = std::min(BATCH, nActive - first);
-        DS_CUDA(ctx, launchDescriptors(sc, lv, layers, dPos, dDir, n, nullptr, dInput, nullptr, ctx->stream, tiled ? 0 : 226, dAngle, nullptr, dIdx + first,
+        DS_CUDA(ctx, launchDescriptors(sc, lv, layers, dPos, dDir, n, nullptr, dInput, nullptr, ctx->stream, tiled ? (ctx->opt["mlp_bf16"] ? -1 : 0) : 226, dAngle, nullptr, dIdx + first,
                                        mipTex));
         if ((rc = disneyForwardDevice(ctx, dInput, n, dPred))) return rc;
         DS_CUDA(ctx, launchBlitPredicted(dPred, dInfo, dIdx + first, n, dFrame, ctx->stream));

@@ -536,36 +536,53 @@ __global__ void __launch_bounds__(256) k_descriptors(const __grid_constant__ Dev
 {
     const uint32_t i = blockIdx.x;
     const int t = threadIdx.x;
-    const bool tiled = layerStride == 0;
+    const bool tiled = layerStride <= 0, bf16 = layerStride < 0;
+    /* tiles: [tile][layer][K group][row 128][16 bytes]; 58 K groups of 4 floats (tf32 operands) or 30 K groups of 8 bf16 per layer */
+    const uint32_t KG = bf16 ? 30u : 58u;
+    unsigned char* const tileRow = reinterpret_cast<unsigned char*>(outF32) + (size_t)(i >> 7) * (10u * KG * 2048u) + (size_t)(i & 127u) * 16;
     if (tiled) {
         /* constants of the tile layout, and the rows that pad the last tile */
-        float* tile = outF32 + (size_t)(i >> 7) * NETWORK_TILE_FLOATS + (size_t)(i & 127u) * 4;
         if (i >= n) {
-            for (int g = t; g < 10 * 58; g += blockDim.x) *reinterpret_cast<float4*>(tile + (size_t)g * 512) = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (uint32_t g = t; g < 10u * KG; g += blockDim.x) *reinterpret_cast<uint4*>(tileRow + (size_t)g * 2048) = make_uint4(0u, 0u, 0u, 0u);
             return;
         }
         if (t >= 225 && t < 235) {
-            const int layer = t - 225;
-            float* p = tile + (size_t)(layer * 58 + 56) * 512; /* K group 56 = k 224..227, group 57 = k 228..231 */
-            p[2] = 1.0f;
-            p[3] = 1.0f;
-            *reinterpret_cast<float4*>(p + 512) = make_float4(0.f, 0.f, 0.f, 0.f);
+            const uint32_t layer = (uint32_t)(t - 225);
+            if (bf16) {
+                /* K group 28 = k 224..231 (224 density, 225 angle, 226 and 227 the bias-carrying ones), group 29 = k 232..239 */
+                unsigned char* p = tileRow + (size_t)(layer * KG + 28) * 2048;
+                *reinterpret_cast<uint32_t*>(p + 4) = 0x3f803f80u;
+                *reinterpret_cast<uint2*>(p + 8) = make_uint2(0u, 0u);
+                *reinterpret_cast<uint4*>(p + 2048) = make_uint4(0u, 0u, 0u, 0u);
+            } else {
+                /* K group 56 = k 224..227, group 57 = k 228..231 */
+                float* p = reinterpret_cast<float*>(tileRow + (size_t)(layer * KG + 56) * 2048);
+                p[2] = 1.0f;
+                p[3] = 1.0f;
+                *reinterpret_cast<float4*>(p + 512) = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
         }
     }
     if (i >= n || t >= 225) return;
     const uint32_t src = gather ? gather[i] : i; /* input sample of output row i */
-    const size_t sampleStride = (size_t)layerStride * 10;
-    /* index of element k of layer `layer` of output row i in outF32 */
-    auto f32At = [&](int layer, int k) -> size_t {
-        if (!tiled) return (size_t)i * sampleStride + (size_t)layer * layerStride + k;
-        return (size_t)(i >> 7) * NETWORK_TILE_FLOATS + ((size_t)(layer * 58 + (k >> 2)) * 128 + (i & 127u)) * 4 + (k & 3);
+    const size_t sampleStride = (size_t)(layerStride > 0 ? layerStride : 0) * 10;
+    /* element k of layer `layer` of output row i: a float of the row-major layouts, or an element of the tile rounded to the operand type */
+    auto storeF = [&](int layer, int k, float v) {
+        if (!tiled) {
+            outF32[(size_t)i * sampleStride + (size_t)layer * layerStride + k] = v;
+        } else if (bf16) {
+            uint32_t u = __float_as_uint(v); /* round to nearest even */
+            u += 0x7fffu + ((u >> 16) & 1u);
+            *reinterpret_cast<uint16_t*>(tileRow + (size_t)((uint32_t)layer * KG + (uint32_t)(k >> 3)) * 2048 + (size_t)(k & 7) * 2) = (uint16_t)(u >> 16);
+        } else {
+            /* tf32 (10 mantissa bits), round to nearest: the tensor core would otherwise truncate */
+            *reinterpret_cast<uint32_t*>(tileRow + (size_t)((uint32_t)layer * KG + (uint32_t)(k >> 2)) * 2048 + (size_t)(k & 3) * 4) = (__float_as_uint(v) + 0x1000u) & 0xffffe000u;
+        }
     };
-    /* tf32 (10 mantissa bits), round to nearest: the tensor core would otherwise truncate */
-    auto tf32If = [&](float v) -> float { return tiled ? __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xffffe000u) : v; };
-    if (angle && outF32 && t < 10) outF32[f32At(t, 225)] = tf32If(angle[src]); /* disneyCamera.cu:32-35 */
+    if (angle && outF32 && t < 10) storeF(t, 225, angle[src]); /* disneyCamera.cu:32-35 */
     if (active && !active[src]) {
         if (outF32)
-            for (int layer = 0; layer < 10; layer++) outF32[f32At(layer, t)] = 0.0f;
+            for (int layer = 0; layer < 10; layer++) storeF(layer, t, 0.0f);
         return;
     }
     const V3 worldPos = mk(positions[3 * (size_t)src], positions[3 * (size_t)src + 1], positions[3 * (size_t)src + 2]);
@@ -597,7 +614,7 @@ __global__ void __launch_bounds__(256) k_descriptors(const __grid_constant__ Dev
         }
         const size_t o = (size_t)i * 2250 + (size_t)layer * 225 + t;
         if (outU8) outU8[o] = (uint8_t)(density * 255.0f); /* TFromFloat<uint8_t>, DisneyDescriptor.cuh:66-69 */
-        if (outF32) outF32[f32At(layer, t)] = tf32If(density);
+        if (outF32) storeF(layer, t, density);
         if (tapIndex) {
             const int nx = lv.nx[l0], ny = lv.ny[l0], nz = lv.nz[l0];
             tapIndex[4 * o + 0] = (int)fminf(fmaxf(floorf(uvw.x * (float)nx - 0.5f), -2.0f), (float)nx + 1.0f);
@@ -615,7 +632,7 @@ cudaError_t KernelSet<FAST>::descriptors(const DevScene& sc, const LevelTable& l
 {
     if (n == 0) return cudaSuccess;
     if (FAST && !mipTex) return cudaErrorInvalidValue; /* the FAST instantiation samples the mip-mapped texture */
-    const uint32_t blocks = layerStride == 0 ? (n + 127u) / 128u * 128u : n; /* tiled output: whole tiles */
+    const uint32_t blocks = layerStride <= 0 ? (n + 127u) / 128u * 128u : n; /* tiled output: whole tiles */
     k_descriptors<FAST><<<blocks, 256, 0, st>>>(sc, lv, layers, pos, dir, n, outU8, outF32, tapIndex, layerStride, angle, active, gather, mipTex);
     return cudaGetLastError();
 }

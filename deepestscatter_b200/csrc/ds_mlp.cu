@@ -34,45 +34,74 @@ float roundTf32(float x)
     return x;
 }
 
-constexpr uint32_t B_LBO = MLP_NPAD / 8 * 128; /* bytes between the two 4-float K groups of one MMA step: all 26 row groups */
+constexpr uint32_t B_LBO = MLP_NPAD / 8 * 128; /* bytes between two K groups (16 bytes of K each) of the weights: all 26 row groups */
 
-/* one K chunk of W [200][ld] (torch Linear layout), k in [k0, k0 + 8 * k8), zero beyond row 200, in the UMMA canonical K-major no-swizzle
- * layout: 8 x 16-byte core matrices, row groups 128 B apart, K groups B_LBO apart.  Columns kValid and kValid + 1 (when bias != NULL)
- * carry the bias split into two tf32 values: the A operand holds 1.0 there, so the MMA adds the bias at nearly fp32 precision */
-void appendWeightChunk(std::vector<uint8_t>& stream, const float* W, int ld, int k0, int k8, int kValid, const float* bias)
+/* bf16: fp32 truncated to 7 mantissa bits, round to nearest even (__float2bfloat16_rn) */
+uint16_t roundBf16(float x)
 {
+    uint32_t u;
+    memcpy(&u, &x, 4);
+    if ((u & 0x7f800000u) == 0x7f800000u) return (uint16_t)(u >> 16);
+    u += 0x7fffu + ((u >> 16) & 1u);
+    return (uint16_t)(u >> 16);
+}
+float bf16ToFloat(uint16_t h)
+{
+    const uint32_t u = (uint32_t)h << 16;
+    float x;
+    memcpy(&x, &u, 4);
+    return x;
+}
+
+/* The tensor-core kernel exists for two operand types.  G = K values per 16-byte K group: 4 (tf32, kept in 4-byte words) or 8 (bf16).  One MMA
+ * step consumes two K groups (K = 8 or 16), a chunk is up to four steps (K = 32 or 64), so chunk and stage sizes in bytes are the same. */
+
+/* one K chunk of W [200][ld] (torch Linear layout), k in [k0, k0 + 2 * G * steps), zero beyond row 200, in the UMMA canonical K-major no-swizzle
+ * layout: 8-row x 16-byte core matrices, row groups 128 B apart, K groups B_LBO apart.  Columns kValid and kValid + 1 (when bias != NULL)
+ * carry the bias split into a rounded value and the rounded remainder: the A operand holds 1.0 there, so the MMA adds the bias at nearly
+ * fp32 precision */
+void appendWeightChunk(std::vector<uint8_t>& stream, const float* W, int ld, int k0, int steps, int kValid, const float* bias, bool bf16)
+{
+    const int G = bf16 ? 8 : 4, E = bf16 ? 2 : 4;
     const size_t base = stream.size();
-    const int kc = 8 * k8;
-    stream.resize(base + (size_t)(kc / 4) * B_LBO, 0);
+    const int kc = 2 * G * steps;
+    stream.resize(base + (size_t)(kc / G) * B_LBO, 0);
     for (int kk = 0; kk < kc; ++kk)
         for (int n = 0; n < MLP_D; ++n) {
             const int k = k0 + kk;
             float v = 0.0f;
             if (k < kValid)
-                v = roundTf32(W[(size_t)n * ld + k]);
+                v = W[(size_t)n * ld + k];
             else if (bias && k == kValid)
-                v = roundTf32(bias[n]);
+                v = bias[n];
             else if (bias && k == kValid + 1)
-                v = roundTf32(bias[n] - roundTf32(bias[n]));
-            const size_t off = base + (size_t)(kk / 4) * B_LBO + (size_t)(n / 8) * 128 + (size_t)(n % 8) * 16 + (size_t)(kk % 4) * 4;
-            memcpy(&stream[off], &v, 4);
+                v = bias[n] - (bf16 ? bf16ToFloat(roundBf16(bias[n])) : roundTf32(bias[n]));
+            const size_t off = base + (size_t)(kk / G) * B_LBO + (size_t)(n / 8) * 128 + (size_t)(n % 8) * 16 + (size_t)(kk % G) * E;
+            if (bf16) {
+                const uint16_t h = roundBf16(v);
+                memcpy(&stream[off], &h, 2);
+            } else {
+                const float r = roundTf32(v);
+                memcpy(&stream[off], &r, 4);
+            }
         }
 }
 
-/* the chunks of one GEMM operand of K values (+ 2 bias columns when bias != NULL; padded to a multiple of 8): MLP_TC_KCHUNK at a time,
- * then the rest */
-void appendGemmPart(DisneyModelHost& out, const float* W, int ld, int K, const float* bias, uint8_t src, uint8_t layer, uint8_t dst, uint8_t gemm,
-                    bool first, bool waitAct, bool last, uint8_t epilogue)
+/* the chunks of one GEMM operand of K values (+ 2 bias columns when bias != NULL; padded to a whole number of MMA steps): four steps at a
+ * time, then the rest */
+void appendGemmPart(std::vector<uint8_t>& stream, std::vector<MlpChunk>& chunks, bool bf16, const float* W, int ld, int K, const float* bias, uint8_t src,
+                    uint8_t layer, uint8_t dst, uint8_t gemm, bool first, bool waitAct, bool last, uint8_t epilogue)
 {
-    const int kPad = (K + (bias ? 2 : 0) + 7) / 8 * 8;
-    for (int k0 = 0; k0 < kPad; k0 += MLP_TC_KCHUNK) {
-        const int k8 = (kPad - k0 >= MLP_TC_KCHUNK ? MLP_TC_KCHUNK : kPad - k0) / 8;
+    const int G = bf16 ? 8 : 4, stepK = 2 * G, chunkK = 4 * stepK;
+    const int kPad = (K + (bias ? 2 : 0) + stepK - 1) / stepK * stepK;
+    for (int k0 = 0; k0 < kPad; k0 += chunkK) {
+        const int steps = (kPad - k0 >= chunkK ? chunkK : kPad - k0) / stepK;
         MlpChunk c{};
-        c.wOffset = (uint32_t)out.stream.size();
-        appendWeightChunk(out.stream, W, ld, k0, k8, K, bias);
-        c.wBytes = (uint32_t)out.stream.size() - c.wOffset;
-        c.k8 = (uint16_t)k8;
-        c.aKGroup = (uint16_t)(src == 0 ? k0 / 4 : k0);
+        c.wOffset = (uint32_t)stream.size();
+        appendWeightChunk(stream, W, ld, k0, steps, K, bias, bf16);
+        c.wBytes = (uint32_t)stream.size() - c.wOffset;
+        c.k8 = (uint16_t)steps;
+        c.aKGroup = (uint16_t)(src == 0 ? k0 / G : k0);
         c.src = src;
         c.layer = layer;
         c.dst = dst;
@@ -80,11 +109,11 @@ void appendGemmPart(DisneyModelHost& out, const float* W, int ld, int K, const f
         c.flags = 0;
         if (k0 == 0 && first) c.flags |= MLP_FIRST;
         if (k0 == 0 && waitAct) c.flags |= MLP_WAIT_ACT;
-        if (k0 + MLP_TC_KCHUNK >= kPad && last) {
+        if (k0 + chunkK >= kPad && last) {
             c.flags |= MLP_LAST;
             c.epilogue = epilogue;
         }
-        out.chunks.push_back(c);
+        chunks.push_back(c);
     }
 }
 
@@ -137,22 +166,27 @@ void packDisneyModel(const float* w, DisneyModelHost& out)
     for (int c = 0; c < MLP_D; ++c) out.w4b4[c] = fc4W[c];
     out.w4b4[MLP_NPAD] = fc4B[0];
 
-    /* tensor-core kernel: the program.  Biases ride in the GEMMs: the descriptor layer is staged with z[226] = z[227] = 1 and the
-     * activation buffer holds 1 in columns 200 and 201 */
-    out.stream.clear();
-    out.chunks.clear();
-    for (int i = 0; i < MLP_NB; ++i) {
-        /* h = relu(z_i . f1z^T + o . f1o^T + b).  The descriptor part goes first: it does not depend on the previous block's epilogue, so its
-         * MMAs run while the workers are still writing o; o = 0 in block 0 (DisneyModel.py:34), whose f1o part is skipped */
-        appendGemmPart(out, blk[i].f1zW, MLP_ZD, MLP_ZD, &out.bias[(size_t)(2 * i) * MLP_NPAD], 1, (uint8_t)i, 0, (uint8_t)(2 * i), true, false, i == 0,
-                       MLP_EPI_H);
-        if (i > 0) appendGemmPart(out, blk[i].f1oW, MLP_D, MLP_D, nullptr, 0, 0, 0, (uint8_t)(2 * i), false, true, true, MLP_EPI_H);
-        /* o = relu(h . f2^T + b + o): D2 still holds o, the MMAs accumulate on top of it */
-        appendGemmPart(out, blk[i].f2W, MLP_D, MLP_D, blk[i].f2B, 0, 0, 1, (uint8_t)(2 * i + 1), i == 0, true, true, MLP_EPI_O);
+    /* tensor-core kernel: the program, once per operand type.  Biases ride in the GEMMs: the descriptor layer is staged with z[226] = z[227] = 1
+     * and the activation buffer holds 1 in columns 200 and 201 */
+    for (int t = 0; t < 2; ++t) {
+        const bool bf16 = t == 1;
+        std::vector<uint8_t>& stream = bf16 ? out.streamBf16 : out.stream;
+        std::vector<MlpChunk>& chunks = bf16 ? out.chunksBf16 : out.chunks;
+        stream.clear();
+        chunks.clear();
+        for (int i = 0; i < MLP_NB; ++i) {
+            /* h = relu(z_i . f1z^T + o . f1o^T + b).  The descriptor part goes first: it does not depend on the previous block's epilogue, so
+             * its MMAs run while the workers are still writing o; o = 0 in block 0 (DisneyModel.py:34), whose f1o part is skipped */
+            appendGemmPart(stream, chunks, bf16, blk[i].f1zW, MLP_ZD, MLP_ZD, &out.bias[(size_t)(2 * i) * MLP_NPAD], 1, (uint8_t)i, 0, (uint8_t)(2 * i), true,
+                           false, i == 0, MLP_EPI_H);
+            if (i > 0) appendGemmPart(stream, chunks, bf16, blk[i].f1oW, MLP_D, MLP_D, nullptr, 0, 0, 0, (uint8_t)(2 * i), false, true, true, MLP_EPI_H);
+            /* o = relu(h . f2^T + b + o): D2 still holds o, the MMAs accumulate on top of it */
+            appendGemmPart(stream, chunks, bf16, blk[i].f2W, MLP_D, MLP_D, blk[i].f2B, 0, 0, 1, (uint8_t)(2 * i + 1), i == 0, true, true, MLP_EPI_O);
+        }
+        appendGemmPart(stream, chunks, bf16, fc0W, MLP_D, MLP_D, fc0B, 0, 0, 0, 20, true, true, true, MLP_EPI_H);
+        /* into D2 (the residual is no longer needed): its first MMAs start while the epilogue of the layer before is still reading D1 */
+        appendGemmPart(stream, chunks, bf16, fc2W, MLP_D, MLP_D, fc2B, 0, 0, 1, 21, true, true, true, MLP_EPI_OUT);
     }
-    appendGemmPart(out, fc0W, MLP_D, MLP_D, fc0B, 0, 0, 0, 20, true, true, true, MLP_EPI_H);
-    /* into D2 (the residual is no longer needed): its first MMAs start while the epilogue of the layer before is still reading D1 */
-    appendGemmPart(out, fc2W, MLP_D, MLP_D, fc2B, 0, 0, 1, 21, true, true, true, MLP_EPI_OUT);
 }
 
 /* ------------------------------------------------------------------------------------------------ fp32 kernel */
@@ -302,22 +336,23 @@ struct MlpProgram {
 };
 constexpr uint32_t TC_A_LBO = TC_M / 8 * 128;           /* 2048: bytes between 4-float K groups of the activations (all 16 row groups) */
 constexpr uint32_t TC_SBO = 128;                        /* bytes between 8-row groups */
-constexpr uint32_t TC_ACT_KGROUPS = MLP_NPAD / 4;       /* 200 activations, the two constant-one columns, padding to 208 */
+constexpr uint32_t TC_ACT_KGROUPS = MLP_NPAD / 4;       /* 200 activations, the two constant-one columns, padding to 208 (tf32; bf16 needs half) */
 constexpr uint32_t TC_ACT_BYTES = TC_ACT_KGROUPS * TC_A_LBO; /* 106496 */
-constexpr uint32_t TC_WSTAGE_BYTES = MLP_TC_KCHUNK / 4 * B_LBO;    /* 26624 */
-constexpr uint32_t TC_ZSTAGE_BYTES = MLP_TC_KCHUNK / 4 * TC_A_LBO; /* 16384 */
+constexpr uint32_t TC_WSTAGE_BYTES = 8 * B_LBO;    /* 26624: a chunk is 8 K groups of 16 bytes: K = 32 (tf32) or 64 (bf16) */
+constexpr uint32_t TC_ZSTAGE_BYTES = 8 * TC_A_LBO; /* 16384 */
 constexpr uint32_t TC_OFF_W = TC_ACT_BYTES;
 constexpr uint32_t TC_OFF_Z = TC_OFF_W + TC_WSTAGES * TC_WSTAGE_BYTES;
 constexpr uint32_t TC_OFF_BAR = TC_OFF_Z + TC_ZSTAGES * TC_ZSTAGE_BYTES;
 constexpr uint32_t TC_SMEM = TC_OFF_BAR + 256;
 static_assert(sizeof(MlpChunk) == 20, "MlpChunk layout (include/ds_abi.h documents it)");
 static_assert(TC_SMEM <= 232448, "shared memory budget");
-static_assert(MLP_TC_KCHUNK == 32, "the epilogue pieces are the K chunks of the next GEMM");
 static_assert(((TC_ACT_BYTES + TC_WSTAGES * TC_WSTAGE_BYTES + TC_ZSTAGES * TC_ZSTAGE_BYTES) >> 4) + 3 * (2 * 3328 >> 4) < 0x4000, "descriptor start field");
 constexpr uint32_t TC_TMEM_COLS = 512, TC_D2_COL = 256;
 /* instruction descriptor (cute/arch/mma_sm100_desc.hpp InstrDescriptor): D = F32 (bits 4-5 = 1), A = B = TF32 (bits 7-9, 10-12 = 2),
  * both K-major (bits 15, 16 = 0), N >> 3 at bits 17-22, M >> 4 at bits 24-28 */
 constexpr uint32_t TC_IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(MLP_NPAD >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
+/* A = B = BF16 (format 1), kind::f16 */
+constexpr uint32_t TC_IDESC_BF16 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(MLP_NPAD >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
 
 /* barrier slots (8 bytes each) */
 enum { BAR_WFULL = 0, BAR_WFREE = BAR_WFULL + TC_WSTAGES, BAR_ZFULL = BAR_WFREE + TC_WSTAGES, BAR_ZFREE = BAR_ZFULL + TC_ZSTAGES,
@@ -369,17 +404,29 @@ __device__ __forceinline__ bool mbarWait(uint32_t bar, uint32_t parity, volatile
 __device__ __forceinline__ uint32_t ummaDescLo(uint32_t saddr, uint32_t lbo) { return ((saddr & 0x3ffffu) >> 4) | ((lbo >> 4) << 16); }
 constexpr uint32_t TC_DESC_HI = (TC_SBO >> 4) | (1u << 14);
 
-__device__ __forceinline__ void ummaTf32(uint32_t tmemD, uint32_t descALo, uint32_t descBLo, uint32_t accumulate)
+template <bool BF16>
+__device__ __forceinline__ void ummaIssue(uint32_t tmemD, uint32_t descALo, uint32_t descBLo, uint32_t accumulate)
 {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
-        "mov.b64 da, {%1, %3};\n\t"
-        "mov.b64 db, {%2, %3};\n\t"
-        "setp.ne.b32 p, %5, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %4, p;\n\t}"
-        ::"r"(tmemD), "r"(descALo), "r"(descBLo), "r"(TC_DESC_HI), "r"(TC_IDESC), "r"(accumulate)
-        : "memory");
+    if (BF16)
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+            "mov.b64 da, {%1, %3};\n\t"
+            "mov.b64 db, {%2, %3};\n\t"
+            "setp.ne.b32 p, %5, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t}"
+            ::"r"(tmemD), "r"(descALo), "r"(descBLo), "r"(TC_DESC_HI), "r"(TC_IDESC_BF16), "r"(accumulate)
+            : "memory");
+    else
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+            "mov.b64 da, {%1, %3};\n\t"
+            "mov.b64 db, {%2, %3};\n\t"
+            "setp.ne.b32 p, %5, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %4, p;\n\t}"
+            ::"r"(tmemD), "r"(descALo), "r"(descBLo), "r"(TC_DESC_HI), "r"(TC_IDESC), "r"(accumulate)
+            : "memory");
 }
+
 /* elect.sync: one lane of the (converged) warp */
 __device__ __forceinline__ bool electOne()
 {
@@ -440,41 +487,60 @@ __device__ __forceinline__ float toTf32(float x)
     return __uint_as_float(u);
 }
 
-/* one piece of an epilogue: N accumulator columns of the thread's row, starting at col0 (a multiple of 16).  The bias is already in the
- * accumulator (it rides in the GEMM), so this is relu + the write-back */
-template <int N>
-__device__ __forceinline__ void epiloguePiece(uint32_t tacc, int col0, int epilogue, unsigned char* actRow, const float* __restrict__ w4, float& y)
+__device__ __forceinline__ uint32_t packBf16(float lo, float hi)
+{
+    uint32_t u;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(u) : "f"(hi), "f"(lo)); /* first source -> upper half */
+    return u;
+}
+
+/* N accumulator columns of the thread's row, starting at col0 (a multiple of 16).  The bias is already in the accumulator (it rides in the
+ * GEMM), so this is relu + the write-back: tf32 as 4-column float4 K groups, bf16 as 8-column K groups */
+template <int N, bool BF16>
+__device__ __forceinline__ void epilogueCols(uint32_t tacc, int col0, int epilogue, unsigned char* actRow, const float* __restrict__ w4, float& y)
 {
     uint32_t v[N];
     tmemLoad(tacc + (uint32_t)col0, v);
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-    for (int q = 0; q < N / 4; ++q) {
-        const int col = col0 + 4 * q;
-        const float x0 = fmaxf(__uint_as_float(v[4 * q]), 0.0f), x1 = fmaxf(__uint_as_float(v[4 * q + 1]), 0.0f);
-        const float x2 = fmaxf(__uint_as_float(v[4 * q + 2]), 0.0f), x3 = fmaxf(__uint_as_float(v[4 * q + 3]), 0.0f);
-        if (epilogue == MLP_EPI_OUT) {
-            const float4 ww = __ldg(reinterpret_cast<const float4*>(w4 + col)); /* zero beyond column 200 */
-            y = fmaf(x0, ww.x, y);
-            y = fmaf(x1, ww.y, y);
-            y = fmaf(x2, ww.z, y);
-            y = fmaf(x3, ww.w, y);
-        } else {
-            v[4 * q] = __float_as_uint(x0);
-            v[4 * q + 1] = __float_as_uint(x1);
-            v[4 * q + 2] = __float_as_uint(x2);
-            v[4 * q + 3] = __float_as_uint(x3);
+    for (int q = 0; q < N; ++q) v[q] = __float_as_uint(fmaxf(__uint_as_float(v[q]), 0.0f));
+    if (epilogue == MLP_EPI_OUT) {
+#pragma unroll
+        for (int q = 0; q < N / 4; ++q) {
+            const float4 ww = __ldg(reinterpret_cast<const float4*>(w4 + col0 + 4 * q)); /* zero beyond column 200 */
+            y = fmaf(__uint_as_float(v[4 * q]), ww.x, y);
+            y = fmaf(__uint_as_float(v[4 * q + 1]), ww.y, y);
+            y = fmaf(__uint_as_float(v[4 * q + 2]), ww.z, y);
+            y = fmaf(__uint_as_float(v[4 * q + 3]), ww.w, y);
+        }
+        return;
+    }
+    if (BF16) {
+#pragma unroll
+        for (int q = 0; q < N / 8; ++q) {
+            const int col = col0 + 8 * q;
             if (col < MLP_D)
-                *reinterpret_cast<float4*>(actRow + (uint32_t)(col / 4) * TC_A_LBO) = make_float4(toTf32(x0), toTf32(x1), toTf32(x2), toTf32(x3));
+                *reinterpret_cast<uint4*>(actRow + (uint32_t)(col / 8) * TC_A_LBO) =
+                    make_uint4(packBf16(__uint_as_float(v[8 * q]), __uint_as_float(v[8 * q + 1])), packBf16(__uint_as_float(v[8 * q + 2]), __uint_as_float(v[8 * q + 3])),
+                               packBf16(__uint_as_float(v[8 * q + 4]), __uint_as_float(v[8 * q + 5])), packBf16(__uint_as_float(v[8 * q + 6]), __uint_as_float(v[8 * q + 7])));
+        }
+    } else {
+#pragma unroll
+        for (int q = 0; q < N / 4; ++q) {
+            const int col = col0 + 4 * q;
+            if (col < MLP_D)
+                *reinterpret_cast<float4*>(actRow + (uint32_t)(col / 4) * TC_A_LBO) =
+                    make_float4(toTf32(__uint_as_float(v[4 * q])), toTf32(__uint_as_float(v[4 * q + 1])), toTf32(__uint_as_float(v[4 * q + 2])),
+                                toTf32(__uint_as_float(v[4 * q + 3])));
         }
     }
     /* the post-activation value is the residual of the next block: the next MMAs accumulate on top of it */
     if (epilogue == MLP_EPI_O) tmemStore(tacc + (uint32_t)col0, v);
 }
 
-template <bool PROFILE>
+template <bool PROFILE, bool BF16>
 __global__ void __launch_bounds__(TC_THREADS, 1)
-    k_disney_mlp_tc(const __grid_constant__ MlpProgram prog, const float* __restrict__ tiles, uint32_t nRows, const uint8_t* __restrict__ stream,
+    k_disney_mlp_tc(const __grid_constant__ MlpProgram prog, const void* __restrict__ tiles, uint32_t nRows, const uint8_t* __restrict__ stream,
                     const float* __restrict__ w4b4, float* __restrict__ out, uint32_t* __restrict__ errorOut, unsigned long long* __restrict__ prof)
 {
     extern __shared__ __align__(1024) unsigned char smem[];
@@ -517,8 +583,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         if (lane == 0) {
             long long wFree = 0, zFree = 0;
             bool ok = true;
-            const char* tile = reinterpret_cast<const char*>(tiles + (size_t)blockIdx.x * NETWORK_TILE_FLOATS);
-            constexpr uint32_t LAYER_BYTES = 58u * 128u * 16u; /* one descriptor layer of the tile: 58 K groups x 128 rows x 4 floats */
+            /* one descriptor layer of the tile: 58 K groups of 4 floats (tf32) or 30 K groups of 8 bf16, x 128 rows x 16 bytes */
+            constexpr uint32_t G = BF16 ? 8u : 4u;
+            constexpr uint32_t LAYER_BYTES = (BF16 ? 30u : 58u) * TC_A_LBO;
+            const char* tile = reinterpret_cast<const char*>(tiles) + (size_t)blockIdx.x * (MLP_NB * LAYER_BYTES);
             uint32_t zFills = 0;
             asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(tile), "r"(LAYER_BYTES) : "memory");
             for (int c = 0; c < nChunks && ok; ++c) {
@@ -542,7 +610,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
                     mbarExpectTx(zbar, zBytes);
                     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
                                      actAddr + TC_OFF_Z + (uint32_t)zs * TC_ZSTAGE_BYTES),
-                                 "l"(tile + (size_t)ch.layer * LAYER_BYTES + (size_t)(ch.aKGroup / 4) * TC_A_LBO), "r"(zBytes), "r"(zbar)
+                                 "l"(tile + (size_t)ch.layer * LAYER_BYTES + (size_t)(ch.aKGroup / G) * TC_A_LBO), "r"(zBytes), "r"(zbar)
                                  : "memory");
                     zFills++;
                     /* the next layer of the tile starts its way into L2 a whole block ahead */
@@ -581,10 +649,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
                 const int k8 = ch.k8;
                 if (electOne()) {
                     /* one MMA per 8 k values: two 4-float K groups of each operand, i.e. 2 * LBO bytes further per step */
-                    ummaTf32(d, aLo, bLo, (ch.flags & MLP_FIRST) ? 0u : 1u);
-                    if (k8 > 1) ummaTf32(d, aLo + (2u * TC_A_LBO >> 4), bLo + (2u * B_LBO >> 4), 1u);
-                    if (k8 > 2) ummaTf32(d, aLo + 2u * (2u * TC_A_LBO >> 4), bLo + 2u * (2u * B_LBO >> 4), 1u);
-                    if (k8 > 3) ummaTf32(d, aLo + 3u * (2u * TC_A_LBO >> 4), bLo + 3u * (2u * B_LBO >> 4), 1u);
+                    ummaIssue<BF16>(d, aLo, bLo, (ch.flags & MLP_FIRST) ? 0u : 1u);
+                    if (k8 > 1) ummaIssue<BF16>(d, aLo + (2u * TC_A_LBO >> 4), bLo + (2u * B_LBO >> 4), 1u);
+                    if (k8 > 2) ummaIssue<BF16>(d, aLo + 2u * (2u * TC_A_LBO >> 4), bLo + 2u * (2u * B_LBO >> 4), 1u);
+                    if (k8 > 3) ummaIssue<BF16>(d, aLo + 3u * (2u * TC_A_LBO >> 4), bLo + 3u * (2u * B_LBO >> 4), 1u);
                     ummaCommit(barBase + 8 * (BAR_WFREE + ws));
                     if (ch.src == 1) ummaCommit(barBase + 8 * (BAR_ZFREE + zs));
                     if (ch.flags & MLP_LAST) ummaCommit(barBase + 8 * BAR_GEMM);
@@ -609,8 +677,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         const uint32_t tmemRow = tmemBase + ((uint32_t)((warp & 3) * 32) << 16);
         /* the constant-one columns 200, 201 that carry the biases through the GEMMs; 202..207 are padding */
         if (half == 0) {
-            *reinterpret_cast<float4*>(actS + (uint32_t)(MLP_D / 4) * TC_A_LBO + rowOff) = make_float4(1.0f, 1.0f, 0.0f, 0.0f);
-            *reinterpret_cast<float4*>(actS + (uint32_t)(MLP_D / 4 + 1) * TC_A_LBO + rowOff) = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+            if (BF16) {
+                *reinterpret_cast<uint4*>(actS + (uint32_t)(MLP_D / 8) * TC_A_LBO + rowOff) = make_uint4(0x3f803f80u, 0u, 0u, 0u); /* bf16 1, 1, 0 x 6 */
+            } else {
+                *reinterpret_cast<float4*>(actS + (uint32_t)(MLP_D / 4) * TC_A_LBO + rowOff) = make_float4(1.0f, 1.0f, 0.0f, 0.0f);
+                *reinterpret_cast<float4*>(actS + (uint32_t)(MLP_D / 4 + 1) * TC_A_LBO + rowOff) = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+            }
         }
         uint32_t gemmWaits = 0;
         bool ok = true;
@@ -627,19 +699,23 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
                 const uint32_t tacc = tmemRow + (ch.dst ? TC_D2_COL : 0u);
                 const int epilogue = ch.epilogue;
                 float y = 0.0f;
-                const int pieceBegin = half ? 4 : 0, pieceEnd = half ? TC_PIECES : 4;
+                /* columns [0, 128) belong to the first half of the workers, [128, 208) to the second; a piece (= K chunk of the next GEMM: 32
+                 * columns for tf32 operands, 64 for bf16) is handed over as soon as it is complete */
+                constexpr int PIECE_COLS = BF16 ? 64 : 32;
+                const int colEnd = half ? MLP_NPAD : 128;
 #pragma unroll 1
-                for (int p = pieceBegin; p < pieceEnd; ++p) {
-                    if (p < TC_PIECES - 1)
-                        epiloguePiece<32>(tacc, 32 * p, epilogue, actS + rowOff, w4b4, y);
+                for (int col0 = half ? 128 : 0; col0 < colEnd; col0 += 32) {
+                    if (col0 + 32 <= MLP_NPAD)
+                        epilogueCols<32, BF16>(tacc, col0, epilogue, actS + rowOff, w4b4, y);
                     else
-                        epiloguePiece<16>(tacc, 32 * p, epilogue, actS + rowOff, w4b4, y);
-                    if (epilogue != MLP_EPI_OUT) {
+                        epilogueCols<16, BF16>(tacc, col0, epilogue, actS + rowOff, w4b4, y);
+                    const int done = min(col0 + 32, MLP_NPAD);
+                    if (epilogue != MLP_EPI_OUT && (done % PIECE_COLS == 0 || done == MLP_NPAD)) {
                         /* hand the piece over: TMEM store done, shared-memory stores visible to the tensor core's async proxy */
                         if (epilogue == MLP_EPI_O) asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
                         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                        mbarArrive(barBase + 8 * (BAR_ACT + p));
+                        mbarArrive(barBase + 8 * (BAR_ACT + (done - 1) / PIECE_COLS));
                     }
                 }
                 if (epilogue == MLP_EPI_OUT) {
@@ -671,22 +747,26 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     }
 }
 
-cudaError_t launchDisneyMlpTc(const DisneyModelDev& m, const float* tiles, uint32_t nRows, float* out, cudaStream_t st, unsigned long long* prof)
+template <bool PROFILE, bool BF16>
+static cudaError_t launchTc(const MlpProgram& prog, const void* tiles, uint32_t nRows, const uint8_t* stream, const float* w4b4, float* out, uint32_t* error,
+                            unsigned long long* prof, cudaStream_t st)
+{
+    cudaError_t e = cudaFuncSetAttribute(k_disney_mlp_tc<PROFILE, BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM);
+    if (e != cudaSuccess) return e;
+    k_disney_mlp_tc<PROFILE, BF16><<<(nRows + TC_M - 1) / TC_M, TC_THREADS, TC_SMEM, st>>>(prog, tiles, nRows, stream, w4b4, out, error, prof);
+    return cudaGetLastError();
+}
+
+cudaError_t launchDisneyMlpTc(const DisneyModelDev& m, const void* tiles, uint32_t nRows, float* out, cudaStream_t st, unsigned long long* prof, bool bf16)
 {
     if (nRows == 0) return cudaSuccess;
-    if (!m.program) return cudaErrorInvalidValue;
-    const unsigned blocks = (nRows + TC_M - 1) / TC_M;
-    cudaError_t e;
-    if (prof) {
-        e = cudaFuncSetAttribute(k_disney_mlp_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM);
-        if (e != cudaSuccess) return e;
-        k_disney_mlp_tc<true><<<blocks, TC_THREADS, TC_SMEM, st>>>(*m.program, tiles, nRows, m.stream, m.w4b4, out, m.error, prof);
-    } else {
-        e = cudaFuncSetAttribute(k_disney_mlp_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM);
-        if (e != cudaSuccess) return e;
-        k_disney_mlp_tc<false><<<blocks, TC_THREADS, TC_SMEM, st>>>(*m.program, tiles, nRows, m.stream, m.w4b4, out, m.error, nullptr);
-    }
-    return cudaGetLastError();
+    const MlpProgram* prog = bf16 ? m.programBf16 : m.program;
+    const uint8_t* stream = bf16 ? m.streamBf16 : m.stream;
+    if (!prog || !stream) return cudaErrorInvalidValue;
+    if (bf16) return prof ? launchTc<true, true>(*prog, tiles, nRows, stream, m.w4b4, out, m.error, prof, st)
+                          : launchTc<false, true>(*prog, tiles, nRows, stream, m.w4b4, out, m.error, nullptr, st);
+    return prof ? launchTc<true, false>(*prog, tiles, nRows, stream, m.w4b4, out, m.error, prof, st)
+                : launchTc<false, false>(*prog, tiles, nRows, stream, m.w4b4, out, m.error, nullptr, st);
 }
 
 /* the chunk table as the kernel-parameter block (host memory, owned by the model) */
@@ -701,36 +781,45 @@ MlpProgram* makeMlpProgram(const std::vector<MlpChunk>& chunks)
 }
 void freeMlpProgram(MlpProgram* p) { delete p; }
 
-/* DisneyNetworkInput rows [n][10][226] -> the tiles the tensor-core kernel consumes (tf32-rounded; k 226, 227 = 1; padding rows zero):
- * one thread per (row, layer, K group) */
-__global__ void __launch_bounds__(256) k_network_input_to_tiles(const float* __restrict__ in, uint32_t nRows, uint32_t nPadded, float* __restrict__ tiles)
+/* DisneyNetworkInput rows [n][10][226] -> the tiles the tensor-core kernel consumes (rounded to the operand type; k 226, 227 = 1; the rest of
+ * the layer's K padding and the padding rows zero): one thread per (row, layer, K group) */
+template <bool BF16>
+__global__ void __launch_bounds__(256) k_network_input_to_tiles(const float* __restrict__ in, uint32_t nRows, uint32_t nPadded, void* __restrict__ tiles)
 {
+    constexpr uint32_t G = BF16 ? 8u : 4u, KG = BF16 ? 30u : 58u; /* K values per group, groups per layer */
     const size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= (size_t)nPadded * 580) return;
-    const uint32_t row = (uint32_t)(g / 580);
-    const uint32_t lk = (uint32_t)(g - (size_t)row * 580); /* layer * 58 + K group */
-    const uint32_t layer = lk / 58, kg = lk % 58;
-    float v[4] = {0.f, 0.f, 0.f, 0.f};
-    if (row < nRows) {
-        const float* src = in + ((size_t)row * MLP_NB + layer) * MLP_ZD;
+    if (g >= (size_t)nPadded * (MLP_NB * KG)) return;
+    const uint32_t row = (uint32_t)(g / (MLP_NB * KG));
+    const uint32_t lk = (uint32_t)(g - (size_t)row * (MLP_NB * KG)); /* layer * KG + K group */
+    const uint32_t layer = lk / KG, kg = lk % KG;
+    float v[G];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            const uint32_t k = kg * 4 + e;
+    for (uint32_t e = 0; e < G; ++e) {
+        const uint32_t k = kg * G + e;
+        v[e] = 0.0f;
+        if (row < nRows) {
             if (k < (uint32_t)MLP_ZD)
-                v[e] = __uint_as_float((__float_as_uint(__ldg(src + k)) + 0x1000u) & 0xffffe000u); /* tf32, round to nearest */
+                v[e] = __ldg(in + ((size_t)row * MLP_NB + layer) * MLP_ZD + k);
             else if (k < (uint32_t)MLP_ZD + 2)
                 v[e] = 1.0f;
         }
     }
-    *reinterpret_cast<float4*>(tiles + (size_t)(row >> 7) * NETWORK_TILE_FLOATS + ((size_t)lk * 128 + (row & 127u)) * 4) = make_float4(v[0], v[1], v[2], v[3]);
+    unsigned char* dst = reinterpret_cast<unsigned char*>(tiles) + ((size_t)(row >> 7) * (MLP_NB * KG) + lk) * TC_A_LBO + (size_t)(row & 127u) * 16;
+    if (BF16)
+        *reinterpret_cast<uint4*>(dst) = make_uint4(packBf16(v[0], v[1]), packBf16(v[2], v[3]), packBf16(v[G - 4], v[G - 3]), packBf16(v[G - 2], v[G - 1]));
+    else
+        *reinterpret_cast<float4*>(dst) = make_float4(toTf32(v[0]), toTf32(v[1]), toTf32(v[2]), toTf32(v[3]));
 }
 
-cudaError_t launchNetworkInputToTiles(const float* in, uint32_t nRows, float* tiles, cudaStream_t st)
+cudaError_t launchNetworkInputToTiles(const float* in, uint32_t nRows, void* tiles, cudaStream_t st, bool bf16)
 {
     if (nRows == 0) return cudaSuccess;
     const uint32_t nPadded = (nRows + 127u) / 128u * 128u;
-    const size_t total = (size_t)nPadded * 580;
-    k_network_input_to_tiles<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(in, nRows, nPadded, tiles);
+    const size_t total = (size_t)nPadded * MLP_NB * (bf16 ? 30 : 58);
+    if (bf16)
+        k_network_input_to_tiles<true><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(in, nRows, nPadded, tiles);
+    else
+        k_network_input_to_tiles<false><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(in, nRows, nPadded, tiles);
     return cudaGetLastError();
 }
 

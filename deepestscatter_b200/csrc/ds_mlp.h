@@ -22,7 +22,6 @@ constexpr int MLP_D = 200;      /* DisneyModel.BLOCK_DIMENSION */
 constexpr int MLP_NB = 10;      /* DisneyModel.BLOCK_COUNT */
 constexpr int MLP_ZD = 226;     /* DESCRIPTOR_LAYER_WITH_ANGLE_DIMENSION */
 constexpr int MLP_NPAD = 208;   /* output width padded to a multiple of 16 (UMMA N for M = 128) */
-constexpr int MLP_TC_KCHUNK = 32; /* K values per weight chunk of the tensor-core kernel's stream (four MMA steps) */
 constexpr int MLP_GEMMS = 22;   /* 2 per block + fullyConnected.0 + fullyConnected.2 */
 constexpr size_t MLP_WEIGHT_COUNT = (size_t)MLP_NB * (MLP_D * MLP_ZD + MLP_D + 2 * (MLP_D * MLP_D + MLP_D)) + 2 * (MLP_D * MLP_D + MLP_D) + MLP_D + 1;
 
@@ -30,8 +29,8 @@ constexpr size_t MLP_WEIGHT_COUNT = (size_t)MLP_NB * (MLP_D * MLP_ZD + MLP_D + 2
 struct MlpChunk {
     uint32_t wOffset;  /* byte offset of the chunk's weights in the packed stream */
     uint32_t wBytes;   /* (k8 * 2) * MLP_NPAD * 16 */
-    uint16_t k8;       /* number of K = 8 MMA steps in the chunk (1..MLP_TC_KCHUNK / 8) */
-    uint16_t aKGroup;  /* src 0: first 4-float K group of the activation buffer; src 1: first k of the descriptor layer */
+    uint16_t k8;       /* number of MMA steps in the chunk (1..4): K = 8 each for tf32 operands, 16 for bf16 */
+    uint16_t aKGroup;  /* src 0: first 16-byte K group of the activation buffer; src 1: first k of the descriptor layer */
     uint8_t src;       /* 0 = activation buffer, 1 = descriptor layer (z) */
     uint8_t layer;     /* src 1: descriptor layer index */
     uint8_t dst;       /* accumulator: 0 = D1 (h), 1 = D2 (o, carries the residual) */
@@ -49,7 +48,9 @@ struct DisneyModelDev {
     float* wT = nullptr;       /* fp32 kernel: per GEMM W^T [K][200] (K = 426 for the first GEMM of a block: o rows, then z rows) */
     float* bias = nullptr;     /* [22][208]; the two biases of a block's first GEMM are pre-summed */
     float* w4b4 = nullptr;     /* fullyConnected.4: 200 weights, zero padding to 208, bias at [208] */
-    uint8_t* stream = nullptr; /* tensor-core kernel: weights in UMMA canonical K-major layout, in consumption order */
+    uint8_t* stream = nullptr; /* tensor-core kernel: weights in UMMA canonical K-major layout, in consumption order (tf32 operands) */
+    uint8_t* streamBf16 = nullptr; /* the same for bf16 operands (option mlp_bf16) */
+    struct MlpProgram* programBf16 = nullptr;
     struct MlpProgram* program = nullptr; /* host: the chunk table, passed to the kernel as its (grid-constant) parameter block */
     int nChunks = 0;
     uint32_t* error = nullptr; /* device word: non-zero if a barrier wait of the tensor-core kernel timed out */
@@ -60,8 +61,8 @@ struct DisneyModelDev {
 /* host-side packing of the flat state_dict array (include/ds_abi.h: ds_disney_model_load) */
 struct DisneyModelHost {
     std::vector<float> wT, bias, w4b4;
-    std::vector<uint8_t> stream;
-    std::vector<MlpChunk> chunks;
+    std::vector<uint8_t> stream, streamBf16;      /* tf32 / bf16 operands */
+    std::vector<MlpChunk> chunks, chunksBf16;
 };
 void packDisneyModel(const float* weights, DisneyModelHost& out);
 struct MlpProgram* makeMlpProgram(const std::vector<MlpChunk>& chunks); /* NULL if the table is too long */
@@ -73,9 +74,12 @@ cudaError_t launchDisneyMlpF32(const DisneyModelDev& m, const float* in, const u
 /* tensor-core kernel: the rows come as 128-row tiles in the layout its MMAs read straight from shared memory (ds_kernels.h
  * NETWORK_TILE_FLOATS: [layer][K group][row][4], so that the K chunk of a layer is one contiguous block a bulk copy can fetch); out[i] for
  * i < nRows.  prof (may be NULL): 16 device words; block 0 leaves its cycle accounting there */
-cudaError_t launchDisneyMlpTc(const DisneyModelDev& m, const float* tiles, uint32_t nRows, float* out, cudaStream_t st, unsigned long long* prof = nullptr);
-/* [nRows][10][226] -> ceil(nRows / 128) tiles */
-cudaError_t launchNetworkInputToTiles(const float* in, uint32_t nRows, float* tiles, cudaStream_t st);
+cudaError_t launchDisneyMlpTc(const DisneyModelDev& m, const void* tiles, uint32_t nRows, float* out, cudaStream_t st, unsigned long long* prof = nullptr,
+                              bool bf16 = false);
+/* [nRows][10][226] -> ceil(nRows / 128) tiles (networkTileBytes per tile) */
+cudaError_t launchNetworkInputToTiles(const float* in, uint32_t nRows, void* tiles, cudaStream_t st, bool bf16 = false);
+/* bytes of one 128-row tile of network input: tf32 operands [10][58][128][4 floats], bf16 operands [10][30][128][8 bf16] */
+inline size_t networkTileBytesOf(bool bf16) { return (size_t)10 * (bf16 ? 30 : 58) * 128 * 16; }
 /* indices of the rows with active[i] != 0: idx[0..*count), unordered */
 cudaError_t launchCompactActive(const uint8_t* active, uint32_t n, uint32_t* idx, uint32_t* count, cudaStream_t st);
 cudaError_t launchReverse(uint32_t* a, uint32_t n, cudaStream_t st); /* test hook: reverse the compacted order */

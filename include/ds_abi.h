@@ -235,17 +235,17 @@ int ds_blit_predicted(uint32_t frame_width, uint32_t frame_height, uint32_t rect
  * = ds_disney_model_weight_count() = 1 338 601 floats (deepestscatter_b200/disney_model.py: flatten_state_dict). */
 size_t ds_disney_model_weight_count(void);
 int ds_disney_model_load(DsContext* ctx, const float* weights, size_t count);
-/* Introspection, host only (no device needed): the program the tensor-core kernel runs for these weights -- the weight stream in
- * UMMA canonical K-major layout (8-row x 16-byte core matrices; row groups 128 B apart, 4-float K groups 26 * 128 B apart; 208 rows,
- * tf32-rounded) and the chunk table (20-byte records: u32 stream offset, u32 bytes, u16 K/8, u16 first K group (activations) or first k
- * (descriptor layer), u8 source, u8 layer, u8 accumulator, u8 flags 1 = overwrite / 2 = last of its GEMM / 4 = waits for the previous
- * epilogue, u8 epilogue 1 = relu -> activations / 2 = same + residual kept in tensor memory / 3 = output, u8 GEMM index, 2 pad).
- * Either output pointer may be NULL to query the sizes. */
-int ds_disney_model_pack(const float* weights, size_t count, void* stream_out, size_t stream_capacity, void* chunks_out, size_t chunks_capacity,
-                         size_t* stream_bytes, size_t* chunk_count);
+/* Introspection, host only (no device needed): the program the tensor-core kernel runs for these weights -- the weight stream in UMMA
+ * canonical K-major no-swizzle layout (8-row x 16-byte core matrices; row groups 128 B apart, 16-byte K groups 26 * 128 B apart; 208 rows;
+ * bf16 = 0: tf32-rounded floats, 4 per K group; bf16 = 1: bfloat16, 8 per K group) and the chunk table (20-byte records: u32 stream offset,
+ * u32 bytes, u16 MMA steps (two K groups each), u16 first K group (activations) or first k (descriptor layer), u8 source, u8 layer,
+ * u8 accumulator, u8 flags 1 = overwrite / 2 = last of its GEMM / 4 = first chunk after an epilogue, u8 epilogue 1 = relu -> activations /
+ * 2 = same + residual kept in tensor memory / 3 = output, u8 GEMM index, 2 pad).  Either output pointer may be NULL to query the sizes. */
+int ds_disney_model_pack(const float* weights, size_t count, int bf16, void* stream_out, size_t stream_capacity, void* chunks_out,
+                         size_t chunks_capacity, size_t* stream_bytes, size_t* chunk_count);
 /* module->forward (DisneyRenderer.cpp:104; DisneyModel.forward, DisneyModel.py:16-29): network_input [n][10][226] floats ->
- * predicted_out [n] (radiance for a sun of 1e6).  DS_PRECISION_EXACT: fp32 FMA kernel; DS_PRECISION_FAST: tcgen05 kind::tf32 tensor-core
- * kernel (inputs and activations rounded to tf32, fp32 accumulation and residual path) */
+ * predicted_out [n] (radiance for a sun of 1e6).  DS_PRECISION_EXACT: fp32 FMA kernel; DS_PRECISION_FAST: tcgen05 tensor-core kernel, inputs
+ * and activations rounded to tf32 (option "mlp_bf16" = 1: to bfloat16), fp32 accumulation and residual path */
 int ds_disney_model_forward(DsContext* ctx, const float* network_input, uint32_t n, float* predicted_out);
 /* Introspection: cycle accounting of block 0 of the last tensor-core model launch made with option "profile_events" = 2 (an instrumented
  * build of the kernel) -- SM clock cycles; [0] MMA-issuing thread: total, [1] weight producer: waiting for a free weight stage, [2] issuer

@@ -182,50 +182,57 @@ CHUNK_DTYPE = np.dtype([("wOffset", "<u4"), ("wBytes", "<u4"), ("k8", "<u2"), ("
                         ("flags", "u1"), ("epilogue", "u1"), ("gemm", "u1"), ("pad", "u1", 2)])
 
 
-def packed_program(built_library, weights):
+def packed_program(built_library, weights, bf16=False):
     import ctypes as C
 
     lib = built_library.load()
     nb, nc = C.c_size_t(), C.c_size_t()
     w = np.ascontiguousarray(weights, np.float32)
-    assert lib.ds_disney_model_pack(w.ctypes.data, w.size, None, 0, None, 0, C.byref(nb), C.byref(nc)) == 0
+    assert lib.ds_disney_model_pack(w.ctypes.data, w.size, int(bf16), None, 0, None, 0, C.byref(nb), C.byref(nc)) == 0
     stream = np.zeros(nb.value, np.uint8)
     chunks = np.zeros(nc.value, CHUNK_DTYPE)
-    assert lib.ds_disney_model_pack(w.ctypes.data, w.size, stream.ctypes.data, stream.size, chunks.ctypes.data, chunks.nbytes, C.byref(nb), C.byref(nc)) == 0
+    assert lib.ds_disney_model_pack(w.ctypes.data, w.size, int(bf16), stream.ctypes.data, stream.size, chunks.ctypes.data, chunks.nbytes, C.byref(nb), C.byref(nc)) == 0
     return stream, chunks
 
 
-def test_tensor_core_program_emulated_on_cpu(built_library, weights, inputs):
+@pytest.mark.parametrize("bf16", [False, True])
+def test_tensor_core_program_emulated_on_cpu(built_library, weights, inputs, bf16):
     """Runs the chunk program of k_disney_mlp_tc in numpy (float64 accumulators): decodes every weight chunk from the canonical
-    core-matrix layout, follows the overwrite / accumulate / residual-in-accumulator / epilogue flags, and must land on the oracle
-    within the tf32 rounding of the weights (activations are not rounded here)."""
+    core-matrix layout (4 tf32 or 8 bf16 per 16-byte K group), follows the overwrite / accumulate / residual-in-accumulator / epilogue
+    flags, and must land on the oracle within the rounding of the weights (activations are not rounded here)."""
     assert CHUNK_DTYPE.itemsize == 20
-    stream, chunks = packed_program(built_library, weights)
-    assert len(chunks) <= 1024 and chunks["wOffset"][0] == 0 and np.all(chunks["wBytes"] == chunks["k8"].astype(np.uint32) * 2 * 26 * 128)
+    G = 8 if bf16 else 4  # K values per 16-byte K group
+    zpad = 240 if bf16 else 232  # descriptor layer padded to whole MMA steps
+    stream, chunks = packed_program(built_library, weights, bf16)
+    assert len(chunks) <= 232 and chunks["wOffset"][0] == 0 and np.all(chunks["wBytes"] == chunks["k8"].astype(np.uint32) * 2 * 26 * 128)
     assert np.all(np.diff(chunks["wOffset"].astype(np.int64)) == chunks["wBytes"][:-1])  # consumption order, no gaps
     assert chunks["wOffset"][-1] + chunks["wBytes"][-1] == stream.size and np.all(chunks["wOffset"] % 16 == 0)
     n = 24
-    x = np.zeros((n, 10, 232))
+    x = np.zeros((n, 10, zpad))
     x[:, :, :226] = inputs[:n]
     x[:, :, 226:228] = 1.0  # the kernel stages z[226] = z[227] = 1: the bias columns of a block's first GEMM
-    words = stream.view(np.float32)
+    if bf16:
+        words = (stream.view(np.uint16).astype(np.uint32) << 16).view(np.float32)
+    else:
+        words = stream.view(np.float32)
+    E = 2 if bf16 else 4
     act = np.zeros((n, 208))
     act[:, 200:202] = 1.0  # the constant-one columns of the activation buffer
     D = [np.zeros((n, 208)), np.zeros((n, 208))]
     unflat = dm.unflatten(weights)
     out = None
-    nn, kk = np.meshgrid(np.arange(208), np.arange(32), indexing="ij")
+    nn, kk = np.meshgrid(np.arange(208), np.arange(64), indexing="ij")
     for ch in chunks:
-        kc = int(ch["k8"]) * 8
-        off = (kk[:, :kc] // 4) * (26 * 128) + (nn[:, :kc] // 8) * 128 + (nn[:, :kc] % 8) * 16 + (kk[:, :kc] % 4) * 4
-        W = words[(int(ch["wOffset"]) + off) // 4].astype(np.float64)  # [208][kc]
+        kc = int(ch["k8"]) * 2 * G
+        off = (kk[:, :kc] // G) * (26 * 128) + (nn[:, :kc] // 8) * 128 + (nn[:, :kc] % 8) * 16 + (kk[:, :kc] % G) * E
+        W = words[(int(ch["wOffset"]) + off) // E].astype(np.float64)  # [208][kc]
         assert np.all(W[200:] == 0)
         if ch["src"] == 1:
             k0 = int(ch["aK"])
-            assert k0 + kc <= 232
+            assert k0 + kc <= zpad
             A = x[:, int(ch["layer"]), k0 : k0 + kc]
         else:
-            k0 = int(ch["aK"]) * 4
+            k0 = int(ch["aK"]) * G
             assert k0 + kc <= 208
             A = act[:, k0 : k0 + kc]
         d = int(ch["dst"])
@@ -241,7 +248,7 @@ def test_tensor_core_program_emulated_on_cpu(built_library, weights, inputs):
                     D[d][:, :200] = v  # the residual of the next block stays in the accumulator
     assert out is not None
     ref = ol.disney_forward(weights, inputs[:n])
-    assert rel(out, ref) <= 2e-3
+    assert rel(out, ref) <= (6e-3 if bf16 else 2e-3)
 
 
 @pytest.mark.gpu
@@ -289,3 +296,41 @@ def test_primary_ray_cache_does_not_change_the_neural_frame_beyond_rounding(buil
         both = la & lb
         assert abs(float(a[both].mean()) / float(b[both].mean()) - 1) < 0.01
     assert not np.array_equal(moved, with_cache)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n", [1, 127, 160, 1000])
+def test_bf16_operands_match_oracle(gpu_ctx, built_library, weights, inputs, n):
+    """Option mlp_bf16: the same kernel with bfloat16 operands (kind::f16; 8 mantissa bits, so 4 x the tf32 rounding: tolerance 1.5e-2),
+    fp32 accumulation, residual and biases as before."""
+    ds = built_library
+    x = inputs[:n] if n <= len(inputs) else dm.synthetic_inputs(n, 21)
+    gpu_ctx.set_option("precision", ds.PRECISION_FAST)
+    gpu_ctx.set_option("mlp_bf16", 1)
+    try:
+        got = gpu_ctx.disney_model_forward(x)
+        again = gpu_ctx.disney_model_forward(x)
+    finally:
+        gpu_ctx.set_option("mlp_bf16", 0)
+    ref = ol.disney_forward(weights, x)
+    assert np.isfinite(got).all() and np.array_equal(got, again)
+    assert rel(got, ref) <= 1.5e-2
+    assert not np.array_equal(got, gpu_ctx.disney_model_forward(x))  # it is not the tf32 path
+
+
+@pytest.mark.gpu
+def test_render_disney_with_bf16_operands(built_library, weights):
+    ds = built_library
+    cam = ds.camera_look_at(aspect=4.0)
+    with ds.Context(0) as ctx:
+        ctx.volume_synth(SCENE_SMALL["n"], SCENE_SMALL["kind"], SCENE_SMALL["seed"])
+        ctx.scene_set(SCENE_SMALL["cloud_size_m"], SCENE_SMALL["light_dir"])
+        ctx.bake()
+        ctx.disney_model_load(weights)
+        a = ctx.render_disney(cam, 160, 40, stream=3)
+        ctx.set_option("mlp_bf16", 1)
+        b = ctx.render_disney(cam, 160, 40, stream=3)
+        b2 = ctx.render_disney(cam, 160, 40, stream=3)
+    lit = a[..., 3] != 0
+    assert np.array_equal(lit, b[..., 3] != 0) and np.array_equal(b, b2) and not np.array_equal(a, b)
+    assert np.abs(a - b)[lit].max() <= 1.5e-2 * np.abs(a)[lit].max()
