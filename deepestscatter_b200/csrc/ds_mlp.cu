@@ -1,8 +1,9 @@
 /*
  * ds_mlp.cu -- the radiance-predicting network of the neural renderer on sm_100a (see ds_mlp.h).
  *
- *   k_disney_mlp_tc   FAST flavour: tcgen05.mma kind::tf32, M = 128 rows per CTA, N = 208, fp32 accumulators in
- *                     tensor memory, weights streamed by 1-D bulk TMA, activations never leave the SM;
+ *   k_disney_mlp_tc   FAST flavour: tcgen05.mma kind::tf32 (or kind::f16 on bf16 operands), M = 128 rows per CTA, N = 208, fp32
+ *                     accumulators and the residual in tensor memory, weight and descriptor chunks streamed by 1-D bulk TMA,
+ *                     activations never leave the SM;
  *   k_disney_mlp_f32  EXACT flavour: plain fp32 FMA in a fixed summation order (register-tiled, shared-memory staged).
  *
  * Both are checked against oracle/ds_oracle_mlp.cpp, which is pinned to the reference's own DisneyModel.py through
@@ -319,13 +320,13 @@ cudaError_t launchDisneyMlpF32(const DisneyModelDev& m, const float* in, const u
 /* ------------------------------------------------------------------------------------------------ tcgen05 kernel */
 
 constexpr int TC_M = 128;          /* rows per CTA = UMMA M = TMEM lanes */
-constexpr int TC_WORKERS = 256;    /* warps 0-7: threads t and t + 128 share row t (TMEM lane t): each stages half of a descriptor chunk and
-                                      runs the epilogue on half of the columns (a warp reaches the TMEM lanes of quadrant warp % 4) */
-constexpr int TC_ISSUER_WARP = TC_WORKERS / 32;     /* TMEM allocation and MMA issue (one lane) */
-constexpr int TC_PRODUCER_WARP = TC_ISSUER_WARP + 1; /* weight stream: bulk copies (one lane) */
+constexpr int TC_WORKERS = 256;    /* warps 0-7 run the epilogues: threads t and t + 128 share row t (TMEM lane t) and split its columns (a warp
+                                      reaches the TMEM lanes of quadrant warp % 4) */
+constexpr int TC_ISSUER_WARP = TC_WORKERS / 32;     /* TMEM allocation; walks the program and issues the MMAs (one elected lane) */
+constexpr int TC_PRODUCER_WARP = TC_ISSUER_WARP + 1; /* operand streams: bulk copies of weight and descriptor chunks (one lane) */
 constexpr int TC_THREADS = TC_WORKERS + 64;
-constexpr int TC_PIECES = 7;       /* epilogue pieces = K chunks of the next GEMM: 32 columns each (the last one 16); pieces 0-3 belong to the
-                                      first half of the workers, 4-6 to the second */
+constexpr int TC_PIECES = 7;       /* epilogue pieces = K chunks of the next GEMM, one hand-off barrier each: 7 of 32 columns (the last one 16) for
+                                      tf32 operands, 4 of 64 (16) for bf16; columns [0, 128) belong to the first half of the workers */
 constexpr int TC_WSTAGES = 3, TC_ZSTAGES = 2;
 constexpr int TC_MAX_CHUNKS = 232;
 /* the program every warp follows, as a kernel parameter: it sits in the constant bank, so a chunk's fields are uniform-register operands for
