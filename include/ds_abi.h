@@ -114,8 +114,15 @@ int ds_context_set_stream(DsContext* ctx, void* cuda_stream);
 /* block until all work queued by this context is complete */
 int ds_sync(DsContext* ctx);
 /* named integer options: "precision" (DsPrecision), "variant", "block_threads", "blocks_per_sm",
- * "skip_empty", "march_keep_quarters", "march_max_iters", "staging_subframes" -- tuning knobs of the
- * estimator kernels; "stream_offset" -- added to the subframe id to form the RNG stream id; "profile_events"  */
+ * "skip_empty", "primary_cache", "march_keep_quarters", "march_keep32", "march_max_iters", "march_unroll", "regen_min", "skip_min",
+ * "skip_max_iters", "skip_open_dist", "zero_check_min", "smem_carveout", "staging_subframes" -- tuning knobs of the estimator kernels;
+ * "radiance_scheduler", "radiance_quota" -- the radiance collector (0 = the reference's host schedule, 1 = device-resident);
+ * "stream_offset" -- added to the subframe id to form the RNG stream id;
+ * neural renderer: "mlp_bf16" (FAST flavour of the model on bf16 instead of tf32 operands), "descriptor_hw" (-1 = the FAST network-input passes
+ * sample a mip-mapped texture, the collectors never; 0 = never; 1 = also the float collector), "compact_reverse" (test hook: process the
+ * scattering pixels in the opposite order);
+ * "profile_events" (1: CUDA events around the trace / model launches, read back through ds_get_launch_stats and "mlp_last_us"; 2: also the
+ * instrumented instantiation of the model kernel, ds_disney_model_profile); read-only: "mlp_last_us", "volume_generation" */
 int ds_set_option(DsContext* ctx, const char* name, int value);
 int ds_get_option(DsContext* ctx, const char* name, int* value);
 int ds_get_counters(DsContext* ctx, DsCounters* out);
