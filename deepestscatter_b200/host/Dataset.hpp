@@ -322,8 +322,24 @@ public:
         }
     }
 
-    /* mdb_txn_commit: make everything appended so far durable and visible to readers */
-    void commit() { file.commit(); }
+    /* mdb_txn_commit: make everything appended so far durable and visible to readers.
+     * DeepestScatter_Train/LmdbDataset.py:36-40 opens five tables the moment it opens a file, with create = False for readers, so a file the
+     * training side can open holds all of them -- also BakedInterpolationSet, whose collector is outside this library's scope (in the reference
+     * a table appears once anything asks for it: getTable opens with MDB_CREATE, Dataset.cpp:78-90).  They are added by the first commit that
+     * writes anything; a dataset that was only opened stays untouched. */
+    void commit()
+    {
+        if (file.dirty())
+            for (const char* name : {"SceneSetup", "ScatterSample", "DisneyDescriptor", "BakedInterpolationSet", "Result"}) file.createTable(name);
+        file.commit();
+    }
+    ~Dataset()
+    {
+        try {
+            commit();
+        } catch (...) {
+        }
+    }
 
     dslmdb::LmdbFile& lmdb() { return file; }
 

@@ -118,6 +118,7 @@ public:
     uint64_t lastPage() const { return nextPg_ - 1; }
     const std::map<std::string, Table>& tables() const { return tables_; }
     bool hasTable(const std::string& name) const { return tables_.count(name) != 0; }
+    bool dirty() const { return dirty_; } /* something was put, created or dropped since the last commit */
     size_t count(const std::string& name) const
     {
         const auto it = tables_.find(name);

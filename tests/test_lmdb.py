@@ -104,8 +104,10 @@ def test_dataset_written_here_reads_like_the_reference_reader(built_library, tmp
         scene = r.get("SceneSetup", i // BATCH_SIZE)  # BaseDataset.py:32
         assert scene == ds.record_scene_setup(f"Clouds/cloud{i // BATCH_SIZE}.vdb", 7000.0 + i // BATCH_SIZE, (-0.03, -0.25, 0.8))
     assert r.get("Result", n) is None and r.get("Result", 2**31 - 1) is None
+    # LmdbDataset.py:36-40 opens five tables with create=False: the one this library never fills exists, empty; any other name is MDB_NOTFOUND
+    assert r.getCountOf("BakedInterpolationSet") == 0 and r.get("BakedInterpolationSet", 0) is None
     with pytest.raises(ds.lmdb_compat.Error):
-        r.env.open_db(b"BakedInterpolationSet", integerkey=True)  # MDB_NOTFOUND with create=False
+        r.env.open_db(b"LightProbes", integerkey=True)
     # cursor order = key order (LmdbDataset.getCountBeforeLastFlatCloud iterates SceneSetup)
     with r.env.begin() as t:
         keys = [int.from_bytes(k, "little") for k, _ in t.cursor(r.db("SceneSetup"))]
@@ -226,3 +228,49 @@ def test_error_paths(built_library, tmp_path):
         assert w.count("Nothing") == 0
     with pytest.raises(ds.lmdb_compat.Error):
         ds.lmdb_compat.Environment(str(tmp_path / "e.lmdb"), subdir=False, readonly=False)
+
+
+REF_TRAIN = Path("/root/reference/DeepestScatter_Train")
+
+
+@pytest.mark.skipif(not (REF_TRAIN / "LmdbDataset.py").is_file(), reason="the reference tree is not mounted here")
+def test_the_references_own_reader_opens_and_decodes_the_file(built_library, tmp_path, monkeypatch):
+    """DeepestScatter_Train/LmdbDataset.py itself, unmodified, on a file written here: `lmdb` is the one module it needs that this image
+    lacks, so the pure-Python reader with py-lmdb's API stands in for it; the protobuf messages are the reference's own."""
+    import importlib
+    import os
+    import sys
+
+    ds = built_library
+    path = tmp_path / "Train.lmdb"
+    pos, d, desc, rad = synth(5, 3)
+    with ds.Dataset(path) as w:
+        w.append_scene_setup(0, "RoundClouds/cloud 01.vdb", 7000.0, (-0.03, -0.25, 0.8))
+        w.append_scatter_samples(0, pos, d)
+        w.append_descriptors(0, desc)
+        w.append_results(0, rad, np.ones(5, np.uint8))
+    monkeypatch.setenv("PROTOCOL_BUFFERS_PYTHON_IMPLEMENTATION", "python")
+    monkeypatch.syspath_prepend(str(REF_TRAIN))
+    monkeypatch.syspath_prepend(str(REF_TRAIN / "PythonProtocols"))
+    monkeypatch.setitem(sys.modules, "lmdb", ds.lmdb_compat)
+    sys.modules.pop("LmdbDataset", None)
+    try:
+        L = importlib.import_module("LmdbDataset")
+    except Exception as exc:  # protobuf runtime incompatible with the generated modules
+        pytest.skip(f"cannot import the reference's LmdbDataset.py: {exc}")
+    try:
+        data = L.LmdbDataset(str(path))
+        assert data.getCountOf(L.ScatterSample) == 5 and data.getCountOf(L.Result) == 5 and data.getCountOf(L.SceneSetup) == 1
+        assert data.getCountOf(L.DisneyDescriptor) == 5 and data.getCountOf(L.BakedInterpolationSet) == 0
+        for i in range(5):
+            s_ = data.get(L.ScatterSample, i)
+            assert np.array_equal(np.float32([s_.point.x, s_.point.y, s_.point.z]), pos[i])
+            assert np.array_equal(np.float32([s_.view_direction.x, s_.view_direction.y, s_.view_direction.z]), d[i])
+            assert bytes(data.get(L.DisneyDescriptor, i).grid) == desc[i].tobytes()
+            res = data.get(L.Result, i)
+            assert np.float32(res.light_intensity) == rad[i] and res.is_converged
+        scene = data.get(L.SceneSetup, 0)
+        assert scene.cloud_path == "RoundClouds/cloud 01.vdb" and scene.cloud_size_m == 7000.0
+        assert data.getCountBeforeLastFlatCloud() == 0  # iterates the SceneSetup cursor (LmdbDataset.py:70-80)
+    finally:
+        sys.modules.pop("LmdbDataset", None)
