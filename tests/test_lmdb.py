@@ -274,3 +274,53 @@ def test_the_references_own_reader_opens_and_decodes_the_file(built_library, tmp
         assert data.getCountBeforeLastFlatCloud() == 0  # iterates the SceneSetup cursor (LmdbDataset.py:70-80)
     finally:
         sys.modules.pop("LmdbDataset", None)
+
+
+@pytest.mark.skipif(not (REF_TRAIN / "Disney" / "DisneyDataset.py").is_file(), reason="the reference tree is not mounted here")
+def test_the_references_training_dataset_consumes_the_file(built_library, tmp_path, monkeypatch):
+    """The whole consumer chain of the training side, unmodified: LmdbDataset.py -> Common/BaseDataset.py -> Disney/DisneyDataset.py turn a
+    record set written here into the (10 x 226 descriptor-with-angle, light) pairs the reference's DisneyModel trains on."""
+    import importlib
+    import math
+    import sys
+
+    torch = pytest.importorskip("torch")
+    ds = built_library
+    n = BATCH_SIZE + 3  # samples of two scenes: scene id = index // 2048 (BaseDataset.py:32)
+    pos, d, desc, rad = synth(n, 8)
+    lights = [(-0.03, -0.25, 0.8), (0.586, -0.766, -0.271)]
+    path = tmp_path / "Train.lmdb"
+    with ds.Dataset(path) as w:
+        for scene, light in enumerate(lights):
+            w.append_scene_setup(scene, f"Clouds/c{scene}.vdb", 3000.0 * (scene + 1), light)
+        w.append_scatter_samples(0, pos, d)
+        w.append_descriptors(0, desc)
+        w.append_results(0, rad, np.ones(n, np.uint8))
+    monkeypatch.setenv("PROTOCOL_BUFFERS_PYTHON_IMPLEMENTATION", "python")
+    for sub in ("", "PythonProtocols", "Common", "Disney"):
+        monkeypatch.syspath_prepend(str(REF_TRAIN / sub))
+    monkeypatch.setitem(sys.modules, "lmdb", ds.lmdb_compat)
+    if not hasattr(np, "math"):
+        monkeypatch.setattr(np, "math", math, raising=False)  # Common/Vector.py:20 predates numpy 2
+    for name in ("LmdbDataset", "BaseDataset", "DisneyDataset", "Vector"):
+        sys.modules.pop(name, None)
+    try:
+        L = importlib.import_module("LmdbDataset")
+        D = importlib.import_module("DisneyDataset")
+    except Exception as exc:
+        pytest.skip(f"cannot import the reference's dataset modules: {exc}")
+    try:
+        data = D.DisneyDataset(L.LmdbDataset(str(path)))
+        assert len(data) == n
+        for i in (0, 1, 2047, 2048, n - 1):
+            z, light = data[i]
+            assert tuple(z.shape) == (10, 226) and z.dtype == torch.float32
+            assert np.array_equal(z[:, :225].numpy(), (desc[i].astype(np.float32) / 256).reshape(10, 225))  # DisneyDataset.py:26-28
+            l = np.float32(lights[i // BATCH_SIZE]).astype(np.float64)
+            v = d[i].astype(np.float64)
+            angle = math.acos(np.dot(l / np.linalg.norm(l), v / np.linalg.norm(v)))
+            assert np.allclose(z[:, 225].numpy(), angle, atol=1e-6)
+            assert np.float32(light) == rad[i]
+    finally:
+        for name in ("LmdbDataset", "BaseDataset", "DisneyDataset", "Vector"):
+            sys.modules.pop(name, None)
