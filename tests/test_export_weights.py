@@ -77,3 +77,33 @@ def test_oracle_matches_torch_on_random_weights(model):
     model.float()
     got = ol.disney_forward(dm.flatten_state_dict(model.state_dict()), x)
     assert np.max(np.abs(got - ref) / (np.abs(ref) + 1e-6)) <= 1e-6
+
+
+REF_DISNEY = Path("/root/reference/DeepestScatter_Train/Disney")
+
+
+@pytest.mark.skipif(not (REF_DISNEY / "DisneyModel.py").is_file(), reason="the reference tree is not mounted here")
+def test_the_references_exported_model_converts_and_evaluates(tmp_path, monkeypatch):
+    """Trainer.exportModel (Common/Trainer.py:65-67) on the reference's own DisneyModel: torch.jit.trace(model, z).save('DisneyModel.pt') -- the
+    file DisneyRenderer::init loads -- converted by the tool and evaluated by the oracle against the traced module itself."""
+    import importlib
+
+    monkeypatch.syspath_prepend(str(REF_DISNEY))
+    sys.modules.pop("DisneyModel", None)
+    sys.modules.pop("DisneyBlock", None)
+    try:
+        DisneyModel = importlib.import_module("DisneyModel").DisneyModel
+        torch.manual_seed(5)
+        ref_model = DisneyModel().eval()
+        z = torch.from_numpy(dm.synthetic_inputs(6, 13))
+        traced = torch.jit.trace(ref_model, z)
+        traced.save(str(tmp_path / "DisneyModel.pt"))
+        flat = export(str(tmp_path / "DisneyModel.pt"), str(tmp_path / "DisneyModel.f32"))
+        assert flat.size == dm.WEIGHT_COUNT
+        with torch.no_grad():
+            want = traced(z).numpy().reshape(-1)
+        got = ol.disney_forward(flat, z.numpy())
+        assert np.max(np.abs(got - want) / (np.abs(want) + 1e-6)) <= 2e-6
+    finally:
+        sys.modules.pop("DisneyModel", None)
+        sys.modules.pop("DisneyBlock", None)
