@@ -1,6 +1,8 @@
 """Pins the host oracle against everything the reference gives us (Mie data, integer algorithms restated
 independently in numpy) and against analytic results (Beer-Lambert slab, phase-function sampling).
 The reference has no tests or golden images: the estimator itself stays 'parity unpinned'."""
+from pathlib import Path
+
 import numpy as np
 import pytest
 
@@ -323,3 +325,57 @@ def test_point_radiance_scheduler_follows_the_collector(oracle_small):
     # every sample got taskRepeatCount * launches experiments in the first update (RadianceCollector.cpp:176-192)
     assert tasks["experimentCount"].min() >= 8 * 20
     assert np.all(tasks["radiance"] >= 0) and np.isfinite(tasks["runningVariance"]).all()
+
+
+REF_VECTOR = Path("/root/reference/DeepestScatter_Train/Common/Vector.py")
+
+
+@pytest.mark.skipif(not REF_VECTOR.is_file(), reason="the reference tree is not mounted here")
+def test_descriptor_stencil_follows_the_references_basis(monkeypatch):
+    """The stencil's tap addresses (integer work) against an independent numpy construction that takes the frame from the reference's own
+    `descriptorBasis` (DeepestScatter_Train/Common/Vector.py:32-37 -- the Python twin of DisneyDescriptor.cuh:74-76): eZ against the light, eX
+    across the view direction; taps z outermost / x innermost on a 5 x 5 x 9 lattice from (-2,-2,-2) to (2,2,6), spacing 0.5 / densityMultiplier
+    doubling per layer, mip level max(0, -log2(voxel in free paths) - 1 + layer).  Float rounding may move a tap that sits on a voxel boundary:
+    at most 0.5 % of the addresses may differ, and then by one voxel."""
+    import importlib
+    import sys
+
+    monkeypatch.syspath_prepend(str(REF_VECTOR.parent))
+    sys.modules.pop("Vector", None)
+    V = importlib.import_module("Vector")
+    try:
+        n = 64
+        o = ol.Oracle()
+        o.volume_synth(n, 0, 1234, True)
+        light = np.float32([0.3, -0.8, 0.52])
+        o.scene_set(7000.0, light)
+        der = o.derived()
+        pos, dirs = o.generate_points(0, 40, 0)
+        _, idx = o.descriptors(pos, dirs, as_float=True, want_index=True)
+        levels = o.level_count()
+        dims = [o.level_dims(l) for l in range(levels)]
+        light_n = der["light"].astype(np.float64)
+        mip0 = -np.log2(float(der["voxel_free_path"])) - 1.0
+        lattice = np.array([(x, y, z) for z in range(-2, 7) for y in range(-2, 3) for x in range(-2, 3)], np.float64)  # sampleId order
+        bad = total = 0
+        for s in range(len(pos)):
+            eX, eY, eZ = V.descriptorBasis(light_n, dirs[s].astype(np.float64))
+            origin = pos[s].astype(np.float64) + 0.5 * der["bbox"].astype(np.float64)
+            for layer in range(10):
+                scale = 0.5 / der["density_multiplier"] * 2.0**layer
+                lod = min(max(mip0 + layer, 0.0), levels - 1)
+                l0 = int(np.floor(lod))
+                nx, ny, nz = dims[l0]
+                p = origin + (lattice[:, 0:1] * eX + lattice[:, 1:2] * eY + lattice[:, 2:3] * eZ) * scale
+                uvw = p * der["texture_scale"].astype(np.float64)
+                want = np.stack([np.clip(np.floor(uvw[:, 0] * nx - 0.5), -2, nx + 1), np.clip(np.floor(uvw[:, 1] * ny - 0.5), -2, ny + 1),
+                                 np.clip(np.floor(uvw[:, 2] * nz - 0.5), -2, nz + 1)], axis=1).astype(np.int64)
+                got = idx[s, layer].astype(np.int64)
+                assert np.all(got[:, 3] == l0)
+                diff = np.abs(got[:, :3] - want)
+                assert diff.max() <= 1
+                bad += int((diff.max(axis=1) > 0).sum())
+                total += 225
+        assert bad <= 0.005 * total, f"{bad} of {total} tap addresses differ"
+    finally:
+        sys.modules.pop("Vector", None)
