@@ -324,3 +324,39 @@ def test_the_references_training_dataset_consumes_the_file(built_library, tmp_pa
     finally:
         for name in ("LmdbDataset", "BaseDataset", "DisneyDataset", "Vector"):
             sys.modules.pop(name, None)
+
+
+def test_page_counts_match_the_statistics_recorded_in_the_references_notebook(built_library, tmp_path):
+    """DeepestScatter_Train/DatasetVisualisation.ipynb keeps the output of `transaction.stat(results_db)` on the authors' dataset, written by
+    the real liblmdb: {'psize': 4096, 'depth': 2, 'branch_pages': 1, 'leaf_pages': 78, 'overflow_pages': 0, 'entries': 14336}.  The same
+    number of Result records (7 bytes each: non-zero radiance, converged) appended in key order here must pack into the same tree.
+    (The ScatterSample line of that output -- 8 663 040 entries in 103 132 leaves = 84 per leaf where 85 fit -- is not reproduced: fill
+    factor is the writer's choice and no reader depends on it.)"""
+    ds = built_library
+    path = tmp_path / "r.lmdb"
+    n = 14336
+    rad = np.linspace(0.5, 3.0, n).astype(np.float32)
+    with ds.Dataset(path) as w:
+        for start in range(0, n, BATCH_SIZE):  # one transaction per batch, as the collectors commit
+            w.append_results(start, rad[start:start + BATCH_SIZE], np.ones(BATCH_SIZE, np.uint8))
+            w.commit()
+    env = ds.lmdb_compat.Environment(str(path), subdir=False, readonly=True, max_dbs=8)
+    db = env.open_db(b"Result", integerkey=True)
+    with env.begin() as txn:
+        stat = txn.stat(db)
+    assert stat == {"psize": 4096, "depth": 2, "branch_pages": 1, "leaf_pages": 78, "overflow_pages": 0, "entries": 14336}
+
+
+def test_full_size_statistics_of_the_references_dataset(built_library):
+    """The ScatterSample line of the same notebook output, at full size: 8 663 040 records of 34 bytes must pack into depth 4, 359 branch and
+    103 132 leaf pages, as the real liblmdb left them (84 records per leaf where 85 fit: mdb_page_split moves the last node of a full page to
+    the new one during ascending inserts).  ~10 s, ~3 GB of RAM, a 420 MB scratch file."""
+    import importlib
+    import sys
+
+    psutil = pytest.importorskip("psutil")
+    if psutil.virtual_memory().available < 8 << 30:
+        pytest.skip("needs 8 GB of free memory")
+    sys.path.insert(0, str(Path(__file__).resolve().parent.parent / "tools"))
+    tool = importlib.import_module("lmdb_notebook_stats")
+    assert tool.main() == 0
