@@ -2,8 +2,11 @@
 independent pure-Python parser with py-lmdb's API (deepestscatter_b200/lmdb_compat.py), the way
 DeepestScatter_Train/LmdbDataset.py:24-66 reads the reference's datasets.  No GPU needed.
 
-FORMAT PARITY IS UNPINNED against liblmdb (neither liblmdb nor py-lmdb exists here): these tests pin the writer against
-the restated format, the record bytes against the golden vectors, and the structural invariants mdb.c relies on."""
+Neither liblmdb nor py-lmdb exists here, so byte-level format parity is unpinned against liblmdb; what IS pinned to the real library:
+the table statistics (depth, branch / leaf / overflow pages, entries) that the reference's DatasetVisualisation.ipynb recorded for the
+authors' dataset, reproduced exactly at full size; and to the reference: its own reader and training dataset classes, unmodified,
+decode a file written here.  The rest pins the writer against the restated format, the record bytes against the golden vectors, and
+the structural invariants mdb.c relies on."""
 import json
 import struct
 from pathlib import Path
