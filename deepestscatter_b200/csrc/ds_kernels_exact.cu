@@ -254,7 +254,9 @@ __global__ void k_reinhard_average(const float* columns, int w, unsigned totalPi
     average[0] = result / (float)totalPixels;
 }
 
-/* applyReinhard; lw == 0 (0/0 in the reference, reinhard.cu:69) is written as black */
+/* applyReinhard.  lw == 0 gives ld / lw = 0/0 = NaN in the reference (reinhard.cu:69); optix::clamp is
+ * fmaxf(a, fminf(f, b)) and fminf(NaN, 1) = 1, so such pixels (the empty background) come out WHITE there.  Kept: the
+ * reference's own sources compiled on the host (oracle/_ref) show it, and tests/test_oracle_vs_ref.py pins it. */
 __global__ void __launch_bounds__(256) k_reinhard_apply(const float4* __restrict__ progressive, size_t pixels, float exposure,
                                                         const float* average, uchar4* __restrict__ screen)
 {
@@ -264,10 +266,10 @@ __global__ void __launch_bounds__(256) k_reinhard_apply(const float4* __restrict
     const float lw = luminance(c);
     float ld = lw * exposure / average[0];
     ld = ld / (1.f + ld);
-    const float k = lw > 0.0f ? ld / lw : 0.0f;
-    const float r = powf(fminf(fmaxf(c.x * k, 0.f), 1.f), 1.f / 2.2f) * 255;
-    const float g = powf(fminf(fmaxf(c.y * k, 0.f), 1.f), 1.f / 2.2f) * 255;
-    const float b = powf(fminf(fmaxf(c.z * k, 0.f), 1.f), 1.f / 2.2f) * 255;
+    const float k = ld / lw;
+    const float r = powf(fmaxf(0.f, fminf(c.x * k, 1.f)), 1.f / 2.2f) * 255;
+    const float g = powf(fmaxf(0.f, fminf(c.y * k, 1.f)), 1.f / 2.2f) * 255;
+    const float b = powf(fmaxf(0.f, fminf(c.z * k, 1.f)), 1.f / 2.2f) * 255;
     screen[i] = make_uchar4((unsigned char)r, (unsigned char)g, (unsigned char)b, 255);
 }
 

@@ -7,13 +7,22 @@
  * may load this library; the product (deepestscatter_b200/csrc) never links or
  * calls it and has no CPU fallback.
  *
- * PARITY STATUS: **parity unpinned** for the estimator.  The reference has no
- * tests, golden images or fixtures and its device code is OptiX
- * 5.1 programs that cannot be compiled here (no OptiX SDK, no GPU).  What is
- * pinned from reference artefacts: the Mie table data (Mie.cpp:8-8203) and the
- * protobuf record bytes (tests/golden/, generated from the reference's own
- * PythonProtocols _pb2 modules).  Everything else is this restatement, which
- * follows the cited reference lines statement by statement.
+ * PARITY STATUS: **pinned to the reference's own source.**  The reference has
+ * no tests, golden images or fixtures, but its DataGen code --
+ * the CUDA/ *.cu device programs AND the host classes that drive them -- is
+ * compiled UNMODIFIED from /root/reference by g++ against a small OptiX 5.1
+ * emulation (oracle/ref_shim/, output oracle/_ref/libds_ref.so).
+ * tests/test_oracle_vs_ref.py holds every entry point of this file to that
+ * library BIT FOR BIT on seeded inputs (estimators in all three modes with
+ * equal step/event counts, bake bytes, mip chain, Mie samplers, scene
+ * variables, camera frames, Welford buffers, Reinhard bytes, generated points,
+ * descriptor bytes, network-input pass, the RadianceCollector schedule, the
+ * importer); tests/golden/ref_path.npz (tools/make_golden_ref.py) keeps vectors
+ * of that library for machines without /root/reference.  Also pinned from
+ * reference artefacts: the protobuf record bytes (tests/golden/records.json,
+ * from the reference's own PythonProtocols _pb2 modules).  What the pin cannot
+ * cover is listed next: arithmetic of the absent SDK, defined identically in
+ * this file and in the emulation.
  *
  * Third-party arithmetic not present under /root/reference and therefore
  * DEFINED here (NVIDIA OptiX SDK 5.1.0 / CUDA 9.2, Dependencies.md:3-4):
@@ -895,8 +904,9 @@ uint32_t orc_unconverged_pixels(const float* progressive, const float* variance,
     return bad;
 }
 
-/* CU/reinhard.cu:26-83.  Returns the average luminance.  lw == 0 gives 0/0 in the
- * reference (:69); here such pixels are written as black and the deviation is documented. */
+/* CU/reinhard.cu:26-83.  Returns the average luminance.  lw == 0 gives ld / lw = 0/0 = NaN in the
+ * reference (:69); optix::clamp(f, a, b) = fmaxf(a, fminf(f, b)) turns the NaN into 1, so the empty
+ * background is written WHITE (255), exactly as oracle/_ref (the reference's own reinhard.cu) does. */
 float orc_tonemap(const float* progressive, int w, int hgt, float exposure, uint8_t* screen)
 {
     std::vector<float> columns(w);
@@ -916,9 +926,9 @@ float orc_tonemap(const float* progressive, int w, int hgt, float exposure, uint
         const float lw = c[0] * 0.265068f + c[1] * 0.67023428f + c[2] * 0.06409157f + c[3] * 0.0f;
         float ld = lw * exposure / result;
         ld = ld / (1.f + ld);
-        const float k = lw > 0.0f ? ld / lw : 0.0f;
+        const float k = ld / lw;
         for (int ch = 0; ch < 3; ch++) {
-            float v = fminf(fmaxf(c[ch] * k, 0.f), 1.f);
+            float v = fmaxf(0.f, fminf(c[ch] * k, 1.f));
             v = powf(v, 1.f / 2.2f);
             screen[4 * i + ch] = (uint8_t)(v * 255);
         }

@@ -1,0 +1,3 @@
+/* TEST INFRASTRUCTURE (oracle/_ref build only): stands in for a third-party header that is not vendored under /root/reference. */
+#pragma once
+#include "../openvdb.h"
