@@ -1,20 +1,23 @@
 #!/usr/bin/env python3
 """bench.py -- headline benchmark of the radiance-estimation hot path on B200.
 
-Workload (BASELINE.json configs[1], "C2"): full multiple-scattering Lorenz-Mie path tracer with sun NEE,
-1920x1080, 512^3 synthetic cumulus density grid (include/ds_synth.h kind 0, seed 1234), cloud size 7000 m,
-sun "Front" (Tasks.cpp:56), default camera (Camera.cpp:37-39,102).  One STEP = `--spp` progressive subframes
-of the whole frame (render + Welford accumulation), i.e. spp * 1920 * 1080 paths per GPU.
+Workloads are BASELINE.json's configurations, all on the synthetic grids of include/ds_synth.h:
+  C1  single-scatter Beer-Lambert + Mie, cloud cube 256^3, 256x256, 64 spp             (configs[0])
+  C2  all-order Lorenz-Mie multi-scatter + sun NEE, cumulus 512^3, 1920x1080, 1024 spp (configs[1], the default: the
+      configuration the metric is quoted on)
+  C4  thick cumulus 1024^3, 12 km, grazing sun, 1920x1080                              (configs[3])
+  C5  as C2 at 3840x2160, 8192 spp, split over 2/4/8 GPUs                              (configs[4])
+One STEP = one progressive frame of `--spp` subframes: frame cleared, spp subframes rendered and Welford-accumulated, and -- on
+more than one GPU -- the per-GPU accumulation buffers combined by ONE NCCL reduce (ds_frame_reduce, inside the library) so that
+rank 0 holds the finished frame.  --scaling weak: every GPU renders --spp subframes (N*spp per frame); --scaling strong: the
+--spp subframes of the frame are split over the GPUs (multigpu.subframe_range).
 
-  python bench.py --gpus N --steps K --warmup W            our arm (CUDA, through the C ABI)
-  python bench.py --impl reference ...                     the reference arm: the host oracle (CPU port of the
-                                                           reference estimator; the reference itself has no CPU
-                                                           implementation and its OptiX 5.1 programs cannot be
-                                                           built here) on all host cores, bounded sample per step
+  python bench.py --gpus N --steps K --warmup W [--config C2] [--scaling weak]     our arm (CUDA, through the C ABI)
+  python bench.py --impl reference ...     the reference arm: the reference's own estimator source compiled for the host
+                                           (oracle/_ref, see oracle/ref_shim/) on all host cores, tracing a stated subset of the
+                                           SAME pixels and subframes; falls back to the oracle port where _ref is not built
 
-For N > 1 launch under torchrun (one rank per GPU): the grid is replicated, every rank renders its own
-subframe ids (weak scaling) and the per-GPU accumulation buffers are combined with ONE NCCL reduce of the
-moment buffers inside the timed region.  Rank 0 prints one JSON line.
+For N > 1 launch under torchrun (one rank per GPU).  Rank 0 prints one JSON line.
 """
 from __future__ import annotations
 
@@ -29,12 +32,23 @@ from pathlib import Path
 ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
-GRID_N = 512
-WIDTH, HEIGHT = 1920, 1080
-CLOUD_SIZE_M = 7000.0
-SUN_FRONT = (-0.586, -0.766, -0.271)
-GRID_KIND, GRID_SEED = 0, 1234
 METRIC = "Mpaths/s"
+SUN_FRONT = (-0.586, -0.766, -0.271)  # Tasks.cpp:56
+SUN_SIDE = (-0.03, -0.25, 0.8)  # Tasks.cpp:58
+SUN_GRAZING = (0.995, -0.0998, 0.0)
+MODE_ALL, MODE_MULTI, MODE_SINGLE = 0, 1, 2
+
+CONFIGS = {
+    "C1": dict(grid=256, kind=1, size_m=7000.0, sun=SUN_SIDE, width=256, height=256, mode=MODE_SINGLE, total_spp=64,
+               what="single-scatter Beer-Lambert + Mie, cloud cube"),
+    "C2": dict(grid=512, kind=0, size_m=7000.0, sun=SUN_FRONT, width=1920, height=1080, mode=MODE_ALL, total_spp=1024,
+               what="all-order Lorenz-Mie multi-scatter + sun NEE, cumulus"),
+    "C4": dict(grid=1024, kind=0, size_m=12000.0, sun=SUN_GRAZING, width=1920, height=1080, mode=MODE_ALL, total_spp=64,
+               what="all-order Mie + NEE, thick cumulus at a grazing sun (divergence stress)"),
+    "C5": dict(grid=512, kind=0, size_m=7000.0, sun=SUN_FRONT, width=3840, height=2160, mode=MODE_ALL, total_spp=8192,
+               what="all-order Mie + NEE, cumulus, 4K frame (multi-GPU scaling sweep)"),
+}
+GRID_SEED = 1234
 
 
 def parse_args():
@@ -43,23 +57,37 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--spp", type=int, default=64, help="progressive subframes per step (per GPU)")
-    ap.add_argument("--grid", type=int, default=GRID_N)
-    ap.add_argument("--width", type=int, default=WIDTH)
-    ap.add_argument("--height", type=int, default=HEIGHT)
+    ap.add_argument("--config", default="C2", choices=sorted(CONFIGS))
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--spp", type=int, default=64, help="subframes per step: per GPU (weak) or per frame (strong)")
+    ap.add_argument("--grid", type=int, default=None, help="override the configuration's grid size (tuning only)")
+    ap.add_argument("--width", type=int, default=None)
+    ap.add_argument("--height", type=int, default=None)
     ap.add_argument("--precision", default="fast", choices=["fast", "exact"])
     ap.add_argument("--opt", action="append", default=[], help="library option name=value (tuning)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-secondary", action="store_true", help="skip the neural-renderer numbers reported next to the main line")
-    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU work for the cpu_baseline sample")
-    ap.add_argument("--ref-width", type=int, default=480)
-    ap.add_argument("--ref-height", type=int, default=270)
-    return ap.parse_args()
+    ap.add_argument("--no-secondary", action="store_true", help="skip the descriptor / bake / neural-renderer legs")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU work per reference step / cpu_baseline sample")
+    ap.add_argument("--ref-stride", type=int, default=0, help="reference arm: trace every stride-th pixel in x and y (0 = auto)")
+    a = ap.parse_args()
+    c = dict(CONFIGS[a.config])
+    for k in ("grid", "width", "height"):
+        if getattr(a, k) is not None:
+            c[k] = getattr(a, k)
+    a.cfg = c
+    return a
 
 
-def workload_name(a) -> str:
-    return (f"C2: all-order Lorenz-Mie multi-scatter + sun NEE, {a.width}x{a.height}, {a.grid}^3 synthetic cumulus "
-            f"(size {CLOUD_SIZE_M:.0f} m, sun Front), {a.spp} spp/step/GPU")
+def config_dict(a) -> dict:
+    """Identical for both arms (the driver compares it); per-arm detail goes elsewhere on the line."""
+    c = a.cfg
+    return {
+        "workload": f"{a.config}: {c['what']} {c['grid']}^3 (ds_synth kind {c['kind']}, seed {GRID_SEED}), size {c['size_m']:.0f} m, "
+                    f"{c['width']}x{c['height']}, {a.spp} spp per step" + (" per GPU" if a.scaling == "weak" else " per frame"),
+        "config": a.config, "grid": c["grid"], "width": c["width"], "height": c["height"], "mode": c["mode"], "spp_per_step": a.spp,
+        "scaling": a.scaling, "target_spp": c["total_spp"],
+        "l2": "inputs (density + sun-transmittance grids, 2*N^3 B) exceed the 126 MB L2 from 512^3 up; no explicit flush",
+    }
 
 
 # ---------------------------------------------------------------- clocks
@@ -68,13 +96,8 @@ class ClockSampler:
     """Samples SM clock / throttle reasons of one GPU every 200 ms during the timed region (pynvml)."""
 
     def __init__(self, index: int):
-        self.index = index
-        self.samples = []
-        self.reasons = set()
-        self.max_mhz = None
-        self._stop = threading.Event()
-        self._thread = None
-        self.ok = False
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop, self._thread, self.ok = threading.Event(), None, False
         try:
             import pynvml
 
@@ -123,38 +146,7 @@ class ClockSampler:
         return {"sm_mhz": s[len(s) // 2], "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(s), "source": "nvml"}
 
 
-# ---------------------------------------------------------------- oracle helpers (cpu_baseline / reference arm only)
-
-def oracle_with_scene(a, density=None, inscatter=None):
-    sys.path.insert(0, str(ROOT / "tests"))
-    import oracle_lib as ol
-
-    o = ol.Oracle()
-    if density is not None:
-        o.volume_upload(density, True)
-    else:
-        o.volume_synth(a.grid, GRID_KIND, GRID_SEED, True)
-    o.scene_set(CLOUD_SIZE_M, SUN_FRONT)
-    if inscatter is not None:
-        o.inscatter_set(inscatter)
-    else:
-        o.bake(skip_empty=True)
-    return o, ol
-
-
-def time_oracle_sample(o, ol, a, w, h, spp, first_subframe=1):
-    """All-order estimator on a w x h down-sampling of the C2 frame (same camera), spp subframes; returns
-    (seconds, counters)."""
-    import numpy as np
-
-    cam = ol.camera_look_at(aspect=a.width / a.height)
-    o.counters_reset()
-    t0 = time.perf_counter()
-    for k in range(spp):
-        o.render_frame(cam, w, h, ol.MODE_ALL, first_subframe + k)
-    dt = time.perf_counter() - t0
-    return dt, o.counters()
-
+# ---------------------------------------------------------------- CPU side (reference arm and cpu_baseline leg only)
 
 def host_threads() -> int:
     try:
@@ -163,60 +155,132 @@ def host_threads() -> int:
         return os.cpu_count() or 1
 
 
-# ---------------------------------------------------------------- reference arm
+class CpuEstimator:
+    """The reference's estimator on the host cores for one configuration: oracle/_ref (the reference's own source, kind
+    "reference") when that library exists, else the oracle port (kind "port").  Traces explicit pixels of the configuration's
+    frame -- same camera ray, same seed tea<4>(x*4096 + y, subframe) as the GPU arm -- so the sample is a subset of the same work.
+    No product code is imported here."""
+
+    def __init__(self, a):
+        sys.path.insert(0, str(ROOT / "tests"))
+        import numpy as np
+        import oracle_lib as ol
+
+        self.np, self.ol, self.a, self.c = np, ol, a, a.cfg
+        self.cores = host_threads()
+        ol.lib().orc_set_threads(self.cores)  # torch.distributed.run exports OMP_NUM_THREADS=1
+        c = self.c
+        self.o = ol.Oracle()
+        self.o.volume_synth(c["grid"], c["kind"], GRID_SEED, True)
+        self.o.scene_set(c["size_m"], c["sun"])
+        self.o.bake(skip_empty=True)  # input preparation (bit-identical to the reference's bake, tests/test_oracle_vs_ref.py)
+        self.cam = ol.camera_look_at(aspect=c["width"] / c["height"])
+        self.ref = None
+        self.kind = "port"
+        try:
+            import ref_lib as rl
+
+            if rl.available():
+                rl.skip_bake(True)
+                r = rl.Reference()
+                r.volume_upload(self.o.level(0))
+                r.scene_init(c["size_m"], c["sun"], 1.0 / 512.0, c["mode"], 8, 8)
+                r.inscatter_set(self.o.inscatter())
+                rl.skip_bake(False)
+                self.ref, self.kind = r, "reference"
+        except Exception as exc:  # the port remains
+            print(f"bench.py: oracle/_ref unavailable ({exc}); timing the oracle port", file=sys.stderr)
+
+    def rays(self, stride: int, subframe: int):
+        """Pixels (i*stride, j*stride) of the frame at `subframe`: origins, directions, seed values, streams."""
+        np, c = self.np, self.c
+        xs, ys = np.arange(0, c["width"], stride, dtype=np.uint32), np.arange(0, c["height"], stride, dtype=np.uint32)
+        px, py = np.meshgrid(xs, ys)
+        px, py = px.reshape(-1), py.reshape(-1)
+        cam = self.cam.astype(np.float32)
+        eye, U, V, W = cam[0:3], cam[3:6], cam[6:9], cam[9:12]
+        # cameraCommon.cuh:22-25 in fp32: d = pixel / size * 2 - 1; dir = normalize(d.x*U + d.y*V + W)
+        dx = (px.astype(np.float32) / np.float32(c["width"]) * np.float32(2) - np.float32(1)).astype(np.float32)
+        dy = (py.astype(np.float32) / np.float32(c["height"]) * np.float32(2) - np.float32(1)).astype(np.float32)
+        d = (dx[:, None] * U[None, :] + dy[:, None] * V[None, :] + W[None, :]).astype(np.float32)
+        inv = (np.float32(1) / np.sqrt((d[:, 0] * d[:, 0] + d[:, 1] * d[:, 1] + d[:, 2] * d[:, 2]).astype(np.float32))).astype(np.float32)
+        d = (d * inv[:, None]).astype(np.float32)
+        o = np.tile(eye, (len(px), 1)).astype(np.float32)
+        val0 = (px * np.uint32(4096) + py).astype(np.uint32)
+        stream = np.full(len(px), subframe, dtype=np.uint32)
+        return o, d, val0, stream
+
+    def trace(self, stride: int, subframe: int):
+        """One sample: returns (seconds, paths, radiance)."""
+        o, d, val0, stream = self.rays(stride, subframe)
+        t0 = time.perf_counter()
+        if self.ref is not None:
+            rad = self.ref.trace_paths(o, d, val0, stream, procs=self.cores)
+        else:
+            rad = self.o.trace_paths(self.c["mode"], o, d, val0, stream)
+        return time.perf_counter() - t0, len(o), rad
+
+    def pick_stride(self, seconds: float) -> int:
+        """Largest sample (smallest stride) whose one-subframe trace fits `seconds`, from a coarse calibration."""
+        c = self.c
+        stride = max(1, int(max(c["width"], c["height"]) // 64))
+        while True:
+            dt, n, _ = self.trace(stride, 1)
+            if dt >= 1.0 or stride == 1:  # long enough that fork / start-up overhead no longer dominates the estimate
+                break
+            stride = max(1, stride // 2)
+        per_path = dt / max(1, n)
+        want = max(64.0, seconds / max(per_path, 1e-9))
+        s = (c["width"] * c["height"] / want) ** 0.5
+        return max(1, int(s + 0.999))
+
+    def sample_text(self, stride: int) -> str:
+        c = self.c
+        nx, ny = len(range(0, c["width"], stride)), len(range(0, c["height"], stride))
+        return (f"pixels (i*{stride}, j*{stride}) of the {c['width']}x{c['height']} frame ({nx}x{ny} = {nx * ny} paths per subframe), "
+                f"same camera rays and RNG streams as the GPU arm, 1 subframe per step")
+
 
 def run_reference(a):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    density = inscatter = None
-    setup = "grid + sun-transmittance bake prepared on the CPU by the oracle"
-    try:
-        import torch
-
-        if torch.cuda.is_available():
-            import deepestscatter_b200 as ds
-
-            with ds.Context(0) as ctx:  # input preparation only; nothing of ours runs inside the timed region
-                ctx.set_option("precision", ds.PRECISION_EXACT)
-                ctx.volume_synth(a.grid, GRID_KIND, GRID_SEED)
-                ctx.scene_set(CLOUD_SIZE_M, SUN_FRONT)
-                ctx.bake()
-                density, inscatter = ctx.level(0), ctx.inscatter()
-            setup = "grid + sun-transmittance bake (inputs) prepared once on the GPU, outside the timed region"
-    except Exception:
-        density = inscatter = None
-    o, ol = oracle_with_scene(a, density, inscatter)
-    w, h = a.ref_width, a.ref_height
-    cores = host_threads()
+    est = CpuEstimator(a)
+    stride = a.ref_stride or est.pick_stride(a.cpu_seconds)
     sub = 1
     for _ in range(a.warmup):
-        time_oracle_sample(o, ol, a, w, h, 1, sub)
+        est.trace(stride, sub)
         sub += 1
-    total_t, paths, events, steps = 0.0, 0, 0, 0
+    total_t, paths = 0.0, 0
     for _ in range(a.steps):
-        dt, c = time_oracle_sample(o, ol, a, w, h, 1, sub)
+        dt, n, _ = est.trace(stride, sub)
         sub += 1
         total_t += dt
-        paths += c["paths"]
-        events += c["events"]
-        steps += c["steps"]
+        paths += n
     value = paths / total_t / 1e6
-    sample = f"{w}x{h} px down-sampling of the C2 frame (same camera, grid and estimator), 1 subframe per step"
+    sample = est.sample_text(stride)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": METRIC, "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
-        "ms_per_step": total_t / a.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-        "data": "synthetic", "config": {"workload": workload_name(a), "sample": sample, "setup": setup},
-        "cpu_baseline": {"value": value, "unit": METRIC, "cores": cores, "kind": "port", "sample": sample},
+        "ms_per_step": total_t / a.steps * 1e3, "higher_is_better": True, "scaling": a.scaling, "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "config": config_dict(a),
+        "cpu_baseline": {"value": value, "unit": METRIC, "cores": est.cores, "kind": est.kind, "sample": sample},
         "e2e": {"value": value, "unit": METRIC, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "events_per_s": events / total_t, "steps_per_s": steps / total_t,
-        "note": "host oracle = CPU port of the reference estimator (the reference has no CPU implementation; OptiX 5.1 cannot be built here)",
+        "note": ("oracle/_ref: the reference's own estimator sources (CUDA/cloud.cuh, cloudRadianceMaterials.cu, random.cuh, cloudBBox.cu) compiled "
+                 "unmodified for the host behind an OptiX emulation, one forked worker per core" if est.kind == "reference" else
+                 "oracle port (oracle/ds_oracle.cpp, OpenMP): oracle/_ref is not built on this machine"),
     }
     print(json.dumps(line))
     return 0
 
 
 # ---------------------------------------------------------------- our arm
+
+def load_json(path: Path):
+    try:
+        return json.loads(path.read_text())
+    except Exception:
+        return None
+
 
 def run_ours(a):
     import numpy as np
@@ -226,6 +290,7 @@ def run_ours(a):
     import deepestscatter_b200 as ds
     from deepestscatter_b200 import multigpu
 
+    c = a.cfg
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -246,55 +311,65 @@ def run_ours(a):
     for kv in a.opt:
         k, v = kv.split("=")
         ctx.set_option(k, int(v))
-    ctx.set_option("staging_subframes", max(1, min(64, a.spp)))
+
+    # per-rank share of a step's subframes and its RNG stream offset inside the step
+    if a.scaling == "strong":
+        offset, n_local = multigpu.subframe_range(rank, world, a.spp)
+        n_total = a.spp
+    else:
+        offset, n_local, n_total = rank * a.spp, a.spp, world * a.spp
+    ctx.set_option("staging_subframes", max(1, min(64, max(1, n_local))))
+
+    # the library's own NCCL communicator: rank 0 draws the id, torch.distributed only ships its 128 bytes
+    if distributed:
+        idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            idt.copy_(torch.frombuffer(bytearray(ds.comm_unique_id()), dtype=torch.uint8))
+        dist.broadcast(idt, src=0)
+        ctx.comm_init(world, rank, bytes(idt.cpu().numpy().tobytes()))
 
     # ---- inputs: resident in HBM before any timed region ----
-    ctx.volume_synth(a.grid, GRID_KIND, GRID_SEED, True)
-    ctx.scene_set(CLOUD_SIZE_M, SUN_FRONT)
-    t0 = time.perf_counter()
+    ctx.volume_synth(c["grid"], c["kind"], GRID_SEED, True)
+    ctx.scene_set(c["size_m"], c["sun"])
+    ctx.set_option("profile_events", 1)
     ctx.bake()
     ctx.sync()
-    bake_s = time.perf_counter() - t0
-    ctx.frame_create(a.width, a.height)
-    cam = ds.camera_look_at(aspect=a.width / a.height)
-    px = a.width * a.height
-    mode = ds.MODE_ALL_SCATTER
-
-    # rank r renders global subframe ids r*B + 1 ... (B = per-rank budget); local Welford weights run 1/k
-    per_rank_budget = (a.warmup + a.steps) * a.spp * 2 + 16
-    ctx.set_option("stream_offset", rank * per_rank_budget)
-    moments = torch.zeros(px * 8, dtype=torch.float64, device="cuda") if distributed else None
+    bake_us = ctx.get_option("bake_last_us")
+    ctx.frame_create(c["width"], c["height"])
+    cam = ds.camera_look_at(aspect=c["width"] / c["height"])
+    px = c["width"] * c["height"]
+    mode = c["mode"]
 
     def barrier():
         if distributed:
             dist.barrier()
         torch.cuda.synchronize()
 
+    def device_step(step_index: int):
+        """One progressive frame: clear, this rank's subframes, the NCCL reduce of the accumulation buffers."""
+        ctx.frame_clear()
+        ctx.set_option("stream_offset", step_index * n_total + offset)
+        if n_local:
+            ctx.render_subframes(cam, mode, 1, n_local)
+        if distributed:
+            ctx.frame_reduce(n_local, n_total, 0)
+
     # ---- device-resident timed region ----
-    sub = 1
+    step_index = 0
     with torch.cuda.stream(stream):
         for _ in range(a.warmup):
-            ctx.render_subframes(cam, mode, sub, a.spp)
-            sub += a.spp
+            device_step(step_index)
+            step_index += 1
         ctx.sync()
-        ctx.set_option("profile_events", 1)
         ctx.counters_reset()
         sampler = ClockSampler(local_rank)
         barrier()
         sampler.start()
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record(stream)
-        n_local = 0
         for _ in range(a.steps):
-            ctx.render_subframes(cam, mode, sub, a.spp)
-            sub += a.spp
-            n_local += a.spp
-        if distributed:
-            # the single NCCL reduce of the per-GPU accumulation buffers (as mergeable moments)
-            ctx.export_moments(sub - 1, moments.data_ptr())
-            multigpu.reduce_moments(moments, dst=0)
-            if rank == 0:
-                ctx.import_moments((sub - 1) * world, moments.data_ptr())
+            device_step(step_index)
+            step_index += 1
         ev1.record(stream)
         barrier()
         clocks = sampler.stop()
@@ -302,134 +377,201 @@ def run_ours(a):
     counters = ctx.counters()
     lstats = ctx.launch_stats()
     ctx.set_option("profile_events", 0)
+    frame_mean = float(ctx.frame_download()[0][..., 0].astype(np.float64).mean()) if rank == 0 else 0.0
 
     t = torch.tensor([ms], dtype=torch.float64, device="cuda")
-    agg = torch.tensor([counters["paths"], counters["events"], counters["steps"], counters["density_taps"]], dtype=torch.float64, device="cuda")
+    keys = ("paths", "events", "steps", "density_taps", "untraced_paths", "untraced_steps")
+    agg = torch.tensor([counters[k] for k in keys], dtype=torch.float64, device="cuda")
     if distributed:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(agg, op=dist.ReduceOp.SUM)
     ms_max = float(t.item())
-    paths, events, steps, taps = (float(x) for x in agg.tolist())
-    value = paths / (ms_max * 1e-3) / 1e6
+    paths, events, steps, taps, untraced_paths, untraced_steps = (float(x) for x in agg.tolist())
+    secs = ms_max * 1e-3
+    value = paths / secs / 1e6
 
-    # ---- end-to-end through the C ABI with HOST buffers (pinned), copies inside the timed region ----
+    # ---- end to end through the C ABI with HOST buffers (pinned): every step uploads the accumulation buffers, renders,
+    # reduces over NCCL and downloads the finished frame on rank 0; copies inside the timed region ----
     hp = torch.zeros(px * 4, dtype=torch.float32).pin_memory()
     hv = torch.zeros(px * 4, dtype=torch.float32).pin_memory()
-    ctx.frame_clear()
-    e2e_sub = 1
+    lib = ctx.lib
+
+    def e2e_step(step_index: int):
+        ctx.set_option("stream_offset", step_index * n_total + offset)
+        if not distributed:
+            hp.zero_()
+            hv.zero_()
+            ctx.render_subframes_host_ptr(cam, mode, 1, n_local, hp.data_ptr(), hv.data_ptr())  # H2D + render + D2H
+            return
+        ctx._ck(lib.ds_frame_upload(ctx.h, hp.data_ptr(), hv.data_ptr()))  # zeros: a new frame starts from host state
+        if n_local:
+            ctx.render_subframes(cam, mode, 1, n_local)
+        ctx.frame_reduce(n_local, n_total, 0)
+        if rank == 0:
+            ctx._ck(lib.ds_frame_download(ctx.h, hp.data_ptr(), hv.data_ptr()))
+        else:
+            ctx.sync()
+
+    if distributed and rank != 0:
+        hp.zero_()
     for _ in range(min(a.warmup, 2)):
-        ctx.render_subframes_host_ptr(cam, mode, e2e_sub, a.spp, hp.data_ptr(), hv.data_ptr())
-        e2e_sub += a.spp
+        e2e_step(step_index)
+        step_index += 1
+        if distributed:
+            hp.zero_(), hv.zero_()
     barrier()
     t0 = time.perf_counter()
     for _ in range(a.steps):
-        ctx.render_subframes_host_ptr(cam, mode, e2e_sub, a.spp, hp.data_ptr(), hv.data_ptr())
-        e2e_sub += a.spp
+        e2e_step(step_index)
+        step_index += 1
+        if distributed and rank == 0:
+            checksum_keep = float(hp.view(-1, 4)[::97, 0].double().mean())
+            hp.zero_(), hv.zero_()
     barrier()
     e2e_s = time.perf_counter() - t0
     te = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
     if distributed:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_value = world * a.steps * a.spp * px / float(te.item()) / 1e6
-    checksum = float(hp.view(-1, 4)[:, 0].double().mean())
+    e2e_paths = a.steps * n_total * px
+    e2e_value = e2e_paths / float(te.item()) / 1e6
+    checksum = float(hp.view(-1, 4)[:, 0].double().mean()) if not distributed else (checksum_keep if rank == 0 else 0.0)
 
-    # ---- roofline of the dominant kernel (k_trace): algorithmic bytes = 8 B/march step + 8 B/scatter event ----
-    peaks_path = ROOT / "MEASURED_PEAKS.json"
-    if peaks_path.exists():
-        peak, peak_src = float(json.loads(peaks_path.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    # ---- roofline of the dominant kernel (k_trace_fast) ----
+    peaks = load_json(ROOT / "MEASURED_PEAKS.json")
+    if peaks and "hbm_gbs" in peaks:
+        peak, peak_src = float(peaks["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     else:
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    l2 = load_json(ROOT / "profiles" / "l2_peaks.json") or {}
     trace_launches = max(1, lstats["trace_launches_timed"])
-    trace_ms_avg = lstats["trace_ms_total"] / trace_launches
-    alg_bytes_per_launch = (8.0 * counters["steps"] + 8.0 * counters["events"]) / trace_launches
-    achieved = alg_bytes_per_launch / (trace_ms_avg * 1e-3) / 1e9 if trace_ms_avg > 0 else 0.0
-    # DRAM traffic of one launch from the committed ncu --set full capture of this very configuration (never measured here:
-    # a number taken under a profiler is not a bench value, and the capture is only valid for the configuration it was taken on)
+    kernel_s = lstats["trace_ms_total"] * 1e-3 / trace_launches  # average launch duration, CUDA events inside the library
+    per = lambda x: x / trace_launches  # noqa: E731  (rank-local counters: this rank's launches)
+    k_steps = counters["steps"] - counters["untraced_steps"]  # what kernel threads counted (executed + leapt inside the kernel)
+    alg_kernel = 8.0 * k_steps + 8.0 * counters["events"]
+    alg_reference = 8.0 * counters["steps"] + 8.0 * counters["events"]  # SURVEY 8d on every march step of the reference algorithm
+    alg_executed = 8.0 * counters["density_taps"] + 8.0 * counters["events"]  # taps actually fetched
+    gbs = lambda b: per(b) / kernel_s / 1e9 if kernel_s > 0 else 0.0  # noqa: E731
+    tex_taps_s = per(counters["density_taps"] + counters["events"]) / kernel_s if kernel_s > 0 else 0.0
     traffic = None
-    tpath = ROOT / "profiles" / "traffic_k_trace_fast.json"
-    if tpath.exists():
-        t = json.loads(tpath.read_text())
-        if t["config"] == {"grid": a.grid, "width": a.width, "height": a.height, "spp": a.spp, "precision": a.precision}:
-            traffic = t["dram_bytes_read"] + t["dram_bytes_write"]
+    tfile = load_json(ROOT / "profiles" / "traffic_k_trace_fast.json")
+    if tfile and tfile.get("config") == {"grid": c["grid"], "width": c["width"], "height": c["height"], "spp": n_local, "precision": a.precision}:
+        traffic = tfile["dram_bytes_read"] + tfile["dram_bytes_write"]
+    resident = "l2" if 2 * c["grid"] ** 3 <= 4 * 126e6 else "dram"
+    tex_peak = (l2.get("tex3d_march_gtaps") or {}).get("l2_320" if resident == "l2" else "dram_1024")
     roofline = {
-        "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-        "kernel": "k_trace", "kernel_ms_avg": trace_ms_avg, "kernel_share_of_step": lstats["trace_ms_total"] / ms if ms > 0 else None,
-        "algorithmic_bytes_per_launch": alg_bytes_per_launch, "peak_source": peak_src,
-        "note": "algorithmic bytes count every march step of the reference algorithm (8 B) and every scatter event (8 B); "
-                "empty-space skipping and L2/texture-cache hits make DRAM traffic (`traffic`, bytes per launch from "
-                "profiles/traffic_k_trace_fast.json) much smaller than this; ncu: L2 throughput 76 %, issue slots 70 % busy",
+        "bound": "hbm", "achieved": gbs(alg_kernel), "peak": peak, "unit": "GB/s", "frac": gbs(alg_kernel) / peak, "traffic": traffic,
+        "kernel": "k_trace_fast" if a.precision == "fast" else "k_trace", "kernel_ms_avg": kernel_s * 1e3,
+        "kernel_share_of_step": lstats["trace_ms_total"] / ms if ms > 0 else None, "algorithmic_bytes_per_launch": per(alg_kernel),
+        "peak_source": peak_src,
+        "definition": "achieved = (8 B x march steps counted by the kernel's own threads + 8 B x scatter events) per launch / launch duration",
+        "frac_reference_steps": gbs(alg_reference) / peak,
+        "frac_executed": gbs(alg_executed) / peak,
+        "executed_gbs": gbs(alg_executed),
+        "l2_frac": gbs(alg_executed) / l2["l2_sector_gather_gbs"] if l2.get("l2_sector_gather_gbs") else None,
+        "tex_taps_per_s": tex_taps_s,
+        "tex_frac": tex_taps_s / (tex_peak * 1e9) if tex_peak else None,
+        "tex_peak_gtaps": tex_peak, "l2_peaks": "profiles/l2_peaks.json (tools/microbench/l2_gather.cu)" if l2 else None,
+        "note": ("frac: SURVEY 8d bytes over the steps the kernel itself accounts for; frac_reference_steps adds the steps of pixels the "
+                 "primary-ray cache settles without tracing (host-side count, DsCounters.untraced_steps); frac_executed counts only taps "
+                 "actually fetched (8 B each) -- the kernel is bound by the texture path (tex_frac = fetched taps/s over the measured "
+                 "trilinear tex3D rate for a march-coherent access pattern at this residency), not by HBM"),
     }
 
     line = {
         "metric": METRIC, "value": value, "unit": METRIC, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
-        "ms_per_step": ms_max / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-        "data": "synthetic",
-        "config": {"workload": workload_name(a), "precision": a.precision, "grid_bytes": 2 * a.grid**3,
-                   "l2": "inputs (density + sun-transmittance grids, 2*N^3 B) are larger than the 126 MB L2; no explicit flush",
-                   "multi_gpu": "replicated grid, subframe ids split over ranks, one NCCL reduce of moment buffers" if distributed else "single GPU",
-                   "options": {k: ctx.get_option(k) for k in ("variant", "block_threads", "blocks_per_sm", "skip_empty", "primary_cache", "regen_min", "skip_min",
-                                                               "skip_max_iters", "march_keep32", "march_max_iters", "staging_subframes")}},
+        "ms_per_step": ms_max / a.steps, "higher_is_better": True, "scaling": a.scaling, "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "config": config_dict(a),
+        "run": {"precision": a.precision, "grid_bytes": 2 * c["grid"] ** 3, "subframes_per_step_this_rank": n_local,
+                "multi_gpu": (f"replicated grid; the {n_total} subframes of a step split over {world} ranks; one ncclReduce (float64 moments, "
+                              f"{px * 64} B) per step inside ds_frame_reduce") if distributed else "single GPU",
+                "options": {k: ctx.get_option(k) for k in ("variant", "block_threads", "blocks_per_sm", "skip_empty", "primary_cache", "region_pixels",
+                                                            "regen_min", "skip_min", "skip_max_iters", "march_keep32", "march_max_iters",
+                                                            "march_unroll", "staging_subframes")}},
         "clocks": clocks,
-        "e2e": {"value": e2e_value, "unit": METRIC, "h2d_bytes_per_step": 2 * px * 16, "d2h_bytes_per_step": 2 * px * 16,
-                "api": "ds_render_subframes_host (progressive + variance float4 buffers in pinned host memory)", "checksum_mean_radiance": checksum},
+        "e2e": {"value": e2e_value, "unit": METRIC, "h2d_bytes_per_step": world * 2 * px * 16, "d2h_bytes_per_step": 2 * px * 16,
+                "api": ("ds_render_subframes_host (progressive + variance float4 buffers in pinned host memory)" if not distributed else
+                        "per rank ds_frame_upload + ds_render_subframes + ds_frame_reduce (NCCL), rank 0 ds_frame_download; pinned host buffers"),
+                "checksum_mean_radiance": checksum},
         "gpu_launches": lstats["kernel_launches"],
         "roofline": roofline,
-        "events_per_s": events / (ms_max * 1e-3), "steps_per_s": steps / (ms_max * 1e-3), "density_taps_per_s": taps / (ms_max * 1e-3),
-        "events_per_path": events / paths, "steps_per_path": steps / paths, "bake_seconds": bake_s,
-        "nonfinite": counters["nonfinite"],
+        "hit_fraction": 1.0 - untraced_paths / paths if paths else None,
+        "hit_mpaths_s": (paths - untraced_paths) / secs / 1e6,
+        "events_per_s": events / secs, "steps_per_s": steps / secs, "density_taps_per_s": taps / secs,
+        "events_per_path": events / paths, "events_per_hit_path": events / max(1.0, paths - untraced_paths), "steps_per_path": steps / paths,
+        "frame_mean_radiance": frame_mean, "nonfinite": counters["nonfinite"],
     }
 
-    # ---- CPU baseline: the oracle on a bounded sample of the same workload (rank 0, N = 1 only) ----
+    # ---- CPU baseline: the reference estimator on the host cores, a bounded subset of the same pixels (rank 0, N = 1 only) ----
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
         try:
-            o, ol = oracle_with_scene(a, ctx.level(0), ctx.inscatter())
-            cores = host_threads()
-            w, h = 96, 54
-            dt, c = time_oracle_sample(o, ol, a, w, h, 1, 1)  # calibration
-            per_path = dt / max(1, c["paths"])
-            want_paths = a.cpu_seconds / max(per_path, 1e-9)
-            scale = max(1.0, min(10.0, (want_paths / (w * h)) ** 0.5))
-            w2, h2 = int(w * scale), int(h * scale)
-            spp = max(1, int(want_paths / (w2 * h2)))
-            spp = min(spp, 64)
-            dt, c = time_oracle_sample(o, ol, a, w2, h2, spp, 1)
-            line["cpu_baseline"] = {
-                "value": c["paths"] / dt / 1e6, "unit": METRIC, "cores": cores, "kind": "port",
-                "sample": f"{w2}x{h2} px down-sampling of the C2 frame x {spp} subframes ({c['paths']} paths, {dt:.1f} s)",
-                "events_per_s": c["events"] / dt, "steps_per_s": c["steps"] / dt,
-            }
+            est = CpuEstimator(a)
+            stride = est.pick_stride(a.cpu_seconds)
+            dt, n, rad = est.trace(stride, 1)
+            line["cpu_baseline"] = {"value": n / dt / 1e6, "unit": METRIC, "cores": est.cores, "kind": est.kind,
+                                    "sample": est.sample_text(stride) + f" ({dt:.1f} s)", "mean_radiance": float(rad[:, 0].astype(np.float64).mean())}
         except Exception as exc:  # the baseline is reporting only; never lose the GPU line
             line["cpu_baseline"] = {"value": None, "unit": METRIC, "cores": host_threads(), "kind": "port", "sample": f"failed: {exc}"}
 
-    # ---- secondary numbers of the same build (rank 0, N = 1 only; never in the timed region, never able to lose the main line):
-    # the neural renderer end to end on the same cloud and frame, and its network alone ----
+    # ---- the other two kernels north_star names, with their own rooflines (rank 0, N = 1 only; outside every timed region) ----
     if rank == 0 and world == 1 and not a.no_secondary:
+        sec = {}
         try:
-            from deepestscatter_b200 import disney_model as dm
-
-            ctx.disney_model_load(dm.synthetic_weights(566))
-            ctx.render_disney(cam, a.width, a.height, stream=1)  # warm-up (scratch allocation, mip-mapped texture)
-            times = []
-            for rep in range(3):
-                t0 = time.perf_counter()
-                frame = ctx.render_disney(cam, a.width, a.height, stream=2 + rep)
-                times.append(time.perf_counter() - t0)
-            rows = 1 << 17
-            x = dm.synthetic_inputs(1024, 33)
-            x = np.ascontiguousarray(np.tile(x, (rows // 1024, 1, 1)))
+            vox = c["grid"] ** 3
+            # bake: 8 B per voxel-step (density tap) + 1 B per voxel written; the executed taps are what the counters cannot see here,
+            # so the leg reports the voxel rate and the write-bound floor
+            sec["bake"] = {"kernel": "k_bake", "us": bake_us, "voxels": vox, "gvoxels_per_s": vox / (bake_us * 1e-6) / 1e9 if bake_us else None,
+                           "roofline": {"bound": "hbm", "unit": "GB/s", "peak": peak,
+                                        "achieved": (vox * 2) / (bake_us * 1e-6) / 1e9 if bake_us else None,
+                                        "frac": (vox * 2) / (bake_us * 1e-6) / 1e9 / peak if bake_us else None,
+                                        "definition": "streaming floor: 1 B density read + 1 B written per voxel (taps along the sun ray are "
+                                                      "cache hits of neighbouring voxels' reads); the kernel is tap/latency-bound, not HBM-bound"}}
+            n_desc = 1 << 18
+            pts, dirs = ctx.generate_points(0, 4096, 0)
+            reps = n_desc // 4096
+            pts, dirs = np.tile(pts, (reps, 1)), np.tile(dirs, (reps, 1))
             ctx.set_option("profile_events", 1)
-            ctx.disney_model_forward(x)
-            ctx.disney_model_forward(x)
-            us = ctx.get_option("mlp_last_us")
-            macs = 10 * (226 * 200 + 2 * 200 * 200) - 200 * 200 + 2 * 200 * 200 + 200
-            line["secondary"] = {
-                "neural_renderer_ms_per_frame": min(times) * 1e3, "neural_renderer_scattering_pixels": int((frame[..., 3] != 0).sum()),
-                "neural_renderer_api": "ds_render_disney (DisneyRenderer::render; host frame buffer out), synthetic weights",
-                "model_kernel": "k_disney_mlp_tc (tcgen05 kind::tf32)", "model_rows": rows, "model_us": us,
-                "model_tflops_tf32": 2 * macs * rows / (us * 1e-6) / 1e12 if us else None,
-            }
-        except Exception as exc:  # reporting only
-            line["secondary"] = {"failed": str(exc)}
+            ctx.descriptors(pts, dirs)  # warm-up
+            t0 = time.perf_counter()
+            ctx.descriptors(pts, dirs)
+            wall = time.perf_counter() - t0
+            us = ctx.get_option("descriptors_last_us")
+            ctx.set_option("profile_events", 0)
+            alg = n_desc * (2250 * 16 + 2250)  # <= 16 B read per LOD tap + 2250 B written per sample
+            sec["descriptors"] = {"kernel": "k_descriptors<EXACT>", "samples": n_desc, "us": us, "samples_per_s": n_desc / (us * 1e-6) if us else None,
+                                  "e2e_samples_per_s": n_desc / wall, "e2e_api": "ds_collect_descriptors (host in, host out)",
+                                  "roofline": {"bound": "hbm", "unit": "GB/s", "peak": peak, "achieved": alg / (us * 1e-6) / 1e9 if us else None,
+                                               "frac": alg / (us * 1e-6) / 1e9 / peak if us else None,
+                                               "definition": "2250 taps x 16 B (two mip levels) + 2250 B written per sample (upper bound: integral LODs read 8 B)"}}
+        except Exception as exc:
+            sec["failed"] = str(exc)
+        if a.config == "C2":
+            try:
+                from deepestscatter_b200 import disney_model as dm
+
+                ctx.disney_model_load(dm.synthetic_weights(566))
+                ctx.render_disney(cam, c["width"], c["height"], stream=1)  # warm-up (scratch allocation, mip-mapped texture)
+                times = []
+                for rep in range(3):
+                    t0 = time.perf_counter()
+                    frame = ctx.render_disney(cam, c["width"], c["height"], stream=2 + rep)
+                    times.append(time.perf_counter() - t0)
+                rows = 1 << 17
+                x = dm.synthetic_inputs(1024, 33)
+                x = np.ascontiguousarray(np.tile(x, (rows // 1024, 1, 1)))
+                ctx.set_option("profile_events", 1)
+                ctx.disney_model_forward(x)
+                ctx.disney_model_forward(x)
+                us = ctx.get_option("mlp_last_us")
+                macs = 10 * (226 * 200 + 2 * 200 * 200) - 200 * 200 + 2 * 200 * 200 + 200
+                sec["neural_renderer"] = {
+                    "ms_per_frame": min(times) * 1e3, "scattering_pixels": int((frame[..., 3] != 0).sum()),
+                    "api": "ds_render_disney (DisneyRenderer::render; host frame buffer out), synthetic weights",
+                    "model_kernel": "k_disney_mlp_tc (tcgen05 kind::tf32)", "model_rows": rows, "model_us": us,
+                    "model_tflops_tf32": 2 * macs * rows / (us * 1e-6) / 1e12 if us else None,
+                }
+            except Exception as exc:  # reporting only
+                sec["neural_renderer"] = {"failed": str(exc)}
+        line["secondary"] = sec
 
     if rank == 0:
         print(json.dumps(line))

@@ -4,7 +4,6 @@ The product is the C-ABI shared library `libdeepestscatter_b200.so` (include/ds_
 deepestscatter_b200/csrc/ for sm_100a).  This package only loads it and marshals numpy / torch buffers.
 """
 from ._lib import LIB_PATH, build_library, load
-from . import lmdb_compat
 from .dataset import Dataset
 from .context import (
     MODE_ALL_SCATTER,
@@ -20,6 +19,7 @@ from .context import (
     camera_array,
     camera_look_at,
     cloud_crop_active,
+    comm_unique_id,
     record_disney_descriptor,
     record_result,
     record_scatter_sample,
@@ -27,7 +27,7 @@ from .context import (
 )
 
 __all__ = [
-    "LIB_PATH", "build_library", "load", "Context", "DsError", "camera_look_at", "camera_array",
+    "LIB_PATH", "build_library", "load", "Context", "DsError", "camera_look_at", "camera_array", "comm_unique_id",
     "MODE_ALL_SCATTER", "MODE_MULTIPLE_SCATTER", "MODE_SINGLE_SCATTER", "PRECISION_EXACT", "PRECISION_FAST", "TASK_DTYPE",
-    "record_scatter_sample", "record_disney_descriptor", "record_result", "record_scene_setup", "Dataset", "lmdb_compat", "cloud_crop_active", "INFO_DTYPE", "blit_predicted",
+    "record_scatter_sample", "record_disney_descriptor", "record_result", "record_scene_setup", "Dataset", "cloud_crop_active", "INFO_DTYPE", "blit_predicted",
 ]

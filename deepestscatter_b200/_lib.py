@@ -51,6 +51,8 @@ class DsCounters(C.Structure):
         ("steps", C.c_uint64),
         ("density_taps", C.c_uint64),
         ("nonfinite", C.c_uint64),
+        ("untraced_paths", C.c_uint64),
+        ("untraced_steps", C.c_uint64),
     ]
 
 
@@ -107,6 +109,10 @@ SIGNATURES = {
     "ds_frame_unconverged": (_i, [_vp, _u32, C.POINTER(_u32)]),
     "ds_frame_export_moments_device": (_i, [_vp, _u32, _vp]),
     "ds_frame_import_moments_device": (_i, [_vp, _u32, _vp]),
+    "ds_comm_unique_id": (_i, [_vp]),
+    "ds_comm_init": (_i, [_vp, _i, _i, _vp]),
+    "ds_comm_destroy": (_i, [_vp]),
+    "ds_frame_reduce": (_i, [_vp, _u32, _u32, _i]),
     "ds_trace_paths": (_i, [_vp, _i, _u32, _vp, _vp, _vp, _vp, _vp]),
     "ds_generate_points": (_i, [_vp, _u32, _u32, _u32, _vp, _vp]),
     "ds_collect_descriptors": (_i, [_vp, _vp, _vp, _u32, _vp]),

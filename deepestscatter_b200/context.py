@@ -70,6 +70,16 @@ def camera_look_at(eye=(2.5, -0.4, 0.0), lookat=(0.0, 0.0, 0.0), up=(0.0, 1.0, 0
     return cam
 
 
+def comm_unique_id() -> bytes:
+    """ncclGetUniqueId (rank 0); ship the 128 bytes to the other ranks by any means (torch.distributed broadcast, a file, MPI)."""
+    lib = _lib.load()
+    buf = (C.c_uint8 * 128)()
+    rc = lib.ds_comm_unique_id(buf)
+    if rc != 0:
+        raise DsError(rc, (lib.ds_last_error(None) or b"").decode())
+    return bytes(buf)
+
+
 def camera_array(cam: DsCamera) -> np.ndarray:
     return np.array(list(cam.eye) + list(cam.U) + list(cam.V) + list(cam.W), dtype=np.float32)
 
@@ -134,7 +144,8 @@ class Context:
     def counters(self) -> dict:
         c = DsCounters()
         self._ck(self.lib.ds_get_counters(self.h, C.byref(c)))
-        return dict(paths=c.paths, events=c.events, steps=c.steps, density_taps=c.density_taps, nonfinite=c.nonfinite)
+        return dict(paths=c.paths, events=c.events, steps=c.steps, density_taps=c.density_taps, nonfinite=c.nonfinite,
+                    untraced_paths=c.untraced_paths, untraced_steps=c.untraced_steps)
 
     def counters_reset(self):
         self._ck(self.lib.ds_reset_counters(self.h))
@@ -272,6 +283,20 @@ class Context:
 
     def import_moments(self, n_total: int, device_ptr: int):
         self._ck(self.lib.ds_frame_import_moments_device(self.h, n_total, C.c_void_p(device_ptr)))
+
+    # ---- multi-GPU accumulation-buffer reduce (NCCL inside the library) ----
+    def comm_init(self, n_ranks: int, rank: int, unique_id: bytes):
+        """ncclCommInitRank on this context's device; collective over all ranks.  `unique_id` = comm_unique_id() of rank 0."""
+        assert len(unique_id) == 128
+        buf = (C.c_uint8 * 128).from_buffer_copy(unique_id)
+        self._ck(self.lib.ds_comm_init(self.h, n_ranks, rank, buf))
+
+    def comm_destroy(self):
+        self._ck(self.lib.ds_comm_destroy(self.h))
+
+    def frame_reduce(self, n_local: int, n_total: int, root: int = 0):
+        """Collective: combine the per-GPU accumulation buffers (one ncclReduce of float64 moments); root < 0 = all ranks."""
+        self._ck(self.lib.ds_frame_reduce(self.h, n_local, n_total, root))
 
     # ---- generic paths ----
     def trace_paths(self, mode: int, origins, dirs, seed_val0, stream) -> np.ndarray:

@@ -12,6 +12,8 @@
 #include <string>
 #include <vector>
 
+#include <dlfcn.h>
+
 #include "ds_kernels.h"
 #include "ds_mlp.h"
 
@@ -78,6 +80,12 @@ struct DsContext {
     std::vector<cudaEvent_t> traceEvents;  /* start/stop pairs around k_trace launches ("profile_events") */
     size_t traceEventsUsed = 0;
 
+    /* multi-GPU reduce (ds_comm_*, ds_frame_reduce) */
+    void* comm = nullptr;       /* ncclComm_t */
+    int commRanks = 0, commRank = -1;
+    double* moments = nullptr;  /* 8 * W * H doubles */
+    size_t momentsPixels = 0;
+
     /* scratch */
     void* scratch[8] = {nullptr};
     size_t scratchSize[8] = {0};
@@ -111,6 +119,30 @@ static thread_local std::string g_createError;
 #define DS_CHECK_CTX(ctx)          \
     if (!(ctx)) return DS_ERR_INVALID; \
     cudaSetDevice((ctx)->device)
+
+/* With option "profile_events" on, the device time of a kernel (CUDA events on the context's stream) is published as the
+ * read-only option `key` in microseconds: what bench.py's roofline legs divide the algorithmic bytes by. */
+struct KernelTimer {
+    DsContext* ctx;
+    const char* key;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    KernelTimer(DsContext* c, const char* k) : ctx(c), key(k)
+    {
+        if (ctx->opt["profile_events"] && cudaEventCreate(&e0) == cudaSuccess && cudaEventCreate(&e1) == cudaSuccess) cudaEventRecord(e0, ctx->stream);
+    }
+    void stop()
+    {
+        if (!e1) return;
+        float ms = 0.0f;
+        cudaEventRecord(e1, ctx->stream);
+        if (cudaEventSynchronize(e1) == cudaSuccess && cudaEventElapsedTime(&ms, e0, e1) == cudaSuccess) ctx->opt[key] = (int)(ms * 1000.0f + 0.5f);
+    }
+    ~KernelTimer()
+    {
+        if (e0) cudaEventDestroy(e0);
+        if (e1) cudaEventDestroy(e1);
+    }
+};
 
 static int ensureScratch(DsContext* ctx, int slot, size_t bytes)
 {
@@ -567,10 +599,13 @@ int ds_context_create(int device, DsContext** out)
     ctx->opt["stream_offset"] = 0;
     ctx->opt["profile_events"] = 0;
     ctx->opt["primary_cache"] = 1;
+    ctx->opt["region_pixels"] = 4096; /* FAST render: hit-list pixels per region of the region-major item order (0 = subframe-major) */
     ctx->opt["descriptor_hw"] = -1;
     ctx->opt["mlp_bf16"] = 0; /* FAST flavour of the model: 0 = tf32 operands (default), 1 = bf16 operands (twice the MMA rate, half the operand bytes) */
     ctx->opt["compact_reverse"] = 0; /* test hook: neural renderer processes the scattering pixels in the opposite order */
     ctx->opt["mlp_last_us"] = 0; /* read-only: device time of the last model launch when profile_events is on */
+    ctx->opt["descriptors_last_us"] = 0; /* read-only: device time of the last descriptor-gather kernel (profile_events) */
+    ctx->opt["bake_last_us"] = 0;        /* read-only: device time of the last sun-transmittance bake kernel (profile_events) */
     ds_scene_params_default(&ctx->params);
     bool ok = cudaMalloc(&ctx->stats, CNT_COUNT * sizeof(unsigned long long)) == cudaSuccess &&
               cudaMalloc(&ctx->queue, sizeof(unsigned long long)) == cudaSuccess &&
@@ -629,6 +664,8 @@ int ds_context_destroy(DsContext* ctx)
     if (!ctx) return DS_ERR_INVALID;
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    ds_comm_destroy(ctx);
+    cudaFree(ctx->moments);
     freeVolume(ctx);
     freeFrame(ctx);
     cudaFree(ctx->stats);
@@ -674,6 +711,7 @@ int ds_set_option(DsContext* ctx, const char* name, int value)
     if (n == "march_unroll" && (value < 0 || value > 2)) DS_FAIL(ctx, DS_ERR_INVALID, "march_unroll must be 0 (auto), 1 or 2");
     if (n == "skip_open_dist" && value < 1) DS_FAIL(ctx, DS_ERR_INVALID, "skip_open_dist must be >= 1 (0 would leap out of occupied cells)");
     if (n == "staging_subframes" && value < 1) DS_FAIL(ctx, DS_ERR_INVALID, "staging_subframes must be >= 1");
+    if (n == "region_pixels" && (value < 0 || value > (1 << 20))) DS_FAIL(ctx, DS_ERR_INVALID, "region_pixels must be 0 .. 2^20");
     if (n == "march_max_iters" && value < 1) DS_FAIL(ctx, DS_ERR_INVALID, "march_max_iters must be >= 1");
     ctx->opt[n] = value;
     return DS_OK;
@@ -699,6 +737,8 @@ int ds_get_counters(DsContext* ctx, DsCounters* out)
     out->steps = h[CNT_STEPS] + ctx->extraSteps;
     out->density_taps = h[CNT_TAPS];
     out->nonfinite = h[CNT_NONFINITE];
+    out->untraced_paths = ctx->extraPaths;
+    out->untraced_steps = ctx->extraSteps;
     return DS_OK;
 }
 
@@ -858,10 +898,12 @@ int ds_bake_sun_transmittance(DsContext* ctx)
     if (rc) return rc;
     DevScene sc;
     fillDevScene(ctx, sc);
+    KernelTimer timer(ctx, "bake_last_us");
     if (ctx->opt["precision"] == DS_PRECISION_FAST)
         DS_CUDA(ctx, KernelSet<true>::bake(sc, ctx->inscatter, ctx->opt["skip_empty"], ctx->stream));
     else
         DS_CUDA(ctx, KernelSet<false>::bake(sc, ctx->inscatter, ctx->opt["skip_empty"], ctx->stream));
+    timer.stop();
     rc = makeTexture(ctx, ctx->inscatter, ctx->lnx[0], ctx->lny[0], ctx->lnz[0], &ctx->inscatterArr, &ctx->inscatterTex);
     if (rc) return rc;
     ctx->baked = true;
@@ -1033,6 +1075,8 @@ static int traceSubframes(DsContext* ctx, const DsCamera* cam, DsMode mode, uint
         job.nHit = ctx->nHit;
         job.entrySteps = ctx->entrySteps;
         job.total = (unsigned long long)ctx->nHit * n;
+        job.regionSize = (uint32_t)ctx->opt["region_pixels"];
+        job.nSub = n;
         ctx->extraPaths += ((unsigned long long)ctx->width * ctx->height - ctx->nHit) * n;
         ctx->extraSteps += ctx->missSteps * n;
         if (ctx->nHit == 0) return DS_OK;
@@ -1177,6 +1221,134 @@ int ds_frame_import_moments_device(DsContext* ctx, uint32_t n_total, const doubl
     return DS_OK;
 }
 
+/* ================================================================ multi-GPU reduce over NCCL */
+
+/* The handful of NCCL entry points the reduce needs, resolved at run time.  Types follow nccl.h 2.x (stable ABI):
+ * ncclUniqueId is 128 opaque bytes, ncclFloat64 = 8, ncclSum = 0, ncclSuccess = 0. */
+namespace {
+struct NcclUniqueId {
+    char internal[DS_COMM_ID_BYTES];
+};
+struct NcclApi {
+    void* lib = nullptr;
+    int (*GetUniqueId)(NcclUniqueId*) = nullptr;
+    int (*CommInitRank)(void**, int, NcclUniqueId, int) = nullptr;
+    int (*CommDestroy)(void*) = nullptr;
+    int (*Reduce)(const void*, void*, size_t, int, int, int, void*, cudaStream_t) = nullptr;
+    int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+    std::string why;
+};
+NcclApi& nccl()
+{
+    static NcclApi api;
+    if (api.lib || !api.why.empty()) return api;
+    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char* n : names)
+        if ((api.lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL))) break;
+    if (!api.lib) {
+        api.why = std::string("NCCL not found (dlopen libnccl.so.2): ") + (dlerror() ? dlerror() : "?");
+        return api;
+    }
+    api.GetUniqueId = (decltype(api.GetUniqueId))dlsym(api.lib, "ncclGetUniqueId");
+    api.CommInitRank = (decltype(api.CommInitRank))dlsym(api.lib, "ncclCommInitRank");
+    api.CommDestroy = (decltype(api.CommDestroy))dlsym(api.lib, "ncclCommDestroy");
+    api.Reduce = (decltype(api.Reduce))dlsym(api.lib, "ncclReduce");
+    api.AllReduce = (decltype(api.AllReduce))dlsym(api.lib, "ncclAllReduce");
+    api.GetErrorString = (decltype(api.GetErrorString))dlsym(api.lib, "ncclGetErrorString");
+    if (!api.GetUniqueId || !api.CommInitRank || !api.CommDestroy || !api.Reduce || !api.AllReduce) {
+        api.why = "NCCL library lacks an entry point (ncclGetUniqueId / ncclCommInitRank / ncclCommDestroy / ncclReduce / ncclAllReduce)";
+        dlclose(api.lib);
+        api.lib = nullptr;
+    }
+    return api;
+}
+const int NCCL_FLOAT64 = 8, NCCL_SUM = 0;
+} // namespace
+
+#define DS_NCCL(ctx, call)                                                                                                        \
+    do {                                                                                                                          \
+        int _r = (call);                                                                                                          \
+        if (_r != 0) DS_FAIL(ctx, DS_ERR_CUDA, "%s: %s", #call, nccl().GetErrorString ? nccl().GetErrorString(_r) : "NCCL error"); \
+    } while (0)
+
+int ds_comm_unique_id(uint8_t id_out[DS_COMM_ID_BYTES])
+{
+    if (!id_out) return DS_ERR_INVALID;
+    NcclApi& api = nccl();
+    if (!api.lib) {
+        g_createError = api.why;
+        return DS_ERR_STATE;
+    }
+    NcclUniqueId id;
+    if (api.GetUniqueId(&id) != 0) {
+        g_createError = "ncclGetUniqueId failed";
+        return DS_ERR_CUDA;
+    }
+    memcpy(id_out, id.internal, DS_COMM_ID_BYTES);
+    return DS_OK;
+}
+
+int ds_comm_init(DsContext* ctx, int n_ranks, int rank, const uint8_t id[DS_COMM_ID_BYTES])
+{
+    DS_CHECK_CTX(ctx);
+    if (!id || n_ranks < 1 || rank < 0 || rank >= n_ranks) DS_FAIL(ctx, DS_ERR_INVALID, "bad rank / n_ranks / id");
+    NcclApi& api = nccl();
+    if (!api.lib) DS_FAIL(ctx, DS_ERR_STATE, "%s", api.why.c_str());
+    ds_comm_destroy(ctx);
+    NcclUniqueId uid;
+    memcpy(uid.internal, id, DS_COMM_ID_BYTES);
+    DS_NCCL(ctx, api.CommInitRank(&ctx->comm, n_ranks, uid, rank));
+    ctx->commRanks = n_ranks;
+    ctx->commRank = rank;
+    return DS_OK;
+}
+
+int ds_comm_destroy(DsContext* ctx)
+{
+    if (!ctx) return DS_ERR_INVALID;
+    if (ctx->comm) {
+        cudaSetDevice(ctx->device);
+        if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+        nccl().CommDestroy(ctx->comm);
+        ctx->comm = nullptr;
+    }
+    ctx->commRanks = 0;
+    ctx->commRank = -1;
+    return DS_OK;
+}
+
+int ds_frame_reduce(DsContext* ctx, uint32_t n_local, uint32_t n_total, int root)
+{
+    DS_CHECK_CTX(ctx);
+    if (!ctx->comm) DS_FAIL(ctx, DS_ERR_STATE, "no communicator (ds_comm_init)");
+    if (!ctx->progressive) DS_FAIL(ctx, DS_ERR_STATE, "no frame (ds_frame_create)");
+    if (n_total == 0 || n_local > n_total || root >= ctx->commRanks) DS_FAIL(ctx, DS_ERR_INVALID, "bad n_local / n_total / root");
+    const size_t pixels = (size_t)ctx->width * ctx->height;
+    if (ctx->momentsPixels != pixels) {
+        cudaFree(ctx->moments);
+        ctx->moments = nullptr;
+        ctx->momentsPixels = 0;
+        DS_CUDA(ctx, cudaMalloc(&ctx->moments, pixels * 8 * sizeof(double)));
+        ctx->momentsPixels = pixels;
+    }
+    /* float64 moments {n*mean, M2 + n*mean^2}: the import subtracts N*mean^2 from the summed second moment, which cancels
+     * catastrophically in fp32 wherever a pixel's variance is small against its squared mean; 64 B/pixel over NVLink is
+     * 0.15 ms at 1080p, so exactness costs nothing that shows. */
+    DS_CUDA(ctx, launchExportMoments(ctx->progressive, ctx->variance, pixels, n_local, ctx->moments, ctx->stream));
+    ctx->launches++;
+    NcclApi& api = nccl();
+    if (root < 0)
+        DS_NCCL(ctx, api.AllReduce(ctx->moments, ctx->moments, pixels * 8, NCCL_FLOAT64, NCCL_SUM, ctx->comm, ctx->stream));
+    else
+        DS_NCCL(ctx, api.Reduce(ctx->moments, ctx->moments, pixels * 8, NCCL_FLOAT64, NCCL_SUM, root, ctx->comm, ctx->stream));
+    if (root < 0 || root == ctx->commRank) {
+        DS_CUDA(ctx, launchImportMoments(ctx->moments, pixels, n_total, ctx->progressive, ctx->variance, ctx->stream));
+        ctx->launches++;
+    }
+    return DS_OK;
+}
+
 /* ================================================================ generic paths */
 
 int ds_trace_paths(DsContext* ctx, DsMode mode, uint32_t n, const float* origins, const float* directions, const uint32_t* seed_val0,
@@ -1279,9 +1451,11 @@ static int collectDescriptors(DsContext* ctx, const float* positions, const floa
     fillDescriptorTables(ctx, lv, layers);
     cudaTextureObject_t mipTex = 0; /* the collectors use the exact software fetch unless option descriptor_hw = 1 asks for the float one */
     if (outF32 && !outU8 && !tapIndex && (rc = descriptorTexture(ctx, false, &mipTex))) return rc;
+    KernelTimer timer(ctx, "descriptors_last_us");
     DS_CUDA(ctx, launchDescriptors(sc, lv, layers, (const float*)ctx->scratch[0], (const float*)ctx->scratch[1], n,
                                    outU8 ? (uint8_t*)ctx->scratch[2] : nullptr, outF32 ? (float*)ctx->scratch[3] : nullptr,
                                    tapIndex ? (int32_t*)ctx->scratch[4] : nullptr, ctx->stream, 225, nullptr, nullptr, nullptr, mipTex));
+    timer.stop();
     if (outU8) DS_CUDA(ctx, cudaMemcpyAsync(outU8, ctx->scratch[2], taps, cudaMemcpyDeviceToHost, ctx->stream));
     if (outF32) DS_CUDA(ctx, cudaMemcpyAsync(outF32, ctx->scratch[3], taps * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
     if (tapIndex) DS_CUDA(ctx, cudaMemcpyAsync(tapIndex, ctx->scratch[4], taps * 4 * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));

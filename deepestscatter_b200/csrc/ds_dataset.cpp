@@ -125,7 +125,8 @@ int ds_dataset_merge(DsDataset* d, const char* other_path)
 {
     if (!other_path) return DS_ERR_INVALID;
     return guarded(d, [&] {
-        DeepestScatter::Dataset other{DeepestScatter::Dataset::Settings(other_path)};
+        /* read-only, never created: a mistyped shard path must fail, not merge an empty dataset (and a read-only shard must merge) */
+        DeepestScatter::Dataset other{DeepestScatter::Dataset::Settings(other_path, /*create=*/false, /*readonly=*/true)};
         d->ds->mergeFrom(other);
         return DS_OK;
     });

@@ -61,6 +61,11 @@ struct TraceJob {
      * number of march steps each of them spends in empty cells before that */
     const uint32_t* hitList;
     uint32_t nHit;
+    /* item order over the hit list: regionSize == 0: subframe-major (all hitting pixels of subframe 0, then subframe 1, ...);
+     * regionSize > 0: REGION-major -- the hit list is cut into runs of regionSize pixels (k_primary_prepass lists them in
+     * 64x64-pixel super-tile order, so a run is a compact patch of the image) and all nSub subframes of a run are handed out
+     * before the next run starts.  The ~130k paths in flight on the GPU then share a column of the volume that fits the L2. */
+    uint32_t regionSize, nSub;
     const uint32_t* entrySteps; /* [H*W], ENTRY_MISS for pixels that never reach an occupied cell */
     /* JOB_PATHS */
     const float* origins;

@@ -267,9 +267,12 @@ __global__ void __launch_bounds__(256) k_reinhard_apply(const float4* __restrict
     float ld = lw * exposure / average[0];
     ld = ld / (1.f + ld);
     const float k = ld / lw;
-    const float r = powf(fmaxf(0.f, fminf(c.x * k, 1.f)), 1.f / 2.2f) * 255;
-    const float g = powf(fmaxf(0.f, fminf(c.y * k, 1.f)), 1.f / 2.2f) * 255;
-    const float b = powf(fmaxf(0.f, fminf(c.z * k, 1.f)), 1.f / 2.2f) * 255;
+    /* nvcc folds fmaxf(0, fminf(x, 1)) into FMUL.SAT, which maps NaN to 0; the IEEE reading of the reference's text maps it
+     * to 1 (what oracle/_ref computes), so the NaN case is spelled out */
+    const float vr = c.x * k, vg = c.y * k, vb = c.z * k;
+    const float r = powf(vr != vr ? 1.f : fmaxf(0.f, fminf(vr, 1.f)), 1.f / 2.2f) * 255;
+    const float g = powf(vg != vg ? 1.f : fmaxf(0.f, fminf(vg, 1.f)), 1.f / 2.2f) * 255;
+    const float b = powf(vb != vb ? 1.f : fmaxf(0.f, fminf(vb, 1.f)), 1.f / 2.2f) * 255;
     screen[i] = make_uchar4((unsigned char)r, (unsigned char)g, (unsigned char)b, 255);
 }
 

@@ -302,8 +302,19 @@ __device__ __forceinline__ bool itemRay(const TraceJob& job, unsigned long long 
         unsigned long long sub;
         uint32_t px, py;
         if (job.hitList) {
-            sub = idx / job.nHit;
-            pixel = job.hitList[(uint32_t)(idx - sub * job.nHit)];
+            if (job.regionSize) {
+                const unsigned long long perRegion = (unsigned long long)job.regionSize * job.nSub;
+                const uint32_t region = (uint32_t)(idx / perRegion);
+                const uint32_t rem = (uint32_t)(idx - (unsigned long long)region * perRegion);
+                const uint32_t first = region * job.regionSize;
+                const uint32_t size = min(job.regionSize, job.nHit - first); /* the last run may be short */
+                const uint32_t s32 = rem / size;
+                sub = s32;
+                pixel = job.hitList[first + (rem - s32 * size)];
+            } else {
+                sub = idx / job.nHit;
+                pixel = job.hitList[(uint32_t)(idx - sub * job.nHit)];
+            }
             px = pixel % (uint32_t)job.width;
             py = pixel / (uint32_t)job.width;
         } else {
@@ -807,15 +818,38 @@ cudaError_t KernelSet<true>::trace(const DevScene& sc, const TraceJob& job, cons
  * records how many march steps precede the first tap that can be non-zero; pixels whose ray never reaches an
  * occupied cell are marked ENTRY_MISS (their radiance sample is exactly 0 for every subframe) and the number of
  * march steps the reference algorithm would spend on them is summed for the work counters.
+ * Pixels are enumerated in SUPER-TILE order (64 x 64 pixels = 8 x 16 tiles of 8 x 4, row-major inside, super-tiles row-major), and
+ * the hitting pixels are compacted in exactly that order (per-block counts -> exclusive scan -> ordered scatter), so a run of
+ * consecutive hit-list entries is a compact patch of the image and the list is the same on every run.
  */
-__global__ void __launch_bounds__(256) k_primary_prepass(const DevScene sc, const TraceJob job, const FastConsts k, uint32_t* __restrict__ entrySteps,
-                                                         uint32_t* __restrict__ hitList, unsigned long long* __restrict__ counts)
+constexpr uint32_t SUPER_TILES_X = 8, SUPER_TILES_Y = 16, SUPER_TILES = SUPER_TILES_X * SUPER_TILES_Y;
+
+__device__ __forceinline__ bool prepassPixel(const TraceJob& job, uint32_t rem, uint32_t& px, uint32_t& py)
 {
-    const uint32_t rem = blockIdx.x * blockDim.x + threadIdx.x; /* tile-ordered pixel enumeration, 32 pixels per 8x4 tile */
     const uint32_t tile = rem >> 5, within = rem & 31u;
-    const uint32_t px = (tile % (uint32_t)job.tilesX) * 8u + (within & 7u);
-    const uint32_t py = (tile / (uint32_t)job.tilesX) * 4u + (within >> 3);
-    const bool valid = rem < job.itemsPerSubframe && px < (uint32_t)job.width && py < (uint32_t)job.height;
+    const uint32_t superCols = ((uint32_t)job.tilesX + SUPER_TILES_X - 1) / SUPER_TILES_X;
+    const uint32_t sup = tile / SUPER_TILES, w = tile % SUPER_TILES;
+    const uint32_t tx = (sup % superCols) * SUPER_TILES_X + (w % SUPER_TILES_X);
+    const uint32_t ty = (sup / superCols) * SUPER_TILES_Y + (w / SUPER_TILES_X);
+    px = tx * 8u + (within & 7u);
+    py = ty * 4u + (within >> 3);
+    return tx < (uint32_t)job.tilesX && px < (uint32_t)job.width && py < (uint32_t)job.height;
+}
+
+static unsigned long long prepassItems(const TraceJob& job)
+{
+    const unsigned long long tilesY = ((unsigned long long)job.height + 3) / 4;
+    const unsigned long long superCols = ((unsigned long long)job.tilesX + SUPER_TILES_X - 1) / SUPER_TILES_X;
+    const unsigned long long superRows = (tilesY + SUPER_TILES_Y - 1) / SUPER_TILES_Y;
+    return superCols * superRows * SUPER_TILES * 32ull;
+}
+
+__global__ void __launch_bounds__(256) k_primary_prepass(const DevScene sc, const TraceJob job, const FastConsts k, uint32_t* __restrict__ entrySteps,
+                                                         uint32_t* __restrict__ blockCounts, unsigned long long* __restrict__ counts)
+{
+    const uint32_t rem = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t px, py;
+    const bool valid = prepassPixel(job, rem, px, py);
     bool hit = false;
     uint32_t steps = 0;
     const uint32_t pixel = py * (uint32_t)job.width + px;
@@ -850,28 +884,73 @@ __global__ void __launch_bounds__(256) k_primary_prepass(const DevScene sc, cons
         }
         entrySteps[pixel] = hit ? steps : ENTRY_MISS;
     }
-    /* compact the hitting pixels, warp-aggregated, in tile order within a warp */
-    const unsigned m = __ballot_sync(0xffffffffu, hit);
+    const int blockHits = __syncthreads_count(hit);
+    if (threadIdx.x == 0) blockCounts[blockIdx.x] = (uint32_t)blockHits;
     const unsigned lane = threadIdx.x & 31u;
-    unsigned long long base = 0;
-    if (m) {
-        const int leader = __ffs(m) - 1;
-        if ((int)lane == leader) base = atomicAdd(counts, (unsigned long long)__popc(m));
-        base = __shfl_sync(0xffffffffu, base, leader);
-        if (hit) hitList[base + __popc(m & ((1u << lane) - 1u))] = pixel;
-    }
     unsigned long long missSteps = (valid && !hit) ? steps : 0ull;
     for (int o = 16; o > 0; o >>= 1) missSteps += __shfl_down_sync(0xffffffffu, missSteps, o);
     if (lane == 0 && missSteps) atomicAdd(counts + 1, missSteps);
+}
+
+/* exclusive scan of the per-block hit counts, in place; counts[0] = total.  One block. */
+__global__ void __launch_bounds__(1024) k_primary_scan(uint32_t* __restrict__ blockCounts, uint32_t nBlocks, unsigned long long* __restrict__ counts)
+{
+    __shared__ uint32_t partial[1024];
+    const uint32_t per = (nBlocks + 1023u) / 1024u;
+    const uint32_t lo = threadIdx.x * per, hi = min(lo + per, nBlocks);
+    uint32_t sum = 0;
+    for (uint32_t i = lo; i < hi; i++) sum += blockCounts[i];
+    partial[threadIdx.x] = sum;
+    __syncthreads();
+    for (uint32_t off = 1; off < 1024u; off <<= 1) { /* Hillis-Steele inclusive scan */
+        const uint32_t v = threadIdx.x >= off ? partial[threadIdx.x - off] : 0u;
+        __syncthreads();
+        partial[threadIdx.x] += v;
+        __syncthreads();
+    }
+    uint32_t run = partial[threadIdx.x] - sum;
+    for (uint32_t i = lo; i < hi; i++) {
+        const uint32_t c = blockCounts[i];
+        blockCounts[i] = run;
+        run += c;
+    }
+    if (threadIdx.x == 1023) counts[0] = partial[1023];
+}
+
+/* ordered scatter of the hitting pixels: same enumeration as k_primary_prepass */
+__global__ void __launch_bounds__(256) k_primary_compact(const TraceJob job, const uint32_t* __restrict__ entrySteps, const uint32_t* __restrict__ blockBase,
+                                                         uint32_t* __restrict__ hitList)
+{
+    __shared__ uint32_t warpBase[8];
+    const uint32_t rem = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t px, py;
+    const bool valid = prepassPixel(job, rem, px, py);
+    const uint32_t pixel = py * (uint32_t)job.width + px;
+    const bool hit = valid && entrySteps[pixel] != ENTRY_MISS;
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const unsigned m = __ballot_sync(0xffffffffu, hit);
+    if (lane == 0) warpBase[warp] = (uint32_t)__popc(m);
+    __syncthreads();
+    uint32_t base = blockBase[blockIdx.x];
+    for (unsigned w = 0; w < warp; w++) base += warpBase[w];
+    if (hit) hitList[base + __popc(m & ((1u << lane) - 1u))] = pixel;
 }
 
 template <>
 cudaError_t KernelSet<true>::primaryPrepass(const DevScene& sc, const TraceJob& cam, uint32_t* entrySteps, uint32_t* hitList,
                                             unsigned long long* counts, cudaStream_t st)
 {
-    const unsigned long long items = cam.itemsPerSubframe;
-    k_primary_prepass<<<(unsigned)((items + 255) / 256), 256, 0, st>>>(sc, cam, makeConsts(sc), entrySteps, hitList, counts);
-    return cudaGetLastError();
+    const unsigned long long items = prepassItems(cam);
+    const unsigned nBlocks = (unsigned)((items + 255) / 256);
+    uint32_t* blockCounts = nullptr;
+    cudaError_t e = cudaMallocAsync((void**)&blockCounts, (size_t)nBlocks * sizeof(uint32_t), st);
+    if (e != cudaSuccess) return e;
+    k_primary_prepass<<<nBlocks, 256, 0, st>>>(sc, cam, makeConsts(sc), entrySteps, blockCounts, counts);
+    k_primary_scan<<<1, 1024, 0, st>>>(blockCounts, nBlocks, counts);
+    k_primary_compact<<<nBlocks, 256, 0, st>>>(cam, entrySteps, blockCounts, hitList);
+    e = cudaGetLastError();
+    cudaFreeAsync(blockCounts, st);
+    return e;
 }
 
 template struct KernelSet<true>;

@@ -12,6 +12,7 @@
 
 #include <cmath>
 #include <cstdio>
+#include <csignal>
 #include <functional>
 #include <fstream>
 #include <iostream>
@@ -371,13 +372,18 @@ public:
                                                    converged.data(), &updates));
         std::vector<Persistance::Result> results(settings.batchSize);
         std::cout << "Serializing emissions..." << std::endl;
+        /* The reference records only once EVERY task converged and then writes is_converged = true (RadianceCollector.cpp:130-136,
+         * 163).  With the max_updates safety cap a sample may stop unconverged: it is recorded as such, never as converged. */
+        size_t unconverged = 0;
         for (int32_t i = 0; i < settings.batchSize; i++) {
             results[i].light_intensity = tasks[i].radiance;
-            results[i].is_converged = true; /* RadianceCollector.cpp:163 */
+            results[i].is_converged = converged[i] != 0;
+            unconverged += converged[i] == 0;
         }
+        if (unconverged) std::cout << "WARNING: " << unconverged << " samples hit the update cap before converging" << std::endl;
         std::cout << "Writing emissions... (" << updates << " updates)" << std::endl;
         dataset->batchAppend(results, settings.batchStartId);
-        allPixelsConverged = true;
+        allPixelsConverged = true; /* the batch is finished (all converged, or the cap ended it) */
     }
     bool isCompleted() override { return allPixelsConverged; }
 
@@ -417,17 +423,27 @@ private:
 class ExecutionLoop {
 public:
     using LazyTask = std::function<std::shared_ptr<Scene>()>;
-    void run(std::queue<LazyTask> tasks)
+    /* afterTask runs when a task (one scene = one batch of records) is complete: the driver commits the dataset there, which is
+     * the reference's one-LMDB-transaction-per-batch (Dataset.h:203-232) and what makes CollectMode::Continue resume after a crash.
+     * stopRequested() (set by SIGINT / SIGTERM in datagen.cpp) ends the loop between tasks. */
+    void run(std::queue<LazyTask> tasks, const std::function<void()>& afterTask = nullptr)
     {
-        while (!tasks.empty()) {
+        while (!tasks.empty() && !stopRequested()) {
             std::shared_ptr<Scene> scene = tasks.front()();
             tasks.pop();
             scene->init();
             do {
                 scene->update();
             } while (!scene->isCompleted());
+            if (afterTask) afterTask();
         }
     }
+    static volatile std::sig_atomic_t& stopFlag()
+    {
+        static volatile std::sig_atomic_t flag = 0;
+        return flag;
+    }
+    static bool stopRequested() { return stopFlag() != 0; }
 };
 
 /* ---- DG/ExecutionLoop/Tasks.cpp ---- */

@@ -39,7 +39,7 @@ struct WireReader {
     {
         uint64_t v = 0;
         int shift = 0;
-        while (p < end) {
+        while (p < end && shift < 64) { /* a varint is at most 10 bytes: never shift by 64 or more */
             const uint8_t b = *p++;
             v |= (uint64_t)(b & 0x7f) << shift;
             if (!(b & 0x80)) return v;
@@ -61,17 +61,25 @@ struct WireReader {
     }
     void skip(int wireType)
     {
-        if (wireType == 0)
+        /* every advance is checked against the bytes that are left BEFORE the pointer moves: a corrupt length must not wrap it */
+        uint64_t n = 0;
+        if (wireType == 0) {
             varint();
-        else if (wireType == 5)
-            p += 4;
+            return;
+        } else if (wireType == 5)
+            n = 4;
         else if (wireType == 1)
-            p += 8;
+            n = 8;
         else if (wireType == 2)
-            p += varint();
+            n = varint();
         else
             ok = false;
-        if (p > end) ok = false;
+        if (!ok || n > (uint64_t)(end - p)) {
+            ok = false;
+            p = end;
+            return;
+        }
+        p += n;
     }
 };
 
@@ -244,12 +252,14 @@ namespace DeepestScatter {
 class Dataset {
 public:
     struct Settings {
-        explicit Settings(std::string path) : path(std::move(path)) {}
+        explicit Settings(std::string path, bool create = true, bool readonly = false) : path(std::move(path)), create(create), readonly(readonly) {}
         std::string path;
+        bool create;   /* false: a missing file is an error (merge sources, readers) instead of a fresh empty dataset */
+        bool readonly; /* opened O_RDONLY, never committed */
     };
     using TableName = std::string;
 
-    explicit Dataset(const Settings& settings) : file(settings.path, /*create=*/true)
+    explicit Dataset(const Settings& settings) : file(settings.path, settings.create && !settings.readonly, settings.readonly), readonly(settings.readonly)
     {
         /* "Opening Dataset..." (Dataset.cpp:10) */
         for (const auto& t : file.tables()) nextIds[t.first] = t.second.empty() ? 0 : (int32_t)t.second.rbegin()->first + 1;
@@ -260,7 +270,7 @@ public:
     template <class T>
     size_t getRecordsCount()
     {
-        file.createTable(T::name()); /* getTable opens with MDB_CREATE (Dataset.cpp:78-90) */
+        if (!readonly) file.createTable(T::name()); /* getTable opens with MDB_CREATE (Dataset.cpp:78-90) */
         return file.count(T::name());
     }
 
@@ -329,6 +339,7 @@ public:
      * writes anything; a dataset that was only opened stays untouched. */
     void commit()
     {
+        if (readonly) return;
         if (file.dirty())
             for (const char* name : {"SceneSetup", "ScatterSample", "DisneyDescriptor", "BakedInterpolationSet", "Result"}) file.createTable(name);
         file.commit();
@@ -345,6 +356,7 @@ public:
 
 private:
     dslmdb::LmdbFile file;
+    bool readonly = false;
     std::map<TableName, int32_t> nextIds;
 };
 

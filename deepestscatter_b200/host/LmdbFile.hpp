@@ -24,11 +24,17 @@
  * parser (deepestscatter_b200/lmdb_compat.py, tests/test_lmdb.py), which also asserts the structural invariants
  * mdb.c relies on (sorted keys, >= 2 keys per branch page, node alignment, page accounting).
  *
- * Write model: bulk loader.  Values that need overflow pages (the 2253-byte DisneyDescriptor records) are written
- * to the file the moment they are put; small values and the key index stay in memory; commit() writes fresh B+tree
- * pages (leaf pages filled front to back -- keys arrive sorted, as with MDB_APPEND), records the pages of the
- * previous trees in the free DB and flips the meta page, so a crash between commits leaves the previous snapshot
- * intact, exactly like an aborted LMDB transaction.
+ * Write model: append-optimised loader.  Values that need overflow pages (the 2253-byte DisneyDescriptor records) are
+ * written to the file the moment they are put; small values and the key index stay in memory; commit() writes B+tree pages
+ * (leaf pages filled front to back -- keys arrive sorted, as with MDB_APPEND), records the pages it replaced in the free DB
+ * and flips the meta page, so a crash between commits leaves the previous snapshot intact, exactly like an aborted LMDB
+ * transaction.
+ * A commit is INCREMENTAL for tables that were only appended to since the last snapshot (what the collectors do,
+ * Dataset.h:203-232): every completed leaf page stays where it is, only the last (partly filled) leaf, the new leaves and the
+ * branch pages above them are written -- about 1/290 of the table -- so committing after every batch of 2048 records, as the
+ * reference does, costs megabytes, not the whole table.  Tables that saw an overwrite or a drop are rebuilt.  Tree pages are
+ * allocated from pages that neither the current nor the previous snapshot references (free-DB records of transactions older
+ * than the previous one, the rule liblmdb applies when no reader is active), so repeated commits do not grow the file.
  */
 #pragma once
 
@@ -42,6 +48,7 @@
 #include <cstring>
 #include <functional>
 #include <map>
+#include <memory>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -142,6 +149,8 @@ public:
         requireWritable();
         if (n > 0xfffffff0u) throw Error("value too large");
         createTable(table);
+        TableTree& tr = trees_[table];
+        if (tr.valid && tr.covered && key <= tr.lastKey) tr.valid = false; /* not an append: this table is rebuilt by the next commit */
         Value& v = tables_[table][key];
         releaseValue(v);
         v = Value{};
@@ -173,52 +182,101 @@ public:
         if (t == tables_.end()) return;
         for (auto& kv : t->second) releaseValue(kv.second);
         t->second.clear();
+        trees_[table].valid = false;
         dirty_ = true;
     }
 
-    /* mdb_txn_commit: new tree pages, free-DB record for the pages of the previous trees, meta flip */
+    /* mdb_txn_commit: tree pages (incremental for append-only tables), free-DB record for the pages replaced, meta flip */
     void commit()
     {
         requireWritable();
         if (!dirty_) return;
         flushPending();
         const uint64_t txn = meta_.txnid + 1;
-        /* pages released by this transaction: every page of the previous trees (tables, main DB, free DB) and the
-         * overflow runs of replaced / dropped values */
+        /* pages no live snapshot references: free-DB records of transactions older than the previous snapshot's */
+        uint64_t poolKey = 0;
+        bool havePool = false;
+        for (auto it = freeRecords_.begin(); it != freeRecords_.end() && it->first + 1 <= meta_.txnid;) {
+            if (!havePool) {
+                poolKey = it->first;
+                havePool = true;
+            }
+            reusable_.insert(reusable_.end(), it->second.begin(), it->second.end());
+            it = freeRecords_.erase(it);
+        }
+        std::sort(reusable_.begin(), reusable_.end(), std::greater<uint64_t>()); /* pop_back hands out the lowest page first */
+        reuseTreePages_ = true;
+
+        /* pages released by this transaction */
         std::vector<uint64_t> freed = pendingFree_;
-        freed.insert(freed.end(), treePages_.begin(), treePages_.end());
-        std::vector<uint64_t> newTreePages;
+        freed.insert(freed.end(), metaTreePages_.begin(), metaTreePages_.end());
+        std::vector<uint64_t> newMetaPages;
 
         std::vector<Item> mainItems;
         for (const auto& t : tables_) {
-            std::vector<Item> items;
-            items.reserve(t.second.size());
-            uint64_t ovf = 0;
-            for (const auto& kv : t.second) {
-                Item it;
-                it.key.resize(4);
-                memcpy(it.key.data(), &kv.first, 4);
-                if (kv.second.big) {
-                    it.flags = F_BIGDATA;
-                    it.dataSize = kv.second.size;
-                    it.data.resize(8);
-                    memcpy(it.data.data(), &kv.second.ovfPage, 8);
-                    ovf += ovPages(kv.second.size);
-                } else {
-                    it.dataSize = kv.second.size;
-                    it.data = kv.second.bytes;
-                }
-                items.push_back(std::move(it));
+            TableTree& tr = trees_[t.first];
+            const Table& tab = t.second;
+            if (!tr.valid) { /* overwritten, dropped or never written: rebuild from the first key */
+                for (const Child& c : tr.leaves) freed.push_back(c.page);
+                freed.insert(freed.end(), tr.branchPages.begin(), tr.branchPages.end());
+                tr = TableTree();
+                tr.valid = true;
             }
-            Db db = buildTree(items, newTreePages);
-            db.flags = MDB_INTEGERKEY;
-            db.overflow_pages = ovf;
+            const bool grew = tr.covered != tab.size();
+            if (grew) {
+                freed.insert(freed.end(), tr.branchPages.begin(), tr.branchPages.end());
+                tr.branchPages.clear();
+                /* reopen the last leaf: its entries are written again together with the new ones */
+                Table::const_iterator from = tab.begin();
+                if (!tr.leaves.empty()) {
+                    uint32_t firstKey;
+                    memcpy(&firstKey, tr.leaves.back().key.data(), 4);
+                    from = tab.lower_bound(firstKey);
+                    freed.push_back(tr.leaves.back().page);
+                    tr.covered -= tr.leafCount.back();
+                    tr.leaves.pop_back();
+                    tr.leafCount.pop_back();
+                    for (Table::const_iterator it = from; it != tab.end() && it->first <= tr.lastKey; ++it)
+                        if (it->second.big) tr.overflowPages -= ovPages(it->second.size);
+                }
+                std::vector<Item> items;
+                for (Table::const_iterator kv = from; kv != tab.end(); ++kv) {
+                    Item it;
+                    it.key.resize(4);
+                    memcpy(it.key.data(), &kv->first, 4);
+                    if (kv->second.big) {
+                        it.flags = F_BIGDATA;
+                        it.dataSize = kv->second.size;
+                        it.data.resize(8);
+                        memcpy(it.data.data(), &kv->second.ovfPage, 8);
+                        tr.overflowPages += ovPages(kv->second.size);
+                    } else {
+                        it.dataSize = kv->second.size;
+                        it.data = kv->second.bytes;
+                    }
+                    items.push_back(std::move(it));
+                }
+                std::vector<uint64_t> leafPages;
+                std::vector<uint32_t> counts;
+                std::vector<Child> fresh = writeLevel(items, true, leafPages, &counts);
+                tr.leaves.insert(tr.leaves.end(), fresh.begin(), fresh.end());
+                tr.leafCount.insert(tr.leafCount.end(), counts.begin(), counts.end());
+                tr.covered = tab.size();
+                tr.lastKey = tab.empty() ? 0 : tab.rbegin()->first;
+                tr.db = buildBranches(tr.leaves, tr.branchPages);
+                tr.db.entries = tab.size();
+                tr.db.flags = MDB_INTEGERKEY;
+                tr.db.overflow_pages = tr.overflowPages;
+            } else if (tr.leaves.empty()) {
+                tr.db = Db();
+                tr.db.flags = MDB_INTEGERKEY;
+            }
             Item m;
             m.key.assign(t.first.begin(), t.first.end());
             m.flags = F_SUBDATA;
             m.dataSize = sizeof(Db);
             m.data.resize(sizeof(Db));
-            memcpy(m.data.data(), &db, sizeof(Db));
+            memcpy(m.data.data(), &tr.db, sizeof(Db));
             mainItems.push_back(std::move(m));
         }
         /* main DB keys compare as byte strings (mdb_cmp_memn) */
@@ -227,12 +285,20 @@ public:
             const int c = memcmp(a.key.data(), b.key.data(), n);
             return c != 0 ? c < 0 : a.key.size() < b.key.size();
         });
-        Db mainDb = buildTree(mainItems, newTreePages);
+        Db mainDb = buildTree(mainItems, newMetaPages);
 
-        /* free DB: earlier records are carried over; this transaction's record lists `freed` */
+        /* free DB: this transaction's record lists `freed`; what is left of the reusable pool goes back under its old id.
+         * The free DB's own pages are fresh ones (their number depends on the records, which depend on the pool). */
+        reuseTreePages_ = false;
         std::sort(freed.begin(), freed.end());
         freed.erase(std::unique(freed.begin(), freed.end()), freed.end());
         if (!freed.empty()) freeRecords_[txn] = freed;
+        if (!reusable_.empty()) {
+            std::vector<uint64_t>& back = freeRecords_[havePool ? poolKey : 0];
+            back.insert(back.end(), reusable_.begin(), reusable_.end());
+            std::sort(back.begin(), back.end());
+            reusable_.clear();
+        }
         std::vector<Item> freeItems;
         uint64_t freeOvf = 0;
         for (const auto& fr : freeRecords_) {
@@ -247,7 +313,7 @@ public:
             if (NODESIZE + 8 + bytes > nodemax()) {
                 const uint64_t pg = writeOverflow((const uint8_t*)idl.data(), bytes);
                 flushPending();
-                for (uint64_t p = 0; p < ovPages(bytes); p++) newTreePages.push_back(pg + p); /* rewritten by the next commit */
+                for (uint64_t p = 0; p < ovPages(bytes); p++) newMetaPages.push_back(pg + p); /* rewritten by the next commit */
                 freeOvf += ovPages(bytes);
                 it.flags = F_BIGDATA;
                 it.data.resize(8);
@@ -257,11 +323,12 @@ public:
             }
             freeItems.push_back(std::move(it));
         }
-        Db freeDb = buildTree(freeItems, newTreePages);
+        Db freeDb = buildTree(freeItems, newMetaPages);
         freeDb.overflow_pages = freeOvf;
         freeDb.pad = (uint32_t)psize_;                             /* mm_psize */
         freeDb.flags = (uint16_t)(MDB_INTEGERKEY | MDB_NOSUBDIR); /* mm_flags: env flags & 0xffff | MDB_INTEGERKEY */
 
+        flushPending();
         if (fsync(fd_) != 0) fail("fsync");
         Meta m = meta_;
         m.dbs[0] = freeDb;
@@ -273,7 +340,7 @@ public:
         writeMeta(m, txn & 1);
         if (fsync(fd_) != 0) fail("fsync");
         meta_ = m;
-        treePages_.swap(newTreePages);
+        metaTreePages_.swap(newMetaPages);
         pendingFree_.clear();
         dirty_ = false;
     }
@@ -319,12 +386,20 @@ private:
     /* write-combining buffer for freshly allocated pages (always a contiguous run ending at nextPg_) */
     void flushPending()
     {
+        for (auto& r : reuseWrites_) pwriteAll(r.second->data(), psize_, r.first * psize_);
+        reuseWrites_.clear();
         if (pendingBuf_.empty()) return;
         pwriteAll(pendingBuf_.data(), pendingBuf_.size(), pendingStart_ * psize_);
         pendingBuf_.clear();
     }
     uint8_t* allocPages(uint64_t n, uint64_t& pgno)
     {
+        if (n == 1 && reuseTreePages_ && !reusable_.empty()) { /* a tree page goes to a page no live snapshot references */
+            pgno = reusable_.back();
+            reusable_.pop_back();
+            reuseWrites_.emplace_back(pgno, std::make_unique<std::vector<uint8_t>>(psize_, (uint8_t)0));
+            return reuseWrites_.back().second->data();
+        }
         if (pendingBuf_.empty()) pendingStart_ = nextPg_;
         pgno = nextPg_;
         nextPg_ += n;
@@ -334,7 +409,7 @@ private:
     }
     void maybeFlush()
     {
-        if (pendingBuf_.size() >= (16u << 20)) flushPending();
+        if (pendingBuf_.size() >= (16u << 20) || reuseWrites_.size() >= 4096) flushPending();
     }
 
     static void putHeader(uint8_t* page, uint64_t pgno, uint16_t flags, uint16_t lower, uint16_t upper)
@@ -388,7 +463,7 @@ private:
         std::vector<uint8_t> key;
         uint64_t page;
     };
-    std::vector<Child> writeLevel(const std::vector<Item>& items, bool leaf, std::vector<uint64_t>& pagesOut)
+    std::vector<Child> writeLevel(const std::vector<Item>& items, bool leaf, std::vector<uint64_t>& pagesOut, std::vector<uint32_t>* countsOut = nullptr)
     {
         /* partition.  Pages are filled the way liblmdb leaves them after inserts in ascending key order (the collectors append): when the
          * next node does not fit, mdb_page_split (newindx >= nkeys: "bias the split so the new page is emptier than the old page") moves the
@@ -451,6 +526,7 @@ private:
             if (lower > upper) throw Error("internal: page overflow");
             putHeader(page, pgno, leaf ? P_LEAF : P_BRANCH, lower, upper);
             pagesOut.push_back(pgno);
+            if (countsOut) countsOut->push_back((uint32_t)(e - b));
             out.push_back(Child{items[b].key, pgno});
             maybeFlush();
         }
@@ -463,6 +539,16 @@ private:
         db.entries = items.size();
         if (items.empty()) return db;
         std::vector<Child> level = writeLevel(items, true, pagesOut);
+        Db up = buildBranches(level, pagesOut);
+        up.entries = items.size();
+        return up;
+    }
+
+    /* the branch levels over a list of leaf pages (first key, page), fresh pages recorded in pagesOut */
+    Db buildBranches(std::vector<Child> level, std::vector<uint64_t>& pagesOut)
+    {
+        Db db;
+        if (level.empty()) return db;
         db.leaf_pages = level.size();
         db.depth = 1;
         while (level.size() > 1) {
@@ -515,7 +601,8 @@ private:
 
     /* depth-first walk of a tree; cb(key, flags, dataSize, node data) for every leaf node */
     void walk(uint64_t root, std::vector<uint64_t>& pages,
-              const std::function<void(const uint8_t*, size_t, uint16_t, uint32_t, const uint8_t*)>& cb, int depth = 0) const
+              const std::function<void(const uint8_t*, size_t, uint16_t, uint32_t, const uint8_t*)>& cb, int depth = 0,
+              const std::function<void(uint64_t, bool, size_t)>* pageCb = nullptr) const
     {
         if (root == P_INVALID) return;
         if (depth > 32) throw Error("tree too deep (corrupt file?)");
@@ -526,6 +613,7 @@ private:
         memcpy(&lower, page.data() + 12, 2);
         pages.push_back(root);
         const size_t n = (lower - PAGEHDRSZ) / 2;
+        if (pageCb) (*pageCb)(root, (flags & P_LEAF) != 0, n);
         for (size_t i = 0; i < n; i++) {
             uint16_t off;
             memcpy(&off, page.data() + PAGEHDRSZ + 2 * i, 2);
@@ -538,7 +626,7 @@ private:
             memcpy(&ks, node + 6, 2);
             if (flags & P_BRANCH) {
                 const uint64_t child = (uint64_t)lo | ((uint64_t)hi << 16) | ((uint64_t)fl << 32);
-                walk(child, pages, cb, depth + 1);
+                walk(child, pages, cb, depth + 1, pageCb);
             } else if (flags & P_LEAF) {
                 const uint32_t dsize = (uint32_t)lo | ((uint32_t)hi << 16);
                 cb(node + NODESIZE, ks, fl, dsize, node + NODESIZE + ks);
@@ -574,7 +662,7 @@ private:
         if (nextPg_ > filePages_) throw Error(path_ + ": last page beyond the end of the file");
 
         std::vector<std::pair<std::string, Db>> subs;
-        walk(meta_.dbs[1].root, treePages_, [&](const uint8_t* k, size_t ks, uint16_t fl, uint32_t ds, const uint8_t* d) {
+        walk(meta_.dbs[1].root, metaTreePages_, [&](const uint8_t* k, size_t ks, uint16_t fl, uint32_t ds, const uint8_t* d) {
             if (!(fl & F_SUBDATA) || ds != sizeof(Db)) throw Error("main DB holds a plain record: not a DeepestScatter dataset");
             Db db;
             memcpy(&db, d, sizeof(Db));
@@ -583,10 +671,24 @@ private:
         for (const auto& s : subs) {
             if (!(s.second.flags & MDB_INTEGERKEY)) throw Error("table " + s.first + " is not MDB_INTEGERKEY");
             Table& t = tables_[s.first];
-            walk(s.second.root, treePages_, [&](const uint8_t* k, size_t ks, uint16_t fl, uint32_t ds, const uint8_t* d) {
+            /* remember where the leaves are: an append-only continuation keeps them (commit()) */
+            TableTree& tr = trees_[s.first];
+            tr.db = s.second;
+            tr.overflowPages = s.second.overflow_pages;
+            std::vector<uint64_t> scratch;
+            const std::function<void(uint64_t, bool, size_t)> onPage = [&](uint64_t pgno, bool leaf, size_t nkeys) {
+                if (leaf) {
+                    tr.leaves.push_back(Child{{}, pgno});
+                    tr.leafCount.push_back((uint32_t)nkeys);
+                } else {
+                    tr.branchPages.push_back(pgno);
+                }
+            };
+            walk(s.second.root, scratch, [&](const uint8_t* k, size_t ks, uint16_t fl, uint32_t ds, const uint8_t* d) {
                 if (ks != 4) throw Error("table " + s.first + ": key is not a 4-byte integer");
                 uint32_t key;
                 memcpy(&key, k, 4);
+                if (!tr.leaves.empty() && tr.leaves.back().key.empty()) tr.leaves.back().key.assign(k, k + 4);
                 Value v;
                 v.size = ds;
                 if (fl & F_BIGDATA) {
@@ -596,9 +698,12 @@ private:
                     v.bytes.assign(d, d + ds);
                 }
                 t[key] = std::move(v);
-            });
+            }, 0, &onPage);
+            tr.covered = t.size();
+            tr.lastKey = t.empty() ? 0 : t.rbegin()->first;
+            tr.valid = true;
         }
-        walk(meta_.dbs[0].root, treePages_, [&](const uint8_t* k, size_t ks, uint16_t fl, uint32_t ds, const uint8_t* d) {
+        walk(meta_.dbs[0].root, metaTreePages_, [&](const uint8_t* k, size_t ks, uint16_t fl, uint32_t ds, const uint8_t* d) {
             if (ks != 8) throw Error("free DB key is not a transaction id");
             uint64_t txn;
             memcpy(&txn, k, 8);
@@ -607,7 +712,7 @@ private:
                 uint64_t pg;
                 memcpy(&pg, d, 8);
                 preadAll(idl.data(), ds, pg * psize_ + PAGEHDRSZ);
-                for (uint64_t p = 0; p < ovPages(ds); p++) treePages_.push_back(pg + p);
+                for (uint64_t p = 0; p < ovPages(ds); p++) metaTreePages_.push_back(pg + p);
             } else {
                 memcpy(idl.data(), d, ds);
             }
@@ -625,7 +730,22 @@ private:
     uint64_t nextPg_ = 2, filePages_ = 0;
     std::map<std::string, Table> tables_;
     std::map<uint64_t, std::vector<uint64_t>> freeRecords_; /* txnid -> pages, ascending */
-    std::vector<uint64_t> treePages_;   /* pages of the trees of the current snapshot */
+    /* where a table's tree lives in the current snapshot */
+    struct TableTree {
+        std::vector<Child> leaves;       /* leaf pages in key order: first key, page */
+        std::vector<uint32_t> leafCount; /* entries per leaf */
+        std::vector<uint64_t> branchPages;
+        uint64_t overflowPages = 0;      /* overflow pages referenced by the covered entries */
+        uint32_t lastKey = 0;            /* largest key the leaves cover */
+        size_t covered = 0;              /* entries the leaves cover */
+        Db db;                           /* MDB_db record of the snapshot */
+        bool valid = false;              /* only appended to since the snapshot: the leaves can stay */
+    };
+    std::map<std::string, TableTree> trees_;
+    std::vector<uint64_t> metaTreePages_; /* pages of the main DB and free DB trees (rewritten by every commit) */
+    std::vector<uint64_t> reusable_;      /* single pages neither the current nor the previous snapshot references */
+    std::vector<std::pair<uint64_t, std::unique_ptr<std::vector<uint8_t>>>> reuseWrites_; /* reused pages waiting for flushPending */
+    bool reuseTreePages_ = false;
     std::vector<uint64_t> pendingFree_; /* overflow pages released since the last commit */
     std::vector<uint8_t> pendingBuf_;
     uint64_t pendingStart_ = 0;

@@ -137,18 +137,21 @@ int cmdCollect(const Args& a)
     const std::string root = a.get("cloud-root", ".");
     const std::string what = a.get("what", "all");
     ExecutionLoop loop;
+    /* One commit per finished batch, like the reference's transaction per batchAppend: a kill, OOM or power cut loses at most
+     * the batch in flight, and `--mode continue` resumes at count / batchSize (Tasks.h:65-68).  LmdbFile commits incrementally
+     * (only the tail of an appended table is rewritten), so this costs megabytes per batch.  SIGINT / SIGTERM finish the
+     * current batch, commit and exit. */
+    std::signal(SIGINT, [](int) { ExecutionLoop::stopFlag() = 1; });
+    std::signal(SIGTERM, [](int) { ExecutionLoop::stopFlag() = 1; });
+    const auto commitBatch = [&] { dataset->commit(); };
     /* the reference runs one collector type per program run, in this order (main.cpp:61, Tasks.cpp:155-178) */
-    if (what == "samples" || what == "all") {
-        loop.run(Tasks::collect<Persistance::ScatterSample>(device, dataset, root, mode, cs));
-        dataset->commit();
-    }
-    if (what == "descriptors" || what == "all") {
-        loop.run(Tasks::collect<Persistance::DisneyDescriptor>(device, dataset, root, mode, cs));
-        dataset->commit();
-    }
-    if (what == "results" || what == "all") {
-        loop.run(Tasks::collect<Persistance::Result>(device, dataset, root, mode, cs));
-        dataset->commit();
+    if (what == "samples" || what == "all") loop.run(Tasks::collect<Persistance::ScatterSample>(device, dataset, root, mode, cs), commitBatch);
+    if (what == "descriptors" || what == "all") loop.run(Tasks::collect<Persistance::DisneyDescriptor>(device, dataset, root, mode, cs), commitBatch);
+    if (what == "results" || what == "all") loop.run(Tasks::collect<Persistance::Result>(device, dataset, root, mode, cs), commitBatch);
+    dataset->commit();
+    if (ExecutionLoop::stopRequested()) {
+        std::cerr << "interrupted: every finished batch is committed; rerun with --mode continue" << std::endl;
+        return 130;
     }
     return 0;
 }
@@ -158,7 +161,7 @@ int cmdMerge(const Args& a)
     if (a.positional.size() < 2) throw std::runtime_error("merge needs an output and at least one shard");
     Dataset out{Dataset::Settings(a.positional[0])};
     for (size_t i = 1; i < a.positional.size(); i++) {
-        Dataset in{Dataset::Settings(a.positional[i])};
+        Dataset in{Dataset::Settings(a.positional[i], /*create=*/false, /*readonly=*/true)}; /* a mistyped shard path is an error */
         out.mergeFrom(in);
     }
     out.commit();

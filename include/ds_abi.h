@@ -89,6 +89,12 @@ typedef struct DsCounters {
     uint64_t steps;        /* ray-march steps of the reference algorithm (CU/cloud.cuh:87-104 iterations) */
     uint64_t density_taps; /* density fetches actually issued (<= steps when empty space is skipped) */
     uint64_t nonfinite;    /* samples that were NaN/Inf (the reference paints an error colour, progressive.cu:36) */
+    /* Part of `paths` / `steps` that NO kernel thread traced: samples of pixels whose primary ray never reaches an occupied
+     * cell (their value is exactly 0; the FAST flavour's primary-ray cache settles them once per camera) and the march steps
+     * the reference would have spent on them.  paths - untraced_paths and steps - untraced_steps are what the path-tracing
+     * kernel itself counted. */
+    uint64_t untraced_paths;
+    uint64_t untraced_steps;
 } DsCounters;
 
 /* RadianceCollector constants (DG/Scene/RadianceCollector.cpp:17,88,112-118) */
@@ -192,6 +198,21 @@ int ds_frame_unconverged(DsContext* ctx, uint32_t subframe_id, uint32_t* unconve
  * pointer, 8*W*H doubles) for `n` subframes; sums over ranks can then be re-imported with the total n. */
 int ds_frame_export_moments_device(DsContext* ctx, uint32_t n, double* moments_device);
 int ds_frame_import_moments_device(DsContext* ctx, uint32_t n_total, const double* moments_device);
+
+/* ---------------------------------------------------------------- multi-GPU accumulation-buffer reduce (NCCL)
+ * The reference is single-GPU.  One context per GPU renders its own subframe ids; the per-GPU accumulation
+ * buffers are combined with ONE ncclReduce (sum, float64) of the mergeable moments over NVLink.  NCCL is loaded at run time
+ * (dlopen "libnccl.so.2"): single-GPU users need no NCCL, and inside a torch process the copy torch already loaded is shared. */
+#define DS_COMM_ID_BYTES 128
+/* ncclGetUniqueId on the calling process (rank 0); ship the bytes to the other ranks by any means */
+int ds_comm_unique_id(uint8_t id_out[DS_COMM_ID_BYTES]);
+/* ncclCommInitRank on the context's device and stream; collective over all ranks */
+int ds_comm_init(DsContext* ctx, int n_ranks, int rank, const uint8_t id[DS_COMM_ID_BYTES]);
+int ds_comm_destroy(DsContext* ctx);
+/* Collective.  The frame of this context holds `n_local` accumulated subframes (0 allowed); after the call the frame of
+ * `root` holds the statistics of all `n_total` = sum n_local subframes (mean and M2 as if one GPU had rendered them all);
+ * root < 0: every rank does (ncclAllReduce).  Runs export -> ncclReduce -> import on the context's stream, no host sync. */
+int ds_frame_reduce(DsContext* ctx, uint32_t n_local, uint32_t n_total, int root);
 
 /* ---------------------------------------------------------------- generic path tracing (tests, tools) */
 

@@ -51,6 +51,10 @@
 #include <cstring>
 #include <vector>
 
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
 #include "../include/ds_detmath.h"
 #include "../include/ds_synth.h"
 
@@ -1217,6 +1221,16 @@ void orc_counters_get(unsigned long long* out /* paths, events, steps */)
     out[0] = gPaths;
     out[1] = gEvents;
     out[2] = gSteps;
+}
+
+/* benchmarks: torch.distributed.run exports OMP_NUM_THREADS=1; the reference arm asks for all host threads explicitly */
+void orc_set_threads(int n)
+{
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
 }
 
 void orc_counters_reset()

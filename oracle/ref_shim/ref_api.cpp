@@ -110,6 +110,7 @@ struct RefScene {
 };
 
 int gNextVolume = 0;
+bool gSkipBake = false; /* ref_set_skip_bake: VDBCloud::disableRendering() before init, the caller supplies the baked volume */
 
 void newContext(RefScene& s)
 {
@@ -143,6 +144,7 @@ void buildScene(RefScene& s, float cloudSizeM, float sampleStep, const float* li
     s.sun = std::make_shared<Sun>(std::make_shared<DirectionalLight>(description.light), s.context);
     s.cloud = std::make_shared<VDBCloud>(std::make_shared<Cloud::Model>(description.cloud.model), s.context, s.resources);
     s.material = std::make_shared<CloudMaterial>(std::make_shared<Cloud::Rendering>(description.cloud.rendering), s.context, s.resources);
+    if (gSkipBake) s.cloud->disableRendering(); /* what the two sample collectors do (ScatterSampleCollector.h:32): no inScatter launch */
     if (pathTracer)
         s.renderer = std::make_shared<PathTracingRenderer>(s.context, s.resources);
     else
@@ -317,6 +319,27 @@ void ref_get_mie(void* h, float* mie, float* chopped, float* integral)
     for (int i = 0; i < 3; i++) {
         const dsref::VariableObj* v = (*s.context)->find(names[i]);
         readBuffer(optix::Buffer(v->sampler->buffer), 0, outs[i]);
+    }
+}
+
+/* Benchmarks only: skip the (single-threaded, minutes at 512^3) inScatter launch of the next ref_scene_init calls and install a
+ * volume baked elsewhere.  tests/test_oracle_vs_ref.py shows the oracle's bake equal to the reference's byte for byte, which is
+ * what makes the oracle's OpenMP bake a legitimate way to PREPARE this input outside any timed region. */
+void ref_set_skip_bake(int on) { gSkipBake = on != 0; }
+
+int ref_inscatter_set(void* h, const uint8_t* in)
+{
+    RefScene& s = *(RefScene*)h;
+    try {
+        RTsize nx, ny, nz;
+        s.cloud->densityBuffer->getSize(nx, ny, nz);
+        s.cloud->inScatterBuffer->setSize(nx, ny, nz);
+        memcpy(s.cloud->inScatterBuffer->map(0), in, nx * ny * nz);
+        s.cloud->inScatterBuffer->unmap(0);
+        return 0;
+    } catch (const std::exception& e) {
+        fprintf(stderr, "ref_inscatter_set: %s\n", e.what());
+        return 1;
     }
 }
 

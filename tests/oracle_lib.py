@@ -92,6 +92,7 @@ def lib() -> C.CDLL:
         L.orc_point_radiance.restype = C.c_int
         L.orc_counters_get.argtypes = [C.POINTER(C.c_ulonglong)]
         L.orc_counters_reset.argtypes = []
+        L.orc_set_threads.argtypes = [C.c_int]
         _lib = L
     return _lib
 

@@ -70,6 +70,8 @@ def lib() -> C.CDLL:
         L.ref_scene_get_derived.argtypes = [C.c_void_p, _f32p]
         L.ref_get_mie.argtypes = [C.c_void_p, _f32p, _f32p, _f32p]
         L.ref_inscatter_get.argtypes = [C.c_void_p, _u8p]
+        L.ref_inscatter_set.argtypes = [C.c_void_p, _u8p]
+        L.ref_set_skip_bake.argtypes = [C.c_int]
         L.ref_trace_paths.argtypes = [C.c_void_p, C.c_int, _f32p, _f32p, _u32p, _u32p, _f32p, C.c_int]
         L.ref_camera_set.argtypes = [C.c_void_p, _f32p, _f32p, _f32p]
         L.ref_camera_get.argtypes = [C.c_void_p, _f32p]
@@ -92,6 +94,10 @@ def lib() -> C.CDLL:
         L.ref_counters_get.argtypes = [C.POINTER(C.c_ulonglong)]
         _lib = L
     return _lib
+
+
+def skip_bake(on: bool):
+    lib().ref_set_skip_bake(int(on))
 
 
 def f32(a) -> np.ndarray:
@@ -185,6 +191,10 @@ class Reference:
         out = np.empty(nx * ny * nz, dtype=np.uint8)
         self.L.ref_inscatter_get(self.h, out)
         return out.reshape(nz, ny, nx)
+
+    def inscatter_set(self, vol: np.ndarray):
+        """Install a sun-transmittance volume baked elsewhere (after scene_init under skip_bake(True)); benchmarks only."""
+        assert self.L.ref_inscatter_set(self.h, np.ascontiguousarray(vol, dtype=np.uint8).reshape(-1)) == 0
 
     # ---- estimator ----
     def trace_paths(self, origins, dirs, seed_val0, stream, procs=1) -> np.ndarray:

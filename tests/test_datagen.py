@@ -1,5 +1,6 @@
 """The C++ headless DataGen driver (deepestscatter_b200/host/datagen.cpp + DataGen.hpp): same class shapes and call
 order as the reference's Tasks / Scene / collectors, every launch a call into the C ABI."""
+import lmdb_compat
 import struct
 import subprocess
 from pathlib import Path
@@ -24,7 +25,7 @@ def test_scenes_merge_stat_are_host_only(built_library, tmp_path):
     run("scenes", db, "--clouds", "a/one.npy,b/two.npy", "--scenes-per-cloud", 3, "--seed", 7)
     out = run("stat", db).stdout
     assert "SceneSetup 6" in out
-    env = ds.lmdb_compat.Environment(str(db), subdir=False, readonly=True, max_dbs=8)
+    env = lmdb_compat.Environment(str(db), subdir=False, readonly=True, max_dbs=8)
     scenes = env.open_db(b"SceneSetup", integerkey=True)
     with env.begin(db=scenes) as t:
         recs = [bytes(v) for _, v in t.cursor(scenes)]
@@ -35,7 +36,7 @@ def test_scenes_merge_stat_are_host_only(built_library, tmp_path):
     with ds.Dataset(other) as w:
         w.append_results(2048, [0.5, 0.25], [1, 1])
     run("merge", db, other)
-    assert "Result 2" in run("stat", db).stdout and ds.lmdb_compat.check(str(db))["pages_leaked"] == 0
+    assert "Result 2" in run("stat", db).stdout and lmdb_compat.check(str(db))["pages_leaked"] == 0
     assert run("collect", check=False).returncode == 1
     assert run("render", "cloud.vdb", check=False).returncode == 1  # no device here, or an unsupported cloud file: loud either way
 
@@ -67,7 +68,7 @@ def test_collect_matches_the_python_binding(built_library, tmp_path):
     run("scenes", db, "--clouds", "cumulus.npy", "--scenes-per-cloud", 2, "--seed", 11)
     run("collect", db, "--what", "all", "--cloud-root", tmp_path, "--batch-size", batch, "--max-threads", 20480, "--launches", 100,
         "--opt", "radiance_scheduler=0")  # the reference update loop: deterministic, comparable bit for bit
-    rep = ds.lmdb_compat.check(str(db))
+    rep = lmdb_compat.check(str(db))
     assert {k: v["entries"] for k, v in rep["tables"].items()} == {"SceneSetup": 2, "ScatterSample": 2 * batch, "DisneyDescriptor": 2 * batch, "Result": 2 * batch,
                                                                    "BakedInterpolationSet": 0}  # the fifth table LmdbDataset.py opens, empty
     # continue mode: nothing left to do, the file does not change
@@ -75,7 +76,7 @@ def test_collect_matches_the_python_binding(built_library, tmp_path):
     run("collect", db, "--what", "all", "--cloud-root", tmp_path, "--batch-size", batch)
     assert db.read_bytes() == before
 
-    env = ds.lmdb_compat.Environment(str(db), subdir=False, readonly=True, max_dbs=8)
+    env = lmdb_compat.Environment(str(db), subdir=False, readonly=True, max_dbs=8)
     tabs = {k: env.open_db(k.encode(), integerkey=True) for k in rep["tables"]}
 
     def get(table, i):

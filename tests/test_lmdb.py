@@ -1,5 +1,5 @@
 """Dataset store: the LMDB data file written by ds_dataset_* (deepestscatter_b200/host/LmdbFile.hpp) read back through an
-independent pure-Python parser with py-lmdb's API (deepestscatter_b200/lmdb_compat.py), the way
+independent pure-Python parser with py-lmdb's API (tests/lmdb_compat.py), the way
 DeepestScatter_Train/LmdbDataset.py:24-66 reads the reference's datasets.  No GPU needed.
 
 Neither liblmdb nor py-lmdb exists here, so byte-level format parity is unpinned against liblmdb; what IS pinned to the real library:
@@ -8,11 +8,14 @@ authors' dataset, reproduced exactly at full size; and to the reference: its own
 decode a file written here.  The rest pins the writer against the restated format, the record bytes against the golden vectors, and
 the structural invariants mdb.c relies on."""
 import json
+import os
 import struct
 from pathlib import Path
 
 import numpy as np
 import pytest
+
+import lmdb_compat
 
 GOLDEN = json.loads((Path(__file__).parent / "golden" / "records.json").read_text())
 BATCH_SIZE = 2048
@@ -22,7 +25,7 @@ class LmdbDatasetMirror:
     """DeepestScatter_Train/LmdbDataset.py, with lmdb -> lmdb_compat and protobuf messages -> raw bytes."""
 
     def __init__(self, ds, path):
-        self.env = ds.lmdb_compat.Environment(str(path), map_size=3e9, subdir=False, max_dbs=64, mode=0, create=False, readonly=True)
+        self.env = lmdb_compat.Environment(str(path), map_size=3e9, subdir=False, max_dbs=64, mode=0, create=False, readonly=True)
         self.dbs = {}
 
     def db(self, name):
@@ -89,7 +92,7 @@ def test_dataset_written_here_reads_like_the_reference_reader(built_library, tmp
             w.commit()  # one transaction per batch, Dataset.h:203-232
         assert w.count("ScatterSample") == n and w.count("SceneSetup") == 3
 
-    report = ds.lmdb_compat.check(str(path))
+    report = lmdb_compat.check(str(path))
     assert report["pages_leaked"] == 0
     assert report["tables"]["DisneyDescriptor"]["overflow_pages"] == n  # 2253-byte values: one overflow page each
     r = LmdbDatasetMirror(ds, path)
@@ -109,7 +112,7 @@ def test_dataset_written_here_reads_like_the_reference_reader(built_library, tmp
     assert r.get("Result", n) is None and r.get("Result", 2**31 - 1) is None
     # LmdbDataset.py:36-40 opens five tables with create=False: the one this library never fills exists, empty; any other name is MDB_NOTFOUND
     assert r.getCountOf("BakedInterpolationSet") == 0 and r.get("BakedInterpolationSet", 0) is None
-    with pytest.raises(ds.lmdb_compat.Error):
+    with pytest.raises(lmdb_compat.Error):
         r.env.open_db(b"LightProbes", integerkey=True)
     # cursor order = key order (LmdbDataset.getCountBeforeLastFlatCloud iterates SceneSetup)
     with r.env.begin() as t:
@@ -149,7 +152,7 @@ def test_meta_page_bytes(built_library, tmp_path):
         assert struct.unpack_from("<Q", page, 40 + 40)[0] == 2**64 - 1  # free root P_INVALID
         assert struct.unpack_from("<Q", page, 88 + 40)[0] == 2**64 - 1  # main root P_INVALID
         assert struct.unpack_from("<QQ", page, 136) == (1, 0)  # last_pg, txnid
-    assert ds.lmdb_compat.check(str(path))["tables"] == {}
+    assert lmdb_compat.check(str(path))["tables"] == {}
     with ds.Dataset(path) as w:
         w.put("Result", 0, b"\x10\x01")
     raw = path.read_bytes()
@@ -164,14 +167,14 @@ def test_continue_mode_appends_and_frees_old_tree_pages(built_library, tmp_path)
     with ds.Dataset(path) as w:
         w.append_scatter_samples(0, pos[:3000], d[:3000])
         w.append_descriptors(0, desc[:100])
-    first = ds.lmdb_compat.check(str(path))
+    first = lmdb_compat.check(str(path))
     assert first["txnid"] == 1 and first["pages_free"] == 0
     with ds.Dataset(path) as w:  # CollectMode::Continue
         assert w.count("ScatterSample") == 3000
         w.append_scatter_samples(3000, pos[3000:], d[3000:])
         w.append_descriptors(100, desc[100:200])
         w.put("DisneyDescriptor", 5, ds.record_disney_descriptor(bytes(desc[4999])))  # replace a big value
-    second = ds.lmdb_compat.check(str(path))
+    second = lmdb_compat.check(str(path))
     assert second["txnid"] == 2 and second["pages_free"] > 0 and second["pages_leaked"] == 0
     assert second["tables"]["ScatterSample"]["entries"] == 5000 and second["tables"]["DisneyDescriptor"]["entries"] == 200
     r = LmdbDatasetMirror(ds, path)
@@ -182,12 +185,12 @@ def test_continue_mode_appends_and_frees_old_tree_pages(built_library, tmp_path)
     with ds.Dataset(path) as w:
         w.drop("DisneyDescriptor")  # mdb_drop(dbi, 0): empty, not deleted
         assert w.count("DisneyDescriptor") == 0
-    third = ds.lmdb_compat.check(str(path))
+    third = lmdb_compat.check(str(path))
     assert third["tables"]["DisneyDescriptor"]["entries"] == 0 and third["pages_leaked"] == 0
     assert third["pages_free"] >= second["pages_free"] + 200
     with ds.Dataset(path) as w:  # a session that writes nothing leaves the file alone
         pass
-    assert ds.lmdb_compat.check(str(path))["txnid"] == third["txnid"]
+    assert lmdb_compat.check(str(path))["txnid"] == third["txnid"]
 
 
 def test_three_level_tree_and_shard_merge(built_library, tmp_path):
@@ -203,7 +206,7 @@ def test_three_level_tree_and_shard_merge(built_library, tmp_path):
     with ds.Dataset(m) as w:
         w.merge(str(b))  # shards may arrive in any order
         w.merge(str(a))
-    rep = ds.lmdb_compat.check(str(m))
+    rep = lmdb_compat.check(str(m))
     assert rep["tables"]["Result"]["entries"] == n and rep["tables"]["Result"]["depth"] == 3
     r = LmdbDatasetMirror(ds, m)
     for i in list(range(0, n, 997)) + [n - 1, n // 2 - 1, n // 2]:
@@ -220,8 +223,8 @@ def test_error_paths(built_library, tmp_path):
     with pytest.raises(ds.DsError) as e:
         ds.Dataset(bad)
     assert "MDB_INVALID" in str(e.value)
-    with pytest.raises(ds.lmdb_compat.Error):
-        ds.lmdb_compat.Environment(str(bad), subdir=False, readonly=True)
+    with pytest.raises(lmdb_compat.Error):
+        lmdb_compat.Environment(str(bad), subdir=False, readonly=True)
     with pytest.raises(ds.DsError):
         ds.Dataset(tmp_path / "no_such_dir" / "x.lmdb")
     with ds.Dataset(tmp_path / "e.lmdb") as w:
@@ -229,8 +232,8 @@ def test_error_paths(built_library, tmp_path):
             w.get("Result", 3)
         assert "MDB_NOTFOUND" in str(e.value)
         assert w.count("Nothing") == 0
-    with pytest.raises(ds.lmdb_compat.Error):
-        ds.lmdb_compat.Environment(str(tmp_path / "e.lmdb"), subdir=False, readonly=False)
+    with pytest.raises(lmdb_compat.Error):
+        lmdb_compat.Environment(str(tmp_path / "e.lmdb"), subdir=False, readonly=False)
 
 
 REF_TRAIN = Path("/root/reference/DeepestScatter_Train")
@@ -255,7 +258,7 @@ def test_the_references_own_reader_opens_and_decodes_the_file(built_library, tmp
     monkeypatch.setenv("PROTOCOL_BUFFERS_PYTHON_IMPLEMENTATION", "python")
     monkeypatch.syspath_prepend(str(REF_TRAIN))
     monkeypatch.syspath_prepend(str(REF_TRAIN / "PythonProtocols"))
-    monkeypatch.setitem(sys.modules, "lmdb", ds.lmdb_compat)
+    monkeypatch.setitem(sys.modules, "lmdb", lmdb_compat)
     sys.modules.pop("LmdbDataset", None)
     try:
         L = importlib.import_module("LmdbDataset")
@@ -302,7 +305,7 @@ def test_the_references_training_dataset_consumes_the_file(built_library, tmp_pa
     monkeypatch.setenv("PROTOCOL_BUFFERS_PYTHON_IMPLEMENTATION", "python")
     for sub in ("", "PythonProtocols", "Common", "Disney"):
         monkeypatch.syspath_prepend(str(REF_TRAIN / sub))
-    monkeypatch.setitem(sys.modules, "lmdb", ds.lmdb_compat)
+    monkeypatch.setitem(sys.modules, "lmdb", lmdb_compat)
     if not hasattr(np, "math"):
         monkeypatch.setattr(np, "math", math, raising=False)  # Common/Vector.py:20 predates numpy 2
     for name in ("LmdbDataset", "BaseDataset", "DisneyDataset", "Vector"):
@@ -343,7 +346,7 @@ def test_page_counts_match_the_statistics_recorded_in_the_references_notebook(bu
         for start in range(0, n, BATCH_SIZE):  # one transaction per batch, as the collectors commit
             w.append_results(start, rad[start:start + BATCH_SIZE], np.ones(BATCH_SIZE, np.uint8))
             w.commit()
-    env = ds.lmdb_compat.Environment(str(path), subdir=False, readonly=True, max_dbs=8)
+    env = lmdb_compat.Environment(str(path), subdir=False, readonly=True, max_dbs=8)
     db = env.open_db(b"Result", integerkey=True)
     with env.begin() as txn:
         stat = txn.stat(db)
@@ -363,3 +366,103 @@ def test_full_size_statistics_of_the_references_dataset(built_library):
     sys.path.insert(0, str(Path(__file__).resolve().parent.parent / "tools"))
     tool = importlib.import_module("lmdb_notebook_stats")
     assert tool.main() == 0
+
+
+def _table_stats(path, names=("ScatterSample", "DisneyDescriptor", "Result")):
+    env = lmdb_compat.Environment(str(path), subdir=False, readonly=True, max_dbs=8)
+    out = {}
+    with env.begin() as txn:
+        for n in names:
+            out[n] = txn.stat(env.open_db(n.encode(), integerkey=True))
+    env.close()
+    return out
+
+
+def test_commit_per_batch_is_incremental_and_equals_the_one_shot_file(built_library, tmp_path):
+    """The collectors commit after every batch of 2048 records (the reference's transaction per batchAppend).  The per-batch file must
+    hold the same trees as a file written in one go (same depth / branch / leaf / overflow page counts, same records), leak no page,
+    and must not grow with the number of commits: the tail of an appended table is rewritten, its completed leaves are not."""
+    ds = built_library
+    rng = np.random.default_rng(3)
+    batches, batch = 24, 2048
+    pos = rng.normal(size=(batches * batch, 3)).astype(np.float32)
+    dirs = rng.normal(size=(batches * batch, 3)).astype(np.float32)
+    desc = rng.integers(0, 256, (batches * batch, 2250), dtype=np.uint8)
+    rad = rng.random(batches * batch).astype(np.float32)
+    one, many = tmp_path / "one.lmdb", tmp_path / "many.lmdb"
+    with ds.Dataset(str(one)) as d:
+        d.append_scatter_samples(0, pos, dirs)
+        d.append_descriptors(0, desc)
+        d.append_results(0, rad, np.ones(len(rad), np.uint8))
+    sizes = []
+    with ds.Dataset(str(many)) as d:
+        for b in range(batches):
+            sl = slice(b * batch, (b + 1) * batch)
+            d.append_scatter_samples(b * batch, pos[sl], dirs[sl])
+            d.commit()
+            sizes.append(many.stat().st_size)
+        for b in range(batches):
+            sl = slice(b * batch, (b + 1) * batch)
+            d.append_descriptors(b * batch, desc[sl])
+            d.commit()
+        for b in range(batches):
+            sl = slice(b * batch, (b + 1) * batch)
+            d.append_results(b * batch, rad[sl], np.ones(batch, np.uint8))
+            d.commit()
+    assert _table_stats(one) == _table_stats(many)
+    rep_one, rep_many = lmdb_compat.check(str(one)), lmdb_compat.check(str(many))
+    assert rep_one["pages_leaked"] == 0 and rep_many["pages_leaked"] == 0
+    assert rep_many["txnid"] >= 3 * batches
+    # 72 commits later the file is at most a few percent larger than the one-shot file (freed tree pages are reused)
+    assert many.stat().st_size < 1.05 * one.stat().st_size + (1 << 20)
+    # the ScatterSample phase: ~25 leaf pages of data per batch; a full rewrite per commit would add the whole table every time
+    growth = np.diff(sizes)
+    assert growth.max() < 3 * (sizes[-1] // batches)
+    env = lmdb_compat.Environment(str(many), subdir=False, readonly=True, max_dbs=8)
+    with env.begin() as txn:
+        dbd = env.open_db(b"DisneyDescriptor", integerkey=True)
+        for k in (0, 2047, 2048, batches * batch - 1):
+            assert txn.get(int(k).to_bytes(4, "little"), db=dbd)[3:] == desc[k].tobytes()
+    env.close()
+    # reopening and appending continues incrementally (Tasks.h:65-68: Continue mode)
+    with ds.Dataset(str(many)) as d:
+        assert d.count("ScatterSample") == batches * batch
+        d.append_scatter_samples(batches * batch, pos[:batch], dirs[:batch])
+    assert lmdb_compat.check(str(many))["pages_leaked"] == 0
+    assert _table_stats(many, ("ScatterSample",))["ScatterSample"]["entries"] == (batches + 1) * batch
+
+
+def test_overwrite_after_commit_rebuilds_the_table(built_library, tmp_path):
+    ds = built_library
+    path = tmp_path / "rw.lmdb"
+    with ds.Dataset(str(path)) as d:
+        for k in range(500):
+            d.put("Result", k, bytes([k % 251, 1, 2]))
+        d.commit()
+        d.put("Result", 7, b"changed")  # not an append
+        d.put("Result", 500, b"tail")
+        d.commit()
+        assert d.get("Result", 7) == b"changed" and d.get("Result", 499) == bytes([499 % 251, 1, 2])
+    rep = lmdb_compat.check(str(path))
+    assert rep["pages_leaked"] == 0 and rep["tables"]["Result"]["entries"] == 501
+    env = lmdb_compat.Environment(str(path), subdir=False, readonly=True, max_dbs=8)
+    with env.begin() as txn:
+        db = env.open_db(b"Result", integerkey=True)
+        assert txn.get((7).to_bytes(4, "little"), db=db) == b"changed"
+        assert txn.get((500).to_bytes(4, "little"), db=db) == b"tail"
+    env.close()
+
+
+def test_merge_source_is_opened_read_only_and_must_exist(built_library, tmp_path):
+    ds = built_library
+    shard = tmp_path / "shard.lmdb"
+    with ds.Dataset(str(shard)) as d:
+        d.put("Result", 3, b"abc")
+    os.chmod(shard, 0o444)  # a read-only shard merges
+    out = tmp_path / "out.lmdb"
+    with ds.Dataset(str(out)) as d:
+        d.merge(str(shard))
+        assert d.get("Result", 3) == b"abc"
+        with pytest.raises(ds.DsError):
+            d.merge(str(tmp_path / "mistyped.lmdb"))
+    assert not (tmp_path / "mistyped.lmdb").exists()  # and is not created as an empty dataset

@@ -2,6 +2,7 @@
 commits and re-opens over several integer-keyed tables must always leave a file that the independent reader (lmdb_compat, the py-lmdb
 API the reference's LmdbDataset.py uses) decodes to exactly the model dictionary, with the structural audit clean (no leaked or
 doubly-used pages, keys sorted, overflow chains of the right length).  Value sizes straddle the leaf / overflow-page boundary."""
+import lmdb_compat
 import numpy as np
 import pytest
 
@@ -57,12 +58,12 @@ def test_any_sequence_of_puts_commits_and_reopens_reads_back(built_library, tmp_
         if w.h:
             w.close()
 
-    report = ds.lmdb_compat.check(str(path))
+    report = lmdb_compat.check(str(path))
     assert report["pages_leaked"] == 0
     used = {t for t, _ in committed}
     for t in used:
         assert report["tables"][t]["entries"] == sum(1 for (tt, _) in committed if tt == t)
-    env = ds.lmdb_compat.Environment(str(path), subdir=False, readonly=True, max_dbs=8)
+    env = lmdb_compat.Environment(str(path), subdir=False, readonly=True, max_dbs=8)
     for t in used:
         db = env.open_db(t.encode(), integerkey=True)
         with env.begin(db=db) as txn:
@@ -77,5 +78,5 @@ def test_any_sequence_of_puts_commits_and_reopens_reads_back(built_library, tmp_
             assert report["tables"][t]["entries"] == 0
             env.open_db(t.encode(), integerkey=True)
         else:
-            with pytest.raises(ds.lmdb_compat.Error):
+            with pytest.raises(lmdb_compat.Error):
                 env.open_db(t.encode(), integerkey=True)

@@ -1,6 +1,7 @@
 """World-size-2 gloo run of the multi-GPU split: two CPU processes each accumulate their own subframe range
 with the oracle, merge with one sum-reduce of the moment buffers, and rank 0 compares against the sequential
 single-process Welford accumulation."""
+import lmdb_compat
 import os
 import socket
 import sys
@@ -140,5 +141,5 @@ def test_two_rank_gloo_scene_queue_and_shard_merge(tmp_path):
         for sid in scenes:
             assert out.get("Result", sid * 8 + 3) == ds.record_result(0.5 + sid, True)
             assert out.get("SceneSetup", sid) == ds.record_scene_setup(f"cloud{sid}.npy", 1000.0 + sid, (0.0, -1.0, 0.0))
-    assert ds.lmdb_compat.check(str(merged))["pages_leaked"] == 0
+    assert lmdb_compat.check(str(merged))["pages_leaked"] == 0
     assert static_scenes(0, 2, scenes) == [0, 2, 4, 9] and static_scenes(1, 2, scenes) == [1, 3, 7]

@@ -24,6 +24,8 @@ import numpy as np
 ROOT = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT))
 
+sys.path.insert(0, str(ROOT / "tests"))
+import lmdb_compat  # noqa: E402  (test-side reader)
 import deepestscatter_b200 as ds  # noqa: E402
 
 BATCH = 2048
@@ -134,7 +136,7 @@ def main():
         c = dict(paths=int(v[5]), events=int(v[6]), steps=int(v[7]))
         t = {k: float(x) / world for k, x in zip(t, v[8:])}
     if rank == 0:
-        rep = ds.lmdb_compat.check(str(shard))
+        rep = lmdb_compat.check(str(shard))
         line = {
             "metric": "samples/s", "value": stats["samples"] / elapsed, "unit": "samples/s", "n_gpus": world,
             "config": {"workload": f"C3: dataset generation, {total} scenes x {a.batch} samples, {a.grid}^3 synthetic cumulus, sizes 1-12 km log-uniform, "

@@ -17,6 +17,8 @@ sys.path.insert(0, str(ROOT))
 
 import numpy as np  # noqa: E402
 
+sys.path.insert(0, str(ROOT / "tests"))
+import lmdb_compat  # noqa: E402  (test-side reader)
 import deepestscatter_b200 as ds  # noqa: E402
 
 WANT = {"ScatterSample": {"psize": 4096, "depth": 4, "branch_pages": 359, "leaf_pages": 103132, "overflow_pages": 0, "entries": 8663040},
@@ -37,7 +39,7 @@ def main():
             w.append_scatter_samples(start, pos, d)
         m = WANT["Result"]["entries"]
         w.append_results(0, rng.uniform(0.5, 3.0, m).astype(np.float32), np.ones(m, np.uint8))
-    env = ds.lmdb_compat.Environment(str(path), subdir=False, readonly=True, max_dbs=8)
+    env = lmdb_compat.Environment(str(path), subdir=False, readonly=True, max_dbs=8)
     ok = True
     with env.begin() as txn:
         for name, want in WANT.items():
