@@ -486,10 +486,12 @@ static LaunchConfig launchConfig(DsContext* ctx)
     cfg.smemCarveout = ctx->opt["smem_carveout"];
     cfg.marchUnroll = ctx->opt["march_unroll"];
     if (cfg.marchUnroll == 0) {
-        /* auto: speculative tap pairs pay while the taps are L2 hits (C2: 268 MB of volumes, 99 % L2 hit rate); once the
-         * volumes dwarf the L2 every wasted tap is a DRAM transaction (C4, 2.1 GB: 449 vs 372 Mpaths/s, profiles/r01z_*) */
+        /* auto: the two-tap pipeline with its second tap fetched only when a collision at the first step is unlikely
+         * (spec_percent, DS_ISSUE_TAPS) wins on both regimes (C2 1100 vs 982 Mpaths/s single-tap; C4 511 vs 503,
+         * profiles/r02g_*).  With the unconditional pair (spec_percent = 0) every wasted tap of a DRAM-resident volume is a DRAM
+         * transaction (C4: 419 vs 503), so that combination falls back to single taps once the volumes dwarf the L2. */
         const size_t volumeBytes = ctx->levels.empty() ? 0 : 2 * (size_t)ctx->lnx[0] * ctx->lny[0] * ctx->lnz[0];
-        cfg.marchUnroll = volumeBytes > 4 * (size_t)ctx->prop.l2CacheSize ? 1 : 2;
+        cfg.marchUnroll = (ctx->opt["spec_percent"] == 0 && volumeBytes > 4 * (size_t)ctx->prop.l2CacheSize) ? 1 : 2;
     }
     return cfg;
 }
@@ -508,6 +510,7 @@ static int runTrace(DsContext* ctx, TraceJob& job)
     job.skipMaxIters = ctx->opt["skip_max_iters"];
     job.skipOpenDist = ctx->opt["skip_open_dist"];
     job.zeroCheckMin = ctx->opt["zero_check_min"];
+    job.specPercent = ctx->opt["spec_percent"];
     DS_CUDA(ctx, cudaMemsetAsync(ctx->queue, 0, sizeof(unsigned long long), ctx->stream));
     const LaunchConfig cfg = launchConfig(ctx);
     const bool prof = ctx->opt["profile_events"] != 0;
@@ -579,7 +582,7 @@ int ds_context_create(int device, DsContext** out)
     }
     ctx->opt["precision"] = DS_PRECISION_FAST;
     ctx->opt["variant"] = 0;
-    ctx->opt["block_threads"] = 896;
+    ctx->opt["block_threads"] = 1024;
     ctx->opt["blocks_per_sm"] = 1;
     ctx->opt["skip_empty"] = 1;
     ctx->opt["march_keep_quarters"] = 2;
@@ -599,6 +602,7 @@ int ds_context_create(int device, DsContext** out)
     ctx->opt["stream_offset"] = 0;
     ctx->opt["profile_events"] = 0;
     ctx->opt["primary_cache"] = 1;
+    ctx->opt["spec_percent"] = 100; /* FAST render, two-tap pipeline: threshold of the speculative second tap (0 = always fetch it) */
     ctx->opt["region_pixels"] = 4096; /* FAST render: hit-list pixels per region of the region-major item order (0 = subframe-major) */
     ctx->opt["descriptor_hw"] = -1;
     ctx->opt["mlp_bf16"] = 0; /* FAST flavour of the model: 0 = tf32 operands (default), 1 = bf16 operands (twice the MMA rate, half the operand bytes) */
@@ -712,6 +716,7 @@ int ds_set_option(DsContext* ctx, const char* name, int value)
     if (n == "skip_open_dist" && value < 1) DS_FAIL(ctx, DS_ERR_INVALID, "skip_open_dist must be >= 1 (0 would leap out of occupied cells)");
     if (n == "staging_subframes" && value < 1) DS_FAIL(ctx, DS_ERR_INVALID, "staging_subframes must be >= 1");
     if (n == "region_pixels" && (value < 0 || value > (1 << 20))) DS_FAIL(ctx, DS_ERR_INVALID, "region_pixels must be 0 .. 2^20");
+    if (n == "spec_percent" && (value < 0 || value > 1000)) DS_FAIL(ctx, DS_ERR_INVALID, "spec_percent must be 0 .. 1000");
     if (n == "march_max_iters" && value < 1) DS_FAIL(ctx, DS_ERR_INVALID, "march_max_iters must be >= 1");
     ctx->opt[n] = value;
     return DS_OK;

@@ -51,6 +51,8 @@ struct TraceJob {
     int skipMaxIters;
     int zeroCheckMin;  /* fast kernel: look at lanes marching through zero density (box exit / open space) when at least this many wait */
     int skipOpenDist;  /* fast kernel: leave the march phase for the empty-space phase when the tap cell is at least this far (cells) from the cloud */
+    int specPercent;   /* fast kernel, two-tap pipeline: skip the speculative second tap when lastDensity * c1 * specPercent / 100 exceeds the optical
+                          depth left to the collision (0 = always fetch both) */
     /* JOB_RENDER: item = (subframe, 8x4 pixel tile, pixel in tile) */
     float eye[3], U[3], V[3], W[3];
     int width, height, tilesX;

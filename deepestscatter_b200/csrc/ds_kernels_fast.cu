@@ -143,6 +143,24 @@ __device__ __forceinline__ float tableLerp(const float* table, float u)
  * what rtTex3D does (cloud.cuh:61) */
 __device__ __forceinline__ float tapVolume(cudaTextureObject_t tex3, V3 q) { return tex3D<float>(tex3, q.x, q.y, q.z); }
 
+/* PIPE: fetch the densities of the next two march steps (base + 1, base + 2) of lane state `s`.  The second tap is speculative -- it
+ * is wasted when the first step already collides -- so it is only issued when a collision at the first step is unlikely: the
+ * optical depth one step adds at the density last seen (the field is trilinear, one step is about one voxel) is compared with what
+ * is left to the collision threshold, both known BEFORE the fetch.  A skipped second tap is marked by pd2 < 0 and fetched by the
+ * march loop if the first step did not collide after all.  Which taps are fetched never changes a path's arithmetic: positions are
+ * functions of the step index alone. */
+#define DS_ISSUE_TAPS(base, lastD)                                                                    \
+    do {                                                                                              \
+        pd1 = tapVolume(sc.densityTex, posAt(s, (base) + 1.0f));                                      \
+        if ((lastD) * specC1 > s.tauStar - s.tau) {                                                   \
+            pd2 = -1.0f;                                                                              \
+            nTaps += 1u;                                                                              \
+        } else {                                                                                      \
+            pd2 = tapVolume(sc.densityTex, posAt(s, (base) + 2.0f));                                  \
+            nTaps += 2u;                                                                              \
+        }                                                                                             \
+    } while (0)
+
 /* start of a free flight (cloudRadianceMaterials.cu:28-35, cloud.cuh:120); the flight origin is s.q0 */
 template <bool CHECK_BOX>
 __device__ __forceinline__ bool beginFlight(const FastConsts& k, FastState& s)
@@ -519,6 +537,8 @@ __global__ void __launch_bounds__(FAST_MAX_THREADS, 1)
      * texture latency of the first march iteration of a round hides behind the rest of the previous round */
     constexpr bool PIPE = !BOXTEST && UNROLL == 2;
     float pd1 = 0.0f, pd2 = 0.0f;
+    /* speculation threshold (DS_ISSUE_TAPS): specPercent = 0 always fetches both taps */
+    const float specC1 = k.c1 * (float)job.specPercent * 0.01f;
     unsigned roundIdx = 0;
     uint32_t wSample = 0, wNext = 0, wQuota = 0; /* ADAPT: the warp's current ticket (uniform across lanes) */
 
@@ -583,11 +603,7 @@ __global__ void __launch_bounds__(FAST_MAX_THREADS, 1)
                     s.out = wSample;
                     st = beginPathFast<MODE>(sc, k, job, sCdfPad, sGuideA, sGuideB, o, d, wSample * 4096u, wNext + rank + 1u, s);
                     nPaths++;
-                    if (PIPE && st == F_MARCH) {
-                        pd1 = tapVolume(sc.densityTex, posAt(s, s.nf + 1.0f));
-                        pd2 = tapVolume(sc.densityTex, posAt(s, s.nf + 2.0f));
-                        nTaps += 2u;
-                    }
+                    if (PIPE && st == F_MARCH) DS_ISSUE_TAPS(s.nf, 0.0f);
                 }
                 wNext += take;
                 wQuota -= take;
@@ -617,11 +633,7 @@ __global__ void __launch_bounds__(FAST_MAX_THREADS, 1)
                         bool valid;
                         st = beginItemFast<MODE>(sc, k, job, sCdfPad, sGuideA, sGuideB, idx, s, valid);
                         if (valid) nPaths++;
-                        if (PIPE && st == F_MARCH) {
-                            pd1 = tapVolume(sc.densityTex, posAt(s, s.nf + 1.0f));
-                            pd2 = tapVolume(sc.densityTex, posAt(s, s.nf + 2.0f));
-                            nTaps += 2u;
-                        }
+                        if (PIPE && st == F_MARCH) DS_ISSUE_TAPS(s.nf, 0.0f);
                     }
                 }
                 mFree = __ballot_sync(FULL, (st & (F_IDLE | F_DONE)) != 0);
@@ -640,11 +652,7 @@ __global__ void __launch_bounds__(FAST_MAX_THREADS, 1)
                 s.nf += kf;
                 /* a walk cut short lands in an empty cell and continues next round; otherwise march on */
                 st = (more && kf >= 1.0f) ? F_SKIP : F_MARCH;
-                if (PIPE && st == F_MARCH) {
-                    pd1 = tapVolume(sc.densityTex, posAt(s, s.nf + 1.0f));
-                    pd2 = tapVolume(sc.densityTex, posAt(s, s.nf + 2.0f));
-                    nTaps += 2u;
-                }
+                if (PIPE && st == F_MARCH) DS_ISSUE_TAPS(s.nf, 0.0f);
             }
             mBusy = __ballot_sync(FULL, (st & (F_MARCH | F_EVENT)) != 0);
         }
@@ -658,17 +666,16 @@ __global__ void __launch_bounds__(FAST_MAX_THREADS, 1)
                     if (st == F_MARCH) {
                         const float n1 = s.nf + 1.0f, n2 = s.nf + 2.0f;
                         const float t1 = fmaf(pd1, k.c1, s.tau);
-                        const float t2 = fmaf(pd2, k.c1, t1); /* pd2 >= 0: t2 >= t1 */
                         const bool hit1 = t1 > s.tauStar;
-                        s.nf = hit1 ? n1 : n2;
-                        s.tau = hit1 ? t1 : t2;
-                        lastDensity = hit1 ? pd1 : pd2;
+                        const bool one = hit1 || pd2 < 0.0f; /* only the first step is consumed: it collided, or the second tap was not fetched */
+                        const float t2 = one ? t1 : fmaf(pd2, k.c1, t1); /* pd2 >= 0: t2 >= t1 */
+                        s.nf = one ? n1 : n2;
+                        s.tau = t2;
+                        lastDensity = one ? pd1 : pd2;
                         if (t2 > s.tauStar) {
                             st = F_EVENT;
                         } else {
-                            pd1 = tapVolume(sc.densityTex, posAt(s, n2 + 1.0f));
-                            pd2 = tapVolume(sc.densityTex, posAt(s, n2 + 2.0f));
-                            nTaps += 2u;
+                            DS_ISSUE_TAPS(s.nf, lastDensity);
                         }
                     }
                 } else {
@@ -745,11 +752,7 @@ __global__ void __launch_bounds__(FAST_MAX_THREADS, 1)
                     const V3 dir = newDirectionFast(sCdfPad, sGuideA, sGuideB, s.seed, s.sv * k.invStepTs);
                     s.sv = dir * k.stepTs;
                     st = beginFlight<false>(k, s) ? F_MARCH : F_DONE; /* q0 is the scatter position just verified in-box */
-                    if (PIPE && st == F_MARCH) {
-                        pd1 = tapVolume(sc.densityTex, posAt(s, 1.0f));
-                        pd2 = tapVolume(sc.densityTex, posAt(s, 2.0f));
-                        nTaps += 2u;
-                    }
+                    if (PIPE && st == F_MARCH) DS_ISSUE_TAPS(0.0f, lastDensity);
                 }
             }
         }

@@ -5,6 +5,9 @@
  *   datagen render <cloud> [--size M] [--width W --height H] [--spp N] [--mode all|multi|single] [--out DIR]
  *                  [--renderer pathtracing|disney --model WEIGHTS.f32]   (the reference's `using TRenderer = ...`, Tasks.cpp:86)
  *       Tasks::renderCloud (Tasks.cpp:108-116): sun "Side", then "Back"; linear image as PFM + tone-mapped PPM
+ *   datagen render <cloud> --gpus N --spp S [--light Side|Back|Front] [--chunk 64] ...
+ *       one frame of S subframes split over N GPUs (one host thread + context each), per-GPU accumulation buffers combined by one
+ *       ncclReduce inside the library (ds_frame_reduce); prints render / reduce seconds of the slowest rank
  *   datagen scenes <db> --clouds a.npy,b.npy,... [--scenes-per-cloud 30] [--seed 566]
  *       DeepestScatter_Train/Utils/GenerateSceneSetups.py: SceneSetup records (size log-uniform 1..12 km, sun uniform on the sphere)
  *   datagen collect <db> --what samples|descriptors|results|all [--cloud-root DIR] [--mode continue|reset]
@@ -18,7 +21,10 @@
 #include <cstring>
 #include <map>
 #include <random>
+#include <algorithm>
+#include <chrono>
 #include <sstream>
+#include <thread>
 
 #include "DataGen.hpp"
 
@@ -72,9 +78,99 @@ std::vector<std::string> split(const std::string& s, char sep)
     return out;
 }
 
+/*
+ * render --gpus N: one host thread and one context per GPU.  Every GPU loads the cloud, bakes its own sun-transmittance volume
+ * (deterministic, so the replicas are identical) and renders a contiguous share of the frame's subframe ids
+ * [offset + 1, offset + count] (option stream_offset keeps the per-(pixel, subframe) RNG streams those of a single-GPU run);
+ * the per-GPU accumulation buffers are then combined by ONE ncclReduce inside the library (ds_frame_reduce) and GPU 0 writes
+ * the EXR.  Prints the wall time of the slowest rank for the render and for the reduce.
+ */
+int cmdRenderMultiGpu(const Args& a, int gpus)
+{
+    const uint32_t total = (uint32_t)a.num("spp", 1024);
+    const uint32_t width = (uint32_t)a.num("width", 512), height = (uint32_t)a.num("height", 256); /* Tasks.cpp:49-50 */
+    const float sizeM = (float)atof(a.get("size", "7000").c_str());
+    const std::string modeName = a.get("mode", "all"), lightName = a.get("light", "Side"), cloudPath = a.positional[0];
+    const Cloud::Rendering::Mode mode = modeName == "single" ? Cloud::Rendering::Mode::SunSingleScatter
+                                        : modeName == "multi" ? Cloud::Rendering::Mode::SunMultipleScatter
+                                                              : Cloud::Rendering::Mode::SunAndSkyAllScatter;
+    const LightDirection light = lightName == "Front" ? LightDirection::Front : lightName == "Back" ? LightDirection::Back : LightDirection::Side;
+    const uint32_t chunk = (uint32_t)a.num("chunk", 64);
+    uint8_t id[DS_COMM_ID_BYTES];
+    if (ds_comm_unique_id(id) != DS_OK) throw std::runtime_error(ds_last_error(nullptr));
+    std::vector<std::string> errors((size_t)gpus);
+    std::vector<double> renderSeconds((size_t)gpus, 0.0), reduceSeconds((size_t)gpus, 0.0);
+    std::vector<std::thread> threads;
+    for (int rank = 0; rank < gpus; rank++)
+        threads.emplace_back([&, rank] {
+            try {
+                auto device = std::make_shared<Device>(rank);
+                for (const std::string& kv : split(a.get("opt", ""), ',')) {
+                    const size_t eq = kv.find('=');
+                    if (eq == std::string::npos) throw std::runtime_error("bad --opt " + kv);
+                    dsCheck(device->ctx, ds_set_option(device->ctx, kv.substr(0, eq).c_str(), atoi(kv.c_str() + eq + 1)));
+                }
+                Persistance::SceneSetup setup;
+                setup.cloud_path = cloudPath;
+                setup.cloud_size_m = sizeM;
+                float d[3];
+                getLightDirection(light, d);
+                setup.light_direction = {d[0], d[1], d[2]};
+                VDBCloud cloud(device, makeSceneDescription(setup, ".", mode, Cloud::Model::Mipmaps::On));
+                cloud.init();
+                dsCheck(device->ctx, ds_frame_create(device->ctx, (int)width, (int)height));
+                dsCheck(device->ctx, ds_comm_init(device->ctx, gpus, rank, id));
+                DsCamera camera;
+                ds_camera_default((int)width, (int)height, &camera);
+                /* contiguous split of the subframe ids 1..total */
+                const uint32_t base = total / (uint32_t)gpus, rem = total % (uint32_t)gpus;
+                const uint32_t count = base + ((uint32_t)rank < rem ? 1u : 0u);
+                const uint32_t offset = (uint32_t)rank * base + std::min((uint32_t)rank, rem);
+                dsCheck(device->ctx, ds_set_option(device->ctx, "stream_offset", (int)offset));
+                dsCheck(device->ctx, ds_set_option(device->ctx, "staging_subframes", (int)std::max(1u, std::min(chunk, count))));
+                dsCheck(device->ctx, ds_sync(device->ctx));
+                const auto t0 = std::chrono::steady_clock::now();
+                for (uint32_t done = 0; done < count;) {
+                    const uint32_t n = std::min(chunk, count - done);
+                    dsCheck(device->ctx, ds_render_subframes(device->ctx, &camera, (DsMode)mode, done + 1, n));
+                    done += n;
+                }
+                dsCheck(device->ctx, ds_sync(device->ctx));
+                const auto t1 = std::chrono::steady_clock::now();
+                dsCheck(device->ctx, ds_frame_reduce(device->ctx, count, total, 0));
+                dsCheck(device->ctx, ds_sync(device->ctx));
+                const auto t2 = std::chrono::steady_clock::now();
+                renderSeconds[(size_t)rank] = std::chrono::duration<double>(t1 - t0).count();
+                reduceSeconds[(size_t)rank] = std::chrono::duration<double>(t2 - t1).count();
+                if (rank == 0) {
+                    std::vector<float> rgba((size_t)width * height * 4);
+                    dsCheck(device->ctx, ds_frame_download(device->ctx, rgba.data(), nullptr));
+                    const std::string out = a.get("out", ".") + "/multigpu." + toString(light) + ".PathTracing.exr";
+                    if (ds_write_exr(out.c_str(), width, height, rgba.data()) != DS_OK) throw std::runtime_error("cannot write " + out);
+                    double mean = 0;
+                    for (size_t i = 0; i < rgba.size(); i += 4) mean += rgba[i];
+                    std::cout << "wrote " << out << " mean radiance " << mean / ((double)width * height) << std::endl;
+                }
+                dsCheck(device->ctx, ds_comm_destroy(device->ctx));
+            } catch (const std::exception& e) {
+                errors[(size_t)rank] = e.what();
+            }
+        });
+    for (std::thread& t : threads) t.join();
+    for (int rank = 0; rank < gpus; rank++)
+        if (!errors[(size_t)rank].empty()) throw std::runtime_error("GPU " + std::to_string(rank) + ": " + errors[(size_t)rank]);
+    const double render = *std::max_element(renderSeconds.begin(), renderSeconds.end());
+    const double reduce = *std::max_element(reduceSeconds.begin(), reduceSeconds.end());
+    std::cout << "{\"gpus\": " << gpus << ", \"width\": " << width << ", \"height\": " << height << ", \"spp\": " << total << ", \"render_s\": " << render
+              << ", \"reduce_s\": " << reduce << ", \"mpaths_s\": " << (double)width * height * total / (render + reduce) / 1e6 << "}" << std::endl;
+    return 0;
+}
+
 int cmdRender(const Args& a)
 {
     if (a.positional.empty()) throw std::runtime_error("render needs a cloud");
+    const int gpus = (int)a.num("gpus", 1);
+    if (gpus > 1) return cmdRenderMultiGpu(a, gpus);
     auto device = std::make_shared<Device>((int)a.num("device", 0));
     Tasks::RenderSettings rs;
     rs.width = (uint32_t)a.num("width", rs.width);

@@ -123,7 +123,7 @@ def test_c4_grid_grazing_sun_fast_flavour_against_the_oracle(built_library):
         o.inscatter_set(ctx.inscatter())
         ctx.set_option("precision", ds.PRECISION_FAST)
         ctx.bake()
-        assert ctx.get_option("march_unroll") == 0  # auto: single taps once the volumes dwarf the L2
+        assert ctx.get_option("march_unroll") == 0 and ctx.get_option("spec_percent") == 100  # the defaults: two-tap pipeline, guarded 2nd tap
         ctx.frame_create(w, h)
         ctx.counters_reset()
         ctx.render_subframes(cam, ds.MODE_ALL_SCATTER, 1, spp)

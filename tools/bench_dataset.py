@@ -44,6 +44,42 @@ def scene_setups(count: int, seed: int = 566):
     return out
 
 
+def cpu_baseline(ctx, a, setup):
+    """the host restatement (oracle port, OpenMP, all cores) on scene 0 x 64 samples: the descriptor gather
+    in full, and a BOUNDED number of RadianceCollector updates (100 launches x 20480 threads each; to the CI rule a sample needs
+    ~5 M experiments, i.e. hours on a CPU).  Grid and sun-transmittance volume are handed over from the GPU context (both bit-exact
+    with the oracle's own, tests/test_gpu_parity.py)."""
+    import oracle_lib as ol
+
+    size, sun = setup
+    cores = len(os.sched_getaffinity(0))
+    ol.lib().orc_set_threads(cores)
+    ctx.set_option("precision", ds.PRECISION_EXACT)
+    ctx.scene_set(size, sun)
+    ctx.bake()
+    o = ol.Oracle()
+    o.volume_upload(ctx.level(0))
+    o.scene_set(size, sun)
+    o.inscatter_set(ctx.inscatter())
+    ctx.set_option("precision", ds.PRECISION_FAST)
+    n = 64
+    t0 = time.perf_counter()
+    pos, dirs = o.generate_points(0, n, 0)
+    t1 = time.perf_counter()
+    reps = 8
+    for _ in range(reps):
+        o.descriptors(pos, dirs)
+    t2 = time.perf_counter()
+    o.counters_reset()
+    tasks, conv, nconv, updates = o.point_radiance(pos, dirs, a.max_threads, a.launches, a.cpu_baseline)
+    t3 = time.perf_counter()
+    c = o.counters()
+    return {"kind": "port", "cores": cores, "sample": f"scene 0 ({size:.0f} m), {n} samples: points + descriptors in full, {updates} RadianceCollector updates "
+                                                      f"of {a.launches} x {a.max_threads} paths (a bounded part of the convergence loop)",
+            "points_per_s": n / (t1 - t0), "descriptors_per_s": n * reps / (t2 - t1), "radiance_mpaths_per_s": c["paths"] / (t3 - t2) / 1e6,
+            "radiance_events_per_s": c["events"] / (t3 - t2), "radiance_seconds": t3 - t2, "converged_in_sample": int(nconv)}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--scenes", type=int, default=4, help="total scenes (all ranks)")
@@ -56,6 +92,8 @@ def main():
     ap.add_argument("--opt", action="append", default=[])
     ap.add_argument("--keep", action="store_true")
     ap.add_argument("--static", action="store_true", help="round-robin scene split instead of the shared scene counter")
+    ap.add_argument("--cpu-baseline", type=int, default=0, metavar="UPDATES",
+                    help="rank 0, one GPU: time the CPU restatement on scene 0 x 64 samples (descriptor gather in full, UPDATES RadianceCollector updates)")
     a = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -147,6 +185,8 @@ def main():
             "steps_per_s": c["steps"] / elapsed, "seconds_per_stage_per_rank": t,
             "shard0": {"pages": rep["pages_total"], "leaked": rep["pages_leaked"], "tables": {k: v["entries"] for k, v in rep["tables"].items()}},
         }
+        if a.cpu_baseline and world == 1:
+            line["cpu_baseline"] = cpu_baseline(ctx, a, setups[0])
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.barrier()
