@@ -486,12 +486,12 @@ static LaunchConfig launchConfig(DsContext* ctx)
     cfg.smemCarveout = ctx->opt["smem_carveout"];
     cfg.marchUnroll = ctx->opt["march_unroll"];
     if (cfg.marchUnroll == 0) {
-        /* auto: the two-tap pipeline with its second tap fetched only when a collision at the first step is unlikely
-         * (spec_percent, DS_ISSUE_TAPS) wins on both regimes (C2 1100 vs 982 Mpaths/s single-tap; C4 511 vs 503,
-         * profiles/r02g_*).  With the unconditional pair (spec_percent = 0) every wasted tap of a DRAM-resident volume is a DRAM
-         * transaction (C4: 419 vs 503), so that combination falls back to single taps once the volumes dwarf the L2. */
+        /* auto: the two-tap pipeline (second tap guarded by spec_percent, DS_ISSUE_TAPS) pays while the taps are L2 hits (C2:
+         * 268 MB of volumes, 99.7 % L2 hit rate: 1177 vs ~1000 Mpaths/s single-tap); once the volumes dwarf the L2 every wasted
+         * tap is a DRAM transaction and a march step is two voxels long, so pairs share no sectors (C4, 2.1 GB: 629 single-tap vs
+         * 595 guarded pairs vs 419 unconditional pairs, profiles/r02c_*, r02j_*, r02g_*) */
         const size_t volumeBytes = ctx->levels.empty() ? 0 : 2 * (size_t)ctx->lnx[0] * ctx->lny[0] * ctx->lnz[0];
-        cfg.marchUnroll = (ctx->opt["spec_percent"] == 0 && volumeBytes > 4 * (size_t)ctx->prop.l2CacheSize) ? 1 : 2;
+        cfg.marchUnroll = volumeBytes > 4 * (size_t)ctx->prop.l2CacheSize ? 1 : 2;
     }
     return cfg;
 }
@@ -1306,6 +1306,13 @@ int ds_comm_init(DsContext* ctx, int n_ranks, int rank, const uint8_t id[DS_COMM
     DS_NCCL(ctx, api.CommInitRank(&ctx->comm, n_ranks, uid, rank));
     ctx->commRanks = n_ranks;
     ctx->commRank = rank;
+    /* NCCL sets its channels up lazily inside the first collective (hundreds of milliseconds); pay that here with one 8-byte
+     * all-reduce so that the first ds_frame_reduce of a render costs what every later one costs */
+    int rc = ensureScratch(ctx, 7, 64);
+    if (rc) return rc;
+    DS_CUDA(ctx, cudaMemsetAsync(ctx->scratch[7], 0, 64, ctx->stream));
+    DS_NCCL(ctx, api.AllReduce(ctx->scratch[7], ctx->scratch[7], 1, NCCL_FLOAT64, NCCL_SUM, ctx->comm, ctx->stream));
+    DS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return DS_OK;
 }
 
@@ -1915,6 +1922,7 @@ int ds_point_radiance_run(DsContext* ctx, const float* positions, const float* d
         ad.zeroMin = cfg.zero_radiance_min_experiments;
         ad.relCI = cfg.relative_ci;
         ad.absCI = cfg.absolute_ci;
+        ad.m2Scale = cfg.launches_per_update > 1 ? (float)(cfg.launches_per_update - 1) / (float)cfg.launches_per_update : 1.0f;
         rc = runTrace(ctx, job);
         if (rc) return rc;
         std::vector<uint8_t> host(stateBytes);
@@ -1930,7 +1938,7 @@ int ds_point_radiance_run(DsContext* ctx, const float* positions, const float* d
             const double mean = N > 0 ? hSum[i] / N : 0.0;
             t.experiment_count = (uint32_t)std::min<unsigned long long>(hCount[i], 0xffffffffull);
             t.radiance = (float)mean;
-            t.running_variance = (float)std::max(hSq[i] - N * mean * mean, 0.0);
+            t.running_variance = (float)(std::max(hSq[i] - N * mean * mean, 0.0) * (double)ad.m2Scale);
             tasks_out[i] = t;
             converged_out[i] = hFlag[i] == 1u ? 1 : 0;
         }

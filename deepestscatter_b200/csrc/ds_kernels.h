@@ -31,6 +31,11 @@ struct AdaptiveCollector {
     uint32_t maxExperiments;   /* 0 = unlimited */
     uint32_t zeroMin;          /* zero-radiance samples need more than this many experiments */
     float relCI, absCI;
+    /* The reference's runningVariance is the SUM of per-thread Welford M2's: each thread accumulates launches_per_update = L
+     * experiments per update and the merge drops the between-thread term (PointRadianceTask.h:54-68), so its expectation is
+     * (L - 1) / L of the true total M2.  The collector keeps the exact total and scales it by that factor wherever the
+     * reference's statistic is meant (the convergence rule, the reported running_variance). */
+    float m2Scale;
 };
 
 /* index of the 64-bit work counters on the device */

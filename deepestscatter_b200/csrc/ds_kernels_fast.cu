@@ -432,7 +432,7 @@ __device__ __forceinline__ void adaptiveCommit(const AdaptiveCollector& ad, uint
      * often stops earlier on an under-estimated variance */
     if ((c0 + c) / ad.minExperiments == c0 / ad.minExperiments) return;
     const double mean = (s0 + dx) / N;
-    const double m2 = fmax((q0 + dxx) - N * mean * mean, 0.0);
+    const double m2 = fmax((q0 + dxx) - N * mean * mean, 0.0) * (double)ad.m2Scale;
     const float Nf = (float)N;
     const float sigma = sqrtf((float)m2 / Nf);
     const float absoluteCI = 1.96f * sigma / sqrtf(Nf);

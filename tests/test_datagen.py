@@ -162,3 +162,37 @@ def test_render_task_with_the_neural_renderer(built_library, tmp_path):
         mean = mean + (f - mean) * np.float32(1.0 / k)
     assert np.abs(mean - p).max() <= 1e-6 * max(1.0, float(np.abs(p).max()))
     assert run("render", "synth:48", "--renderer", "disney", check=False).returncode == 1  # no --model
+
+
+@pytest.mark.gpu
+def test_collect_commits_every_batch_and_survives_an_interrupt(built_library, tmp_path):
+    """One LMDB commit per finished batch (the reference's transaction per batchAppend): SIGINT ends the run between batches with
+    exit code 130 and a consistent file holding every finished batch; --mode continue then completes the dataset."""
+    import signal
+    import time
+
+    batch, scenes = 64, 6
+    db = tmp_path / "Train.lmdb"
+    run("scenes", db, "--clouds", "synth:64", "--scenes-per-cloud", scenes, "--seed", 3)
+    args = [str(DATAGEN), "collect", str(db), "--what", "results", "--batch-size", str(batch), "--opt", "radiance_scheduler=1"]
+    run("collect", db, "--what", "samples", "--batch-size", batch)
+    assert lmdb_compat.check(str(db))["txnid"] >= scenes  # one commit per batch, not one per phase
+    p = subprocess.Popen(args, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    deadline = time.time() + 120
+    while time.time() < deadline and p.poll() is None:  # wait until at least one Result batch is durable, then interrupt
+        try:
+            if lmdb_compat.check(str(db))["tables"].get("Result", {}).get("entries", 0) >= batch:
+                break
+        except Exception:  # the writer may be in the middle of a commit
+            pass
+        time.sleep(0.05)
+    p.send_signal(signal.SIGINT)
+    out, err = p.communicate(timeout=300)
+    rep = lmdb_compat.check(str(db))
+    done = rep["tables"]["Result"]["entries"]
+    assert rep["pages_leaked"] == 0 and done % batch == 0 and done >= batch
+    if done < scenes * batch:  # the signal arrived before the last batch finished
+        assert p.returncode == 130 and "continue" in err
+    run("collect", db, "--what", "results", "--batch-size", batch, "--mode", "continue")
+    rep = lmdb_compat.check(str(db))
+    assert rep["tables"]["Result"]["entries"] == scenes * batch and rep["pages_leaked"] == 0
