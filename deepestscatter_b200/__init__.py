@@ -19,6 +19,7 @@ from .context import (
     camera_array,
     camera_look_at,
     cloud_crop_active,
+    cloud_read_vdb,
     comm_unique_id,
     record_disney_descriptor,
     record_result,
@@ -29,5 +30,5 @@ from .context import (
 __all__ = [
     "LIB_PATH", "build_library", "load", "Context", "DsError", "camera_look_at", "camera_array", "comm_unique_id",
     "MODE_ALL_SCATTER", "MODE_MULTIPLE_SCATTER", "MODE_SINGLE_SCATTER", "PRECISION_EXACT", "PRECISION_FAST", "TASK_DTYPE",
-    "record_scatter_sample", "record_disney_descriptor", "record_result", "record_scene_setup", "Dataset", "cloud_crop_active", "INFO_DTYPE", "blit_predicted",
+    "record_scatter_sample", "record_disney_descriptor", "record_result", "record_scene_setup", "Dataset", "cloud_crop_active", "cloud_read_vdb", "INFO_DTYPE", "blit_predicted",
 ]

@@ -136,6 +136,7 @@ SIGNATURES = {
     "ds_cloud_forget": (None, [_vp]),
     "ds_cloud_last_error": (C.c_char_p, []),
     "ds_cloud_crop_active": (_i, [_vp, _i, _i, _i, _vp, _sz, C.POINTER(_i), C.POINTER(C.c_double)]),
+    "ds_cloud_read_vdb": (_i, [C.c_char_p, _vp, _sz, C.POINTER(_i), C.POINTER(C.c_double)]),
     "ds_write_exr": (_i, [C.c_char_p, _u32, _u32, _vp]),
     "ds_dataset_open": (_i, [C.c_char_p, C.POINTER(_vp)]),
     "ds_dataset_close": (_i, [_vp]),

@@ -379,6 +379,21 @@ class Context:
         return tasks, conv.astype(bool), int(conv.sum()), upd.value
 
 
+def cloud_read_vdb(path: str):
+    """The .vdb front end alone (host only): (dense float32 grid [nz][ny][nx] over the active box + 1, maximum active value)."""
+    lib = _lib.load()
+    dims = (C.c_int * 3)()
+    mx = C.c_double()
+    rc = lib.ds_cloud_read_vdb(str(path).encode(), None, 0, dims, C.byref(mx))
+    if rc != 0:
+        raise DsError(rc, (lib.ds_cloud_last_error() or b"").decode())
+    out = np.empty((dims[2], dims[1], dims[0]), dtype=np.float32)
+    rc = lib.ds_cloud_read_vdb(str(path).encode(), _ptr(out), out.size, dims, C.byref(mx))
+    if rc != 0:
+        raise DsError(rc, (lib.ds_cloud_last_error() or b"").decode())
+    return out, mx.value
+
+
 def cloud_crop_active(dense: np.ndarray):
     """Active bounding box expanded by one voxel (Resources.cpp:97-101) of a dense (nz, ny, nx) float grid; host only."""
     lib = _lib.load()

@@ -75,6 +75,25 @@ int ds_cloud_crop_active(const float* dense, int nx, int ny, int nz, float* out,
     }
 }
 
+int ds_cloud_read_vdb(const char* path, float* out, size_t out_capacity, int dims_out[3], double* max_density_out)
+{
+    if (!path || !dims_out) return DS_ERR_INVALID;
+    try {
+        std::vector<float> dense;
+        double mx = 0.0;
+        dsvdb::toDense(dsvdb::readFirstFloatGrid(dsvdb::readFile(path)), dense, dims_out, mx);
+        if (max_density_out) *max_density_out = mx;
+        if (out) {
+            if (out_capacity < dense.size()) return DS_ERR_INVALID;
+            memcpy(out, dense.data(), dense.size() * sizeof(float));
+        }
+        return DS_OK;
+    } catch (const std::exception& e) {
+        g_error = e.what();
+        return DS_ERR_IO;
+    }
+}
+
 int ds_write_exr(const char* path, uint32_t width, uint32_t height, const float* rgba)
 {
     if (!path || !rgba) return DS_ERR_INVALID;

@@ -3,9 +3,11 @@
  *
  * The reference reads a Houdini-exported OpenVDB FloatGrid (Resources::loadVolumeBuffer, DG/Util/Resources.cpp:68-155):
  * maximum over the active voxels, active-voxel bounding box expanded by one voxel, dense u8 = uint8(v / max * 255) over
- * that box, then the box-filter mip chain.  OpenVDB does not exist in this environment and the repository holds no
- * .vdb file to pin a hand-written parser against, so the front end accepts the same dense data in two open forms:
+ * that box, then the box-filter mip chain.  OpenVDB does not exist in this environment; the front end accepts:
  *
+ *   <file>.vdb                      an OpenVDB file whose first grid is a FloatGrid, read by host/VdbReader.hpp (the container format
+ *                                   restated from the OpenVDB sources; unpinned against the library itself, see there): active =
+ *                                   the grid's value masks and active tiles, exactly what the reference iterates
  *   <file>.npy                      NumPy array, C order, shape (nz, ny, nx), dtype float32 / float64 / uint8 -- e.g. the
  *                                   output of `pyopenvdb`'s copyToArray, or of Houdini's volume export
  *   synth:<n>[:<kind>[:<seed>]]     the procedural grids of include/ds_synth.h, generated on the device
@@ -29,6 +31,7 @@
 #include <vector>
 
 #include "../../include/ds_abi.h"
+#include "VdbReader.hpp"
 
 namespace DeepestScatter {
 
@@ -186,9 +189,21 @@ public:
             cachedSize[0] = g.nx;
             cachedSize[1] = g.ny;
             cachedSize[2] = g.nz;
+        } else if (path.size() > 4 && path.compare(path.size() - 4, 4, ".vdb") == 0) {
+            /* Resources.cpp:80-141: first grid as FloatGrid, maximum over the active values, active box + 1, accessor values */
+            DenseGrid g;
+            int dims[3];
+            dsvdb::toDense(dsvdb::readFirstFloatGrid(dsvdb::readFile(path)), g.f32, dims, g.maxDensity);
+            g.nx = dims[0];
+            g.ny = dims[1];
+            g.nz = dims[2];
+            if (!(g.maxDensity > 0.0)) throw std::runtime_error("cloud grid has no positive active value: " + path);
+            check(ds_volume_upload_float(ctx, g.f32.data(), g.nx, g.ny, g.nz, g.maxDensity, createMipmaps ? 1 : 0));
+            cachedSize[0] = g.nx;
+            cachedSize[1] = g.ny;
+            cachedSize[2] = g.nz;
         } else {
-            throw std::runtime_error("unsupported cloud file " + path +
-                                     ": OpenVDB is not available here; export the grid as a dense .npy (nz, ny, nx) array or use synth:<n>");
+            throw std::runtime_error("unsupported cloud file " + path + ": .vdb (OpenVDB FloatGrid), dense .npy (nz, ny, nx) or synth:<n>");
         }
         cachedPath = path;
         cachedMips = createMipmaps;

@@ -325,6 +325,10 @@ const char* ds_cloud_last_error(void);
 /* the crop step alone, on the host: active bounding box + one voxel of zero padding.  dims_out = cropped size; when `out`
  * is not NULL it receives the cropped grid (out_capacity in floats). */
 int ds_cloud_crop_active(const float* dense, int nx, int ny, int nz, float* out, size_t out_capacity, int dims_out[3], double* max_density_out);
+/* The .vdb front end alone, on the host (Resources.cpp:80-141 up to the quantisation): first grid of an OpenVDB file as a FloatGrid
+ * (host/VdbReader.hpp), maximum over its active values, active bounding box expanded by one voxel, accessor value of every voxel of
+ * that box.  Same calling convention as ds_cloud_crop_active: dims_out always, `out` ([nz][ny][nx] floats) when not NULL. */
+int ds_cloud_read_vdb(const char* path, float* out, size_t out_capacity, int dims_out[3], double* max_density_out);
 
 /* Camera::saveToDisk (DG/Scene/Cameras/Camera.cpp:149-175), host only: the float4 [height][width] progressive buffer as a
  * single-part scanline OpenEXR file with FLOAT channels R, G, B, lineOrder DECREASING_Y, scanline y = buffer row y

@@ -71,5 +71,8 @@ def test_cloud_load_npy_matches_the_reference_quantisation(built_library, tmp_pa
         with pytest.raises(ds.DsError):
             ctx.cloud_load(str(tmp_path / "missing.npy"))
         with pytest.raises(ds.DsError) as e:
-            ctx.cloud_load("cloud.vdb")
-        assert "OpenVDB" in str(e.value)
+            ctx.cloud_load("cloud.vdb")  # a .vdb path goes to host/VdbReader.hpp (tests/test_vdb_reader.py); this one does not exist
+        assert "cannot open" in str(e.value)
+        with pytest.raises(ds.DsError) as e:
+            ctx.cloud_load("cloud.xyz")
+        assert "unsupported cloud file" in str(e.value)
