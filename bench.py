@@ -487,7 +487,7 @@ def run_ours(a):
                               f"{px * 64} B) per step inside ds_frame_reduce") if distributed else "single GPU",
                 "options": {k: ctx.get_option(k) for k in ("variant", "block_threads", "blocks_per_sm", "skip_empty", "primary_cache", "region_pixels",
                                                             "regen_min", "skip_min", "skip_max_iters", "march_keep32", "march_max_iters",
-                                                            "march_unroll", "staging_subframes")}},
+                                                            "march_unroll", "spec_percent", "fused_volume", "staging_subframes")}},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": METRIC, "h2d_bytes_per_step": world * 2 * px * 16, "d2h_bytes_per_step": 2 * px * 16,
                 "api": ("ds_render_subframes_host (progressive + variance float4 buffers in pinned host memory)" if not distributed else

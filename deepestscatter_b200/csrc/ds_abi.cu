@@ -40,6 +40,9 @@ struct DsContext {
     bool baked = false;
     cudaArray_t densityArr = nullptr, inscatterArr = nullptr;
     cudaTextureObject_t densityTex = 0, inscatterTex = 0;
+    cudaArray_t fusedArr = nullptr; /* RG8 {density, sun transmittance}: what k_trace_fast reads when option fused_volume is on */
+    cudaTextureObject_t fusedTex = 0;
+    bool fusedValid = false;
     cudaMipmappedArray_t densityMip = nullptr; /* the whole mip chain as one mip-mapped array (FAST descriptor gather of the neural renderer) */
     cudaTextureObject_t densityMipTex = 0;
     uint32_t* occ = nullptr;
@@ -198,9 +201,13 @@ static void freeVolume(DsContext* ctx)
     ctx->densityMipTex = 0;
     if (ctx->densityMip) cudaFreeMipmappedArray(ctx->densityMip);
     ctx->densityMip = nullptr;
+    if (ctx->fusedTex) cudaDestroyTextureObject(ctx->fusedTex);
+    ctx->fusedTex = 0;
+    ctx->fusedValid = false;
     if (ctx->densityArr) cudaFreeArray(ctx->densityArr);
     if (ctx->inscatterArr) cudaFreeArray(ctx->inscatterArr);
-    ctx->densityArr = ctx->inscatterArr = nullptr;
+    if (ctx->fusedArr) cudaFreeArray(ctx->fusedArr);
+    ctx->densityArr = ctx->inscatterArr = ctx->fusedArr = nullptr;
     if (ctx->occ) cudaFree(ctx->occ);
     ctx->occ = nullptr;
     if (ctx->cellDist) cudaFree(ctx->cellDist);
@@ -279,6 +286,38 @@ static int makeTexture(DsContext* ctx, const uint8_t* linear, int nx, int ny, in
     return DS_OK;
 }
 
+/* The volume k_trace_fast marches through when option fused_volume is on: one block-linear RG8 array whose texel is {density, sun
+ * transmittance}, filled on the device from the two u8 volumes (surface writes) after every bake.  Same sampler as makeTexture. */
+static int ensureFusedTexture(DsContext* ctx)
+{
+    if (ctx->fusedValid) return DS_OK;
+    const int nx = ctx->lnx[0], ny = ctx->lny[0], nz = ctx->lnz[0];
+    if (!ctx->fusedArr) {
+        cudaChannelFormatDesc cd = cudaCreateChannelDesc<uchar2>();
+        DS_CUDA(ctx, cudaMalloc3DArray(&ctx->fusedArr, &cd, make_cudaExtent(nx, ny, nz), cudaArraySurfaceLoadStore));
+    }
+    cudaResourceDesc rd = {};
+    rd.resType = cudaResourceTypeArray;
+    rd.res.array.array = ctx->fusedArr;
+    cudaSurfaceObject_t surf = 0;
+    DS_CUDA(ctx, cudaCreateSurfaceObject(&surf, &rd));
+    cudaError_t e = launchInterleave(ctx->levels[0], ctx->inscatter, nx, ny, nz, surf, ctx->stream);
+    ctx->launches++;
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaDestroySurfaceObject(surf);
+    DS_CUDA(ctx, e);
+    if (!ctx->fusedTex) {
+        cudaTextureDesc td = {};
+        td.addressMode[0] = td.addressMode[1] = td.addressMode[2] = cudaAddressModeClamp;
+        td.filterMode = cudaFilterModeLinear;
+        td.readMode = cudaReadModeNormalizedFloat;
+        td.normalizedCoords = 1;
+        DS_CUDA(ctx, cudaCreateTextureObject(&ctx->fusedTex, &rd, &td, nullptr));
+    }
+    ctx->fusedValid = true;
+    return DS_OK;
+}
+
 /* rtTex3DLod's texture (DisneyDescriptor.cuh:38-42; sampler of VDBCloud.cpp:119-137 with the mip chain of Resources.cpp:169-209): the u8 levels
  * this library built, copied into one mip-mapped array; trilinear within a level, linear between levels, clamp, normalised.  Built on first
  * use, dropped with the volume. */
@@ -342,6 +381,7 @@ static void fillDevScene(DsContext* ctx, DevScene& sc)
     sc.inscatter = ctx->inscatter;
     sc.densityTex = ctx->densityTex;
     sc.inscatterTex = ctx->inscatterTex;
+    sc.fusedTex = 0; /* runTrace sets it */
     if (!ctx->levels.empty()) {
         sc.nx = ctx->lnx[0];
         sc.ny = ctx->lny[0];
@@ -513,6 +553,11 @@ static int runTrace(DsContext* ctx, TraceJob& job)
     job.specPercent = ctx->opt["spec_percent"];
     DS_CUDA(ctx, cudaMemsetAsync(ctx->queue, 0, sizeof(unsigned long long), ctx->stream));
     const LaunchConfig cfg = launchConfig(ctx);
+    if (ctx->opt["precision"] == DS_PRECISION_FAST && cfg.variant == 0 && ctx->opt["fused_volume"] != 0 && ctx->baked) {
+        const int rc = ensureFusedTexture(ctx);
+        if (rc) return rc;
+        sc.fusedTex = ctx->fusedTex;
+    }
     const bool prof = ctx->opt["profile_events"] != 0;
     if (prof) {
         while (ctx->traceEvents.size() < ctx->traceEventsUsed + 2) {
@@ -603,6 +648,7 @@ int ds_context_create(int device, DsContext** out)
     ctx->opt["profile_events"] = 0;
     ctx->opt["primary_cache"] = 1;
     ctx->opt["spec_percent"] = 100; /* FAST render, two-tap pipeline: threshold of the speculative second tap (0 = always fetch it) */
+    ctx->opt["fused_volume"] = 1; /* FAST estimator: march through one RG8 {density, sun transmittance} array instead of two R8 arrays */
     ctx->opt["region_pixels"] = 4096; /* FAST render: hit-list pixels per region of the region-major item order (0 = subframe-major) */
     ctx->opt["descriptor_hw"] = -1;
     ctx->opt["mlp_bf16"] = 0; /* FAST flavour of the model: 0 = tf32 operands (default), 1 = bf16 operands (twice the MMA rate, half the operand bytes) */
@@ -911,6 +957,7 @@ int ds_bake_sun_transmittance(DsContext* ctx)
     timer.stop();
     rc = makeTexture(ctx, ctx->inscatter, ctx->lnx[0], ctx->lny[0], ctx->lnz[0], &ctx->inscatterArr, &ctx->inscatterTex);
     if (rc) return rc;
+    ctx->fusedValid = false;
     ctx->baked = true;
     return DS_OK;
 }
@@ -931,6 +978,7 @@ int ds_inscatter_upload(DsContext* ctx, const uint8_t* in)
     DS_CUDA(ctx, cudaMemcpyAsync(ctx->inscatter, in, (size_t)ctx->lnx[0] * ctx->lny[0] * ctx->lnz[0], cudaMemcpyHostToDevice, ctx->stream));
     int rc = makeTexture(ctx, ctx->inscatter, ctx->lnx[0], ctx->lny[0], ctx->lnz[0], &ctx->inscatterArr, &ctx->inscatterTex);
     if (rc) return rc;
+    ctx->fusedValid = false;
     ctx->baked = true;
     return DS_OK;
 }

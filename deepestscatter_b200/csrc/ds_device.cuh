@@ -78,6 +78,7 @@ struct DevScene {
     const uint8_t* inscatter;
     cudaTextureObject_t densityTex;   /* FAST only */
     cudaTextureObject_t inscatterTex; /* FAST only */
+    cudaTextureObject_t fusedTex;     /* k_trace_fast only: RG8 texels {density, sun transmittance}; 0 = use the two R8 arrays */
     int nx, ny, nz;
     /* DG/Scene/VDBCloud.cpp:99-110 */
     V3 bbox;

@@ -165,6 +165,8 @@ cudaError_t launchDescriptors(const DevScene& sc, const LevelTable& lv, const De
                               uint32_t n, uint8_t* outU8, float* outF32, int32_t* tapIndex, cudaStream_t st, int layerStride = 225,
                               const float* angle = nullptr, const uint8_t* active = nullptr, const uint32_t* gather = nullptr,
                               cudaTextureObject_t mipTex = 0);
+/* RG8 array of {a, b} texels from two u8 volumes of the same shape (the fused volume of k_trace_fast) */
+cudaError_t launchInterleave(const uint8_t* a, const uint8_t* b, int nx, int ny, int nz, cudaSurfaceObject_t surf, cudaStream_t st);
 cudaError_t launchTaskWelford(DsPointRadianceTask* tasks, const float* x, uint32_t nThreads, uint32_t launches, cudaStream_t st);
 
 } // namespace dsk

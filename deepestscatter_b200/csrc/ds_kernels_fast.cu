@@ -143,6 +143,23 @@ __device__ __forceinline__ float tableLerp(const float* table, float u)
  * what rtTex3D does (cloud.cuh:61) */
 __device__ __forceinline__ float tapVolume(cudaTextureObject_t tex3, V3 q) { return tex3D<float>(tex3, q.x, q.y, q.z); }
 
+/* FUSED: density and sun transmittance interleaved in ONE block-linear RG8 array (texel = {density, transmittance}; DevScene::fusedTex).
+ * The filter weights depend on the coordinate alone, so each channel filters to exactly the value the separate R8 array gives; what
+ * changes is where the bytes live: the sun tap of an event (at the collision point, within one step of the march tap that collided)
+ * reads the sectors that march tap has just brought in, instead of four cold sectors of a second volume. */
+template <bool FUSED>
+__device__ __forceinline__ float tapDensity(const DevScene& sc, V3 q)
+{
+    if (FUSED) return tex3D<float2>(sc.fusedTex, q.x, q.y, q.z).x;
+    return tex3D<float>(sc.densityTex, q.x, q.y, q.z);
+}
+template <bool FUSED>
+__device__ __forceinline__ float tapSun(const DevScene& sc, V3 q)
+{
+    if (FUSED) return tex3D<float2>(sc.fusedTex, q.x, q.y, q.z).y;
+    return tex3D<float>(sc.inscatterTex, q.x, q.y, q.z);
+}
+
 /* PIPE: fetch the densities of the next two march steps (base + 1, base + 2) of lane state `s`.  The second tap is speculative -- it
  * is wasted when the first step already collides -- so it is only issued when a collision at the first step is unlikely: the
  * optical depth one step adds at the density last seen (the field is trilinear, one step is about one voxel) is compared with what
@@ -151,12 +168,12 @@ __device__ __forceinline__ float tapVolume(cudaTextureObject_t tex3, V3 q) { ret
  * functions of the step index alone. */
 #define DS_ISSUE_TAPS(base, lastD)                                                                    \
     do {                                                                                              \
-        pd1 = tapVolume(sc.densityTex, posAt(s, (base) + 1.0f));                                      \
+        pd1 = tapDensity<FUSED>(sc, posAt(s, (base) + 1.0f));                                      \
         if ((lastD) * specC1 > s.tauStar - s.tau) {                                                   \
             pd2 = -1.0f;                                                                              \
             nTaps += 1u;                                                                              \
         } else {                                                                                      \
-            pd2 = tapVolume(sc.densityTex, posAt(s, (base) + 2.0f));                                  \
+            pd2 = tapDensity<FUSED>(sc, posAt(s, (base) + 2.0f));                                  \
             nTaps += 2u;                                                                              \
         }                                                                                             \
     } while (0)
@@ -497,7 +514,7 @@ __device__ __forceinline__ void writeResultFast(const DevScene& sc, const TraceJ
  * instruction stream, which is what the thresholds avoid.  Thresholds are ignored when nothing else can run.
  * MODE >= 0 fixes the estimator at compile time (DsMode); MODE = -1 reads job.mode.
  */
-template <bool SKIP, bool BOXTEST, int UNROLL, int MODE, bool ADAPT>
+template <bool SKIP, bool BOXTEST, int UNROLL, int MODE, bool ADAPT, bool FUSED>
 __global__ void __launch_bounds__(FAST_MAX_THREADS, 1)
     k_trace_fast(const __grid_constant__ DevScene sc, const __grid_constant__ TraceJob job, const __grid_constant__ FastConsts k)
 {
@@ -687,7 +704,7 @@ __global__ void __launch_bounds__(FAST_MAX_THREADS, 1)
                                 st = F_DONE;
                             } else {
                                 s.nf += 1.0f;
-                                lastDensity = tapVolume(sc.densityTex, posAt(s, s.nf));
+                                lastDensity = tapDensity<FUSED>(sc, posAt(s, s.nf));
                                 s.tau = fmaf(lastDensity, k.c1, s.tau);
                                 if (s.tau > s.tauStar) st = F_EVENT;
                                 nTaps++;
@@ -738,7 +755,7 @@ __global__ void __launch_bounds__(FAST_MAX_THREADS, 1)
             if (!inBoxTs(k, s.q0)) {
                 st = F_DONE;
             } else {
-                s.pendT = tapVolume(sc.inscatterTex, s.q0); /* consumed at the next event */
+                s.pendT = tapSun<FUSED>(sc, s.q0); /* consumed at the next event */
                 const float cosLightAngle = -dot(k.lightTs, s.sv);
                 const float u = (cosLightAngle + 1.0f) * 0.5f;
                 if (mode == DS_MODE_SUN_MULTIPLE_SCATTER || (mode == DS_MODE_SUN_AND_SKY_ALL_SCATTER && s.depth != 1))
@@ -767,16 +784,16 @@ __global__ void __launch_bounds__(FAST_MAX_THREADS, 1)
     }
 }
 
-template <bool SKIP, bool BOXTEST, int UNROLL, int MODE, bool ADAPT = false>
+template <bool SKIP, bool BOXTEST, int UNROLL, int MODE, bool ADAPT = false, bool FUSED = false>
 static cudaError_t launchFast(const DevScene& sc, const TraceJob& job, int blocks, int threads, size_t smem, cudaStream_t st, int carveout = -1)
 {
-    cudaError_t e = cudaFuncSetAttribute(k_trace_fast<SKIP, BOXTEST, UNROLL, MODE, ADAPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(k_trace_fast<SKIP, BOXTEST, UNROLL, MODE, ADAPT, FUSED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     if (carveout >= 0) {
-        e = cudaFuncSetAttribute(k_trace_fast<SKIP, BOXTEST, UNROLL, MODE, ADAPT>, cudaFuncAttributePreferredSharedMemoryCarveout, carveout);
+        e = cudaFuncSetAttribute(k_trace_fast<SKIP, BOXTEST, UNROLL, MODE, ADAPT, FUSED>, cudaFuncAttributePreferredSharedMemoryCarveout, carveout);
         if (e != cudaSuccess) return e;
     }
-    k_trace_fast<SKIP, BOXTEST, UNROLL, MODE, ADAPT><<<blocks, threads, smem, st>>>(sc, job, makeConsts(sc));
+    k_trace_fast<SKIP, BOXTEST, UNROLL, MODE, ADAPT, FUSED><<<blocks, threads, smem, st>>>(sc, job, makeConsts(sc));
     return cudaGetLastError();
 }
 
@@ -794,7 +811,8 @@ cudaError_t KernelSet<true>::trace(const DevScene& sc, const TraceJob& job, cons
         /* the collector always runs multipleScatterSunRadiance (Tasks.cpp:134); the host falls back to the update loop for
          * grids with non-zero faces */
         if (boxtest || !cfg.skipEmpty || job.mode != DS_MODE_SUN_MULTIPLE_SCATTER) return cudaErrorInvalidValue;
-        return launchFast<true, false, 2, DS_MODE_SUN_MULTIPLE_SCATTER, true>(sc, job, (int)maxBlocks, threads, smem, st);
+        if (sc.fusedTex) return launchFast<true, false, 2, DS_MODE_SUN_MULTIPLE_SCATTER, true, true>(sc, job, (int)maxBlocks, threads, smem, st);
+        return launchFast<true, false, 2, DS_MODE_SUN_MULTIPLE_SCATTER, true, false>(sc, job, (int)maxBlocks, threads, smem, st);
     }
     if (!cfg.skipEmpty || boxtest) {
         /* uncommon configurations (grids with non-zero faces, empty-space skipping switched off): estimator read at run time */
@@ -803,17 +821,18 @@ cudaError_t KernelSet<true>::trace(const DevScene& sc, const TraceJob& job, cons
         return launchFast<false, false, 1, -1>(sc, job, blocks, threads, smem, st);
     }
     const bool u2 = cfg.marchUnroll >= 2;
+    const bool fused = sc.fusedTex != 0;
+#define DS_LAUNCH_MODE(M)                                                                                                           \
+    (fused ? (u2 ? launchFast<true, false, 2, M, false, true>(sc, job, blocks, threads, smem, st, cfg.smemCarveout)                 \
+                 : launchFast<true, false, 1, M, false, true>(sc, job, blocks, threads, smem, st, cfg.smemCarveout))                \
+           : (u2 ? launchFast<true, false, 2, M, false, false>(sc, job, blocks, threads, smem, st, cfg.smemCarveout)                \
+                 : launchFast<true, false, 1, M, false, false>(sc, job, blocks, threads, smem, st, cfg.smemCarveout)))
     switch (job.mode) {
-    case DS_MODE_SUN_AND_SKY_ALL_SCATTER:
-        return u2 ? launchFast<true, false, 2, DS_MODE_SUN_AND_SKY_ALL_SCATTER>(sc, job, blocks, threads, smem, st, cfg.smemCarveout)
-                  : launchFast<true, false, 1, DS_MODE_SUN_AND_SKY_ALL_SCATTER>(sc, job, blocks, threads, smem, st, cfg.smemCarveout);
-    case DS_MODE_SUN_MULTIPLE_SCATTER:
-        return u2 ? launchFast<true, false, 2, DS_MODE_SUN_MULTIPLE_SCATTER>(sc, job, blocks, threads, smem, st, cfg.smemCarveout)
-                  : launchFast<true, false, 1, DS_MODE_SUN_MULTIPLE_SCATTER>(sc, job, blocks, threads, smem, st, cfg.smemCarveout);
-    default:
-        return u2 ? launchFast<true, false, 2, DS_MODE_SUN_SINGLE_SCATTER>(sc, job, blocks, threads, smem, st, cfg.smemCarveout)
-                  : launchFast<true, false, 1, DS_MODE_SUN_SINGLE_SCATTER>(sc, job, blocks, threads, smem, st, cfg.smemCarveout);
+    case DS_MODE_SUN_AND_SKY_ALL_SCATTER: return DS_LAUNCH_MODE(DS_MODE_SUN_AND_SKY_ALL_SCATTER);
+    case DS_MODE_SUN_MULTIPLE_SCATTER: return DS_LAUNCH_MODE(DS_MODE_SUN_MULTIPLE_SCATTER);
+    default: return DS_LAUNCH_MODE(DS_MODE_SUN_SINGLE_SCATTER);
     }
+#undef DS_LAUNCH_MODE
 }
 
 /*
@@ -957,5 +976,22 @@ cudaError_t KernelSet<true>::primaryPrepass(const DevScene& sc, const TraceJob& 
 }
 
 template struct KernelSet<true>;
+
+__global__ void __launch_bounds__(256) k_interleave(const uint8_t* __restrict__ a, const uint8_t* __restrict__ b, int nx, int ny, int nz,
+                                                    cudaSurfaceObject_t surf)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y, z = blockIdx.z;
+    if (x >= nx) return;
+    const size_t i = ((size_t)z * ny + y) * nx + x;
+    surf3Dwrite(make_uchar2(a[i], b[i]), surf, x * (int)sizeof(uchar2), y, z);
+}
+
+cudaError_t launchInterleave(const uint8_t* a, const uint8_t* b, int nx, int ny, int nz, cudaSurfaceObject_t surf, cudaStream_t st)
+{
+    if (ny > 65535 || nz > 65535) return cudaErrorInvalidValue;
+    k_interleave<<<dim3((nx + 255) / 256, ny, nz), 256, 0, st>>>(a, b, nx, ny, nz, surf);
+    return cudaGetLastError();
+}
 
 } // namespace dsk

@@ -27,10 +27,14 @@ def main():
     ap.add_argument("--kind", type=int, default=0)
     ap.add_argument("--tag", default="")
     ap.add_argument("--out", default=None)
+    ap.add_argument("--pre", action="append", default=[], help="name=value set before the volume is created")
     ap.add_argument("--set", action="append", default=[], help="name=v1,v2,... (cartesian product)")
     a = ap.parse_args()
     sun = tuple(float(x) for x in a.sun.split(","))
     ctx = ds.Context(0)
+    for s in a.pre:
+        k, v = s.split("=")
+        ctx.set_option(k, int(v))
     ctx.volume_synth(a.grid, a.kind, 1234, True)
     ctx.scene_set(a.size, sun)
     baked = {}
@@ -64,7 +68,7 @@ def main():
         c = ctx.counters()
         ls = ctx.launch_stats()
         p, _ = ctx.frame_download()
-        rec = dict(tag=a.tag, opts=opts, nonfinite=c['nonfinite'], precision=prec, mpaths_s=c["paths"] / dt / 1e6, gevents_s=c["events"] / dt / 1e9, gsteps_s=c["steps"] / dt / 1e9,
+        rec = dict(tag=a.tag, pre=a.pre, opts=opts, nonfinite=c['nonfinite'], precision=prec, mpaths_s=c["paths"] / dt / 1e6, gevents_s=c["events"] / dt / 1e9, gsteps_s=c["steps"] / dt / 1e9,
                    gtaps_s=c["density_taps"] / dt / 1e9, events_per_path=c["events"] / c["paths"], steps_per_path=c["steps"] / c["paths"],
                    trace_ms=ls["trace_ms_total"] / max(1, ls["trace_launches_timed"]), wall_s=dt, bake_s=bake_s,
                    alg_gbs=(8 * c["steps"] + 8 * c["events"]) / (ls["trace_ms_total"] * 1e-3) / 1e9, mean=float(p[..., 0].mean()))
