@@ -47,6 +47,7 @@ struct DsContext {
     cudaTextureObject_t densityMipTex = 0;
     uint32_t* occ = nullptr;
     uint8_t* cellDist = nullptr;
+    uint8_t* cellEscape = nullptr; /* per cell: bit o set when every cell of octant o seen from the cell is empty (k_trace_fast, emptySteps) */
     int occShift = 0, ocx = 0, ocy = 0, ocz = 0, occWords = 0;
     int borderEmpty = 0;
 
@@ -212,6 +213,8 @@ static void freeVolume(DsContext* ctx)
     ctx->occ = nullptr;
     if (ctx->cellDist) cudaFree(ctx->cellDist);
     ctx->cellDist = nullptr;
+    if (ctx->cellEscape) cudaFree(ctx->cellEscape);
+    ctx->cellEscape = nullptr;
 }
 
 static void freeFrame(DsContext* ctx)
@@ -406,6 +409,7 @@ static void fillDevScene(DsContext* ctx, DevScene& sc)
     sc.ocz = ctx->ocz;
     sc.occWords = ctx->occWords;
     sc.cellDist = ctx->cellDist;
+    sc.cellEscape = ctx->opt["escape_octants"] ? ctx->cellEscape : nullptr;
     sc.guideA = ctx->guide;
     sc.guideB = ctx->guide + GUIDE_A_N;
     sc.borderEmpty = ctx->borderEmpty;
@@ -496,6 +500,40 @@ static int finishVolume(DsContext* ctx, int buildMips)
         ctx->borderEmpty = h == 0 ? 1 : 0;
     }
     DS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (ctx->borderEmpty) {
+        /* escape octants: bit o = (dx > 0) | (dy > 0) << 1 | (dz > 0) << 2 of cell c is set when c and every cell on its far side in all
+         * three directions of octant o are empty.  A ray in c with those direction signs only visits such cells and then leaves a grid
+         * whose faces are zero: every tap up to the box exit reads 0.  Three suffix-AND sweeps per octant over <= 2^18 cells, on the host. */
+        const int ox = ctx->ocx, oy = ctx->ocy, oz = ctx->ocz;
+        const size_t cells = (size_t)ox * oy * oz;
+        std::vector<uint32_t> bits(ctx->occWords);
+        DS_CUDA(ctx, cudaMemcpy(bits.data(), ctx->occ, (size_t)ctx->occWords * 4, cudaMemcpyDeviceToHost));
+        std::vector<uint8_t> esc(cells, 0), r(cells);
+        for (int o = 0; o < 8; o++) {
+            for (size_t i = 0; i < cells; i++) r[i] = ((bits[i >> 5] >> (i & 31)) & 1u) ? 0 : 1;
+            const int sx = (o & 1) ? 1 : -1, sy = (o & 2) ? 1 : -1, sz = (o & 4) ? 1 : -1;
+            auto at = [&](int x, int y, int z) -> uint8_t& { return r[((size_t)z * oy + y) * ox + x]; };
+            for (int z = 0; z < oz; z++)
+                for (int y = 0; y < oy; y++)
+                    for (int i = 1; i < ox; i++) {
+                        const int x = sx > 0 ? ox - 1 - i : i;
+                        at(x, y, z) &= at(x + sx, y, z);
+                    }
+            for (int z = 0; z < oz; z++)
+                for (int i = 1; i < oy; i++) {
+                    const int y = sy > 0 ? oy - 1 - i : i;
+                    for (int x = 0; x < ox; x++) at(x, y, z) &= at(x, y + sy, z);
+                }
+            for (int i = 1; i < oz; i++) {
+                const int z = sz > 0 ? oz - 1 - i : i;
+                for (int y = 0; y < oy; y++)
+                    for (int x = 0; x < ox; x++) at(x, y, z) &= at(x, y, z + sz);
+            }
+            for (size_t i = 0; i < cells; i++) esc[i] |= (uint8_t)(r[i] << o);
+        }
+        DS_CUDA(ctx, cudaMalloc(&ctx->cellEscape, cells));
+        DS_CUDA(ctx, cudaMemcpy(ctx->cellEscape, esc.data(), cells, cudaMemcpyHostToDevice));
+    }
     return DS_OK;
 }
 
@@ -531,7 +569,9 @@ static LaunchConfig launchConfig(DsContext* ctx)
          * tap is a DRAM transaction and a march step is two voxels long, so pairs share no sectors (C4, 2.1 GB: 629 single-tap vs
          * 595 guarded pairs vs 419 unconditional pairs, profiles/r02c_*, r02j_*, r02g_*) */
         const size_t volumeBytes = ctx->levels.empty() ? 0 : 2 * (size_t)ctx->lnx[0] * ctx->lny[0] * ctx->lnz[0];
-        cfg.marchUnroll = volumeBytes > 4 * (size_t)ctx->prop.l2CacheSize ? 1 : 2;
+        /* with the fused RG8 volume the pair wins there as well (C4: 561 vs 544 Mpaths/s at 16 spp per launch, profiles/r02r_*) */
+        const bool fused = ctx->opt["fused_volume"] != 0 && ctx->opt["precision"] == DS_PRECISION_FAST;
+        cfg.marchUnroll = (volumeBytes > 4 * (size_t)ctx->prop.l2CacheSize && !fused) ? 1 : 2;
     }
     return cfg;
 }
@@ -637,7 +677,7 @@ int ds_context_create(int device, DsContext** out)
     ctx->opt["skip_min"] = 8;
     ctx->opt["skip_max_iters"] = 32;
     ctx->opt["skip_open_dist"] = 1;
-    ctx->opt["zero_check_min"] = 2;
+    ctx->opt["zero_check_min"] = 4;
     ctx->opt["radiance_scheduler"] = 1;
     ctx->opt["smem_carveout"] = -1;
     ctx->opt["volume_generation"] = 0;
@@ -648,6 +688,7 @@ int ds_context_create(int device, DsContext** out)
     ctx->opt["profile_events"] = 0;
     ctx->opt["primary_cache"] = 1;
     ctx->opt["spec_percent"] = 100; /* FAST render, two-tap pipeline: threshold of the speculative second tap (0 = always fetch it) */
+    ctx->opt["escape_octants"] = 1; /* FAST estimator: a path in an empty cell whose whole octant ahead is empty ends without walking the leap DDA */
     ctx->opt["fused_volume"] = 1; /* FAST estimator: march through one RG8 {density, sun transmittance} array instead of two R8 arrays */
     ctx->opt["region_pixels"] = 4096; /* FAST render: hit-list pixels per region of the region-major item order (0 = subframe-major) */
     ctx->opt["descriptor_hw"] = -1;

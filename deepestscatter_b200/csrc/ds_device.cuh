@@ -101,6 +101,9 @@ struct DevScene {
     int occWords;
     /* Chebyshev distance (in cells, saturated at 255) from each cell to the nearest occupied cell; 0 = occupied */
     const uint8_t* cellDist;
+    /* escape octants (NULL = none): bit (dx > 0) | (dy > 0) << 1 | (dz > 0) << 2 of a cell is set when the cell and every cell beyond it in
+     * those three directions are empty and the grid's faces are zero: a ray there reads 0 until it leaves the box */
+    const uint8_t* cellEscape;
     /* two-level guide of the chopped-Mie CDF (k_trace_fast): bucket k of guideA covers val in [k, k+1) / GUIDE_A_N,
      * bucket k of guideB covers val in [k, k+1) * GUIDE_B_LIMIT / GUIDE_B_N (val < GUIDE_B_LIMIT, where the CDF is flat
      * and its knots are dense).  Entry = lo | n << 13: lo = first index i with cdf[i] >= bucket start, n <= 2 = number

@@ -226,7 +226,7 @@ __device__ __forceinline__ float stepsToLeaveBox(const FastConsts& k, V3 q, V3 s
 
 /* The footprint at q is outside the grid and all face voxels are zero: every tap reads 0 until the ray enters the
  * region floor(x) in [0, N-2] (slab test), or until it leaves the box if it never does. */
-__device__ __forceinline__ float outsideGridSteps(const FastConsts& k, V3 q, V3 sv, float x, float y, float z)
+__device__ __forceinline__ float outsideGridSteps(const FastConsts& k, V3 q, V3 sv, float x, float y, float z, bool& leaves)
 {
     const float vx = sv.x * k.nxf, vy = sv.y * k.nyf, vz = sv.z * k.nzf;
     const float big = 1.0e30f;
@@ -248,6 +248,7 @@ __device__ __forceinline__ float outsideGridSteps(const FastConsts& k, V3 q, V3 
         }
     }
     if (tn < tf && tf > 0.0f) return fmaxf(floorf(fminf(tn - 0.01f * margin, 65535.0f)), 0.0f); /* enters the grid */
+    leaves = true;
     return stepsToLeaveBox(k, q, sv);
 }
 
@@ -261,18 +262,26 @@ __device__ __forceinline__ float outsideGridSteps(const FastConsts& k, V3 q, V3 
  * cells; the ray leaves that cube through one face, lands in the adjacent cell and repeats.  When the ray leaves
  * the grid and all face voxels are zero (borderEmpty), the rest of its way out of the box reads 0 as well.
  */
-__device__ __forceinline__ float emptySteps(const DevScene& sc, const FastConsts& k, V3 q, V3 sv, int maxLeaps, bool& more)
+__device__ __forceinline__ float emptySteps(const DevScene& sc, const FastConsts& k, V3 q, V3 sv, int maxLeaps, bool& more, bool& leaves)
 {
     more = false;
+    leaves = false; /* set when every tap from here to the box exit reads 0: the returned count then reaches (about) the exit */
     const float x = fmaf(q.x, k.nxf, -0.5f), y = fmaf(q.y, k.nyf, -0.5f), z = fmaf(q.z, k.nzf, -0.5f);
     const int fx = __float2int_rd(x), fy = __float2int_rd(y), fz = __float2int_rd(z);
     /* outside the grid the footprint is clamped to edge voxels */
     if ((unsigned)fx >= (unsigned)(sc.nx - 1) || (unsigned)fy >= (unsigned)(sc.ny - 1) || (unsigned)fz >= (unsigned)(sc.nz - 1))
-        return sc.borderEmpty ? outsideGridSteps(k, q, sv, x, y, z) : 0.0f;
+        return sc.borderEmpty ? outsideGridSteps(k, q, sv, x, y, z, leaves) : 0.0f;
     const int sh = sc.occShift;
     int cx = fx >> sh, cy = fy >> sh, cz = fz >> sh;
     int dist = (int)__ldg(sc.cellDist + (cz * sc.ocy + cy) * sc.ocx + cx);
     if (dist == 0) return 0.0f; /* the tap cell is occupied */
+    if (sc.cellEscape) {
+        const int oct = (sv.x > 0.0f ? 1 : 0) | (sv.y > 0.0f ? 2 : 0) | (sv.z > 0.0f ? 4 : 0);
+        if ((__ldg(sc.cellEscape + (cz * sc.ocy + cy) * sc.ocx + cx) >> oct) & 1) {
+            leaves = true; /* nothing but empty cells ahead */
+            return stepsToLeaveBox(k, q, sv);
+        }
+    }
     const float cs = (float)(1 << sh);
     const float vx = sv.x * k.nxf, vy = sv.y * k.nyf, vz = sv.z * k.nzf; /* voxels per step */
     const float big = 1.0e30f;
@@ -322,7 +331,10 @@ __device__ __forceinline__ float emptySteps(const DevScene& sc, const FastConsts
         blocked = dist == 0;
         if (blocked) break;
     }
-    if (leftGrid && sc.borderEmpty) return stepsToLeaveBox(k, q, sv);
+    if (leftGrid && sc.borderEmpty) {
+        leaves = true;
+        return stepsToLeaveBox(k, q, sv);
+    }
     more = !leftGrid && !blocked;
     /* stay 0.01 voxel short of the plane that stopped the walk */
     return fmaxf(floorf(fminf(t - 0.01f * margin, 65535.0f)), 0.0f);
@@ -664,12 +676,22 @@ __global__ void __launch_bounds__(FAST_MAX_THREADS, 1)
         /* ---- B: empty-space phase: the tap at the current position fell into an empty cell ---- */
         if (SKIP && mSkip && (__popc(mSkip) >= job.skipMin || mBusy == 0u)) {
             if (st == F_SKIP) {
-                bool more;
-                const float kf = emptySteps(sc, k, posAt(s, s.nf), s.sv, job.skipMaxIters, more);
+                bool more, leaves;
+                const float kf = emptySteps(sc, k, posAt(s, s.nf), s.sv, job.skipMaxIters, more, leaves);
                 s.nf += kf;
-                /* a walk cut short lands in an empty cell and continues next round; otherwise march on */
-                st = (more && kf >= 1.0f) ? F_SKIP : F_MARCH;
-                if (PIPE && st == F_MARCH) DS_ISSUE_TAPS(s.nf, 0.0f);
+                if (!BOXTEST && leaves && !inBoxTs(k, posAt(s, s.nf))) {
+                    /* nothing but zeros up to the box exit, and the landing position is outside: the path ends here.  The reference
+                     * stops at the first position outside the box (a landing position that rounding left inside marches on below) */
+                    float n = s.nf;
+#pragma unroll 1
+                    while (n >= 2.0f && !inBoxTs(k, posAt(s, n - 1.0f))) n -= 1.0f;
+                    nSteps += (uint32_t)n;
+                    st = F_DONE;
+                } else {
+                    /* a walk cut short lands in an empty cell and continues next round; otherwise march on */
+                    st = (more && kf >= 1.0f) ? F_SKIP : F_MARCH;
+                    if (PIPE && st == F_MARCH) DS_ISSUE_TAPS(s.nf, 0.0f);
+                }
             }
             mBusy = __ballot_sync(FULL, (st & (F_MARCH | F_EVENT)) != 0);
         }
@@ -897,8 +919,8 @@ __global__ void __launch_bounds__(256) k_primary_prepass(const DevScene sc, cons
                     break;
                 }
                 n += 1.0f;
-                bool more;
-                n += emptySteps(sc, k, posAt(f, n), f.sv, 256, more);
+                bool more, leaves;
+                n += emptySteps(sc, k, posAt(f, n), f.sv, 256, more, leaves);
             }
             /* a ray that leaves the box: the reference stops at the first position outside it */
             while (!hit && n >= 2.0f && !inBoxTs(k, posAt(f, n - 1.0f))) n -= 1.0f;

@@ -264,14 +264,16 @@ def test_fast_flavour_is_deterministic_under_scheduling_knobs(built_library):
         base = ctx.render_frame(cam, 0, 7)
         c0 = ctx.counters()
         defaults = dict(regen_min=2, skip_min=8, march_keep32=12, march_max_iters=64, skip_open_dist=1, skip_max_iters=32, march_unroll=2,
-                        zero_check_min=1, block_threads=576, blocks_per_sm=2, fused_volume=1)
+                        zero_check_min=1, block_threads=576, blocks_per_sm=2, fused_volume=1, escape_octants=1)
         # positions are a function of the step index (q0 + n * sv), so neither the phase votes, nor how leaps are cut,
         # nor the number of march steps per vote can change a single bit of a path
         for opts in (dict(regen_min=1, skip_min=1), dict(regen_min=32, skip_min=32), dict(march_keep32=0),
                      dict(march_keep32=31, march_max_iters=2), dict(block_threads=64, blocks_per_sm=1), dict(march_unroll=1), dict(zero_check_min=4), dict(zero_check_min=32, march_unroll=1),
                      dict(skip_max_iters=1, skip_open_dist=3), dict(block_threads=512), dict(block_threads=640, march_unroll=2),
                      # the two R8 arrays instead of the fused RG8 {density, sun transmittance} array: each channel filters to the same value
-                     dict(fused_volume=0), dict(fused_volume=0, march_unroll=1)):
+                     dict(fused_volume=0), dict(fused_volume=0, march_unroll=1),
+                     # without the escape octants a leaving path walks the leap DDA to the grid face: same steps, same bits
+                     dict(escape_octants=0), dict(escape_octants=0, skip_max_iters=2)):
             for k, val in opts.items():
                 ctx.set_option(k, val)
             ctx.counters_reset()
