@@ -567,8 +567,8 @@ def run_ours(a):
                 sec["neural_renderer"] = {
                     "ms_per_frame": min(times) * 1e3, "scattering_pixels": int((frame[..., 3] != 0).sum()),
                     "api": "ds_render_disney (DisneyRenderer::render; host frame buffer out), synthetic weights",
-                    "model_kernel": "k_disney_mlp_tc (tcgen05 kind::tf32)", "model_rows": rows, "model_us": us,
-                    "model_tflops_tf32": 2 * macs * rows / (us * 1e-6) / 1e12 if us else None,
+                    "model_kernel": "k_disney_mlp_tc (tcgen05 kind::f16 on IEEE half operands, fp32 accumulation; option mlp_fp16=0: kind::tf32)",
+                    "model_rows": rows, "model_us": us, "model_tflops": 2 * macs * rows / (us * 1e-6) / 1e12 if us else None,
                 }
             except Exception as exc:  # reporting only
                 sec["neural_renderer"] = {"failed": str(exc)}

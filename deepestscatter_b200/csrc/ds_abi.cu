@@ -180,6 +180,7 @@ static void freeDisneyModel(DsContext* ctx)
     freeMlpProgram(m.program);
     freeMlpProgram(m.programBf16);
     cudaFree(m.streamBf16);
+    cudaFree(m.streamF16);
     cudaFree(m.error);
     cudaFree(m.prof);
     m = DisneyModelDev();
@@ -692,6 +693,9 @@ int ds_context_create(int device, DsContext** out)
     ctx->opt["fused_volume"] = 1; /* FAST estimator: march through one RG8 {density, sun transmittance} array instead of two R8 arrays */
     ctx->opt["region_pixels"] = 4096; /* FAST render: hit-list pixels per region of the region-major item order (0 = subframe-major) */
     ctx->opt["descriptor_hw"] = -1;
+    ctx->opt["mlp_fp16"] = 1; /* FAST flavour of the model on IEEE half operands (default): the MMA rate and operand bytes of bf16 with the 10 mantissa
+                                 bits of tf32 (656 vs 357 TFLOP/s, max error against the fp32 model 1.2e-3 either way); 0 = tf32 operands.  Activations
+                                 are converted with .satfinite: beyond 65504 they would clamp, where tf32 would carry on */
     ctx->opt["mlp_bf16"] = 0; /* FAST flavour of the model: 0 = tf32 operands (default), 1 = bf16 operands (twice the MMA rate, half the operand bytes) */
     ctx->opt["compact_reverse"] = 0; /* test hook: neural renderer processes the scattering pixels in the opposite order */
     ctx->opt["mlp_last_us"] = 0; /* read-only: device time of the last model launch when profile_events is on */
@@ -1648,7 +1652,7 @@ int ds_disney_model_pack(const float* weights, size_t count, int bf16, void* str
     if (!weights || count != MLP_WEIGHT_COUNT || !stream_bytes || !chunk_count) return DS_ERR_INVALID;
     DisneyModelHost h;
     packDisneyModel(weights, h);
-    const std::vector<uint8_t>& stream = bf16 ? h.streamBf16 : h.stream;
+    const std::vector<uint8_t>& stream = bf16 == 2 ? h.streamF16 : bf16 ? h.streamBf16 : h.stream;
     const std::vector<MlpChunk>& chunks = bf16 ? h.chunksBf16 : h.chunks;
     *stream_bytes = stream.size();
     *chunk_count = chunks.size();
@@ -1681,6 +1685,7 @@ int ds_disney_model_load(DsContext* ctx, const float* weights, size_t count)
     DS_CUDA(ctx, cudaMalloc(&m.w4b4, h.w4b4.size() * sizeof(float)));
     DS_CUDA(ctx, cudaMalloc(&m.stream, h.stream.size()));
     DS_CUDA(ctx, cudaMalloc(&m.streamBf16, h.streamBf16.size()));
+    DS_CUDA(ctx, cudaMalloc(&m.streamF16, h.streamF16.size()));
     DS_CUDA(ctx, cudaMalloc(&m.error, sizeof(uint32_t)));
     DS_CUDA(ctx, cudaMalloc(&m.prof, 16 * sizeof(unsigned long long)));
     DS_CUDA(ctx, cudaMemset(m.prof, 0, 16 * sizeof(unsigned long long)));
@@ -1689,6 +1694,7 @@ int ds_disney_model_load(DsContext* ctx, const float* weights, size_t count)
     DS_CUDA(ctx, cudaMemcpy(m.w4b4, h.w4b4.data(), h.w4b4.size() * sizeof(float), cudaMemcpyHostToDevice));
     DS_CUDA(ctx, cudaMemcpy(m.stream, h.stream.data(), h.stream.size(), cudaMemcpyHostToDevice));
     DS_CUDA(ctx, cudaMemcpy(m.streamBf16, h.streamBf16.data(), h.streamBf16.size(), cudaMemcpyHostToDevice));
+    DS_CUDA(ctx, cudaMemcpy(m.streamF16, h.streamF16.data(), h.streamF16.size(), cudaMemcpyHostToDevice));
     m.program = makeMlpProgram(h.chunks);
     m.programBf16 = makeMlpProgram(h.chunksBf16);
     if (!m.program || !m.programBf16) DS_FAIL(ctx, DS_ERR_INVALID, "model program has %zu chunks", h.chunks.size());
@@ -1698,7 +1704,9 @@ int ds_disney_model_load(DsContext* ctx, const float* weights, size_t count)
     return DS_OK;
 }
 
-static size_t networkTileBytes(DsContext* ctx, size_t rows) { return (rows + 127) / 128 * networkTileBytesOf(ctx->opt["mlp_bf16"] != 0); }
+/* operand type of the tensor-core model kernel: 1 = bfloat16 (option mlp_bf16), else 2 = IEEE half (option mlp_fp16, the default), else 0 = tf32 */
+static int mlpOperands(DsContext* ctx) { return ctx->opt["mlp_bf16"] ? 1 : ctx->opt["mlp_fp16"] ? 2 : 0; }
+static size_t networkTileBytes(DsContext* ctx, size_t rows) { return (rows + 127) / 128 * networkTileBytesOf(mlpOperands(ctx)); }
 
 /* evaluates the loaded model on device rows.  FAST flavour: tcgen05 tf32 kernel, dIn = 128-row tiles (NETWORK_TILE_FLOATS); EXACT flavour: fp32
  * FMA kernel, dIn = DisneyNetworkInput rows [n][10][226] */
@@ -1713,7 +1721,7 @@ static int disneyForwardDevice(DsContext* ctx, const float* dIn, uint32_t nRows,
         DS_CUDA(ctx, cudaEventRecord(e0, ctx->stream));
     }
     if (ctx->opt["precision"] == DS_PRECISION_FAST)
-        DS_CUDA(ctx, launchDisneyMlpTc(ctx->model, dIn, nRows, dOut, ctx->stream, prof >= 2 ? ctx->model.prof : nullptr, ctx->opt["mlp_bf16"] != 0));
+        DS_CUDA(ctx, launchDisneyMlpTc(ctx->model, dIn, nRows, dOut, ctx->stream, prof >= 2 ? ctx->model.prof : nullptr, mlpOperands(ctx)));
     else
         DS_CUDA(ctx, launchDisneyMlpF32(ctx->model, dIn, nullptr, nRows, dOut, ctx->stream));
     ctx->launches += 1;
@@ -1764,7 +1772,7 @@ int ds_disney_model_forward(DsContext* ctx, const float* network_input, uint32_t
     if (ctx->opt["precision"] == DS_PRECISION_FAST) {
         /* rows -> the tiles the tensor-core kernel reads (the renderer's descriptor gather writes tiles directly) */
         if ((rc = ensureMlpScratch(ctx, 4, networkTileBytes(ctx, n)))) return rc;
-        DS_CUDA(ctx, launchNetworkInputToTiles(dIn, n, ctx->mlpScratch[4], ctx->stream, ctx->opt["mlp_bf16"] != 0));
+        DS_CUDA(ctx, launchNetworkInputToTiles(dIn, n, ctx->mlpScratch[4], ctx->stream, mlpOperands(ctx)));
         ctx->launches += 1;
         dIn = (const float*)ctx->mlpScratch[4];
     }
@@ -1862,7 +1870,7 @@ static int renderDisneyDevice(DsContext* ctx, const DsCamera* cam, uint32_t fram
     if ((rc = descriptorTexture(ctx, true, &mipTex))) return rc;
     for (uint32_t first = 0; first < nActive; first += BATCH) {
         const uint32_t n = std::min(BATCH, nActive - first);
-        DS_CUDA(ctx, launchDescriptors(sc, lv, layers, dPos, dDir, n, nullptr, dInput, nullptr, ctx->stream, tiled ? (ctx->opt["mlp_bf16"] ? -1 : 0) : 226, dAngle, nullptr, dIdx + first,
+        DS_CUDA(ctx, launchDescriptors(sc, lv, layers, dPos, dDir, n, nullptr, dInput, nullptr, ctx->stream, tiled ? -mlpOperands(ctx) : 226, dAngle, nullptr, dIdx + first,
                                        mipTex));
         if ((rc = disneyForwardDevice(ctx, dInput, n, dPred))) return rc;
         DS_CUDA(ctx, launchBlitPredicted(dPred, dInfo, dIdx + first, n, dFrame, ctx->stream));

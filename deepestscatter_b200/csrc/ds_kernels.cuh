@@ -536,7 +536,7 @@ __global__ void __launch_bounds__(256) k_descriptors(const __grid_constant__ Dev
 {
     const uint32_t i = blockIdx.x;
     const int t = threadIdx.x;
-    const bool tiled = layerStride <= 0, bf16 = layerStride < 0;
+    const bool tiled = layerStride <= 0, bf16 = layerStride < 0 /* 16-bit tiles: -1 bfloat16, -2 IEEE half */, f16 = layerStride == -2;
     /* tiles: [tile][layer][K group][row 128][16 bytes]; 58 K groups of 4 floats (tf32 operands) or 30 K groups of 8 bf16 per layer */
     const uint32_t KG = bf16 ? 30u : 58u;
     unsigned char* const tileRow = reinterpret_cast<unsigned char*>(outF32) + (size_t)(i >> 7) * (10u * KG * 2048u) + (size_t)(i & 127u) * 16;
@@ -551,7 +551,7 @@ __global__ void __launch_bounds__(256) k_descriptors(const __grid_constant__ Dev
             if (bf16) {
                 /* K group 28 = k 224..231 (224 density, 225 angle, 226 and 227 the bias-carrying ones), group 29 = k 232..239 */
                 unsigned char* p = tileRow + (size_t)(layer * KG + 28) * 2048;
-                *reinterpret_cast<uint32_t*>(p + 4) = 0x3f803f80u;
+                *reinterpret_cast<uint32_t*>(p + 4) = f16 ? 0x3c003c00u : 0x3f803f80u;
                 *reinterpret_cast<uint2*>(p + 8) = make_uint2(0u, 0u);
                 *reinterpret_cast<uint4*>(p + 2048) = make_uint4(0u, 0u, 0u, 0u);
             } else {
@@ -571,9 +571,15 @@ __global__ void __launch_bounds__(256) k_descriptors(const __grid_constant__ Dev
         if (!tiled) {
             outF32[(size_t)i * sampleStride + (size_t)layer * layerStride + k] = v;
         } else if (bf16) {
-            uint32_t u = __float_as_uint(v); /* round to nearest even */
-            u += 0x7fffu + ((u >> 16) & 1u);
-            *reinterpret_cast<uint16_t*>(tileRow + (size_t)((uint32_t)layer * KG + (uint32_t)(k >> 3)) * 2048 + (size_t)(k & 7) * 2) = (uint16_t)(u >> 16);
+            uint16_t h16;
+            if (f16) {
+                h16 = __half_as_ushort(__float2half_rn(v)); /* densities and angles are far inside the range of a half */
+            } else {
+                uint32_t u = __float_as_uint(v); /* round to nearest even */
+                u += 0x7fffu + ((u >> 16) & 1u);
+                h16 = (uint16_t)(u >> 16);
+            }
+            *reinterpret_cast<uint16_t*>(tileRow + (size_t)((uint32_t)layer * KG + (uint32_t)(k >> 3)) * 2048 + (size_t)(k & 7) * 2) = h16;
         } else {
             /* tf32 (10 mantissa bits), round to nearest: the tensor core would otherwise truncate */
             *reinterpret_cast<uint32_t*>(tileRow + (size_t)((uint32_t)layer * KG + (uint32_t)(k >> 2)) * 2048 + (size_t)(k & 3) * 4) = (__float_as_uint(v) + 0x1000u) & 0xffffe000u;

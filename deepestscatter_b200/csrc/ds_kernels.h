@@ -158,8 +158,8 @@ constexpr size_t NETWORK_TILE_FLOATS = (size_t)10 * 58 * 128 * 4;
 
 /* layerStride 225: DisneyDescriptor layout [n][10][225]; 226: DisneyNetworkInput layout [n][10][226] whose last element per layer is
  * angle[i] (may be NULL) -- samples with active[i] == 0 (active may be NULL) get all-zero densities; gather (may be NULL): output row i
- * is computed from input sample gather[i]; layerStride 0 / -1: outF32 is written as 128-row tiles for the tensor-core model kernel, rounded to
- * tf32 (NETWORK_TILE_FLOATS floats each) / bf16 (half that), the rows that pad the last tile zeroed; mipTex (0 = none): mip-mapped density texture, the taps then run on the texture units (what the
+ * is computed from input sample gather[i]; layerStride 0 / -1 / -2: outF32 is written as 128-row tiles for the tensor-core model kernel, rounded to
+ * tf32 (NETWORK_TILE_FLOATS floats each) / bfloat16 / IEEE half (half that), the rows that pad the last tile zeroed; mipTex (0 = none): mip-mapped density texture, the taps then run on the texture units (what the
  * reference's rtTex3DLod does) instead of the exact software fetch */
 cudaError_t launchDescriptors(const DevScene& sc, const LevelTable& lv, const DescriptorLayers& layers, const float* pos, const float* dir,
                               uint32_t n, uint8_t* outU8, float* outF32, int32_t* tapIndex, cudaStream_t st, int layerStride = 225,

@@ -53,6 +53,50 @@ float bf16ToFloat(uint16_t h)
     memcpy(&x, &u, 4);
     return x;
 }
+/* IEEE half: round to nearest even, subnormals kept, saturating at the largest finite value (what cvt.rn.satfinite.f16.f32 does) */
+uint16_t roundF16(float x)
+{
+    uint32_t u;
+    memcpy(&u, &x, 4);
+    const uint16_t sign = (uint16_t)((u >> 16) & 0x8000u);
+    const uint32_t a = u & 0x7fffffffu;
+    if (a > 0x7f800000u) return (uint16_t)(sign | 0x7fffu); /* NaN */
+    if (a >= 0x477ff000u) return (uint16_t)(sign | 0x7bffu); /* >= 65520 rounds beyond the largest half: saturate at 65504 */
+    if (a < 0x33000001u) return sign;                        /* <= 2^-25: rounds to zero */
+    if (a < 0x38800000u) {                                   /* subnormal half: units of 2^-24 */
+        const int shift = 126 - (int)(a >> 23); /* 14..24 */
+        const uint32_t mant = (a & 0x7fffffu) | 0x800000u;
+        uint32_t h = mant >> shift;
+        const uint32_t rem = mant & ((1u << shift) - 1u), halfway = 1u << (shift - 1);
+        if (rem > halfway || (rem == halfway && (h & 1u))) h++;
+        return (uint16_t)(sign | h);
+    }
+    uint32_t h = ((a - 0x38000000u) >> 13);
+    const uint32_t rem = a & 0x1fffu;
+    if (rem > 0x1000u || (rem == 0x1000u && (h & 1u))) h++;
+    return (uint16_t)(sign | h);
+}
+float f16ToFloat(uint16_t h)
+{
+    const uint32_t sign = (uint32_t)(h & 0x8000u) << 16, e = (h >> 10) & 0x1fu, m = h & 0x3ffu;
+    float x;
+    uint32_t u;
+    if (e == 0) {
+        x = (float)m * 5.9604644775390625e-08f; /* 2^-24 */
+        memcpy(&u, &x, 4);
+        u |= sign;
+    } else if (e == 31) {
+        u = sign | 0x7f800000u | (m << 13);
+    } else {
+        u = sign | ((e + 112u) << 23) | (m << 13);
+    }
+    memcpy(&x, &u, 4);
+    return x;
+}
+/* operand types of the tensor-core kernel */
+enum { OPS_TF32 = 0, OPS_BF16 = 1, OPS_F16 = 2 };
+uint16_t roundHalf(float x, int ops) { return ops == OPS_F16 ? roundF16(x) : roundBf16(x); }
+float halfToFloat(uint16_t h, int ops) { return ops == OPS_F16 ? f16ToFloat(h) : bf16ToFloat(h); }
 
 /* The tensor-core kernel exists for two operand types.  G = K values per 16-byte K group: 4 (tf32, kept in 4-byte words) or 8 (bf16).  One MMA
  * step consumes two K groups (K = 8 or 16), a chunk is up to four steps (K = 32 or 64), so chunk and stage sizes in bytes are the same. */
@@ -61,8 +105,9 @@ float bf16ToFloat(uint16_t h)
  * layout: 8-row x 16-byte core matrices, row groups 128 B apart, K groups B_LBO apart.  Columns kValid and kValid + 1 (when bias != NULL)
  * carry the bias split into a rounded value and the rounded remainder: the A operand holds 1.0 there, so the MMA adds the bias at nearly
  * fp32 precision */
-void appendWeightChunk(std::vector<uint8_t>& stream, const float* W, int ld, int k0, int steps, int kValid, const float* bias, bool bf16)
+void appendWeightChunk(std::vector<uint8_t>& stream, const float* W, int ld, int k0, int steps, int kValid, const float* bias, int ops)
 {
+    const bool bf16 = ops != OPS_TF32; /* 16-bit operands: bfloat16 or IEEE half */
     const int G = bf16 ? 8 : 4, E = bf16 ? 2 : 4;
     const size_t base = stream.size();
     const int kc = 2 * G * steps;
@@ -76,10 +121,10 @@ void appendWeightChunk(std::vector<uint8_t>& stream, const float* W, int ld, int
             else if (bias && k == kValid)
                 v = bias[n];
             else if (bias && k == kValid + 1)
-                v = bias[n] - (bf16 ? bf16ToFloat(roundBf16(bias[n])) : roundTf32(bias[n]));
+                v = bias[n] - (bf16 ? halfToFloat(roundHalf(bias[n], ops), ops) : roundTf32(bias[n]));
             const size_t off = base + (size_t)(kk / G) * B_LBO + (size_t)(n / 8) * 128 + (size_t)(n % 8) * 16 + (size_t)(kk % G) * E;
             if (bf16) {
-                const uint16_t h = roundBf16(v);
+                const uint16_t h = roundHalf(v, ops);
                 memcpy(&stream[off], &h, 2);
             } else {
                 const float r = roundTf32(v);
@@ -90,16 +135,16 @@ void appendWeightChunk(std::vector<uint8_t>& stream, const float* W, int ld, int
 
 /* the chunks of one GEMM operand of K values (+ 2 bias columns when bias != NULL; padded to a whole number of MMA steps): four steps at a
  * time, then the rest */
-void appendGemmPart(std::vector<uint8_t>& stream, std::vector<MlpChunk>& chunks, bool bf16, const float* W, int ld, int K, const float* bias, uint8_t src,
+void appendGemmPart(std::vector<uint8_t>& stream, std::vector<MlpChunk>& chunks, int ops, const float* W, int ld, int K, const float* bias, uint8_t src,
                     uint8_t layer, uint8_t dst, uint8_t gemm, bool first, bool waitAct, bool last, uint8_t epilogue)
 {
-    const int G = bf16 ? 8 : 4, stepK = 2 * G, chunkK = 4 * stepK;
+    const int G = ops != OPS_TF32 ? 8 : 4, stepK = 2 * G, chunkK = 4 * stepK;
     const int kPad = (K + (bias ? 2 : 0) + stepK - 1) / stepK * stepK;
     for (int k0 = 0; k0 < kPad; k0 += chunkK) {
         const int steps = (kPad - k0 >= chunkK ? chunkK : kPad - k0) / stepK;
         MlpChunk c{};
         c.wOffset = (uint32_t)stream.size();
-        appendWeightChunk(stream, W, ld, k0, steps, K, bias, bf16);
+        appendWeightChunk(stream, W, ld, k0, steps, K, bias, ops);
         c.wBytes = (uint32_t)stream.size() - c.wOffset;
         c.k8 = (uint16_t)steps;
         c.aKGroup = (uint16_t)(src == 0 ? k0 / G : k0);
@@ -169,10 +214,11 @@ void packDisneyModel(const float* w, DisneyModelHost& out)
 
     /* tensor-core kernel: the program, once per operand type.  Biases ride in the GEMMs: the descriptor layer is staged with z[226] = z[227] = 1
      * and the activation buffer holds 1 in columns 200 and 201 */
-    for (int t = 0; t < 2; ++t) {
-        const bool bf16 = t == 1;
-        std::vector<uint8_t>& stream = bf16 ? out.streamBf16 : out.stream;
-        std::vector<MlpChunk>& chunks = bf16 ? out.chunksBf16 : out.chunks;
+    for (int t = 0; t < 3; ++t) {
+        const int bf16 = t; /* OPS_TF32, OPS_BF16, OPS_F16; the two 16-bit types share one chunk table */
+        std::vector<MlpChunk> chunksF16;
+        std::vector<uint8_t>& stream = t == OPS_F16 ? out.streamF16 : t == OPS_BF16 ? out.streamBf16 : out.stream;
+        std::vector<MlpChunk>& chunks = t == OPS_F16 ? chunksF16 : t == OPS_BF16 ? out.chunksBf16 : out.chunks;
         stream.clear();
         chunks.clear();
         for (int i = 0; i < MLP_NB; ++i) {
@@ -354,6 +400,8 @@ constexpr uint32_t TC_TMEM_COLS = 512, TC_D2_COL = 256;
 constexpr uint32_t TC_IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(MLP_NPAD >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
 /* A = B = BF16 (format 1), kind::f16 */
 constexpr uint32_t TC_IDESC_BF16 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(MLP_NPAD >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
+/* A = B = F16 (format 0), kind::f16 */
+constexpr uint32_t TC_IDESC_F16 = (1u << 4) | ((uint32_t)(MLP_NPAD >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
 
 /* barrier slots (8 bytes each) */
 enum { BAR_WFULL = 0, BAR_WFREE = BAR_WFULL + TC_WSTAGES, BAR_ZFULL = BAR_WFREE + TC_WSTAGES, BAR_ZFREE = BAR_ZFULL + TC_ZSTAGES,
@@ -405,17 +453,17 @@ __device__ __forceinline__ bool mbarWait(uint32_t bar, uint32_t parity, volatile
 __device__ __forceinline__ uint32_t ummaDescLo(uint32_t saddr, uint32_t lbo) { return ((saddr & 0x3ffffu) >> 4) | ((lbo >> 4) << 16); }
 constexpr uint32_t TC_DESC_HI = (TC_SBO >> 4) | (1u << 14);
 
-template <bool BF16>
+template <int OPS>
 __device__ __forceinline__ void ummaIssue(uint32_t tmemD, uint32_t descALo, uint32_t descBLo, uint32_t accumulate)
 {
-    if (BF16)
+    if (OPS != OPS_TF32)
         asm volatile(
             "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
             "mov.b64 da, {%1, %3};\n\t"
             "mov.b64 db, {%2, %3};\n\t"
             "setp.ne.b32 p, %5, 0;\n\t"
             "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t}"
-            ::"r"(tmemD), "r"(descALo), "r"(descBLo), "r"(TC_DESC_HI), "r"(TC_IDESC_BF16), "r"(accumulate)
+            ::"r"(tmemD), "r"(descALo), "r"(descBLo), "r"(TC_DESC_HI), "r"(OPS == OPS_F16 ? TC_IDESC_F16 : TC_IDESC_BF16), "r"(accumulate)
             : "memory");
     else
         asm volatile(
@@ -488,16 +536,21 @@ __device__ __forceinline__ float toTf32(float x)
     return __uint_as_float(u);
 }
 
+/* two fp32 -> two 16-bit operands in one word (bfloat16, or IEEE half saturating at the largest finite value) */
+template <int OPS>
 __device__ __forceinline__ uint32_t packBf16(float lo, float hi)
 {
     uint32_t u;
-    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(u) : "f"(hi), "f"(lo)); /* first source -> upper half */
+    if (OPS == OPS_F16)
+        asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(u) : "f"(hi), "f"(lo));
+    else
+        asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(u) : "f"(hi), "f"(lo)); /* first source -> upper half */
     return u;
 }
 
 /* N accumulator columns of the thread's row, starting at col0 (a multiple of 16).  The bias is already in the accumulator (it rides in the
  * GEMM), so this is relu + the write-back: tf32 as 4-column float4 K groups, bf16 as 8-column K groups */
-template <int N, bool BF16>
+template <int N, int OPS>
 __device__ __forceinline__ void epilogueCols(uint32_t tacc, int col0, int epilogue, unsigned char* actRow, const float* __restrict__ w4, float& y)
 {
     uint32_t v[N];
@@ -516,14 +569,14 @@ __device__ __forceinline__ void epilogueCols(uint32_t tacc, int col0, int epilog
         }
         return;
     }
-    if (BF16) {
+    if (OPS != OPS_TF32) {
 #pragma unroll
         for (int q = 0; q < N / 8; ++q) {
             const int col = col0 + 8 * q;
             if (col < MLP_D)
                 *reinterpret_cast<uint4*>(actRow + (uint32_t)(col / 8) * TC_A_LBO) =
-                    make_uint4(packBf16(__uint_as_float(v[8 * q]), __uint_as_float(v[8 * q + 1])), packBf16(__uint_as_float(v[8 * q + 2]), __uint_as_float(v[8 * q + 3])),
-                               packBf16(__uint_as_float(v[8 * q + 4]), __uint_as_float(v[8 * q + 5])), packBf16(__uint_as_float(v[8 * q + 6]), __uint_as_float(v[8 * q + 7])));
+                    make_uint4(packBf16<OPS>(__uint_as_float(v[8 * q]), __uint_as_float(v[8 * q + 1])), packBf16<OPS>(__uint_as_float(v[8 * q + 2]), __uint_as_float(v[8 * q + 3])),
+                               packBf16<OPS>(__uint_as_float(v[8 * q + 4]), __uint_as_float(v[8 * q + 5])), packBf16<OPS>(__uint_as_float(v[8 * q + 6]), __uint_as_float(v[8 * q + 7])));
         }
     } else {
 #pragma unroll
@@ -539,11 +592,12 @@ __device__ __forceinline__ void epilogueCols(uint32_t tacc, int col0, int epilog
     if (epilogue == MLP_EPI_O) tmemStore(tacc + (uint32_t)col0, v);
 }
 
-template <bool PROFILE, bool BF16>
+template <bool PROFILE, int OPS>
 __global__ void __launch_bounds__(TC_THREADS, 1)
     k_disney_mlp_tc(const __grid_constant__ MlpProgram prog, const void* __restrict__ tiles, uint32_t nRows, const uint8_t* __restrict__ stream,
                     const float* __restrict__ w4b4, float* __restrict__ out, uint32_t* __restrict__ errorOut, unsigned long long* __restrict__ prof)
 {
+    constexpr bool BF16 = OPS != OPS_TF32; /* 16-bit operands (bfloat16 or IEEE half): 8 values per K group */
     extern __shared__ __align__(1024) unsigned char smem[];
     unsigned char* actS = smem;
     const long long tStart = clock64();
@@ -650,10 +704,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
                 const int k8 = ch.k8;
                 if (electOne()) {
                     /* one MMA per 8 k values: two 4-float K groups of each operand, i.e. 2 * LBO bytes further per step */
-                    ummaIssue<BF16>(d, aLo, bLo, (ch.flags & MLP_FIRST) ? 0u : 1u);
-                    if (k8 > 1) ummaIssue<BF16>(d, aLo + (2u * TC_A_LBO >> 4), bLo + (2u * B_LBO >> 4), 1u);
-                    if (k8 > 2) ummaIssue<BF16>(d, aLo + 2u * (2u * TC_A_LBO >> 4), bLo + 2u * (2u * B_LBO >> 4), 1u);
-                    if (k8 > 3) ummaIssue<BF16>(d, aLo + 3u * (2u * TC_A_LBO >> 4), bLo + 3u * (2u * B_LBO >> 4), 1u);
+                    ummaIssue<OPS>(d, aLo, bLo, (ch.flags & MLP_FIRST) ? 0u : 1u);
+                    if (k8 > 1) ummaIssue<OPS>(d, aLo + (2u * TC_A_LBO >> 4), bLo + (2u * B_LBO >> 4), 1u);
+                    if (k8 > 2) ummaIssue<OPS>(d, aLo + 2u * (2u * TC_A_LBO >> 4), bLo + 2u * (2u * B_LBO >> 4), 1u);
+                    if (k8 > 3) ummaIssue<OPS>(d, aLo + 3u * (2u * TC_A_LBO >> 4), bLo + 3u * (2u * B_LBO >> 4), 1u);
                     ummaCommit(barBase + 8 * (BAR_WFREE + ws));
                     if (ch.src == 1) ummaCommit(barBase + 8 * (BAR_ZFREE + zs));
                     if (ch.flags & MLP_LAST) ummaCommit(barBase + 8 * BAR_GEMM);
@@ -679,7 +733,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         /* the constant-one columns 200, 201 that carry the biases through the GEMMs; 202..207 are padding */
         if (half == 0) {
             if (BF16) {
-                *reinterpret_cast<uint4*>(actS + (uint32_t)(MLP_D / 8) * TC_A_LBO + rowOff) = make_uint4(0x3f803f80u, 0u, 0u, 0u); /* bf16 1, 1, 0 x 6 */
+                *reinterpret_cast<uint4*>(actS + (uint32_t)(MLP_D / 8) * TC_A_LBO + rowOff) =
+                    make_uint4(OPS == OPS_F16 ? 0x3c003c00u : 0x3f803f80u, 0u, 0u, 0u); /* 1, 1, 0 x 6 in the operand type */
             } else {
                 *reinterpret_cast<float4*>(actS + (uint32_t)(MLP_D / 4) * TC_A_LBO + rowOff) = make_float4(1.0f, 1.0f, 0.0f, 0.0f);
                 *reinterpret_cast<float4*>(actS + (uint32_t)(MLP_D / 4 + 1) * TC_A_LBO + rowOff) = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
@@ -707,9 +762,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
 #pragma unroll 1
                 for (int col0 = half ? 128 : 0; col0 < colEnd; col0 += 32) {
                     if (col0 + 32 <= MLP_NPAD)
-                        epilogueCols<32, BF16>(tacc, col0, epilogue, actS + rowOff, w4b4, y);
+                        epilogueCols<32, OPS>(tacc, col0, epilogue, actS + rowOff, w4b4, y);
                     else
-                        epilogueCols<16, BF16>(tacc, col0, epilogue, actS + rowOff, w4b4, y);
+                        epilogueCols<16, OPS>(tacc, col0, epilogue, actS + rowOff, w4b4, y);
                     const int done = min(col0 + 32, MLP_NPAD);
                     if (epilogue != MLP_EPI_OUT && (done % PIECE_COLS == 0 || done == MLP_NPAD)) {
                         /* hand the piece over: TMEM store done, shared-memory stores visible to the tensor core's async proxy */
@@ -748,26 +803,28 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     }
 }
 
-template <bool PROFILE, bool BF16>
+template <bool PROFILE, int OPS>
 static cudaError_t launchTc(const MlpProgram& prog, const void* tiles, uint32_t nRows, const uint8_t* stream, const float* w4b4, float* out, uint32_t* error,
                             unsigned long long* prof, cudaStream_t st)
 {
-    cudaError_t e = cudaFuncSetAttribute(k_disney_mlp_tc<PROFILE, BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM);
+    cudaError_t e = cudaFuncSetAttribute(k_disney_mlp_tc<PROFILE, OPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM);
     if (e != cudaSuccess) return e;
-    k_disney_mlp_tc<PROFILE, BF16><<<(nRows + TC_M - 1) / TC_M, TC_THREADS, TC_SMEM, st>>>(prog, tiles, nRows, stream, w4b4, out, error, prof);
+    k_disney_mlp_tc<PROFILE, OPS><<<(nRows + TC_M - 1) / TC_M, TC_THREADS, TC_SMEM, st>>>(prog, tiles, nRows, stream, w4b4, out, error, prof);
     return cudaGetLastError();
 }
 
-cudaError_t launchDisneyMlpTc(const DisneyModelDev& m, const void* tiles, uint32_t nRows, float* out, cudaStream_t st, unsigned long long* prof, bool bf16)
+cudaError_t launchDisneyMlpTc(const DisneyModelDev& m, const void* tiles, uint32_t nRows, float* out, cudaStream_t st, unsigned long long* prof, int ops)
 {
     if (nRows == 0) return cudaSuccess;
-    const MlpProgram* prog = bf16 ? m.programBf16 : m.program;
-    const uint8_t* stream = bf16 ? m.streamBf16 : m.stream;
+    const MlpProgram* prog = ops != OPS_TF32 ? m.programBf16 : m.program;
+    const uint8_t* stream = ops == OPS_F16 ? m.streamF16 : ops == OPS_BF16 ? m.streamBf16 : m.stream;
     if (!prog || !stream) return cudaErrorInvalidValue;
-    if (bf16) return prof ? launchTc<true, true>(*prog, tiles, nRows, stream, m.w4b4, out, m.error, prof, st)
-                          : launchTc<false, true>(*prog, tiles, nRows, stream, m.w4b4, out, m.error, nullptr, st);
-    return prof ? launchTc<true, false>(*prog, tiles, nRows, stream, m.w4b4, out, m.error, prof, st)
-                : launchTc<false, false>(*prog, tiles, nRows, stream, m.w4b4, out, m.error, nullptr, st);
+    if (ops == OPS_F16) return prof ? launchTc<true, OPS_F16>(*prog, tiles, nRows, stream, m.w4b4, out, m.error, prof, st)
+                                    : launchTc<false, OPS_F16>(*prog, tiles, nRows, stream, m.w4b4, out, m.error, nullptr, st);
+    if (ops == OPS_BF16) return prof ? launchTc<true, OPS_BF16>(*prog, tiles, nRows, stream, m.w4b4, out, m.error, prof, st)
+                                     : launchTc<false, OPS_BF16>(*prog, tiles, nRows, stream, m.w4b4, out, m.error, nullptr, st);
+    return prof ? launchTc<true, OPS_TF32>(*prog, tiles, nRows, stream, m.w4b4, out, m.error, prof, st)
+                : launchTc<false, OPS_TF32>(*prog, tiles, nRows, stream, m.w4b4, out, m.error, nullptr, st);
 }
 
 /* the chunk table as the kernel-parameter block (host memory, owned by the model) */
@@ -784,9 +841,10 @@ void freeMlpProgram(MlpProgram* p) { delete p; }
 
 /* DisneyNetworkInput rows [n][10][226] -> the tiles the tensor-core kernel consumes (rounded to the operand type; k 226, 227 = 1; the rest of
  * the layer's K padding and the padding rows zero): one thread per (row, layer, K group) */
-template <bool BF16>
+template <int OPS>
 __global__ void __launch_bounds__(256) k_network_input_to_tiles(const float* __restrict__ in, uint32_t nRows, uint32_t nPadded, void* __restrict__ tiles)
 {
+    constexpr bool BF16 = OPS != OPS_TF32;
     constexpr uint32_t G = BF16 ? 8u : 4u, KG = BF16 ? 30u : 58u; /* K values per group, groups per layer */
     const size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= (size_t)nPadded * (MLP_NB * KG)) return;
@@ -807,20 +865,22 @@ __global__ void __launch_bounds__(256) k_network_input_to_tiles(const float* __r
     }
     unsigned char* dst = reinterpret_cast<unsigned char*>(tiles) + ((size_t)(row >> 7) * (MLP_NB * KG) + lk) * TC_A_LBO + (size_t)(row & 127u) * 16;
     if (BF16)
-        *reinterpret_cast<uint4*>(dst) = make_uint4(packBf16(v[0], v[1]), packBf16(v[2], v[3]), packBf16(v[G - 4], v[G - 3]), packBf16(v[G - 2], v[G - 1]));
+        *reinterpret_cast<uint4*>(dst) = make_uint4(packBf16<OPS>(v[0], v[1]), packBf16<OPS>(v[2], v[3]), packBf16<OPS>(v[G - 4], v[G - 3]), packBf16<OPS>(v[G - 2], v[G - 1]));
     else
         *reinterpret_cast<float4*>(dst) = make_float4(toTf32(v[0]), toTf32(v[1]), toTf32(v[2]), toTf32(v[3]));
 }
 
-cudaError_t launchNetworkInputToTiles(const float* in, uint32_t nRows, void* tiles, cudaStream_t st, bool bf16)
+cudaError_t launchNetworkInputToTiles(const float* in, uint32_t nRows, void* tiles, cudaStream_t st, int ops)
 {
     if (nRows == 0) return cudaSuccess;
     const uint32_t nPadded = (nRows + 127u) / 128u * 128u;
-    const size_t total = (size_t)nPadded * MLP_NB * (bf16 ? 30 : 58);
-    if (bf16)
-        k_network_input_to_tiles<true><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(in, nRows, nPadded, tiles);
+    const size_t total = (size_t)nPadded * MLP_NB * (ops != OPS_TF32 ? 30 : 58);
+    if (ops == OPS_F16)
+        k_network_input_to_tiles<OPS_F16><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(in, nRows, nPadded, tiles);
+    else if (ops == OPS_BF16)
+        k_network_input_to_tiles<OPS_BF16><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(in, nRows, nPadded, tiles);
     else
-        k_network_input_to_tiles<false><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(in, nRows, nPadded, tiles);
+        k_network_input_to_tiles<OPS_TF32><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(in, nRows, nPadded, tiles);
     return cudaGetLastError();
 }
 

@@ -50,6 +50,7 @@ struct DisneyModelDev {
     float* w4b4 = nullptr;     /* fullyConnected.4: 200 weights, zero padding to 208, bias at [208] */
     uint8_t* stream = nullptr; /* tensor-core kernel: weights in UMMA canonical K-major layout, in consumption order (tf32 operands) */
     uint8_t* streamBf16 = nullptr; /* the same for bf16 operands (option mlp_bf16) */
+    uint8_t* streamF16 = nullptr;  /* ... and for IEEE half operands (option mlp_fp16); same chunk table as bf16 */
     struct MlpProgram* programBf16 = nullptr;
     struct MlpProgram* program = nullptr; /* host: the chunk table, passed to the kernel as its (grid-constant) parameter block */
     int nChunks = 0;
@@ -61,7 +62,7 @@ struct DisneyModelDev {
 /* host-side packing of the flat state_dict array (include/ds_abi.h: ds_disney_model_load) */
 struct DisneyModelHost {
     std::vector<float> wT, bias, w4b4;
-    std::vector<uint8_t> stream, streamBf16;      /* tf32 / bf16 operands */
+    std::vector<uint8_t> stream, streamBf16, streamF16; /* tf32 / bf16 / IEEE half operands */
     std::vector<MlpChunk> chunks, chunksBf16;
 };
 void packDisneyModel(const float* weights, DisneyModelHost& out);
@@ -75,11 +76,11 @@ cudaError_t launchDisneyMlpF32(const DisneyModelDev& m, const float* in, const u
  * NETWORK_TILE_FLOATS: [layer][K group][row][4], so that the K chunk of a layer is one contiguous block a bulk copy can fetch); out[i] for
  * i < nRows.  prof (may be NULL): 16 device words; block 0 leaves its cycle accounting there */
 cudaError_t launchDisneyMlpTc(const DisneyModelDev& m, const void* tiles, uint32_t nRows, float* out, cudaStream_t st, unsigned long long* prof = nullptr,
-                              bool bf16 = false);
+                              int ops = 0 /* operand type: 0 = tf32, 1 = bfloat16, 2 = IEEE half */);
 /* [nRows][10][226] -> ceil(nRows / 128) tiles (networkTileBytes per tile) */
-cudaError_t launchNetworkInputToTiles(const float* in, uint32_t nRows, void* tiles, cudaStream_t st, bool bf16 = false);
-/* bytes of one 128-row tile of network input: tf32 operands [10][58][128][4 floats], bf16 operands [10][30][128][8 bf16] */
-inline size_t networkTileBytesOf(bool bf16) { return (size_t)10 * (bf16 ? 30 : 58) * 128 * 16; }
+cudaError_t launchNetworkInputToTiles(const float* in, uint32_t nRows, void* tiles, cudaStream_t st, int ops = 0);
+/* bytes of one 128-row tile of network input: tf32 operands [10][58][128][4 floats], 16-bit operands [10][30][128][8] */
+inline size_t networkTileBytesOf(int ops) { return (size_t)10 * (ops ? 30 : 58) * 128 * 16; }
 /* indices of the rows with active[i] != 0: idx[0..*count), unordered */
 cudaError_t launchCompactActive(const uint8_t* active, uint32_t n, uint32_t* idx, uint32_t* count, cudaStream_t st);
 cudaError_t launchReverse(uint32_t* a, uint32_t n, cudaStream_t st); /* test hook: reverse the compacted order */

@@ -124,7 +124,7 @@ int ds_sync(DsContext* ctx);
  * "skip_max_iters", "skip_open_dist", "zero_check_min", "smem_carveout", "staging_subframes" -- tuning knobs of the estimator kernels;
  * "radiance_scheduler", "radiance_quota" -- the radiance collector (0 = the reference's host schedule, 1 = device-resident);
  * "stream_offset" -- added to the subframe id to form the RNG stream id;
- * neural renderer: "mlp_bf16" (FAST flavour of the model on bf16 instead of tf32 operands), "descriptor_hw" (-1 = the FAST network-input passes
+ * neural renderer: "mlp_bf16" / "mlp_fp16" (FAST flavour of the model on bfloat16 / IEEE half instead of tf32 operands), "descriptor_hw" (-1 = the FAST network-input passes
  * sample a mip-mapped texture, the collectors never; 0 = never; 1 = also the float collector), "compact_reverse" (test hook: process the
  * scattering pixels in the opposite order);
  * "profile_events" (1: CUDA events around the trace / model launches, read back through ds_get_launch_stats and "mlp_last_us"; 2: also the
@@ -265,7 +265,7 @@ size_t ds_disney_model_weight_count(void);
 int ds_disney_model_load(DsContext* ctx, const float* weights, size_t count);
 /* Introspection, host only (no device needed): the program the tensor-core kernel runs for these weights -- the weight stream in UMMA
  * canonical K-major no-swizzle layout (8-row x 16-byte core matrices; row groups 128 B apart, 16-byte K groups 26 * 128 B apart; 208 rows;
- * bf16 = 0: tf32-rounded floats, 4 per K group; bf16 = 1: bfloat16, 8 per K group) and the chunk table (20-byte records: u32 stream offset,
+ * bf16 = 0: tf32-rounded floats, 4 per K group; bf16 = 1: bfloat16, bf16 = 2: IEEE half, 8 per K group) and the chunk table (20-byte records: u32 stream offset,
  * u32 bytes, u16 MMA steps (two K groups each), u16 first K group (activations) or first k (descriptor layer), u8 source, u8 layer,
  * u8 accumulator, u8 flags 1 = overwrite / 2 = last of its GEMM / 4 = first chunk after an epilogue, u8 epilogue 1 = relu -> activations /
  * 2 = same + residual kept in tensor memory / 3 = output, u8 GEMM index, 2 pad).  Either output pointer may be NULL to query the sizes. */
@@ -273,7 +273,7 @@ int ds_disney_model_pack(const float* weights, size_t count, int bf16, void* str
                          size_t chunks_capacity, size_t* stream_bytes, size_t* chunk_count);
 /* module->forward (DisneyRenderer.cpp:104; DisneyModel.forward, DisneyModel.py:16-29): network_input [n][10][226] floats ->
  * predicted_out [n] (radiance for a sun of 1e6).  DS_PRECISION_EXACT: fp32 FMA kernel; DS_PRECISION_FAST: tcgen05 tensor-core kernel, inputs
- * and activations rounded to tf32 (option "mlp_bf16" = 1: to bfloat16), fp32 accumulation and residual path */
+ * and activations rounded to tf32 (option "mlp_bf16" = 1: to bfloat16, "mlp_fp16" = 1: to IEEE half), fp32 accumulation and residual path */
 int ds_disney_model_forward(DsContext* ctx, const float* network_input, uint32_t n, float* predicted_out);
 /* Introspection: cycle accounting of block 0 of the last tensor-core model launch made with option "profile_events" = 2 (an instrumented
  * build of the kernel) -- SM clock cycles; [0] MMA-issuing thread: total, [1] weight producer: waiting for a free weight stage, [2] issuer

@@ -7,7 +7,7 @@ Tolerances (written here as the task asks):
   oracle vs reference float64 outputs      1e-6 relative (double accumulation against torch float64)
   oracle vs reference float32 outputs      2e-6 relative (torch's own float32 rounding)
   EXACT flavour (fp32 FMA kernel) vs oracle   1e-5 relative
-  FAST flavour (tcgen05 kind::tf32) vs oracle 5e-3 relative: operands carry 10 mantissa bits (2^-11 relative rounding) through 23
+  FAST flavour (tcgen05 kind::f16 on IEEE half operands by default, kind::tf32 with option mlp_fp16 = 0) vs oracle 5e-3 relative: operands carry 10 mantissa bits (2^-11 relative rounding) through 23
       layers with fp32 accumulation and an fp32 residual path
 """
 import json
@@ -195,10 +195,10 @@ def packed_program(built_library, weights, bf16=False):
     return stream, chunks
 
 
-@pytest.mark.parametrize("bf16", [False, True])
+@pytest.mark.parametrize("bf16", [0, 1, 2])
 def test_tensor_core_program_emulated_on_cpu(built_library, weights, inputs, bf16):
     """Runs the chunk program of k_disney_mlp_tc in numpy (float64 accumulators): decodes every weight chunk from the canonical
-    core-matrix layout (4 tf32 or 8 bf16 per 16-byte K group), follows the overwrite / accumulate / residual-in-accumulator / epilogue
+    core-matrix layout (4 tf32, or 8 bfloat16 (1) / IEEE half (2) per 16-byte K group), follows the overwrite / accumulate / residual-in-accumulator / epilogue
     flags, and must land on the oracle within the rounding of the weights (activations are not rounded here)."""
     assert CHUNK_DTYPE.itemsize == 20
     G = 8 if bf16 else 4  # K values per 16-byte K group
@@ -211,7 +211,9 @@ def test_tensor_core_program_emulated_on_cpu(built_library, weights, inputs, bf1
     x = np.zeros((n, 10, zpad))
     x[:, :, :226] = inputs[:n]
     x[:, :, 226:228] = 1.0  # the kernel stages z[226] = z[227] = 1: the bias columns of a block's first GEMM
-    if bf16:
+    if bf16 == 2:
+        words = stream.view(np.float16).astype(np.float32)
+    elif bf16:
         words = (stream.view(np.uint16).astype(np.uint32) << 16).view(np.float32)
     else:
         words = stream.view(np.float32)
@@ -248,7 +250,7 @@ def test_tensor_core_program_emulated_on_cpu(built_library, weights, inputs, bf1
                     D[d][:, :200] = v  # the residual of the next block stays in the accumulator
     assert out is not None
     ref = ol.disney_forward(weights, inputs[:n])
-    assert rel(out, ref) <= (6e-3 if bf16 else 2e-3)
+    assert rel(out, ref) <= (6e-3 if bf16 == 1 else 2e-3)  # a half has the 10 mantissa bits of tf32
 
 
 @pytest.mark.gpu
@@ -316,6 +318,87 @@ def test_bf16_operands_match_oracle(gpu_ctx, built_library, weights, inputs, n):
     assert np.isfinite(got).all() and np.array_equal(got, again)
     assert rel(got, ref) <= 1.5e-2
     assert not np.array_equal(got, gpu_ctx.disney_model_forward(x))  # it is not the tf32 path
+
+
+def test_half_weights_are_numpy_float16(built_library, weights):
+    """The host packer's float -> half rounding (nearest even, subnormals, saturation) is numpy's, element for element, on the model's own
+    weights and on values around every boundary of the format."""
+    weights = np.array(weights, np.float32)
+    unflat0 = dm.unflatten(weights)
+    probe = unflat0["fullyConnected.0.weight"]
+    specials = np.array([65504.0, 65519.9, 65520.0, 1e9, -7e4, 6.103515625e-05, 6.1e-05, 6.0975552e-05, 5.9604645e-08, 8.9e-08, 8.95e-08, 2.9802322e-08,
+                         2.9802326e-08, 1e-09, -1e-07, 0.33325195, 0.33337402, 1.0009766, 1.0004883, 1.0014648, 0.0], np.float32)
+    # write the probes into row 0 of fullyConnected.0.weight inside the flat array
+    sizes = [(k, v.size) for k, v in unflat0.items()]
+    pos = 0
+    for k, n_ in sizes:
+        if k == "fullyConnected.0.weight":
+            break
+        pos += n_
+    assert np.array_equal(weights[pos : pos + probe.size].reshape(probe.shape), probe)  # unflatten keeps the flat order
+    weights[pos : pos + specials.size] = specials
+    s16, c16 = packed_program(built_library, weights, 2)
+    sbf, cbf = packed_program(built_library, weights, 1)
+    assert np.array_equal(c16, cbf) and s16.size == sbf.size  # one chunk table for both 16-bit types
+    # the stream holds round(w) and, in the bias columns, round(b) and round(b - round(b)): decode one GEMM's plain weights and compare
+    unflat = dm.unflatten(weights)
+    W = unflat["fullyConnected.0.weight"]  # [200][200]
+    ch = [c for c in c16 if c["gemm"] == 20]
+    half = s16.view(np.float16)
+    got = np.zeros((200, 208), np.float16)
+    for c in ch:
+        kc = int(c["k8"]) * 16
+        k0 = int(c["aK"]) * 8
+        nn, kk = np.meshgrid(np.arange(200), np.arange(kc), indexing="ij")
+        off = (kk // 8) * (26 * 128) + (nn // 8) * 128 + (nn % 8) * 16 + (kk % 8) * 2
+        got[:, k0 : k0 + kc] = half[(int(c["wOffset"]) + off) // 2]
+    with np.errstate(over="ignore"):
+        want = W.astype(np.float16)
+    want[np.isinf(want)] = np.sign(want[np.isinf(want)]) * np.float16(65504)  # the packer saturates (cvt.rn.satfinite), numpy overflows to inf
+    assert np.array_equal(got[:, :200].view(np.uint16), want.view(np.uint16))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n", [1, 127, 160, 1000, 16384])
+def test_half_operands_match_oracle_like_tf32(gpu_ctx, built_library, weights, inputs, n):
+    """Option mlp_fp16: kind::f16 on IEEE half operands -- the MMA rate and operand bytes of bf16, the 10 mantissa bits of tf32: held to the
+    tf32 tolerance (5e-3), not to the bf16 one."""
+    ds = built_library
+    x = inputs[:n] if n <= len(inputs) else dm.synthetic_inputs(n, 21)
+    gpu_ctx.set_option("precision", ds.PRECISION_FAST)
+    assert gpu_ctx.get_option("mlp_fp16") == 1  # the default
+    got = gpu_ctx.disney_model_forward(x)
+    again = gpu_ctx.disney_model_forward(x)
+    gpu_ctx.set_option("mlp_fp16", 0)
+    try:
+        tf32 = gpu_ctx.disney_model_forward(x)
+    finally:
+        gpu_ctx.set_option("mlp_fp16", 1)
+    ref = ol.disney_forward(weights, x)
+    assert np.isfinite(got).all() and np.array_equal(got, again)
+    assert rel(got, ref) <= 5e-3
+    assert rel(tf32, ref) <= 5e-3  # option mlp_fp16 = 0: the tf32 kernel stays held to the same bar
+    assert rel(got, ref) <= 3 * max(rel(tf32, ref), 5e-4)
+    assert not np.array_equal(got, tf32)  # it is not the tf32 path
+
+
+@pytest.mark.gpu
+def test_render_disney_with_half_operands(built_library, weights):
+    ds = built_library
+    cam = ds.camera_look_at(aspect=4.0)
+    with ds.Context(0) as ctx:
+        ctx.volume_synth(SCENE_SMALL["n"], SCENE_SMALL["kind"], SCENE_SMALL["seed"])
+        ctx.scene_set(SCENE_SMALL["cloud_size_m"], SCENE_SMALL["light_dir"])
+        ctx.bake()
+        ctx.disney_model_load(weights)
+        ctx.set_option("mlp_fp16", 0)
+        a = ctx.render_disney(cam, 160, 40, stream=3)  # tf32 operands
+        ctx.set_option("mlp_fp16", 1)
+        b = ctx.render_disney(cam, 160, 40, stream=3)
+        b2 = ctx.render_disney(cam, 160, 40, stream=3)
+    lit = a[..., 3] != 0
+    assert np.array_equal(lit, b[..., 3] != 0) and np.array_equal(b, b2) and not np.array_equal(a, b)
+    assert np.abs(a - b)[lit].max() <= 5e-3 * np.abs(a)[lit].max()
 
 
 @pytest.mark.gpu

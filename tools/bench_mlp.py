@@ -25,9 +25,11 @@ def main():
         ctx.disney_model_load(w)
         ctx.set_option("profile_events", 1)
         outs = {}
-        for name, prec in (("exact_f32_fma", ds.PRECISION_EXACT), ("fast_tcgen05_tf32", ds.PRECISION_FAST), ("fast_tcgen05_bf16", ds.PRECISION_FAST)):
+        for name, prec in (("exact_f32_fma", ds.PRECISION_EXACT), ("fast_tcgen05_tf32", ds.PRECISION_FAST), ("fast_tcgen05_bf16", ds.PRECISION_FAST),
+                           ("fast_tcgen05_fp16", ds.PRECISION_FAST)):
             ctx.set_option("precision", prec)
             ctx.set_option("mlp_bf16", 1 if name.endswith("bf16") else 0)
+            ctx.set_option("mlp_fp16", 1 if name.endswith("fp16") else 0)  # on by default
             us = []
             for _ in range(reps):
                 outs[name] = ctx.disney_model_forward(x)
@@ -40,9 +42,10 @@ def main():
                 ctx.disney_model_forward(x)
                 print(json.dumps({"block0_cycles": ctx.disney_model_profile(), "instrumented_us": ctx.get_option("mlp_last_us")}), flush=True)
                 ctx.set_option("profile_events", 1)
-        a, b, c = outs["exact_f32_fma"], outs["fast_tcgen05_tf32"], outs["fast_tcgen05_bf16"]
+        a, b, c, d = outs["exact_f32_fma"], outs["fast_tcgen05_tf32"], outs["fast_tcgen05_bf16"], outs["fast_tcgen05_fp16"]
         print(json.dumps({"max_rel_diff_tf32_vs_exact": float(np.max(np.abs(a - b) / (np.abs(a) + 1e-6))),
-                          "max_rel_diff_bf16_vs_exact": float(np.max(np.abs(a - c) / (np.abs(a) + 1e-6)))}))
+                          "max_rel_diff_bf16_vs_exact": float(np.max(np.abs(a - c) / (np.abs(a) + 1e-6))),
+                          "max_rel_diff_fp16_vs_exact": float(np.max(np.abs(a - d) / (np.abs(a) + 1e-6)))}))
 
 
 if __name__ == "__main__":
