@@ -488,11 +488,11 @@ __device__ __forceinline__ uint32_t adaptiveTicket(const AdaptiveCollector& ad, 
     return AD_NONE;
 }
 
-__device__ __forceinline__ void writeResultFast(const DevScene& sc, const TraceJob& job, const FastState& s, uint32_t& nonfinite)
+__device__ __forceinline__ void writeResultFast(const DevScene& sc, const TraceJob& job, const FastState& s)
 {
     const float scale = sc.lightIntensity * SUN_TO_SPHERE * fmaf(s.pendT, s.pendP, s.rad);
     const float r = sc.lightColor.x * scale, g = sc.lightColor.y * scale, b = sc.lightColor.z * scale;
-    if (!(fabsf(r + g + b) <= 3.0e38f)) nonfinite++;
+    if (!(fabsf(r + g + b) <= 3.0e38f)) atomicAdd(job.stats + CNT_NONFINITE, 1ull); /* never in a healthy run: not worth a register */
     if (job.kind == JOB_RENDER) {
         job.staging[s.out] = make_float4(r, g, b, 1.0f);
     } else if (job.kind == JOB_POINT) {
@@ -559,7 +559,7 @@ __global__ void __launch_bounds__(FAST_MAX_THREADS, 1)
     s.depth = 0;
     s.out = 0;
     int st = F_IDLE;
-    uint32_t nPaths = 0, nEvents = 0, nSteps = 0, nTaps = 0, nNonfinite = 0;
+    uint32_t nPaths = 0, nEvents = 0, nSteps = 0, nTaps = 0;
     float lastDensity = 0.0f;
     /* PIPE: every lane in F_MARCH holds the densities of its next two steps (nf + 1, nf + 2), fetched when the lane
      * ENTERED that state -- at the end of the event phase, of the empty-space phase or of regeneration -- so the
@@ -585,7 +585,7 @@ __global__ void __launch_bounds__(FAST_MAX_THREADS, 1)
             if (isDone) {
                 x = sc.lightColor.x * (sc.lightIntensity * SUN_TO_SPHERE * fmaf(s.pendT, s.pendP, s.rad)); /* pointEmissionCamera.cu:32: result.x */
                 if (!(fabsf(x) <= 3.0e38f)) {
-                    nNonfinite++;
+                    atomicAdd(job.stats + CNT_NONFINITE, 1ull);
                     x = 0.0f;
                 }
                 st = F_IDLE;
@@ -645,7 +645,7 @@ __global__ void __launch_bounds__(FAST_MAX_THREADS, 1)
 #pragma unroll 1
             for (int r = 0; r < 4; ++r) {
                 if (st == F_DONE) {
-                    writeResultFast(sc, job, s, nNonfinite);
+                    writeResultFast(sc, job, s);
                     st = F_IDLE;
                 }
                 const unsigned need = __ballot_sync(FULL, st == F_IDLE);
@@ -797,9 +797,9 @@ __global__ void __launch_bounds__(FAST_MAX_THREADS, 1)
         }
     }
 
-    unsigned long long c[5] = {nPaths, nEvents, nSteps, nTaps, nNonfinite};
+    unsigned long long c[4] = {nPaths, nEvents, nSteps, nTaps};
 #pragma unroll
-    for (int i = 0; i < 5; i++) {
+    for (int i = 0; i < 4; i++) {
         unsigned long long v = c[i];
         for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(FULL, v, o);
         if (lane == 0 && v) atomicAdd(job.stats + i, v);
