@@ -75,6 +75,11 @@ struct DsContext {
     unsigned long long missSteps = 0;
     unsigned long long extraPaths = 0, extraSteps = 0; /* work of untraced (missing) pixels, added to the counters */
 
+    /* ds_render_subframes_host: the frame buffers travel on a second stream while the first trace kernel runs */
+    cudaStream_t copyStream = nullptr;
+    cudaEvent_t copyFence = nullptr, copyDone = nullptr;
+    bool uploadPending = false; /* copyDone must be waited for before the accumulation buffers are touched */
+
     /* counters + queue */
     unsigned long long* stats = nullptr; /* CNT_COUNT */
     unsigned long long* queue = nullptr;
@@ -771,6 +776,11 @@ int ds_context_destroy(DsContext* ctx)
     for (int i = 0; i < 7; i++) cudaFree(ctx->mlpScratch[i]);
     freeDisneyModel(ctx);
     for (cudaEvent_t e : ctx->traceEvents) cudaEventDestroy(e);
+    if (ctx->copyStream) {
+        cudaStreamDestroy(ctx->copyStream);
+        cudaEventDestroy(ctx->copyFence);
+        cudaEventDestroy(ctx->copyDone);
+    }
     if (ctx->ownStream && ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
     return DS_OK;
@@ -1229,6 +1239,10 @@ int ds_render_subframes(DsContext* ctx, const DsCamera* cam, DsMode mode, uint32
         bool cached;
         rc = traceSubframes(ctx, cam, mode, first_subframe + done, chunk, &cached);
         if (rc) return rc;
+        if (ctx->uploadPending) { /* the upload of ds_render_subframes_host ran beside the trace kernel; the accumulation needs it now */
+            DS_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->copyDone, 0));
+            ctx->uploadPending = false;
+        }
         DS_CUDA(ctx, launchUpdateFrame(ctx->staging, cached ? ctx->entrySteps : nullptr, ctx->progressive, ctx->variance, px,
                                        first_subframe + done, chunk, ctx->stream));
         ctx->launches++;
@@ -1242,9 +1256,26 @@ int ds_render_subframes_host(DsContext* ctx, const DsCamera* cam, DsMode mode, u
 {
     DS_CHECK_CTX(ctx);
     if (!progressive_inout || !variance_inout) DS_FAIL(ctx, DS_ERR_INVALID, "host buffers are NULL");
-    int rc = ds_frame_upload(ctx, progressive_inout, variance_inout);
-    if (rc) return rc;
-    rc = ds_render_subframes(ctx, cam, mode, first_subframe, n);
+    if (!ctx->progressive) DS_FAIL(ctx, DS_ERR_STATE, "no frame (ds_frame_create)");
+    /* host -> device on a second stream, behind everything queued so far, so that it overlaps the trace kernel (which only writes the staging
+     * buffer); ds_render_subframes waits for it before the first accumulation */
+    if (!ctx->copyStream) {
+        DS_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copyStream, cudaStreamNonBlocking));
+        DS_CUDA(ctx, cudaEventCreateWithFlags(&ctx->copyFence, cudaEventDisableTiming));
+        DS_CUDA(ctx, cudaEventCreateWithFlags(&ctx->copyDone, cudaEventDisableTiming));
+    }
+    const size_t bytes = (size_t)ctx->width * ctx->height * sizeof(float4);
+    DS_CUDA(ctx, cudaEventRecord(ctx->copyFence, ctx->stream));
+    DS_CUDA(ctx, cudaStreamWaitEvent(ctx->copyStream, ctx->copyFence, 0));
+    DS_CUDA(ctx, cudaMemcpyAsync(ctx->progressive, progressive_inout, bytes, cudaMemcpyHostToDevice, ctx->copyStream));
+    DS_CUDA(ctx, cudaMemcpyAsync(ctx->variance, variance_inout, bytes, cudaMemcpyHostToDevice, ctx->copyStream));
+    DS_CUDA(ctx, cudaEventRecord(ctx->copyDone, ctx->copyStream));
+    ctx->uploadPending = true;
+    int rc = ds_render_subframes(ctx, cam, mode, first_subframe, n);
+    if (ctx->uploadPending) { /* nothing was accumulated (n == 0 or an error): order the stream behind the upload all the same */
+        cudaStreamWaitEvent(ctx->stream, ctx->copyDone, 0);
+        ctx->uploadPending = false;
+    }
     if (rc) return rc;
     return ds_frame_download(ctx, progressive_inout, variance_inout);
 }

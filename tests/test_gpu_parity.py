@@ -628,6 +628,26 @@ def test_edge_cases_exact_bit_exact_and_fast_consistent(built_library, name):
         ctx.render_subframes(cam, 0, 1, spp)
         pf, vf = ctx.frame_download()
         c = ctx.counters()
+        # the fused RG8 {density, sun transmittance} volume against the two R8 arrays on this grid: same bits, same counters -- also after the
+        # sun moved (the fused array is rebuilt by the next render) and after a sun-transmittance volume uploaded from the host
+        def frame_and_counters():
+            ctx.frame_clear()
+            ctx.counters_reset()
+            ctx.render_subframes(cam, 0, 1, 4)
+            cc = ctx.counters()
+            return ctx.frame_download()[0].view(np.uint32), (cc["paths"], cc["events"], cc["steps"])
+
+        for step in range(3):
+            if step == 1:
+                ctx.scene_set(size_m, (sun[2], sun[0], sun[1]))
+                ctx.bake()
+            if step == 2:
+                ctx.inscatter_set(np.ascontiguousarray(o.inscatter()[::-1]))
+            ctx.set_option("fused_volume", 1)
+            f1, c1 = frame_and_counters()
+            ctx.set_option("fused_volume", 0)
+            f0, c0 = frame_and_counters()
+            assert np.array_equal(f1, f0) and c1 == c0, (name, step)
     assert c["nonfinite"] == 0 and np.isfinite(pf).all() and c["paths"] == w * h * spp
     a, b = pf[..., 0].astype(np.float64), rp[..., 0].astype(np.float64)
     sigma = np.sqrt((vf[..., 0].astype(np.float64) + rv[..., 0].astype(np.float64)) / (spp - 1) / spp)
