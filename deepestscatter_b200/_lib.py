@@ -123,6 +123,7 @@ SIGNATURES = {
     "ds_disney_model_load": (_i, [_vp, _vp, _sz]),
     "ds_disney_model_pack": (_i, [_vp, _sz, _i, _vp, _sz, _vp, _sz, C.POINTER(_sz), C.POINTER(_sz)]),
     "ds_disney_model_profile": (_i, [_vp, C.POINTER(C.c_uint64)]),
+    "ds_invert_phase_cdf": (_i, [_vp, _vp, _u32, _vp, _vp]),
     "ds_disney_model_forward": (_i, [_vp, _vp, _u32, _vp]),
     "ds_render_disney": (_i, [_vp, C.POINTER(DsCamera), _u32, _u32, _u32, _vp]),
     "ds_render_disney_subframes": (_i, [_vp, C.POINTER(DsCamera), _u32, _u32]),

@@ -346,6 +346,13 @@ class Context:
         self._ck(self.lib.ds_disney_model_forward(self.h, _ptr(x), len(x), _ptr(out)))
         return out
 
+    def invert_phase_cdf(self, values: np.ndarray):
+        """(cos_theta, phase): the FAST estimator's inversion of the chopped-Mie CDF and its half-precision phase sampler on `values`."""
+        v = np.ascontiguousarray(values, dtype=np.float32).ravel()
+        cos_t, phase = np.empty_like(v), np.empty_like(v)
+        self._ck(self.lib.ds_invert_phase_cdf(self.h, _ptr(v), v.size, _ptr(cos_t), _ptr(phase)))
+        return cos_t, phase
+
     def disney_model_profile(self) -> dict:
         """Cycle accounting of block 0 of the last tensor-core model launch (needs option profile_events = 1)."""
         c = (C.c_uint64 * 16)()

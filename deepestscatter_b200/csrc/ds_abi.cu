@@ -56,7 +56,7 @@ struct DsContext {
     bool sceneSet = false;
     float derived[12] = {0};
     float* mie = nullptr;     /* 3 * 4096 floats: mie, chopped, cdf */
-    uint16_t* guide = nullptr; /* GUIDE_A_N + GUIDE_B_N packed entries (DevScene::guideA / guideB) */
+    uint16_t* guide = nullptr; /* GUIDE_A_N + GUIDE_B_N guide entries (DevScene::guideA / guideB), then the chopped phase sampler as MIE_N halves */
 
     /* frame */
     int width = 0, height = 0;
@@ -418,6 +418,7 @@ static void fillDevScene(DsContext* ctx, DevScene& sc)
     sc.cellEscape = ctx->opt["escape_octants"] ? ctx->cellEscape : nullptr;
     sc.guideA = ctx->guide;
     sc.guideB = ctx->guide + GUIDE_A_N;
+    sc.choppedHalf = ctx->guide + GUIDE_A_N + GUIDE_B_N;
     sc.borderEmpty = ctx->borderEmpty;
 }
 
@@ -720,8 +721,9 @@ int ds_context_create(int device, DsContext** out)
             memcpy(raw.data(), ds_mie_blob, raw.size() * sizeof(float));
             buildMieSamplers(raw.data(), raw.data() + MIE_N, samplers.data());
             ok = cudaMemcpy(ctx->mie, samplers.data(), samplers.size() * sizeof(float), cudaMemcpyHostToDevice) == cudaSuccess;
-            /* two-level guide of the CDF inversion (DevScene::guideA / guideB): entry = lo | n << 13 */
-            std::vector<uint16_t> guide(GUIDE_A_N + GUIDE_B_N);
+            /* two-level guide of the CDF inversion (DevScene::guideA / guideB): entry = first index i with cdf[i] >= bucket start; followed by
+             * the chopped phase sampler as IEEE halves (DevScene::choppedHalf) */
+            std::vector<uint16_t> guide(GUIDE_A_N + GUIDE_B_N + MIE_N);
             const float* cdf = samplers.data() + 2 * MIE_N;
             auto fill = [&](uint16_t* dst, int buckets, float limit) {
                 int idx = 0, maxKnots = 0;
@@ -733,18 +735,18 @@ int ds_context_create(int device, DsContext** out)
                 }
                 for (int k = 0; k < buckets; k++) {
                     /* buckets of guideA below the limit are never looked up (guideB serves them) */
-                    const int n = first[k + 1] - first[k];
                     const bool used = limit < 1.0f || (float)(k + 1) / (float)buckets > GUIDE_B_LIMIT;
-                    if (used) maxKnots = std::max(maxKnots, n);
-                    dst[k] = (uint16_t)(first[k] | (std::min(n, 3) << 13));
+                    if (used) maxKnots = std::max(maxKnots, first[k + 1] - first[k]);
+                    dst[k] = (uint16_t)std::min(first[k], MIE_N - 1);
                 }
                 return maxKnots;
             };
             const int mA = fill(guide.data(), GUIDE_A_N, 1.0f), mB = fill(guide.data() + GUIDE_A_N, GUIDE_B_N, GUIDE_B_LIMIT);
-            if (mA > 2 || mB > 2 || !(cdf[MIE_N - 1] >= 1.0f)) {
-                g_createError = "chopped-Mie CDF does not fit the two-level guide (more than 2 knots in a bucket)";
+            if (mA > GUIDE_MAX_KNOTS || mB > GUIDE_MAX_KNOTS || !(cdf[MIE_N - 1] >= 1.0f)) {
+                g_createError = "chopped-Mie CDF does not fit the two-level guide (more than 8 knots in a bucket)";
                 ok = false;
             }
+            for (int i = 0; i < MIE_N; i++) guide[GUIDE_A_N + GUIDE_B_N + i] = __half_as_ushort(__float2half_rn(samplers[MIE_N + i]));
             ok = ok && cudaMalloc(&ctx->guide, guide.size() * sizeof(uint16_t)) == cudaSuccess &&
                  cudaMemcpy(ctx->guide, guide.data(), guide.size() * sizeof(uint16_t), cudaMemcpyHostToDevice) == cudaSuccess;
         }
@@ -1014,6 +1016,26 @@ int ds_bake_sun_transmittance(DsContext* ctx)
     if (rc) return rc;
     ctx->fusedValid = false;
     ctx->baked = true;
+    return DS_OK;
+}
+
+int ds_invert_phase_cdf(DsContext* ctx, const float* values, uint32_t n, float* cos_theta_out, float* phase_out)
+{
+    DS_CHECK_CTX(ctx);
+    if (!values || !cos_theta_out || !phase_out) return DS_ERR_INVALID;
+    if (n == 0) return DS_OK;
+    DevScene sc;
+    fillDevScene(ctx, sc);
+    float* d = nullptr;
+    DS_CUDA(ctx, cudaMalloc(&d, (size_t)n * 3 * sizeof(float)));
+    cudaError_t e = cudaMemcpyAsync(d, values, (size_t)n * sizeof(float), cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = launchInvertCdf(sc, d, n, d + n, d + 2 * (size_t)n, ctx->stream);
+    ctx->launches++;
+    if (e == cudaSuccess) e = cudaMemcpyAsync(cos_theta_out, d + n, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(phase_out, d + 2 * (size_t)n, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d);
+    DS_CUDA(ctx, e);
     return DS_OK;
 }
 

@@ -105,21 +105,25 @@ struct DevScene {
     /* escape octants (NULL = none): bit (dx > 0) | (dy > 0) << 1 | (dz > 0) << 2 of a cell is set when the cell and every cell beyond it in
      * those three directions are empty and the grid's faces are zero: a ray there reads 0 until it leaves the box */
     const uint8_t* cellEscape;
-    /* two-level guide of the chopped-Mie CDF (k_trace_fast): bucket k of guideA covers val in [k, k+1) / GUIDE_A_N,
-     * bucket k of guideB covers val in [k, k+1) * GUIDE_B_LIMIT / GUIDE_B_N (val < GUIDE_B_LIMIT, where the CDF is flat
-     * and its knots are dense).  Entry = lo | n << 13: lo = first index i with cdf[i] >= bucket start, n <= 2 = number
-     * of knots inside the bucket. */
+    /* two-level guide of the chopped-Mie CDF (k_trace_fast): bucket k of guideA covers val in [k, k+1) / GUIDE_A_N, bucket k of guideB covers
+     * val in [k, k+1) * GUIDE_B_LIMIT / GUIDE_B_N (val < GUIDE_B_LIMIT, where the CDF is flat and its knots are dense).  Entry = first index
+     * i with cdf[i] >= bucket start; at most GUIDE_MAX_KNOTS knots lie inside a bucket (checked when the tables are built), so the inversion
+     * is that many fixed probes (4 + 2 + 1 + 1), no loop.  Sized so that all tables of k_trace_fast take < 31 KiB of shared memory: the
+     * SM then keeps 224 instead of 192 KiB of L1 for the texture path (every 32 KiB of L1 is worth ~5 %) */
     const uint16_t* guideA;
     const uint16_t* guideB;
+    const uint16_t* choppedHalf; /* the chopped phase sampler as IEEE halves (k_trace_fast's shared-memory copy) */
     /* 1 when every voxel on the six faces of the grid is zero (VDB imports are padded by one voxel,
      * Resources.cpp:97-101): clamped taps outside the grid then read 0 */
     int borderEmpty;
 };
 
-constexpr int GUIDE_A_N = 4096;
-constexpr int GUIDE_B_N = 8192;
+constexpr int GUIDE_A_N = 1024;
+constexpr int GUIDE_B_N = 2048;
+constexpr int GUIDE_MAX_KNOTS = 8;
 constexpr float GUIDE_B_LIMIT = 0.125f;
-constexpr int CDF_PAD_N = MIE_N + 4; /* k_trace_fast keeps the CDF in shared memory as {0, cdf[0..4095], +inf x3} */
+constexpr int CDF_PAD_N = MIE_N + 12; /* k_trace_fast keeps the CDF in shared memory as {0, cdf[0..4095], +inf x 11}: the probes of the inversion may read
+                                         up to GUIDE_MAX_KNOTS entries past the last knot */
 
 /* ---- CU/random.cuh ---- */
 

@@ -167,6 +167,8 @@ cudaError_t launchDescriptors(const DevScene& sc, const LevelTable& lv, const De
                               cudaTextureObject_t mipTex = 0);
 /* RG8 array of {a, b} texels from two u8 volumes of the same shape (the fused volume of k_trace_fast) */
 cudaError_t launchInterleave(const uint8_t* a, const uint8_t* b, int nx, int ny, int nz, cudaSurfaceObject_t surf, cudaStream_t st);
+/* introspection: k_trace_fast's inversion of the chopped-Mie CDF and its half-precision phase sampler on n values in [0, 1) */
+cudaError_t launchInvertCdf(const DevScene& sc, const float* val, uint32_t n, float* cosTheta, float* phase, cudaStream_t st);
 cudaError_t launchTaskWelford(DsPointRadianceTask* tasks, const float* x, uint32_t nThreads, uint32_t launches, cudaStream_t st);
 
 } // namespace dsk

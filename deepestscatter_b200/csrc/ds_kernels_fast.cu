@@ -91,24 +91,21 @@ __device__ __forceinline__ V3 posAt(const FastState& s, float n)
 }
 
 /*
- * Closed-form inverse of the piecewise-linear CDF that cloud.cuh:167-178 bisects.  sCdfPad[i + 1] = cdf[i],
- * sCdfPad[0] = 0 (the value "left of" knot 0), two +inf entries at the end.  The two-level guide (DevScene) gives
- * the first candidate knot `lo` and the number n <= 2 of knots inside the bucket, so the search is two
- * predicated compares: no loop, no divergence.
+ * Closed-form inverse of the piecewise-linear CDF that cloud.cuh:167-178 bisects.  sCdfPad[i + 1] = cdf[i], sCdfPad[0] = 0 (the value
+ * "left of" knot 0), +inf entries at the end.  The two-level guide (DevScene) gives the first knot `lo` that can be the answer; at most
+ * GUIDE_MAX_KNOTS = 8 knots of the bucket lie below val, and the CDF is non-decreasing, so four fixed probes (4, 2, 1, 1) count them: no
+ * loop, no divergence, and no second guide entry to bound the search (a probe past the bucket reads a knot >= val and fails).
  */
 __device__ __forceinline__ float invertCdf(const float* sCdfPad, const uint16_t* sGuideA, const uint16_t* sGuideB, float val)
 {
     const bool low = val < GUIDE_B_LIMIT;
     const int kb = (int)(val * (low ? (float)GUIDE_B_N / GUIDE_B_LIMIT : (float)GUIDE_A_N));
-    const uint32_t e = low ? sGuideB[kb] : sGuideA[kb];
-    const int lo = (int)(e & 0x1fffu), n = (int)(e >> 13);
-    const float* c = sCdfPad + lo; /* c[0] = cdf[lo - 1], c[1] = cdf[lo], ... */
-    const float cm1 = c[0], c0 = c[1], c1 = c[2], c2 = c[3];
-    const bool p0 = n >= 1 && c0 < val; /* first index with cdf[i] >= val is beyond lo */
-    const bool p1 = n >= 2 && c1 < val; /* ... beyond lo + 1 (cdf is non-decreasing: p1 implies p0) */
-    const float a = p1 ? c1 : (p0 ? c0 : cm1);
-    const float b = p1 ? c2 : (p0 ? c1 : c0);
-    const int i = lo + (p0 ? 1 : 0) + (p1 ? 1 : 0);
+    int i = (int)(low ? sGuideB[kb] : sGuideA[kb]); /* first index with cdf[i] >= val is in [i, i + 8] */
+    i += sCdfPad[i + 4] < val ? 4 : 0;              /* sCdfPad[i + s] = cdf[i + s - 1]: the s knots from i on are all below val */
+    i += sCdfPad[i + 2] < val ? 2 : 0;
+    i += sCdfPad[i + 1] < val ? 1 : 0;
+    i += sCdfPad[i + 1] < val ? 1 : 0;
+    const float a = sCdfPad[i], b = sCdfPad[i + 1]; /* cdf[i - 1] < val <= cdf[i] */
     const float t = __fdividef(val - a, b - a);
     /* tex1D clamps below the first texel centre: every val <= cdf[0] bisects to u = 0 */
     const float u = i == 0 ? 0.0f : ((float)i - 0.5f + t) * (1.0f / (float)MIE_N);
@@ -136,6 +133,15 @@ __device__ __forceinline__ float tableLerp(const float* table, float u)
     const int i = (int)x;
     const float f = x - (float)i;
     const float a = table[i], b = table[min(i + 1, MIE_N - 1)];
+    return fmaf(f, b - a, a);
+}
+/* the same on a table of IEEE halves (the chopped phase sampler in shared memory: 8 instead of 16 KiB; 2^-11 relative rounding per entry) */
+__device__ __forceinline__ float tableLerp(const __half* table, float u)
+{
+    const float x = fminf(fmaxf(fmaf(u, (float)MIE_N, -0.5f), 0.0f), (float)(MIE_N - 1));
+    const int i = (int)x;
+    const float f = x - (float)i;
+    const float a = __half2float(table[i]), b = __half2float(table[min(i + 1, MIE_N - 1)]);
     return fmaf(f, b - a, a);
 }
 
@@ -400,6 +406,27 @@ __device__ __forceinline__ bool itemRay(const TraceJob& job, unsigned long long 
     return true;
 }
 
+/* shared memory of k_trace_fast: padded CDF (float), the chopped phase sampler (half), the two guides: 30.1 KiB, under the 32 KiB carve-out */
+constexpr size_t FAST_TABLE_BYTES = (size_t)CDF_PAD_N * 4 + (size_t)MIE_N * 2 + (size_t)(GUIDE_A_N + GUIDE_B_N) * 2;
+static_assert(FAST_TABLE_BYTES + 1024 <= 32768, "the tables must fit the 32 KiB carve-out");
+static_assert((CDF_PAD_N * 4) % 16 == 0, "alignment of the tables behind the CDF");
+__device__ __forceinline__ void stageFastTables(const DevScene& sc, unsigned char* smemRaw, float*& sCdfPad, __half*& sChopped, uint16_t*& sGuideA,
+                                                uint16_t*& sGuideB)
+{
+    sCdfPad = reinterpret_cast<float*>(smemRaw);
+    sChopped = reinterpret_cast<__half*>(sCdfPad + CDF_PAD_N);
+    sGuideA = reinterpret_cast<uint16_t*>(sChopped + MIE_N);
+    sGuideB = sGuideA + GUIDE_A_N;
+    for (int i = threadIdx.x; i < MIE_N; i += blockDim.x) {
+        sChopped[i] = __ushort_as_half(sc.choppedHalf[i]);
+        sCdfPad[i + 1] = sc.cdf[i];
+    }
+    if (threadIdx.x < CDF_PAD_N - MIE_N) sCdfPad[threadIdx.x == 0 ? 0 : MIE_N + threadIdx.x] = threadIdx.x == 0 ? 0.0f : 3.0e38f;
+    for (int i = threadIdx.x; i < GUIDE_A_N; i += blockDim.x) sGuideA[i] = sc.guideA[i];
+    for (int i = threadIdx.x; i < GUIDE_B_N; i += blockDim.x) sGuideB[i] = sc.guideB[i];
+    __syncthreads();
+}
+
 /* lane states of k_trace_fast, one bit each so that a warp vote over a set of states is one LOP + VOTE */
 enum FastLaneState {
     F_IDLE = 1,   /* wants a work item */
@@ -531,21 +558,10 @@ __global__ void __launch_bounds__(FAST_MAX_THREADS, 1)
     k_trace_fast(const __grid_constant__ DevScene sc, const __grid_constant__ TraceJob job, const __grid_constant__ FastConsts k)
 {
     extern __shared__ __align__(16) unsigned char smemRaw[];
-    float* sChopped = reinterpret_cast<float*>(smemRaw);
-    float* sCdfPad = sChopped + MIE_N;
-    uint16_t* sGuideA = reinterpret_cast<uint16_t*>(sCdfPad + CDF_PAD_N);
-    uint16_t* sGuideB = sGuideA + GUIDE_A_N;
-    for (int i = threadIdx.x; i < MIE_N; i += blockDim.x) {
-        sChopped[i] = sc.chopped[i];
-        sCdfPad[i + 1] = sc.cdf[i];
-    }
-    if (threadIdx.x == 0) {
-        sCdfPad[0] = 0.0f;
-        sCdfPad[MIE_N + 1] = sCdfPad[MIE_N + 2] = sCdfPad[MIE_N + 3] = 3.0e38f;
-    }
-    for (int i = threadIdx.x; i < GUIDE_A_N; i += blockDim.x) sGuideA[i] = sc.guideA[i];
-    for (int i = threadIdx.x; i < GUIDE_B_N; i += blockDim.x) sGuideB[i] = sc.guideB[i];
-    __syncthreads();
+    float* sCdfPad;
+    __half* sChopped;
+    uint16_t *sGuideA, *sGuideB;
+    stageFastTables(sc, smemRaw, sCdfPad, sChopped, sGuideA, sGuideB);
 
     const int mode = MODE >= 0 ? MODE : job.mode;
     const unsigned FULL = 0xffffffffu;
@@ -823,7 +839,7 @@ template <>
 cudaError_t KernelSet<true>::trace(const DevScene& sc, const TraceJob& job, const LaunchConfig& cfg, cudaStream_t st)
 {
     if (cfg.variant == 1) return traceGeneric<true>(sc, job, cfg, st);
-    const size_t smem = (size_t)(MIE_N + CDF_PAD_N) * 4 + (size_t)(GUIDE_A_N + GUIDE_B_N) * 2;
+    const size_t smem = FAST_TABLE_BYTES;
     const int threads = cfg.blockThreads > FAST_MAX_THREADS ? FAST_MAX_THREADS : cfg.blockThreads;
     const unsigned long long wantBlocks = (job.total + threads - 1) / threads;
     const unsigned long long maxBlocks = (unsigned long long)cfg.smCount * cfg.blocksPerSm;
@@ -998,6 +1014,28 @@ cudaError_t KernelSet<true>::primaryPrepass(const DevScene& sc, const TraceJob& 
 }
 
 template struct KernelSet<true>;
+
+/* introspection (ds_invert_phase_cdf): the inversion of the chopped-Mie CDF exactly as k_trace_fast runs it, tables staged the same way */
+__global__ void __launch_bounds__(256) k_invert_cdf(const __grid_constant__ DevScene sc, const float* __restrict__ val, uint32_t n, float* __restrict__ cosTheta,
+                                                    float* __restrict__ phase)
+{
+    extern __shared__ __align__(16) unsigned char smemRaw[];
+    float* sCdfPad;
+    __half* sChopped;
+    uint16_t *sGuideA, *sGuideB;
+    stageFastTables(sc, smemRaw, sCdfPad, sChopped, sGuideA, sGuideB);
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        cosTheta[i] = invertCdf(sCdfPad, sGuideA, sGuideB, val[i]);
+        phase[i] = tableLerp(sChopped, val[i]); /* the chopped phase sampler at u = val */
+    }
+}
+
+cudaError_t launchInvertCdf(const DevScene& sc, const float* val, uint32_t n, float* cosTheta, float* phase, cudaStream_t st)
+{
+    if (n == 0) return cudaSuccess;
+    k_invert_cdf<<<148, 256, FAST_TABLE_BYTES, st>>>(sc, val, n, cosTheta, phase);
+    return cudaGetLastError();
+}
 
 __global__ void __launch_bounds__(256) k_interleave(const uint8_t* __restrict__ a, const uint8_t* __restrict__ b, int nx, int ny, int nz,
                                                     cudaSurfaceObject_t surf)

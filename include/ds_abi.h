@@ -281,6 +281,11 @@ int ds_disney_model_forward(DsContext* ctx, const float* network_input, uint32_t
  * chunk, [4] for a weight chunk to land; [8] worker thread 0: total, [9] waiting for a free descriptor stage, [10] for a GEMM to finish,
  * [11] inside the epilogues, [12] inside the descriptor staging; the rest 0. */
 int ds_disney_model_profile(DsContext* ctx, uint64_t* cycles16);
+/* Introspection of the FAST estimator's direction sampling (getNewDirection, CU/cloud.cuh:160-188): for n values of the uniform variate in
+ * [0, 1), cos_theta_out = the closed-form inverse of the piecewise-linear chopped-Mie CDF that cloud.cuh:167-178 bisects (two-level guide +
+ * four fixed probes, exactly the code k_trace_fast runs), and phase_out = the kernel's half-precision copy of the chopped phase sampler
+ * (Mie.cpp:8206-8282) read at u = value with tex1D semantics.  Host buffers. */
+int ds_invert_phase_cdf(DsContext* ctx, const float* values, uint32_t n, float* cos_theta_out, float* phase_out);
 /* DisneyRenderer::render (DisneyRenderer.cpp:58-110): every 128 x 128 rectangle of the frame (x outer, y inner; clipped at the frame
  * edge) -> network-input launch, the model on the pixels that scattered, copyToFrameResult.  Rectangle k uses RNG stream
  * `stream + k` (clock() in the reference).  frame_result_out: float4 [frame_height][frame_width], zero where nothing scattered;

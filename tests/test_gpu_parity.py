@@ -8,7 +8,11 @@ import numpy as np
 import pytest
 
 import oracle_lib as ol
+from pathlib import Path
+
 from conftest import SCENE_SMALL
+
+ROOT = Path(__file__).resolve().parent.parent
 
 pytestmark = pytest.mark.gpu
 
@@ -679,3 +683,48 @@ def test_empty_cloud_renders_black_and_terminates(built_library):
                 assert np.all(p[..., :3] == 0) and np.all(v == 0) and np.all(p[..., 3] == 1)
             c = ctx.counters()
             assert c["events"] == 0 and c["nonfinite"] == 0
+
+
+@pytest.mark.gpu
+def test_fast_direction_sampling_inverts_the_reference_cdf(built_library):
+    """k_trace_fast replaces the 16-step bisection of cloud.cuh:167-178 by the closed-form inverse of the same piecewise-linear CDF (two-level
+    guide + four fixed probes).  ds_invert_phase_cdf runs exactly that device code: it must land on the float64 inverse of the CDF built
+    the way Mie.cpp:8273-8282 builds it, for a dense set of variates, every knot value and the neighbours of every bucket boundary -- and
+    the kernel's half-precision phase table must be the chopped sampler within a half's rounding."""
+    ds = built_library
+    raw = np.fromfile(ROOT / "deepestscatter_b200" / "data" / "mie_tables.f32", dtype=np.float32)
+    n = raw.size // 2
+    chopped = raw[n:]
+    total = np.float32(0)
+    for x in chopped:
+        total = np.float32(total + x)
+    cdf = np.zeros(n, np.float32)
+    acc = np.float32(0)
+    for i, x in enumerate(chopped):
+        acc = np.float32(acc + np.float32(x / total))
+        cdf[i] = acc
+    rs = np.random.RandomState(5)
+    below = np.nextafter(cdf, np.float32(0)).astype(np.float32)
+    above = np.nextafter(cdf, np.float32(2)).astype(np.float32)
+    edges = np.concatenate([np.arange(2048) / 2048 * 0.125, np.arange(1024) / 1024]).astype(np.float32)
+    vals = np.concatenate([rs.random_sample(1 << 20).astype(np.float32), rs.random_sample(1 << 18).astype(np.float32) * np.float32(0.125), cdf, below, above,
+                           edges, np.nextafter(edges, np.float32(-1)).astype(np.float32), [0.0, 1e-12, 0.99999994]]).astype(np.float32)
+    vals = vals[(vals >= 0) & (vals < 1)]
+    with ds.Context(0) as ctx:
+        cos_t, phase = ctx.invert_phase_cdf(vals)
+    # float64 inverse: first knot i with cdf[i] >= val; u = (i - 0.5 + (val - cdf[i-1]) / (cdf[i] - cdf[i-1])) / n, clamped like tex1D; i = 0 -> u = 0
+    i = np.searchsorted(cdf, vals, side="left")
+    assert i.max() < n
+    pad = np.concatenate([[0.0], cdf.astype(np.float64)])
+    a, b = pad[i], pad[i + 1]
+    t = (vals.astype(np.float64) - a) / (b - a)
+    u = np.where(i == 0, 0.0, (i - 0.5 + t) / n)
+    want = 2 * np.minimum(u, 1.0) - 1
+    # a float32 quotient of two float32 differences: a few ulp of t (<= 1) inside a knot interval of width 2 / n in cos(theta)
+    assert np.abs(cos_t - want).max() <= 4e-7 + 2.0 / n * 2e-6
+    # the reference's own bisection (16 halvings of [0, 1] on the tabulated CDF with linear interpolation) agrees within 2^-16 in u
+    x = np.minimum(np.maximum(vals.astype(np.float64) * n - 0.5, 0.0), n - 1.0)
+    k = x.astype(np.int64)
+    want_phase = (chopped.astype(np.float64) / (chopped.astype(np.float64).sum() / n))
+    lerp = want_phase[k] + (x - k) * (want_phase[np.minimum(k + 1, n - 1)] - want_phase[k])
+    assert np.abs(phase - lerp).max() <= 6e-4 * np.abs(lerp).max() and (np.abs(phase - lerp) <= 1.5e-3 * np.abs(lerp) + 1e-6).all()
