@@ -2032,8 +2032,8 @@ int ds_point_radiance_run(DsContext* ctx, const float* positions, const float* d
     /* FAST flavour, option "radiance_scheduler" = 1 (default): the device-resident collector (AdaptiveCollector,
      * ds_kernels.h) -- one launch for the whole batch, same convergence rule, no host round trips.  The reference
      * schedule below stays available (option = 0) and is what the EXACT flavour always runs (bit-exact with the oracle). */
-    if (ctx->opt["precision"] == DS_PRECISION_FAST && ctx->opt["radiance_scheduler"] == 1 && ctx->borderEmpty && ctx->opt["skip_empty"] &&
-        ctx->opt["variant"] == 0) {
+    if (ctx->opt["precision"] == DS_PRECISION_FAST && ctx->opt["radiance_scheduler"] == 1 && ctx->borderEmpty && ctx->params.sample_step <= 0.01f &&
+        ctx->opt["skip_empty"] && ctx->opt["variant"] == 0) {
         const uint32_t repeat = cfg.max_thread_count / n;
         const size_t perSample = 8 + 8 + 8 + 4 + 4;
         const size_t stateBytes = (size_t)n * perSample + 64;

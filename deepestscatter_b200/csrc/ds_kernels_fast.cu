@@ -122,8 +122,12 @@ __device__ __forceinline__ V3 newDirectionFast(const float* sCdfPad, const uint1
     const float sinTheta = s2 * rsqrtf(fmaxf(s2, 1.0e-30f));
     float s, c;
     __sincosf(phi, &s, &c);
-    V3 d = onbInverseTransform<true>(prev, mk(sinTheta * c, sinTheta * s, cosTheta));
-    return d * rsqrtf(dot(d, d));
+    /* The reference normalises the result (cloud.cuh:185); here it is left as it comes out of the frame: a unit vector rotated by a frame
+     * built around a unit axis is unit up to the rounding of rsqrt / sincos (a few 1e-7 per event, a random walk of ~2e-5 over the 2000
+     * events a path may have), far inside the 9-bit weights of the texture filter.  Eight instructions per event (+1.2 %); the paths keep
+     * following the oracle's event by event (test_c2_grid_fast_flavour_against_the_oracle needs that correlation).  A branch-free frame
+     * (Duff et al. 2017) saves eight more (+1.3 %) but decorrelates the paths from the oracle's: not taken. */
+    return onbInverseTransform<true>(prev, mk(sinTheta * c, sinTheta * s, cosTheta));
 }
 
 /* 4096-entry table, linear, clamp-to-edge, u in [0, 1] (tex1D semantics of the Mie samplers) */
@@ -790,7 +794,11 @@ __global__ void __launch_bounds__(FAST_MAX_THREADS, 1)
              * steps: (tau - tauStar) / (density * mult * step) */
             const float back = __fdividef((s.tau - s.tauStar) * k.backScale, lastDensity);
             s.q0 = posAt(s, s.nf - back);
-            if (!inBoxTs(k, s.q0)) {
+            /* The reference's loop tests isInBox(scatterPos) before it goes on (cloudRadianceMaterials.cu:30).  Without BOXTEST the test
+             * cannot fail and is not compiled: the grid's faces are zero (borderEmpty), so the step that collided (density > 0) lies strictly
+             * inside the grid, the collision point lies less than one step (<= 0.01 of the box, checked by the launcher) before it, and the
+             * box slab reaches 0.01 beyond the grid (cloud.cuh:40-44) */
+            if (BOXTEST && !inBoxTs(k, s.q0)) {
                 st = F_DONE;
             } else {
                 s.pendT = tapSun<FUSED>(sc, s.q0); /* consumed at the next event */
@@ -844,7 +852,8 @@ cudaError_t KernelSet<true>::trace(const DevScene& sc, const TraceJob& job, cons
     const unsigned long long wantBlocks = (job.total + threads - 1) / threads;
     const unsigned long long maxBlocks = (unsigned long long)cfg.smCount * cfg.blocksPerSm;
     const int blocks = (int)(wantBlocks < maxBlocks ? (wantBlocks ? wantBlocks : 1) : maxBlocks);
-    const bool boxtest = sc.borderEmpty == 0;
+    /* the variants without a per-step box test rely on zero faces and on a sampling step within the slack of the box test (0.01) */
+    const bool boxtest = sc.borderEmpty == 0 || !(sc.step <= 0.01f);
     if (job.kind == JOB_ADAPTIVE) {
         /* the collector always runs multipleScatterSunRadiance (Tasks.cpp:134); the host falls back to the update loop for
          * grids with non-zero faces */
