@@ -432,18 +432,26 @@ __device__ __forceinline__ void stageFastTables(const DevScene& sc, unsigned cha
 }
 
 /* lane states of k_trace_fast, one bit each so that a warp vote over a set of states is one LOP + VOTE */
-enum FastLaneState {
-    F_IDLE = 1,   /* wants a work item */
-    F_SKIP = 2,   /* the tap at the current position fell into an empty cell */
-    F_MARCH = 4,  /* marching */
-    F_EVENT = 8,  /* collided: next-event estimate + new direction pending */
-    F_DONE = 16,  /* path ended, sample not yet written */
-    F_OFF = 32    /* idle and the queue is exhausted */
+enum FastLaneState : unsigned {
+    /* one identity bit each (bits 24-29), plus a 1 in the byte that counts the lane's class: byte 0 = wants work (idle / done), byte 1 = waits
+     * for the empty-space phase, byte 2 = busy (marching / event pending).  One warp-wide integer add over st & 0xffffff then gives the three
+     * lane counts every phase decision of a round needs -- one REDUX instead of three votes and three population counts */
+    F_IDLE = 0x01000001u,  /* wants a work item */
+    F_SKIP = 0x02000100u,  /* the tap at the current position fell into an empty cell */
+    F_MARCH = 0x04010000u, /* marching */
+    F_EVENT = 0x08010000u, /* collided: next-event estimate + new direction pending */
+    F_DONE = 0x10000001u,  /* path ended, sample not yet written */
+    F_OFF = 0x20000000u    /* idle and the queue is exhausted */
 };
+/* lane counts of a warp: {free, skip, busy} in bytes 0, 1, 2 */
+__device__ __forceinline__ unsigned laneCounts(unsigned st) { return __reduce_add_sync(0xffffffffu, st & 0x00ffffffu); }
+#define DS_N_FREE(c) ((c) & 0xffu)
+#define DS_N_SKIP(c) (((c) >> 8) & 0xffu)
+#define DS_N_BUSY(c) ((c) >> 16)
 
 /* start of the path of one radiance ray (closest-hit entry, cloudRadianceMaterials.cu:9-27 / 72-90) */
 template <int MODE>
-__device__ __forceinline__ int beginPathFast(const DevScene& sc, const FastConsts& k, const TraceJob& job, const float* sCdfPad, const uint16_t* sGuideA,
+__device__ __forceinline__ unsigned beginPathFast(const DevScene& sc, const FastConsts& k, const TraceJob& job, const float* sCdfPad, const uint16_t* sGuideA,
                                              const uint16_t* sGuideB, V3 o, V3 d, uint32_t val0, uint32_t stream, FastState& s)
 {
     s.rad = s.pendT = s.pendP = 0.0f;
@@ -463,14 +471,14 @@ __device__ __forceinline__ int beginPathFast(const DevScene& sc, const FastConst
 }
 
 template <int MODE>
-__device__ __forceinline__ int beginItemFast(const DevScene& sc, const FastConsts& k, const TraceJob& job, const float* sCdfPad,
+__device__ __forceinline__ unsigned beginItemFast(const DevScene& sc, const FastConsts& k, const TraceJob& job, const float* sCdfPad,
                                              const uint16_t* sGuideA, const uint16_t* sGuideB, unsigned long long idx, FastState& s, bool& valid)
 {
     V3 o, d;
     uint32_t val0, stream, pixel;
     valid = itemRay(job, idx, o, d, val0, stream, s.out, pixel);
     if (!valid) return F_IDLE;
-    const int st = beginPathFast<MODE>(sc, k, job, sCdfPad, sGuideA, sGuideB, o, d, val0, stream, s);
+    const unsigned st = beginPathFast<MODE>(sc, k, job, sCdfPad, sGuideA, sGuideB, o, d, val0, stream, s);
     /* cached empty-space leg of the primary ray: the first taps that can be non-zero follow step entrySteps[pixel] */
     if (st == F_MARCH && job.kind == JOB_RENDER && job.entrySteps) s.nf = (float)job.entrySteps[pixel];
     return st;
@@ -578,7 +586,7 @@ __global__ void __launch_bounds__(FAST_MAX_THREADS, 1)
     s.seed = 0;
     s.depth = 0;
     s.out = 0;
-    int st = F_IDLE;
+    unsigned st = F_IDLE;
     uint32_t nPaths = 0, nEvents = 0, nSteps = 0, nTaps = 0;
     float lastDensity = 0.0f;
     /* PIPE: every lane in F_MARCH holds the densities of its next two steps (nf + 1, nf + 2), fetched when the lane
@@ -592,12 +600,10 @@ __global__ void __launch_bounds__(FAST_MAX_THREADS, 1)
     uint32_t wSample = 0, wNext = 0, wQuota = 0; /* ADAPT: the warp's current ticket (uniform across lanes) */
 
     for (;;) {
-        unsigned mBusy = __ballot_sync(FULL, (st & (F_MARCH | F_EVENT)) != 0);
-        unsigned mSkip = __ballot_sync(FULL, (st & F_SKIP) != 0);
-        unsigned mFree = __ballot_sync(FULL, (st & (F_IDLE | F_DONE)) != 0);
+        unsigned cnt = laneCounts(st);
 
         /* ---- A: retire + regenerate ---- */
-        if (ADAPT && mFree && (__popc(mFree) >= job.regenMin || (mBusy == 0u && (mSkip == 0u || __popc(mSkip) < job.skipMin)))) {
+        if (ADAPT && DS_N_FREE(cnt) && ((int)DS_N_FREE(cnt) >= job.regenMin || (DS_N_BUSY(cnt) == 0u && (int)DS_N_SKIP(cnt) < max(job.skipMin, 1)))) {
             /* retire: finished paths are summed per sample (lanes of a warp mostly share one) and committed by one lane */
             const bool isDone = st == F_DONE;
             unsigned rem = __ballot_sync(FULL, isDone);
@@ -657,11 +663,9 @@ __global__ void __launch_bounds__(FAST_MAX_THREADS, 1)
                 wNext += take;
                 wQuota -= take;
             }
-            mFree = __ballot_sync(FULL, (st & (F_IDLE | F_DONE)) != 0);
-            mSkip = __ballot_sync(FULL, (st & F_SKIP) != 0);
-            mBusy = __ballot_sync(FULL, (st & (F_MARCH | F_EVENT)) != 0);
+            cnt = laneCounts(st);
         }
-        if (!ADAPT && mFree && (__popc(mFree) >= job.regenMin || (mBusy == 0u && (mSkip == 0u || __popc(mSkip) < job.skipMin)))) {
+        if (!ADAPT && DS_N_FREE(cnt) && ((int)DS_N_FREE(cnt) >= job.regenMin || (DS_N_BUSY(cnt) == 0u && (int)DS_N_SKIP(cnt) < max(job.skipMin, 1)))) {
 #pragma unroll 1
             for (int r = 0; r < 4; ++r) {
                 if (st == F_DONE) {
@@ -685,16 +689,14 @@ __global__ void __launch_bounds__(FAST_MAX_THREADS, 1)
                         if (PIPE && st == F_MARCH) DS_ISSUE_TAPS(s.nf, 0.0f);
                     }
                 }
-                mFree = __ballot_sync(FULL, (st & (F_IDLE | F_DONE)) != 0);
-                if (__popc(mFree) < job.regenMin) break;
+                cnt = laneCounts(st);
+                if ((int)DS_N_FREE(cnt) < job.regenMin) break;
             }
-            mSkip = __ballot_sync(FULL, (st & F_SKIP) != 0);
-            mBusy = __ballot_sync(FULL, (st & (F_MARCH | F_EVENT)) != 0);
         }
-        if ((mBusy | mSkip | mFree) == 0u) break; /* every lane off: the queue is exhausted */
+        if (cnt == 0u) break; /* every lane off: the queue is exhausted */
 
         /* ---- B: empty-space phase: the tap at the current position fell into an empty cell ---- */
-        if (SKIP && mSkip && (__popc(mSkip) >= job.skipMin || mBusy == 0u)) {
+        if (SKIP && DS_N_SKIP(cnt) && ((int)DS_N_SKIP(cnt) >= job.skipMin || DS_N_BUSY(cnt) == 0u)) {
             if (st == F_SKIP) {
                 bool more, leaves;
                 const float kf = emptySteps(sc, k, posAt(s, s.nf), s.sv, job.skipMaxIters, more, leaves);
@@ -713,12 +715,13 @@ __global__ void __launch_bounds__(FAST_MAX_THREADS, 1)
                     if (PIPE && st == F_MARCH) DS_ISSUE_TAPS(s.nf, 0.0f);
                 }
             }
-            mBusy = __ballot_sync(FULL, (st & (F_MARCH | F_EVENT)) != 0);
+            cnt = laneCounts(st);
         }
 
         /* ---- C: march phase (CU/cloud.cuh:87-104) ---- */
-        if (mBusy) {
-            const int keep = (__popc(mBusy) * job.marchKeep32) >> 5; /* leave when at most this many lanes still march */
+        if (DS_N_BUSY(cnt)) {
+            const int keep = ((int)DS_N_BUSY(cnt) * job.marchKeep32) >> 5; /* leave when at most this many lanes still march */
+            unsigned mMarch = 0;
 #pragma unroll 1
             for (int it = 0; it < job.marchMaxIters; it += UNROLL) {
                 if (PIPE) {
@@ -754,19 +757,17 @@ __global__ void __launch_bounds__(FAST_MAX_THREADS, 1)
                         }
                     }
                 }
-                if (__popc(__ballot_sync(FULL, st == F_MARCH)) <= keep) break;
+                mMarch = __ballot_sync(FULL, st == F_MARCH);
+                if (__popc(mMarch) <= keep) break;
             }
 
             /* once per round: lanes whose last tap read 0 */
             /* (with zeroCheckMin > 1 the look is postponed until that many lanes wait, but never beyond 4 rounds and
              * never when every marching lane waits: a lane past the cloud only wastes zero taps meanwhile) */
             const bool zero = st == F_MARCH && lastDensity == 0.0f;
-            bool look = job.zeroCheckMin <= 1 || (++roundIdx & 3u) == 0u;
-            if (!look) {
-                const int nZero = __popc(__ballot_sync(FULL, zero));
-                look = nZero >= job.zeroCheckMin || (nZero > 0 && nZero == __popc(__ballot_sync(FULL, st == F_MARCH)));
-            }
-            if (look) {
+            const unsigned mZero = __ballot_sync(FULL, zero);
+            /* mMarch is the vote that ended the loop: the lanes still marching */
+            if (mZero && (__popc(mZero) >= job.zeroCheckMin || mZero == mMarch || (++roundIdx & 3u) == 0u)) {
                 if (zero) {
                     const V3 q = posAt(s, s.nf);
                     if (!BOXTEST && !inBoxTs(k, q)) {
