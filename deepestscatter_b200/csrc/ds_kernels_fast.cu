@@ -298,19 +298,16 @@ __device__ __forceinline__ float emptySteps(const DevScene& sc, const FastConsts
     const bool mx = fabsf(vx) > 1e-9f, my = fabsf(vy) > 1e-9f, mz = fabsf(vz) > 1e-9f;
     const float ix = mx ? __fdividef(1.0f, vx) : 0.0f, iy = my ? __fdividef(1.0f, vy) : 0.0f, iz = mz ? __fdividef(1.0f, vz) : 0.0f;
     const bool px = vx > 0.0f, py = vy > 0.0f, pz = vz > 0.0f;
-    /* the walk stays where floor(x) <= N-2, i.e. inside the region the test above calls "inside the grid" */
-    const float gx = px ? k.nxf - 1.0f : 0.0f, gy = py ? k.nyf - 1.0f : 0.0f, gz = pz ? k.nzf - 1.0f : 0.0f;
+    /* A cube that reaches beyond the grid is empty there as well: taps outside the grid read the face voxels of cells the cube covers
+     * (clamp addressing).  So the exit planes need no clamping to the grid; the walk has left the grid when the cell it would enter does
+     * not exist. */
     float t = 0.0f, margin = 0.0f;
     bool leftGrid = false, blocked = false;
 #pragma unroll 1
     for (int it = 0; it < maxLeaps; ++it) {
         const int r = dist - 1; /* cells [c-r, c+r]^3 are empty */
-        /* exit planes of the cube along the direction of travel, clamped to the grid */
-        float ex = (float)(px ? cx + r + 1 : cx - r) * cs, ey = (float)(py ? cy + r + 1 : cy - r) * cs, ez = (float)(pz ? cz + r + 1 : cz - r) * cs;
-        const bool cxg = px ? ex >= gx : ex <= gx, cyg = py ? ey >= gy : ey <= gy, czg = pz ? ez >= gz : ez <= gz;
-        ex = cxg ? gx : ex;
-        ey = cyg ? gy : ey;
-        ez = czg ? gz : ez;
+        /* exit planes of the cube along the direction of travel */
+        const float ex = (float)(px ? cx + r + 1 : cx - r) * cs, ey = (float)(py ? cy + r + 1 : cy - r) * cs, ez = (float)(pz ? cz + r + 1 : cz - r) * cs;
         const float tx = mx ? (ex - x) * ix : big, ty = my ? (ey - y) * iy : big, tz = mz ? (ez - z) * iz : big;
         t = fminf(tx, fminf(ty, tz));
         /* cell the ray enters: the exit axis moves one cell past the cube face, the others follow the ray */
@@ -319,20 +316,12 @@ __device__ __forceinline__ float emptySteps(const DevScene& sc, const FastConsts
         nx_ = min(max(nx_, cx - r), cx + r);
         ny_ = min(max(ny_, cy - r), cy + r);
         nz_ = min(max(nz_, cz - r), cz + r);
-        if (ax) {
-            nx_ = px ? cx + r + 1 : cx - r - 1;
-            margin = fabsf(ix);
-            leftGrid = cxg;
-        } else if (ay) {
-            ny_ = py ? cy + r + 1 : cy - r - 1;
-            margin = fabsf(iy);
-            leftGrid = cyg;
-        } else {
-            nz_ = pz ? cz + r + 1 : cz - r - 1;
-            margin = fabsf(iz);
-            leftGrid = czg;
-        }
-        leftGrid = leftGrid || (unsigned)nx_ >= (unsigned)sc.ocx || (unsigned)ny_ >= (unsigned)sc.ocy || (unsigned)nz_ >= (unsigned)sc.ocz;
+        const bool az = !ax && !ay;
+        nx_ = ax ? (px ? cx + r + 1 : cx - r - 1) : nx_;
+        ny_ = ay ? (py ? cy + r + 1 : cy - r - 1) : ny_;
+        nz_ = az ? (pz ? cz + r + 1 : cz - r - 1) : nz_;
+        margin = fabsf(ax ? ix : (ay ? iy : iz));
+        leftGrid = (unsigned)nx_ >= (unsigned)sc.ocx || (unsigned)ny_ >= (unsigned)sc.ocy || (unsigned)nz_ >= (unsigned)sc.ocz;
         if (leftGrid) break;
         cx = nx_;
         cy = ny_;
