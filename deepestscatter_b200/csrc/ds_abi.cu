@@ -125,9 +125,21 @@ static thread_local std::string g_createError;
         if (_e != cudaSuccess) DS_FAIL(ctx, DS_ERR_CUDA, "%s: %s (%s:%d)", #call, cudaGetErrorString(_e), __FILE__, __LINE__); \
     } while (0)
 
-#define DS_CHECK_CTX(ctx)          \
+/* ds_frame_upload copies on a second stream; every entry point orders the context's stream behind that copy before it does anything else --
+ * except ds_render_subframes, which defers the wait to its first accumulation kernel so that the copy runs beside the trace kernel */
+static inline void settleUpload(DsContext* ctx)
+{
+    if (ctx->uploadPending) {
+        cudaStreamWaitEvent(ctx->stream, ctx->copyDone, 0);
+        ctx->uploadPending = false;
+    }
+}
+#define DS_CHECK_CTX_DEFER(ctx)        \
     if (!(ctx)) return DS_ERR_INVALID; \
     cudaSetDevice((ctx)->device)
+#define DS_CHECK_CTX(ctx)   \
+    DS_CHECK_CTX_DEFER(ctx); \
+    settleUpload(ctx)
 
 /* With option "profile_events" on, the device time of a kernel (CUDA events on the context's stream) is published as the
  * read-only option `key` in microseconds: what bench.py's roofline legs divide the algorithmic bytes by. */
@@ -1248,7 +1260,7 @@ int ds_render_frame_result(DsContext* ctx, const DsCamera* cam, DsMode mode, uin
 
 int ds_render_subframes(DsContext* ctx, const DsCamera* cam, DsMode mode, uint32_t first_subframe, uint32_t n)
 {
-    DS_CHECK_CTX(ctx);
+    DS_CHECK_CTX_DEFER(ctx);
     int rc = checkRender(ctx, cam, mode);
     if (rc) return rc;
     if (first_subframe == 0) DS_FAIL(ctx, DS_ERR_INVALID, "subframe ids are 1-based (Camera.cpp:191)");
@@ -1260,16 +1272,17 @@ int ds_render_subframes(DsContext* ctx, const DsCamera* cam, DsMode mode, uint32
         const uint32_t chunk = std::min<uint32_t>(chunkMax, n - done);
         bool cached;
         rc = traceSubframes(ctx, cam, mode, first_subframe + done, chunk, &cached);
-        if (rc) return rc;
-        if (ctx->uploadPending) { /* the upload of ds_render_subframes_host ran beside the trace kernel; the accumulation needs it now */
-            DS_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->copyDone, 0));
-            ctx->uploadPending = false;
+        if (rc) {
+            settleUpload(ctx);
+            return rc;
         }
+        settleUpload(ctx); /* a frame upload (ds_frame_upload) ran beside the trace kernel; the accumulation needs it now */
         DS_CUDA(ctx, launchUpdateFrame(ctx->staging, cached ? ctx->entrySteps : nullptr, ctx->progressive, ctx->variance, px,
                                        first_subframe + done, chunk, ctx->stream));
         ctx->launches++;
         done += chunk;
     }
+    settleUpload(ctx);
     return DS_OK;
 }
 
@@ -1278,26 +1291,9 @@ int ds_render_subframes_host(DsContext* ctx, const DsCamera* cam, DsMode mode, u
 {
     DS_CHECK_CTX(ctx);
     if (!progressive_inout || !variance_inout) DS_FAIL(ctx, DS_ERR_INVALID, "host buffers are NULL");
-    if (!ctx->progressive) DS_FAIL(ctx, DS_ERR_STATE, "no frame (ds_frame_create)");
-    /* host -> device on a second stream, behind everything queued so far, so that it overlaps the trace kernel (which only writes the staging
-     * buffer); ds_render_subframes waits for it before the first accumulation */
-    if (!ctx->copyStream) {
-        DS_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copyStream, cudaStreamNonBlocking));
-        DS_CUDA(ctx, cudaEventCreateWithFlags(&ctx->copyFence, cudaEventDisableTiming));
-        DS_CUDA(ctx, cudaEventCreateWithFlags(&ctx->copyDone, cudaEventDisableTiming));
-    }
-    const size_t bytes = (size_t)ctx->width * ctx->height * sizeof(float4);
-    DS_CUDA(ctx, cudaEventRecord(ctx->copyFence, ctx->stream));
-    DS_CUDA(ctx, cudaStreamWaitEvent(ctx->copyStream, ctx->copyFence, 0));
-    DS_CUDA(ctx, cudaMemcpyAsync(ctx->progressive, progressive_inout, bytes, cudaMemcpyHostToDevice, ctx->copyStream));
-    DS_CUDA(ctx, cudaMemcpyAsync(ctx->variance, variance_inout, bytes, cudaMemcpyHostToDevice, ctx->copyStream));
-    DS_CUDA(ctx, cudaEventRecord(ctx->copyDone, ctx->copyStream));
-    ctx->uploadPending = true;
-    int rc = ds_render_subframes(ctx, cam, mode, first_subframe, n);
-    if (ctx->uploadPending) { /* nothing was accumulated (n == 0 or an error): order the stream behind the upload all the same */
-        cudaStreamWaitEvent(ctx->stream, ctx->copyDone, 0);
-        ctx->uploadPending = false;
-    }
+    int rc = ds_frame_upload(ctx, progressive_inout, variance_inout); /* on the copy stream: overlaps the trace kernel */
+    if (rc) return rc;
+    rc = ds_render_subframes(ctx, cam, mode, first_subframe, n);
     if (rc) return rc;
     return ds_frame_download(ctx, progressive_inout, variance_inout);
 }
@@ -1318,8 +1314,19 @@ int ds_frame_upload(DsContext* ctx, const float* progressive, const float* varia
     DS_CHECK_CTX(ctx);
     if (!ctx->progressive) DS_FAIL(ctx, DS_ERR_STATE, "no frame (ds_frame_create)");
     const size_t bytes = (size_t)ctx->width * ctx->height * sizeof(float4);
-    if (progressive) DS_CUDA(ctx, cudaMemcpyAsync(ctx->progressive, progressive, bytes, cudaMemcpyHostToDevice, ctx->stream));
-    if (variance) DS_CUDA(ctx, cudaMemcpyAsync(ctx->variance, variance, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    /* host -> device on a second stream, behind everything queued so far; the next entry point waits for it (settleUpload) -- a following
+     * ds_render_subframes only before its first accumulation, so the copy runs beside the trace kernel, which only writes the staging buffer */
+    if (!ctx->copyStream) {
+        DS_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copyStream, cudaStreamNonBlocking));
+        DS_CUDA(ctx, cudaEventCreateWithFlags(&ctx->copyFence, cudaEventDisableTiming));
+        DS_CUDA(ctx, cudaEventCreateWithFlags(&ctx->copyDone, cudaEventDisableTiming));
+    }
+    DS_CUDA(ctx, cudaEventRecord(ctx->copyFence, ctx->stream));
+    DS_CUDA(ctx, cudaStreamWaitEvent(ctx->copyStream, ctx->copyFence, 0));
+    if (progressive) DS_CUDA(ctx, cudaMemcpyAsync(ctx->progressive, progressive, bytes, cudaMemcpyHostToDevice, ctx->copyStream));
+    if (variance) DS_CUDA(ctx, cudaMemcpyAsync(ctx->variance, variance, bytes, cudaMemcpyHostToDevice, ctx->copyStream));
+    DS_CUDA(ctx, cudaEventRecord(ctx->copyDone, ctx->copyStream));
+    ctx->uploadPending = true;
     return DS_OK;
 }
 
