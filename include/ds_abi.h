@@ -121,7 +121,10 @@ int ds_context_set_stream(DsContext* ctx, void* cuda_stream);
 int ds_sync(DsContext* ctx);
 /* named integer options: "precision" (DsPrecision), "variant", "block_threads", "blocks_per_sm",
  * "skip_empty", "primary_cache", "march_keep_quarters", "march_keep32", "march_max_iters", "march_unroll", "regen_min", "skip_min",
- * "skip_max_iters", "skip_open_dist", "zero_check_min", "smem_carveout", "staging_subframes" -- tuning knobs of the estimator kernels;
+ * "skip_max_iters", "skip_open_dist", "zero_check_min", "smem_carveout", "staging_subframes", "spec_percent", "region_pixels" -- tuning knobs
+ * of the estimator kernels; "fused_volume" (FAST estimator: march through one RG8 {density, sun transmittance} array, default 1),
+ * "escape_octants" (FAST estimator: per-cell flags that end a path in empty space whose whole octant ahead is empty, default 1) -- both
+ * leave every result bit unchanged;
  * "radiance_scheduler", "radiance_quota" -- the radiance collector (0 = the reference's host schedule, 1 = device-resident);
  * "stream_offset" -- added to the subframe id to form the RNG stream id;
  * neural renderer: "mlp_bf16" / "mlp_fp16" (FAST flavour of the model on bfloat16 / IEEE half instead of tf32 operands), "descriptor_hw" (-1 = the FAST network-input passes
