@@ -19,7 +19,7 @@ def main():
     w, h, grid = 1920, 1080, 512
     if len(sys.argv) > 1:
         w, h, grid = int(sys.argv[1]), int(sys.argv[2]), int(sys.argv[3])
-    flavours = sys.argv[4].split(",") if len(sys.argv) > 4 else ["fast", "fast_fp16", "fast_bf16", "exact"]
+    flavours = sys.argv[4].split(",") if len(sys.argv) > 4 else ["fast", "fast_tf32", "fast_bf16", "exact"]
     cam = ds.camera_look_at(aspect=w / h)
     with ds.Context(0) as ctx:
         ctx.volume_synth(grid, 0, 1234, True)
@@ -28,7 +28,7 @@ def main():
         for name in flavours:
             ctx.set_option("precision", ds.PRECISION_EXACT if name == "exact" else ds.PRECISION_FAST)
             ctx.set_option("mlp_bf16", 1 if name == "fast_bf16" else 0)
-            ctx.set_option("mlp_fp16", 1 if name == "fast_fp16" else 0)
+            ctx.set_option("mlp_fp16", 0 if name == "fast_tf32" else 1)  # IEEE half operands are the default
             ctx.bake()
             ctx.sync()
             times = []
