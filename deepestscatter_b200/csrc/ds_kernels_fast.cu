@@ -258,8 +258,8 @@ __device__ __forceinline__ float outsideGridSteps(const FastConsts& k, V3 q, V3 
         }
     }
     if (tn < tf && tf > 0.0f) return fmaxf(floorf(fminf(tn - 0.01f * margin, 65535.0f)), 0.0f); /* enters the grid */
-    leaves = true;
-    return stepsToLeaveBox(k, q, sv);
+    leaves = true; /* never enters the grid: the caller adds the steps to the box exit (stepsToLeaveBox) */
+    return 0.0f;
 }
 
 /*
@@ -275,7 +275,8 @@ __device__ __forceinline__ float outsideGridSteps(const FastConsts& k, V3 q, V3 
 __device__ __forceinline__ float emptySteps(const DevScene& sc, const FastConsts& k, V3 q, V3 sv, int maxLeaps, bool& more, bool& leaves)
 {
     more = false;
-    leaves = false; /* set when every tap from here to the box exit reads 0: the returned count then reaches (about) the exit */
+    leaves = false; /* set when every tap from here to the box exit reads 0: the caller then takes stepsToLeaveBox(k, q, sv) steps (kept out of
+                       this function so that its code exists once per call site, not once per way of leaving) */
     const float x = fmaf(q.x, k.nxf, -0.5f), y = fmaf(q.y, k.nyf, -0.5f), z = fmaf(q.z, k.nzf, -0.5f);
     const int fx = __float2int_rd(x), fy = __float2int_rd(y), fz = __float2int_rd(z);
     /* outside the grid the footprint is clamped to edge voxels */
@@ -289,7 +290,7 @@ __device__ __forceinline__ float emptySteps(const DevScene& sc, const FastConsts
         const int oct = (sv.x > 0.0f ? 1 : 0) | (sv.y > 0.0f ? 2 : 0) | (sv.z > 0.0f ? 4 : 0);
         if ((__ldg(sc.cellEscape + (cz * sc.ocy + cy) * sc.ocx + cx) >> oct) & 1) {
             leaves = true; /* nothing but empty cells ahead */
-            return stepsToLeaveBox(k, q, sv);
+            return 0.0f;
         }
     }
     const float cs = (float)(1 << sh);
@@ -332,7 +333,7 @@ __device__ __forceinline__ float emptySteps(const DevScene& sc, const FastConsts
     }
     if (leftGrid && sc.borderEmpty) {
         leaves = true;
-        return stepsToLeaveBox(k, q, sv);
+        return 0.0f;
     }
     more = !leftGrid && !blocked;
     /* stay 0.01 voxel short of the plane that stopped the walk */
@@ -688,7 +689,9 @@ __global__ void __launch_bounds__(FAST_MAX_THREADS, 1)
         if (SKIP && DS_N_SKIP(cnt) && ((int)DS_N_SKIP(cnt) >= job.skipMin || DS_N_BUSY(cnt) == 0u)) {
             if (st == F_SKIP) {
                 bool more, leaves;
-                const float kf = emptySteps(sc, k, posAt(s, s.nf), s.sv, job.skipMaxIters, more, leaves);
+                const V3 qs = posAt(s, s.nf);
+                float kf = emptySteps(sc, k, qs, s.sv, job.skipMaxIters, more, leaves);
+                if (leaves) kf = stepsToLeaveBox(k, qs, s.sv);
                 s.nf += kf;
                 if (!BOXTEST && leaves && !inBoxTs(k, posAt(s, s.nf))) {
                     /* nothing but zeros up to the box exit, and the landing position is outside: the path ends here.  The reference
@@ -935,7 +938,9 @@ __global__ void __launch_bounds__(256) k_primary_prepass(const DevScene sc, cons
                 }
                 n += 1.0f;
                 bool more, leaves;
-                n += emptySteps(sc, k, posAt(f, n), f.sv, 256, more, leaves);
+                const V3 qs = posAt(f, n);
+                const float kf = emptySteps(sc, k, qs, f.sv, 256, more, leaves);
+                n += leaves ? stepsToLeaveBox(k, qs, f.sv) : kf;
             }
             /* a ray that leaves the box: the reference stops at the first position outside it */
             while (!hit && n >= 2.0f && !inBoxTs(k, posAt(f, n - 1.0f))) n -= 1.0f;
