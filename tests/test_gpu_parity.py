@@ -728,3 +728,56 @@ def test_fast_direction_sampling_inverts_the_reference_cdf(built_library):
     want_phase = (chopped.astype(np.float64) / (chopped.astype(np.float64).sum() / n))
     lerp = want_phase[k] + (x - k) * (want_phase[np.minimum(k + 1, n - 1)] - want_phase[k])
     assert np.abs(phase - lerp).max() <= 6e-4 * np.abs(lerp).max() and (np.abs(phase - lerp) <= 1.5e-3 * np.abs(lerp) + 1e-6).all()
+
+
+@pytest.mark.parametrize("case", ["nonzero_faces", "coarse_step"])
+def test_fast_variants_with_a_box_test(built_library, case):
+    """k_trace_fast drops the per-step box test and the in-box test of the collision point only when the grid's faces are zero AND the
+    sampling step stays within the 0.01 slack of the reference's isInBox (cloud.cuh:40-44).  The two configurations that break a
+    premise -- a cloud that fills its grid up to the faces, and a sampling step of 0.02 -- must take the variants that keep the tests:
+    frames statistically equal to the oracle's, identical with and without empty-space skipping, EXACT bit-exact as everywhere."""
+    ds = built_library
+    rs = np.random.RandomState(11)
+    if case == "nonzero_faces":
+        grid = (rs.uniform(0, 1, size=(24, 28, 20)) ** 3 * 0.3 * 255).astype(np.uint8)  # haze up to the faces, with a hole
+        grid[8:16, 10:18, 6:14] = 0
+        step, size_m = 1.0 / 512.0, 1500.0
+    else:
+        grid = _edge_grid((32, 32, 32), 3)
+        step, size_m = 0.02, 5000.0
+    sun = (-0.586, -0.766, -0.271)
+    w, h, spp = 36, 20, 32
+    cam = ds.camera_look_at(eye=(2.5, -0.4, 0.3), aspect=w / h)
+    o = ol.Oracle()
+    o.volume_upload(grid, True)
+    o.scene_set(size_m, sun, sample_step=step)
+    o.bake()
+    rp, rv = o.render_accumulate(ds.camera_array(cam), w, h, 0, 1, spp)
+    assert rp[..., 0].max() > 0
+    with ds.Context(0) as ctx:
+        ctx.volume_upload(grid, True)
+        ctx.scene_set(size_m, sun, sample_step=step)
+        ctx.set_option("precision", ds.PRECISION_EXACT)
+        ctx.bake()
+        ctx.frame_create(w, h)
+        ctx.render_subframes(cam, 0, 1, spp)
+        p, v = ctx.frame_download()
+        assert np.array_equal(p, rp) and np.array_equal(v, rv)
+        ctx.set_option("precision", ds.PRECISION_FAST)
+        ctx.bake()
+        frames = {}
+        for skip in (1, 0):
+            ctx.set_option("skip_empty", skip)
+            ctx.frame_clear()
+            ctx.counters_reset()
+            ctx.render_subframes(cam, 0, 1, spp)
+            frames[skip] = (ctx.frame_download(), ctx.counters())
+        (pf, vf), c = frames[1]
+        assert np.array_equal(pf.view(np.uint32), frames[0][0][0].view(np.uint32))
+        assert (c["paths"], c["events"], c["steps"]) == tuple(frames[0][1][k] for k in ("paths", "events", "steps"))
+    assert c["nonfinite"] == 0 and np.isfinite(pf).all() and c["paths"] == w * h * spp
+    a, b = pf[..., 0].astype(np.float64), rp[..., 0].astype(np.float64)
+    sigma = np.sqrt((vf[..., 0].astype(np.float64) + rv[..., 0].astype(np.float64)) / (spp - 1) / spp)
+    lit = sigma > 0
+    assert (np.abs(a - b)[lit] / sigma[lit] < 3).mean() > 0.98
+    assert abs(a.mean() - b.mean()) < 0.01 * b.mean() + 3 * np.sqrt((sigma**2).sum()) / a.size
