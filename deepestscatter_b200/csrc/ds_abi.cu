@@ -709,7 +709,8 @@ int ds_context_create(int device, DsContext** out)
     ctx->opt["spec_percent"] = 100; /* FAST render, two-tap pipeline: threshold of the speculative second tap (0 = always fetch it) */
     ctx->opt["escape_octants"] = 1; /* FAST estimator: a path in an empty cell whose whole octant ahead is empty ends without walking the leap DDA */
     ctx->opt["fused_volume"] = 1; /* FAST estimator: march through one RG8 {density, sun transmittance} array instead of two R8 arrays */
-    ctx->opt["region_pixels"] = 4096; /* FAST render: hit-list pixels per region of the region-major item order (0 = subframe-major) */
+    ctx->opt["region_pixels"] = -1; /* FAST render: hit-list pixels per region of the region-major item order (0 = subframe-major; -1 = auto =
+                                       1024: against 4096, C4 730 -> 757 and C2 1408 -> 1421 Mpaths/s, profiles/r04a_*, r04c_*) */
     ctx->opt["descriptor_hw"] = -1;
     ctx->opt["mlp_fp16"] = 1; /* FAST flavour of the model on IEEE half operands (default): the MMA rate and operand bytes of bf16 with the 10 mantissa
                                  bits of tf32 (656 vs 357 TFLOP/s, max error against the fp32 model 1.2e-3 either way); 0 = tf32 operands.  Activations
@@ -830,7 +831,7 @@ int ds_set_option(DsContext* ctx, const char* name, int value)
     if (n == "march_unroll" && (value < 0 || value > 2)) DS_FAIL(ctx, DS_ERR_INVALID, "march_unroll must be 0 (auto), 1 or 2");
     if (n == "skip_open_dist" && value < 1) DS_FAIL(ctx, DS_ERR_INVALID, "skip_open_dist must be >= 1 (0 would leap out of occupied cells)");
     if (n == "staging_subframes" && value < 1) DS_FAIL(ctx, DS_ERR_INVALID, "staging_subframes must be >= 1");
-    if (n == "region_pixels" && (value < 0 || value > (1 << 20))) DS_FAIL(ctx, DS_ERR_INVALID, "region_pixels must be 0 .. 2^20");
+    if (n == "region_pixels" && (value < -1 || value > (1 << 20))) DS_FAIL(ctx, DS_ERR_INVALID, "region_pixels must be -1 (auto) or 0 .. 2^20");
     if (n == "spec_percent" && (value < 0 || value > 1000)) DS_FAIL(ctx, DS_ERR_INVALID, "spec_percent must be 0 .. 1000");
     if (n == "march_max_iters" && value < 1) DS_FAIL(ctx, DS_ERR_INVALID, "march_max_iters must be >= 1");
     ctx->opt[n] = value;
@@ -1217,7 +1218,9 @@ static int traceSubframes(DsContext* ctx, const DsCamera* cam, DsMode mode, uint
         job.nHit = ctx->nHit;
         job.entrySteps = ctx->entrySteps;
         job.total = (unsigned long long)ctx->nHit * n;
-        job.regionSize = (uint32_t)ctx->opt["region_pixels"];
+        int regionPixels = ctx->opt["region_pixels"];
+        if (regionPixels < 0) regionPixels = 1024;
+        job.regionSize = (uint32_t)regionPixels;
         job.nSub = n;
         ctx->extraPaths += ((unsigned long long)ctx->width * ctx->height - ctx->nHit) * n;
         ctx->extraSteps += ctx->missSteps * n;
