@@ -691,12 +691,12 @@ int ds_context_create(int device, DsContext** out)
     ctx->opt["skip_empty"] = 1;
     ctx->opt["march_keep_quarters"] = 2;
     ctx->opt["march_max_iters"] = 64;
-    ctx->opt["march_keep32"] = 14;
+    ctx->opt["march_keep32"] = 11;
     ctx->opt["regen_min"] = 4;
-    ctx->opt["skip_min"] = 8;
+    ctx->opt["skip_min"] = 10;
     ctx->opt["skip_max_iters"] = 32;
     ctx->opt["skip_open_dist"] = 1;
-    ctx->opt["zero_check_min"] = 4;
+    ctx->opt["zero_check_min"] = 8;
     ctx->opt["radiance_scheduler"] = 1;
     ctx->opt["smem_carveout"] = -1;
     ctx->opt["volume_generation"] = 0;
