@@ -474,8 +474,10 @@ def run_ours(a):
         "tex_peak_gtaps": tex_peak, "l2_peaks": "profiles/l2_peaks.json (tools/microbench/l2_gather.cu)" if l2 else None,
         "note": ("frac: SURVEY 8d bytes over the steps the kernel itself accounts for; frac_reference_steps adds the steps of pixels the "
                  "primary-ray cache settles without tracing (host-side count, DsCounters.untraced_steps); frac_executed counts only taps "
-                 "actually fetched (8 B each) -- the kernel is bound by the texture path (tex_frac = fetched taps/s over the measured "
-                 "trilinear tex3D rate for a march-coherent access pattern at this residency), not by HBM"),
+                 "actually fetched (8 B each) -- the kernel is bound by instruction issue under divergence and by the texture path together "
+                 "(ncu: profiles/r04g_*), not by HBM; tex_frac = fetched taps/s over the measured trilinear tex3D rate of an R8 volume for a "
+                 "march-coherent access pattern at this residency -- the kernel reads a fused RG8 {density, sun transmittance} volume whose "
+                 "sun taps are mostly L1 hits, which is how the fraction can pass 1"),
     }
 
     line = {
